@@ -1,0 +1,231 @@
+/*
+ * moosecad_b200 — C ABI of the B200-native meshing hot path.
+ *
+ * Drop-in boundary for ONE path of dvc94ch/moosecad: evaluating the luascad CSG
+ * signed-distance tree over tessellate3d's 5-tet cubic lattice and running isosurface
+ * stuffing on it.  The reference has no FFI of its own; its seams are Rust
+ * traits.  Each entry point below names the reference interface it replaces (paths are
+ * relative to the reference repository).  INTEGRATION.md shows the Rust `extern "C"`
+ * block and the patched call sites.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature.  A CUDA stream is
+ *     passed as `void*` (cudaStream_t), device memory as `void*`.
+ *   - every function returning `int` returns MC_OK (0) or a negative mc_status; the
+ *     message is available from mc_last_error() (thread-local).  Nothing throws or
+ *     aborts across the ABI (the reference panics on e.g. a non-finite bbox,
+ *     tessellate3d/src/lib.rs:44-46; here that is MC_ERR_BBOX).
+ *   - the caller owns tapes and contexts; the library owns every buffer reachable from a
+ *     mc_mesh until mc_mesh_free().
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device and fails
+ *     with MC_ERR_CUDA when none is usable.
+ *   - a context is bound to one device and one stream; calls on one context are
+ *     synchronous with respect to the host unless stated otherwise and must not be
+ *     issued concurrently from several threads (the reference is single-threaded).
+ */
+#ifndef MOOSECAD_B200_H
+#define MOOSECAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+typedef enum mc_status {
+    MC_OK = 0,
+    MC_ERR_ARG = -1,         /* bad handle / node id / argument */
+    MC_ERR_BBOX = -2,        /* non-finite root bounding box (reference: unwrap() panic) */
+    MC_ERR_SINGULAR = -3,    /* affine matrix not invertible (reference: panic) */
+    MC_ERR_UNSUPPORTED = -4, /* node kind outside this path (bend / twist) */
+    MC_ERR_CUDA = -5,        /* CUDA runtime error or no device */
+    MC_ERR_LIMIT = -6,       /* tape deeper / larger than the device evaluator supports */
+    MC_ERR_DIVERGED = -7,    /* edge bisection did not reach the error threshold */
+    MC_ERR_STATE = -8        /* call made in the wrong phase */
+} mc_status;
+
+typedef struct mc_tape mc_tape; /* a recorded scene: the flat node list luascad lowers to */
+typedef struct mc_ctx mc_ctx;   /* device + stream + reusable workspace */
+typedef struct mc_mesh mc_mesh; /* result of one tessellation (device resident, host views on demand) */
+
+const char* mc_last_error(void);
+int mc_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * Scene lowering.  One call per node created in luascad::geom (luascad/src/lib.rs:89-281).
+ * Nodes are immutable once pushed; functions return the new node id (>= 0) or a negative
+ * mc_status.  Children are referenced by id and may be shared (the reference clones them).
+ * Bounding boxes are propagated with the rules of implicit3d 0.14.2 / bbox 0.11.2.
+ * ------------------------------------------------------------------------------------ */
+mc_tape* mc_tape_new(void);
+void mc_tape_free(mc_tape*);
+int32_t mc_tape_num_nodes(const mc_tape*);
+
+/* geom.plane_x/y/z (negative=0) and geom.plane_neg_x/y/z (negative=1); luascad/src/lib.rs:89-123 */
+int32_t mc_tape_plane(mc_tape*, int axis, int negative, double d);
+/* geom.plane_hesian; luascad/src/lib.rs:125-132 */
+int32_t mc_tape_plane_hesian(mc_tape*, double nx, double ny, double nz, double p);
+/* geom.plane_3_points; luascad/src/lib.rs:134-152 */
+int32_t mc_tape_plane_3_points(mc_tape*, const double a[3], const double b[3], const double c[3]);
+/* geom.sphere; luascad/src/lib.rs:154-158 */
+int32_t mc_tape_sphere(mc_tape*, double radius);
+/* geom.i_cylinder; luascad/src/lib.rs:160-164 */
+int32_t mc_tape_i_cylinder(mc_tape*, double radius);
+/* geom.i_cone (offset 0) and the cone inside geom.cylinder; luascad/src/lib.rs:166-170,200 */
+int32_t mc_tape_i_cone(mc_tape*, double slope, double offset);
+/* Cone::set_bbox; luascad/src/lib.rs:202-205.  bbox = {minx,miny,minz,maxx,maxy,maxz} */
+int mc_tape_set_bbox(mc_tape*, int32_t node, const double bbox[6]);
+/* test fixture of tessellate3d's own tests (`UnitSphere`, tessellate3d/src/lib.rs:460-484):
+ * value = |p|^2 - 1, bbox [-1,1]^3 */
+int32_t mc_tape_unit_sphere_sq(mc_tape*);
+/* Union::from_vec / Intersection::from_vec / Intersection::difference_from_vec
+ * (luascad/src/lib.rs:173-187,209-217,252-273).  n == 1 returns a copy of the child. */
+int32_t mc_tape_union(mc_tape*, const int32_t* children, int n, double r);
+int32_t mc_tape_intersection(mc_tape*, const int32_t* children, int n, double r);
+int32_t mc_tape_difference(mc_tape*, const int32_t* children, int n, double r);
+int32_t mc_tape_negation(mc_tape*, int32_t child);
+/* Object::translate / rotate / scale (luascad/src/lib.rs:221-237): a fresh affine node, or
+ * the composed matrix when `node` already is an affine node */
+int32_t mc_tape_translate(mc_tape*, int32_t node, double x, double y, double z);
+int32_t mc_tape_rotate(mc_tape*, int32_t node, double x, double y, double z);
+int32_t mc_tape_scale(mc_tape*, int32_t node, double x, double y, double z);
+/* geom.bend / geom.twist (luascad/src/lib.rs:239-249): not on this path -> MC_ERR_UNSUPPORTED */
+int32_t mc_tape_bend(mc_tape*, int32_t node, double width);
+int32_t mc_tape_twist(mc_tape*, int32_t node, double height);
+/* Object::set_parameters(&PrimitiveParameters{fade_range, r_multiplier}); src/main.rs:53-58.
+ * Applies to every node of the tape (main applies it to every output). */
+int mc_tape_set_parameters(mc_tape*, double fade_range, double r_multiplier);
+/* Object::bbox(); src/main.rs:29-31 */
+int mc_tape_bbox(const mc_tape*, int32_t node, double out_bbox[6]);
+/* size of the device program for (root, slack): 8-byte words, value-stack depth, affine depth */
+int mc_tape_program_info(const mc_tape*, int32_t root, double slack, uint64_t* words,
+                         int32_t* value_depth, int32_t* point_depth, uint64_t* flops_per_point);
+
+/* ------------------------------------------------------------------------------------
+ * Device context.
+ * ------------------------------------------------------------------------------------ */
+/* device: CUDA ordinal; stream: cudaStream_t to launch on (NULL = the legacy default stream) */
+mc_ctx* mc_ctx_new(int device, void* stream);
+void mc_ctx_free(mc_ctx*);
+int mc_ctx_device(const mc_ctx*);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t mc_ctx_launch_count(const mc_ctx*);
+/* bytes currently held by the reusable workspace */
+uint64_t mc_ctx_workspace_bytes(const mc_ctx*);
+/* release the cached workspace */
+int mc_ctx_trim(mc_ctx*);
+
+/* ------------------------------------------------------------------------------------
+ * ObjectAdaptor::value — Object::approx_value(p, slack) for a batch of points
+ * (src/main.rs:33-35,95).  points: n * 3 doubles (xyz AoS), out: n doubles; HOST buffers.
+ * ------------------------------------------------------------------------------------ */
+int mc_eval_points(mc_ctx*, const mc_tape*, int32_t root, double slack, const double* points,
+                   uint64_t n, double* out);
+/* same, DEVICE buffers, asynchronous on the context's stream */
+int mc_eval_points_device(mc_ctx*, const mc_tape*, int32_t root, double slack,
+                          const void* d_points, uint64_t n, void* d_out);
+
+/* ------------------------------------------------------------------------------------
+ * The mesher.  Replaces
+ *   IsosurfaceStuffing::new(&ObjectAdaptor{implicit, res}, res, err).tessellate()
+ * (src/main.rs:74-82 -> tessellate3d/src/lib.rs:36-52,420-431).
+ * ------------------------------------------------------------------------------------ */
+typedef struct mc_slab {
+    /* z-slab sharding: this call meshes cell layers [z_begin, z_end) of the
+     * global lattice.  {0, 0} means the whole lattice (single GPU). */
+    uint64_t z_begin, z_end;
+} mc_slab;
+
+typedef struct mc_options {
+    uint32_t struct_size;       /* sizeof(mc_options) */
+    uint32_t flags;             /* MC_OPT_* */
+    uint32_t max_bisect_iters;  /* 0 = default (200); reference loops until convergence */
+    uint32_t reserved;
+} mc_options;
+#define MC_OPT_KEEP_PHI 1u     /* keep the lattice SDF field readable after the call */
+#define MC_OPT_SKIP_QUALITY 2u /* skip check_for_inverted_tets (stdout-only in the reference) */
+
+/* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts
+ * (mc_mesh_counts) are known; nothing has been emitted yet. */
+int mc_tessellate_begin(mc_ctx*, const mc_tape* volume, int32_t root, double resolution,
+                        double relative_error, const mc_slab* slab, const mc_options* opts,
+                        mc_mesh** out);
+/* Phase 2: number and emit this slab's vertices (lattice vertices, warped where applicable,
+ * and the bisected cut vertices).  vertex_base: global index of this slab's first vertex
+ * (exclusive scan of mc_mesh_counts()[0] over the ranks; 0 on one GPU).  Afterwards
+ * mc_mesh_upper_plane_table() is valid. */
+int mc_tessellate_emit_vertices(mc_mesh*, uint64_t vertex_base);
+/* Phase 3: emit this slab's tets with global vertex ids.  tet_base: global index of this
+ * slab's first tet.  d_lower_plane: device pointer to the id table of the lattice plane
+ * z = z_begin produced by the rank below (its mc_mesh_upper_plane_table), or NULL for the
+ * first slab. */
+int mc_tessellate_emit_tets(mc_mesh*, uint64_t tet_base, const void* d_lower_plane);
+/* all phases for the whole lattice on one device */
+int mc_tessellate(mc_ctx*, const mc_tape* volume, int32_t root, double resolution,
+                  double relative_error, const mc_options* opts, mc_mesh** out);
+void mc_mesh_free(mc_mesh*);
+
+/* counts: [0] vertices owned by this slab, [1] tets, [2] lattice points evaluated (incl.
+ * halo), [3] lattice points owned, [4] cut edges, [5] warped vertices */
+int mc_mesh_counts(const mc_mesh*, uint64_t counts[6]);
+/* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
+ * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
+int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);
+/* mirrors the reference's stdout (tessellate3d/src/lib.rs:247,355,366,408-417,421,424):
+ * dim, tet count after cut_lattice / before trim / after trim, the 7 case counters,
+ * aspect-ratio min/max and the number of inverted tets */
+int mc_mesh_stats(const mc_mesh*, uint64_t dim[3], uint64_t ntets_stage[3], uint64_t stats[7],
+                  double ar_minmax[2], uint64_t* inverted);
+/* CUDA-event stage times of the last run in milliseconds:
+ * [0] sdf field [1] warp [2] classify+count [3] vertex scan+emit [4] bisection
+ * [5] tet emit [6] quality [7] boundary [8] side-sets */
+int mc_mesh_stage_ms(const mc_mesh*, double ms[9]);
+
+/* Result views.  Layout = the mesh crate's (mesh/src/lib.rs:58-65): coords xyz AoS f64,
+ * tets 4 x node id, 0-based.  Host copies are made on first request and stay valid until
+ * mc_mesh_free. */
+uint64_t mc_mesh_num_vertices(const mc_mesh*);
+uint64_t mc_mesh_num_tets(const mc_mesh*);
+const double* mc_mesh_coords(mc_mesh*);
+const uint64_t* mc_mesh_tets(mc_mesh*);
+/* device-resident views (global ids as uint32 when index_bytes == 4, else uint64) */
+int mc_mesh_device_views(mc_mesh*, void** d_coords, void** d_tets, int* index_bytes);
+/* copy into caller-provided HOST buffers (pinned or pageable): coords = 3*nv doubles,
+ * tets = 4*nt entries of index_bytes (4 or 8) each */
+int mc_mesh_copy_to_host(mc_mesh*, double* coords, void* tets, int index_bytes);
+/* the lattice SDF field (MC_OPT_KEEP_PHI): (dim+1)^3 doubles, x fastest, z slowest */
+int mc_mesh_copy_phi(mc_mesh*, double* out, uint64_t n);
+
+/* ------------------------------------------------------------------------------------
+ * Mesh::boundary() (mesh/src/lib.rs:341-357; src/main.rs:86) and the side-set loop
+ * (src/main.rs:87-106).
+ * ------------------------------------------------------------------------------------ */
+/* number of surface sides; computes them on first call */
+int mc_mesh_boundary(mc_mesh*, uint64_t* n_sides);
+/* (elem, side) pairs, side in 0..3 per Tet4::face (mesh/src/lib.rs:661-668); host view */
+const uint64_t* mc_mesh_boundary_sides(mc_mesh*);
+/* adds one side-set: surface sides whose three nodes all satisfy
+ * |approx_value(p, EPSILON)| <= EPSILON for the given boundary object.  Returns its index. */
+int mc_mesh_add_sideset(mc_mesh*, const mc_tape* boundary, int32_t root);
+uint64_t mc_mesh_sideset_len(const mc_mesh*, int index);
+const uint64_t* mc_mesh_sideset(mc_mesh*, int index);
+
+/* ------------------------------------------------------------------------------------
+ * mesh crate predicates on arbitrary tet meshes (mesh/src/lib.rs:292-316), evaluated on the
+ * device; used by the parity tests of check_for_inverted_tets.  HOST buffers.
+ * ------------------------------------------------------------------------------------ */
+int mc_tet_quality(mc_ctx*, const double* coords, uint64_t nv, const uint64_t* tets, uint64_t nt,
+                   double* volume, double* aspect_ratio);
+
+/* ------------------------------------------------------------------------------------
+ * Device capability probes used by bench.py's roofline (measured, not assumed).
+ * ------------------------------------------------------------------------------------ */
+/* sustained DADD+DMUL (no FMA) rate in flop/s over `ms` milliseconds of work */
+int mc_probe_fp64_nofma(mc_ctx*, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOOSECAD_B200_H */

@@ -1,0 +1,431 @@
+// Mesh::boundary() (mesh/src/lib.rs:341-357) and the side-set loop (src/main.rs:87-106).
+//
+// The reference toggles every face of every tet in and out of a HashMap keyed by the sorted
+// node triple.  Here only the faces that can possibly be unmatched are generated: a "full"
+// cell (all five lattice tets emitted untouched) pairs all its internal faces by
+// construction and its cell-face triangles pair with those of a full neighbour, so it only
+// contributes the triangles facing a non-full neighbour or the lattice border; every other
+// cell contributes all faces of its output tets.  The candidates (O(surface)) are radix
+// sorted by key; a key that occurs an odd number of times is a boundary side, owned by its
+// last occurrence in element order (the toggle semantics).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <limits>
+
+#include "mc_internal.hpp"
+#include "mc_kernels.cuh"
+
+namespace mc {
+
+// the two triangles of every cell face, as (tet, side) of the un-mirrored tile; derived once
+// on the host from Tile::TETS / Tet4::face (a triangle lies in a cell face iff its three
+// corners share a coordinate).
+struct FaceTri { int8_t tet, side; };
+static __constant__ FaceTri C_CELLFACE[6][2];  // [axis*2 + (coordinate==1)][k]
+
+static void build_cellface_table(FaceTri out[6][2]) {
+    static const int LAT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    static const int TETS[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};
+    static const int FACE[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
+    int cnt[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < 5; ++t)
+        for (int s = 0; s < 4; ++s)
+            for (int ax = 0; ax < 3; ++ax)
+                for (int v = 0; v < 2; ++v) {
+                    bool all = true;
+                    for (int k = 0; k < 3; ++k) all = all && LAT[TETS[t][FACE[s][k]]][ax] == v;
+                    if (all) { out[ax * 2 + v][cnt[ax * 2 + v]++] = {(int8_t)t, (int8_t)s}; }
+                }
+}
+
+// After the cut_lattice flip (nodes 0 and 1 swapped) the face table is applied to the flipped
+// node order: side s of the emitted tet consists of flipped nodes FACE[s][*].  A triangle that
+// is (un-flipped) side s0 keeps its node SET but may sit at a different side index.
+__device__ __forceinline__ int side_after_flip(int s0) {
+    // un-flipped nodes of side s0 -> positions after swapping 0<->1 -> which FACE row has that set
+    int mask = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int n = C_FACE[s0][k];
+        n = n < 2 ? 1 - n : n;
+        mask |= 1 << n;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int m = (1 << C_FACE[s][0]) | (1 << C_FACE[s][1]) | (1 << C_FACE[s][2]);
+        if (m == mask) return s;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ bool cell_is_full(const Lattice& L, const uint16_t* __restrict__ cinfo, uint32_t cl0,
+                                             uint32_t cl1, int64_t cx, int64_t cy, int64_t cz) {
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= (int64_t)L.nx || cy >= (int64_t)L.ny || cz >= (int64_t)L.nz) return false;
+    if (cz < (int64_t)cl0 || cz >= (int64_t)cl1) return false;
+    const uint64_t i = ((uint64_t)(cz - cl0) * L.ny + (uint64_t)cy) * L.nx + (uint64_t)cx;
+    return (cinfo[i] & CI_FULL) != 0;
+}
+
+// number of candidate faces of a cell
+__device__ __forceinline__ uint32_t cell_face_count(const Lattice& L, const uint16_t* __restrict__ cinfo, uint32_t cl0,
+                                                    uint32_t cl1, uint32_t cx, uint32_t cy, uint32_t cz, uint16_t ci) {
+    const uint32_t count = ci & CI_COUNT_MASK;
+    if (!(ci & CI_FULL)) return 4u * count;
+    uint32_t n = 0;
+    n += cell_is_full(L, cinfo, cl0, cl1, (int64_t)cx - 1, cy, cz) ? 0u : 2u;
+    n += cell_is_full(L, cinfo, cl0, cl1, (int64_t)cx + 1, cy, cz) ? 0u : 2u;
+    n += cell_is_full(L, cinfo, cl0, cl1, cx, (int64_t)cy - 1, cz) ? 0u : 2u;
+    n += cell_is_full(L, cinfo, cl0, cl1, cx, (int64_t)cy + 1, cz) ? 0u : 2u;
+    n += cell_is_full(L, cinfo, cl0, cl1, cx, cy, (int64_t)cz - 1) ? 0u : 2u;
+    n += cell_is_full(L, cinfo, cl0, cl1, cx, cy, (int64_t)cz + 1) ? 0u : 2u;
+    return n;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_face_count(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
+             unsigned long long* __restrict__ tile_tot) {
+    __shared__ unsigned long long s_tot;
+    if (threadIdx.x == 0) s_tot = 0ull;
+    __syncthreads();
+    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
+    const uint64_t first = per_layer * (c0 - cl0), last = per_layer * (c1 - cl0);
+    unsigned long long mine = 0;
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        if (i < first || i >= last) continue;
+        const uint16_t ci = cinfo[i];
+        if (!(ci & CI_COUNT_MASK)) continue;
+        const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
+        const uint64_t r = i % per_layer;
+        mine += cell_face_count(L, cinfo, cl0, cl1, (uint32_t)(r % L.nx), (uint32_t)(r / L.nx), cz, ci);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_tot, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+}
+
+__device__ __forceinline__ void sort3(unsigned long long& a, unsigned long long& b, unsigned long long& c) {
+    unsigned long long t;
+    if (a > b) { t = a; a = b; b = t; }
+    if (b > c) { t = b; b = c; c = t; }
+    if (a > b) { t = a; a = b; b = t; }
+}
+
+// emit candidate faces: key = sorted global node ids (k0 <= k1 <= k2), payload = tet * 4 + side
+__global__ void __launch_bounds__(TILE_THREADS)
+k_face_emit(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
+            const unsigned long long* __restrict__ tile_tbase, const unsigned long long* __restrict__ tile_fbase,
+            const uint16_t* __restrict__ vmask, const int32_t* __restrict__ vbase, int64_t vertex_base,
+            unsigned long long tet_base, unsigned long long* __restrict__ key_hi, unsigned long long* __restrict__ key_lo,
+            unsigned long long* __restrict__ payload) {
+    __shared__ uint32_t s_scan[9];
+    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
+    const uint64_t first = per_layer * (c0 - cl0), last = per_layer * (c1 - cl0);
+    uint64_t trun = tile_tbase[blockIdx.x], frun = tile_fbase[blockIdx.x];
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        const bool owned = i >= first && i < last;
+        const uint16_t ci = owned ? cinfo[i] : (uint16_t)0;
+        const uint32_t count = ci & CI_COUNT_MASK;
+        uint32_t cx = 0, cy = 0, cz = 0, nf = 0;
+        if (count) {
+            cz = cl0 + (uint32_t)(i / per_layer);
+            const uint64_t r = i % per_layer;
+            cy = (uint32_t)(r / L.nx); cx = (uint32_t)(r % L.nx);
+            nf = cell_face_count(L, cinfo, cl0, cl1, cx, cy, cz, ci);
+        }
+        uint32_t ttot, ftot;
+        const uint32_t tex = block_exscan(count, &ttot, s_scan);
+        const uint32_t fex = block_exscan(nf, &ftot, s_scan);
+        if (nf) {
+            const Cell c = make_cell(cx, cy, cz);
+            uint64_t o = trun + tex;   // slab-local index of the cell's first output tet
+            uint64_t f = frun + fex;
+            if (ci & CI_FULL) {
+                // tets 0..4 are emitted in order; only triangles on open cell faces are candidates
+                for (int ax = 0; ax < 3; ++ax)
+                    for (int v = 0; v < 2; ++v) {
+                        // un-mirrored face (axis, v) sits at global offset v' = mirrored ? 1 - v : v
+                        const bool mir = ax == 0 ? c.fx : (ax == 1 ? c.fy : c.fz);
+                        const int gv = mir ? 1 - v : v;
+                        int64_t ncx = cx, ncy = cy, ncz = cz;
+                        (ax == 0 ? ncx : (ax == 1 ? ncy : ncz)) += gv ? 1 : -1;
+                        if (cell_is_full(L, cinfo, cl0, cl1, ncx, ncy, ncz)) continue;
+                        for (int k = 0; k < 2; ++k) {
+                            const FaceTri ft = C_CELLFACE[ax * 2 + v][k];
+                            TetNodes tn;
+                            load_tet(L, c, ft.tet, tn);
+                            const int s = c.flip() ? side_after_flip(ft.side) : ft.side;
+                            unsigned long long g[3];
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)
+                                g[q] = node_global_id<unsigned long long>(L, tn, C_FACE[s][q], vmask, vbase, vertex_base);
+                            sort3(g[0], g[1], g[2]);
+                            key_hi[f] = (g[0] << 32) | g[1];
+                            key_lo[f] = g[2];
+                            payload[f] = ((tet_base + o + (uint64_t)ft.tet) << 2) | (unsigned long long)s;
+                            ++f;
+                        }
+                    }
+            } else {
+                for (int t = 0; t < 5; ++t) {
+                    TetNodes tn;
+                    load_tet(L, c, t, tn);
+                    TetOut to;
+                    classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+                    for (int q = 0; q < to.n; ++q) {
+                        unsigned long long id[4];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            id[m] = node_global_id<unsigned long long>(L, tn, to.node[q][m], vmask, vbase, vertex_base);
+                        for (int s = 0; s < 4; ++s) {
+                            unsigned long long g0 = id[C_FACE[s][0]], g1 = id[C_FACE[s][1]], g2 = id[C_FACE[s][2]];
+                            sort3(g0, g1, g2);
+                            key_hi[f] = (g0 << 32) | g1;
+                            key_lo[f] = g2;
+                            payload[f] = ((tet_base + o) << 2) | (unsigned long long)s;
+                            ++f;
+                        }
+                        ++o;
+                    }
+                }
+            }
+        }
+        trun += ttot;
+        frun += ftot;
+    }
+}
+
+__global__ void k_iota(unsigned long long* p, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void k_gather(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ idx,
+                         uint64_t n, unsigned long long* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// one thread per sorted candidate: the first element of every run of equal keys counts the run
+// and, when the length is odd, appends the run's last element (largest tet id) to the output
+__global__ void k_face_select(const unsigned long long* __restrict__ key_hi, const unsigned long long* __restrict__ key_lo,
+                              const unsigned long long* __restrict__ payload,
+                              const unsigned long long* __restrict__ order, uint64_t n,
+                              unsigned long long* __restrict__ out_sides, unsigned long long* __restrict__ out_count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long me = order[i];
+    const unsigned long long h = key_hi[me], l = key_lo[me];
+    if (i > 0) {
+        const unsigned long long pr = order[i - 1];
+        if (key_hi[pr] == h && key_lo[pr] == l) return;  // not a run start
+    }
+    uint64_t j = i + 1;
+    unsigned long long lastp = payload[me];
+    while (j < n) {
+        const unsigned long long nx = order[j];
+        if (key_hi[nx] != h || key_lo[nx] != l) break;
+        const unsigned long long p = payload[nx];
+        if (p > lastp) lastp = p;
+        ++j;
+    }
+    if ((j - i) & 1ull) {
+        const unsigned long long at = atomicAdd(out_count, 1ull);
+        out_sides[2 * at] = lastp >> 2;
+        out_sides[2 * at + 1] = lastp & 3ull;
+    }
+}
+
+// side-set membership: |approx_value(p, EPS)| <= EPS at the three nodes of every surface side
+template <typename IndexT>
+__global__ void k_sideset(const uint64_t* __restrict__ prog, const double* __restrict__ coords,
+                          const IndexT* __restrict__ tets, int64_t vertex_base, unsigned long long tet_base,
+                          const unsigned long long* __restrict__ sides, uint64_t n, uint8_t* __restrict__ member) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t ic = i < n ? i : n - 1;
+    const unsigned long long e = sides[2 * ic] - tet_base, s = sides[2 * ic + 1];
+    const double EPS = 2.220446049250313e-16;  // f64::EPSILON
+    bool add = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t id = (int64_t)tets[4 * e + C_FACE[s][k]] - vertex_base;
+        const double phi = vm_eval<true>(prog, coords[3 * id], coords[3 * id + 1], coords[3 * id + 2]);
+        if (phi > EPS || phi < -EPS) add = false;
+    }
+    if (i < n) member[i] = add ? 1 : 0;
+}
+
+static int sort_u64(mc_ctx* c, unsigned long long* keys_in, unsigned long long* keys_out, unsigned long long* vals_in,
+                    unsigned long long* vals_out, uint64_t n, int end_bit) {
+    size_t tmp_bytes = 0;
+    MC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n, 0,
+                                            end_bit, c->stream));
+    DevBuf tmp;
+    int rc = c->alloc(tmp_bytes, tmp);
+    if (rc != MC_OK) return rc;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n,
+                                                    0, end_bit, c->stream);
+    c->launches += 4;
+    c->release(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "cub::DeviceRadixSort::SortPairs");
+    return MC_OK;
+}
+
+int compute_boundary(mc_mesh* m) {
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const Lattice& L = m->L;
+    if (m->c0 != 0 || m->c1 != L.nz)
+        return fail(MC_ERR_UNSUPPORTED, "Mesh::boundary on a z-slab: gather the slabs on one device first");
+    static bool table_ready = false;
+    {
+        FaceTri tab[6][2];
+        build_cellface_table(tab);
+        MC_CUDA(cudaMemcpyToSymbolAsync(C_CELLFACE, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
+        table_ready = true;
+    }
+    (void)table_ready;
+    cudaEvent_t e0, e1;
+    MC_CUDA(cudaEventCreate(&e0));
+    MC_CUDA(cudaEventCreate(&e1));
+    MC_CUDA(cudaEventRecord(e0, s));
+    DevBuf ftot, fbase, dtotal;
+    int rc = c->alloc((m->n_ctiles + 1) * 8, ftot);
+    if (rc == MC_OK) rc = c->alloc((m->n_ctiles + 1) * 8, fbase);
+    if (rc == MC_OK) rc = c->alloc(4 * 8, dtotal);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(cudaMemsetAsync(dtotal.p, 0, 32, s));
+    unsigned long long* totals = (unsigned long long*)dtotal.p;
+    uint64_t nf = 0;
+    if (m->n_ctiles > 0) {
+        k_face_count<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(L, m->cl0, m->cl1, m->c0, m->c1,
+                                                                     (const uint16_t*)m->d_cinfo.p,
+                                                                     (unsigned long long*)ftot.p);
+        k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)ftot.p, m->n_ctiles, (unsigned long long*)fbase.p,
+                                        nullptr, totals);
+        c->launches += 2;
+        MC_CUDA(cudaGetLastError());
+        unsigned long long h[2];
+        MC_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, s));
+        MC_CUDA(cudaStreamSynchronize(s));
+        nf = h[0];  // face totals never exceed 32 bits per tile, the scan keeps 64-bit sums
+    }
+    m->n_sides = 0;
+    m->h_sides.clear();
+    if (nf > 0) {
+        DevBuf khi, klo, pay, ia, ib, ka, kb;
+        rc = c->alloc(nf * 8, khi);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, klo);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, pay);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, ia);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, ib);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, ka);
+        if (rc == MC_OK) rc = c->alloc(nf * 8, kb);
+        if (rc == MC_OK) rc = c->alloc(nf * 16, m->d_sides);
+        if (rc != MC_OK) return rc;
+        k_face_emit<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
+            L, m->cl0, m->cl1, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
+            (const unsigned long long*)fbase.p, (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p,
+            (int64_t)m->vertex_base, m->tet_base, (unsigned long long*)khi.p, (unsigned long long*)klo.p,
+            (unsigned long long*)pay.p);
+        const unsigned nb = (unsigned)((nf + 255) / 256);
+        k_iota<<<nb, 256, 0, s>>>((unsigned long long*)ia.p, nf);
+        c->launches += 2;
+        MC_CUDA(cudaGetLastError());
+        // LSD: by the low key first, then (stable) by the high key
+        rc = sort_u64(c, (unsigned long long*)klo.p, (unsigned long long*)ka.p, (unsigned long long*)ia.p,
+                      (unsigned long long*)ib.p, nf, 64);
+        if (rc != MC_OK) return rc;
+        k_gather<<<nb, 256, 0, s>>>((const unsigned long long*)khi.p, (const unsigned long long*)ib.p, nf,
+                                    (unsigned long long*)kb.p);
+        c->launches++;
+        rc = sort_u64(c, (unsigned long long*)kb.p, (unsigned long long*)ka.p, (unsigned long long*)ib.p,
+                      (unsigned long long*)ia.p, nf, 64);
+        if (rc != MC_OK) return rc;
+        k_face_select<<<nb, 256, 0, s>>>((const unsigned long long*)khi.p, (const unsigned long long*)klo.p,
+                                         (const unsigned long long*)pay.p, (const unsigned long long*)ia.p, nf,
+                                         (unsigned long long*)m->d_sides.p, totals + 2);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+        unsigned long long ns = 0;
+        MC_CUDA(cudaMemcpyAsync(&ns, totals + 2, 8, cudaMemcpyDeviceToHost, s));
+        MC_CUDA(cudaStreamSynchronize(s));
+        m->n_sides = ns;
+        c->release(khi); c->release(klo); c->release(pay); c->release(ia); c->release(ib); c->release(ka); c->release(kb);
+    }
+    MC_CUDA(cudaEventRecord(e1, s));
+    // host view, sorted (the reference's HashSet order is arbitrary)
+    m->h_sides.resize(m->n_sides * 2);
+    if (m->n_sides) MC_CUDA(cudaMemcpyAsync(m->h_sides.data(), m->d_sides.p, m->n_sides * 16, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    MC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    m->stage_ms[7] = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    {
+        std::vector<std::pair<uint64_t, uint64_t>> v(m->n_sides);
+        for (uint64_t i = 0; i < m->n_sides; ++i) v[i] = {m->h_sides[2 * i], m->h_sides[2 * i + 1]};
+        std::sort(v.begin(), v.end());
+        for (uint64_t i = 0; i < m->n_sides; ++i) { m->h_sides[2 * i] = v[i].first; m->h_sides[2 * i + 1] = v[i].second; }
+        if (m->n_sides) MC_CUDA(cudaMemcpyAsync(m->d_sides.p, m->h_sides.data(), m->n_sides * 16, cudaMemcpyHostToDevice, s));
+        MC_CUDA(cudaStreamSynchronize(s));
+    }
+    c->release(ftot); c->release(fbase); c->release(dtotal);
+    m->have_boundary = true;
+    return MC_OK;
+}
+
+int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, std::vector<uint64_t>& out) {
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    out.clear();
+    if (m->n_sides == 0) return MC_OK;
+    Program p;
+    std::string err;
+    // boundary.approx_value(point, f64::EPSILON), src/main.rs:95
+    int rc = tape->compile(root, std::numeric_limits<double>::epsilon(), p, err);
+    if (rc != MC_OK) return fail(rc, err);
+    DevBuf dp, dm;
+    rc = upload_program(c, p, dp);
+    if (rc != MC_OK) return rc;
+    rc = c->alloc(m->n_sides, dm);
+    if (rc != MC_OK) return rc;
+    cudaEvent_t e0, e1;
+    MC_CUDA(cudaEventCreate(&e0));
+    MC_CUDA(cudaEventCreate(&e1));
+    MC_CUDA(cudaEventRecord(e0, s));
+    const unsigned nb = (unsigned)((m->n_sides + 255) / 256);
+    if (m->index_bytes == 4)
+        k_sideset<uint32_t><<<nb, 256, 0, s>>>((const uint64_t*)dp.p, (const double*)m->d_coords.p,
+                                               (const uint32_t*)m->d_tets.p, (int64_t)m->vertex_base, m->tet_base,
+                                               (const unsigned long long*)m->d_sides.p, m->n_sides, (uint8_t*)dm.p);
+    else
+        k_sideset<unsigned long long><<<nb, 256, 0, s>>>((const uint64_t*)dp.p, (const double*)m->d_coords.p,
+                                                         (const unsigned long long*)m->d_tets.p, (int64_t)m->vertex_base,
+                                                         m->tet_base, (const unsigned long long*)m->d_sides.p,
+                                                         m->n_sides, (uint8_t*)dm.p);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
+    MC_CUDA(cudaEventRecord(e1, s));
+    std::vector<uint8_t> member(m->n_sides);
+    MC_CUDA(cudaMemcpyAsync(member.data(), dm.p, m->n_sides, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    MC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    m->stage_ms[8] += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (uint64_t i = 0; i < m->n_sides; ++i)
+        if (member[i]) { out.push_back(m->h_sides[2 * i]); out.push_back(m->h_sides[2 * i + 1]); }
+    c->release(dp);
+    c->release(dm);
+    return MC_OK;
+}
+
+}  // namespace mc

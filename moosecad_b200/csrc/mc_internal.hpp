@@ -1,0 +1,90 @@
+// Internal host-side structures behind the opaque C handles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/moosecad_b200.h"
+#include "mc_error.hpp"
+#include "mc_lattice.cuh"
+#include "mc_tape.hpp"
+
+namespace mc {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace mc
+
+struct mc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    std::vector<mc::DevBuf> free_list;  // cached device allocations
+    uint64_t held_bytes = 0;
+
+    int alloc(size_t bytes, mc::DevBuf& out);
+    void release(mc::DevBuf& b);
+    void trim();
+};
+
+struct mc_mesh {
+    mc_ctx* ctx = nullptr;
+    int phase = 0;  // 1 after begin, 2 after emit_vertices, 3 after emit_tets
+    mc::Lattice L{};
+    uint32_t c0 = 0, c1 = 0;    // owned cell layers [c0, c1)
+    uint32_t cl0 = 0, cl1 = 0;  // classified cell layers
+    uint32_t oz0 = 0, oz1 = 0;  // owned point planes [oz0, oz1]
+    uint32_t wz0 = 0, wz1 = 0;  // planes with warp codes
+    double resolution = 0, error_threshold = 0;
+    uint32_t flags = 0, max_bisect = 200;
+    mc::Program prog;
+
+    mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vbase, d_cinfo;
+    mc::DevBuf d_ctile_tot, d_ctile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
+    mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
+    uint64_t n_ctiles = 0, n_vtiles = 0;
+
+    uint64_t counters[32] = {0};
+    uint64_t n_verts = 0, n_cuts = 0, n_tets = 0, n_kept = 0;
+    uint64_t points_evaluated = 0, points_owned = 0;
+    uint64_t vertex_base = 0, tet_base = 0;
+    int index_bytes = 4;
+    uint64_t dim[3] = {0, 0, 0};
+
+    cudaEvent_t ev[12] = {nullptr};
+    double stage_ms[9] = {0};
+
+    // host copies made on demand
+    std::vector<double> h_coords;
+    std::vector<uint64_t> h_tets;
+    bool have_h_coords = false, have_h_tets = false;
+
+    // boundary / side-sets (mc_boundary.cu)
+    bool have_boundary = false;
+    mc::DevBuf d_sides;  // (elem, side) pairs, uint64 x 2
+    uint64_t n_sides = 0;
+    std::vector<uint64_t> h_sides;
+    std::vector<std::vector<uint64_t>> h_sidesets;
+};
+
+namespace mc {
+int cuda_fail(cudaError_t e, const char* what);
+#define MC_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return mc::cuda_fail(e_, #call);    \
+    } while (0)
+
+// upload a compiled program into a pooled device buffer
+int upload_program(mc_ctx* ctx, const Program& p, DevBuf& out);
+// boundary + side-sets implementation (mc_boundary.cu)
+int compute_boundary(mc_mesh* m);
+int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, std::vector<uint64_t>& out);
+}  // namespace mc

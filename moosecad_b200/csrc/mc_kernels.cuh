@@ -1,0 +1,604 @@
+// CUDA kernels of the meshing hot path (sm_100a, f64, --fmad=false).
+// Stage map (SURVEY.md §8a -> kernel):
+//   a2  ObjectAdaptor::value over the lattice      k_sdf_field      (FP64-bound, 8 B/pt written)
+//   a6  warp_vertices                              k_warp_codes     (HBM-bound, 8 B read + 1 B written /pt)
+//   a5/a7/a9 cut_lattice, trim_spikes, exterior    k_classify_cells (HBM-bound, ~9 B read + 2 B written /cell)
+//   a10 compact (vertex numbering)                 k_vertex_count / k_vertex_emit (+ k_scan_tiles)
+//   a8  cut_edge bisection                         k_bisect_edges   (FP64-bound, O(surface))
+//   a7/a10 tet emission                            k_tet_emit       (HBM-bound, 16 B written /tet)
+//   a11 check_for_inverted_tets                    k_tet_quality
+#pragma once
+#include "mc_stuffing.cuh"
+
+namespace mc {
+
+// device-side counters, one uint64 each
+enum Counter : int {
+    CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
+    CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_COUNT
+};
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_ITEMS = 8;
+constexpr int TILE_SIZE = TILE_THREADS * TILE_ITEMS;  // lattice points / cells per tile
+
+// per-cell info written by k_classify_cells
+constexpr uint16_t CI_COUNT_MASK = 0x000f;
+constexpr uint16_t CI_REMOVED_SHIFT = 4;   // 5 bits: tet t dropped by the exterior test
+constexpr uint16_t CI_FULL = 1u << 9;      // all five lattice tets emitted untouched
+// per-vertex mask written by k_vertex_count
+constexpr uint16_t VM_CUT_MASK = 0x01ff;   // bit s: the edge along canonical direction s is cut
+constexpr uint16_t VM_USED = 1u << 15;     // the lattice vertex itself is in the output
+
+// ---------------------------------------------------------------------------------------
+// block-wide exclusive scan of one uint32 per thread (TILE_THREADS threads); returns the
+// exclusive prefix, *total receives the block sum
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* total, uint32_t* smem /*[9]*/) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += n;
+    }
+    __syncthreads();  // protect smem reuse between calls
+    if (lane == 31u) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = (lane < TILE_THREADS / 32) ? smem[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o) winc += n;
+        }
+        if (lane < TILE_THREADS / 32) smem[lane] = winc - w;
+        if (lane == TILE_THREADS / 32 - 1) smem[8] = winc;
+    }
+    __syncthreads();
+    *total = smem[8];
+    return smem[wid] + inc - v;
+}
+
+// ---------------------------------------------------------------------------------------
+// a2: the lattice SDF field.  Persistent blocks; the program is staged once per block into
+// shared memory; each warp evaluates WX x WY points of one z-plane per step with a
+// warp-uniform program counter and writes them with coalesced stores.
+template <int WX, int WY>
+__global__ void __launch_bounds__(512)
+k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict__ prog_g, int nwords,
+            int prog_in_smem, uint32_t zplane0, uint32_t nplanes) {
+    extern __shared__ uint64_t s_prog[];
+    const uint64_t* prog = prog_g;
+    if (prog_in_smem) {
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_prog[i] = prog_g[i];
+        __syncthreads();
+        prog = s_prog;
+    }
+    const uint32_t ntx = (L.NX + WX - 1) / WX, nty = (L.NY + WY - 1) / WY;
+    const uint64_t ntiles = (uint64_t)ntx * nty * nplanes;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lx = lane % WX, ly = lane / WX;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles;
+         tile += warps_total) {
+        const uint32_t tx = (uint32_t)(tile % ntx);
+        const uint64_t r = tile / ntx;
+        const uint32_t ty = (uint32_t)(r % nty);
+        const uint32_t Z = zplane0 + (uint32_t)(r / nty);
+        const uint32_t X = tx * WX + lx, Y = ty * WY + ly;
+        const bool inside = X < L.NX && Y < L.NY;
+        // out-of-range lanes evaluate a clamped point so that the warp stays converged
+        const uint32_t Xc = inside ? X : (X < L.NX ? X : L.NX - 1), Yc = Y < L.NY ? Y : L.NY - 1;
+        const double v = vm_eval<true>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z));
+        if (inside) phi_out[pidx(L, X, Y, Z)] = v;
+    }
+}
+
+// ObjectAdaptor::value for arbitrary points (src/main.rs:33-35,95): one point per thread
+static __global__ void k_eval_points(const uint64_t* __restrict__ prog, const double* __restrict__ pts, uint64_t n,
+                              double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t ic = i < n ? i : (n - 1);
+    const double v = vm_eval<true>(prog, pts[3 * ic], pts[3 * ic + 1], pts[3 * ic + 2]);
+    if (i < n) out[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// a6: warp codes for the vertices of planes [z0, z1]
+static __global__ void __launch_bounds__(256)
+k_warp_codes(Lattice L, uint32_t z0, uint32_t z1, unsigned long long* __restrict__ counters, uint32_t own_z0,
+             uint32_t own_z1) {
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t n = per_plane * (z1 - z0 + 1);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t code = 0u;
+    bool owned = false;
+    if (i < n) {
+        const uint32_t Z = z0 + (uint32_t)(i / per_plane);
+        const uint64_t r = i % per_plane;
+        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+        code = warp_eval(L, X, Y, Z);
+        L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
+        owned = Z >= own_z0 && Z <= own_z1;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, code != 0u && owned);
+    if (b && (threadIdx.x & 31u) == 0u) atomicAdd(&counters[CN_WARPED], (unsigned long long)__popc(b));
+}
+
+// ---------------------------------------------------------------------------------------
+// a5/a7/a9: classify the five tets of every cell of layers [cl0, cl1): output-tet count,
+// exterior-test results, "full cell" flag; mark zero-valued vertices that appear in the
+// output; per-tile totals (low 32 bits: output tets, high 32 bits: kept lattice tets) for the
+// cells of the owned layers [c0, c1).
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_classify_cells(Lattice L, const uint64_t* __restrict__ prog, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1,
+                 uint16_t* __restrict__ cinfo, unsigned long long* __restrict__ tile_tot,
+                 unsigned long long* __restrict__ counters) {
+    __shared__ unsigned long long s_tot;
+    if (threadIdx.x == 0) s_tot = 0ull;
+    __syncthreads();
+    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
+    const uint64_t ncell = per_layer * (cl1 - cl0);
+    uint32_t my_out = 0, my_kept = 0;
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        if (i >= ncell) break;
+        const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
+        const uint64_t r = i % per_layer;
+        const uint32_t cy = (uint32_t)(r / L.nx), cx = (uint32_t)(r % L.nx);
+        const Cell c = make_cell(cx, cy, cz);
+        const bool own = cz >= c0 && cz < c1;  // halo layers only contribute flags
+        // corner signs decide the two trivial classes
+        bool all_neg = true, all_pos_raw = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const size_t pi = pidx(L, cx + (uint32_t)C_LAT[k][0], cy + (uint32_t)C_LAT[k][1], cz + (uint32_t)C_LAT[k][2]);
+            const double raw = L.phi[pi];
+            const double w = (L.wcode[pi] & 0x7f) ? 0.0 : raw;
+            all_neg = all_neg && (w < 0.0);
+            all_pos_raw = all_pos_raw && (raw > 0.0);
+        }
+        uint32_t count = 0, kept = 0, removed_bits = 0;
+        bool full = false;
+        if (all_neg) {
+            count = 5; kept = 5; full = true;
+        } else if (!all_pos_raw) {
+            bool untouched = true;
+            for (int t = 0; t < 5; ++t) {
+                TetNodes tn;
+                load_tet(L, c, t, tn);
+                TetOut to;
+                classify_tet(L, c, t, tn, prog, -1, to);
+                if (to.kase == -2) { untouched = false; continue; }
+                ++kept;
+                if (to.ext_removed) { removed_bits |= 1u << t; if (own) atomicAdd(&counters[CN_EXT_REMOVED], 1ull); }
+                if (to.kase >= 0 && own) atomicAdd(&counters[CN_STAT0 + to.kase], 1ull);
+                if (to.kase != -1 || to.ext_removed) untouched = false;
+                count += (uint32_t)to.n;
+                // zero-valued original vertices that made it into the output are "used"
+                for (int q = 0; q < to.n; ++q)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int nd = to.node[q][m];
+                        if (nd < 4 && tn.p[nd] == 0.0) {
+                            const size_t pi = pidx(L, tn.X[nd], tn.Y[nd], tn.Z[nd]);
+                            L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
+                        }
+                    }
+            }
+            full = untouched && count == 5;
+        }
+        cinfo[i] = (uint16_t)(count | (removed_bits << CI_REMOVED_SHIFT) | (full ? CI_FULL : 0));
+        if (own) { my_out += count; my_kept += kept; }
+    }
+    // block total
+    unsigned long long v = (unsigned long long)my_out | ((unsigned long long)my_kept << 32);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0u && v) atomicAdd(&s_tot, v);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+}
+
+// ---------------------------------------------------------------------------------------
+// exclusive scan of per-tile totals (one block).  Entries pack two 32-bit counters; the low
+// halves are scanned into base_lo, the high halves into base_hi (either may be null);
+// totals[0] / totals[1] receive the sums.
+static __global__ void __launch_bounds__(1024)
+k_scan_tiles(const unsigned long long* __restrict__ tot, uint64_t n, unsigned long long* __restrict__ base_lo,
+             unsigned long long* __restrict__ base_hi, unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long s_w[2][32];
+    __shared__ unsigned long long s_carry[2];
+    if (threadIdx.x == 0) { s_carry[0] = 0ull; s_carry[1] = 0ull; }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    for (uint64_t start = 0; start < n; start += 1024) {
+        const uint64_t i = start + threadIdx.x;
+        const unsigned long long e = i < n ? tot[i] : 0ull;
+        unsigned long long v[2] = {e & 0xffffffffull, e >> 32};
+        unsigned long long inc[2] = {v[0], v[1]};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long n0 = __shfl_up_sync(0xffffffffu, inc[0], o);
+            const unsigned long long n1 = __shfl_up_sync(0xffffffffu, inc[1], o);
+            if (lane >= (unsigned)o) { inc[0] += n0; inc[1] += n1; }
+        }
+        if (lane == 31u) { s_w[0][wid] = inc[0]; s_w[1][wid] = inc[1]; }
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w0 = s_w[0][lane], w1 = s_w[1][lane];
+            unsigned long long i0 = w0, i1 = w1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long n0 = __shfl_up_sync(0xffffffffu, i0, o);
+                const unsigned long long n1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= (unsigned)o) { i0 += n0; i1 += n1; }
+            }
+            s_w[0][lane] = i0 - w0;
+            s_w[1][lane] = i1 - w1;
+        }
+        __syncthreads();
+        const unsigned long long ex0 = s_carry[0] + s_w[0][wid] + inc[0] - v[0];
+        const unsigned long long ex1 = s_carry[1] + s_w[1][wid] + inc[1] - v[1];
+        if (i < n) {
+            if (base_lo) base_lo[i] = ex0;
+            if (base_hi) base_hi[i] = ex1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry[0] = ex0 + v[0]; s_carry[1] = ex1 + v[1]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = s_carry[0]; totals[1] = s_carry[1]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// a10 (vertices), pass 1: for every owned lattice vertex decide whether it is in the output
+// and which of its nine owned edges carry a cut vertex.  Tile totals: low = output vertices,
+// high = cut edges.
+__device__ __forceinline__ uint16_t vertex_mask(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    const size_t pi = pidx(L, X, Y, Z);
+    const uint8_t wc = L.wcode[pi];
+    const double pv = (wc & 0x7f) ? 0.0 : L.phi[pi];
+    uint16_t m = 0;
+    if (pv < 0.0 || (pv == 0.0 && (wc & 0x80))) m |= VM_USED;
+    if (pv != 0.0) {
+        const bool even = ((X + Y + Z) & 1u) == 0u;
+        const int nd = even ? 9 : 3;
+        for (int s = 0; s < nd; ++s) {
+            const int64_t wx = (int64_t)X + C_DIR[s][0], wy = (int64_t)Y + C_DIR[s][1], wz = (int64_t)Z + C_DIR[s][2];
+            if (wx < 0 || wy < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
+            const double pw = warped_phi(L, pidx(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz));
+            if ((pv > 0.0 && pw < 0.0) || (pv < 0.0 && pw > 0.0)) m |= (uint16_t)(1u << s);
+        }
+    }
+    return m;
+}
+
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_vertex_count(Lattice L, uint32_t oz0, uint32_t oz1, uint16_t* __restrict__ vmask,
+               unsigned long long* __restrict__ tile_tot) {
+    __shared__ unsigned long long s_tot;
+    if (threadIdx.x == 0) s_tot = 0ull;
+    __syncthreads();
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t n = per_plane * (oz1 - oz0 + 1);
+    unsigned long long mine = 0ull;
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        if (i >= n) break;
+        const uint32_t Z = oz0 + (uint32_t)(i / per_plane);
+        const uint64_t r = i % per_plane;
+        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+        const uint16_t m = vertex_mask(L, X, Y, Z);
+        vmask[pidx(L, X, Y, Z)] = m;
+        const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
+        mine += (unsigned long long)(ncut + ((m & VM_USED) ? 1u : 0u)) | ((unsigned long long)ncut << 32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_tot, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+}
+
+// a10 (vertices), pass 2: number the output vertices (lattice vertex first, then its cut
+// edges in slot order), write the coordinates of the lattice vertices (warped where
+// applicable) and append the cut edges to the bisection work list.
+// vbase holds the slab-local id (signed 32-bit offset from `vertex_base`).
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_vertex_emit(Lattice L, uint32_t oz0, uint32_t oz1, const uint16_t* __restrict__ vmask,
+              const unsigned long long* __restrict__ tile_vbase, const unsigned long long* __restrict__ tile_cbase,
+              int32_t* __restrict__ vbase, double* __restrict__ coords, unsigned long long* __restrict__ cutlist) {
+    __shared__ uint32_t s_scan[9];
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t n = per_plane * (oz1 - oz0 + 1);
+    uint64_t vrun = tile_vbase[blockIdx.x], crun = tile_cbase[blockIdx.x];
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        uint16_t m = 0;
+        uint32_t X = 0, Y = 0, Z = 0;
+        size_t pi = 0;
+        if (i < n) {
+            Z = oz0 + (uint32_t)(i / per_plane);
+            const uint64_t r = i % per_plane;
+            Y = (uint32_t)(r / L.NX); X = (uint32_t)(r % L.NX);
+            pi = pidx(L, X, Y, Z);
+            m = vmask[pi];
+        }
+        const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
+        const uint32_t nout = ncut + ((m & VM_USED) ? 1u : 0u);
+        uint32_t vtot, ctot;
+        const uint32_t vex = block_exscan(nout, &vtot, s_scan);
+        const uint32_t cex = block_exscan(ncut, &ctot, s_scan);
+        if (i < n) {
+            const uint64_t id0 = vrun + vex;
+            vbase[pi] = (int32_t)id0;
+            if (m & VM_USED) {
+                double p[3];
+                warped_pos(L, X, Y, Z, p);
+                coords[3 * id0] = p[0]; coords[3 * id0 + 1] = p[1]; coords[3 * id0 + 2] = p[2];
+            }
+            uint64_t ci = crun + cex;
+            for (int s = 0; s < 9; ++s)
+                if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
+        }
+        vrun += vtot;
+        crun += ctot;
+    }
+}
+
+// slab-local id of the cut vertex on the edge leaving `owner` along canonical slot s
+__device__ __forceinline__ int64_t cut_vertex_id(int32_t owner_base, uint16_t owner_mask, int s) {
+    return (int64_t)owner_base + ((owner_mask & VM_USED) ? 1 : 0) + __popc(owner_mask & ((1u << s) - 1u));
+}
+
+// a8: cut_edge — bisection of the real SDF between the positive and the negative end of
+// every cut edge until |phi| <= resolution * relative_error (tessellate3d/src/lib.rs:198-210).
+// One edge per thread; lanes that have converged idle until the warp is done so that the
+// evaluator stays warp-uniform.
+static __global__ void __launch_bounds__(256)
+k_bisect_edges(Lattice L, const uint64_t* __restrict__ prog, const unsigned long long* __restrict__ cutlist,
+               uint64_t ncut, const uint16_t* __restrict__ vmask, const int32_t* __restrict__ vbase,
+               double error_threshold, uint32_t max_iters, double* __restrict__ coords,
+               unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < ncut;
+    const unsigned long long e = cutlist[active ? i : (ncut - 1)];
+    const size_t pi = (size_t)(e >> 4);
+    const int s = (int)(e & 15ull);
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint32_t Z = L.pz0 + (uint32_t)(pi / per_plane);
+    const uint64_t r = pi % per_plane;
+    const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+    const uint32_t WX = X + C_DIR[s][0], WY = Y + C_DIR[s][1], WZ = Z + C_DIR[s][2];
+    const double pv = L.phi[pi];
+    // `a` starts at the positive end (every call site passes the phi > 0 vertex first)
+    double ax, ay, az, bx, by, bz;
+    if (pv > 0.0) {
+        ax = lat_x(L, X); ay = lat_y(L, Y); az = lat_z(L, Z);
+        bx = lat_x(L, WX); by = lat_y(L, WY); bz = lat_z(L, WZ);
+    } else {
+        bx = lat_x(L, X); by = lat_y(L, Y); bz = lat_z(L, Z);
+        ax = lat_x(L, WX); ay = lat_y(L, WY); az = lat_z(L, WZ);
+    }
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    bool done = !active;
+    uint32_t iters = 0;
+    while (__any_sync(0xffffffffu, !done)) {
+        const double mx = (ax + bx) * 0.5, my = (ay + by) * 0.5, mz = (az + bz) * 0.5;
+        const double phi = vm_eval<true>(prog, mx, my, mz);
+        if (!done) {
+            cx = mx; cy = my; cz = mz;
+            ++iters;
+            if (fabs(phi) <= error_threshold) done = true;
+            else if (phi > 0.0) { ax = mx; ay = my; az = mz; }   // phia stays positive
+            else { bx = mx; by = my; bz = mz; }
+            if (!done && iters >= max_iters) {
+                done = true;
+                atomicAdd(&counters[CN_BISECT_FAIL], 1ull);
+            }
+        }
+    }
+    if (active) {
+        const int64_t id = cut_vertex_id(vbase[pi], vmask[pi], s);
+        coords[3 * id] = cx; coords[3 * id + 1] = cy; coords[3 * id + 2] = cz;
+    }
+    unsigned long long it64 = active ? iters : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) it64 += __shfl_xor_sync(0xffffffffu, it64, o);
+    if ((threadIdx.x & 31u) == 0u && it64) atomicAdd(&counters[CN_BISECT_ITERS], it64);
+}
+
+// ---------------------------------------------------------------------------------------
+// a7/a10: emit the output tets of the owned cells.  Ids written are global
+// (vertex_base + slab-local id).
+template <typename IndexT>
+__device__ __forceinline__ IndexT node_global_id(const Lattice& L, const TetNodes& tn, int code,
+                                                 const uint16_t* __restrict__ vmask,
+                                                 const int32_t* __restrict__ vbase, int64_t vertex_base) {
+    if (code < 4) return (IndexT)(vertex_base + (int64_t)vbase[pidx(L, tn.X[code], tn.Y[code], tn.Z[code])]);
+    const int i = (code - 4) >> 2, j = (code - 4) & 3;
+    const int dx = (int)tn.X[j] - (int)tn.X[i], dy = (int)tn.Y[j] - (int)tn.Y[i], dz = (int)tn.Z[j] - (int)tn.Z[i];
+    int d = dir_index(dx, dy, dz);
+    int owner = i;
+    if (d >= 9) { d -= 9; owner = j; }
+    const size_t pi = pidx(L, tn.X[owner], tn.Y[owner], tn.Z[owner]);
+    return (IndexT)(vertex_base + cut_vertex_id(vbase[pi], vmask[pi], d));
+}
+
+template <typename IndexT>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_tet_emit(Lattice L, uint32_t cl0, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
+           const unsigned long long* __restrict__ tile_tbase, const uint16_t* __restrict__ vmask,
+           const int32_t* __restrict__ vbase, int64_t vertex_base, IndexT* __restrict__ tets) {
+    __shared__ uint32_t s_scan[9];
+    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
+    const uint64_t first = per_layer * (c0 - cl0);        // owned cells inside the classified range
+    const uint64_t last = per_layer * (c1 - cl0);
+    uint64_t trun = tile_tbase[blockIdx.x];
+    for (int it = 0; it < TILE_ITEMS; ++it) {
+        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
+        const bool owned = i >= first && i < last;
+        const uint16_t ci = owned ? cinfo[i] : (uint16_t)0;
+        const uint32_t count = ci & CI_COUNT_MASK;
+        uint32_t ttot;
+        const uint32_t tex = block_exscan(count, &ttot, s_scan);
+        if (count) {
+            const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
+            const uint64_t r = i % per_layer;
+            const uint32_t cy = (uint32_t)(r / L.nx), cx = (uint32_t)(r % L.nx);
+            const Cell c = make_cell(cx, cy, cz);
+            uint64_t o = trun + tex;
+            for (int t = 0; t < 5; ++t) {
+                TetNodes tn;
+                load_tet(L, c, t, tn);
+                TetOut to;
+                if (ci & CI_FULL) {
+                    to.n = 1;
+                    to.node[0][0] = 0; to.node[0][1] = 1; to.node[0][2] = 2; to.node[0][3] = 3;
+                } else {
+                    classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+                }
+                for (int q = 0; q < to.n; ++q) {
+                    IndexT id[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        id[m] = node_global_id<IndexT>(L, tn, to.node[q][m], vmask, vbase, vertex_base);
+                    IndexT* dst = tets + 4 * o;
+                    dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
+                    ++o;
+                }
+            }
+        }
+        trun += ttot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// a11: Mesh::volume and Mesh::aspect_ratio (mesh/src/lib.rs:292-316)
+__device__ __forceinline__ void tet_quality(const double a[3], const double b[3], const double c[3],
+                                            const double d[3], double& vol, double& ar) {
+    // determinant of the matrix with columns a-d, b-d, c-d (nalgebra 3x3 closed form)
+    const double m11 = a[0] - d[0], m21 = a[1] - d[1], m31 = a[2] - d[2];
+    const double m12 = b[0] - d[0], m22 = b[1] - d[1], m32 = b[2] - d[2];
+    const double m13 = c[0] - d[0], m23 = c[1] - d[1], m33 = c[2] - d[2];
+    const double minor_m12_m23 = m22 * m33 - m32 * m23;
+    const double minor_m11_m23 = m21 * m33 - m31 * m23;
+    const double minor_m11_m22 = m21 * m32 - m31 * m22;
+    vol = (m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22) / 6.0;
+    const double* P[4] = {a, b, c, d};
+    double ab[3], ac[3], ad[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ad[k] = d[k] - a[k]; }
+    const double cr0 = ac[1] * ad[2] - ac[2] * ad[1], cr1 = ac[2] * ad[0] - ac[0] * ad[2], cr2 = ac[0] * ad[1] - ac[1] * ad[0];
+    const double alpha = fabs((ab[0] * cr0 + ab[1] * cr1) + ab[2] * cr2);
+    double sum_normals = 0.0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const double* q0 = P[C_FACE[f][0]]; const double* q1 = P[C_FACE[f][1]]; const double* q2 = P[C_FACE[f][2]];
+        const double u0 = q1[0] - q0[0], u1 = q1[1] - q0[1], u2 = q1[2] - q0[2];
+        const double v0 = q2[0] - q0[0], v1 = q2[1] - q0[1], v2 = q2[2] - q0[2];
+        const double n0 = u1 * v2 - u2 * v1, n1 = u2 * v0 - u0 * v2, n2 = u0 * v1 - u1 * v0;
+        sum_normals += sqrt((n0 * n0 + n1 * n1) + n2 * n2);
+    }
+    double max_length2 = 0.0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        const double* q0 = P[C_EDGE[e][0]]; const double* q1 = P[C_EDGE[e][1]];
+        const double u0 = q1[0] - q0[0], u1 = q1[1] - q0[1], u2 = q1[2] - q0[2];
+        max_length2 = fmax(max_length2, (u0 * u0 + u1 * u1) + u2 * u2);
+    }
+    const double max_length = sqrt(max_length2);
+    const double radius = alpha / sum_normals;
+    ar = 1.0 / (max_length / radius / (2.0 * sqrt(6.0)));
+}
+
+// per-tet quality for explicit arrays (mc_tet_quality)
+static __global__ void k_tet_quality_arrays(const double* __restrict__ coords, const unsigned long long* __restrict__ tets,
+                                     uint64_t nt, double* __restrict__ vol, double* __restrict__ ar) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    double p[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[n][k] = coords[3 * tets[4 * i + n] + k];
+    tet_quality(p[0], p[1], p[2], p[3], vol[i], ar[i]);
+}
+
+// check_for_inverted_tets over the emitted mesh: min / max aspect ratio, inverted count
+// (tessellate3d/src/lib.rs:400-418).  Aspect ratios are >= 0, so their bit patterns order
+// like unsigned integers.
+template <typename IndexT>
+__global__ void __launch_bounds__(256)
+k_tet_quality(const double* __restrict__ coords, const IndexT* __restrict__ tets, uint64_t nt, int64_t vertex_base,
+              unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double armin = 1.0, armax = 0.0;
+    unsigned inv = 0;
+    if (i < nt) {
+        double p[4][3];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int64_t id = (int64_t)tets[4 * i + n] - vertex_base;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p[n][k] = coords[3 * id + k];
+        }
+        double vol, ar;
+        tet_quality(p[0], p[1], p[2], p[3], vol, ar);
+        if (vol <= 0.0) inv = 1;
+        armin = fmin(armin, ar);
+        armax = fmax(armax, ar);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        armin = fmin(armin, __shfl_xor_sync(0xffffffffu, armin, o));
+        armax = fmax(armax, __shfl_xor_sync(0xffffffffu, armax, o));
+        inv += __shfl_xor_sync(0xffffffffu, inv, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (inv) atomicAdd(&counters[CN_INVERTED], (unsigned long long)inv);
+        const unsigned long long bmin = (unsigned long long)__double_as_longlong(armin);
+        const unsigned long long bmax = (unsigned long long)__double_as_longlong(armax);
+        if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
+        if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
+    }
+}
+
+// import the id table of a plane owned by the rank below (multi-GPU)
+static __global__ void k_import_plane(Lattice L, uint32_t Z, const unsigned long long* __restrict__ table, int64_t vertex_base,
+                               uint16_t* __restrict__ vmask, int32_t* __restrict__ vbase) {
+    const uint64_t n = (uint64_t)L.NX * L.NY;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long e = table[i];
+    const size_t pi = (size_t)(Z - L.pz0) * n + i;
+    vmask[pi] = (uint16_t)(e & 0xffffull);
+    vbase[pi] = (int32_t)((int64_t)(e >> 16) - vertex_base);
+}
+static __global__ void k_export_plane(Lattice L, uint32_t Z, const uint16_t* __restrict__ vmask,
+                               const int32_t* __restrict__ vbase, int64_t vertex_base,
+                               unsigned long long* __restrict__ table) {
+    const uint64_t n = (uint64_t)L.NX * L.NY;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t pi = (size_t)(Z - L.pz0) * n + i;
+    table[i] = ((unsigned long long)(vertex_base + (int64_t)vbase[pi]) << 16) | (unsigned long long)vmask[pi];
+}
+
+// DADD + DMUL throughput probe (no FMA): 8 independent chains per thread
+static __global__ void k_probe_fp64(double* out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m; a1 = a1 * m; a2 = a2 * m; a3 = a3 * m; a4 = a4 * m; a5 = a5 * m; a6 = a6 * m; a7 = a7 * m;
+        a0 = a0 + c; a1 = a1 + c; a2 = a2 + c; a3 = a3 + c; a4 = a4 + c; a5 = a5 + c; a6 = a6 + c; a7 = a7 + c;
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace mc

@@ -1,0 +1,674 @@
+// C ABI — device context, point evaluation and the mesher (include/moosecad_b200.h).
+// Host orchestration of the kernels in mc_kernels.cuh.  No CPU fallback anywhere: every
+// entry point here launches CUDA kernels or fails with MC_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "mc_internal.hpp"
+#include "mc_kernels.cuh"
+
+using namespace mc;
+
+namespace mc {
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int upload_program(mc_ctx* ctx, const Program& p, DevBuf& out) {
+    int rc = ctx->alloc(p.words.size() * 8, out);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(cudaMemcpyAsync(out.p, p.words.data(), p.words.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // the host vector must outlive the copy: pageable memcpy is staged before returning
+    return MC_OK;
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+}  // namespace mc
+
+// ---- pooled device memory ---------------------------------------------------------------
+int mc_ctx::alloc(size_t bytes, DevBuf& out) {
+    if (bytes == 0) bytes = 8;
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (int i = 0; i < (int)free_list.size(); ++i)
+        if (free_list[i].bytes >= bytes && (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+    if (best >= 0 && free_list[best].bytes <= bytes + bytes / 4 + (1u << 20)) {
+        out = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        return MC_OK;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // release the cache and retry once
+        trim();
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    }
+    held_bytes += bytes;
+    out.p = p;
+    out.bytes = bytes;
+    return MC_OK;
+}
+void mc_ctx::release(DevBuf& b) {
+    if (b.p) free_list.push_back(b);
+    b = DevBuf();
+}
+void mc_ctx::trim() {
+    for (auto& b : free_list) {
+        cudaFree(b.p);
+        held_bytes -= b.bytes;
+    }
+    free_list.clear();
+}
+
+static void mesh_release_all(mc_mesh* m) {
+    mc_ctx* c = m->ctx;
+    DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vbase, &m->d_cinfo, &m->d_ctile_tot,
+                      &m->d_ctile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
+                      &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides};
+    for (DevBuf* b : bufs) c->release(*b);
+    for (auto& e : m->ev)
+        if (e) { cudaEventDestroy(e); e = nullptr; }
+}
+
+extern "C" {
+
+// ---- context ----------------------------------------------------------------------------
+mc_ctx* mc_ctx_new(int device, void* stream) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fail(MC_ERR_CUDA, std::string("mc_ctx_new: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { fail(MC_ERR_ARG, "mc_ctx_new: bad device ordinal"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(MC_ERR_CUDA, "mc_ctx_new: cudaSetDevice failed"); return nullptr; }
+    mc_ctx* c = new mc_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->sm_count = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    return c;
+}
+void mc_ctx_free(mc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->trim();
+    delete c;
+}
+int mc_ctx_device(const mc_ctx* c) { return c ? c->device : MC_ERR_ARG; }
+uint64_t mc_ctx_launch_count(const mc_ctx* c) { return c ? c->launches : 0; }
+uint64_t mc_ctx_workspace_bytes(const mc_ctx* c) { return c ? c->held_bytes : 0; }
+int mc_ctx_trim(mc_ctx* c) {
+    if (!c) return fail(MC_ERR_ARG, "mc_ctx_trim: null context");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->trim();
+    return MC_OK;
+}
+
+// ---- ObjectAdaptor::value ---------------------------------------------------------------
+int mc_eval_points_device(mc_ctx* c, const mc_tape* t, int32_t root, double slack, const void* d_points, uint64_t n,
+                          void* d_out) {
+    if (!c || !t) return fail(MC_ERR_ARG, "mc_eval_points_device: null handle");
+    if (n == 0) return MC_OK;
+    MC_CUDA(cudaSetDevice(c->device));
+    Program p;
+    std::string err;
+    int rc = t->compile(root, slack, p, err);
+    if (rc != MC_OK) return fail(rc, err);
+    DevBuf dp;
+    rc = upload_program(c, p, dp);
+    if (rc != MC_OK) return rc;
+    k_eval_points<<<blocks_for(n, 256), 256, 0, c->stream>>>((const uint64_t*)dp.p, (const double*)d_points, n,
+                                                              (double*)d_out);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
+    MC_CUDA(cudaStreamSynchronize(c->stream));  // dp is recycled below
+    c->release(dp);
+    return MC_OK;
+}
+
+int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, const double* points, uint64_t n,
+                   double* out) {
+    if (!c || !t || (n && (!points || !out))) return fail(MC_ERR_ARG, "mc_eval_points: bad argument");
+    if (n == 0) return MC_OK;
+    MC_CUDA(cudaSetDevice(c->device));
+    DevBuf dpts, dout;
+    int rc = c->alloc(n * 24, dpts);
+    if (rc != MC_OK) return rc;
+    rc = c->alloc(n * 8, dout);
+    if (rc != MC_OK) { c->release(dpts); return rc; }
+    MC_CUDA(cudaMemcpyAsync(dpts.p, points, n * 24, cudaMemcpyHostToDevice, c->stream));
+    rc = mc_eval_points_device(c, t, root, slack, dpts.p, n, dout.p);
+    if (rc == MC_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy back");
+    }
+    c->release(dpts);
+    c->release(dout);
+    return rc;
+}
+
+// ---- the mesher -------------------------------------------------------------------------
+static int launch_sdf_field(mc_mesh* m) {
+    mc_ctx* c = m->ctx;
+    const int nwords = (int)m->prog.words.size();
+    const size_t prog_bytes = (size_t)nwords * 8;
+    // stage the program in shared memory when it fits (leave room for 2 blocks per SM when small)
+    const size_t smem_cap = c->smem_optin ? c->smem_optin : 48 * 1024;
+    const int in_smem = prog_bytes <= smem_cap ? 1 : 0;
+    const size_t smem = in_smem ? prog_bytes : 0;
+    const uint32_t nplanes = m->L.pz1 - m->L.pz0 + 1;
+    // cheap programs are HBM-write bound: 32 consecutive x per warp; heavy ones want compact
+    // warp footprints so that bbox guards are warp-coherent
+    const bool linear = m->prog.flops < 64;
+    auto kern = linear ? k_sdf_field<32, 1> : k_sdf_field<8, 4>;
+    if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t ntiles = (uint64_t)((m->L.NX + (linear ? 31 : 7)) / (linear ? 32 : 8)) *
+                            ((m->L.NY + (linear ? 0 : 3)) / (linear ? 1 : 4)) * nplanes;
+    uint64_t grid = (uint64_t)c->sm_count * per_sm;
+    const uint64_t need = (ntiles + 15) / 16;
+    if (grid > need) grid = need ? need : 1;
+    kern<<<(unsigned)grid, 512, smem, c->stream>>>(m->L, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p, nwords,
+                                                   in_smem, m->L.pz0, nplanes);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
+    return MC_OK;
+}
+
+int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double relative_error,
+                        const mc_slab* slab, const mc_options* opts, mc_mesh** out) {
+    if (!c || !volume || !out) return fail(MC_ERR_ARG, "mc_tessellate_begin: null handle");
+    *out = nullptr;
+    if (!volume->valid(root)) return fail(MC_ERR_ARG, "mc_tessellate_begin: invalid root node");
+    if (!(resolution > 0.0)) return fail(MC_ERR_ARG, "mc_tessellate_begin: resolution must be positive");
+    MC_CUDA(cudaSetDevice(c->device));
+
+    // IsosurfaceStuffing::new (tessellate3d/src/lib.rs:36-52): dim = ceil(bbox.dim / resolution)
+    const Box& bb = volume->nodes[(size_t)root].bbox;
+    uint64_t dim[3];
+    for (int k = 0; k < 3; ++k) {
+        const double d = std::ceil((bb.hi[k] - bb.lo[k]) / resolution);
+        if (!(d >= 0.0) || !(d < 4294967295.0) || !std::isfinite(bb.lo[k]))
+            return fail(MC_ERR_BBOX, "mc_tessellate_begin: the volume's bounding box is not finite (or the lattice exceeds 2^32 cells per axis)");
+        dim[k] = (uint64_t)d;
+    }
+    mc_mesh* m = new mc_mesh();
+    m->ctx = c;
+    for (int k = 0; k < 3; ++k) m->dim[k] = dim[k];
+    m->resolution = resolution;
+    m->error_threshold = resolution * relative_error;
+    if (opts && opts->struct_size >= sizeof(mc_options)) {
+        m->flags = opts->flags;
+        if (opts->max_bisect_iters) m->max_bisect = opts->max_bisect_iters;
+    }
+    std::string err;
+    // ObjectAdaptor::value = approx_value(p, tessellation_resolution), src/main.rs:33-35
+    int rc = volume->compile(root, resolution, m->prog, err);
+    if (rc != MC_OK) { delete m; return fail(rc, err); }
+
+    Lattice& L = m->L;
+    L.nx = (uint32_t)dim[0]; L.ny = (uint32_t)dim[1]; L.nz = (uint32_t)dim[2];
+    L.NX = L.nx + 1; L.NY = L.ny + 1; L.NZ = L.nz + 1;
+    L.ox = bb.lo[0]; L.oy = bb.lo[1]; L.oz = bb.lo[2];
+    L.res = resolution;
+    uint64_t zb = 0, ze = dim[2];
+    if (slab && !(slab->z_begin == 0 && slab->z_end == 0)) { zb = slab->z_begin; ze = slab->z_end; }
+    if (zb > ze || ze > dim[2]) { delete m; return fail(MC_ERR_ARG, "mc_tessellate_begin: bad slab range"); }
+    m->c0 = (uint32_t)zb; m->c1 = (uint32_t)ze;
+    const uint32_t nz = L.nz;
+    L.pz0 = m->c0 >= 2 ? m->c0 - 2 : 0;
+    L.pz1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 2);
+    m->wz0 = m->c0 >= 1 ? m->c0 - 1 : 0;
+    m->wz1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
+    m->cl0 = m->c0 >= 1 ? m->c0 - 1 : 0;
+    m->cl1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
+    m->oz0 = m->c0 == 0 ? 0 : m->c0 + 1;
+    m->oz1 = m->c1;
+    const bool empty_slab = (m->c0 == m->c1 && !(m->c0 == 0 && nz == 0));
+
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t npts = per_plane * (L.pz1 - L.pz0 + 1);
+    const uint64_t ncls = (uint64_t)L.nx * L.ny * (m->cl1 - m->cl0);
+    const uint64_t nown = (m->oz1 >= m->oz0 && !empty_slab) ? per_plane * (m->oz1 - m->oz0 + 1) : 0;
+    m->points_evaluated = npts;
+    m->points_owned = nown;
+    m->n_ctiles = (ncls + TILE_SIZE - 1) / TILE_SIZE;
+    m->n_vtiles = (nown + TILE_SIZE - 1) / TILE_SIZE;
+
+#define MC_TRY(x) do { rc = (x); if (rc != MC_OK) { mesh_release_all(m); delete m; return rc; } } while (0)
+#define MC_TRY_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { mesh_release_all(m); delete m; return cuda_fail(e_, #x); } } while (0)
+    for (auto& e : m->ev) MC_TRY_CUDA(cudaEventCreate(&e));
+    MC_TRY(upload_program(c, m->prog, m->d_prog));
+    MC_TRY(c->alloc(npts * 8, m->d_phi));
+    MC_TRY(c->alloc(npts, m->d_wcode));
+    MC_TRY(c->alloc(npts * 2, m->d_vmask));
+    MC_TRY(c->alloc(npts * 4, m->d_vbase));
+    MC_TRY(c->alloc(std::max<uint64_t>(ncls, 1) * 2, m->d_cinfo));
+    MC_TRY(c->alloc((m->n_ctiles + 1) * 8, m->d_ctile_tot));
+    MC_TRY(c->alloc((m->n_ctiles + 1) * 8, m->d_ctile_base));
+    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_tot));
+    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_vbase));
+    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_cbase));
+    MC_TRY(c->alloc(64 * 8, m->d_counters));
+    L.phi = (const double*)m->d_phi.p;
+    L.wcode = (uint8_t*)m->d_wcode.p;
+
+    cudaStream_t s = c->stream;
+    {
+        uint64_t init[64] = {0};
+        const double one = 1.0;
+        std::memcpy(&init[CN_AR_MIN_BITS], &one, 8);  // aspect_ratio = (one, zero), tessellate3d/src/lib.rs:404
+        MC_TRY_CUDA(cudaMemcpyAsync(m->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    }
+    MC_TRY_CUDA(cudaMemsetAsync(m->d_wcode.p, 0, npts, s));
+    unsigned long long* counters = (unsigned long long*)m->d_counters.p;
+
+    // a2: SDF field on all stored planes
+    MC_TRY_CUDA(cudaEventRecord(m->ev[0], s));
+    MC_TRY(launch_sdf_field(m));
+    MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
+    // a6: warp codes
+    {
+        const uint64_t n = per_plane * (m->wz1 - m->wz0 + 1);
+        k_warp_codes<<<blocks_for(n, 256), 256, 0, s>>>(L, m->wz0, m->wz1, counters, m->oz0, m->oz1);
+        c->launches++;
+        MC_TRY_CUDA(cudaGetLastError());
+    }
+    MC_TRY_CUDA(cudaEventRecord(m->ev[2], s));
+    // a5/a7/a9: classification + counts
+    if (ncls > 0) {
+        k_classify_cells<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
+            L, (const uint64_t*)m->d_prog.p, m->cl0, m->cl1, m->c0, m->c1, (uint16_t*)m->d_cinfo.p,
+            (unsigned long long*)m->d_ctile_tot.p, counters);
+        c->launches++;
+        MC_TRY_CUDA(cudaGetLastError());
+    }
+    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_ctile_tot.p, m->n_ctiles,
+                                    (unsigned long long*)m->d_ctile_base.p, nullptr, counters + CN_TETS);
+    c->launches++;
+    MC_TRY_CUDA(cudaGetLastError());
+    // CN_TETS / CN_KEPT are adjacent: totals[0] = output tets, totals[1] = kept lattice tets
+    static_assert(CN_KEPT == CN_TETS + 1, "scan totals layout");
+    MC_TRY_CUDA(cudaEventRecord(m->ev[3], s));
+    // a10 pass 1: vertex masks + counts
+    if (nown > 0) {
+        k_vertex_count<<<(unsigned)m->n_vtiles, TILE_THREADS, 0, s>>>(L, m->oz0, m->oz1, (uint16_t*)m->d_vmask.p,
+                                                                       (unsigned long long*)m->d_vtile_tot.p);
+        c->launches++;
+        MC_TRY_CUDA(cudaGetLastError());
+    }
+    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_vtile_tot.p, m->n_vtiles,
+                                    (unsigned long long*)m->d_vtile_vbase.p, (unsigned long long*)m->d_vtile_cbase.p,
+                                    counters + CN_VERTS);
+    c->launches++;
+    MC_TRY_CUDA(cudaGetLastError());
+    static_assert(CN_CUTS == CN_VERTS + 1, "scan totals layout");
+    MC_TRY_CUDA(cudaEventRecord(m->ev[4], s));
+    MC_TRY_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    MC_TRY_CUDA(cudaStreamSynchronize(s));
+    m->n_verts = m->counters[CN_VERTS];
+    m->n_cuts = m->counters[CN_CUTS];
+    m->n_tets = m->counters[CN_TETS];
+    m->n_kept = m->counters[CN_KEPT];
+    if (m->n_verts >= (1ull << 31)) {
+        mesh_release_all(m);
+        delete m;
+        return fail(MC_ERR_LIMIT, "more than 2^31 vertices in one slab; shard the lattice over more GPUs");
+    }
+    m->phase = 1;
+    *out = m;
+    return MC_OK;
+}
+
+int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
+    if (!m || m->phase != 1) return fail(MC_ERR_STATE, "mc_tessellate_emit_vertices: call mc_tessellate_begin first");
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    m->vertex_base = vertex_base;
+    int rc;
+    rc = c->alloc(std::max<uint64_t>(m->n_verts, 1) * 24, m->d_coords);
+    if (rc != MC_OK) return rc;
+    rc = c->alloc(std::max<uint64_t>(m->n_cuts, 1) * 8, m->d_cutlist);
+    if (rc != MC_OK) return rc;
+    const Lattice& L = m->L;
+    unsigned long long* counters = (unsigned long long*)m->d_counters.p;
+    MC_CUDA(cudaEventRecord(m->ev[5], s));
+    if (m->n_vtiles > 0) {
+        k_vertex_emit<<<(unsigned)m->n_vtiles, TILE_THREADS, 0, s>>>(
+            L, m->oz0, m->oz1, (const uint16_t*)m->d_vmask.p, (const unsigned long long*)m->d_vtile_vbase.p,
+            (const unsigned long long*)m->d_vtile_cbase.p, (int32_t*)m->d_vbase.p, (double*)m->d_coords.p,
+            (unsigned long long*)m->d_cutlist.p);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    MC_CUDA(cudaEventRecord(m->ev[6], s));
+    if (m->n_cuts > 0) {
+        k_bisect_edges<<<blocks_for(m->n_cuts, 256), 256, 0, s>>>(
+            L, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts,
+            (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, m->error_threshold, m->max_bisect,
+            (double*)m->d_coords.p, counters);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    MC_CUDA(cudaEventRecord(m->ev[7], s));
+    // id table of the top owned plane for the rank above
+    if (m->c1 < L.nz && m->points_owned > 0) {
+        const uint64_t n = (uint64_t)L.NX * L.NY;
+        rc = c->alloc(n * 8, m->d_plane_table);
+        if (rc != MC_OK) return rc;
+        k_export_plane<<<blocks_for(n, 256), 256, 0, s>>>(L, m->oz1, (const uint16_t*)m->d_vmask.p,
+                                                          (const int32_t*)m->d_vbase.p, (int64_t)vertex_base,
+                                                          (unsigned long long*)m->d_plane_table.p);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    m->phase = 2;
+    return MC_OK;
+}
+
+int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_plane) {
+    if (!m || m->phase != 2) return fail(MC_ERR_STATE, "mc_tessellate_emit_tets: call mc_tessellate_emit_vertices first");
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    m->tet_base = tet_base;
+    const Lattice& L = m->L;
+    unsigned long long* counters = (unsigned long long*)m->d_counters.p;
+    if (m->c0 > 0) {
+        if (!d_lower_plane) return fail(MC_ERR_ARG, "mc_tessellate_emit_tets: slab does not start at z = 0, the lower plane table is required");
+        const uint64_t n = (uint64_t)L.NX * L.NY;
+        k_import_plane<<<blocks_for(n, 256), 256, 0, s>>>(L, m->c0, (const unsigned long long*)d_lower_plane,
+                                                          (int64_t)m->vertex_base, (uint16_t*)m->d_vmask.p,
+                                                          (int32_t*)m->d_vbase.p);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    m->index_bytes = (m->vertex_base + m->n_verts < (1ull << 32)) ? 4 : 8;
+    int rc = c->alloc(std::max<uint64_t>(m->n_tets, 1) * 4 * (size_t)m->index_bytes, m->d_tets);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(cudaEventRecord(m->ev[8], s));
+    if (m->n_ctiles > 0 && m->n_tets > 0) {
+        if (m->index_bytes == 4)
+            k_tet_emit<uint32_t><<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
+                L, m->cl0, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
+                (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, (int64_t)m->vertex_base,
+                (uint32_t*)m->d_tets.p);
+        else
+            k_tet_emit<unsigned long long><<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
+                L, m->cl0, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
+                (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, (int64_t)m->vertex_base,
+                (unsigned long long*)m->d_tets.p);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    MC_CUDA(cudaEventRecord(m->ev[9], s));
+    // a11: quality.  Tets of a slab may reference vertices of the plane below (owned by another
+    // rank); the single-device path (vertex_base == 0, c0 == 0) sees every vertex.
+    if (!(m->flags & MC_OPT_SKIP_QUALITY) && m->n_tets > 0 && m->c0 == 0) {
+        if (m->index_bytes == 4)
+            k_tet_quality<uint32_t><<<blocks_for(m->n_tets, 256), 256, 0, s>>>(
+                (const double*)m->d_coords.p, (const uint32_t*)m->d_tets.p, m->n_tets, (int64_t)m->vertex_base, counters);
+        else
+            k_tet_quality<unsigned long long><<<blocks_for(m->n_tets, 256), 256, 0, s>>>(
+                (const double*)m->d_coords.p, (const unsigned long long*)m->d_tets.p, m->n_tets,
+                (int64_t)m->vertex_base, counters);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    MC_CUDA(cudaEventRecord(m->ev[10], s));
+    MC_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    float ms;
+    const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {5, 6}, {6, 7}, {8, 9}, {9, 10}};
+    for (int i = 0; i < 7; ++i) {
+        MC_CUDA(cudaEventElapsedTime(&ms, m->ev[pairs[i][0]], m->ev[pairs[i][1]]));
+        m->stage_ms[i] = ms;
+    }
+    MC_CUDA(cudaEventElapsedTime(&ms, m->ev[3], m->ev[4]));
+    m->stage_ms[3] += ms;  // vertex count + scan belongs to "vertex scan+emit"
+    // scratch that is no longer needed goes back to the pool now
+    c->release(m->d_cutlist);
+    if (!(m->flags & MC_OPT_KEEP_PHI)) { /* phi / wcode stay: boundary + side-sets re-classify cells */ }
+    m->phase = 3;
+    if (m->counters[CN_BISECT_FAIL])
+        return fail(MC_ERR_DIVERGED, "edge bisection did not reach the error threshold within the iteration cap on " +
+                                         std::to_string(m->counters[CN_BISECT_FAIL]) + " edges");
+    return MC_OK;
+}
+
+int mc_tessellate(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double relative_error,
+                  const mc_options* opts, mc_mesh** out) {
+    mc_mesh* m = nullptr;
+    int rc = mc_tessellate_begin(c, volume, root, resolution, relative_error, nullptr, opts, &m);
+    if (rc != MC_OK) return rc;
+    rc = mc_tessellate_emit_vertices(m, 0);
+    if (rc == MC_OK) rc = mc_tessellate_emit_tets(m, 0, nullptr);
+    if (rc != MC_OK && rc != MC_ERR_DIVERGED) { mc_mesh_free(m); return rc; }
+    *out = m;
+    return rc;
+}
+
+void mc_mesh_free(mc_mesh* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    mesh_release_all(m);
+    delete m;
+}
+
+int mc_mesh_counts(const mc_mesh* m, uint64_t counts[6]) {
+    if (!m || !counts) return fail(MC_ERR_ARG, "mc_mesh_counts: bad argument");
+    counts[0] = m->n_verts; counts[1] = m->n_tets; counts[2] = m->points_evaluated;
+    counts[3] = m->points_owned; counts[4] = m->n_cuts; counts[5] = m->counters[CN_WARPED];
+    return MC_OK;
+}
+
+int mc_mesh_upper_plane_table(mc_mesh* m, void** d_table, uint64_t* n_entries) {
+    if (!m || !d_table || !n_entries) return fail(MC_ERR_ARG, "mc_mesh_upper_plane_table: bad argument");
+    if (m->phase < 2) return fail(MC_ERR_STATE, "mc_mesh_upper_plane_table: emit the vertices first");
+    *d_table = m->d_plane_table.p;
+    *n_entries = m->d_plane_table.p ? (uint64_t)m->L.NX * m->L.NY : 0;
+    return MC_OK;
+}
+
+int mc_mesh_stats(const mc_mesh* m, uint64_t dim[3], uint64_t ntets_stage[3], uint64_t stats[7], double ar_minmax[2],
+                  uint64_t* inverted) {
+    if (!m) return fail(MC_ERR_ARG, "mc_mesh_stats: null mesh");
+    if (dim) for (int k = 0; k < 3; ++k) dim[k] = m->dim[k];
+    if (ntets_stage) {
+        ntets_stage[0] = m->n_kept;                                   // after cut_lattice (:424)
+        ntets_stage[1] = m->n_kept;                                   // trim_spikes entry (:247)
+        ntets_stage[2] = m->n_tets + m->counters[CN_EXT_REMOVED];     // trim_spikes exit (:366)
+    }
+    if (stats) for (int k = 0; k < 7; ++k) stats[k] = m->counters[CN_STAT0 + k];
+    if (ar_minmax) {
+        std::memcpy(&ar_minmax[0], &m->counters[CN_AR_MIN_BITS], 8);
+        std::memcpy(&ar_minmax[1], &m->counters[CN_AR_MAX_BITS], 8);
+    }
+    if (inverted) *inverted = m->counters[CN_INVERTED];
+    return MC_OK;
+}
+
+int mc_mesh_stage_ms(const mc_mesh* m, double ms[9]) {
+    if (!m || !ms) return fail(MC_ERR_ARG, "mc_mesh_stage_ms: bad argument");
+    for (int i = 0; i < 9; ++i) ms[i] = m->stage_ms[i];
+    return MC_OK;
+}
+
+uint64_t mc_mesh_num_vertices(const mc_mesh* m) { return m ? m->n_verts : 0; }
+uint64_t mc_mesh_num_tets(const mc_mesh* m) { return m ? m->n_tets : 0; }
+
+int mc_mesh_device_views(mc_mesh* m, void** d_coords, void** d_tets, int* index_bytes) {
+    if (!m || m->phase < 3) return fail(MC_ERR_STATE, "mc_mesh_device_views: mesh not emitted");
+    if (d_coords) *d_coords = m->d_coords.p;
+    if (d_tets) *d_tets = m->d_tets.p;
+    if (index_bytes) *index_bytes = m->index_bytes;
+    return MC_OK;
+}
+
+int mc_mesh_copy_to_host(mc_mesh* m, double* coords, void* tets, int index_bytes) {
+    if (!m || m->phase < 3) return fail(MC_ERR_STATE, "mc_mesh_copy_to_host: mesh not emitted");
+    if (index_bytes != 4 && index_bytes != 8) return fail(MC_ERR_ARG, "mc_mesh_copy_to_host: index_bytes must be 4 or 8");
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    if (coords && m->n_verts)
+        MC_CUDA(cudaMemcpyAsync(coords, m->d_coords.p, m->n_verts * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (tets && m->n_tets) {
+        if (index_bytes == m->index_bytes) {
+            MC_CUDA(cudaMemcpyAsync(tets, m->d_tets.p, m->n_tets * 4 * (size_t)index_bytes, cudaMemcpyDeviceToHost, c->stream));
+            MC_CUDA(cudaStreamSynchronize(c->stream));
+        } else if (index_bytes == 8) {  // widen on the host
+            std::vector<uint32_t> tmp(m->n_tets * 4);
+            MC_CUDA(cudaMemcpyAsync(tmp.data(), m->d_tets.p, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+            MC_CUDA(cudaStreamSynchronize(c->stream));
+            uint64_t* o = (uint64_t*)tets;
+            for (size_t i = 0; i < tmp.size(); ++i) o[i] = tmp[i];
+        } else {
+            return fail(MC_ERR_ARG, "mc_mesh_copy_to_host: ids do not fit 32 bits");
+        }
+    }
+    MC_CUDA(cudaStreamSynchronize(c->stream));
+    return MC_OK;
+}
+
+const double* mc_mesh_coords(mc_mesh* m) {
+    if (!m || m->phase < 3) { fail(MC_ERR_STATE, "mc_mesh_coords: mesh not emitted"); return nullptr; }
+    if (!m->have_h_coords) {
+        m->h_coords.resize(m->n_verts * 3);
+        if (mc_mesh_copy_to_host(m, m->h_coords.data(), nullptr, 8) != MC_OK) return nullptr;
+        m->have_h_coords = true;
+    }
+    return m->h_coords.data();
+}
+const uint64_t* mc_mesh_tets(mc_mesh* m) {
+    if (!m || m->phase < 3) { fail(MC_ERR_STATE, "mc_mesh_tets: mesh not emitted"); return nullptr; }
+    if (!m->have_h_tets) {
+        m->h_tets.resize(m->n_tets * 4);
+        if (mc_mesh_copy_to_host(m, nullptr, m->h_tets.data(), 8) != MC_OK) return nullptr;
+        m->have_h_tets = true;
+    }
+    return m->h_tets.data();
+}
+
+int mc_mesh_copy_phi(mc_mesh* m, double* out, uint64_t n) {
+    if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_copy_phi: bad argument");
+    const uint64_t have = (uint64_t)m->L.NX * m->L.NY * (m->L.pz1 - m->L.pz0 + 1);
+    if (n != have) return fail(MC_ERR_ARG, "mc_mesh_copy_phi: expected " + std::to_string(have) + " values");
+    MC_CUDA(cudaSetDevice(m->ctx->device));
+    MC_CUDA(cudaMemcpyAsync(out, m->d_phi.p, n * 8, cudaMemcpyDeviceToHost, m->ctx->stream));
+    MC_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return MC_OK;
+}
+
+// ---- boundary / side-sets (implementation in mc_boundary.cu) -----------------------------
+int mc_mesh_boundary(mc_mesh* m, uint64_t* n_sides) {
+    if (!m || m->phase < 3) return fail(MC_ERR_STATE, "mc_mesh_boundary: mesh not emitted");
+    if (!m->have_boundary) {
+        int rc = compute_boundary(m);
+        if (rc != MC_OK) return rc;
+    }
+    if (n_sides) *n_sides = m->n_sides;
+    return MC_OK;
+}
+const uint64_t* mc_mesh_boundary_sides(mc_mesh* m) {
+    if (mc_mesh_boundary(m, nullptr) != MC_OK) return nullptr;
+    return m->h_sides.data();
+}
+int mc_mesh_add_sideset(mc_mesh* m, const mc_tape* boundary, int32_t root) {
+    if (!m || !boundary) return fail(MC_ERR_ARG, "mc_mesh_add_sideset: null handle");
+    int rc = mc_mesh_boundary(m, nullptr);
+    if (rc != MC_OK) return rc;
+    std::vector<uint64_t> set;
+    rc = compute_sideset(m, boundary, root, set);
+    if (rc != MC_OK) return rc;
+    m->h_sidesets.push_back(std::move(set));
+    return (int)m->h_sidesets.size() - 1;
+}
+uint64_t mc_mesh_sideset_len(const mc_mesh* m, int i) {
+    if (!m || i < 0 || (size_t)i >= m->h_sidesets.size()) return 0;
+    return m->h_sidesets[(size_t)i].size() / 2;
+}
+const uint64_t* mc_mesh_sideset(mc_mesh* m, int i) {
+    if (!m || i < 0 || (size_t)i >= m->h_sidesets.size()) { fail(MC_ERR_ARG, "mc_mesh_sideset: bad index"); return nullptr; }
+    return m->h_sidesets[(size_t)i].data();
+}
+
+// ---- mesh-crate predicates ---------------------------------------------------------------
+int mc_tet_quality(mc_ctx* c, const double* coords, uint64_t nv, const uint64_t* tets, uint64_t nt, double* volume,
+                   double* aspect_ratio) {
+    if (!c || !coords || !tets || !volume || !aspect_ratio) return fail(MC_ERR_ARG, "mc_tet_quality: bad argument");
+    if (nt == 0) return MC_OK;
+    MC_CUDA(cudaSetDevice(c->device));
+    DevBuf dc, dt, dv, da;
+    int rc = c->alloc(nv * 24, dc);
+    if (rc == MC_OK) rc = c->alloc(nt * 32, dt);
+    if (rc == MC_OK) rc = c->alloc(nt * 8, dv);
+    if (rc == MC_OK) rc = c->alloc(nt * 8, da);
+    if (rc == MC_OK) {
+        cudaError_t e = cudaMemcpyAsync(dc.p, coords, nv * 24, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dt.p, tets, nt * 32, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            k_tet_quality_arrays<<<blocks_for(nt, 256), 256, 0, c->stream>>>(
+                (const double*)dc.p, (const unsigned long long*)dt.p, nt, (double*)dv.p, (double*)da.p);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(volume, dv.p, nt * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(aspect_ratio, da.p, nt * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "mc_tet_quality");
+    }
+    c->release(dc); c->release(dt); c->release(dv); c->release(da);
+    return rc;
+}
+
+// ---- probes -----------------------------------------------------------------------------
+int mc_probe_fp64_nofma(mc_ctx* c, double* flops_per_s) {
+    if (!c || !flops_per_s) return fail(MC_ERR_ARG, "mc_probe_fp64_nofma: bad argument");
+    MC_CUDA(cudaSetDevice(c->device));
+    DevBuf d;
+    int rc = c->alloc(8, d);
+    if (rc != MC_OK) return rc;
+    cudaEvent_t a, b;
+    MC_CUDA(cudaEventCreate(&a));
+    MC_CUDA(cudaEventCreate(&b));
+    const int iters = 4096, threads = 256, blocks = c->sm_count * 8;
+    k_probe_fp64<<<blocks, threads, 0, c->stream>>>((double*)d.p, 64);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        MC_CUDA(cudaEventRecord(a, c->stream));
+        k_probe_fp64<<<blocks, threads, 0, c->stream>>>((double*)d.p, iters);
+        MC_CUDA(cudaEventRecord(b, c->stream));
+        MC_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        MC_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flops = (double)blocks * threads * (double)iters * 16.0;
+        best = std::max(best, flops / (ms * 1e-3));
+        c->launches++;
+    }
+    c->launches++;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    c->release(d);
+    *flops_per_s = best;
+    return MC_OK;
+}
+
+}  // extern "C"

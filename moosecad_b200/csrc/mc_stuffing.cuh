@@ -1,0 +1,275 @@
+// Order-free device restatement of tessellate3d's isosurface stuffing:
+//   warp_vertices         tessellate3d/src/lib.rs:138-181   -> warp_eval / warped_pos
+//   first-touch vertex id tessellate3d/src/lib.rs:114-124   -> first_touch_key
+//   trim_spikes           tessellate3d/src/lib.rs:242-367   -> classify_tet
+//   remove_exterior_tets  tessellate3d/src/lib.rs:370-398   -> exterior test inside classify_tet
+// Everything is a pure function of the lattice SDF field, so any thread can recompute any
+// piece; nothing depends on a traversal order.
+#pragma once
+#include "mc_lattice.cuh"
+#include "mc_vm.cuh"
+
+namespace mc {
+
+__device__ __forceinline__ double raw_phi(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    return L.phi[pidx(L, X, Y, Z)];
+}
+// phi after warp_vertices: warped vertices are snapped to 0 (tessellate3d/src/lib.rs:178)
+__device__ __forceinline__ double warped_phi(const Lattice& L, size_t i) {
+    return (L.wcode[i] & 0x7f) ? 0.0 : L.phi[i];
+}
+
+// cut_lattice keeps a tet iff any corner has value <= 0 (tessellate3d/src/lib.rs:105-111)
+__device__ __forceinline__ bool tet_kept(const Lattice& L, const Cell& c, int t) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        uint32_t X, Y, Z;
+        corner_xyz(c, C_TETS[t][n], X, Y, Z);
+        if (raw_phi(L, X, Y, Z) <= 0.0) return true;
+    }
+    return false;
+}
+
+// Order-isomorphic stand-in for the reference's sequential vertex id: position of the vertex's
+// first appearance in cut_lattice's loop (cells x-major, then tet, then node, kept tets only).
+static __device__ uint64_t first_touch_key(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    for (int ax = -1; ax <= 0; ++ax) {
+        const int64_t cx = (int64_t)X + ax;
+        if (cx < 0 || cx >= (int64_t)L.nx) continue;
+        for (int ay = -1; ay <= 0; ++ay) {
+            const int64_t cy = (int64_t)Y + ay;
+            if (cy < 0 || cy >= (int64_t)L.ny) continue;
+            for (int az = -1; az <= 0; ++az) {
+                const int64_t cz = (int64_t)Z + az;
+                if (cz < 0 || cz >= (int64_t)L.nz) continue;
+                const Cell c = make_cell((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+                const int k = corner_of(c, X, Y, Z);
+                for (int t = 0; t < 5; ++t) {
+                    int pos = -1;
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+                        if (C_TETS[t][n] == k) pos = n;
+                    if (pos < 0) continue;
+                    if (!tet_kept(L, c, t)) continue;
+                    const uint64_t cell_linear = ((uint64_t)cx * L.ny + (uint64_t)cy) * L.nz + (uint64_t)cz;
+                    return (cell_linear * 5u + (uint64_t)t) * 4u + (uint64_t)pos;
+                }
+            }
+        }
+    }
+    return ~0ull;
+}
+
+// warp_vertices for one lattice vertex.  Returns 0 (not warped) or 1 + 2*dir + orient where
+// dir indexes C_DIR (the neighbour the winning edge leads to) and orient says whether the
+// vertex was node 0 (orient 0, `alpha < 0.3` branch) or node 1 (orient 1, `alpha > 0.7`
+// branch) of the winning edge visit.  Strict `<` keeps the FIRST minimal candidate in the
+// reference's visit order: tets in cut_lattice order, edges in Tet4::edge order.
+static __device__ uint32_t warp_eval(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    const double pv = raw_phi(L, X, Y, Z);
+    // fast reject: an edge visit produces a candidate only if the two ends do not have the
+    // same strict sign
+    {
+        const bool even = ((X + Y + Z) & 1u) == 0u;
+        const int nd = even ? 18 : 6;
+        bool any = false;
+        for (int d = 0; d < 18; ++d) {
+            if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
+            const int64_t wx = (int64_t)X + C_DIR[d][0], wy = (int64_t)Y + C_DIR[d][1], wz = (int64_t)Z + C_DIR[d][2];
+            if (wx < 0 || wy < 0 || wz < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
+            const double pw = raw_phi(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz);
+            if (!((pv > 0.0 && pw > 0.0) || (pv < 0.0 && pw < 0.0))) { any = true; break; }
+        }
+        (void)nd;
+        if (!any) return 0u;
+    }
+    const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
+    bool has = false;
+    double best = 0.0;
+    uint32_t code = 0u;
+    for (int ax = -1; ax <= 0; ++ax) {
+        const int64_t cx = (int64_t)X + ax;
+        if (cx < 0 || cx >= (int64_t)L.nx) continue;
+        for (int ay = -1; ay <= 0; ++ay) {
+            const int64_t cy = (int64_t)Y + ay;
+            if (cy < 0 || cy >= (int64_t)L.ny) continue;
+            for (int az = -1; az <= 0; ++az) {
+                const int64_t cz = (int64_t)Z + az;
+                if (cz < 0 || cz >= (int64_t)L.nz) continue;
+                const Cell c = make_cell((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+                const int k = corner_of(c, X, Y, Z);
+                for (int t = 0; t < 5; ++t) {
+                    int me = -1;  // my node index in the flipped tet
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+                        if (tet_corner(c, t, n) == k) me = n;
+                    if (me < 0) continue;
+                    if (!tet_kept(L, c, t)) continue;
+                    for (int e = 0; e < 6; ++e) {
+                        const int i0 = C_EDGE[e][0], i1 = C_EDGE[e][1];
+                        if (i0 != me && i1 != me) continue;
+                        const int other = (i0 == me) ? i1 : i0;
+                        uint32_t WX, WY, WZ;
+                        corner_xyz(c, tet_corner(c, t, other), WX, WY, WZ);
+                        const double pw = raw_phi(L, WX, WY, WZ);
+                        const double phi0 = (i0 == me) ? pv : pw;
+                        const double phi1 = (i0 == me) ? pw : pv;
+                        if ((phi0 > 0.0 && phi1 > 0.0) || (phi0 < 0.0 && phi1 < 0.0)) continue;
+                        const double alpha = phi0 / (phi0 - phi1);
+                        // nalgebra::distance(x0, x1) = norm(x1 - x0); the squares make the sign moot
+                        const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
+                        double d;
+                        uint32_t orient;
+                        if (alpha < 0.3) {
+                            if (i0 != me) continue;  // candidate belongs to node 0
+                            d = alpha * sqrt((dx * dx + dy * dy) + dz * dz);
+                            orient = 0u;
+                        } else if (alpha > 1.0 - 0.3) {
+                            if (i1 != me) continue;  // candidate belongs to node 1
+                            d = (1.0 - alpha) * sqrt((dx * dx + dy * dy) + dz * dz);
+                            orient = 1u;
+                        } else {
+                            continue;
+                        }
+                        if (!has || d < best) {
+                            has = true;
+                            best = d;
+                            const int di = dir_index((int)WX - (int)X, (int)WY - (int)Y, (int)WZ - (int)Z);
+                            code = 1u + 2u * (uint32_t)di + orient;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return has ? code : 0u;
+}
+
+// position after warp_vertices (tessellate3d/src/lib.rs:163,170,177): x += delta
+static __device__ void warped_pos(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z, double out[3]) {
+    const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
+    const uint32_t code = L.wcode[pidx(L, X, Y, Z)] & 0x7fu;
+    if (code == 0u) { out[0] = xv; out[1] = yv; out[2] = zv; return; }
+    const uint32_t di = (code - 1u) >> 1, orient = (code - 1u) & 1u;
+    const uint32_t WX = X + C_DIR[di][0], WY = Y + C_DIR[di][1], WZ = Z + C_DIR[di][2];
+    const double pv = raw_phi(L, X, Y, Z), pw = raw_phi(L, WX, WY, WZ);
+    const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
+    double f;
+    if (orient == 0u) {
+        f = pv / (pv - pw);             // delta = (x1 - x0) * alpha, me = node 0
+    } else {
+        f = 1.0 - pw / (pw - pv);       // delta = (x0 - x1) * (1 - alpha), me = node 1
+    }
+    out[0] = xv + dx * f; out[1] = yv + dy * f; out[2] = zv + dz * f;
+}
+
+// ---------------------------------------------------------------------------------------
+// trim_spikes + remove_exterior_tets for one lattice tet.
+// Output tets reference either an original node of the tet (code 0..3, index into the flipped
+// node order) or the cut vertex on the edge between a positive node i and a negative node j
+// (code 4 + 4*i + j).
+struct TetOut {
+    int n;               // number of output tets (0..3)
+    int kase;            // -2 not kept, -1 passed through, 0..6 trim case
+    bool ext_removed;    // all-zero tet dropped by the centroid test
+    uint8_t node[3][4];
+};
+
+// symbolic a,b,c,d = 0..3; cut(x,y) = 4 + 4x + y
+#define MC_CUT(x, y) (4 + 4 * (x) + (y))
+static __constant__ uint8_t C_CASE_N[7] = {0, 1, 3, 3, 1, 2, 1};
+static __constant__ uint8_t C_CASE_TET[7][3][5] = {
+    // {n0, n1, n2, n3, toggles_flip}
+    {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},
+    {{MC_CUT(0, 3), MC_CUT(1, 3), MC_CUT(2, 3), 3, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},
+    {{MC_CUT(0, 1), 1, 2, 3, 0}, {2, MC_CUT(0, 1), MC_CUT(0, 2), 3, 1}, {MC_CUT(0, 1), 3, MC_CUT(0, 2), MC_CUT(0, 3), 0}},
+    {{MC_CUT(0, 2), MC_CUT(1, 3), 2, 3, 0}, {MC_CUT(0, 2), MC_CUT(1, 3), MC_CUT(1, 2), 3, 0}, {MC_CUT(0, 2), MC_CUT(0, 3), MC_CUT(1, 3), 3, 0}},
+    {{MC_CUT(0, 3), 1, 2, 3, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},
+    {{1, MC_CUT(0, 2), 2, 3, 1}, {MC_CUT(0, 3), 1, MC_CUT(0, 2), 3, 0}, {0, 0, 0, 0, 0}},
+    {{MC_CUT(0, 3), MC_CUT(1, 3), 2, 3, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}},
+};
+
+struct TetNodes {
+    uint32_t X[4], Y[4], Z[4];  // lattice coordinates of the flipped node order
+    double p[4];                // post-warp phi
+};
+
+__device__ __forceinline__ void load_tet(const Lattice& L, const Cell& c, int t, TetNodes& tn) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        corner_xyz(c, tet_corner(c, t, n), tn.X[n], tn.Y[n], tn.Z[n]);
+        tn.p[n] = warped_phi(L, pidx(L, tn.X[n], tn.Y[n], tn.Z[n]));
+    }
+}
+
+// `removed_hint`: < 0 -> evaluate the exterior test with the SDF program; 0/1 -> cached result
+static __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNodes& tn,
+                             const uint64_t* __restrict__ prog, int removed_hint, TetOut& out) {
+    out.n = 0;
+    out.kase = -2;
+    out.ext_removed = false;
+    if (!tet_kept(L, c, t)) return;
+    const double* p = tn.p;
+    if (p[0] <= 0.0 && p[1] <= 0.0 && p[2] <= 0.0 && p[3] <= 0.0) {
+        out.kase = -1;
+        if (p[0] == 0.0 && p[1] == 0.0 && p[2] == 0.0 && p[3] == 0.0) {
+            bool removed;
+            if (removed_hint >= 0) {
+                removed = removed_hint != 0;
+            } else {
+                // centroid = (((a + b) + c) + d) / 4 of the warped positions
+                double a[3], b[3], cc[3], d[3];
+                warped_pos(L, tn.X[0], tn.Y[0], tn.Z[0], a);
+                warped_pos(L, tn.X[1], tn.Y[1], tn.Z[1], b);
+                warped_pos(L, tn.X[2], tn.Y[2], tn.Z[2], cc);
+                warped_pos(L, tn.X[3], tn.Y[3], tn.Z[3], d);
+                const double qx = (((a[0] + b[0]) + cc[0]) + d[0]) / 4.0;
+                const double qy = (((a[1] + b[1]) + cc[1]) + d[1]) / 4.0;
+                const double qz = (((a[2] + b[2]) + cc[2]) + d[2]) / 4.0;
+                removed = vm_eval<false>(prog, qx, qy, qz) > 0.0;
+            }
+            if (removed) { out.ext_removed = true; return; }
+        }
+        out.n = 1;
+        out.node[0][0] = 0; out.node[0][1] = 1; out.node[0][2] = 2; out.node[0][3] = 3;
+        return;
+    }
+    // 5-comparator network, descending by (phi, first-touch order); tessellate3d/src/lib.rs:262-282
+    int ia = 0, ib = 1, ic = 2, id = 3;
+    bool flipped = false;
+#define MC_LESS(i, j)                                                                               \
+    (p[i] < p[j] || (p[i] == p[j] && first_touch_key(L, tn.X[i], tn.Y[i], tn.Z[i]) <              \
+                                         first_touch_key(L, tn.X[j], tn.Y[j], tn.Z[j])))
+#define MC_CSWAP(u, v) if (MC_LESS(u, v)) { const int tmp_ = u; u = v; v = tmp_; flipped = !flipped; }
+    MC_CSWAP(ia, ib)
+    MC_CSWAP(ic, id)
+    MC_CSWAP(ia, ic)
+    MC_CSWAP(ib, id)
+    MC_CSWAP(ib, ic)
+#undef MC_CSWAP
+#undef MC_LESS
+    int kase;
+    if (p[id] == 0.0) kase = 0;
+    else if (p[ic] > 0.0) kase = 1;
+    else if (p[ib] < 0.0) kase = 2;
+    else if (p[ib] > 0.0 && p[ic] < 0.0) kase = 3;
+    else if (p[ib] == 0.0 && p[ic] == 0.0) kase = 4;
+    else if (p[ib] == 0.0) kase = 5;
+    else kase = 6;
+    out.kase = kase;
+    out.n = C_CASE_N[kase];
+    const int idx[4] = {ia, ib, ic, id};
+    for (int q = 0; q < out.n; ++q) {
+        uint8_t nd[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int s = C_CASE_TET[kase][q][m];
+            nd[m] = (s < 4) ? (uint8_t)idx[s] : (uint8_t)(4 + 4 * idx[(s - 4) >> 2] + idx[(s - 4) & 3]);
+        }
+        const bool f = flipped != (C_CASE_TET[kase][q][4] != 0);
+        if (f) { const uint8_t tmp = nd[0]; nd[0] = nd[1]; nd[1] = tmp; }
+        out.node[q][0] = nd[0]; out.node[q][1] = nd[1]; out.node[q][2] = nd[2]; out.node[q][3] = nd[3];
+    }
+}
+
+}  // namespace mc

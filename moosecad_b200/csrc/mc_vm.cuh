@@ -1,0 +1,193 @@
+// Device evaluator of the flat SDF program (mc_program.h): one lattice point per lane,
+// the program counter is warp-uniform when UNIFORM is set (all 32 lanes must be converged):
+// a bbox guard is skipped only when NO lane passes it, otherwise every lane evaluates the
+// subtree and the guard's select is applied per lane — value-identical to the reference's
+// `if approx <= slack { exact } else { approx }` because the tree is side-effect free.
+//
+// Arithmetic follows implicit3d 0.14.2 / bbox 0.11.2 / nalgebra 0.22.1 operation order
+// (DESIGN.md §SDF); compiled with --fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mc_math.cuh"
+#include "mc_program.h"
+
+namespace mc {
+
+__device__ __forceinline__ double ld_f64(const uint64_t* __restrict__ w, int i) {
+    return __longlong_as_double((long long)w[i]);
+}
+
+// BoundingBox::distance: max(xval, max(yval, zval)), *val = max(p - hi, lo - p)
+__device__ __forceinline__ double box_distance(const uint64_t* __restrict__ w, int at, double x, double y,
+                                               double z) {
+    const double xv = fmax(x - ld_f64(w, at + 3), ld_f64(w, at + 0) - x);
+    const double yv = fmax(y - ld_f64(w, at + 4), ld_f64(w, at + 1) - y);
+    const double zv = fmax(z - ld_f64(w, at + 5), ld_f64(w, at + 2) - z);
+    return fmax(xv, fmax(yv, zv));
+}
+
+// rvmin / rvmax over k stacked child values v[0..k) (v[k-1] is `top`)
+template <bool IS_UNION>
+__device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int base, int k, double top,
+                                              double r, double exact_range) {
+    // pass 1: running extremum + "two children are within exact_range" flag
+    bool close = false;
+    double m = IS_UNION ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL);
+    for (int i = 0; i < k; ++i) {
+        const double x = (i == k - 1) ? top : vs[base + i];
+        if (IS_UNION) {
+            if (x < m) { close = (m - x) < exact_range; m = x; }
+            else if ((x - m) < exact_range) close = true;
+        } else {
+            if (x > m) { close = (x - m) < exact_range; m = x; }
+            else if ((m - x) < exact_range) close = true;
+        }
+    }
+    if (!close) return m;
+    const double lim = IS_UNION ? (m + r) : (m - r);
+    const double r4 = r / 4.0;
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) {
+        const double x = (i == k - 1) ? top : vs[base + i];
+        if (IS_UNION) { if (x < lim) s = s + mc_exp(-x / r4); }
+        else          { if (x > lim) s = s + mc_exp(x / r4); }
+    }
+    return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
+}
+
+// Evaluate the program at (x, y, z).  `w` may point to shared or global memory.
+template <bool UNIFORM>
+__device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, double z) {
+    double vs[MC_MAX_VALUE_DEPTH + 1];   // element i lives in vs[i + 1]; the newest is `top`
+    double ps[3 * MC_MAX_POINT_DEPTH];
+    int sp = 0, psp = 0, pc = 0;
+    double top = 0.0;
+    unsigned long long allpass = 0ull;  // bit L: every lane passed the guard at nesting level L
+    const unsigned FULL = 0xffffffffu;
+#define MC_PUSH(v) do { vs[sp] = top; ++sp; top = (v); } while (0)
+    for (;;) {
+        const uint64_t h = w[pc];
+        switch (MC_HDR_OP(h)) {
+        case MC_OP_END:
+            return top;
+        case MC_OP_PLANE: {
+            const unsigned sm = MC_HDR_SMALL(h);
+            const unsigned axis = sm & 3u;
+            const double q = axis == 0 ? x : (axis == 1 ? y : z);
+            const double d = ld_f64(w, pc + 1);
+            const double ap = fabs(q);
+            const bool sign_positive = __double_as_longlong(q) >= 0;
+            const bool inverted = (sm & 4u) != 0;
+            MC_PUSH((sign_positive != inverted) ? (ap - d) : (-ap - d));
+            pc += 2;
+            break;
+        }
+        case MC_OP_NPLANE: {
+            const double v = ((x * ld_f64(w, pc + 1) + y * ld_f64(w, pc + 2)) + z * ld_f64(w, pc + 3)) -
+                             ld_f64(w, pc + 4);
+            MC_PUSH(v);
+            pc += 5;
+            break;
+        }
+        case MC_OP_USQ: {
+            MC_PUSH(((x * x + y * y) + z * z) - 1.0);
+            pc += 1;
+            break;
+        }
+        case MC_OP_CONE: {
+            const double radius = fabs(ld_f64(w, pc + 1) * (z + ld_f64(w, pc + 2)));
+            MC_PUSH((sqrt(x * x + y * y) - radius) * ld_f64(w, pc + 3));
+            pc += 4;
+            break;
+        }
+        case MC_OP_GSPHERE:
+        case MC_OP_GCYL: {
+            const double a = box_distance(w, pc + 1, x, y, z);
+            const bool pass = a <= ld_f64(w, pc + 7);
+            double v = a;
+            if (UNIFORM ? __any_sync(FULL, pass) : pass) {
+                const double r = ld_f64(w, pc + 8);
+                const double e = (MC_HDR_OP(h) == MC_OP_GSPHERE) ? (sqrt((x * x + y * y) + z * z) - r)
+                                                                 : (sqrt(x * x + y * y) - r);
+                if (pass) v = e;
+            }
+            MC_PUSH(v);
+            pc += 9;
+            break;
+        }
+        case MC_OP_GUARD: {
+            const double a = box_distance(w, pc + 1, x, y, z);
+            const bool pass = a <= ld_f64(w, pc + 7);
+            const unsigned level = MC_HDR_LEVEL(h);
+            if (UNIFORM) {
+                const unsigned b = __ballot_sync(FULL, pass);
+                if (b == 0u) { MC_PUSH(a); pc = (int)MC_HDR_IDX(h); break; }
+                if (level < 64u) {
+                    if (b == FULL) allpass |= (1ull << level);
+                    else allpass &= ~(1ull << level);
+                }
+            } else {
+                if (!pass) { MC_PUSH(a); pc = (int)MC_HDR_IDX(h); break; }
+            }
+            pc += 8;
+            break;
+        }
+        case MC_OP_ENDG: {
+            // lanes that failed the guard take bbox.distance instead of the subtree value
+            if (UNIFORM) {
+                const unsigned level = MC_HDR_LEVEL(h);
+                if (level >= 64u || !((allpass >> level) & 1ull)) {
+                    const int g = (int)MC_HDR_IDX(h);
+                    const double a = box_distance(w, g + 1, x, y, z);
+                    if (!(a <= ld_f64(w, g + 7))) top = a;
+                }
+            }
+            // non-uniform mode: only lanes that passed reach ENDG, nothing to select
+            pc += 1;
+            break;
+        }
+        case MC_OP_NEG:
+            top = -top;
+            pc += 1;
+            break;
+        case MC_OP_BOOL: {
+            const unsigned sm = MC_HDR_SMALL(h);
+            const int k = (int)(sm & 0x7fu);
+            const double r = ld_f64(w, pc + 1);
+            const double er = ld_f64(w, pc + 2);
+            const int base = sp - k + 1;  // v[i] (i < k-1) is vs[base + i]
+            const double res = (sm & 0x80u) ? smooth_fold<true>(vs, base, k, top, r, er)
+                                            : smooth_fold<false>(vs, base, k, top, r, er);
+            sp -= k - 1;
+            top = res;
+            pc += 3;
+            break;
+        }
+        case MC_OP_APUSH: {
+            ps[psp] = x; ps[psp + 1] = y; ps[psp + 2] = z;
+            psp += 3;
+            // nalgebra transform_point: ((m0*x + m1*y) + m2*z) + t   (n == 1 for affine matrices)
+            const double nx = ((ld_f64(w, pc + 1) * x + ld_f64(w, pc + 2) * y) + ld_f64(w, pc + 3) * z) + ld_f64(w, pc + 4);
+            const double ny = ((ld_f64(w, pc + 5) * x + ld_f64(w, pc + 6) * y) + ld_f64(w, pc + 7) * z) + ld_f64(w, pc + 8);
+            const double nz = ((ld_f64(w, pc + 9) * x + ld_f64(w, pc + 10) * y) + ld_f64(w, pc + 11) * z) + ld_f64(w, pc + 12);
+            x = nx; y = ny; z = nz;
+            pc += 13;
+            break;
+        }
+        case MC_OP_APOP: {
+            psp -= 3;
+            x = ps[psp]; y = ps[psp + 1]; z = ps[psp + 2];
+            top = top * ld_f64(w, pc + 1);
+            pc += 2;
+            break;
+        }
+        default:
+            return __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+#undef MC_PUSH
+}
+
+}  // namespace mc

@@ -1,0 +1,260 @@
+"""Host-side mirror of ``tessellate3d`` + the parts of ``mesh`` on the accelerated path.
+
+    IsosurfaceStuffing(function, resolution, relative_error).tessellate() -> Mesh
+        tessellate3d/src/lib.rs:36-52,420-431 (called from src/main.rs:74-82)
+    Mesh.vertices() / elems() / boundary() / add_side_set()
+        mesh/src/lib.rs:58-65,138-140,183-185,341-357,198-202
+    ObjectAdaptor(implicit, tessellation_resolution).value(points)
+        src/main.rs:23-40
+
+Everything runs on the GPU through the C ABI (``_lib``); there is no host fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .luascad import LObject, Tape
+
+
+class Context:
+    """One ``mc_ctx``: a device, a stream and the reusable device workspace."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.lib()
+        self.handle = self._lib.mc_ctx_new(int(device), C.c_void_p(stream) if stream else None)
+        if not self.handle:
+            raise _lib.McError(_lib.MC_ERR_CUDA, _lib.last_error())
+        self.device = int(device)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self._lib.mc_ctx_free(h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.mc_ctx_launch_count(self.handle))
+
+    @property
+    def workspace_bytes(self):
+        return int(self._lib.mc_ctx_workspace_bytes(self.handle))
+
+    def trim(self):
+        _lib.check(self._lib.mc_ctx_trim(self.handle))
+
+    def probe_fp64_nofma(self):
+        out = C.c_double()
+        _lib.check(self._lib.mc_probe_fp64_nofma(self.handle, C.byref(out)))
+        return out.value
+
+    def tet_quality(self, coords, tets):
+        """Mesh::volume / Mesh::aspect_ratio (mesh/src/lib.rs:292-316) for explicit arrays."""
+        coords = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, 3)
+        tets = np.ascontiguousarray(tets, dtype=np.uint64).reshape(-1, 4)
+        vol = np.empty(len(tets), dtype=np.float64)
+        ar = np.empty(len(tets), dtype=np.float64)
+        _lib.check(self._lib.mc_tet_quality(
+            self.handle, coords.ctypes.data_as(_lib._PD), len(coords), tets.ctypes.data_as(_lib._PU64), len(tets),
+            vol.ctypes.data_as(_lib._PD), ar.ctypes.data_as(_lib._PD)))
+        return vol, ar
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class ObjectAdaptor:
+    """``ObjectAdaptor`` of src/main.rs:23-40: an implicit object + the slack passed to approx_value."""
+
+    def __init__(self, implicit, tessellation_resolution, ctx=None):
+        if not isinstance(implicit, LObject) or not isinstance(implicit.backend, Tape):
+            raise TypeError("ObjectAdaptor needs an LObject recorded on a Tape")
+        self.implicit = implicit
+        self.tessellation_resolution = float(tessellation_resolution)
+        self.ctx = ctx
+
+    def bbox(self):
+        return self.implicit.bbox()
+
+    def value(self, points, slack=None):
+        """approx_value(p, slack) for an (n, 3) array of points; evaluated on the device."""
+        ctx = self.ctx or default_context()
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pts), dtype=np.float64)
+        lib = _lib.lib()
+        _lib.check(lib.mc_eval_points(ctx.handle, self.implicit.backend.handle, self.implicit.node,
+                                      self.tessellation_resolution if slack is None else float(slack),
+                                      pts.ctypes.data_as(_lib._PD), len(pts), out.ctypes.data_as(_lib._PD)))
+        return out
+
+
+class SideSet:
+    """``mesh::SideSet`` (mesh/src/lib.rs:68-102): a named set of (elem, side) pairs."""
+
+    def __init__(self, sides=(), name=None):
+        self._name = name
+        self._sides = {(int(e), int(s)) for e, s in sides}
+
+    def name(self):
+        return self._name
+
+    def set_name(self, name):
+        self._name = str(name)
+
+    def add_side(self, elem, side):
+        new = (int(elem), int(side)) not in self._sides
+        self._sides.add((int(elem), int(side)))
+        return new
+
+    def sides(self):
+        return self._sides
+
+
+class Mesh:
+    """Result of a tessellation: ``Mesh<Tet4, f64>`` (mesh/src/lib.rs:58-65), device backed."""
+
+    def __init__(self, ctx, handle, tape):
+        self._lib = _lib.lib()
+        self.ctx = ctx
+        self.handle = handle
+        self._tape = tape  # keeps the scene alive
+        self._name = None
+        self._side_sets = []
+        self._coords = None
+        self._tets = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self._lib.mc_mesh_free(h)
+
+    def name(self):
+        return self._name
+
+    def set_name(self, name):
+        self._name = str(name)
+
+    def vertices(self):
+        """(n, 3) float64 — ``Mesh::vertices`` (mesh/src/lib.rs:138-140)."""
+        if self._coords is None:
+            n = int(self._lib.mc_mesh_num_vertices(self.handle))
+            p = self._lib.mc_mesh_coords(self.handle)
+            if n and not p:
+                raise _lib.McError(_lib.MC_ERR_CUDA, _lib.last_error())
+            self._coords = np.ctypeslib.as_array(p, shape=(n, 3)).copy() if n else np.zeros((0, 3))
+        return self._coords
+
+    def elems(self):
+        """(n, 4) uint64 node ids — ``Mesh::elems`` (mesh/src/lib.rs:183-185)."""
+        if self._tets is None:
+            n = int(self._lib.mc_mesh_num_tets(self.handle))
+            p = self._lib.mc_mesh_tets(self.handle)
+            if n and not p:
+                raise _lib.McError(_lib.MC_ERR_CUDA, _lib.last_error())
+            self._tets = np.ctypeslib.as_array(p, shape=(n, 4)).copy() if n else np.zeros((0, 4), dtype=np.uint64)
+        return self._tets
+
+    def num_vertices(self):
+        return int(self._lib.mc_mesh_num_vertices(self.handle))
+
+    def num_elems(self):
+        return int(self._lib.mc_mesh_num_tets(self.handle))
+
+    def boundary(self):
+        """``Mesh::boundary`` (mesh/src/lib.rs:341-357): the sides that belong to one tet only."""
+        n = C.c_uint64()
+        _lib.check(self._lib.mc_mesh_boundary(self.handle, C.byref(n)))
+        if n.value == 0:
+            return SideSet()
+        p = self._lib.mc_mesh_boundary_sides(self.handle)
+        arr = np.ctypeslib.as_array(p, shape=(n.value, 2))
+        return SideSet(map(tuple, arr.tolist()))
+
+    def add_boundary_side_set(self, name, boundary_obj):
+        """One iteration of the side-set loop of src/main.rs:87-106 for a ``:boundary()`` object."""
+        idx = _lib.check(self._lib.mc_mesh_add_sideset(self.handle, boundary_obj.backend.handle, boundary_obj.node))
+        n = int(self._lib.mc_mesh_sideset_len(self.handle, idx))
+        sides = []
+        if n:
+            arr = np.ctypeslib.as_array(self._lib.mc_mesh_sideset(self.handle, idx), shape=(n, 2))
+            sides = list(map(tuple, arr.tolist()))
+        ss = SideSet(sides, name)
+        self._side_sets.append(ss)
+        return ss
+
+    def add_side_set(self, side_set):
+        self._side_sets.append(side_set)
+        return len(self._side_sets) - 1
+
+    def side_sets(self):
+        return self._side_sets
+
+    def stats(self):
+        """The numbers the reference prints (tessellate3d/src/lib.rs:247,355,366,408-417,421,424)."""
+        dim = (C.c_uint64 * 3)()
+        stage = (C.c_uint64 * 3)()
+        st = (C.c_uint64 * 7)()
+        ar = (C.c_double * 2)()
+        inv = C.c_uint64()
+        _lib.check(self._lib.mc_mesh_stats(self.handle, dim, stage, st, ar, C.byref(inv)))
+        counts = (C.c_uint64 * 6)()
+        _lib.check(self._lib.mc_mesh_counts(self.handle, counts))
+        ms = (C.c_double * 9)()
+        _lib.check(self._lib.mc_mesh_stage_ms(self.handle, ms))
+        return {"dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar),
+                "inverted": inv.value, "n_vertices": counts[0], "n_tets": counts[1],
+                "points_evaluated": counts[2], "points_owned": counts[3], "n_cut": counts[4],
+                "n_warped": counts[5], "stage_ms": list(ms)}
+
+    def phi(self):
+        """The lattice SDF field, shape (nz+1, ny+1, nx+1)."""
+        d = self.stats()["dim"]
+        shape = (d[2] + 1, d[1] + 1, d[0] + 1)
+        out = np.empty(shape, dtype=np.float64)
+        _lib.check(self._lib.mc_mesh_copy_phi(self.handle, out.ctypes.data_as(_lib._PD), out.size))
+        return out
+
+
+class IsosurfaceStuffing:
+    """``tessellate3d::IsosurfaceStuffing`` (tessellate3d/src/lib.rs:24-52,420-431)."""
+
+    def __init__(self, function, resolution, relative_error, ctx=None, flags=0, max_bisect_iters=0):
+        if isinstance(function, LObject):
+            function = ObjectAdaptor(function, resolution, ctx)
+        if not isinstance(function, ObjectAdaptor):
+            raise TypeError("function must be an ObjectAdaptor or an LObject")
+        if function.tessellation_resolution != float(resolution):
+            # src/main.rs:74-81 always passes the same number for both
+            raise ValueError("the accelerated path evaluates approx_value with slack == resolution")
+        self.function = function
+        self.resolution = float(resolution)
+        self.relative_error = float(relative_error)
+        self.ctx = ctx or function.ctx or default_context()
+        self.flags = int(flags)
+        self.max_bisect_iters = int(max_bisect_iters)
+
+    def tessellate(self):
+        lib = _lib.lib()
+        opts = _lib.mc_options(C.sizeof(_lib.mc_options), self.flags, self.max_bisect_iters, 0)
+        out = C.c_void_p()
+        obj = self.function.implicit
+        rc = lib.mc_tessellate(self.ctx.handle, obj.backend.handle, obj.node, self.resolution, self.relative_error,
+                               C.byref(opts), C.byref(out))
+        if rc != _lib.MC_OK:
+            err = _lib.McError(rc, _lib.last_error())
+            if out.value:
+                lib.mc_mesh_free(out)
+            raise err
+        return Mesh(self.ctx, out, obj.backend)
+
+
+class Tile:
+    """``tessellate3d::Tile`` (tessellate3d/src/lib.rs:434-454)."""
+    LATTICE = [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]]
+    TETS = [[0, 1, 5, 2], [0, 2, 5, 7], [0, 7, 5, 4], [2, 6, 5, 7], [0, 2, 7, 3]]

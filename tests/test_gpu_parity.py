@@ -1,0 +1,230 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+Bit-exact for SDF values (oracle libm_mode 1 = the portable exp/ln the device implements),
+vertex coordinates, tet connectivity and side-sets after canonical sorting."""
+import math
+
+import numpy as np
+import pytest
+
+import moosecad_b200 as mc
+from moosecad_b200 import _lib, luascad, main, scenes
+
+import canon
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_run(oracle, script, res, err=0.2, fade=0.1, rmul=1.0):
+    out = luascad.eval(script, backend=oracle.OracleScene())
+    for o in out.values():
+        o.obj.backend.set_parameters_node(o.obj.node, fade, rmul)
+    vols = [(n, o.volume()) for n, o in sorted(out.items()) if o.volume() is not None]
+    bnds = [(n, o.boundary()) for n, o in sorted(out.items()) if o.boundary() is not None]
+    v = vols[0][1]
+    om = v.backend.tessellate(v.node, res, err)
+    assert om.ok()
+    sets = {n: om.add_sideset(b.backend, b.node) for n, b in bnds}
+    return om, sets, v
+
+
+def _compare(oracle, ctx, script, res, err=0.2, bitwise=True):
+    mesh = main.run(script, tessellation_resolution=res, tessellation_error=err, ctx=ctx)
+    om, osets, _ = _oracle_run(oracle, script, res, err)
+    gsets = {ss.name(): sorted(ss.sides()) for ss in mesh.side_sets()}
+    a = canon.canonical(mesh.vertices(), mesh.elems(), gsets)
+    b = canon.canonical(om.vertices(), om.elems(), osets)
+    canon.assert_same_mesh(a, b, bitwise=bitwise)
+    st, ost = mesh.stats(), om.stats()
+    assert st["dim"] == ost["dim"]
+    assert st["ntets_stage"] == ost["ntets_stage"]
+    assert st["stats"] == ost["stats"]
+    assert st["n_warped"] == ost["n_warped"]
+    assert st["n_cut"] == ost["n_cut"]
+    assert st["inverted"] == ost["inverted"]
+    assert ost["n_exterior_skipped_by_swap"] == 0  # precondition of the set-semantics restatement
+    np.testing.assert_allclose(st["aspect_ratio"], ost["aspect_ratio"], rtol=1e-12)
+    # Mesh::boundary as a set of node triples
+    gb = canon.canonical(mesh.vertices(), mesh.elems(), {"surface": sorted(mesh.boundary().sides())})[2]["surface"]
+    ob = canon.canonical(om.vertices(), om.elems(), {"surface": om.boundary()})[2]["surface"]
+    assert np.array_equal(gb, ob)
+    return mesh, om
+
+
+def test_luascad_primitives_asserts(ctx):
+    # luascad/src/lib.rs:375-377, evaluated on the device
+    res = luascad.eval(scenes.CUBE_LUA)
+    top = res["top"].boundary()
+    v = mc.ObjectAdaptor(top, 0.0, ctx).value([[0.0, 0.0, 0.5], [0.0, 0.0, 1.0]])
+    assert v[0] == 0.0 and v[1] == 0.5
+
+
+SCRIPTS = {
+    "cube": scenes.CUBE_LUA,
+    "sphere": scenes.SPHERE_LUA,
+    "xplicit": scenes.XPLICIT_LUA,
+    "cyl_cone": "return { c = geom.cylinder(2.0, 0.5, 0.25, 0.1):rotate(0.3, 0.2, 0.1):translate(1, 2, 3):scale(2, 3, 4):volume() }",
+    "cyl": "return { c = geom.cylinder(1.0, 0.5, 0.5, 0.05):translate(0.1, 0.2, 0.3):volume() }",
+    "mixed": "a = geom.sphere(0.3):translate(0.2, 0, 0)\nb = geom.cube(0.5, 0.4, 0.3, 0.05):rotate(1, 2, 3)\n"
+             "c = geom.plane_hesian(1, 2, 3, 0.1)\nd = geom.plane_3_points(0,0,0.2, 1,0,0.25, 0,1,0.3)\n"
+             "return { u = a:union(b, 0.1):intersection(c, 0.05):difference(d, 0.0):volume() }",
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCRIPTS))
+def test_sdf_values_bit_exact(name, oracle, ctx):
+    a = luascad.eval(SCRIPTS[name])
+    b = luascad.eval(SCRIPTS[name], backend=oracle.OracleScene())
+    rng = np.random.default_rng(1)
+    for k in a:
+        bb = np.array(a[k].obj.bbox())
+        lo = np.where(np.isfinite(bb[:3]), bb[:3], -2.0) - 0.3
+        hi = np.where(np.isfinite(bb[3:]), bb[3:], 2.0) + 0.3
+        pts = rng.uniform(lo, hi, size=(20000, 3))
+        pts[:100] = 0.0
+        pts[100:200, 0] = bb[0] if np.isfinite(bb[0]) else 0.0
+        for slack in (0.0, 0.05, 1.0):
+            got = mc.ObjectAdaptor(a[k].obj, slack, ctx).value(pts)
+            want = b[k].obj.backend.eval_points(b[k].obj.node, slack, pts)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or np.array_equal(got, want), \
+                (name, k, slack, np.abs(got - want).max())
+
+
+def test_sdf_values_vs_platform_libm(oracle, ctx):
+    # the reference calls the platform libm; the device's portable exp/ln stays within the
+    # north-star tolerance (1e-12 relative) of it
+    a = luascad.eval(scenes.XPLICIT_LUA)["xplicit"].obj
+    b = luascad.eval(scenes.XPLICIT_LUA, backend=oracle.OracleScene())["xplicit"].obj
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-8, 8, size=(50000, 3))
+    got = mc.ObjectAdaptor(a, 0.05, ctx).value(pts)
+    oracle.set_libm_mode(0)
+    try:
+        want = b.backend.eval_points(b.node, 0.05, pts)
+    finally:
+        oracle.set_libm_mode(1)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)
+
+
+def test_lattice_field_bit_exact(oracle, ctx):
+    res = 15.0 / 24
+    a = luascad.eval(scenes.XPLICIT_LUA)["xplicit"].obj
+    mesh = mc.IsosurfaceStuffing(a, res, 0.2, ctx=ctx).tessellate()
+    b = luascad.eval(scenes.XPLICIT_LUA, backend=oracle.OracleScene())["xplicit"].obj
+    want = b.backend.eval_lattice(b.node, res, res, mesh.stats()["dim"])
+    got = mesh.phi()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_config1_cube_lua(oracle, ctx):
+    mesh, om = _compare(oracle, ctx, scenes.CUBE_LUA, 1.0)
+    assert mesh.num_vertices() == 8 and mesh.num_elems() == 5
+    assert len(mesh.boundary().sides()) == 12
+    assert {ss.name(): len(ss.sides()) for ss in mesh.side_sets()} == {"top": 2, "bottom": 2}
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 33, 64])
+def test_sphere_lua(n, oracle, ctx):
+    _compare(oracle, ctx, scenes.SPHERE_LUA, 1.0 / n)
+
+
+@pytest.mark.parametrize("res", [0.5, 0.3, 0.11])
+def test_cube_lua_fine(res, oracle, ctx):
+    # exact zeros on the whole surface, side-sets on lattice planes
+    _compare(oracle, ctx, scenes.CUBE_LUA, res)
+
+
+@pytest.mark.parametrize("n", [9, 24, 48])
+def test_xplicit_lua(n, oracle, ctx):
+    _compare(oracle, ctx, scenes.XPLICIT_WITH_TOP_LUA, 15.0 / n)
+
+
+def test_unit_sphere_fixture(oracle, ctx):
+    # tessellate3d/src/lib.rs:486-490 (test_convert_mesh) with the reference's own UnitSphere
+    t = mc.Tape()
+    f = mc.LObject(t, t.unit_sphere_sq())
+    mesh = mc.IsosurfaceStuffing(f, 0.1, 0.2, ctx=ctx).tessellate()
+    sc = oracle.OracleScene()
+    om = sc.tessellate(sc.unit_sphere_sq(), 0.1, 0.2)
+    canon.assert_same_mesh(canon.canonical(mesh.vertices(), mesh.elems()), canon.canonical(om.vertices(), om.elems()))
+    assert mesh.stats()["stats"] == om.stats()["stats"]
+
+
+@pytest.mark.parametrize("name,res", [("cyl_cone", 0.21), ("cyl", 0.043), ("mixed", 0.031)])
+def test_ragged_scenes(name, res, oracle, ctx):
+    # non-cubic lattices, rotated / scaled / translated objects, cone + hessian planes
+    _compare(oracle, ctx, SCRIPTS[name].replace(":volume()", ":volume()"), res)
+
+
+def test_synthetic_csg(oracle, ctx):
+    # BASELINE config 4's scene shape at a lattice the oracle finishes in seconds
+    g = mc.Geom()
+    root = scenes.synthetic_csg(g, 16, seed=64)
+    g.backend.set_parameters(0.1, 1.0)
+    res = 1.0 / 40
+    mesh = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx).tessellate()
+    go = mc.Geom(oracle.OracleScene())
+    ro = scenes.synthetic_csg(go, 16, seed=64)
+    ro.backend.set_parameters_node(ro.node, 0.1, 1.0)
+    om = ro.backend.tessellate(ro.node, res, 0.2)
+    canon.assert_same_mesh(canon.canonical(mesh.vertices(), mesh.elems()), canon.canonical(om.vertices(), om.elems()))
+    assert mesh.stats()["stats"] == om.stats()["stats"]
+
+
+def test_tet_quality_matches_oracle(oracle, ctx):
+    rng = np.random.default_rng(3)
+    coords = rng.normal(size=(400, 3))
+    tets = rng.integers(0, 400, size=(1000, 4)).astype(np.uint64)
+    vol, ar = ctx.tet_quality(coords, tets)
+    om = oracle.OracleMesh.from_arrays(coords, tets)
+    want_v = np.array([om.volume(i) for i in range(len(tets))])
+    want_a = np.array([om.aspect_ratio(i) for i in range(len(tets))])
+    assert np.array_equal(vol, want_v)
+    assert np.array_equal(ar, want_a, equal_nan=True)
+    # mesh/src/lib.rs:817-826: the regular tet has aspect ratio exactly 1
+    _, ar = ctx.tet_quality([(1, 1, 1), (-1, -1, 1), (-1, 1, -1), (1, -1, -1)], [[0, 1, 3, 2]])
+    assert ar[0] == 1.0
+
+
+def test_error_behaviour(ctx):
+    # infinite bounding box: the reference panics in to_usize().unwrap() (tessellate3d/src/lib.rs:44-46)
+    g = mc.Geom()
+    with pytest.raises(_lib.McError) as e:
+        mc.IsosurfaceStuffing(g.plane_x(1.0), 0.1, 0.2, ctx=ctx).tessellate()
+    assert e.value.code == _lib.MC_ERR_BBOX
+    with pytest.raises(_lib.McError) as e:
+        mc.IsosurfaceStuffing(g.sphere(1.0), -1.0, 0.2, ctx=ctx).tessellate()
+    assert e.value.code == _lib.MC_ERR_ARG
+
+
+def test_empty_result(oracle, ctx):
+    # a volume with no lattice point inside: zero tets, zero vertices
+    script = "return { s = geom.sphere(0.01):translate(0.05, 0.05, 0.05):intersection(geom.cube(1, 1, 1, 0), 0):volume() }"
+    mesh, om = _compare(oracle, ctx, script, 0.5)
+    assert mesh.num_elems() == len(om.elems())
+
+
+def test_full_size_properties_sphere_256(ctx):
+    """BASELINE config 2 at full size (256^3), checked through size-independent properties."""
+    mesh = main.run(scenes.SPHERE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
+    st = mesh.stats()
+    assert st["dim"] == [256, 256, 256]
+    assert st["inverted"] == 0
+    v, e = mesh.vertices(), mesh.elems().astype(np.int64)
+    assert e.max() == len(v) - 1 and np.unique(e).size == len(v)       # compact: every vertex used
+    a, b, c, d = v[e[:, 0]], v[e[:, 1]], v[e[:, 2]], v[e[:, 3]]
+    vol = np.einsum("ij,ij->i", a - d, np.cross(b - d, c - d)) / 6.0
+    assert (vol > 0).all()
+    assert abs(vol.sum() - math.pi / 6) / (math.pi / 6) < 2e-4              # 4/3 pi 0.5^3
+    # the surface is closed: every edge of the boundary triangles is shared by exactly two of them
+    sides = np.array(sorted(mesh.boundary().sides()), dtype=np.int64)
+    tri = e[sides[:, 0][:, None], canon.FACE[sides[:, 1]]]
+    edges = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    # every boundary vertex lies within the bisection tolerance of the sphere
+    r = np.linalg.norm(v[np.unique(tri)], axis=1)
+    assert np.abs(r - 0.5).max() <= 0.2 / 256 + 1e-12
+    # idempotence: a second run gives the identical arrays
+    mesh2 = main.run(scenes.SPHERE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
+    assert np.array_equal(mesh2.vertices(), v) and np.array_equal(mesh2.elems().astype(np.int64), e)
