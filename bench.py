@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the meshing hot path (BASELINE.json): evaluating the CSG signed-distance tree
+over the lattice and running isosurface stuffing on it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one full meshing pass (SDF field -> warp -> classify -> vertex numbering ->
+bisection -> tet emission -> quality) of the workload.  N = 1 runs BASELINE config 4: the
+synthetic 64-primitive smooth union/difference scene on a 1024^3-cell lattice.  N > 1 shards
+that same lattice into z-slabs (strong scaling), one process per GPU under torchrun.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_primitives, cells per axis)
+    "csg64_1024": (64, 1024),
+    "csg64_512": (64, 512),
+    "csg64_256": (64, 256),
+    "csg256_2048": (256, 2048),
+    "csg16_64": (16, 64),
+}
+REL_ERR = 0.2  # --tessellation-error default, src/main.rs:48
+
+
+def build_scene(geom_factory, name):
+    from moosecad_b200 import scenes
+    nprim, n = WORKLOADS[name]
+    g = geom_factory()
+    root = scenes.synthetic_csg(g, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
+    return g, root, 1.0 / n, n
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md's clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_sample(name, seconds_hint=15.0):
+    """The oracle (C++ restatement of the reference's serial Rust path) timed on the host, one
+    core, on a bounded sample: the SAME scene on a coarser lattice."""
+    import moosecad_b200 as mc
+    from oracle import pyoracle
+    pyoracle.set_libm_mode(0)  # the reference calls the platform libm
+    nprim, _ = WORKLOADS[name]
+    n = 40 if nprim <= 64 else 24
+    from moosecad_b200 import scenes
+    go = mc.Geom(pyoracle.OracleScene())
+    root = scenes.synthetic_csg(go, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
+    root.backend.set_parameters_node(root.node, 0.1, 1.0)
+    t0 = time.perf_counter()
+    om = root.backend.tessellate(root.node, 1.0 / n, REL_ERR)
+    dt = time.perf_counter() - t0
+    pyoracle.set_libm_mode(1)
+    pts = (n + 1) ** 3
+    nt = len(om.elems())
+    return {"value": pts / dt, "unit": "lattice pts/s", "cores": 1, "kind": "port",
+            "sample": f"same scene ({nprim} primitives) on a {n}^3-cell lattice, {pts} lattice points, "
+                      f"{nt} tets, {dt:.2f} s; serial like the reference (no threads in tessellate3d/mesh/main)",
+            "tets_per_s": nt / dt, "seconds": dt, "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust reference
+    cannot be built here (no toolchain, un-vendored crates), so this times the oracle port."""
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    vals, last = [], None
+    for i in range(warm + steps):
+        last = cpu_baseline_sample(args.workload)
+        if i >= warm:
+            vals.append(last)
+    secs = sum(v["seconds"] for v in vals) / len(vals)
+    v = sum(v["value"] for v in vals) / len(vals)
+    nprim, n = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "lattice_points_per_s", "value": v, "unit": "lattice pts/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": secs * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {nprim}-primitive smooth CSG scene, {n}^3-cell lattice "
+                                   f"(each step: bounded sample, see cpu_baseline.sample)"},
+            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": v, "unit": "lattice pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "tets_per_s": sum(x["tets_per_s"] for x in vals) / len(vals)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="csg64_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import moosecad_b200 as mc
+    from moosecad_b200 import _lib, slabs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (moosecad_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+
+    stream = torch.cuda.Stream(device=dev)
+    lib = _lib.lib()
+    with torch.cuda.stream(stream):
+        ctx = mc.Context(local_rank, stream.cuda_stream)
+        g, root, res, n = build_scene(mc.Geom, args.workload)
+        g.backend.set_parameters(0.1, 1.0)
+        info = g.backend.program_info(root.node, res)
+        P_total = (n + 1) ** 3
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        def one_step():
+            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev)
+            return sm.run()
+
+        def stage_ms(h):
+            ms = (C.c_double * 9)()
+            lib.mc_mesh_stage_ms(h, ms)
+            return list(ms)
+
+        def counts(h):
+            c = (C.c_uint64 * 6)()
+            lib.mc_mesh_counts(h, c)
+            return list(c)
+
+        # ---- device-resident throughput ("value") ----
+        for _ in range(warm):
+            h = one_step()
+            lib.mc_mesh_free(h)
+        fp64_peak = ctx.probe_fp64_nofma()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = ctx.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_acc = [0.0] * 9
+        ev0.record(stream)
+        last_counts = None
+        for _ in range(steps):
+            h = one_step()
+            st = stage_ms(h)
+            stage_acc = [a + b for a, b in zip(stage_acc, st)]
+            last_counts = counts(h)
+            lib.mc_mesh_free(h)
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = ev0.elapsed_time(ev1)
+        launches = ctx.launch_count - launches0
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        cnt = torch.tensor(last_counts[:2] + [launches], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms_step = float(t.item()) / steps
+        n_verts, n_tets, launches_all = (int(x) for x in cnt.tolist())
+        stage_avg = [a / steps for a in stage_acc]
+
+        # ---- end to end through the C ABI with HOST buffers ----
+        e2e = None
+        if not args.no_e2e:
+            my_c = last_counts
+            idx_bytes = 4
+            coords_h = torch.empty(max(1, my_c[0]) * 3, dtype=torch.float64).pin_memory()
+            tets_h = torch.empty(max(1, my_c[1]) * 4, dtype=torch.int32).pin_memory()
+            e_steps = max(1, min(steps, 2))
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            a0.record(stream)
+            h2d = 0
+            for _ in range(e_steps):
+                g2, root2, _, _ = build_scene(mc.Geom, args.workload)     # scene lowering from host data
+                g2.backend.set_parameters(0.1, 1.0)
+                sm = slabs.SlabMesher(ctx, root2, res, REL_ERR, rank, world, None, dev)
+                h = sm.run()
+                ib = C.c_int()
+                lib.mc_mesh_device_views(h, None, None, C.byref(ib))
+                idx_bytes = ib.value
+                _lib.check(lib.mc_mesh_copy_to_host(h, C.c_void_p(coords_h.data_ptr()), C.c_void_p(tets_h.data_ptr()), 4))
+                h2d = g2.backend.program_info(root2.node, res)["words"] * 8
+                lib.mc_mesh_free(h)
+            a1.record(stream)
+            barrier()
+            wall = time.perf_counter() - w0
+            te = torch.tensor([max(a0.elapsed_time(a1), wall * 1e3)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            ms_e2e = float(te.item()) / e_steps
+            d2h = torch.tensor([my_c[0] * 24 + my_c[1] * 16], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
+            e2e = {"value": P_total / (ms_e2e * 1e-3), "unit": "lattice pts/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h.item()),
+                   "tets_per_s": n_tets / (ms_e2e * 1e-3),
+                   "what": "scene lowering + program upload + meshing + copy of coords (f64) and tets "
+                           f"(u{idx_bytes * 8}) into pinned host buffers, via the C ABI"}
+            del coords_h, tets_h
+
+        if rank == 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except OSError:
+                pass
+            hbm_peak = peaks.get("hbm_gbs", 6650.0)
+            # dominant kernel: k_sdf_field.  Algorithmic flops = evaluate-all flop model of the tape
+            # (mc_tape_program_info) x lattice points evaluated by one launch.
+            p_eval = (n + 1) ** 2 * (min(n, n // world + 4) + 1) if world > 1 else P_total
+            sdf_s = stage_avg[0] * 1e-3
+            sdf_flops = info["flops"] * p_eval
+            roof = {"bound": "fp64_nofma", "kernel": "k_sdf_field",
+                    "achieved": sdf_flops / sdf_s / 1e12 if sdf_s > 0 else None,
+                    "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                    "frac": (sdf_flops / sdf_s) / fp64_peak if sdf_s > 0 else None, "traffic": None,
+                    "peak_source": "measured live: mc_probe_fp64_nofma (DADD+DMUL, --fmad=false); "
+                                   "not in MEASURED_PEAKS.json (SURVEY.md §8d)",
+                    "flops_per_point_evaluate_all": info["flops"], "ms": stage_avg[0]}
+            stuff_ms = sum(stage_avg[1:7])
+            bytes_alg = 8 * P_total + 24 * n_verts + 4 * 4 * n_tets
+            roof2 = {"bound": "hbm", "kernels": "warp..quality (stages 1-6)",
+                     "achieved": bytes_alg / (stuff_ms * 1e-3) / 1e9 if stuff_ms > 0 else None, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": bytes_alg / (stuff_ms * 1e-3) / 1e9 / hbm_peak if stuff_ms > 0 else None,
+                     "algorithmic_bytes": bytes_alg, "ms": stuff_ms,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}
+            nprim, _ = WORKLOADS[args.workload]
+            line = {"metric": "lattice_points_per_s", "value": P_total / (ms_step * 1e-3), "unit": "lattice pts/s",
+                    "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic",
+                    "config": {"workload": f"synthetic {nprim}-primitive smooth CSG scene "
+                                           f"(numpy default_rng({nprim})), {n}^3-cell lattice, "
+                                           f"tessellation error {REL_ERR}, {'z-slabs over %d GPUs' % world if world > 1 else 'single GPU'}",
+                               "lattice_points": P_total, "output_vertices": n_verts, "output_tets": n_tets,
+                               "l2": "working set (>= 8 B x lattice points per array) is far larger than the 126 MB L2; no flush needed",
+                               "tape_words": info["words"]},
+                    "tets_per_s": n_tets / (ms_step * 1e-3),
+                    "sdf_points_per_s": p_eval * world / sdf_s if sdf_s > 0 else None,
+                    "stage_ms": dict(zip(["sdf_field", "warp", "classify", "vertex", "bisect", "tet_emit", "quality",
+                                          "boundary", "sidesets"], [round(x, 3) for x in stage_avg])),
+                    "roofline": roof, "roofline_stuffing": roof2,
+                    "gpu_launches": launches_all, "clocks": clocks, "e2e": e2e}
+            if not args.no_cpu_baseline and world == 1:
+                line["cpu_baseline"] = cpu_baseline_sample(args.workload)
+            print(json.dumps(line), flush=True)
+        del ctx
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,9 @@ int mc_mesh_counts(const mc_mesh*, uint64_t counts[6]);
 /* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
  * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
 int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);
+/* copy that table into a caller-provided DEVICE buffer (n_entries * 8 bytes), asynchronously on
+ * the context's stream: the send buffer of the NVLink exchange */
+int mc_mesh_copy_upper_plane_table(mc_mesh*, void* d_dst);
 /* mirrors the reference's stdout (tessellate3d/src/lib.rs:247,355,366,408-417,421,424):
  * dim, tet count after cut_lattice / before trim / after trim, the 7 case counters,
  * aspect-ratio min/max and the number of inverted tets */

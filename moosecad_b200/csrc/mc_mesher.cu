@@ -488,6 +488,14 @@ int mc_mesh_upper_plane_table(mc_mesh* m, void** d_table, uint64_t* n_entries) {
     return MC_OK;
 }
 
+int mc_mesh_copy_upper_plane_table(mc_mesh* m, void* d_dst) {
+    if (!m || !d_dst) return fail(MC_ERR_ARG, "mc_mesh_copy_upper_plane_table: bad argument");
+    if (m->phase < 2 || !m->d_plane_table.p) return fail(MC_ERR_STATE, "mc_mesh_copy_upper_plane_table: no table (last slab or vertices not emitted)");
+    MC_CUDA(cudaSetDevice(m->ctx->device));
+    MC_CUDA(cudaMemcpyAsync(d_dst, m->d_plane_table.p, (size_t)m->L.NX * m->L.NY * 8, cudaMemcpyDeviceToDevice, m->ctx->stream));
+    return MC_OK;
+}
+
 int mc_mesh_stats(const mc_mesh* m, uint64_t dim[3], uint64_t ntets_stage[3], uint64_t stats[7], double ar_minmax[2],
                   uint64_t* inverted) {
     if (!m) return fail(MC_ERR_ARG, "mc_mesh_stats: null mesh");

@@ -224,7 +224,8 @@ class Mesh:
 class IsosurfaceStuffing:
     """``tessellate3d::IsosurfaceStuffing`` (tessellate3d/src/lib.rs:24-52,420-431)."""
 
-    def __init__(self, function, resolution, relative_error, ctx=None, flags=0, max_bisect_iters=0):
+    def __init__(self, function, resolution, relative_error, ctx=None, flags=0, max_bisect_iters=0,
+                 allow_diverged=False):
         if isinstance(function, LObject):
             function = ObjectAdaptor(function, resolution, ctx)
         if not isinstance(function, ObjectAdaptor):
@@ -238,6 +239,9 @@ class IsosurfaceStuffing:
         self.ctx = ctx or function.ctx or default_context()
         self.flags = int(flags)
         self.max_bisect_iters = int(max_bisect_iters)
+        # the reference's cut_edge loops forever when the SDF jumps across zero by more than the
+        # error threshold; here that is MC_ERR_DIVERGED (the mesh is still returned on request)
+        self.allow_diverged = bool(allow_diverged)
 
     def tessellate(self):
         lib = _lib.lib()
@@ -246,7 +250,7 @@ class IsosurfaceStuffing:
         obj = self.function.implicit
         rc = lib.mc_tessellate(self.ctx.handle, obj.backend.handle, obj.node, self.resolution, self.relative_error,
                                C.byref(opts), C.byref(out))
-        if rc != _lib.MC_OK:
+        if rc != _lib.MC_OK and not (rc == _lib.MC_ERR_DIVERGED and self.allow_diverged and out.value):
             err = _lib.McError(rc, _lib.last_error())
             if out.value:
                 lib.mc_mesh_free(out)
