@@ -146,6 +146,8 @@ typedef struct mc_options {
 } mc_options;
 #define MC_OPT_KEEP_PHI 1u     /* keep the lattice SDF field readable after the call */
 #define MC_OPT_SKIP_QUALITY 2u /* skip check_for_inverted_tets (stdout-only in the reference) */
+#define MC_OPT_NO_TILE_PRUNING 4u /* evaluate the full SDF program at every lattice point */
+#define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
 
 /* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts
  * (mc_mesh_counts) are known; nothing has been emitted yet. */
@@ -170,6 +172,9 @@ void mc_mesh_free(mc_mesh*);
 /* counts: [0] vertices owned by this slab, [1] tets, [2] lattice points evaluated (incl.
  * halo), [3] lattice points owned, [4] cut edges, [5] warped vertices */
 int mc_mesh_counts(const mc_mesh*, uint64_t counts[6]);
+/* tile specialisation of the SDF program (0 tiles when the plain evaluator was used): number of
+ * tiles, sum over tiles of the compacted program size in 8-byte words, size of the full program */
+int mc_mesh_prune_stats(const mc_mesh*, uint64_t* n_tiles, uint64_t* pruned_words_total, uint64_t* full_words);
 /* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
  * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
 int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmoosecad_b200.so")
 MC_OK = 0
 MC_ERR_ARG, MC_ERR_BBOX, MC_ERR_SINGULAR, MC_ERR_UNSUPPORTED = -1, -2, -3, -4
 MC_ERR_CUDA, MC_ERR_LIMIT, MC_ERR_DIVERGED, MC_ERR_STATE = -5, -6, -7, -8
-MC_OPT_KEEP_PHI, MC_OPT_SKIP_QUALITY = 1, 2
+MC_OPT_KEEP_PHI, MC_OPT_SKIP_QUALITY, MC_OPT_NO_TILE_PRUNING, MC_OPT_FORCE_TILE_PRUNING = 1, 2, 4, 8
 
 
 class McError(RuntimeError):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "mc_tessellate": (C.c_int, [_P, _P, _I32, _D, _D, C.POINTER(mc_options), C.POINTER(_P)]),
     "mc_mesh_free": (None, [_P]),
     "mc_mesh_counts": (C.c_int, [_P, _PU64]),
+    "mc_mesh_prune_stats": (C.c_int, [_P, _PU64, _PU64, _PU64]),
     "mc_mesh_upper_plane_table": (C.c_int, [_P, C.POINTER(_P), _PU64]),
     "mc_mesh_copy_upper_plane_table": (C.c_int, [_P, _P]),
     "mc_mesh_stats": (C.c_int, [_P, _PU64, _PU64, _PU64, _PD, _PU64]),

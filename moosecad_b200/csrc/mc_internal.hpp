@@ -49,6 +49,9 @@ struct mc_mesh {
     mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vbase, d_cinfo;
     mc::DevBuf d_ctile_tot, d_ctile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
     mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
+    mc::DevBuf d_inst_start, d_word_inst, d_dec;  // tile specialisation (mc_prune.cuh)
+    uint64_t n_tiles = 0;
+    double avg_pruned_words = 0;
     uint64_t n_ctiles = 0, n_vtiles = 0;
 
     uint64_t counters[32] = {0};

@@ -16,7 +16,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;

@@ -8,6 +8,7 @@
 
 #include "mc_internal.hpp"
 #include "mc_kernels.cuh"
+#include "mc_prune.cuh"
 
 using namespace mc;
 
@@ -71,7 +72,8 @@ static void mesh_release_all(mc_mesh* m) {
     mc_ctx* c = m->ctx;
     DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vbase, &m->d_cinfo, &m->d_ctile_tot,
                       &m->d_ctile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
-                      &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides};
+                      &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
+                      &m->d_inst_start, &m->d_word_inst, &m->d_dec};
     for (DevBuf* b : bufs) c->release(*b);
     for (auto& e : m->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -162,11 +164,62 @@ int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, cons
 }
 
 // ---- the mesher -------------------------------------------------------------------------
+// tile-specialised evaluation (mc_prune.cuh): worth it once the program is more than a few nodes
+static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
+    mc_ctx* c = m->ctx;
+    *done = false;
+    const Program& p = m->prog;
+    const uint32_t n_inst = (uint32_t)p.inst_start.size(), n_words = (uint32_t)p.words.size();
+    if (n_inst >= 0xffffu || p.n_decisions == 0) return MC_OK;
+    const size_t smem = (size_t)n_words * 8 + ((p.n_decisions + 15u) & ~15u) + (size_t)(n_inst + 1) * 8;
+    const size_t smem_cap = c->smem_optin ? c->smem_optin : 48 * 1024;
+    if (smem > smem_cap) return MC_OK;
+    const Lattice& L = m->L;
+    TileGrid g;
+    g.tx = 16; g.ty = 16; g.tz = 16;
+    const uint32_t nplanes = L.pz1 - L.pz0 + 1;
+    g.ntx = (L.NX + g.tx - 1) / g.tx; g.nty = (L.NY + g.ty - 1) / g.ty; g.ntz = (nplanes + g.tz - 1) / g.tz;
+    g.z0 = L.pz0;
+    const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
+    m->n_tiles = ntiles;
+    int rc = c->alloc((size_t)n_inst * 4, m->d_inst_start);
+    if (rc == MC_OK) rc = c->alloc((size_t)n_words * 2, m->d_word_inst);
+    if (rc == MC_OK) rc = c->alloc((size_t)p.n_decisions * ntiles, m->d_dec);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(cudaMemcpyAsync(m->d_inst_start.p, p.inst_start.data(), (size_t)n_inst * 4, cudaMemcpyHostToDevice, c->stream));
+    MC_CUDA(cudaMemcpyAsync(m->d_word_inst.p, p.word_inst.data(), (size_t)n_words * 2, cudaMemcpyHostToDevice, c->stream));
+    k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)m->d_prog.p, ntiles,
+                                                                  (uint8_t*)m->d_dec.p);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
+    auto kern = k_sdf_field_tiled<8, 4>;
+    if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)c->sm_count * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    unsigned long long* pruned_total = (unsigned long long*)m->d_counters.p + CN_PRUNED_WORDS;
+    kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
+                                                   (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
+                                                   n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
+                                                   pruned_total);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
+    *done = true;
+    return MC_OK;
+}
+
 static int launch_sdf_field(mc_mesh* m) {
     mc_ctx* c = m->ctx;
+    if ((m->prog.flops >= 256 || (m->flags & MC_OPT_FORCE_TILE_PRUNING)) && !(m->flags & MC_OPT_NO_TILE_PRUNING)) {
+        bool done = false;
+        int rc = launch_sdf_field_tiled(m, &done);
+        if (rc != MC_OK || done) return rc;
+    }
     const int nwords = (int)m->prog.words.size();
     const size_t prog_bytes = (size_t)nwords * 8;
-    // stage the program in shared memory when it fits (leave room for 2 blocks per SM when small)
+    // stage the program in shared memory when it fits
     const size_t smem_cap = c->smem_optin ? c->smem_optin : 48 * 1024;
     const int in_smem = prog_bytes <= smem_cap ? 1 : 0;
     const size_t smem = in_smem ? prog_bytes : 0;
@@ -477,6 +530,14 @@ int mc_mesh_counts(const mc_mesh* m, uint64_t counts[6]) {
     if (!m || !counts) return fail(MC_ERR_ARG, "mc_mesh_counts: bad argument");
     counts[0] = m->n_verts; counts[1] = m->n_tets; counts[2] = m->points_evaluated;
     counts[3] = m->points_owned; counts[4] = m->n_cuts; counts[5] = m->counters[CN_WARPED];
+    return MC_OK;
+}
+
+int mc_mesh_prune_stats(const mc_mesh* m, uint64_t* n_tiles, uint64_t* pruned_words_total, uint64_t* full_words) {
+    if (!m) return fail(MC_ERR_ARG, "mc_mesh_prune_stats: null mesh");
+    if (n_tiles) *n_tiles = m->n_tiles;
+    if (pruned_words_total) *pruned_words_total = m->counters[CN_PRUNED_WORDS];
+    if (full_words) *full_words = m->prog.words.size();
     return MC_OK;
 }
 

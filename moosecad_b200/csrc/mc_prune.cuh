@@ -1,0 +1,398 @@
+// Tile specialisation of the SDF program.
+//
+// The reference evaluates the whole CSG tree at every lattice point; on a 1024^3 lattice with
+// a 64-primitive scene that is ~10^13 operations although, around any given point, only a
+// handful of primitives can influence the value.  Here the lattice is cut into tiles; for
+// every tile an INTERVAL evaluation of the program (lanes = tiles, the program counter is
+// warp-uniform) decides, rigorously,
+//   * for every bbox guard: passes at every point of the tile / fails at every point / mixed,
+//   * for every child of a smooth boolean: whether it can influence the result anywhere in
+//     the tile.  A child x_i of rvmin can be dropped when x_i >= m + max(r, exact_range) at
+//     every point (m = the minimum): it then never changes the running minimum, never sets
+//     the `close` flag and is excluded from the exponential sum, so rvmin returns the same
+//     bits with or without it (mirror image for rvmax).
+// The evaluation kernel then compacts, per tile, the program into shared memory (dead
+// subtrees removed, always-pass guards dropped, always-fail guards replaced by a plain bbox
+// distance, single-child booleans elided, jump targets re-based) and runs the ordinary point
+// evaluator on it.  Values are bit-identical to evaluating the full program; only work that
+// provably cannot matter is skipped.
+//
+// Interval bounds are computed in floating point and then widened by PAD (1e-9 relative +
+// absolute), many orders of magnitude above the rounding error of the few dozen operations
+// involved, and every decision keeps that margin; NaN bounds fall through to "keep".
+#pragma once
+#include "mc_kernels.cuh"
+
+namespace mc {
+
+struct Ival { double lo, hi; };
+
+__device__ __forceinline__ double pad_of(double v) { return 1e-9 * (1.0 + fabs(v)); }
+__device__ __forceinline__ Ival widen(Ival a) { return {a.lo - pad_of(a.lo), a.hi + pad_of(a.hi)}; }
+__device__ __forceinline__ Ival iv_scale(double m, double q0, double q1) {
+    const double a = m * q0, b = m * q1;
+    return {fmin(a, b), fmax(a, b)};
+}
+// interval of |q| over [q0, q1]
+__device__ __forceinline__ Ival iv_abs(double q0, double q1) {
+    const double a = fabs(q0), b = fabs(q1);
+    if (q0 <= 0.0 && q1 >= 0.0) return {0.0, fmax(a, b)};
+    return {fmin(a, b), fmax(a, b)};
+}
+// interval of bbox.distance over a box
+__device__ __forceinline__ Ival iv_box_distance(const uint64_t* __restrict__ w, int at, const double* b) {
+    double lo = -__longlong_as_double(0x7ff0000000000000LL), hi = lo;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double blo = ld_f64(w, at + k), bhi = ld_f64(w, at + 3 + k);
+        const double q0 = b[2 * k], q1 = b[2 * k + 1];
+        hi = fmax(hi, fmax(q1 - bhi, blo - q0));
+        lo = fmax(lo, fmax(q0 - bhi, blo - q1));
+    }
+    return widen({lo, hi});
+}
+
+// Interval evaluation of the program for one tile (this lane); decisions are written to
+// dec[id * dec_stride].  All 32 lanes of the warp run in lock step.
+__device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
+                          size_t dec_stride) {
+    Ival vs[MC_MAX_VALUE_DEPTH + 1];
+    double bs[6 * MC_MAX_POINT_DEPTH];
+    double b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = box0[k];
+    int sp = 0, bsp = 0, pc = 0;
+    Ival top = {0.0, 0.0};
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+#define MC_IPUSH(v) do { vs[sp] = top; ++sp; top = (v); } while (0)
+    for (;;) {
+        const uint64_t h = w[pc];
+        const uint32_t op = MC_HDR_OP(h);
+        if (op == MC_OP_END) return;
+        switch (op) {
+        case MC_OP_PLANE: {
+            const unsigned sm = MC_HDR_SMALL(h);
+            const unsigned axis = sm & 3u;
+            const double d = ld_f64(w, pc + 1);
+            const double q0 = b[2 * axis], q1 = b[2 * axis + 1];
+            Ival v;
+            if (sm & 4u) v = {-q1 - d, -q0 - d}; else v = {q0 - d, q1 - d};
+            MC_IPUSH(widen(v));
+            break;
+        }
+        case MC_OP_NPLANE: {
+            Ival s = {-ld_f64(w, pc + 4), -ld_f64(w, pc + 4)};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const Ival t = iv_scale(ld_f64(w, pc + 1 + k), b[2 * k], b[2 * k + 1]);
+                s.lo += t.lo; s.hi += t.hi;
+            }
+            MC_IPUSH(widen(s));
+            break;
+        }
+        case MC_OP_USQ: {
+            Ival s = {-1.0, -1.0};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const Ival a = iv_abs(b[2 * k], b[2 * k + 1]);
+                s.lo += a.lo * a.lo; s.hi += a.hi * a.hi;
+            }
+            MC_IPUSH(widen(s));
+            break;
+        }
+        case MC_OP_CONE: {
+            const Ival ax = iv_abs(b[0], b[1]), ay = iv_abs(b[2], b[3]);
+            const Ival rho = {sqrt(ax.lo * ax.lo + ay.lo * ay.lo), sqrt(ax.hi * ax.hi + ay.hi * ay.hi)};
+            const double off = ld_f64(w, pc + 2);
+            const Ival u = iv_scale(ld_f64(w, pc + 1), b[4] + off, b[5] + off);
+            const Ival rad = iv_abs(u.lo, u.hi);
+            const Ival v = iv_scale(ld_f64(w, pc + 3), rho.lo - rad.hi, rho.hi - rad.lo);
+            MC_IPUSH(widen(widen(v)));
+            break;
+        }
+        case MC_OP_GSPHERE:
+        case MC_OP_GCYL: {
+            const Ival a = iv_box_distance(w, pc + 1, b);
+            const double slack = ld_f64(w, pc + 7), r = ld_f64(w, pc + 8);
+            const Ival ax = iv_abs(b[0], b[1]), ay = iv_abs(b[2], b[3]), az = iv_abs(b[4], b[5]);
+            Ival e;
+            if (op == MC_OP_GSPHERE)
+                e = {sqrt((ax.lo * ax.lo + ay.lo * ay.lo) + az.lo * az.lo) - r,
+                     sqrt((ax.hi * ax.hi + ay.hi * ay.hi) + az.hi * az.hi) - r};
+            else
+                e = {sqrt(ax.lo * ax.lo + ay.lo * ay.lo) - r, sqrt(ax.hi * ax.hi + ay.hi * ay.hi) - r};
+            e = widen(e);
+            uint8_t d = MC_DEC_KEEP;
+            Ival v = {fmin(a.lo, e.lo), fmax(a.hi, e.hi)};
+            if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
+            else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
+            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            MC_IPUSH(v);
+            break;
+        }
+        case MC_OP_GUARD: {
+            const Ival a = iv_box_distance(w, pc + 1, b);
+            const double slack = ld_f64(w, pc + 7);
+            uint8_t d = MC_DEC_KEEP;
+            if (a.hi <= slack) d = MC_DEC_PASS;
+            else if (a.lo > slack) d = MC_DEC_FAIL;
+            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            // the subtree is skipped only when it is dead for all 32 tiles of the warp
+            if (__all_sync(0xffffffffu, d == MC_DEC_FAIL)) {
+                MC_IPUSH(a);
+                pc = (int)MC_HDR_IDX(h);
+                continue;
+            }
+            break;
+        }
+        case MC_OP_ENDG: {
+            const int g = (int)MC_HDR_IDX(h);
+            const Ival a = iv_box_distance(w, g + 1, b);
+            const double slack = ld_f64(w, g + 7);
+            if (a.hi <= slack) { /* pass everywhere: subtree value */ }
+            else if (a.lo > slack) top = a;
+            else top = {fmin(top.lo, a.lo), fmax(top.hi, a.hi)};
+            break;
+        }
+        case MC_OP_NEG:
+            top = {-top.hi, -top.lo};
+            break;
+        case MC_OP_CHILD:
+            break;
+        case MC_OP_BOOL: {
+            const unsigned sm = MC_HDR_SMALL(h);
+            const int k = (int)(sm & 0x7fu);
+            const bool is_union = (sm & 0x80u) != 0;
+            const double r = ld_f64(w, pc + 1), er = ld_f64(w, pc + 2);
+            const double margin = fmax(r, er);
+            const int base = sp - k + 1;
+            // bound of the extremum: min of the upper bounds (union) / max of the lower bounds
+            double ext = is_union ? INF : -INF;
+            for (int i = 0; i < k; ++i) {
+                const Ival x = (i == k - 1) ? top : vs[base + i];
+                ext = is_union ? fmin(ext, x.hi) : fmax(ext, x.lo);
+            }
+            int kept = 0;
+            Ival res = is_union ? Ival{INF, INF} : Ival{-INF, -INF};
+            const uint32_t dbase = MC_HDR_DEC(h);
+            for (int i = 0; i < k; ++i) {
+                const Ival x = (i == k - 1) ? top : vs[base + i];
+                bool drop;
+                if (is_union) drop = x.lo >= ext + margin + pad_of(ext + margin);
+                else drop = x.hi <= ext - margin - pad_of(ext - margin);
+                dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
+                if (!drop) {
+                    ++kept;
+                    if (is_union) { res.lo = fmin(res.lo, x.lo); res.hi = fmin(res.hi, x.hi); }
+                    else { res.lo = fmax(res.lo, x.lo); res.hi = fmax(res.hi, x.hi); }
+                }
+            }
+            if (kept > 1) {
+                // smooth branch: rvmin in [min - r/4 ln k, min], rvmax in [max, max + r/4 ln k]
+                const double wdn = 0.25 * r * 1.3862943611198906 * (double)(kept <= 4 ? 1 : 2) * (kept <= 16 ? 1.0 : 2.5);
+                if (is_union) res.lo -= wdn; else res.hi += wdn;
+                res = widen(res);
+            }
+            sp -= k - 1;
+            top = res;
+            break;
+        }
+        case MC_OP_APUSH: {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bs[bsp + k] = b[k];
+            bsp += 6;
+            double nb[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                Ival s = {ld_f64(w, pc + 4 + 4 * i), ld_f64(w, pc + 4 + 4 * i)};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const Ival t = iv_scale(ld_f64(w, pc + 1 + 4 * i + j), b[2 * j], b[2 * j + 1]);
+                    s.lo += t.lo; s.hi += t.hi;
+                }
+                s = widen(s);
+                nb[2 * i] = s.lo; nb[2 * i + 1] = s.hi;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) b[k] = nb[k];
+            break;
+        }
+        case MC_OP_APOP: {
+            bsp -= 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) b[k] = bs[bsp + k];
+            top = widen(iv_scale(ld_f64(w, pc + 1), top.lo, top.hi));
+            break;
+        }
+        default:
+            return;
+        }
+        pc += mc_op_words(op);
+    }
+#undef MC_IPUSH
+}
+
+struct TileGrid {
+    uint32_t tx, ty, tz;        // tile extent in lattice points
+    uint32_t ntx, nty, ntz;     // tiles per axis (over the stored planes)
+    uint32_t z0;                // first stored plane
+};
+
+__device__ __forceinline__ void tile_origin(const TileGrid& g, uint64_t t, uint32_t& X0, uint32_t& Y0, uint32_t& Z0) {
+    X0 = (uint32_t)(t % g.ntx) * g.tx;
+    const uint64_t r = t / g.ntx;
+    Y0 = (uint32_t)(r % g.nty) * g.ty;
+    Z0 = g.z0 + (uint32_t)(r / g.nty) * g.tz;
+}
+
+// decisions for every tile: one tile per lane
+static __global__ void __launch_bounds__(128)
+k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint8_t* __restrict__ dec) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t tc = t < ntiles ? t : ntiles - 1;
+    uint32_t X0, Y0, Z0;
+    tile_origin(g, tc, X0, Y0, Z0);
+    const uint32_t X1 = min(X0 + g.tx, L.NX) - 1, Y1 = min(Y0 + g.ty, L.NY) - 1, Z1 = min(Z0 + g.tz, L.pz1 + 1) - 1;
+    // lattice coordinates are monotone in the index, so the end points bound the tile exactly
+    const double box[6] = {lat_x(L, X0), lat_x(L, X1), lat_y(L, Y0), lat_y(L, Y1), lat_z(L, Z0), lat_z(L, Z1)};
+    // lanes past the end redo the last tile (same decisions, benign duplicate stores)
+    vm_decide(prog, box, dec + tc, (size_t)ntiles);
+}
+
+// per-tile compaction of the program into shared memory + evaluation of the tile's points
+// smem layout: [out program (max_words)] [dec (n_dec bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
+template <int WX, int WY>
+__global__ void __launch_bounds__(256)
+k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
+                  const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
+                  uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
+                  unsigned long long* __restrict__ pruned_words_total) {
+    extern __shared__ uint64_t smem[];
+    uint64_t* s_prog = smem;
+    uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
+    int* s_delta = (int*)(s_dec + ((n_dec + 15u) & ~15u));
+    uint32_t* s_newpos = (uint32_t*)(s_delta + (n_inst + 1));
+    __shared__ uint32_t s_scan[9];
+    const uint32_t tid = threadIdx.x;
+
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();  // previous tile's evaluation is done with s_prog
+        for (uint32_t i = tid; i < n_dec; i += blockDim.x) s_dec[i] = dec_g[(size_t)i * ntiles + tile];
+        for (uint32_t i = tid; i <= n_inst; i += blockDim.x) s_delta[i] = 0;
+        __syncthreads();
+        // 1. dead ranges: dropped boolean children and always-failing guards
+        for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
+            const uint64_t h = prog[inst_start[i]];
+            const uint32_t op = MC_HDR_OP(h);
+            if (op == MC_OP_CHILD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
+                atomicAdd(&s_delta[i + 1], 1);
+                atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
+            } else if (op == MC_OP_GUARD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
+                atomicAdd(&s_delta[i + 1], 1);
+                atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
+            }
+        }
+        __syncthreads();
+        // 2. inclusive scan of the deltas -> nesting depth of dead ranges; new length of every
+        //    instruction; exclusive scan of the lengths -> new word positions
+        uint32_t run_depth = 0, run_pos = 0;
+        for (uint32_t base = 0; base <= n_inst; base += blockDim.x) {
+            const uint32_t i = base + tid;
+            const int dlt = (i <= n_inst) ? s_delta[i] : 0;
+            uint32_t tot;
+            // depths are non-negative at every prefix, so unsigned wrap-around arithmetic is safe
+            const uint32_t ex = block_exscan((uint32_t)dlt, &tot, s_scan);
+            const uint32_t depth = run_depth + ex + (uint32_t)dlt;
+            run_depth += tot;
+            uint32_t len = 0;
+            if (i < n_inst && depth == 0) {
+                const uint64_t h = prog[inst_start[i]];
+                const uint32_t op = MC_HDR_OP(h);
+                const uint8_t d = (op == MC_OP_GUARD || op == MC_OP_ENDG || op == MC_OP_GSPHERE || op == MC_OP_GCYL)
+                                      ? s_dec[MC_HDR_DEC(h)] : (uint8_t)MC_DEC_KEEP;
+                switch (op) {
+                case MC_OP_GUARD: len = d == MC_DEC_PASS ? 0u : (d == MC_DEC_FAIL ? 7u : 8u); break;
+                case MC_OP_ENDG: len = d == MC_DEC_KEEP ? 1u : 0u; break;
+                case MC_OP_GSPHERE: case MC_OP_GCYL: len = d == MC_DEC_PASS ? 2u : (d == MC_DEC_FAIL ? 7u : 9u); break;
+                case MC_OP_CHILD: len = 0u; break;
+                case MC_OP_BOOL: {
+                    const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
+                    uint32_t kept = 0;
+                    for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
+                    len = kept > 1 ? 3u : 0u;
+                    break;
+                }
+                default: len = (uint32_t)mc_op_words(op); break;
+                }
+            }
+            const uint32_t pex = block_exscan(len, &tot, s_scan);
+            if (i <= n_inst) { s_newpos[i] = run_pos + pex; s_delta[i] = (int)len; }
+            run_pos += tot;
+        }
+        __syncthreads();
+        // 3. write the compacted program
+        for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
+            const uint32_t len = (uint32_t)s_delta[i];
+            if (len == 0) continue;
+            const uint32_t src = inst_start[i], dst = s_newpos[i];
+            const uint64_t h = prog[src];
+            const uint32_t op = MC_HDR_OP(h);
+            switch (op) {
+            case MC_OP_GUARD:
+                if (len == 7u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+                } else {
+                    s_prog[dst] = MC_HDR(MC_OP_GUARD, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+                    for (uint32_t q = 1; q < 8; ++q) s_prog[dst + q] = prog[src + q];
+                }
+                break;
+            case MC_OP_ENDG:
+                s_prog[dst] = MC_HDR(MC_OP_ENDG, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+                break;
+            case MC_OP_GSPHERE: case MC_OP_GCYL:
+                if (len == 2u) {
+                    s_prog[dst] = MC_HDR(op == MC_OP_GSPHERE ? MC_OP_SPHERE : MC_OP_CYL, 0, 0, 0, 0);
+                    s_prog[dst + 1] = prog[src + 8];
+                } else if (len == 7u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+                } else {
+                    for (uint32_t q = 0; q < 9; ++q) s_prog[dst + q] = prog[src + q];
+                }
+                break;
+            case MC_OP_BOOL: {
+                const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
+                uint32_t kept = 0;
+                for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
+                s_prog[dst] = MC_HDR(MC_OP_BOOL, kept | (MC_HDR_SMALL(h) & 0x80u), 0, 0, 0);
+                s_prog[dst + 1] = prog[src + 1];
+                s_prog[dst + 2] = prog[src + 2];
+                break;
+            }
+            default:
+                for (uint32_t q = 0; q < len; ++q) s_prog[dst + q] = prog[src + q];
+                break;
+            }
+        }
+        if (tid == 0 && pruned_words_total) atomicAdd(pruned_words_total, (unsigned long long)s_newpos[n_inst]);
+        __syncthreads();
+        // 4. evaluate the tile: WX x WY points of one z-plane per warp step
+        uint32_t X0, Y0, Z0;
+        tile_origin(g, tile, X0, Y0, Z0);
+        const uint32_t wpx = g.tx / WX, wpy = g.ty / WY;
+        const uint32_t steps = wpx * wpy * g.tz;
+        const uint32_t lane = tid & 31u, lx = lane % WX, ly = lane / WX;
+        for (uint32_t s = tid >> 5; s < steps; s += (blockDim.x >> 5)) {
+            const uint32_t sx = s % wpx, sy = (s / wpx) % wpy, sz = s / (wpx * wpy);
+            const uint32_t X = X0 + sx * WX + lx, Y = Y0 + sy * WY + ly, Z = Z0 + sz;
+            if (Z > L.pz1) continue;  // warp-uniform
+            const bool inside = X < L.NX && Y < L.NY;
+            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
+            const double v = vm_eval<true>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z));
+            if (inside) phi_out[pidx(L, X, Y, Z)] = v;
+        }
+    }
+}
+
+}  // namespace mc

@@ -187,6 +187,8 @@ struct Lowering {
     int depth = 0, max_depth = 0;      // value stack
     int pdepth = 0, max_pdepth = 0;    // point stack
     int level = 0;                     // guard nesting
+    uint32_t next_dec = 0;             // tile-pruning decision ids
+    int lvl(int l) const { return l < 255 ? l : 255; }
 
     void word(uint64_t w) { prog.words.push_back(w); }
     void dword(double d) {
@@ -209,31 +211,31 @@ struct Lowering {
         const Node& n = tape.nodes[(size_t)id];
         switch (n.kind) {
         case NK_PLANE:
-            word(MC_HDR(MC_OP_PLANE, n.axis | (n.inverted ? 4 : 0), 0, 0));
+            word(MC_HDR(MC_OP_PLANE, n.axis | (n.inverted ? 4 : 0), 0, 0, 0));
             dword(n.p[0]);
             prog.flops += 3;
             pushed();
             return MC_OK;
         case NK_NPLANE:
-            word(MC_HDR(MC_OP_NPLANE, 0, 0, 0));
+            word(MC_HDR(MC_OP_NPLANE, 0, 0, 0, 0));
             for (int k = 0; k < 4; ++k) dword(n.p[k]);
             prog.flops += 6;
             pushed();
             return MC_OK;
         case NK_USQ:
-            word(MC_HDR(MC_OP_USQ, 0, 0, 0));
+            word(MC_HDR(MC_OP_USQ, 0, 0, 0, 0));
             prog.flops += 6;
             pushed();
             return MC_OK;
         case NK_CONE:
-            word(MC_HDR(MC_OP_CONE, 0, 0, 0));
+            word(MC_HDR(MC_OP_CONE, 0, 0, 0, 0));
             dword(n.p[0]); dword(n.p[1]); dword(n.p[2]);
             prog.flops += 8;
             pushed();
             return MC_OK;
         case NK_SPHERE:
         case NK_CYL:
-            word(MC_HDR(n.kind == NK_SPHERE ? MC_OP_GSPHERE : MC_OP_GCYL, 0, 0, 0));
+            word(MC_HDR(n.kind == NK_SPHERE ? MC_OP_GSPHERE : MC_OP_GCYL, 0, 0, next_dec++, 0));
             box_words(n.bbox, slack);
             dword(n.p[0]);
             prog.flops += 12 + (n.kind == NK_SPHERE ? 7 : 5);
@@ -242,7 +244,7 @@ struct Lowering {
         case NK_NEG: {
             int rc = emit(n.children[0], slack);
             if (rc != MC_OK) return rc;
-            word(MC_HDR(MC_OP_NEG, 0, 0, 0));
+            word(MC_HDR(MC_OP_NEG, 0, 0, 0, 0));
             prog.flops += 1;
             return MC_OK;
         }
@@ -252,19 +254,27 @@ struct Lowering {
             if (k > 127) { err = "boolean node with more than 127 children"; return MC_ERR_LIMIT; }
             const bool guarded = !box_is_infinite(n.bbox);
             size_t guard_at = 0;
+            uint32_t guard_dec = 0;
+            int my_level = 0;
             if (guarded) {
                 guard_at = prog.words.size();
+                guard_dec = next_dec++;
                 word(0);  // patched below
                 box_words(n.bbox, slack);
-                ++level;
+                my_level = level++;
                 prog.flops += 12;
             }
             const double child_slack = slack + n.r;  // approx_value(p, slack + self.r)
-            for (int32_t c : n.children) {
-                int rc = emit(c, child_slack);
+            const uint32_t dec_base = next_dec;
+            next_dec += (uint32_t)k;
+            for (size_t ci = 0; ci < k; ++ci) {
+                const size_t child_at = prog.words.size();
+                word(0);  // CHILD marker, patched with the end of the child
+                int rc = emit(n.children[ci], child_slack);
                 if (rc != MC_OK) return rc;
+                prog.words[child_at] = MC_HDR(MC_OP_CHILD, n.kind == NK_UNION ? 1 : 0, 0, dec_base + ci, prog.words.size());
             }
-            word(MC_HDR(MC_OP_BOOL, (int)k | (n.kind == NK_UNION ? 0x80 : 0), 0, 0));
+            word(MC_HDR(MC_OP_BOOL, (int)k | (n.kind == NK_UNION ? 0x80 : 0), 0, dec_base, 0));
             dword(n.r);
             dword(n.r * tape.r_multiplier);  // exact_range, set_parameters (src/main.rs:53-58)
             depth -= (int)k - 1;
@@ -273,17 +283,18 @@ struct Lowering {
             prog.n_ln += 1;
             if (guarded) {
                 --level;
-                word(MC_HDR(MC_OP_ENDG, 0, level, guard_at));
-                prog.words[guard_at] = MC_HDR(MC_OP_GUARD, 0, level, prog.words.size());
+                word(MC_HDR(MC_OP_ENDG, 0, lvl(my_level), guard_dec, guard_at));
+                prog.words[guard_at] = MC_HDR(MC_OP_GUARD, 0, lvl(my_level), guard_dec, prog.words.size());
             }
             return MC_OK;
         }
         case NK_AFFINE: {
             const size_t guard_at = prog.words.size();
+            const uint32_t guard_dec = next_dec++;
             word(0);
             box_words(n.bbox, slack);
             const int my_level = level++;
-            word(MC_HDR(MC_OP_APUSH, 0, 0, 0));
+            word(MC_HDR(MC_OP_APUSH, 0, 0, 0, 0));
             for (int i = 0; i < 3; ++i)
                 for (int j = 0; j < 4; ++j) dword(n.m.a[i][j]);
             ++pdepth;
@@ -291,11 +302,11 @@ struct Lowering {
             int rc = emit(n.children[0], slack / n.scale_min);
             if (rc != MC_OK) return rc;
             --pdepth;
-            word(MC_HDR(MC_OP_APOP, 0, 0, 0));
+            word(MC_HDR(MC_OP_APOP, 0, 0, 0, 0));
             dword(n.scale_min);
             --level;
-            word(MC_HDR(MC_OP_ENDG, 0, my_level, guard_at));
-            prog.words[guard_at] = MC_HDR(MC_OP_GUARD, 0, my_level, prog.words.size());
+            word(MC_HDR(MC_OP_ENDG, 0, lvl(my_level), guard_dec, guard_at));
+            prog.words[guard_at] = MC_HDR(MC_OP_GUARD, 0, lvl(my_level), guard_dec, prog.words.size());
             prog.flops += 12 + 21 + 1;
             return MC_OK;
         }
@@ -319,9 +330,10 @@ int mc_tape::compile(int32_t root, double slack, mc::Program& out, std::string& 
     mc::Lowering lw{*this, out, err};
     int rc = lw.emit(root, slack);
     if (rc != MC_OK) return rc;
-    out.words.push_back(MC_HDR(MC_OP_END, 0, 0, 0));
+    out.words.push_back(MC_HDR(MC_OP_END, 0, 0, 0, 0));
     out.value_depth = lw.max_depth;
     out.point_depth = lw.max_pdepth;
+    out.n_decisions = lw.next_dec;
     if (out.value_depth > MC_MAX_VALUE_DEPTH) {
         err = "SDF tree needs a deeper value stack than the device evaluator has";
         return MC_ERR_LIMIT;
@@ -329,6 +341,17 @@ int mc_tape::compile(int32_t root, double slack, mc::Program& out, std::string& 
     if (out.point_depth > MC_MAX_POINT_DEPTH) {
         err = "affine transforms nested deeper than the device evaluator supports";
         return MC_ERR_LIMIT;
+    }
+    if (out.words.size() > MC_MAX_PROGRAM_WORDS || out.n_decisions > MC_MAX_DECISIONS) {
+        err = "SDF program too large for the device evaluator";
+        return MC_ERR_LIMIT;
+    }
+    // instruction table
+    out.word_inst.assign(out.words.size(), 0xffff);
+    for (size_t pc = 0; pc < out.words.size();) {
+        if (out.inst_start.size() < 0xffff) out.word_inst[pc] = (uint16_t)out.inst_start.size();
+        out.inst_start.push_back((uint32_t)pc);
+        pc += (size_t)mc_op_words(MC_HDR_OP(out.words[pc]));
     }
     return MC_OK;
 }

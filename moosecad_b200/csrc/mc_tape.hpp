@@ -40,6 +40,10 @@ struct Program {
     int point_depth = 0;  // nested affine depth
     uint64_t flops = 0;   // evaluate-all flop model per point
     uint64_t n_exp = 0, n_ln = 0;
+    // tile pruning side tables (mc_prune.cuh)
+    std::vector<uint32_t> inst_start;   // word index of every instruction, in program order
+    std::vector<uint16_t> word_inst;    // instruction index of every word that starts an instruction (else 0xffff)
+    uint32_t n_decisions = 0;
 };
 
 }  // namespace mc

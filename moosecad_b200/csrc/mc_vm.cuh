@@ -152,6 +152,21 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             top = -top;
             pc += 1;
             break;
+        case MC_OP_CHILD:
+            pc += 1;
+            break;
+        case MC_OP_BOXDIST:
+            MC_PUSH(box_distance(w, pc + 1, x, y, z));
+            pc += 7;
+            break;
+        case MC_OP_SPHERE:
+            MC_PUSH(sqrt((x * x + y * y) + z * z) - ld_f64(w, pc + 1));
+            pc += 2;
+            break;
+        case MC_OP_CYL:
+            MC_PUSH(sqrt(x * x + y * y) - ld_f64(w, pc + 1));
+            pc += 2;
+            break;
         case MC_OP_BOOL: {
             const unsigned sm = MC_HDR_SMALL(h);
             const int k = (int)(sm & 0x7fu);

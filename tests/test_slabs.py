@@ -1,0 +1,90 @@
+"""z-slab sharding.
+
+CPU: partitioning, the exclusive scan of counts and the neighbour exchange over a
+world_size-2 gloo group.  GPU: the slab phases on one device against the single-slab mesh
+(and, through the oracle, against the reference path)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from moosecad_b200 import slabs
+
+import canon
+
+
+def test_partition():
+    assert slabs.partition(10, 1) == [(0, 10)]
+    assert slabs.partition(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert slabs.partition(1024, 8) == [(128 * i, 128 * (i + 1)) for i in range(8)]
+    p = slabs.partition(3, 4)
+    assert p[-1] == (3, 3) and sum(b - a for a, b in p) == 3
+    assert slabs.bases_from_counts([(10, 100), (20, 200), (30, 300)], 2) == (30, 300)
+    assert slabs.lattice_dim([-0.5, -0.5, -0.5, 0.5, 0.5, 0.5], 1.0 / 1024) == [1024, 1024, 1024]
+    assert slabs.lattice_dim([-7.5] * 3 + [7.5] * 3, 15.0 / 512) == [512, 512, 512]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        counts = slabs.exchange_counts(100 + rank, 1000 * (rank + 1), None, "cpu")
+        vb, tb = slabs.bases_from_counts(counts, rank)
+        n = 7
+        send = torch.arange(n, dtype=torch.int64) + 1000 * rank if rank + 1 < world else None
+        recv = torch.zeros(n, dtype=torch.int64) if rank > 0 else None
+        slabs.exchange_plane_tables(send, recv, rank, world, None)
+        q.put((rank, counts, vb, tb, None if recv is None else recv.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_count_scan_and_plane_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == [(100, 1000), (101, 2000)]
+    assert (res[0][2], res[0][3]) == (0, 0) and (res[1][2], res[1][3]) == (100, 1000)
+    assert res[0][4] is None and res[1][4] == list(range(7))   # rank 1 received rank 0's table
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_slabs", [2, 3, 5])
+@pytest.mark.parametrize("scene", ["sphere", "csg"])
+def test_slabs_match_single_slab(scene, n_slabs, ctx):
+    import moosecad_b200 as mc
+    from moosecad_b200 import luascad, scenes
+    if scene == "sphere":
+        obj, res = luascad.eval(scenes.SPHERE_LUA)["sphere"].obj, 1.0 / 37
+    else:
+        g = mc.Geom()
+        obj, res = scenes.synthetic_csg(g, 12, seed=5), 1.0 / 45
+    obj.backend.set_parameters(0.1, 1.0)
+    whole = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx).tessellate()
+    coords, tets = slabs.tessellate_slabs_one_device(ctx, obj, res, 0.2, n_slabs)
+    a = canon.canonical(whole.vertices(), whole.elems())
+    b = canon.canonical(coords, tets)
+    canon.assert_same_mesh(a, b)
+    # global ids: every vertex referenced, none duplicated
+    assert np.unique(tets).size == len(coords)
+    assert len(np.unique(coords, axis=0)) == len(coords)
