@@ -59,52 +59,62 @@ __device__ __forceinline__ int side_after_flip(int s0) {
     return -1;
 }
 
-__device__ __forceinline__ bool cell_is_full(const Lattice& L, const uint16_t* __restrict__ cinfo, uint32_t cl0,
-                                             uint32_t cl1, int64_t cx, int64_t cy, int64_t cz) {
+Stuff make_stuff(const mc_mesh* m);  // mc_mesher.cu
+
+__device__ __forceinline__ bool cell_is_full(const Stuff& S, int64_t cx, int64_t cy, int64_t cz) {
+    const Lattice& L = S.L;
     if (cx < 0 || cy < 0 || cz < 0 || cx >= (int64_t)L.nx || cy >= (int64_t)L.ny || cz >= (int64_t)L.nz) return false;
-    if (cz < (int64_t)cl0 || cz >= (int64_t)cl1) return false;
-    const uint64_t i = ((uint64_t)(cz - cl0) * L.ny + (uint64_t)cy) * L.nx + (uint64_t)cx;
-    return (cinfo[i] & CI_FULL) != 0;
+    if (cz < (int64_t)S.cl0 || cz >= (int64_t)S.cl1) return false;
+    const uint8_t cu = S.cuni[tile_of(S.g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)];
+    if (cu == CU_FULL) return true;
+    if (cu == CU_EMPTY) return false;
+    return (S.cinfo[cidx(S, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)] & CI_FULL) != 0;
 }
 
-// number of candidate faces of a cell
-__device__ __forceinline__ uint32_t cell_face_count(const Lattice& L, const uint16_t* __restrict__ cinfo, uint32_t cl0,
-                                                    uint32_t cl1, uint32_t cx, uint32_t cy, uint32_t cz, uint16_t ci) {
-    const uint32_t count = ci & CI_COUNT_MASK;
-    if (!(ci & CI_FULL)) return 4u * count;
+// number of candidate faces of a cell with `count` output tets
+__device__ __forceinline__ uint32_t cell_face_count(const Stuff& S, uint32_t cx, uint32_t cy, uint32_t cz, bool full,
+                                                    uint32_t count) {
+    if (!full) return 4u * count;
     uint32_t n = 0;
-    n += cell_is_full(L, cinfo, cl0, cl1, (int64_t)cx - 1, cy, cz) ? 0u : 2u;
-    n += cell_is_full(L, cinfo, cl0, cl1, (int64_t)cx + 1, cy, cz) ? 0u : 2u;
-    n += cell_is_full(L, cinfo, cl0, cl1, cx, (int64_t)cy - 1, cz) ? 0u : 2u;
-    n += cell_is_full(L, cinfo, cl0, cl1, cx, (int64_t)cy + 1, cz) ? 0u : 2u;
-    n += cell_is_full(L, cinfo, cl0, cl1, cx, cy, (int64_t)cz - 1) ? 0u : 2u;
-    n += cell_is_full(L, cinfo, cl0, cl1, cx, cy, (int64_t)cz + 1) ? 0u : 2u;
+    n += cell_is_full(S, (int64_t)cx - 1, cy, cz) ? 0u : 2u;
+    n += cell_is_full(S, (int64_t)cx + 1, cy, cz) ? 0u : 2u;
+    n += cell_is_full(S, cx, (int64_t)cy - 1, cz) ? 0u : 2u;
+    n += cell_is_full(S, cx, (int64_t)cy + 1, cz) ? 0u : 2u;
+    n += cell_is_full(S, cx, cy, (int64_t)cz - 1) ? 0u : 2u;
+    n += cell_is_full(S, cx, cy, (int64_t)cz + 1) ? 0u : 2u;
     return n;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
-k_face_count(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
-             unsigned long long* __restrict__ tile_tot) {
-    __shared__ unsigned long long s_tot;
-    if (threadIdx.x == 0) s_tot = 0ull;
-    __syncthreads();
-    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
-    const uint64_t first = per_layer * (c0 - cl0), last = per_layer * (c1 - cl0);
+// (full?, output tets) of an owned cell of this tile
+__device__ __forceinline__ void cell_state(const Stuff& S, uint8_t cu, uint32_t cx, uint32_t cy, uint32_t cz, bool& full,
+                                           uint32_t& count, uint16_t& ci) {
+    if (cu == CU_FULL) { full = true; count = 5; ci = (uint16_t)(5 | CI_FULL); return; }
+    ci = S.cinfo[cidx(S, cx, cy, cz)];
+    full = (ci & CI_FULL) != 0;
+    count = ci & CI_COUNT_MASK;
+}
+
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_face_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
+    __shared__ unsigned long long s_acc;
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    const uint8_t cu = S.cuni[blockIdx.x];
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
     unsigned long long mine = 0;
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        if (i < first || i >= last) continue;
-        const uint16_t ci = cinfo[i];
-        if (!(ci & CI_COUNT_MASK)) continue;
-        const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
-        const uint64_t r = i % per_layer;
-        mine += cell_face_count(L, cinfo, cl0, cl1, (uint32_t)(r % L.nx), (uint32_t)(r / L.nx), cz, ci);
+    if (cu != CU_EMPTY && X0 < L.nx && Y0 < L.ny && zhi > zlo) {
+        for (int r = 0; r < TILE_ROUNDS; ++r) {
+            const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+            if (cx >= L.nx || cy >= L.ny || cz < zlo || cz >= zhi) continue;
+            bool full; uint32_t count; uint16_t ci;
+            cell_state(S, cu, cx, cy, cz, full, count, ci);
+            if (count) mine += cell_face_count(S, cx, cy, cz, full, count);
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_tot, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+    const unsigned long long tot = block_sum(mine, &s_acc);
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
 }
 
 __device__ __forceinline__ void sort3(unsigned long long& a, unsigned long long& b, unsigned long long& c) {
@@ -115,36 +125,36 @@ __device__ __forceinline__ void sort3(unsigned long long& a, unsigned long long&
 }
 
 // emit candidate faces: key = sorted global node ids (k0 <= k1 <= k2), payload = tet * 4 + side
-__global__ void __launch_bounds__(TILE_THREADS)
-k_face_emit(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
-            const unsigned long long* __restrict__ tile_tbase, const unsigned long long* __restrict__ tile_fbase,
-            const uint16_t* __restrict__ vmask, const int32_t* __restrict__ vbase, int64_t vertex_base,
-            unsigned long long tet_base, unsigned long long* __restrict__ key_hi, unsigned long long* __restrict__ key_lo,
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_face_emit(Stuff S, const unsigned long long* __restrict__ tile_fbase, unsigned long long tet_base,
+            unsigned long long* __restrict__ key_hi, unsigned long long* __restrict__ key_lo,
             unsigned long long* __restrict__ payload) {
     __shared__ uint32_t s_scan[9];
-    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
-    const uint64_t first = per_layer * (c0 - cl0), last = per_layer * (c1 - cl0);
-    uint64_t trun = tile_tbase[blockIdx.x], frun = tile_fbase[blockIdx.x];
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        const bool owned = i >= first && i < last;
-        const uint16_t ci = owned ? cinfo[i] : (uint16_t)0;
-        const uint32_t count = ci & CI_COUNT_MASK;
-        uint32_t cx = 0, cy = 0, cz = 0, nf = 0;
-        if (count) {
-            cz = cl0 + (uint32_t)(i / per_layer);
-            const uint64_t r = i % per_layer;
-            cy = (uint32_t)(r / L.nx); cx = (uint32_t)(r % L.nx);
-            nf = cell_face_count(L, cinfo, cl0, cl1, cx, cy, cz, ci);
-        }
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    const uint8_t cu = S.cuni[blockIdx.x];
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (cu == CU_EMPTY || X0 >= L.nx || Y0 >= L.ny || zhi <= zlo) return;
+    const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
+    const uint64_t tb = S.ttbase[blockIdx.x];
+    uint64_t trun = tb, frun = tile_fbase[blockIdx.x];
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+        const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
+        bool full = false; uint32_t count = 0; uint16_t ci = 0;
+        if (owned) cell_state(S, cu, cx, cy, cz, full, count, ci);
+        const uint32_t nf = count ? cell_face_count(S, cx, cy, cz, full, count) : 0u;
         uint32_t ttot, ftot;
         const uint32_t tex = block_exscan(count, &ttot, s_scan);
         const uint32_t fex = block_exscan(nf, &ftot, s_scan);
         if (nf) {
             const Cell c = make_cell(cx, cy, cz);
-            uint64_t o = trun + tex;   // slab-local index of the cell's first output tet
+            // slab-local index of the cell's first output tet (same numbering as k_tet_emit)
+            uint64_t o = cu == CU_FULL ? tb + 5ull * (((cz - zlo) * nyt + (cy - Y0)) * nxt + (cx - X0)) : trun + tex;
             uint64_t f = frun + fex;
-            if (ci & CI_FULL) {
+            if (full) {
                 // tets 0..4 are emitted in order; only triangles on open cell faces are candidates
                 for (int ax = 0; ax < 3; ++ax)
                     for (int v = 0; v < 2; ++v) {
@@ -153,20 +163,19 @@ k_face_emit(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, con
                         const int gv = mir ? 1 - v : v;
                         int64_t ncx = cx, ncy = cy, ncz = cz;
                         (ax == 0 ? ncx : (ax == 1 ? ncy : ncz)) += gv ? 1 : -1;
-                        if (cell_is_full(L, cinfo, cl0, cl1, ncx, ncy, ncz)) continue;
+                        if (cell_is_full(S, ncx, ncy, ncz)) continue;
                         for (int k = 0; k < 2; ++k) {
                             const FaceTri ft = C_CELLFACE[ax * 2 + v][k];
                             TetNodes tn;
                             load_tet(L, c, ft.tet, tn);
-                            const int s = c.flip() ? side_after_flip(ft.side) : ft.side;
+                            const int sd = c.flip() ? side_after_flip(ft.side) : ft.side;
                             unsigned long long g[3];
 #pragma unroll
-                            for (int q = 0; q < 3; ++q)
-                                g[q] = node_global_id<unsigned long long>(L, tn, C_FACE[s][q], vmask, vbase, vertex_base);
+                            for (int q = 0; q < 3; ++q) g[q] = node_global_id<unsigned long long>(S, tn, C_FACE[sd][q]);
                             sort3(g[0], g[1], g[2]);
                             key_hi[f] = (g[0] << 32) | g[1];
                             key_lo[f] = g[2];
-                            payload[f] = ((tet_base + o + (uint64_t)ft.tet) << 2) | (unsigned long long)s;
+                            payload[f] = ((tet_base + o + (uint64_t)ft.tet) << 2) | (unsigned long long)sd;
                             ++f;
                         }
                     }
@@ -179,14 +188,13 @@ k_face_emit(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, con
                     for (int q = 0; q < to.n; ++q) {
                         unsigned long long id[4];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            id[m] = node_global_id<unsigned long long>(L, tn, to.node[q][m], vmask, vbase, vertex_base);
-                        for (int s = 0; s < 4; ++s) {
-                            unsigned long long g0 = id[C_FACE[s][0]], g1 = id[C_FACE[s][1]], g2 = id[C_FACE[s][2]];
+                        for (int m = 0; m < 4; ++m) id[m] = node_global_id<unsigned long long>(S, tn, to.node[q][m]);
+                        for (int sd = 0; sd < 4; ++sd) {
+                            unsigned long long g0 = id[C_FACE[sd][0]], g1 = id[C_FACE[sd][1]], g2 = id[C_FACE[sd][2]];
                             sort3(g0, g1, g2);
                             key_hi[f] = (g0 << 32) | g1;
                             key_lo[f] = g2;
-                            payload[f] = ((tet_base + o) << 2) | (unsigned long long)s;
+                            payload[f] = ((tet_base + o) << 2) | (unsigned long long)sd;
                             ++f;
                         }
                         ++o;
@@ -199,11 +207,11 @@ k_face_emit(Lattice L, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1, con
     }
 }
 
-__global__ void k_iota(unsigned long long* p, uint64_t n) {
+static __global__ void k_iota(unsigned long long* p, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
 }
-__global__ void k_gather(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ idx,
+static __global__ void k_gather(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ idx,
                          uint64_t n, unsigned long long* __restrict__ dst) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
@@ -211,7 +219,7 @@ __global__ void k_gather(const unsigned long long* __restrict__ src, const unsig
 
 // one thread per sorted candidate: the first element of every run of equal keys counts the run
 // and, when the length is odd, appends the run's last element (largest tet id) to the output
-__global__ void k_face_select(const unsigned long long* __restrict__ key_hi, const unsigned long long* __restrict__ key_lo,
+static __global__ void k_face_select(const unsigned long long* __restrict__ key_hi, const unsigned long long* __restrict__ key_lo,
                               const unsigned long long* __restrict__ payload,
                               const unsigned long long* __restrict__ order, uint64_t n,
                               unsigned long long* __restrict__ out_sides, unsigned long long* __restrict__ out_count) {
@@ -294,18 +302,17 @@ int compute_boundary(mc_mesh* m) {
     MC_CUDA(cudaEventCreate(&e1));
     MC_CUDA(cudaEventRecord(e0, s));
     DevBuf ftot, fbase, dtotal;
-    int rc = c->alloc((m->n_ctiles + 1) * 8, ftot);
-    if (rc == MC_OK) rc = c->alloc((m->n_ctiles + 1) * 8, fbase);
+    int rc = c->alloc((m->n_tiles + 1) * 8, ftot);
+    if (rc == MC_OK) rc = c->alloc((m->n_tiles + 1) * 8, fbase);
     if (rc == MC_OK) rc = c->alloc(4 * 8, dtotal);
     if (rc != MC_OK) return rc;
     MC_CUDA(cudaMemsetAsync(dtotal.p, 0, 32, s));
     unsigned long long* totals = (unsigned long long*)dtotal.p;
     uint64_t nf = 0;
-    if (m->n_ctiles > 0) {
-        k_face_count<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(L, m->cl0, m->cl1, m->c0, m->c1,
-                                                                     (const uint16_t*)m->d_cinfo.p,
-                                                                     (unsigned long long*)ftot.p);
-        k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)ftot.p, m->n_ctiles, (unsigned long long*)fbase.p,
+    const Stuff S = make_stuff(m);
+    if (m->n_tiles > 0) {
+        k_face_count<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)ftot.p);
+        k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)ftot.p, m->n_tiles, (unsigned long long*)fbase.p,
                                         nullptr, totals);
         c->launches += 2;
         MC_CUDA(cudaGetLastError());
@@ -327,10 +334,8 @@ int compute_boundary(mc_mesh* m) {
         if (rc == MC_OK) rc = c->alloc(nf * 8, kb);
         if (rc == MC_OK) rc = c->alloc(nf * 16, m->d_sides);
         if (rc != MC_OK) return rc;
-        k_face_emit<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
-            L, m->cl0, m->cl1, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
-            (const unsigned long long*)fbase.p, (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p,
-            (int64_t)m->vertex_base, m->tet_base, (unsigned long long*)khi.p, (unsigned long long*)klo.p,
+        k_face_emit<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(
+            S, (const unsigned long long*)fbase.p, m->tet_base, (unsigned long long*)khi.p, (unsigned long long*)klo.p,
             (unsigned long long*)pay.p);
         const unsigned nb = (unsigned)((nf + 255) / 256);
         k_iota<<<nb, 256, 0, s>>>((unsigned long long*)ia.p, nf);

@@ -46,13 +46,16 @@ struct mc_mesh {
     uint32_t flags = 0, max_bisect = 200;
     mc::Program prog;
 
-    mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vbase, d_cinfo;
-    mc::DevBuf d_ctile_tot, d_ctile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
+    mc::TileGrid g{};
+    mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo;
+    mc::DevBuf d_tflag, d_vuni, d_cuni;
+    mc::DevBuf d_ttile_tot, d_ttile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
+    const void* lower_table = nullptr;  // id table of plane c0 from the rank below (caller-owned)
+    bool tiled_sdf = false;
     mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
     mc::DevBuf d_inst_start, d_word_inst, d_dec;  // tile specialisation (mc_prune.cuh)
     uint64_t n_tiles = 0;
     double avg_pruned_words = 0;
-    uint64_t n_ctiles = 0, n_vtiles = 0;
 
     uint64_t counters[32] = {0};
     uint64_t n_verts = 0, n_cuts = 0, n_tets = 0, n_kept = 0;

@@ -1,12 +1,18 @@
 // CUDA kernels of the meshing hot path (sm_100a, f64, --fmad=false).
 // Stage map (SURVEY.md §8a -> kernel):
-//   a2  ObjectAdaptor::value over the lattice      k_sdf_field      (FP64-bound, 8 B/pt written)
-//   a6  warp_vertices                              k_warp_codes     (HBM-bound, 8 B read + 1 B written /pt)
-//   a5/a7/a9 cut_lattice, trim_spikes, exterior    k_classify_cells (HBM-bound, ~9 B read + 2 B written /cell)
+//   a2  ObjectAdaptor::value over the lattice      k_sdf_field / k_sdf_field_tiled (mc_prune.cuh)
+//   --  per-tile sign summary                      k_tile_minmax, k_tile_neighbourhood, k_cell_tile_class
+//   a6  warp_vertices                              k_warp_codes
+//   a5/a7/a9 cut_lattice, trim_spikes, exterior    k_classify_cells
 //   a10 compact (vertex numbering)                 k_vertex_count / k_vertex_emit (+ k_scan_tiles)
-//   a8  cut_edge bisection                         k_bisect_edges   (FP64-bound, O(surface))
-//   a7/a10 tet emission                            k_tet_emit       (HBM-bound, 16 B written /tet)
-//   a11 check_for_inverted_tets                    k_tet_quality
+//   a8  cut_edge bisection                         k_bisect_edges
+//   a7/a10/a11 tet emission + quality              k_tet_emit
+//
+// All stuffing kernels run one block per TS^3 tile.  A tile whose neighbourhood has one strict
+// sign takes a fast path that never reads the SDF field: exterior tiles produce nothing,
+// interior tiles produce lattice vertices / the five lattice tets of every cell with ids that
+// are pure arithmetic (vertex and tet numbering is tile-major), so the bulk of the lattice costs
+// only the bytes of its output.
 #pragma once
 #include "mc_stuffing.cuh"
 
@@ -16,20 +22,48 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
-constexpr int TILE_ITEMS = 8;
-constexpr int TILE_SIZE = TILE_THREADS * TILE_ITEMS;  // lattice points / cells per tile
+constexpr uint32_t TILE_POINTS = TS * TS * TS;
+constexpr int TILE_ROUNDS = (int)(TILE_POINTS / TILE_THREADS);
 
-// per-cell info written by k_classify_cells
+// per-tile flags
+constexpr uint8_t TF_NEG = 1, TF_POS = 2, TF_HASWARP = 4;
+constexpr uint8_t VU_ACTIVE = 0, VU_NEG = 1, VU_POS = 2;    // point tile: 27-neighbourhood all NEG / all POS
+constexpr uint8_t CU_ACTIVE = 0, CU_FULL = 1, CU_EMPTY = 2; // cell tile: every cell emits its 5 lattice tets / nothing
+// per-cell info written by k_classify_cells (ACTIVE cell tiles only)
 constexpr uint16_t CI_COUNT_MASK = 0x000f;
 constexpr uint16_t CI_REMOVED_SHIFT = 4;   // 5 bits: tet t dropped by the exterior test
 constexpr uint16_t CI_FULL = 1u << 9;      // all five lattice tets emitted untouched
-// per-vertex mask written by k_vertex_count
+// per-vertex mask written by k_vertex_count (ACTIVE point tiles only)
 constexpr uint16_t VM_CUT_MASK = 0x01ff;   // bit s: the edge along canonical direction s is cut
 constexpr uint16_t VM_USED = 1u << 15;     // the lattice vertex itself is in the output
+
+// everything the stuffing kernels need about one slab
+struct Stuff {
+    Lattice L;
+    TileGrid g;
+    uint32_t c0, c1;      // owned cell layers [c0, c1)
+    uint32_t cl0, cl1;    // classified cell layers (halo layers only contribute "used" flags)
+    uint32_t oz0, oz1;    // owned point planes [oz0, oz1]
+    uint32_t wz0, wz1;    // planes with warp codes
+    uint8_t* tflag;       // [tiles] TF_*
+    uint8_t* vuni;        // [tiles] VU_*
+    uint8_t* cuni;        // [tiles] CU_*
+    uint16_t* vmask;      // [points] VM_*
+    uint16_t* vloc;       // [points] offset of the vertex's first output inside its tile
+    uint16_t* cinfo;      // [cells of classified layers] CI_*
+    const unsigned long long* tvbase;  // [tiles] first output vertex of the tile (slab-local)
+    const unsigned long long* ttbase;  // [tiles] first output tet of the tile (slab-local)
+    const unsigned long long* lower_table;  // id table of plane c0 from the rank below, or null
+    long long vertex_base;             // global id of this slab's first vertex
+};
+
+__device__ __forceinline__ size_t cidx(const Stuff& S, uint32_t cx, uint32_t cy, uint32_t cz) {
+    return ((size_t)(cz - S.cl0) * S.L.ny + cy) * S.L.nx + cx;
+}
 
 // ---------------------------------------------------------------------------------------
 // block-wide exclusive scan of one uint32 per thread (TILE_THREADS threads); returns the
@@ -61,9 +95,20 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* total, ui
     return smem[wid] + inc - v;
 }
 
+// block-wide sum of one uint64 per thread (every thread gets it)
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* s_acc) {
+    if (threadIdx.x == 0) *s_acc = 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0u && v) atomicAdd(s_acc, v);
+    __syncthreads();
+    return *s_acc;
+}
+
 // ---------------------------------------------------------------------------------------
-// a2: the lattice SDF field.  Persistent blocks; the program is staged once per block into
-// shared memory; each warp evaluates WX x WY points of one z-plane per step with a
+// a2: the lattice SDF field, plain evaluator.  Persistent blocks; the program is staged once per
+// block into shared memory; each warp evaluates WX x WY points of one z-plane per step with a
 // warp-uniform program counter and writes them with coalesced stores.
 template <int WX, int WY>
 __global__ void __launch_bounds__(512)
@@ -90,7 +135,7 @@ k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict_
         const uint32_t X = tx * WX + lx, Y = ty * WY + ly;
         const bool inside = X < L.NX && Y < L.NY;
         // out-of-range lanes evaluate a clamped point so that the warp stays converged
-        const uint32_t Xc = inside ? X : (X < L.NX ? X : L.NX - 1), Yc = Y < L.NY ? Y : L.NY - 1;
+        const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
         const double v = vm_eval<true>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z));
         if (inside) phi_out[pidx(L, X, Y, Z)] = v;
     }
@@ -98,7 +143,7 @@ k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict_
 
 // ObjectAdaptor::value for arbitrary points (src/main.rs:33-35,95): one point per thread
 static __global__ void k_eval_points(const uint64_t* __restrict__ prog, const double* __restrict__ pts, uint64_t n,
-                              double* __restrict__ out) {
+                                     double* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t ic = i < n ? i : (n - 1);
     const double v = vm_eval<true>(prog, pts[3 * ic], pts[3 * ic + 1], pts[3 * ic + 2]);
@@ -106,50 +151,138 @@ static __global__ void k_eval_points(const uint64_t* __restrict__ prog, const do
 }
 
 // ---------------------------------------------------------------------------------------
-// a6: warp codes for the vertices of planes [z0, z1]
-static __global__ void __launch_bounds__(256)
-k_warp_codes(Lattice L, uint32_t z0, uint32_t z1, unsigned long long* __restrict__ counters, uint32_t own_z0,
-             uint32_t own_z1) {
-    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
-    const uint64_t n = per_plane * (z1 - z0 + 1);
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t code = 0u;
-    bool owned = false;
-    if (i < n) {
-        const uint32_t Z = z0 + (uint32_t)(i / per_plane);
-        const uint64_t r = i % per_plane;
-        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
-        code = warp_eval(L, X, Y, Z);
-        L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
-        owned = Z >= own_z0 && Z <= own_z1;
+// per-tile sign summary of the raw field: TF_NEG (max < 0), TF_POS (min > 0)
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_tile_minmax(Stuff S) {
+    __shared__ double s_lo[TILE_THREADS / 32], s_hi[TILE_THREADS / 32];
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo = INF, hi = -INF;
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t X = X0 + (j & 15u), Y = Y0 + ((j >> 4) & 15u), Z = Z0 + (j >> 8);
+        if (X < L.NX && Y < L.NY && Z <= L.pz1) {
+            const double v = L.phi[pidx(L, X, Y, Z)];
+            if (v != v) { lo = -INF; hi = INF; }  // NaN: neither sign
+            lo = fmin(lo, v); hi = fmax(hi, v);
+        }
     }
-    const unsigned b = __ballot_sync(0xffffffffu, code != 0u && owned);
-    if (b && (threadIdx.x & 31u) == 0u) atomicAdd(&counters[CN_WARPED], (unsigned long long)__popc(b));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31u) == 0u) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TILE_THREADS / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+        S.tflag[blockIdx.x] = (uint8_t)((hi < 0.0 ? TF_NEG : 0) | (lo > 0.0 ? TF_POS : 0));
+    }
+}
+
+// point tiles: 27-neighbourhood uniformly negative / positive?
+static __global__ void k_tile_neighbourhood(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
+    uint8_t all = TF_NEG | TF_POS;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = tix + dx, y = tiy + dy, z = tiz + dz;
+                if (x < 0 || y < 0 || z < 0 || x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) continue;
+                all &= S.tflag[((size_t)z * S.g.nty + y) * S.g.ntx + x];
+            }
+    const uint8_t u = (all & TF_NEG) ? VU_NEG : ((all & TF_POS) ? VU_POS : VU_ACTIVE);
+    S.vuni[t] = u;
+    if (u == VU_ACTIVE) atomicAdd(&counters[CN_ACTIVE_VTILES], 1ull);
+}
+
+// cell tiles: the 8 tiles holding the corners are all negative and un-warped (every cell emits
+// its five lattice tets) / all positive (nothing is kept)?
+static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
+    uint8_t all = TF_NEG | TF_POS, any = 0;
+    for (int dz = 0; dz <= 1; ++dz)
+        for (int dy = 0; dy <= 1; ++dy)
+            for (int dx = 0; dx <= 1; ++dx) {
+                const int x = tix + dx, y = tiy + dy, z = tiz + dz;
+                if (x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) continue;
+                const uint8_t f = S.tflag[((size_t)z * S.g.nty + y) * S.g.ntx + x];
+                all &= f; any |= f;
+            }
+    const uint8_t u = ((all & TF_NEG) && !(any & TF_HASWARP)) ? CU_FULL : ((all & TF_POS) ? CU_EMPTY : CU_ACTIVE);
+    S.cuni[t] = u;
+    if (u == CU_ACTIVE) atomicAdd(&counters[CN_ACTIVE_CTILES], 1ull);
 }
 
 // ---------------------------------------------------------------------------------------
-// a5/a7/a9: classify the five tets of every cell of layers [cl0, cl1): output-tet count,
-// exterior-test results, "full cell" flag; mark zero-valued vertices that appear in the
-// output; per-tile totals (low 32 bits: output tets, high 32 bits: kept lattice tets) for the
-// cells of the owned layers [c0, c1).
+// a6: warp codes (only tiles whose neighbourhood is not of one strict sign can have any)
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_classify_cells(Lattice L, const uint64_t* __restrict__ prog, uint32_t cl0, uint32_t cl1, uint32_t c0, uint32_t c1,
-                 uint16_t* __restrict__ cinfo, unsigned long long* __restrict__ tile_tot,
+k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
+    if (S.vuni[blockIdx.x] != VU_ACTIVE) return;
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    unsigned warped_any = 0, warped_owned = 0;
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t X = X0 + (j & 15u), Y = Y0 + ((j >> 4) & 15u), Z = Z0 + (j >> 8);
+        if (X < L.NX && Y < L.NY && Z >= S.wz0 && Z <= S.wz1) {
+            const uint32_t code = warp_eval(L, X, Y, Z);
+            if (code) {
+                L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
+                warped_any = 1;
+                warped_owned += (Z >= S.oz0 && Z <= S.oz1) ? 1u : 0u;
+            }
+        }
+    }
+    // tflag bytes are updated through their aligned 32-bit word
+    if (__any_sync(0xffffffffu, warped_any) && (threadIdx.x & 31u) == 0u)
+        atomicOr((unsigned int*)(S.tflag + (blockIdx.x & ~3u)), (unsigned int)TF_HASWARP << (8u * (blockIdx.x & 3u)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warped_owned += __shfl_xor_sync(0xffffffffu, warped_owned, o);
+    if (warped_owned && (threadIdx.x & 31u) == 0u) atomicAdd(&counters[CN_WARPED], (unsigned long long)warped_owned);
+}
+
+// ---------------------------------------------------------------------------------------
+// a5/a7/a9: classify the five tets of every cell: output-tet count, exterior-test results,
+// "full cell" flag; mark zero-valued vertices that appear in the output.  Per-tile totals
+// (low 32 bits: output tets, high 32 bits: kept lattice tets) count owned cells only.
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long* __restrict__ tile_tot,
                  unsigned long long* __restrict__ counters) {
-    __shared__ unsigned long long s_tot;
-    if (threadIdx.x == 0) s_tot = 0ull;
-    __syncthreads();
-    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
-    const uint64_t ncell = per_layer * (cl1 - cl0);
+    __shared__ unsigned long long s_acc;
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    const uint8_t cu = S.cuni[blockIdx.x];
+    if (cu != CU_ACTIVE) {
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0ull;
+            if (cu == CU_FULL && X0 < L.nx && Y0 < L.ny) {
+                const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+                if (zhi > zlo) {
+                    const unsigned long long n =
+                        (unsigned long long)min(TS, L.nx - X0) * min(TS, L.ny - Y0) * (zhi - zlo) * 5ull;
+                    tot = n | (n << 32);
+                }
+            }
+            tile_tot[blockIdx.x] = tot;
+        }
+        return;
+    }
     uint32_t my_out = 0, my_kept = 0;
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        if (i >= ncell) break;
-        const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
-        const uint64_t r = i % per_layer;
-        const uint32_t cy = (uint32_t)(r / L.nx), cx = (uint32_t)(r % L.nx);
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+        if (cx >= L.nx || cy >= L.ny || cz < S.cl0 || cz >= S.cl1) continue;
         const Cell c = make_cell(cx, cy, cz);
-        const bool own = cz >= c0 && cz < c1;  // halo layers only contribute flags
+        const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
         // corner signs decide the two trivial classes
         bool all_neg = true, all_pos_raw = true;
 #pragma unroll
@@ -190,16 +323,11 @@ k_classify_cells(Lattice L, const uint64_t* __restrict__ prog, uint32_t cl0, uin
             }
             full = untouched && count == 5;
         }
-        cinfo[i] = (uint16_t)(count | (removed_bits << CI_REMOVED_SHIFT) | (full ? CI_FULL : 0));
+        S.cinfo[cidx(S, cx, cy, cz)] = (uint16_t)(count | (removed_bits << CI_REMOVED_SHIFT) | (full ? CI_FULL : 0));
         if (own) { my_out += count; my_kept += kept; }
     }
-    // block total
-    unsigned long long v = (unsigned long long)my_out | ((unsigned long long)my_kept << 32);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31u) == 0u && v) atomicAdd(&s_tot, v);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+    const unsigned long long tot = block_sum((unsigned long long)my_out | ((unsigned long long)my_kept << 32), &s_acc);
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -276,82 +404,119 @@ __device__ __forceinline__ uint16_t vertex_mask(const Lattice& L, uint32_t X, ui
     return m;
 }
 
+// owned points of a tile: x, y extents and the owned z range [zlo, zhi) (may be empty)
+struct TileBox { uint32_t X0, Y0, Z0, nxt, nyt, zlo, zhi; };
+__device__ __forceinline__ TileBox tile_box(const Stuff& S, uint64_t t) {
+    TileBox b;
+    tile_origin(S.g, t, b.X0, b.Y0, b.Z0);
+    b.nxt = min(TS, S.L.NX - b.X0);
+    b.nyt = min(TS, S.L.NY - b.Y0);
+    b.zlo = max(b.Z0, S.oz0);
+    b.zhi = min(b.Z0 + TS, S.oz1 + 1);
+    if (b.zhi < b.zlo) b.zhi = b.zlo;
+    return b;
+}
+
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_vertex_count(Lattice L, uint32_t oz0, uint32_t oz1, uint16_t* __restrict__ vmask,
-               unsigned long long* __restrict__ tile_tot) {
-    __shared__ unsigned long long s_tot;
-    if (threadIdx.x == 0) s_tot = 0ull;
-    __syncthreads();
-    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
-    const uint64_t n = per_plane * (oz1 - oz0 + 1);
+k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
+    __shared__ unsigned long long s_acc;
+    const Lattice& L = S.L;
+    const TileBox b = tile_box(S, blockIdx.x);
+    const uint8_t vu = S.vuni[blockIdx.x];
+    if (vu != VU_ACTIVE) {
+        if (threadIdx.x == 0)
+            tile_tot[blockIdx.x] = vu == VU_NEG ? (unsigned long long)b.nxt * b.nyt * (b.zhi - b.zlo) : 0ull;
+        return;
+    }
     unsigned long long mine = 0ull;
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        if (i >= n) break;
-        const uint32_t Z = oz0 + (uint32_t)(i / per_plane);
-        const uint64_t r = i % per_plane;
-        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t X = b.X0 + (j & 15u), Y = b.Y0 + ((j >> 4) & 15u), Z = b.Z0 + (j >> 8);
+        if (X >= L.NX || Y >= L.NY || Z < b.zlo || Z >= b.zhi) continue;
         const uint16_t m = vertex_mask(L, X, Y, Z);
-        vmask[pidx(L, X, Y, Z)] = m;
+        S.vmask[pidx(L, X, Y, Z)] = m;
         const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
         mine += (unsigned long long)(ncut + ((m & VM_USED) ? 1u : 0u)) | ((unsigned long long)ncut << 32);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(&s_tot, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = s_tot;
+    const unsigned long long tot = block_sum(mine, &s_acc);
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
 }
 
-// a10 (vertices), pass 2: number the output vertices (lattice vertex first, then its cut
-// edges in slot order), write the coordinates of the lattice vertices (warped where
+// global id of a lattice vertex's first output + its mask.  Interior tiles are pure arithmetic.
+__device__ __forceinline__ long long vertex_gid(const Stuff& S, uint32_t X, uint32_t Y, uint32_t Z, uint16_t& mask) {
+    const Lattice& L = S.L;
+    if (S.lower_table != nullptr && Z == S.c0) {
+        const unsigned long long e = S.lower_table[(size_t)Y * L.NX + X];
+        mask = (uint16_t)(e & 0xffffull);
+        return (long long)(e >> 16);
+    }
+    const uint32_t t = tile_of(S.g, X, Y, Z);
+    if (S.vuni[t] == VU_NEG) {
+        const TileBox b = tile_box(S, t);
+        mask = VM_USED;
+        return S.vertex_base + (long long)S.tvbase[t] +
+               (long long)(((Z - b.zlo) * b.nyt + (Y - b.Y0)) * b.nxt + (X - b.X0));
+    }
+    const size_t pi = pidx(L, X, Y, Z);
+    mask = S.vmask[pi];
+    return S.vertex_base + (long long)S.tvbase[t] + (long long)S.vloc[pi];
+}
+// id of the cut vertex on the edge leaving the owner along canonical slot s
+__device__ __forceinline__ long long cut_vertex_id(long long owner_base, uint16_t owner_mask, int s) {
+    return owner_base + ((owner_mask & VM_USED) ? 1 : 0) + __popc(owner_mask & ((1u << s) - 1u));
+}
+
+// a10 (vertices), pass 2: number the output vertices tile by tile (lattice vertex first, then
+// its cut edges in slot order), write the coordinates of the lattice vertices (warped where
 // applicable) and append the cut edges to the bisection work list.
-// vbase holds the slab-local id (signed 32-bit offset from `vertex_base`).
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_vertex_emit(Lattice L, uint32_t oz0, uint32_t oz1, const uint16_t* __restrict__ vmask,
-              const unsigned long long* __restrict__ tile_vbase, const unsigned long long* __restrict__ tile_cbase,
-              int32_t* __restrict__ vbase, double* __restrict__ coords, unsigned long long* __restrict__ cutlist) {
+k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double* __restrict__ coords,
+              unsigned long long* __restrict__ cutlist) {
     __shared__ uint32_t s_scan[9];
-    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
-    const uint64_t n = per_plane * (oz1 - oz0 + 1);
-    uint64_t vrun = tile_vbase[blockIdx.x], crun = tile_cbase[blockIdx.x];
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        uint16_t m = 0;
-        uint32_t X = 0, Y = 0, Z = 0;
-        size_t pi = 0;
-        if (i < n) {
-            Z = oz0 + (uint32_t)(i / per_plane);
-            const uint64_t r = i % per_plane;
-            Y = (uint32_t)(r / L.NX); X = (uint32_t)(r % L.NX);
-            pi = pidx(L, X, Y, Z);
-            m = vmask[pi];
+    const Lattice& L = S.L;
+    const TileBox b = tile_box(S, blockIdx.x);
+    const uint8_t vu = S.vuni[blockIdx.x];
+    if (vu == VU_POS || b.zhi == b.zlo) return;
+    const uint64_t vb = S.tvbase[blockIdx.x];
+    if (vu == VU_NEG) {
+        // every owned point is an un-warped output vertex: id = tile base + linear index
+        const uint32_t n = b.nxt * b.nyt * (b.zhi - b.zlo);
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_THREADS) {
+            const uint32_t x = j % b.nxt, y = (j / b.nxt) % b.nyt, z = j / (b.nxt * b.nyt);
+            double* o = coords + 3 * (vb + j);
+            o[0] = lat_x(L, b.X0 + x); o[1] = lat_y(L, b.Y0 + y); o[2] = lat_z(L, b.zlo + z);
         }
+        return;
+    }
+    uint32_t vrun = 0;
+    uint64_t crun = tile_cbase[blockIdx.x];
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t X = b.X0 + (j & 15u), Y = b.Y0 + ((j >> 4) & 15u), Z = b.Z0 + (j >> 8);
+        const bool in = X < L.NX && Y < L.NY && Z >= b.zlo && Z < b.zhi;
+        size_t pi = 0;
+        uint16_t m = 0;
+        if (in) { pi = pidx(L, X, Y, Z); m = S.vmask[pi]; }
         const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
         const uint32_t nout = ncut + ((m & VM_USED) ? 1u : 0u);
-        uint32_t vtot, ctot;
-        const uint32_t vex = block_exscan(nout, &vtot, s_scan);
-        const uint32_t cex = block_exscan(ncut, &ctot, s_scan);
-        if (i < n) {
-            const uint64_t id0 = vrun + vex;
-            vbase[pi] = (int32_t)id0;
+        uint32_t tot;
+        const uint32_t ex = block_exscan(nout | (ncut << 16), &tot, s_scan);
+        if (in) {
+            const uint32_t loc = vrun + (ex & 0xffffu);
+            S.vloc[pi] = (uint16_t)loc;
             if (m & VM_USED) {
                 double p[3];
                 warped_pos(L, X, Y, Z, p);
-                coords[3 * id0] = p[0]; coords[3 * id0 + 1] = p[1]; coords[3 * id0 + 2] = p[2];
+                double* o = coords + 3 * (vb + loc);
+                o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
             }
-            uint64_t ci = crun + cex;
+            uint64_t ci = crun + (ex >> 16);
             for (int s = 0; s < 9; ++s)
                 if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
         }
-        vrun += vtot;
-        crun += ctot;
+        vrun += tot & 0xffffu;
+        crun += tot >> 16;
     }
-}
-
-// slab-local id of the cut vertex on the edge leaving `owner` along canonical slot s
-__device__ __forceinline__ int64_t cut_vertex_id(int32_t owner_base, uint16_t owner_mask, int s) {
-    return (int64_t)owner_base + ((owner_mask & VM_USED) ? 1 : 0) + __popc(owner_mask & ((1u << s) - 1u));
 }
 
 // a8: cut_edge — bisection of the real SDF between the positive and the negative end of
@@ -359,10 +524,10 @@ __device__ __forceinline__ int64_t cut_vertex_id(int32_t owner_base, uint16_t ow
 // One edge per thread; lanes that have converged idle until the warp is done so that the
 // evaluator stays warp-uniform.
 static __global__ void __launch_bounds__(256)
-k_bisect_edges(Lattice L, const uint64_t* __restrict__ prog, const unsigned long long* __restrict__ cutlist,
-               uint64_t ncut, const uint16_t* __restrict__ vmask, const int32_t* __restrict__ vbase,
-               double error_threshold, uint32_t max_iters, double* __restrict__ coords,
+k_bisect_edges(Stuff S, const uint64_t* __restrict__ prog, const unsigned long long* __restrict__ cutlist,
+               uint64_t ncut, double error_threshold, uint32_t max_iters, double* __restrict__ coords,
                unsigned long long* __restrict__ counters) {
+    const Lattice& L = S.L;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < ncut;
     const unsigned long long e = cutlist[active ? i : (ncut - 1)];
@@ -402,78 +567,15 @@ k_bisect_edges(Lattice L, const uint64_t* __restrict__ prog, const unsigned long
         }
     }
     if (active) {
-        const int64_t id = cut_vertex_id(vbase[pi], vmask[pi], s);
+        uint16_t mask;
+        const long long base = vertex_gid(S, X, Y, Z, mask);
+        const long long id = cut_vertex_id(base, mask, s) - S.vertex_base;
         coords[3 * id] = cx; coords[3 * id + 1] = cy; coords[3 * id + 2] = cz;
     }
     unsigned long long it64 = active ? iters : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) it64 += __shfl_xor_sync(0xffffffffu, it64, o);
     if ((threadIdx.x & 31u) == 0u && it64) atomicAdd(&counters[CN_BISECT_ITERS], it64);
-}
-
-// ---------------------------------------------------------------------------------------
-// a7/a10: emit the output tets of the owned cells.  Ids written are global
-// (vertex_base + slab-local id).
-template <typename IndexT>
-__device__ __forceinline__ IndexT node_global_id(const Lattice& L, const TetNodes& tn, int code,
-                                                 const uint16_t* __restrict__ vmask,
-                                                 const int32_t* __restrict__ vbase, int64_t vertex_base) {
-    if (code < 4) return (IndexT)(vertex_base + (int64_t)vbase[pidx(L, tn.X[code], tn.Y[code], tn.Z[code])]);
-    const int i = (code - 4) >> 2, j = (code - 4) & 3;
-    const int dx = (int)tn.X[j] - (int)tn.X[i], dy = (int)tn.Y[j] - (int)tn.Y[i], dz = (int)tn.Z[j] - (int)tn.Z[i];
-    int d = dir_index(dx, dy, dz);
-    int owner = i;
-    if (d >= 9) { d -= 9; owner = j; }
-    const size_t pi = pidx(L, tn.X[owner], tn.Y[owner], tn.Z[owner]);
-    return (IndexT)(vertex_base + cut_vertex_id(vbase[pi], vmask[pi], d));
-}
-
-template <typename IndexT>
-__global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit(Lattice L, uint32_t cl0, uint32_t c0, uint32_t c1, const uint16_t* __restrict__ cinfo,
-           const unsigned long long* __restrict__ tile_tbase, const uint16_t* __restrict__ vmask,
-           const int32_t* __restrict__ vbase, int64_t vertex_base, IndexT* __restrict__ tets) {
-    __shared__ uint32_t s_scan[9];
-    const uint64_t per_layer = (uint64_t)L.nx * L.ny;
-    const uint64_t first = per_layer * (c0 - cl0);        // owned cells inside the classified range
-    const uint64_t last = per_layer * (c1 - cl0);
-    uint64_t trun = tile_tbase[blockIdx.x];
-    for (int it = 0; it < TILE_ITEMS; ++it) {
-        const uint64_t i = (uint64_t)blockIdx.x * TILE_SIZE + (uint64_t)it * TILE_THREADS + threadIdx.x;
-        const bool owned = i >= first && i < last;
-        const uint16_t ci = owned ? cinfo[i] : (uint16_t)0;
-        const uint32_t count = ci & CI_COUNT_MASK;
-        uint32_t ttot;
-        const uint32_t tex = block_exscan(count, &ttot, s_scan);
-        if (count) {
-            const uint32_t cz = cl0 + (uint32_t)(i / per_layer);
-            const uint64_t r = i % per_layer;
-            const uint32_t cy = (uint32_t)(r / L.nx), cx = (uint32_t)(r % L.nx);
-            const Cell c = make_cell(cx, cy, cz);
-            uint64_t o = trun + tex;
-            for (int t = 0; t < 5; ++t) {
-                TetNodes tn;
-                load_tet(L, c, t, tn);
-                TetOut to;
-                if (ci & CI_FULL) {
-                    to.n = 1;
-                    to.node[0][0] = 0; to.node[0][1] = 1; to.node[0][2] = 2; to.node[0][3] = 3;
-                } else {
-                    classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
-                }
-                for (int q = 0; q < to.n; ++q) {
-                    IndexT id[4];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m)
-                        id[m] = node_global_id<IndexT>(L, tn, to.node[q][m], vmask, vbase, vertex_base);
-                    IndexT* dst = tets + 4 * o;
-                    dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
-                    ++o;
-                }
-            }
-        }
-        trun += ttot;
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -517,7 +619,7 @@ __device__ __forceinline__ void tet_quality(const double a[3], const double b[3]
 
 // per-tet quality for explicit arrays (mc_tet_quality)
 static __global__ void k_tet_quality_arrays(const double* __restrict__ coords, const unsigned long long* __restrict__ tets,
-                                     uint64_t nt, double* __restrict__ vol, double* __restrict__ ar) {
+                                            uint64_t nt, double* __restrict__ vol, double* __restrict__ ar) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     double p[4][3];
@@ -528,64 +630,159 @@ static __global__ void k_tet_quality_arrays(const double* __restrict__ coords, c
     tet_quality(p[0], p[1], p[2], p[3], vol[i], ar[i]);
 }
 
-// check_for_inverted_tets over the emitted mesh: min / max aspect ratio, inverted count
-// (tessellate3d/src/lib.rs:400-418).  Aspect ratios are >= 0, so their bit patterns order
-// like unsigned integers.
-template <typename IndexT>
-__global__ void __launch_bounds__(256)
-k_tet_quality(const double* __restrict__ coords, const IndexT* __restrict__ tets, uint64_t nt, int64_t vertex_base,
-              unsigned long long* __restrict__ counters) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double armin = 1.0, armax = 0.0;
-    unsigned inv = 0;
-    if (i < nt) {
-        double p[4][3];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            const int64_t id = (int64_t)tets[4 * i + n] - vertex_base;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) p[n][k] = coords[3 * id + k];
-        }
+struct QualityAcc {
+    double armin, armax;
+    unsigned inverted;
+    __device__ __forceinline__ void add(const double a[3], const double b[3], const double c[3], const double d[3]) {
         double vol, ar;
-        tet_quality(p[0], p[1], p[2], p[3], vol, ar);
-        if (vol <= 0.0) inv = 1;
-        armin = fmin(armin, ar);
+        tet_quality(a, b, c, d, vol, ar);
+        if (vol <= 0.0) ++inverted;
+        armin = fmin(armin, ar);  // Float::min / max ignore NaN like fmin / fmax
         armax = fmax(armax, ar);
     }
+};
+
+// ---------------------------------------------------------------------------------------
+// a7/a10/a11: emit the output tets of the owned cells, tile by tile, with global vertex ids, and
+// accumulate check_for_inverted_tets' statistics (min / max aspect ratio, inverted count).
+template <typename IndexT>
+__device__ __forceinline__ IndexT node_global_id(const Stuff& S, const TetNodes& tn, int code) {
+    uint16_t mask;
+    if (code < 4) return (IndexT)vertex_gid(S, tn.X[code], tn.Y[code], tn.Z[code], mask);
+    const int i = (code - 4) >> 2, j = (code - 4) & 3;
+    const int dx = (int)tn.X[j] - (int)tn.X[i], dy = (int)tn.Y[j] - (int)tn.Y[i], dz = (int)tn.Z[j] - (int)tn.Z[i];
+    int d = dir_index(dx, dy, dz);
+    int owner = i;
+    if (d >= 9) { d -= 9; owner = j; }
+    const long long base = vertex_gid(S, tn.X[owner], tn.Y[owner], tn.Z[owner], mask);
+    return (IndexT)cut_vertex_id(base, mask, d);
+}
+
+template <typename IndexT, bool QUALITY>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords,
+           unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_scan[9];
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    const uint8_t cu = S.cuni[blockIdx.x];
+    if (cu == CU_EMPTY || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    const uint64_t tb = S.ttbase[blockIdx.x];
+    QualityAcc qa = {1.0, 0.0, 0u};
+    if (cu == CU_FULL) {
+        constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
+        const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
+        const uint32_t n = nxt * nyt * (zhi - zlo);
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_THREADS) {
+            const uint32_t cx = X0 + j % nxt, cy = Y0 + (j / nxt) % nyt, cz = zlo + j / (nxt * nyt);
+            const Cell c = make_cell(cx, cy, cz);
+            const bool flip = c.flip();
+            IndexT id[8];
+            double pos[8][3];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        armin = fmin(armin, __shfl_xor_sync(0xffffffffu, armin, o));
-        armax = fmax(armax, __shfl_xor_sync(0xffffffffu, armax, o));
-        inv += __shfl_xor_sync(0xffffffffu, inv, o);
+            for (int k = 0; k < 8; ++k) {
+                uint32_t X, Y, Z;
+                corner_xyz(c, k, X, Y, Z);
+                uint16_t mask;
+                id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
+                if (QUALITY) { pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z); }
+            }
+            IndexT* dst = tets + 4 * (tb + 5ull * j);
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                // nodes 0 and 1 swapped when the cell is mirrored an odd number of times
+                dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
+                dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
+                dst[4 * t + 2] = id[T[t][2]];
+                dst[4 * t + 3] = id[T[t][3]];
+                if (QUALITY) {
+                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
+                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
+                }
+            }
+        }
+    } else {
+        uint64_t trun = tb;
+        for (int r = 0; r < TILE_ROUNDS; ++r) {
+            const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+            const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
+            const uint16_t ci = owned ? S.cinfo[cidx(S, cx, cy, cz)] : (uint16_t)0;
+            const uint32_t count = ci & CI_COUNT_MASK;
+            uint32_t ttot;
+            const uint32_t tex = block_exscan(count, &ttot, s_scan);
+            if (count) {
+                const Cell c = make_cell(cx, cy, cz);
+                uint64_t o = trun + tex;
+                for (int t = 0; t < 5; ++t) {
+                    TetNodes tn;
+                    load_tet(L, c, t, tn);
+                    TetOut to;
+                    if (ci & CI_FULL) {
+                        to.n = 1;
+                        to.node[0][0] = 0; to.node[0][1] = 1; to.node[0][2] = 2; to.node[0][3] = 3;
+                    } else {
+                        classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+                    }
+                    for (int q = 0; q < to.n; ++q) {
+                        IndexT id[4];
+                        double pos[4][3];
+                        bool have_pos = true;
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int code = to.node[q][m];
+                            id[m] = node_global_id<IndexT>(S, tn, code);
+                            if (QUALITY) {
+                                if (code < 4) {
+                                    warped_pos(L, tn.X[code], tn.Y[code], tn.Z[code], pos[m]);
+                                } else {
+                                    const long long lid = (long long)id[m] - S.vertex_base;
+                                    if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
+                                    else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
+                                }
+                            }
+                        }
+                        IndexT* dst = tets + 4 * o;
+                        dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
+                        if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
+                        ++o;
+                    }
+                }
+            }
+            trun += ttot;
+        }
     }
-    if ((threadIdx.x & 31u) == 0u) {
-        if (inv) atomicAdd(&counters[CN_INVERTED], (unsigned long long)inv);
-        const unsigned long long bmin = (unsigned long long)__double_as_longlong(armin);
-        const unsigned long long bmax = (unsigned long long)__double_as_longlong(armax);
-        if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
-        if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
+    if (QUALITY) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));
+            qa.armax = fmax(qa.armax, __shfl_xor_sync(0xffffffffu, qa.armax, o));
+            qa.inverted += __shfl_xor_sync(0xffffffffu, qa.inverted, o);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            // aspect ratios are >= 0, so their bit patterns order like unsigned integers
+            if (qa.inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)qa.inverted);
+            const unsigned long long bmin = (unsigned long long)__double_as_longlong(qa.armin);
+            const unsigned long long bmax = (unsigned long long)__double_as_longlong(qa.armax);
+            if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
+            if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
+        }
     }
 }
 
-// import the id table of a plane owned by the rank below (multi-GPU)
-static __global__ void k_import_plane(Lattice L, uint32_t Z, const unsigned long long* __restrict__ table, int64_t vertex_base,
-                               uint16_t* __restrict__ vmask, int32_t* __restrict__ vbase) {
-    const uint64_t n = (uint64_t)L.NX * L.NY;
+// id table of the plane z = Z for the rank above: (global id of the vertex's first output << 16) | mask
+static __global__ void k_export_plane(Stuff S, uint32_t Z, unsigned long long* __restrict__ table) {
+    const uint64_t n = (uint64_t)S.L.NX * S.L.NY;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long e = table[i];
-    const size_t pi = (size_t)(Z - L.pz0) * n + i;
-    vmask[pi] = (uint16_t)(e & 0xffffull);
-    vbase[pi] = (int32_t)((int64_t)(e >> 16) - vertex_base);
-}
-static __global__ void k_export_plane(Lattice L, uint32_t Z, const uint16_t* __restrict__ vmask,
-                               const int32_t* __restrict__ vbase, int64_t vertex_base,
-                               unsigned long long* __restrict__ table) {
-    const uint64_t n = (uint64_t)L.NX * L.NY;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t pi = (size_t)(Z - L.pz0) * n + i;
-    table[i] = ((unsigned long long)(vertex_base + (int64_t)vbase[pi]) << 16) | (unsigned long long)vmask[pi];
+    const uint32_t Y = (uint32_t)(i / S.L.NX), X = (uint32_t)(i % S.L.NX);
+    uint16_t mask = 0;
+    long long base = 0;
+    if (S.vuni[tile_of(S.g, X, Y, Z)] != VU_POS) base = vertex_gid(S, X, Y, Z, mask);
+    table[i] = ((unsigned long long)base << 16) | (unsigned long long)mask;
 }
 
 // DADD + DMUL throughput probe (no FMA): 8 independent chains per thread

@@ -24,6 +24,23 @@ struct Lattice {
     uint8_t* wcode;                  // bits 0..6 warp code (0 = not warped), bit 7 = zero-vertex used
 };
 
+// The lattice is processed in tiles of TS^3 points; tile (i,j,k) also names the TS^3 CELLS whose
+// lowest corner lies in it.  Tiles are laid out x fastest over the stored planes.
+constexpr uint32_t TS = 16;
+struct TileGrid {
+    uint32_t ntx, nty, ntz;  // tiles per axis
+    uint32_t z0;             // first stored plane (= Lattice::pz0)
+};
+__device__ __forceinline__ uint32_t tile_of(const TileGrid& g, uint32_t X, uint32_t Y, uint32_t Z) {
+    return (((Z - g.z0) / TS) * g.nty + Y / TS) * g.ntx + X / TS;
+}
+__device__ __forceinline__ void tile_origin(const TileGrid& g, uint64_t t, uint32_t& X0, uint32_t& Y0, uint32_t& Z0) {
+    X0 = (uint32_t)(t % g.ntx) * TS;
+    const uint64_t r = t / g.ntx;
+    Y0 = (uint32_t)(r % g.nty) * TS;
+    Z0 = g.z0 + (uint32_t)(r / g.nty) * TS;
+}
+
 __device__ __forceinline__ size_t pidx(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
     return ((size_t)(Z - L.pz0) * L.NY + Y) * L.NX + X;
 }

@@ -70,8 +70,9 @@ void mc_ctx::trim() {
 
 static void mesh_release_all(mc_mesh* m) {
     mc_ctx* c = m->ctx;
-    DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vbase, &m->d_cinfo, &m->d_ctile_tot,
-                      &m->d_ctile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
+    DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vloc, &m->d_cinfo, &m->d_ttile_tot,
+                      &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
+                      &m->d_tflag, &m->d_vuni, &m->d_cuni,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
                       &m->d_inst_start, &m->d_word_inst, &m->d_dec};
     for (DevBuf* b : bufs) c->release(*b);
@@ -164,6 +165,24 @@ int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, cons
 }
 
 // ---- the mesher -------------------------------------------------------------------------
+namespace mc {
+// kernel-side view of a mesh's slab
+Stuff make_stuff(const mc_mesh* m) {
+    Stuff S;
+    S.L = m->L;
+    S.g = m->g;
+    S.c0 = m->c0; S.c1 = m->c1; S.cl0 = m->cl0; S.cl1 = m->cl1;
+    S.oz0 = m->oz0; S.oz1 = m->oz1; S.wz0 = m->wz0; S.wz1 = m->wz1;
+    S.tflag = (uint8_t*)m->d_tflag.p; S.vuni = (uint8_t*)m->d_vuni.p; S.cuni = (uint8_t*)m->d_cuni.p;
+    S.vmask = (uint16_t*)m->d_vmask.p; S.vloc = (uint16_t*)m->d_vloc.p; S.cinfo = (uint16_t*)m->d_cinfo.p;
+    S.tvbase = (const unsigned long long*)m->d_vtile_vbase.p;
+    S.ttbase = (const unsigned long long*)m->d_ttile_base.p;
+    S.lower_table = (const unsigned long long*)m->lower_table;
+    S.vertex_base = (long long)m->vertex_base;
+    return S;
+}
+}  // namespace mc
+
 // tile-specialised evaluation (mc_prune.cuh): worth it once the program is more than a few nodes
 static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     mc_ctx* c = m->ctx;
@@ -175,20 +194,14 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     const size_t smem_cap = c->smem_optin ? c->smem_optin : 48 * 1024;
     if (smem > smem_cap) return MC_OK;
     const Lattice& L = m->L;
-    TileGrid g;
-    g.tx = 16; g.ty = 16; g.tz = 16;
-    const uint32_t nplanes = L.pz1 - L.pz0 + 1;
-    g.ntx = (L.NX + g.tx - 1) / g.tx; g.nty = (L.NY + g.ty - 1) / g.ty; g.ntz = (nplanes + g.tz - 1) / g.tz;
-    g.z0 = L.pz0;
-    const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
-    m->n_tiles = ntiles;
+    const uint64_t ntiles = m->n_tiles;
     int rc = c->alloc((size_t)n_inst * 4, m->d_inst_start);
     if (rc == MC_OK) rc = c->alloc((size_t)n_words * 2, m->d_word_inst);
     if (rc == MC_OK) rc = c->alloc((size_t)p.n_decisions * ntiles, m->d_dec);
     if (rc != MC_OK) return rc;
     MC_CUDA(cudaMemcpyAsync(m->d_inst_start.p, p.inst_start.data(), (size_t)n_inst * 4, cudaMemcpyHostToDevice, c->stream));
     MC_CUDA(cudaMemcpyAsync(m->d_word_inst.p, p.word_inst.data(), (size_t)n_words * 2, cudaMemcpyHostToDevice, c->stream));
-    k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)m->d_prog.p, ntiles,
+    k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, m->g, (const uint64_t*)m->d_prog.p, ntiles,
                                                                   (uint8_t*)m->d_dec.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
@@ -200,12 +213,13 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     uint64_t grid = (uint64_t)c->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;
     unsigned long long* pruned_total = (unsigned long long*)m->d_counters.p + CN_PRUNED_WORDS;
-    kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
+    kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, m->g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                                                    n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
                                                    pruned_total);
     c->launches++;
     MC_CUDA(cudaGetLastError());
+    m->tiled_sdf = true;
     *done = true;
     return MC_OK;
 }
@@ -232,10 +246,10 @@ static int launch_sdf_field(mc_mesh* m) {
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
     if (per_sm < 1) per_sm = 1;
-    const uint64_t ntiles = (uint64_t)((m->L.NX + (linear ? 31 : 7)) / (linear ? 32 : 8)) *
+    const uint64_t nsteps = (uint64_t)((m->L.NX + (linear ? 31 : 7)) / (linear ? 32 : 8)) *
                             ((m->L.NY + (linear ? 0 : 3)) / (linear ? 1 : 4)) * nplanes;
     uint64_t grid = (uint64_t)c->sm_count * per_sm;
-    const uint64_t need = (ntiles + 15) / 16;
+    const uint64_t need = (nsteps + 15) / 16;
     if (grid > need) grid = need ? need : 1;
     kern<<<(unsigned)grid, 512, smem, c->stream>>>(m->L, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p, nwords,
                                                    in_smem, m->L.pz0, nplanes);
@@ -286,23 +300,27 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     m->c0 = (uint32_t)zb; m->c1 = (uint32_t)ze;
     const uint32_t nz = L.nz;
     L.pz0 = m->c0 >= 2 ? m->c0 - 2 : 0;
-    L.pz1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 2);
+    L.pz1 = (uint32_t)std::min<uint64_t>(nz, (uint64_t)m->c1 + 2);
     m->wz0 = m->c0 >= 1 ? m->c0 - 1 : 0;
-    m->wz1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
+    m->wz1 = (uint32_t)std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
     m->cl0 = m->c0 >= 1 ? m->c0 - 1 : 0;
-    m->cl1 = std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
+    m->cl1 = (uint32_t)std::min<uint64_t>(nz, (uint64_t)m->c1 + 1);
     m->oz0 = m->c0 == 0 ? 0 : m->c0 + 1;
     m->oz1 = m->c1;
-    const bool empty_slab = (m->c0 == m->c1 && !(m->c0 == 0 && nz == 0));
+    if (m->c0 == m->c1 && nz > 0) { m->oz0 = 1; m->oz1 = 0; }  // empty slab owns nothing
 
     const uint64_t per_plane = (uint64_t)L.NX * L.NY;
-    const uint64_t npts = per_plane * (L.pz1 - L.pz0 + 1);
+    const uint32_t nplanes = L.pz1 - L.pz0 + 1;
+    const uint64_t npts = per_plane * nplanes;
     const uint64_t ncls = (uint64_t)L.nx * L.ny * (m->cl1 - m->cl0);
-    const uint64_t nown = (m->oz1 >= m->oz0 && !empty_slab) ? per_plane * (m->oz1 - m->oz0 + 1) : 0;
+    const uint64_t nown = (m->oz1 >= m->oz0) ? per_plane * (m->oz1 - m->oz0 + 1) : 0;
     m->points_evaluated = npts;
     m->points_owned = nown;
-    m->n_ctiles = (ncls + TILE_SIZE - 1) / TILE_SIZE;
-    m->n_vtiles = (nown + TILE_SIZE - 1) / TILE_SIZE;
+    m->g.ntx = (L.NX + TS - 1) / TS; m->g.nty = (L.NY + TS - 1) / TS; m->g.ntz = (nplanes + TS - 1) / TS;
+    m->g.z0 = L.pz0;
+    const uint64_t ntiles = (uint64_t)m->g.ntx * m->g.nty * m->g.ntz;
+    m->n_tiles = ntiles;
+    if (ntiles >= (1ull << 31)) { delete m; return fail(MC_ERR_LIMIT, "lattice too large for one slab"); }
 
 #define MC_TRY(x) do { rc = (x); if (rc != MC_OK) { mesh_release_all(m); delete m; return rc; } } while (0)
 #define MC_TRY_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { mesh_release_all(m); delete m; return cuda_fail(e_, #x); } } while (0)
@@ -311,13 +329,16 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->alloc(npts * 8, m->d_phi));
     MC_TRY(c->alloc(npts, m->d_wcode));
     MC_TRY(c->alloc(npts * 2, m->d_vmask));
-    MC_TRY(c->alloc(npts * 4, m->d_vbase));
+    MC_TRY(c->alloc(npts * 2, m->d_vloc));
     MC_TRY(c->alloc(std::max<uint64_t>(ncls, 1) * 2, m->d_cinfo));
-    MC_TRY(c->alloc((m->n_ctiles + 1) * 8, m->d_ctile_tot));
-    MC_TRY(c->alloc((m->n_ctiles + 1) * 8, m->d_ctile_base));
-    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_tot));
-    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_vbase));
-    MC_TRY(c->alloc((m->n_vtiles + 1) * 8, m->d_vtile_cbase));
+    MC_TRY(c->alloc(ntiles + 4, m->d_tflag));
+    MC_TRY(c->alloc(ntiles + 4, m->d_vuni));
+    MC_TRY(c->alloc(ntiles + 4, m->d_cuni));
+    MC_TRY(c->alloc((ntiles + 1) * 8, m->d_ttile_tot));
+    MC_TRY(c->alloc((ntiles + 1) * 8, m->d_ttile_base));
+    MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_tot));
+    MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_vbase));
+    MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_cbase));
     MC_TRY(c->alloc(64 * 8, m->d_counters));
     L.phi = (const double*)m->d_phi.p;
     L.wcode = (uint8_t*)m->d_wcode.p;
@@ -331,45 +352,37 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     }
     MC_TRY_CUDA(cudaMemsetAsync(m->d_wcode.p, 0, npts, s));
     unsigned long long* counters = (unsigned long long*)m->d_counters.p;
+    const Stuff S = make_stuff(m);
+    const unsigned tgrid = (unsigned)ntiles;
 
     // a2: SDF field on all stored planes
     MC_TRY_CUDA(cudaEventRecord(m->ev[0], s));
     MC_TRY(launch_sdf_field(m));
     MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
-    // a6: warp codes
-    {
-        const uint64_t n = per_plane * (m->wz1 - m->wz0 + 1);
-        k_warp_codes<<<blocks_for(n, 256), 256, 0, s>>>(L, m->wz0, m->wz1, counters, m->oz0, m->oz1);
-        c->launches++;
-        MC_TRY_CUDA(cudaGetLastError());
-    }
+    // tile sign summary + a6: warp codes
+    k_tile_minmax<<<tgrid, TILE_THREADS, 0, s>>>(S);
+    k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
+    k_warp_codes<<<tgrid, TILE_THREADS, 0, s>>>(S, counters);
+    c->launches += 3;
+    MC_TRY_CUDA(cudaGetLastError());
     MC_TRY_CUDA(cudaEventRecord(m->ev[2], s));
     // a5/a7/a9: classification + counts
-    if (ncls > 0) {
-        k_classify_cells<<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
-            L, (const uint64_t*)m->d_prog.p, m->cl0, m->cl1, m->c0, m->c1, (uint16_t*)m->d_cinfo.p,
-            (unsigned long long*)m->d_ctile_tot.p, counters);
-        c->launches++;
-        MC_TRY_CUDA(cudaGetLastError());
-    }
-    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_ctile_tot.p, m->n_ctiles,
-                                    (unsigned long long*)m->d_ctile_base.p, nullptr, counters + CN_TETS);
-    c->launches++;
+    k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
+    k_classify_cells<<<tgrid, TILE_THREADS, 0, s>>>(S, (const uint64_t*)m->d_prog.p,
+                                                    (unsigned long long*)m->d_ttile_tot.p, counters);
+    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_ttile_tot.p, ntiles,
+                                    (unsigned long long*)m->d_ttile_base.p, nullptr, counters + CN_TETS);
+    c->launches += 3;
     MC_TRY_CUDA(cudaGetLastError());
     // CN_TETS / CN_KEPT are adjacent: totals[0] = output tets, totals[1] = kept lattice tets
     static_assert(CN_KEPT == CN_TETS + 1, "scan totals layout");
     MC_TRY_CUDA(cudaEventRecord(m->ev[3], s));
     // a10 pass 1: vertex masks + counts
-    if (nown > 0) {
-        k_vertex_count<<<(unsigned)m->n_vtiles, TILE_THREADS, 0, s>>>(L, m->oz0, m->oz1, (uint16_t*)m->d_vmask.p,
-                                                                       (unsigned long long*)m->d_vtile_tot.p);
-        c->launches++;
-        MC_TRY_CUDA(cudaGetLastError());
-    }
-    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_vtile_tot.p, m->n_vtiles,
+    k_vertex_count<<<tgrid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_vtile_tot.p);
+    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_vtile_tot.p, ntiles,
                                     (unsigned long long*)m->d_vtile_vbase.p, (unsigned long long*)m->d_vtile_cbase.p,
                                     counters + CN_VERTS);
-    c->launches++;
+    c->launches += 2;
     MC_TRY_CUDA(cudaGetLastError());
     static_assert(CN_CUTS == CN_VERTS + 1, "scan totals layout");
     MC_TRY_CUDA(cudaEventRecord(m->ev[4], s));
@@ -379,10 +392,10 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     m->n_cuts = m->counters[CN_CUTS];
     m->n_tets = m->counters[CN_TETS];
     m->n_kept = m->counters[CN_KEPT];
-    if (m->n_verts >= (1ull << 31)) {
+    if (m->n_verts >= (1ull << 40)) {
         mesh_release_all(m);
         delete m;
-        return fail(MC_ERR_LIMIT, "more than 2^31 vertices in one slab; shard the lattice over more GPUs");
+        return fail(MC_ERR_LIMIT, "too many vertices in one slab");
     }
     m->phase = 1;
     *out = m;
@@ -401,22 +414,18 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
     rc = c->alloc(std::max<uint64_t>(m->n_cuts, 1) * 8, m->d_cutlist);
     if (rc != MC_OK) return rc;
     const Lattice& L = m->L;
+    const Stuff S = make_stuff(m);
     unsigned long long* counters = (unsigned long long*)m->d_counters.p;
     MC_CUDA(cudaEventRecord(m->ev[5], s));
-    if (m->n_vtiles > 0) {
-        k_vertex_emit<<<(unsigned)m->n_vtiles, TILE_THREADS, 0, s>>>(
-            L, m->oz0, m->oz1, (const uint16_t*)m->d_vmask.p, (const unsigned long long*)m->d_vtile_vbase.p,
-            (const unsigned long long*)m->d_vtile_cbase.p, (int32_t*)m->d_vbase.p, (double*)m->d_coords.p,
-            (unsigned long long*)m->d_cutlist.p);
-        c->launches++;
-        MC_CUDA(cudaGetLastError());
-    }
+    k_vertex_emit<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (const unsigned long long*)m->d_vtile_cbase.p,
+                                                               (double*)m->d_coords.p, (unsigned long long*)m->d_cutlist.p);
+    c->launches++;
+    MC_CUDA(cudaGetLastError());
     MC_CUDA(cudaEventRecord(m->ev[6], s));
     if (m->n_cuts > 0) {
         k_bisect_edges<<<blocks_for(m->n_cuts, 256), 256, 0, s>>>(
-            L, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts,
-            (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, m->error_threshold, m->max_bisect,
-            (double*)m->d_coords.p, counters);
+            S, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts, m->error_threshold,
+            m->max_bisect, (double*)m->d_coords.p, counters);
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }
@@ -426,9 +435,7 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
         const uint64_t n = (uint64_t)L.NX * L.NY;
         rc = c->alloc(n * 8, m->d_plane_table);
         if (rc != MC_OK) return rc;
-        k_export_plane<<<blocks_for(n, 256), 256, 0, s>>>(L, m->oz1, (const uint16_t*)m->d_vmask.p,
-                                                          (const int32_t*)m->d_vbase.p, (int64_t)vertex_base,
-                                                          (unsigned long long*)m->d_plane_table.p);
+        k_export_plane<<<blocks_for(n, 256), 256, 0, s>>>(S, m->oz1, (unsigned long long*)m->d_plane_table.p);
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }
@@ -442,63 +449,44 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     MC_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     m->tet_base = tet_base;
-    const Lattice& L = m->L;
     unsigned long long* counters = (unsigned long long*)m->d_counters.p;
-    if (m->c0 > 0) {
-        if (!d_lower_plane) return fail(MC_ERR_ARG, "mc_tessellate_emit_tets: slab does not start at z = 0, the lower plane table is required");
-        const uint64_t n = (uint64_t)L.NX * L.NY;
-        k_import_plane<<<blocks_for(n, 256), 256, 0, s>>>(L, m->c0, (const unsigned long long*)d_lower_plane,
-                                                          (int64_t)m->vertex_base, (uint16_t*)m->d_vmask.p,
-                                                          (int32_t*)m->d_vbase.p);
-        c->launches++;
-        MC_CUDA(cudaGetLastError());
-    }
+    if (m->c0 > 0 && !d_lower_plane)
+        return fail(MC_ERR_ARG, "mc_tessellate_emit_tets: slab does not start at z = 0, the lower plane table is required");
+    m->lower_table = m->c0 > 0 ? d_lower_plane : nullptr;
     m->index_bytes = (m->vertex_base + m->n_verts < (1ull << 32)) ? 4 : 8;
     int rc = c->alloc(std::max<uint64_t>(m->n_tets, 1) * 4 * (size_t)m->index_bytes, m->d_tets);
     if (rc != MC_OK) return rc;
+    const Stuff S = make_stuff(m);
+    const bool quality = !(m->flags & MC_OPT_SKIP_QUALITY);
     MC_CUDA(cudaEventRecord(m->ev[8], s));
-    if (m->n_ctiles > 0 && m->n_tets > 0) {
-        if (m->index_bytes == 4)
-            k_tet_emit<uint32_t><<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
-                L, m->cl0, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
-                (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, (int64_t)m->vertex_base,
-                (uint32_t*)m->d_tets.p);
-        else
-            k_tet_emit<unsigned long long><<<(unsigned)m->n_ctiles, TILE_THREADS, 0, s>>>(
-                L, m->cl0, m->c0, m->c1, (const uint16_t*)m->d_cinfo.p, (const unsigned long long*)m->d_ctile_base.p,
-                (const uint16_t*)m->d_vmask.p, (const int32_t*)m->d_vbase.p, (int64_t)m->vertex_base,
-                (unsigned long long*)m->d_tets.p);
+    if (m->n_tets > 0) {
+        const unsigned grid = (unsigned)m->n_tiles;
+        const double* coords = (const double*)m->d_coords.p;
+        if (m->index_bytes == 4) {
+            if (quality) k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, (uint32_t*)m->d_tets.p, coords, counters);
+            else k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, (uint32_t*)m->d_tets.p, coords, counters);
+        } else {
+            if (quality) k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_tets.p, coords, counters);
+            else k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_tets.p, coords, counters);
+        }
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }
     MC_CUDA(cudaEventRecord(m->ev[9], s));
-    // a11: quality.  Tets of a slab may reference vertices of the plane below (owned by another
-    // rank); the single-device path (vertex_base == 0, c0 == 0) sees every vertex.
-    if (!(m->flags & MC_OPT_SKIP_QUALITY) && m->n_tets > 0 && m->c0 == 0) {
-        if (m->index_bytes == 4)
-            k_tet_quality<uint32_t><<<blocks_for(m->n_tets, 256), 256, 0, s>>>(
-                (const double*)m->d_coords.p, (const uint32_t*)m->d_tets.p, m->n_tets, (int64_t)m->vertex_base, counters);
-        else
-            k_tet_quality<unsigned long long><<<blocks_for(m->n_tets, 256), 256, 0, s>>>(
-                (const double*)m->d_coords.p, (const unsigned long long*)m->d_tets.p, m->n_tets,
-                (int64_t)m->vertex_base, counters);
-        c->launches++;
-        MC_CUDA(cudaGetLastError());
-    }
-    MC_CUDA(cudaEventRecord(m->ev[10], s));
     MC_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
     MC_CUDA(cudaStreamSynchronize(s));
     float ms;
-    const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {5, 6}, {6, 7}, {8, 9}, {9, 10}};
-    for (int i = 0; i < 7; ++i) {
+    const int pairs[6][2] = {{0, 1}, {1, 2}, {2, 3}, {5, 6}, {6, 7}, {8, 9}};
+    for (int i = 0; i < 6; ++i) {
         MC_CUDA(cudaEventElapsedTime(&ms, m->ev[pairs[i][0]], m->ev[pairs[i][1]]));
         m->stage_ms[i] = ms;
     }
+    m->stage_ms[6] = 0.0;  // quality is fused into the tet emission
     MC_CUDA(cudaEventElapsedTime(&ms, m->ev[3], m->ev[4]));
     m->stage_ms[3] += ms;  // vertex count + scan belongs to "vertex scan+emit"
     // scratch that is no longer needed goes back to the pool now
     c->release(m->d_cutlist);
-    if (!(m->flags & MC_OPT_KEEP_PHI)) { /* phi / wcode stay: boundary + side-sets re-classify cells */ }
+    c->release(m->d_dec);
     m->phase = 3;
     if (m->counters[CN_BISECT_FAIL])
         return fail(MC_ERR_DIVERGED, "edge bisection did not reach the error threshold within the iteration cap on " +
@@ -535,7 +523,7 @@ int mc_mesh_counts(const mc_mesh* m, uint64_t counts[6]) {
 
 int mc_mesh_prune_stats(const mc_mesh* m, uint64_t* n_tiles, uint64_t* pruned_words_total, uint64_t* full_words) {
     if (!m) return fail(MC_ERR_ARG, "mc_mesh_prune_stats: null mesh");
-    if (n_tiles) *n_tiles = m->n_tiles;
+    if (n_tiles) *n_tiles = m->tiled_sdf ? m->n_tiles : 0;
     if (pruned_words_total) *pruned_words_total = m->counters[CN_PRUNED_WORDS];
     if (full_words) *full_words = m->prog.words.size();
     return MC_OK;

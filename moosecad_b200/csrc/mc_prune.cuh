@@ -232,19 +232,6 @@ __device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
 #undef MC_IPUSH
 }
 
-struct TileGrid {
-    uint32_t tx, ty, tz;        // tile extent in lattice points
-    uint32_t ntx, nty, ntz;     // tiles per axis (over the stored planes)
-    uint32_t z0;                // first stored plane
-};
-
-__device__ __forceinline__ void tile_origin(const TileGrid& g, uint64_t t, uint32_t& X0, uint32_t& Y0, uint32_t& Z0) {
-    X0 = (uint32_t)(t % g.ntx) * g.tx;
-    const uint64_t r = t / g.ntx;
-    Y0 = (uint32_t)(r % g.nty) * g.ty;
-    Z0 = g.z0 + (uint32_t)(r / g.nty) * g.tz;
-}
-
 // decisions for every tile: one tile per lane
 static __global__ void __launch_bounds__(128)
 k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint8_t* __restrict__ dec) {
@@ -252,7 +239,7 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
     tile_origin(g, tc, X0, Y0, Z0);
-    const uint32_t X1 = min(X0 + g.tx, L.NX) - 1, Y1 = min(Y0 + g.ty, L.NY) - 1, Z1 = min(Z0 + g.tz, L.pz1 + 1) - 1;
+    const uint32_t X1 = min(X0 + TS, L.NX) - 1, Y1 = min(Y0 + TS, L.NY) - 1, Z1 = min(Z0 + TS, L.pz1 + 1) - 1;
     // lattice coordinates are monotone in the index, so the end points bound the tile exactly
     const double box[6] = {lat_x(L, X0), lat_x(L, X1), lat_y(L, Y0), lat_y(L, Y1), lat_z(L, Z0), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
@@ -380,8 +367,8 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         // 4. evaluate the tile: WX x WY points of one z-plane per warp step
         uint32_t X0, Y0, Z0;
         tile_origin(g, tile, X0, Y0, Z0);
-        const uint32_t wpx = g.tx / WX, wpy = g.ty / WY;
-        const uint32_t steps = wpx * wpy * g.tz;
+        const uint32_t wpx = TS / WX, wpy = TS / WY;
+        const uint32_t steps = wpx * wpy * TS;
         const uint32_t lane = tid & 31u, lx = lane % WX, ly = lane / WX;
         for (uint32_t s = tid >> 5; s < steps; s += (blockDim.x >> 5)) {
             const uint32_t sx = s % wpx, sy = (s / wpx) % wpy, sz = s / (wpx * wpy);
