@@ -165,6 +165,7 @@ int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, cons
 }
 
 // ---- the mesher -------------------------------------------------------------------------
+extern "C++" {
 namespace mc {
 // kernel-side view of a mesh's slab
 Stuff make_stuff(const mc_mesh* m) {
@@ -182,6 +183,7 @@ Stuff make_stuff(const mc_mesh* m) {
     return S;
 }
 }  // namespace mc
+}  // extern "C++"
 
 // tile-specialised evaluation (mc_prune.cuh): worth it once the program is more than a few nodes
 static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
