@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -221,23 +221,51 @@ static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long
 }
 
 // ---------------------------------------------------------------------------------------
-// a6: warp codes (only tiles whose neighbourhood is not of one strict sign can have any)
+// a6: warp codes (only tiles whose neighbourhood is not of one strict sign can have any).
+// The tile's sign classes (with a one-point halo) are staged in shared memory; a vertex runs
+// the full visit-order procedure only when one of its lattice edges does not join two
+// vertices of the same strict sign.
 static __global__ void __launch_bounds__(TILE_THREADS)
 k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
     if (S.vuni[blockIdx.x] != VU_ACTIVE) return;
+    constexpr int H = (int)TS + 2;
+    __shared__ int8_t s_sg[H * H * H];  // -1 / 0 / +1, 2 = no such lattice point
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
+        const int64_t X = (int64_t)X0 + idx % H - 1, Y = (int64_t)Y0 + (idx / H) % H - 1, Z = (int64_t)Z0 + idx / (H * H) - 1;
+        int8_t sg = 2;
+        if (X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1) {
+            const double v = L.phi[pidx(L, (uint32_t)X, (uint32_t)Y, (uint32_t)Z)];
+            sg = v > 0.0 ? (int8_t)1 : (v < 0.0 ? (int8_t)-1 : (int8_t)0);
+        }
+        s_sg[idx] = sg;
+    }
+    __syncthreads();
     unsigned warped_any = 0, warped_owned = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t X = X0 + (j & 15u), Y = Y0 + ((j >> 4) & 15u), Z = Z0 + (j >> 8);
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
         if (X < L.NX && Y < L.NY && Z >= S.wz0 && Z <= S.wz1) {
-            const uint32_t code = warp_eval(L, X, Y, Z);
-            if (code) {
-                L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
-                warped_any = 1;
-                warped_owned += (Z >= S.oz0 && Z <= S.oz1) ? 1u : 0u;
+            const int me = (int)((lz + 1) * H + (ly + 1)) * H + (int)(lx + 1);
+            const int sv = s_sg[me];
+            const bool even = ((X + Y + Z) & 1u) == 0u;
+            bool any = false;
+#pragma unroll
+            for (int d = 0; d < 18; ++d) {
+                if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
+                const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
+                if (sw != 2 && !(sv != 0 && sw == sv)) any = true;
+            }
+            if (any) {
+                const uint32_t code = warp_eval(L, X, Y, Z);
+                if (code) {
+                    L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
+                    warped_any = 1;
+                    warped_owned += (Z >= S.oz0 && Z <= S.oz1) ? 1u : 0u;
+                }
             }
         }
     }
@@ -276,23 +304,35 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
         }
         return;
     }
+    // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0
+    constexpr int H = (int)TS + 1;
+    __shared__ uint8_t s_cls[H * H * H];
+    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
+        const uint32_t X = X0 + idx % H, Y = Y0 + (idx / H) % H, Z = Z0 + idx / (H * H);
+        uint8_t cl = 0;
+        if (X < L.NX && Y < L.NY && Z <= L.pz1) {
+            const size_t pi = pidx(L, X, Y, Z);
+            const double raw = L.phi[pi];
+            const double w = (L.wcode[pi] & 0x7f) ? 0.0 : raw;
+            cl = (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0));
+        }
+        s_cls[idx] = cl;
+    }
+    __syncthreads();
     uint32_t my_out = 0, my_kept = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const uint32_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
         if (cx >= L.nx || cy >= L.ny || cz < S.cl0 || cz >= S.cl1) continue;
         const Cell c = make_cell(cx, cy, cz);
         const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
         // corner signs decide the two trivial classes
-        bool all_neg = true, all_pos_raw = true;
+        uint8_t andc = 3;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const size_t pi = pidx(L, cx + (uint32_t)C_LAT[k][0], cy + (uint32_t)C_LAT[k][1], cz + (uint32_t)C_LAT[k][2]);
-            const double raw = L.phi[pi];
-            const double w = (L.wcode[pi] & 0x7f) ? 0.0 : raw;
-            all_neg = all_neg && (w < 0.0);
-            all_pos_raw = all_pos_raw && (raw > 0.0);
-        }
+        for (int k = 0; k < 8; ++k)
+            andc &= s_cls[((lz + (uint32_t)C_LAT[k][2]) * H + (ly + (uint32_t)C_LAT[k][1])) * H + (lx + (uint32_t)C_LAT[k][0])];
+        const bool all_neg = (andc & 1) != 0, all_pos_raw = (andc & 2) != 0;
         uint32_t count = 0, kept = 0, removed_bits = 0;
         bool full = false;
         if (all_neg) {
@@ -633,10 +673,12 @@ static __global__ void k_tet_quality_arrays(const double* __restrict__ coords, c
 struct QualityAcc {
     double armin, armax;
     unsigned inverted;
-    __device__ __forceinline__ void add(const double a[3], const double b[3], const double c[3], const double d[3]) {
+    // `mult`: number of congruent tets this one stands for
+    __device__ __forceinline__ void add(const double a[3], const double b[3], const double c[3], const double d[3],
+                                        unsigned mult = 1u) {
         double vol, ar;
         tet_quality(a, b, c, d, vol, ar);
-        if (vol <= 0.0) ++inverted;
+        if (vol <= 0.0) inverted += mult;
         armin = fmin(armin, ar);  // Float::min / max ignore NaN like fmin / fmax
         armax = fmax(armax, ar);
     }
@@ -675,20 +717,94 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
     if (cu == CU_FULL) {
         constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
         const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
+        // the (up to) 8 point tiles holding the corners of this cell tile
+        __shared__ uint8_t s_nvu[8];
+        __shared__ unsigned long long s_nbase[8];
+        __shared__ TileBox s_nbox[8];
+        // quality: an un-warped lattice tet only depends on the coordinate steps of its cell along
+        // the three axes and on the cell's mirroring, so it is evaluated once per distinct
+        // (step, parity) combination of the tile and weighted by its multiplicity
+        __shared__ double s_step[3][TS];
+        __shared__ uint8_t s_rep[3][TS];
+        __shared__ uint16_t s_mult[3][TS];
+        if (threadIdx.x < 8) {
+            const uint32_t tix = (uint32_t)(blockIdx.x % S.g.ntx) + (threadIdx.x & 1u);
+            const uint32_t tiy = (uint32_t)((blockIdx.x / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
+            const uint32_t tiz = (uint32_t)(blockIdx.x / (S.g.ntx * S.g.nty)) + (threadIdx.x >> 2);
+            uint8_t vu = VU_ACTIVE;
+            if (tix < S.g.ntx && tiy < S.g.nty && tiz < S.g.ntz) {
+                const uint32_t t = (tiz * S.g.nty + tiy) * S.g.ntx + tix;
+                vu = S.vuni[t];
+                s_nbase[threadIdx.x] = S.tvbase[t];
+                s_nbox[threadIdx.x] = tile_box(S, t);
+            }
+            s_nvu[threadIdx.x] = vu;
+        }
+        if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
+            const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
+            const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+            const bool valid = a == 0 ? cc < L.nx : (a == 1 ? cc < L.ny : (cc >= zlo && cc < zhi));
+            double d = 0.0;
+            if (valid) d = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
+            s_step[a][i] = d;
+            s_rep[a][i] = valid ? 1 : 0;
+        }
+        __syncthreads();
+        if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
+            const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
+            const uint32_t base = a == 0 ? X0 : (a == 1 ? Y0 : Z0);
+            bool rep = s_rep[a][i] != 0;
+            uint32_t mult = 0;
+            if (rep) {
+                for (uint32_t q = 0; q < TS; ++q) {
+                    const bool same = s_rep[a][q] != 0 && s_step[a][q] == s_step[a][i] && (((base + q) ^ (base + i)) & 1u) == 0u;
+                    if (same) { ++mult; if (q < i) rep = false; }
+                }
+            }
+            __syncwarp();
+            s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
+        }
+        __syncthreads();
+        if (QUALITY) {
+            for (uint32_t j = threadIdx.x; j < TS * TS * TS; j += TILE_THREADS) {
+                const uint32_t ix = j & 15u, iy = (j >> 4) & 15u, iz = j >> 8;
+                const uint32_t mult = (uint32_t)s_mult[0][ix] * s_mult[1][iy] * s_mult[2][iz];
+                if (mult == 0u) continue;
+                const Cell c = make_cell(X0 + ix, Y0 + iy, Z0 + iz);
+                const bool flip = c.flip();
+                double pos[8][3];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t X, Y, Z;
+                    corner_xyz(c, k, X, Y, Z);
+                    pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z);
+                }
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]], mult);
+                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]], mult);
+                }
+            }
+        }
         const uint32_t n = nxt * nyt * (zhi - zlo);
         for (uint32_t j = threadIdx.x; j < n; j += TILE_THREADS) {
             const uint32_t cx = X0 + j % nxt, cy = Y0 + (j / nxt) % nyt, cz = zlo + j / (nxt * nyt);
             const Cell c = make_cell(cx, cy, cz);
             const bool flip = c.flip();
             IndexT id[8];
-            double pos[8][3];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 uint32_t X, Y, Z;
                 corner_xyz(c, k, X, Y, Z);
-                uint16_t mask;
-                id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
-                if (QUALITY) { pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z); }
+                const uint32_t which = (X >= X0 + TS ? 1u : 0u) | (Y >= Y0 + TS ? 2u : 0u) | (Z >= Z0 + TS ? 4u : 0u);
+                if (s_nvu[which] == VU_NEG && !(S.lower_table != nullptr && Z == S.c0)) {
+                    const TileBox& nb = s_nbox[which];
+                    id[k] = (IndexT)(S.vertex_base + (long long)s_nbase[which] +
+                                     (long long)(((Z - nb.zlo) * nb.nyt + (Y - nb.Y0)) * nb.nxt + (X - nb.X0)));
+                } else {
+                    uint16_t mask;
+                    id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
+                }
             }
             IndexT* dst = tets + 4 * (tb + 5ull * j);
 #pragma unroll
@@ -698,10 +814,6 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                 dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
                 dst[4 * t + 2] = id[T[t][2]];
                 dst[4 * t + 3] = id[T[t][3]];
-                if (QUALITY) {
-                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
-                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
-                }
             }
         }
     } else {

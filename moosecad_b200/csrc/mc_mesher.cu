@@ -72,7 +72,7 @@ static void mesh_release_all(mc_mesh* m) {
     mc_ctx* c = m->ctx;
     DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vloc, &m->d_cinfo, &m->d_ttile_tot,
                       &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
-                      &m->d_tflag, &m->d_vuni, &m->d_cuni,
+                      &m->d_tflag, &m->d_vuni, &m->d_cuni, &m->d_tsign,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
                       &m->d_inst_start, &m->d_word_inst, &m->d_dec};
     for (DevBuf* b : bufs) c->release(*b);
@@ -200,11 +200,12 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     int rc = c->alloc((size_t)n_inst * 4, m->d_inst_start);
     if (rc == MC_OK) rc = c->alloc((size_t)n_words * 2, m->d_word_inst);
     if (rc == MC_OK) rc = c->alloc((size_t)p.n_decisions * ntiles, m->d_dec);
+    if (rc == MC_OK) rc = c->alloc(ntiles + 4, m->d_tsign);
     if (rc != MC_OK) return rc;
     MC_CUDA(cudaMemcpyAsync(m->d_inst_start.p, p.inst_start.data(), (size_t)n_inst * 4, cudaMemcpyHostToDevice, c->stream));
     MC_CUDA(cudaMemcpyAsync(m->d_word_inst.p, p.word_inst.data(), (size_t)n_words * 2, cudaMemcpyHostToDevice, c->stream));
     k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, m->g, (const uint64_t*)m->d_prog.p, ntiles,
-                                                                  (uint8_t*)m->d_dec.p);
+                                                                  (uint8_t*)m->d_dec.p, (int8_t*)m->d_tsign.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     auto kern = k_sdf_field_tiled<8, 4>;
@@ -218,7 +219,8 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, m->g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                                                    n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
-                                                   pruned_total);
+                                                   (const int8_t*)m->d_tsign.p, (m->flags & MC_OPT_KEEP_PHI) ? 0 : 1,
+                                                   pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     m->tiled_sdf = true;

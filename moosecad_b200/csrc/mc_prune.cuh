@@ -54,7 +54,7 @@ __device__ __forceinline__ Ival iv_box_distance(const uint64_t* __restrict__ w, 
 
 // Interval evaluation of the program for one tile (this lane); decisions are written to
 // dec[id * dec_stride].  All 32 lanes of the warp run in lock step.
-__device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
+__device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
                           size_t dec_stride) {
     Ival vs[MC_MAX_VALUE_DEPTH + 1];
     double bs[6 * MC_MAX_POINT_DEPTH];
@@ -68,7 +68,7 @@ __device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
     for (;;) {
         const uint64_t h = w[pc];
         const uint32_t op = MC_HDR_OP(h);
-        if (op == MC_OP_END) return;
+        if (op == MC_OP_END) return top;
         switch (op) {
         case MC_OP_PLANE: {
             const unsigned sm = MC_HDR_SMALL(h);
@@ -225,7 +225,7 @@ __device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         default:
-            return;
+            return Ival{-INF, INF};
         }
         pc += mc_op_words(op);
     }
@@ -234,7 +234,8 @@ __device__ void vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
 
 // decisions for every tile: one tile per lane
 static __global__ void __launch_bounds__(128)
-k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint8_t* __restrict__ dec) {
+k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint8_t* __restrict__ dec,
+              int8_t* __restrict__ tsign) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
@@ -243,7 +244,9 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     // lattice coordinates are monotone in the index, so the end points bound the tile exactly
     const double box[6] = {lat_x(L, X0), lat_x(L, X1), lat_y(L, Y0), lat_y(L, Y1), lat_z(L, Z0), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
-    vm_decide(prog, box, dec + tc, (size_t)ntiles);
+    const Ival root = vm_decide(prog, box, dec + tc, (size_t)ntiles);
+    // proven sign of the whole tile (the bounds are padded; NaN proves nothing)
+    tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
 }
 
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(256)
 k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
-                  unsigned long long* __restrict__ pruned_words_total) {
+                  const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
+                  unsigned long long* __restrict__ skipped_tiles) {
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
     uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
@@ -264,6 +268,35 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();  // previous tile's evaluation is done with s_prog
+        // A tile whose whole 27-neighbourhood is PROVEN to have one strict sign is never read for
+        // its values: every consumer (warp, the 4-sort, bisection end points) only looks at values
+        // of tets / edges that contain a vertex of another sign class, and those lie within one
+        // lattice step, i.e. inside the neighbourhood.  Such tiles get a placeholder of the right
+        // sign instead of being evaluated (unless the caller wants the field itself).
+        if (skip_uniform) {
+            const int sg = tsign[tile];
+            bool uniform = sg != 0;
+            if (uniform) {
+                const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
+                for (int q = (int)tid; q < 27 && uniform; q += 32) {
+                    if (tid >= 32) break;
+                    const int x = tix + q % 3 - 1, y = tiy + (q / 3) % 3 - 1, z = tiz + q / 9 - 1;
+                    if (x < 0 || y < 0 || z < 0 || x >= (int)g.ntx || y >= (int)g.nty || z >= (int)g.ntz) continue;
+                    if (tsign[((size_t)z * g.nty + y) * g.ntx + x] != sg) uniform = false;
+                }
+            }
+            if (__syncthreads_and(uniform ? 1 : 0)) {
+                uint32_t X0, Y0, Z0;
+                tile_origin(g, tile, X0, Y0, Z0);
+                const double fill = sg < 0 ? -1.0 : 1.0;
+                for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
+                    const uint32_t X = X0 + (j & 15u), Y = Y0 + ((j >> 4) & 15u), Z = Z0 + (j >> 8);
+                    if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = fill;
+                }
+                if (tid == 0 && skipped_tiles) atomicAdd(skipped_tiles, 1ull);
+                continue;
+            }
+        }
         for (uint32_t i = tid; i < n_dec; i += blockDim.x) s_dec[i] = dec_g[(size_t)i * ntiles + tile];
         for (uint32_t i = tid; i <= n_inst; i += blockDim.x) s_delta[i] = 0;
         __syncthreads();

@@ -65,24 +65,23 @@ static __device__ uint64_t first_touch_key(const Lattice& L, uint32_t X, uint32_
 // vertex was node 0 (orient 0, `alpha < 0.3` branch) or node 1 (orient 1, `alpha > 0.7`
 // branch) of the winning edge visit.  Strict `<` keeps the FIRST minimal candidate in the
 // reference's visit order: tets in cut_lattice order, edges in Tet4::edge order.
+// cheap necessary condition for warp_eval != 0: some lattice edge at the vertex does not join two
+// vertices of the same strict sign
+__device__ __forceinline__ bool warp_candidate_possible(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    const double pv = raw_phi(L, X, Y, Z);
+    const bool even = ((X + Y + Z) & 1u) == 0u;
+    for (int d = 0; d < 18; ++d) {
+        if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
+        const int64_t wx = (int64_t)X + C_DIR[d][0], wy = (int64_t)Y + C_DIR[d][1], wz = (int64_t)Z + C_DIR[d][2];
+        if (wx < 0 || wy < 0 || wz < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
+        const double pw = raw_phi(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz);
+        if (!((pv > 0.0 && pw > 0.0) || (pv < 0.0 && pw < 0.0))) return true;
+    }
+    return false;
+}
+
 static __device__ uint32_t warp_eval(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
     const double pv = raw_phi(L, X, Y, Z);
-    // fast reject: an edge visit produces a candidate only if the two ends do not have the
-    // same strict sign
-    {
-        const bool even = ((X + Y + Z) & 1u) == 0u;
-        const int nd = even ? 18 : 6;
-        bool any = false;
-        for (int d = 0; d < 18; ++d) {
-            if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
-            const int64_t wx = (int64_t)X + C_DIR[d][0], wy = (int64_t)Y + C_DIR[d][1], wz = (int64_t)Z + C_DIR[d][2];
-            if (wx < 0 || wy < 0 || wz < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
-            const double pw = raw_phi(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz);
-            if (!((pv > 0.0 && pw > 0.0) || (pv < 0.0 && pw < 0.0))) { any = true; break; }
-        }
-        (void)nd;
-        if (!any) return 0u;
-    }
     const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
     bool has = false;
     double best = 0.0;

@@ -168,7 +168,14 @@ def test_tile_pruning_is_value_neutral(nprim, n, ctx):
     g.backend.set_parameters(0.1, 1.0)
     res = 1.0 / n
     a = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_NO_TILE_PRUNING).tessellate()
-    b = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_FORCE_TILE_PRUNING).tessellate()
+    # KEEP_PHI: evaluate every tile (by default tiles proven to lie deep inside / outside get a
+    # placeholder of the right sign instead of values nobody reads)
+    b = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx,
+                              flags=_lib.MC_OPT_FORCE_TILE_PRUNING | _lib.MC_OPT_KEEP_PHI).tessellate()
+    c = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_FORCE_TILE_PRUNING).tessellate()
+    assert np.array_equal(a.vertices(), c.vertices()) and np.array_equal(a.elems(), c.elems())
+    pc = c.phi()
+    assert np.array_equal(np.sign(pc), np.sign(a.phi()))
     pa, pb = a.phi(), b.phi()
     assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64))
     assert np.array_equal(a.vertices(), b.vertices()) and np.array_equal(a.elems(), b.elems())
