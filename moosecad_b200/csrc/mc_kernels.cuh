@@ -761,7 +761,6 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                     if (same) { ++mult; if (q < i) rep = false; }
                 }
             }
-            __syncwarp();
             s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
         }
         __syncthreads();
