@@ -88,10 +88,10 @@ __device__ __forceinline__ uint32_t cell_face_count(const Stuff& S, uint32_t cx,
 // (full?, output tets) of an owned cell of this tile
 __device__ __forceinline__ void cell_state(const Stuff& S, uint8_t cu, uint32_t cx, uint32_t cy, uint32_t cz, bool& full,
                                            uint32_t& count, uint16_t& ci) {
-    if (cu == CU_FULL) { full = true; count = 5; ci = (uint16_t)(5 | CI_FULL); return; }
+    if (cu == CU_FULL) { full = true; count = 5; ci = CI_ALL_FULL; return; }
     ci = S.cinfo[cidx(S, cx, cy, cz)];
     full = (ci & CI_FULL) != 0;
-    count = ci & CI_COUNT_MASK;
+    count = ci_count(ci);
 }
 
 static __global__ void __launch_bounds__(TILE_THREADS)
@@ -184,11 +184,11 @@ k_face_emit(Stuff S, const unsigned long long* __restrict__ tile_fbase, unsigned
                     TetNodes tn;
                     load_tet(L, c, t, tn);
                     TetOut to;
-                    classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+                    classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
                     for (int q = 0; q < to.n; ++q) {
                         unsigned long long id[4];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) id[m] = node_global_id<unsigned long long>(S, tn, to.node[q][m]);
+                        for (int m = 0; m < 4; ++m) id[m] = node_global_id<unsigned long long>(S, tn, to.node(q, m));
                         for (int sd = 0; sd < 4; ++sd) {
                             unsigned long long g0 = id[C_FACE[sd][0]], g1 = id[C_FACE[sd][1]], g2 = id[C_FACE[sd][2]];
                             sort3(g0, g1, g2);

@@ -26,6 +26,7 @@ struct mc_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    mc::DevBuf d_warp_table;            // visit-order table of warp_vertices (k_warp_codes)
     std::vector<mc::DevBuf> free_list;  // cached device allocations
     uint64_t held_bytes = 0;
 

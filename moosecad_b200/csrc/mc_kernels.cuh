@@ -33,10 +33,16 @@ constexpr int TILE_ROUNDS = (int)(TILE_POINTS / TILE_THREADS);
 constexpr uint8_t TF_NEG = 1, TF_POS = 2, TF_HASWARP = 4;
 constexpr uint8_t VU_ACTIVE = 0, VU_NEG = 1, VU_POS = 2;    // point tile: 27-neighbourhood all NEG / all POS
 constexpr uint8_t CU_ACTIVE = 0, CU_FULL = 1, CU_EMPTY = 2; // cell tile: every cell emits its 5 lattice tets / nothing
-// per-cell info written by k_classify_cells (ACTIVE cell tiles only)
-constexpr uint16_t CI_COUNT_MASK = 0x000f;
-constexpr uint16_t CI_REMOVED_SHIFT = 4;   // 5 bits: tet t dropped by the exterior test
-constexpr uint16_t CI_FULL = 1u << 9;      // all five lattice tets emitted untouched
+// per-cell info written by k_classify_cells (ACTIVE cell tiles only):
+// bits 2t..2t+1 = number of output tets of lattice tet t (0..3), bits 10..14 = tet t dropped by the
+// exterior test, bit 15 = all five lattice tets emitted untouched
+constexpr uint16_t CI_REMOVED_SHIFT = 10;
+constexpr uint16_t CI_FULL = 1u << 15;
+constexpr uint16_t CI_ALL_FULL = (uint16_t)(0x155u | CI_FULL);  // one output tet per lattice tet
+__host__ __device__ __forceinline__ uint32_t ci_tet_n(uint16_t ci, int t) { return (ci >> (2 * t)) & 3u; }
+__host__ __device__ __forceinline__ uint32_t ci_count(uint16_t ci) {
+    return (ci & 3u) + ((ci >> 2) & 3u) + ((ci >> 4) & 3u) + ((ci >> 6) & 3u) + ((ci >> 8) & 3u);
+}
 // per-vertex mask written by k_vertex_count (ACTIVE point tiles only)
 constexpr uint16_t VM_CUT_MASK = 0x01ff;   // bit s: the edge along canonical direction s is cut
 constexpr uint16_t VM_USED = 1u << 15;     // the lattice vertex itself is in the output
@@ -55,6 +61,7 @@ struct Stuff {
     uint16_t* vmask;      // [points] VM_*
     uint16_t* vloc;       // [points] offset of the vertex's first output inside its tile
     uint16_t* cinfo;      // [cells of classified layers] CI_*
+    const unsigned long long* warp_table;  // visit-order table of warp_vertices, see build_warp_table
     const unsigned long long* tvbase;  // [tiles] first output vertex of the tile (slab-local)
     const unsigned long long* ttbase;  // [tiles] first output tet of the tile (slab-local)
     const unsigned long long* lower_table;  // id table of plane c0 from the rank below, or null
@@ -222,28 +229,39 @@ static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long
 
 // ---------------------------------------------------------------------------------------
 // a6: warp codes (only tiles whose neighbourhood is not of one strict sign can have any).
-// The tile's sign classes (with a one-point halo) are staged in shared memory; a vertex runs
-// the full visit-order procedure only when one of its lattice edges does not join two
-// vertices of the same strict sign.
+//
+// warp_vertices' visit order around a vertex (8 cells x-major, 5 tets, 6 edges on the flipped
+// node order) only depends on the parity of the vertex' coordinates, so it is tabulated once on
+// the host (mc_mesher.cu build_warp_table): entry = cell offset | neighbour direction << 3 |
+// orientation << 8 | offsets of the tet's 4 corners << 9.  The tile's sign classes (with a
+// one-point halo) are staged in shared memory; vertices with an edge that does not join two
+// vertices of the same strict sign are collected in a list and processed one per thread.
+constexpr int WT_STRIDE = 97;  // [count, 96 entries] per parity class
+constexpr int8_t SG_NEG = -1, SG_ZERO = 0, SG_POS = 1, SG_NONE = 2, SG_NAN = 3;
+
 static __global__ void __launch_bounds__(TILE_THREADS)
 k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
     if (S.vuni[blockIdx.x] != VU_ACTIVE) return;
     constexpr int H = (int)TS + 2;
-    __shared__ int8_t s_sg[H * H * H];  // -1 / 0 / +1, 2 = no such lattice point
+    __shared__ int8_t s_sg[H * H * H];
+    __shared__ unsigned long long s_tab[8 * WT_STRIDE];
+    __shared__ uint16_t s_list[TILE_POINTS];
+    __shared__ uint32_t s_n;
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (threadIdx.x == 0) s_n = 0u;
+    for (int i = (int)threadIdx.x; i < 8 * WT_STRIDE; i += TILE_THREADS) s_tab[i] = S.warp_table[i];
     for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
         const int64_t X = (int64_t)X0 + idx % H - 1, Y = (int64_t)Y0 + (idx / H) % H - 1, Z = (int64_t)Z0 + idx / (H * H) - 1;
-        int8_t sg = 2;
+        int8_t sg = SG_NONE;
         if (X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1) {
             const double v = L.phi[pidx(L, (uint32_t)X, (uint32_t)Y, (uint32_t)Z)];
-            sg = v > 0.0 ? (int8_t)1 : (v < 0.0 ? (int8_t)-1 : (int8_t)0);
+            sg = v > 0.0 ? SG_POS : (v < 0.0 ? SG_NEG : (v == 0.0 ? SG_ZERO : SG_NAN));
         }
         s_sg[idx] = sg;
     }
     __syncthreads();
-    unsigned warped_any = 0, warped_owned = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
@@ -257,16 +275,66 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
             for (int d = 0; d < 18; ++d) {
                 if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
                 const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
-                if (sw != 2 && !(sv != 0 && sw == sv)) any = true;
+                if (sw != SG_NONE && !((sv == SG_POS || sv == SG_NEG) && sw == sv)) any = true;
             }
-            if (any) {
-                const uint32_t code = warp_eval(L, X, Y, Z);
-                if (code) {
-                    L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
-                    warped_any = 1;
-                    warped_owned += (Z >= S.oz0 && Z <= S.oz1) ? 1u : 0u;
-                }
+            if (any) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    unsigned warped_owned = 0;
+    bool warped_any = false;
+    for (uint32_t q = threadIdx.x; q < n; q += TILE_THREADS) {
+        const uint32_t j = s_list[q];
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+        const int me = (int)((lz + 1) * H + (ly + 1)) * H + (int)(lx + 1);
+        const int sv = s_sg[me];
+        const double pv = L.phi[pidx(L, X, Y, Z)];
+        const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
+        const unsigned long long* tab = s_tab + ((X & 1u) | ((Y & 1u) << 1) | ((Z & 1u) << 2)) * WT_STRIDE;
+        const uint32_t nvis = (uint32_t)tab[0];
+        unsigned long long seen = 0ull;
+        bool has = false;
+        double best = 0.0;
+        uint32_t code = 0u;
+        for (uint32_t i = 1; i <= nvis; ++i) {
+            const unsigned long long e = tab[i];
+            // the cell must exist
+            if (((e & 1ull) && X == 0u) || (!(e & 1ull) && X >= L.nx) || ((e & 2ull) && Y == 0u) || (!(e & 2ull) && Y >= L.ny) ||
+                ((e & 4ull) && Z == 0u) || (!(e & 4ull) && Z >= L.nz)) continue;
+            const uint32_t d = (uint32_t)(e >> 3) & 31u, o = (uint32_t)(e >> 8) & 1u;
+            const uint32_t bit = d * 2u + o;
+            if ((seen >> bit) & 1ull) continue;
+            const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
+            if ((sv == SG_POS || sv == SG_NEG) && sw == sv) continue;  // both ends of one strict sign
+            bool kept = false;  // cut_lattice kept the tet iff a corner has value <= 0
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t off = (uint32_t)(e >> (9 + 6 * c)) & 63u;
+                const int cs = s_sg[me + (((int)((off >> 4) & 3u) - 1) * H + ((int)((off >> 2) & 3u) - 1)) * H + ((int)(off & 3u) - 1)];
+                kept = kept || cs == SG_NEG || cs == SG_ZERO;
             }
+            if (!kept) continue;
+            seen |= 1ull << bit;
+            const uint32_t WX = X + C_DIR[d][0], WY = Y + C_DIR[d][1], WZ = Z + C_DIR[d][2];
+            const double pw = L.phi[pidx(L, WX, WY, WZ)];
+            const double alpha = o == 0u ? pv / (pv - pw) : pw / (pw - pv);
+            const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
+            double dd;
+            if (o == 0u) {
+                if (!(alpha < 0.3)) continue;
+                dd = alpha * sqrt((dx * dx + dy * dy) + dz * dz);
+            } else {
+                if (!(alpha > 1.0 - 0.3)) continue;
+                dd = (1.0 - alpha) * sqrt((dx * dx + dy * dy) + dz * dz);
+            }
+            if (!has || dd < best) { has = true; best = dd; code = 1u + 2u * d + o; }
+        }
+        if (has) {
+            L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
+            warped_any = true;
+            warped_owned += (Z >= S.oz0 && Z <= S.oz1) ? 1u : 0u;
         }
     }
     // tflag bytes are updated through their aligned 32-bit word
@@ -278,9 +346,11 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
 }
 
 // ---------------------------------------------------------------------------------------
-// a5/a7/a9: classify the five tets of every cell: output-tet count, exterior-test results,
-// "full cell" flag; mark zero-valued vertices that appear in the output.  Per-tile totals
-// (low 32 bits: output tets, high 32 bits: kept lattice tets) count owned cells only.
+// a5/a7/a9: classify the five tets of every cell: output tets per lattice tet, exterior-test
+// results, "full cell" flag; mark zero-valued vertices that appear in the output.  Per-tile
+// totals (low 32 bits: output tets, high 32 bits: kept lattice tets) count owned cells only.
+// Cells whose corners are all negative / all positive are settled from the staged classes;
+// the tets of the remaining (surface) cells are collected and classified one per thread.
 static __global__ void __launch_bounds__(TILE_THREADS)
 k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long* __restrict__ tile_tot,
                  unsigned long long* __restrict__ counters) {
@@ -307,6 +377,10 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0
     constexpr int H = (int)TS + 1;
     __shared__ uint8_t s_cls[H * H * H];
+    __shared__ uint16_t s_list[TILE_POINTS];   // surface cells (local index)
+    __shared__ uint32_t s_ci[TILE_POINTS / 2]; // cinfo of the surface cells being assembled, by list slot
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0u;
     for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
         const uint32_t X = X0 + idx % H, Y = Y0 + (idx / H) % H, Z = Z0 + idx / (H * H);
         uint8_t cl = 0;
@@ -325,46 +399,65 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
         const uint32_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
         if (cx >= L.nx || cy >= L.ny || cz < S.cl0 || cz >= S.cl1) continue;
-        const Cell c = make_cell(cx, cy, cz);
-        const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
-        // corner signs decide the two trivial classes
         uint8_t andc = 3;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             andc &= s_cls[((lz + (uint32_t)C_LAT[k][2]) * H + (ly + (uint32_t)C_LAT[k][1])) * H + (lx + (uint32_t)C_LAT[k][0])];
-        const bool all_neg = (andc & 1) != 0, all_pos_raw = (andc & 2) != 0;
-        uint32_t count = 0, kept = 0, removed_bits = 0;
-        bool full = false;
-        if (all_neg) {
-            count = 5; kept = 5; full = true;
-        } else if (!all_pos_raw) {
-            bool untouched = true;
-            for (int t = 0; t < 5; ++t) {
-                TetNodes tn;
-                load_tet(L, c, t, tn);
-                TetOut to;
-                classify_tet(L, c, t, tn, prog, -1, to);
-                if (to.kase == -2) { untouched = false; continue; }
-                ++kept;
-                if (to.ext_removed) { removed_bits |= 1u << t; if (own) atomicAdd(&counters[CN_EXT_REMOVED], 1ull); }
-                if (to.kase >= 0 && own) atomicAdd(&counters[CN_STAT0 + to.kase], 1ull);
-                if (to.kase != -1 || to.ext_removed) untouched = false;
-                count += (uint32_t)to.n;
-                // zero-valued original vertices that made it into the output are "used"
-                for (int q = 0; q < to.n; ++q)
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int nd = to.node[q][m];
-                        if (nd < 4 && tn.p[nd] == 0.0) {
-                            const size_t pi = pidx(L, tn.X[nd], tn.Y[nd], tn.Z[nd]);
-                            L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
-                        }
-                    }
-            }
-            full = untouched && count == 5;
+        if (andc & 1) {          // every corner negative: five untouched lattice tets
+            S.cinfo[cidx(S, cx, cy, cz)] = CI_ALL_FULL;
+            if (cz >= S.c0 && cz < S.c1) { my_out += 5; my_kept += 5; }
+        } else if (andc & 2) {   // every corner positive: nothing kept
+            S.cinfo[cidx(S, cx, cy, cz)] = 0;
+        } else {
+            s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
         }
-        S.cinfo[cidx(S, cx, cy, cz)] = (uint16_t)(count | (removed_bits << CI_REMOVED_SHIFT) | (full ? CI_FULL : 0));
-        if (own) { my_out += count; my_kept += kept; }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    // a tile has at most 4096 surface cells; the assembly buffer holds 2048 list slots per pass
+    for (uint32_t pass = 0; pass < n; pass += TILE_POINTS / 2) {
+        const uint32_t m = min(n - pass, TILE_POINTS / 2);
+        for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) s_ci[q] = 0u;
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < 5u * m; w += TILE_THREADS) {
+            const uint32_t q = w / 5u, t = w % 5u;
+            const uint32_t j = s_list[pass + q];
+            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+            const Cell c = make_cell(cx, cy, cz);
+            const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
+            TetNodes tn;
+            load_tet(L, c, (int)t, tn);
+            TetOut to;
+            classify_tet<true>(L, c, (int)t, tn, prog, -1, to);
+            if (to.kase == -2) continue;  // not kept by cut_lattice
+            uint32_t bits = ((uint32_t)to.n << (2u * t)) | (1u << (16u + t));  // bit 16+t: kept
+            if (to.ext_removed) { bits |= 1u << (CI_REMOVED_SHIFT + t); if (own) atomicAdd(&counters[CN_EXT_REMOVED], 1ull); }
+            if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&counters[CN_STAT0 + to.kase], 1ull); }  // bit 24+t: trimmed
+            atomicOr(&s_ci[q], bits);
+            // zero-valued original vertices that made it into the output are "used"
+            for (int o = 0; o < to.n; ++o)
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm) {
+                    const int nd = to.node(o, mm);
+                    if (nd < 4 && tet_p(tn, nd) == 0.0) {
+                        const size_t pi = pidx(L, tet_X(tn, nd), tet_Y(tn, nd), tet_Z(tn, nd));
+                        L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
+                    }
+                }
+        }
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) {
+            const uint32_t j = s_list[pass + q];
+            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+            const uint32_t b = s_ci[q];
+            uint16_t ci = (uint16_t)(b & 0x7fffu);
+            const uint32_t kept = (uint32_t)__popc((b >> 16) & 31u);
+            const bool untouched = kept == 5u && ((b >> 24) & 31u) == 0u && ((b >> CI_REMOVED_SHIFT) & 31u) == 0u;
+            if (untouched && ci_count(ci) == 5u) ci |= CI_FULL;
+            S.cinfo[cidx(S, cx, cy, cz)] = ci;
+            if (cz >= S.c0 && cz < S.c1) { my_out += ci_count(ci); my_kept += kept; }
+        }
+        __syncthreads();
     }
     const unsigned long long tot = block_sum((unsigned long long)my_out | ((unsigned long long)my_kept << 32), &s_acc);
     if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
@@ -630,7 +723,10 @@ __device__ __forceinline__ void tet_quality(const double a[3], const double b[3]
     const double minor_m11_m23 = m21 * m33 - m31 * m23;
     const double minor_m11_m22 = m21 * m32 - m31 * m22;
     vol = (m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22) / 6.0;
-    const double* P[4] = {a, b, c, d};
+    // Tet4::face / Tet4::edge tables as compile-time constants so that everything stays in registers
+    constexpr int F[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
+    constexpr int E[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    const double P[4][3] = {{a[0], a[1], a[2]}, {b[0], b[1], b[2]}, {c[0], c[1], c[2]}, {d[0], d[1], d[2]}};
     double ab[3], ac[3], ad[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ad[k] = d[k] - a[k]; }
@@ -639,17 +735,15 @@ __device__ __forceinline__ void tet_quality(const double a[3], const double b[3]
     double sum_normals = 0.0;
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-        const double* q0 = P[C_FACE[f][0]]; const double* q1 = P[C_FACE[f][1]]; const double* q2 = P[C_FACE[f][2]];
-        const double u0 = q1[0] - q0[0], u1 = q1[1] - q0[1], u2 = q1[2] - q0[2];
-        const double v0 = q2[0] - q0[0], v1 = q2[1] - q0[1], v2 = q2[2] - q0[2];
+        const double u0 = P[F[f][1]][0] - P[F[f][0]][0], u1 = P[F[f][1]][1] - P[F[f][0]][1], u2 = P[F[f][1]][2] - P[F[f][0]][2];
+        const double v0 = P[F[f][2]][0] - P[F[f][0]][0], v1 = P[F[f][2]][1] - P[F[f][0]][1], v2 = P[F[f][2]][2] - P[F[f][0]][2];
         const double n0 = u1 * v2 - u2 * v1, n1 = u2 * v0 - u0 * v2, n2 = u0 * v1 - u1 * v0;
         sum_normals += sqrt((n0 * n0 + n1 * n1) + n2 * n2);
     }
     double max_length2 = 0.0;
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
-        const double* q0 = P[C_EDGE[e][0]]; const double* q1 = P[C_EDGE[e][1]];
-        const double u0 = q1[0] - q0[0], u1 = q1[1] - q0[1], u2 = q1[2] - q0[2];
+        const double u0 = P[E[e][1]][0] - P[E[e][0]][0], u1 = P[E[e][1]][1] - P[E[e][0]][1], u2 = P[E[e][1]][2] - P[E[e][0]][2];
         max_length2 = fmax(max_length2, (u0 * u0 + u1 * u1) + u2 * u2);
     }
     const double max_length = sqrt(max_length2);
@@ -690,13 +784,14 @@ struct QualityAcc {
 template <typename IndexT>
 __device__ __forceinline__ IndexT node_global_id(const Stuff& S, const TetNodes& tn, int code) {
     uint16_t mask;
-    if (code < 4) return (IndexT)vertex_gid(S, tn.X[code], tn.Y[code], tn.Z[code], mask);
+    if (code < 4) return (IndexT)vertex_gid(S, tet_X(tn, code), tet_Y(tn, code), tet_Z(tn, code), mask);
     const int i = (code - 4) >> 2, j = (code - 4) & 3;
-    const int dx = (int)tn.X[j] - (int)tn.X[i], dy = (int)tn.Y[j] - (int)tn.Y[i], dz = (int)tn.Z[j] - (int)tn.Z[i];
-    int d = dir_index(dx, dy, dz);
-    int owner = i;
-    if (d >= 9) { d -= 9; owner = j; }
-    const long long base = vertex_gid(S, tn.X[owner], tn.Y[owner], tn.Z[owner], mask);
+    const uint32_t Xi = tet_X(tn, i), Yi = tet_Y(tn, i), Zi = tet_Z(tn, i);
+    const uint32_t Xj = tet_X(tn, j), Yj = tet_Y(tn, j), Zj = tet_Z(tn, j);
+    int d = dir_index((int)Xj - (int)Xi, (int)Yj - (int)Yi, (int)Zj - (int)Zi);
+    const bool own_i = d < 9;
+    if (!own_i) d -= 9;
+    const long long base = own_i ? vertex_gid(S, Xi, Yi, Zi, mask) : vertex_gid(S, Xj, Yj, Zj, mask);
     return (IndexT)cut_vertex_id(base, mask, d);
 }
 
@@ -816,54 +911,99 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
             }
         }
     } else {
-        uint64_t trun = tb;
+        constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
+        __shared__ uint16_t s_ci[TILE_POINTS];    // cinfo of the owned cells (0 elsewhere)
+        __shared__ uint16_t s_off[TILE_POINTS];   // first output tet of the cell, relative to the tile
+        __shared__ uint16_t s_list[TILE_POINTS];  // cells with trimmed / dropped tets
+        __shared__ uint32_t s_n;
+        if (threadIdx.x == 0) s_n = 0u;
+        uint32_t run = 0;
         for (int r = 0; r < TILE_ROUNDS; ++r) {
             const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
             const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
             const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
             const uint16_t ci = owned ? S.cinfo[cidx(S, cx, cy, cz)] : (uint16_t)0;
-            const uint32_t count = ci & CI_COUNT_MASK;
+            const uint32_t count = ci_count(ci);
             uint32_t ttot;
             const uint32_t tex = block_exscan(count, &ttot, s_scan);
-            if (count) {
-                const Cell c = make_cell(cx, cy, cz);
-                uint64_t o = trun + tex;
-                for (int t = 0; t < 5; ++t) {
-                    TetNodes tn;
-                    load_tet(L, c, t, tn);
-                    TetOut to;
-                    if (ci & CI_FULL) {
-                        to.n = 1;
-                        to.node[0][0] = 0; to.node[0][1] = 1; to.node[0][2] = 2; to.node[0][3] = 3;
-                    } else {
-                        classify_tet(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
-                    }
-                    for (int q = 0; q < to.n; ++q) {
-                        IndexT id[4];
-                        double pos[4][3];
-                        bool have_pos = true;
+            s_ci[j] = ci;
+            s_off[j] = (uint16_t)(run + tex);
+            if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+            run += ttot;
+        }
+        __syncthreads();
+        // (a) cells whose five lattice tets are emitted untouched
+        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+            if (!(s_ci[j] & CI_FULL)) continue;
+            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+            const bool flip = c.flip();
+            IndexT id[8];
+            double pos[8][3];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const int code = to.node[q][m];
-                            id[m] = node_global_id<IndexT>(S, tn, code);
-                            if (QUALITY) {
-                                if (code < 4) {
-                                    warped_pos(L, tn.X[code], tn.Y[code], tn.Z[code], pos[m]);
-                                } else {
-                                    const long long lid = (long long)id[m] - S.vertex_base;
-                                    if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
-                                    else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
-                                }
-                            }
-                        }
-                        IndexT* dst = tets + 4 * o;
-                        dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
-                        if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
-                        ++o;
-                    }
+            for (int k = 0; k < 8; ++k) {
+                uint32_t X, Y, Z;
+                corner_xyz(c, k, X, Y, Z);
+                uint16_t mask;
+                id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
+                if (QUALITY) { pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z); }
+            }
+            IndexT* dst = tets + 4 * (tb + s_off[j]);
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
+                dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
+                dst[4 * t + 2] = id[T[t][2]];
+                dst[4 * t + 3] = id[T[t][3]];
+                if (QUALITY) {
+                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
+                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
                 }
             }
-            trun += ttot;
+        }
+        // (b) the lattice tets of the surface cells, one per thread
+        const uint32_t n = s_n;
+        for (uint32_t w = threadIdx.x; w < 5u * n; w += TILE_THREADS) {
+            const uint32_t j = s_list[w / 5u];
+            const int t = (int)(w % 5u);
+            const uint16_t ci = s_ci[j];
+            const uint32_t nt = ci_tet_n(ci, t);
+            if (nt == 0u) continue;
+            uint64_t o = tb + s_off[j];
+            for (int u = 0; u < t; ++u) o += ci_tet_n(ci, u);
+            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+            TetNodes tn;
+            load_tet(L, c, t, tn);
+            TetOut to;
+            classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+            double P[4][3];
+            if (QUALITY) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) warped_pos(L, tn.X[m], tn.Y[m], tn.Z[m], P[m]);
+            }
+            for (int q = 0; q < to.n; ++q) {
+                IndexT id[4];
+                double pos[4][3];
+                bool have_pos = true;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int code = to.node(q, m);
+                    id[m] = node_global_id<IndexT>(S, tn, code);
+                    if (QUALITY) {
+                        if (code < 4) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) pos[m][k] = pick4(P[0][k], P[1][k], P[2][k], P[3][k], code);
+                        } else {
+                            const long long lid = (long long)id[m] - S.vertex_base;
+                            if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
+                            else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
+                        }
+                    }
+                }
+                IndexT* dst = tets + 4 * o;
+                dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
+                if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
+                ++o;
+            }
         }
     }
     if (QUALITY) {

@@ -26,6 +26,65 @@ int upload_program(mc_ctx* ctx, const Program& p, DevBuf& out) {
     return MC_OK;
 }
 
+// Visit order of warp_vertices around one vertex (tessellate3d/src/lib.rs:146-173): tets in
+// cut_lattice order (8 cells x-major, Tile::TETS order), edges in Tet4::edge order on the flipped
+// node order.  It only depends on the parity of the vertex' coordinates.  Entry layout: see
+// k_warp_codes.
+static void build_warp_table(std::vector<unsigned long long>& tab) {
+    static const int LAT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    static const int TETS[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};
+    static const int EDGE[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    static const int DIR[18][3] = {{1, 0, 0},  {0, 1, 0},  {0, 0, 1},  {1, 1, 0},   {-1, 1, 0}, {1, 0, 1},  {-1, 0, 1}, {0, 1, 1},  {0, -1, 1},
+                                   {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {-1, 0, -1}, {1, 0, -1}, {0, -1, -1}, {0, 1, -1}};
+    tab.assign(8 * WT_STRIDE, 0ull);
+    for (int pc = 0; pc < 8; ++pc) {
+        const int par[3] = {pc & 1, (pc >> 1) & 1, (pc >> 2) & 1};
+        int n = 0;
+        for (int ax = -1; ax <= 0; ++ax)
+            for (int ay = -1; ay <= 0; ++ay)
+                for (int az = -1; az <= 0; ++az) {
+                    const int off[3] = {ax, ay, az};
+                    bool mir[3];
+                    for (int k = 0; k < 3; ++k) mir[k] = ((par[k] + (off[k] ? 1 : 0)) & 1) != 0;  // cell coordinate odd
+                    const bool flip = mir[0] ^ mir[1] ^ mir[2];
+                    // offset of tile corner k relative to the vertex
+                    auto corner_off = [&](int k, int o[3]) {
+                        for (int q = 0; q < 3; ++q) o[q] = off[q] + (mir[q] ? 1 - LAT[k][q] : LAT[k][q]);
+                    };
+                    for (int t = 0; t < 5; ++t) {
+                        int node[4];
+                        for (int m = 0; m < 4; ++m) node[m] = TETS[t][(flip && m < 2) ? 1 - m : m];
+                        int me = -1;
+                        for (int m = 0; m < 4; ++m) {
+                            int o[3];
+                            corner_off(node[m], o);
+                            if (o[0] == 0 && o[1] == 0 && o[2] == 0) me = m;
+                        }
+                        if (me < 0) continue;
+                        unsigned long long corners = 0ull;
+                        for (int m = 0; m < 4; ++m) {
+                            int o[3];
+                            corner_off(node[m], o);
+                            corners |= (unsigned long long)((o[0] + 1) | ((o[1] + 1) << 2) | ((o[2] + 1) << 4)) << (6 * m);
+                        }
+                        for (int e = 0; e < 6; ++e) {
+                            const int i0 = EDGE[e][0], i1 = EDGE[e][1];
+                            if (i0 != me && i1 != me) continue;
+                            int o[3];
+                            corner_off(node[i0 == me ? i1 : i0], o);
+                            int d = -1;
+                            for (int q = 0; q < 18; ++q)
+                                if (DIR[q][0] == o[0] && DIR[q][1] == o[1] && DIR[q][2] == o[2]) d = q;
+                            const unsigned long long orient = i0 == me ? 0ull : 1ull;
+                            tab[pc * WT_STRIDE + 1 + n++] = (unsigned long long)((ax ? 1 : 0) | (ay ? 2 : 0) | (az ? 4 : 0)) |
+                                                            ((unsigned long long)d << 3) | (orient << 8) | (corners << 9);
+                        }
+                    }
+                }
+        tab[pc * WT_STRIDE] = (unsigned long long)n;
+    }
+}
+
 static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
 }  // namespace mc
@@ -100,6 +159,19 @@ mc_ctx* mc_ctx_new(int device, void* stream) {
         c->sm_count = prop.multiProcessorCount;
         c->smem_optin = prop.sharedMemPerBlockOptin;
     }
+    {
+        std::vector<unsigned long long> tab;
+        build_warp_table(tab);
+        void* p = nullptr;
+        if (cudaMalloc(&p, tab.size() * 8) != cudaSuccess ||
+            cudaMemcpy(p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail(MC_ERR_CUDA, "mc_ctx_new: cannot upload the warp visit table");
+            delete c;
+            return nullptr;
+        }
+        c->d_warp_table.p = p;
+        c->d_warp_table.bytes = tab.size() * 8;
+    }
     return c;
 }
 void mc_ctx_free(mc_ctx* c) {
@@ -107,6 +179,7 @@ void mc_ctx_free(mc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->trim();
+    if (c->d_warp_table.p) cudaFree(c->d_warp_table.p);
     delete c;
 }
 int mc_ctx_device(const mc_ctx* c) { return c ? c->device : MC_ERR_ARG; }
@@ -179,6 +252,7 @@ Stuff make_stuff(const mc_mesh* m) {
     S.tvbase = (const unsigned long long*)m->d_vtile_vbase.p;
     S.ttbase = (const unsigned long long*)m->d_ttile_base.p;
     S.lower_table = (const unsigned long long*)m->lower_table;
+    S.warp_table = (const unsigned long long*)m->ctx->d_warp_table.p;
     S.vertex_base = (long long)m->vertex_base;
     return S;
 }

@@ -167,11 +167,17 @@ static __device__ void warped_pos(const Lattice& L, uint32_t X, uint32_t Y, uint
 // Output tets reference either an original node of the tet (code 0..3, index into the flipped
 // node order) or the cut vertex on the edge between a positive node i and a negative node j
 // (code 4 + 4*i + j).
+// `pick` helpers keep the small per-tet arrays in registers (dynamic indexing would put them in
+// local memory)
+template <typename T>
+__device__ __forceinline__ T pick4(T a, T b, T c, T d, int i) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
+
 struct TetOut {
     int n;               // number of output tets (0..3)
     int kase;            // -2 not kept, -1 passed through, 0..6 trim case
     bool ext_removed;    // all-zero tet dropped by the centroid test
-    uint8_t node[3][4];
+    unsigned long long nodes;  // 5 bits per node code, node m of output tet q at bit 5 * (4 q + m)
+    __device__ __forceinline__ int node(int q, int m) const { return (int)((nodes >> (5 * (4 * q + m))) & 31ull); }
 };
 
 // symbolic a,b,c,d = 0..3; cut(x,y) = 4 + 4x + y
@@ -192,6 +198,10 @@ struct TetNodes {
     uint32_t X[4], Y[4], Z[4];  // lattice coordinates of the flipped node order
     double p[4];                // post-warp phi
 };
+__device__ __forceinline__ uint32_t tet_X(const TetNodes& t, int i) { return pick4(t.X[0], t.X[1], t.X[2], t.X[3], i); }
+__device__ __forceinline__ uint32_t tet_Y(const TetNodes& t, int i) { return pick4(t.Y[0], t.Y[1], t.Y[2], t.Y[3], i); }
+__device__ __forceinline__ uint32_t tet_Z(const TetNodes& t, int i) { return pick4(t.Z[0], t.Z[1], t.Z[2], t.Z[3], i); }
+__device__ __forceinline__ double tet_p(const TetNodes& t, int i) { return pick4(t.p[0], t.p[1], t.p[2], t.p[3], i); }
 
 __device__ __forceinline__ void load_tet(const Lattice& L, const Cell& c, int t, TetNodes& tn) {
 #pragma unroll
@@ -202,20 +212,22 @@ __device__ __forceinline__ void load_tet(const Lattice& L, const Cell& c, int t,
 }
 
 // `removed_hint`: < 0 -> evaluate the exterior test with the SDF program; 0/1 -> cached result
-static __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNodes& tn,
+template <bool CAN_EVAL>
+__device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNodes& tn,
                              const uint64_t* __restrict__ prog, int removed_hint, TetOut& out) {
     out.n = 0;
     out.kase = -2;
     out.ext_removed = false;
+    out.nodes = 0ull;
     if (!tet_kept(L, c, t)) return;
     const double* p = tn.p;
     if (p[0] <= 0.0 && p[1] <= 0.0 && p[2] <= 0.0 && p[3] <= 0.0) {
         out.kase = -1;
         if (p[0] == 0.0 && p[1] == 0.0 && p[2] == 0.0 && p[3] == 0.0) {
             bool removed;
-            if (removed_hint >= 0) {
-                removed = removed_hint != 0;
-            } else {
+            if (!CAN_EVAL || removed_hint >= 0) {
+                removed = removed_hint > 0;
+            } else if (CAN_EVAL) {
                 // centroid = (((a + b) + c) + d) / 4 of the warped positions
                 double a[3], b[3], cc[3], d[3];
                 warped_pos(L, tn.X[0], tn.Y[0], tn.Z[0], a);
@@ -230,15 +242,16 @@ static __device__ void classify_tet(const Lattice& L, const Cell& c, int t, cons
             if (removed) { out.ext_removed = true; return; }
         }
         out.n = 1;
-        out.node[0][0] = 0; out.node[0][1] = 1; out.node[0][2] = 2; out.node[0][3] = 3;
+        out.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
         return;
     }
     // 5-comparator network, descending by (phi, first-touch order); tessellate3d/src/lib.rs:262-282
     int ia = 0, ib = 1, ic = 2, id = 3;
     bool flipped = false;
 #define MC_LESS(i, j)                                                                               \
-    (p[i] < p[j] || (p[i] == p[j] && first_touch_key(L, tn.X[i], tn.Y[i], tn.Z[i]) <              \
-                                         first_touch_key(L, tn.X[j], tn.Y[j], tn.Z[j])))
+    (tet_p(tn, i) < tet_p(tn, j) ||                                                                 \
+     (tet_p(tn, i) == tet_p(tn, j) && first_touch_key(L, tet_X(tn, i), tet_Y(tn, i), tet_Z(tn, i)) <  \
+                                          first_touch_key(L, tet_X(tn, j), tet_Y(tn, j), tet_Z(tn, j))))
 #define MC_CSWAP(u, v) if (MC_LESS(u, v)) { const int tmp_ = u; u = v; v = tmp_; flipped = !flipped; }
     MC_CSWAP(ia, ib)
     MC_CSWAP(ic, id)
@@ -247,28 +260,32 @@ static __device__ void classify_tet(const Lattice& L, const Cell& c, int t, cons
     MC_CSWAP(ib, ic)
 #undef MC_CSWAP
 #undef MC_LESS
+    const double pb = tet_p(tn, ib), pc = tet_p(tn, ic), pd = tet_p(tn, id);
     int kase;
-    if (p[id] == 0.0) kase = 0;
-    else if (p[ic] > 0.0) kase = 1;
-    else if (p[ib] < 0.0) kase = 2;
-    else if (p[ib] > 0.0 && p[ic] < 0.0) kase = 3;
-    else if (p[ib] == 0.0 && p[ic] == 0.0) kase = 4;
-    else if (p[ib] == 0.0) kase = 5;
+    if (pd == 0.0) kase = 0;
+    else if (pc > 0.0) kase = 1;
+    else if (pb < 0.0) kase = 2;
+    else if (pb > 0.0 && pc < 0.0) kase = 3;
+    else if (pb == 0.0 && pc == 0.0) kase = 4;
+    else if (pb == 0.0) kase = 5;
     else kase = 6;
     out.kase = kase;
     out.n = C_CASE_N[kase];
-    const int idx[4] = {ia, ib, ic, id};
+    unsigned long long nodes = 0ull;
     for (int q = 0; q < out.n; ++q) {
-        uint8_t nd[4];
+        int nd[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const int s = C_CASE_TET[kase][q][m];
-            nd[m] = (s < 4) ? (uint8_t)idx[s] : (uint8_t)(4 + 4 * idx[(s - 4) >> 2] + idx[(s - 4) & 3]);
+            const int sy = C_CASE_TET[kase][q][m];
+            nd[m] = (sy < 4) ? pick4(ia, ib, ic, id, sy)
+                             : (4 + 4 * pick4(ia, ib, ic, id, (sy - 4) >> 2) + pick4(ia, ib, ic, id, (sy - 4) & 3));
         }
         const bool f = flipped != (C_CASE_TET[kase][q][4] != 0);
-        if (f) { const uint8_t tmp = nd[0]; nd[0] = nd[1]; nd[1] = tmp; }
-        out.node[q][0] = nd[0]; out.node[q][1] = nd[1]; out.node[q][2] = nd[2]; out.node[q][3] = nd[3];
+        if (f) { const int tmp = nd[0]; nd[0] = nd[1]; nd[1] = tmp; }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) nodes |= (unsigned long long)nd[m] << (5 * (4 * q + m));
     }
+    out.nodes = nodes;
 }
 
 }  // namespace mc
