@@ -945,7 +945,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                 corner_xyz(c, k, X, Y, Z);
                 uint16_t mask;
                 id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
-                if (QUALITY) { pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z); }
+                if (QUALITY) warped_pos(L, X, Y, Z, pos[k]);  // untouched tets may still have warped (zero) corners
             }
             IndexT* dst = tets + 4 * (tb + s_off[j]);
 #pragma unroll
