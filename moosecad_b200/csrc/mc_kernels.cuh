@@ -795,93 +795,102 @@ __device__ __forceinline__ IndexT node_global_id(const Stuff& S, const TetNodes&
     return (IndexT)cut_vertex_id(base, mask, d);
 }
 
+// quality of the five un-warped lattice tets of one cell (kept out of line: it is evaluated for a
+// handful of representative cells per tile and would otherwise dictate the register budget)
+static __device__ __noinline__ void lattice_cell_quality(const Lattice& L, uint32_t cx, uint32_t cy, uint32_t cz,
+                                                         unsigned mult, QualityAcc& qa) {
+    constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
+    const Cell c = make_cell(cx, cy, cz);
+    const bool flip = c.flip();
+    double pos[8][3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t X, Y, Z;
+        corner_xyz(c, k, X, Y, Z);
+        pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z);
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]], mult);
+        else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]], mult);
+    }
+}
+
+// Interior tiles (every cell emits its five lattice tets, no vertex is warped): ids are pure
+// arithmetic, the tets of 256 cells at a time are staged in shared memory and written with
+// fully coalesced 16-byte stores.  Quality: an un-warped lattice tet only depends on the
+// coordinate steps of its cell along the three axes and on the cell's mirroring, so it is
+// evaluated once per distinct (step, parity) combination of the tile, weighted by multiplicity.
 template <typename IndexT, bool QUALITY>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords,
-           unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t s_scan[9];
+k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ counters) {
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    const uint8_t cu = S.cuni[blockIdx.x];
-    if (cu == CU_EMPTY || X0 >= L.nx || Y0 >= L.ny) return;
+    if (S.cuni[blockIdx.x] != CU_FULL || X0 >= L.nx || Y0 >= L.ny) return;
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
     if (zhi <= zlo) return;
     const uint64_t tb = S.ttbase[blockIdx.x];
     QualityAcc qa = {1.0, 0.0, 0u};
-    if (cu == CU_FULL) {
-        constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
-        const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
-        // the (up to) 8 point tiles holding the corners of this cell tile
-        __shared__ uint8_t s_nvu[8];
-        __shared__ unsigned long long s_nbase[8];
-        __shared__ TileBox s_nbox[8];
-        // quality: an un-warped lattice tet only depends on the coordinate steps of its cell along
-        // the three axes and on the cell's mirroring, so it is evaluated once per distinct
-        // (step, parity) combination of the tile and weighted by its multiplicity
-        __shared__ double s_step[3][TS];
-        __shared__ uint8_t s_rep[3][TS];
-        __shared__ uint16_t s_mult[3][TS];
-        if (threadIdx.x < 8) {
-            const uint32_t tix = (uint32_t)(blockIdx.x % S.g.ntx) + (threadIdx.x & 1u);
-            const uint32_t tiy = (uint32_t)((blockIdx.x / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
-            const uint32_t tiz = (uint32_t)(blockIdx.x / (S.g.ntx * S.g.nty)) + (threadIdx.x >> 2);
-            uint8_t vu = VU_ACTIVE;
-            if (tix < S.g.ntx && tiy < S.g.nty && tiz < S.g.ntz) {
-                const uint32_t t = (tiz * S.g.nty + tiy) * S.g.ntx + tix;
-                vu = S.vuni[t];
-                s_nbase[threadIdx.x] = S.tvbase[t];
-                s_nbox[threadIdx.x] = tile_box(S, t);
-            }
-            s_nvu[threadIdx.x] = vu;
+    constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
+    const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
+    // the (up to) 8 point tiles holding the corners of this cell tile
+    __shared__ uint8_t s_nvu[8];
+    __shared__ unsigned long long s_nbase[8];
+    __shared__ TileBox s_nbox[8];
+    __shared__ double s_step[3][TS];
+    __shared__ uint8_t s_rep[3][TS];
+    __shared__ uint16_t s_mult[3][TS];
+    __shared__ IndexT s_out[5][TILE_THREADS][4];
+    if (threadIdx.x < 8) {
+        const uint32_t tix = (uint32_t)(blockIdx.x % S.g.ntx) + (threadIdx.x & 1u);
+        const uint32_t tiy = (uint32_t)((blockIdx.x / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
+        const uint32_t tiz = (uint32_t)(blockIdx.x / (S.g.ntx * S.g.nty)) + (threadIdx.x >> 2);
+        uint8_t vu = VU_ACTIVE;
+        if (tix < S.g.ntx && tiy < S.g.nty && tiz < S.g.ntz) {
+            const uint32_t t = (tiz * S.g.nty + tiy) * S.g.ntx + tix;
+            vu = S.vuni[t];
+            s_nbase[threadIdx.x] = S.tvbase[t];
+            s_nbox[threadIdx.x] = tile_box(S, t);
         }
-        if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
-            const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
-            const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
-            const bool valid = a == 0 ? cc < L.nx : (a == 1 ? cc < L.ny : (cc >= zlo && cc < zhi));
-            double d = 0.0;
-            if (valid) d = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
-            s_step[a][i] = d;
-            s_rep[a][i] = valid ? 1 : 0;
-        }
-        __syncthreads();
-        if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
-            const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
-            const uint32_t base = a == 0 ? X0 : (a == 1 ? Y0 : Z0);
-            bool rep = s_rep[a][i] != 0;
-            uint32_t mult = 0;
-            if (rep) {
-                for (uint32_t q = 0; q < TS; ++q) {
-                    const bool same = s_rep[a][q] != 0 && s_step[a][q] == s_step[a][i] && (((base + q) ^ (base + i)) & 1u) == 0u;
-                    if (same) { ++mult; if (q < i) rep = false; }
-                }
-            }
-            s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
-        }
-        __syncthreads();
-        if (QUALITY) {
-            for (uint32_t j = threadIdx.x; j < TS * TS * TS; j += TILE_THREADS) {
-                const uint32_t ix = j & 15u, iy = (j >> 4) & 15u, iz = j >> 8;
-                const uint32_t mult = (uint32_t)s_mult[0][ix] * s_mult[1][iy] * s_mult[2][iz];
-                if (mult == 0u) continue;
-                const Cell c = make_cell(X0 + ix, Y0 + iy, Z0 + iz);
-                const bool flip = c.flip();
-                double pos[8][3];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    uint32_t X, Y, Z;
-                    corner_xyz(c, k, X, Y, Z);
-                    pos[k][0] = lat_x(L, X); pos[k][1] = lat_y(L, Y); pos[k][2] = lat_z(L, Z);
-                }
-#pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]], mult);
-                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]], mult);
-                }
+        s_nvu[threadIdx.x] = vu;
+    }
+    if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
+        const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
+        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+        const bool valid = a == 0 ? cc < L.nx : (a == 1 ? cc < L.ny : (cc >= zlo && cc < zhi));
+        double d = 0.0;
+        if (valid) d = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
+        s_step[a][i] = d;
+        s_rep[a][i] = valid ? 1 : 0;
+    }
+    __syncthreads();
+    if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
+        const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
+        const uint32_t base = a == 0 ? X0 : (a == 1 ? Y0 : Z0);
+        bool rep = s_rep[a][i] != 0;
+        uint32_t mult = 0;
+        if (rep) {
+            for (uint32_t q = 0; q < TS; ++q) {
+                const bool same = s_rep[a][q] != 0 && s_step[a][q] == s_step[a][i] && (((base + q) ^ (base + i)) & 1u) == 0u;
+                if (same) { ++mult; if (q < i) rep = false; }
             }
         }
-        const uint32_t n = nxt * nyt * (zhi - zlo);
-        for (uint32_t j = threadIdx.x; j < n; j += TILE_THREADS) {
+        s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
+    }
+    __syncthreads();
+    if (QUALITY) {
+        for (uint32_t j = threadIdx.x; j < TS * TS * TS; j += TILE_THREADS) {
+            const uint32_t ix = j & 15u, iy = (j >> 4) & 15u, iz = j >> 8;
+            const uint32_t mult = (uint32_t)s_mult[0][ix] * s_mult[1][iy] * s_mult[2][iz];
+            if (mult == 0u) continue;
+            lattice_cell_quality(L, X0 + ix, Y0 + iy, Z0 + iz, mult, qa);
+        }
+    }
+    const uint32_t n = nxt * nyt * (zhi - zlo);
+    for (uint32_t base = 0; base < n; base += TILE_THREADS) {
+        const uint32_t j = base + threadIdx.x;
+        if (j < n) {
             const uint32_t cx = X0 + j % nxt, cy = Y0 + (j / nxt) % nyt, cz = zlo + j / (nxt * nyt);
             const Cell c = make_cell(cx, cy, cz);
             const bool flip = c.flip();
@@ -900,17 +909,61 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                     id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
                 }
             }
-            IndexT* dst = tets + 4 * (tb + 5ull * j);
 #pragma unroll
             for (int t = 0; t < 5; ++t) {
                 // nodes 0 and 1 swapped when the cell is mirrored an odd number of times
-                dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
-                dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
-                dst[4 * t + 2] = id[T[t][2]];
-                dst[4 * t + 3] = id[T[t][3]];
+                s_out[t][threadIdx.x][0] = flip ? id[T[t][1]] : id[T[t][0]];
+                s_out[t][threadIdx.x][1] = flip ? id[T[t][0]] : id[T[t][1]];
+                s_out[t][threadIdx.x][2] = id[T[t][2]];
+                s_out[t][threadIdx.x][3] = id[T[t][3]];
             }
         }
-    } else {
+        __syncthreads();
+        // coalesced copy: output tet g of this round = cell g / 5, lattice tet g % 5
+        const uint32_t ncell = min((uint32_t)TILE_THREADS, n - base);
+        IndexT* dst = tets + 4 * (tb + 5ull * base);
+        if (sizeof(IndexT) == 4) {
+            uint4* dst4 = reinterpret_cast<uint4*>(dst);
+            for (uint32_t g = threadIdx.x; g < 5u * ncell; g += TILE_THREADS)
+                dst4[g] = *reinterpret_cast<const uint4*>(&s_out[g % 5u][g / 5u][0]);
+        } else {
+            for (uint32_t g = threadIdx.x; g < 20u * ncell; g += TILE_THREADS)
+                dst[g] = s_out[(g >> 2) % 5u][(g >> 2) / 5u][g & 3u];
+        }
+        __syncthreads();
+    }
+    if (QUALITY) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));
+            qa.armax = fmax(qa.armax, __shfl_xor_sync(0xffffffffu, qa.armax, o));
+            qa.inverted += __shfl_xor_sync(0xffffffffu, qa.inverted, o);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            if (qa.inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)qa.inverted);
+            const unsigned long long bmin = (unsigned long long)__double_as_longlong(qa.armin);
+            const unsigned long long bmax = (unsigned long long)__double_as_longlong(qa.armax);
+            if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
+            if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
+        }
+    }
+}
+
+// Surface tiles.
+template <typename IndexT, bool QUALITY>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords,
+           unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_scan[9];
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    const uint64_t tb = S.ttbase[blockIdx.x];
+    QualityAcc qa = {1.0, 0.0, 0u};
+    {
         constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
         __shared__ uint16_t s_ci[TILE_POINTS];    // cinfo of the owned cells (0 elsewhere)
         __shared__ uint16_t s_off[TILE_POINTS];   // first output tet of the cell, relative to the tile

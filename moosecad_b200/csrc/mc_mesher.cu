@@ -541,12 +541,25 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         const unsigned grid = (unsigned)m->n_tiles;
         const double* coords = (const double*)m->d_coords.p;
         if (m->index_bytes == 4) {
-            if (quality) k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, (uint32_t*)m->d_tets.p, coords, counters);
-            else k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, (uint32_t*)m->d_tets.p, coords, counters);
+            uint32_t* out = (uint32_t*)m->d_tets.p;
+            if (quality) {
+                k_tet_emit_full<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+            } else {
+                k_tet_emit_full<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+            }
         } else {
-            if (quality) k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_tets.p, coords, counters);
-            else k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_tets.p, coords, counters);
+            unsigned long long* out = (unsigned long long*)m->d_tets.p;
+            if (quality) {
+                k_tet_emit_full<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+            } else {
+                k_tet_emit_full<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+            }
         }
+        c->launches++;
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }
