@@ -797,7 +797,7 @@ __device__ __forceinline__ IndexT node_global_id(const Stuff& S, const TetNodes&
 
 // quality of the five un-warped lattice tets of one cell (kept out of line: it is evaluated for a
 // handful of representative cells per tile and would otherwise dictate the register budget)
-static __device__ __noinline__ void lattice_cell_quality(const Lattice& L, uint32_t cx, uint32_t cy, uint32_t cz,
+static __device__ __forceinline__ void lattice_cell_quality(const Lattice& L, uint32_t cx, uint32_t cy, uint32_t cz,
                                                          unsigned mult, QualityAcc& qa) {
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const Cell c = make_cell(cx, cy, cz);
@@ -821,9 +821,9 @@ static __device__ __noinline__ void lattice_cell_quality(const Lattice& L, uint3
 // fully coalesced 16-byte stores.  Quality: an un-warped lattice tet only depends on the
 // coordinate steps of its cell along the three axes and on the cell's mirroring, so it is
 // evaluated once per distinct (step, parity) combination of the tile, weighted by multiplicity.
-template <typename IndexT, bool QUALITY>
+template <typename IndexT>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ counters) {
+k_tet_emit_full(Stuff S, IndexT* __restrict__ tets) {
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
@@ -831,17 +831,13 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restri
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
     if (zhi <= zlo) return;
     const uint64_t tb = S.ttbase[blockIdx.x];
-    QualityAcc qa = {1.0, 0.0, 0u};
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
     // the (up to) 8 point tiles holding the corners of this cell tile
     __shared__ uint8_t s_nvu[8];
     __shared__ unsigned long long s_nbase[8];
     __shared__ TileBox s_nbox[8];
-    __shared__ double s_step[3][TS];
-    __shared__ uint8_t s_rep[3][TS];
-    __shared__ uint16_t s_mult[3][TS];
-    __shared__ IndexT s_out[5][TILE_THREADS][4];
+    __shared__ __align__(16) IndexT s_out[5][TILE_THREADS][4];
     if (threadIdx.x < 8) {
         const uint32_t tix = (uint32_t)(blockIdx.x % S.g.ntx) + (threadIdx.x & 1u);
         const uint32_t tiy = (uint32_t)((blockIdx.x / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
@@ -855,38 +851,7 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restri
         }
         s_nvu[threadIdx.x] = vu;
     }
-    if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
-        const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
-        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
-        const bool valid = a == 0 ? cc < L.nx : (a == 1 ? cc < L.ny : (cc >= zlo && cc < zhi));
-        double d = 0.0;
-        if (valid) d = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
-        s_step[a][i] = d;
-        s_rep[a][i] = valid ? 1 : 0;
-    }
     __syncthreads();
-    if (QUALITY && threadIdx.x >= 32 && threadIdx.x < 32 + 3 * TS) {
-        const uint32_t a = (threadIdx.x - 32) / TS, i = (threadIdx.x - 32) % TS;
-        const uint32_t base = a == 0 ? X0 : (a == 1 ? Y0 : Z0);
-        bool rep = s_rep[a][i] != 0;
-        uint32_t mult = 0;
-        if (rep) {
-            for (uint32_t q = 0; q < TS; ++q) {
-                const bool same = s_rep[a][q] != 0 && s_step[a][q] == s_step[a][i] && (((base + q) ^ (base + i)) & 1u) == 0u;
-                if (same) { ++mult; if (q < i) rep = false; }
-            }
-        }
-        s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
-    }
-    __syncthreads();
-    if (QUALITY) {
-        for (uint32_t j = threadIdx.x; j < TS * TS * TS; j += TILE_THREADS) {
-            const uint32_t ix = j & 15u, iy = (j >> 4) & 15u, iz = j >> 8;
-            const uint32_t mult = (uint32_t)s_mult[0][ix] * s_mult[1][iy] * s_mult[2][iz];
-            if (mult == 0u) continue;
-            lattice_cell_quality(L, X0 + ix, Y0 + iy, Z0 + iz, mult, qa);
-        }
-    }
     const uint32_t n = nxt * nyt * (zhi - zlo);
     for (uint32_t base = 0; base < n; base += TILE_THREADS) {
         const uint32_t j = base + threadIdx.x;
@@ -932,20 +897,65 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restri
         }
         __syncthreads();
     }
-    if (QUALITY) {
+}
+
+// check_for_inverted_tets over the interior tiles: an un-warped lattice tet only depends on the
+// coordinate steps of its cell along the three axes and on the cell's mirroring, so it is
+// evaluated once per distinct (step, parity) combination of the tile, weighted by multiplicity.
+static __global__ void __launch_bounds__(64)
+k_full_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (S.cuni[blockIdx.x] != CU_FULL || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    __shared__ double s_step[3][TS];
+    __shared__ uint8_t s_rep[3][TS];
+    __shared__ uint16_t s_mult[3][TS];
+    if (threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+        const bool valid = a == 0 ? cc < L.nx : (a == 1 ? cc < L.ny : (cc >= zlo && cc < zhi));
+        double d = 0.0;
+        if (valid) d = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
+        s_step[a][i] = d;
+        s_rep[a][i] = valid ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        const uint32_t base = a == 0 ? X0 : (a == 1 ? Y0 : Z0);
+        bool rep = s_rep[a][i] != 0;
+        uint32_t mult = 0;
+        if (rep) {
+            for (uint32_t q = 0; q < TS; ++q) {
+                const bool same = s_rep[a][q] != 0 && s_step[a][q] == s_step[a][i] && (((base + q) ^ (base + i)) & 1u) == 0u;
+                if (same) { ++mult; if (q < i) rep = false; }
+            }
+        }
+        s_mult[a][i] = (uint16_t)(rep ? mult : 0u);  // 0 = not a representative
+    }
+    __syncthreads();
+    QualityAcc qa = {1.0, 0.0, 0u};
+    for (uint32_t j = threadIdx.x; j < TS * TS * TS; j += 64) {
+        const uint32_t ix = j & 15u, iy = (j >> 4) & 15u, iz = j >> 8;
+        const uint32_t mult = (uint32_t)s_mult[0][ix] * s_mult[1][iy] * s_mult[2][iz];
+        if (mult == 0u) continue;
+        lattice_cell_quality(L, X0 + ix, Y0 + iy, Z0 + iz, mult, qa);
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));
-            qa.armax = fmax(qa.armax, __shfl_xor_sync(0xffffffffu, qa.armax, o));
-            qa.inverted += __shfl_xor_sync(0xffffffffu, qa.inverted, o);
-        }
-        if ((threadIdx.x & 31u) == 0u) {
-            if (qa.inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)qa.inverted);
-            const unsigned long long bmin = (unsigned long long)__double_as_longlong(qa.armin);
-            const unsigned long long bmax = (unsigned long long)__double_as_longlong(qa.armax);
-            if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
-            if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));
+        qa.armax = fmax(qa.armax, __shfl_xor_sync(0xffffffffu, qa.armax, o));
+        qa.inverted += __shfl_xor_sync(0xffffffffu, qa.inverted, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (qa.inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)qa.inverted);
+        const unsigned long long bmin = (unsigned long long)__double_as_longlong(qa.armin);
+        const unsigned long long bmax = (unsigned long long)__double_as_longlong(qa.armax);
+        if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
+        if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
     }
 }
 

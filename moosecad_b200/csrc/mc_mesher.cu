@@ -543,24 +543,26 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         if (m->index_bytes == 4) {
             uint32_t* out = (uint32_t*)m->d_tets.p;
             if (quality) {
-                k_tet_emit_full<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
+                k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                 k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
             } else {
-                k_tet_emit_full<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
             }
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
             if (quality) {
-                k_tet_emit_full<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
+                k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                 k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
             } else {
-                k_tet_emit_full<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, out, counters);
+                k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
             }
         }
         c->launches++;
-        c->launches++;
+        c->launches += quality ? 3 : 2;
         MC_CUDA(cudaGetLastError());
     }
     MC_CUDA(cudaEventRecord(m->ev[9], s));
