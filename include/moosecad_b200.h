@@ -175,6 +175,10 @@ int mc_mesh_counts(const mc_mesh*, uint64_t counts[6]);
 /* tile specialisation of the SDF program (0 tiles when the plain evaluator was used): number of
  * tiles, sum over tiles of the compacted program size in 8-byte words, size of the full program */
 int mc_mesh_prune_stats(const mc_mesh*, uint64_t* n_tiles, uint64_t* pruned_words_total, uint64_t* full_words);
+/* tile bookkeeping of the last run: [0] tiles (16^3 lattice points each), [1] tiles whose SDF
+ * evaluation was skipped (proven interior / exterior), [2] point tiles and [3] cell tiles that
+ * needed the general stuffing path (the rest took the uniform-sign fast paths) */
+int mc_mesh_tile_stats(const mc_mesh*, uint64_t out[4]);
 /* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
  * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
 int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);

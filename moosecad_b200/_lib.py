@@ -82,6 +82,7 @@ SIGNATURES = {
     "mc_mesh_free": (None, [_P]),
     "mc_mesh_counts": (C.c_int, [_P, _PU64]),
     "mc_mesh_prune_stats": (C.c_int, [_P, _PU64, _PU64, _PU64]),
+    "mc_mesh_tile_stats": (C.c_int, [_P, _PU64]),
     "mc_mesh_upper_plane_table": (C.c_int, [_P, C.POINTER(_P), _PU64]),
     "mc_mesh_copy_upper_plane_table": (C.c_int, [_P, _P]),
     "mc_mesh_stats": (C.c_int, [_P, _PU64, _PU64, _PU64, _PD, _PU64]),

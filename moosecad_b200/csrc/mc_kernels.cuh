@@ -995,20 +995,42 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
             run += ttot;
         }
         __syncthreads();
+        // quality of the un-warped untouched cells: counted per (step, parity) class, see k_full_tile_quality
+        __shared__ double s_step[3][TS];
+        __shared__ uint8_t s_repidx[3][TS];
+        __shared__ __align__(4) uint16_t s_cnt[TILE_POINTS];
+        if (QUALITY) {
+            for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) s_cnt[j] = 0;
+            if (threadIdx.x < 3 * TS) {
+                const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+                const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+                s_step[a][i] = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
+            }
+            __syncthreads();
+            if (threadIdx.x < 3 * TS) {
+                const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+                uint32_t rep = i;
+                for (uint32_t q = 0; q < i; ++q)
+                    if (s_step[a][q] == s_step[a][i] && ((q ^ i) & 1u) == 0u) { rep = q; break; }
+                s_repidx[a][i] = (uint8_t)rep;
+            }
+            __syncthreads();
+        }
         // (a) cells whose five lattice tets are emitted untouched
         for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
             if (!(s_ci[j] & CI_FULL)) continue;
-            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+            const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+            const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
             const bool flip = c.flip();
             IndexT id[8];
-            double pos[8][3];
+            bool warped = false;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 uint32_t X, Y, Z;
                 corner_xyz(c, k, X, Y, Z);
                 uint16_t mask;
                 id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
-                if (QUALITY) warped_pos(L, X, Y, Z, pos[k]);  // untouched tets may still have warped (zero) corners
+                if (QUALITY) warped = warped || (L.wcode[pidx(L, X, Y, Z)] & 0x7f) != 0;
             }
             IndexT* dst = tets + 4 * (tb + s_off[j]);
 #pragma unroll
@@ -1017,10 +1039,33 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                 dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
                 dst[4 * t + 2] = id[T[t][2]];
                 dst[4 * t + 3] = id[T[t][3]];
-                if (QUALITY) {
-                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
-                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
+            }
+            if (QUALITY) {
+                if (!warped) {
+                    atomicAdd((unsigned int*)(s_cnt + ((((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx]) & ~1u)),
+                              1u << (16u * (s_repidx[0][lx] & 1u)));
+                } else {
+                    // untouched tets with warped (zero) corners
+                    double pos[8][3];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint32_t X, Y, Z;
+                        corner_xyz(c, k, X, Y, Z);
+                        warped_pos(L, X, Y, Z, pos[k]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) {
+                        if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
+                        else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
+                    }
                 }
+            }
+        }
+        if (QUALITY) {
+            __syncthreads();
+            for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+                const uint32_t cnt = s_cnt[j];
+                if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
             }
         }
         // (b) the lattice tets of the surface cells, one per thread

@@ -622,6 +622,15 @@ int mc_mesh_prune_stats(const mc_mesh* m, uint64_t* n_tiles, uint64_t* pruned_wo
     return MC_OK;
 }
 
+int mc_mesh_tile_stats(const mc_mesh* m, uint64_t out[4]) {
+    if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_tile_stats: bad argument");
+    out[0] = m->n_tiles;
+    out[1] = m->counters[CN_SKIPPED_TILES];
+    out[2] = m->counters[CN_ACTIVE_VTILES];
+    out[3] = m->counters[CN_ACTIVE_CTILES];
+    return MC_OK;
+}
+
 int mc_mesh_upper_plane_table(mc_mesh* m, void** d_table, uint64_t* n_entries) {
     if (!m || !d_table || !n_entries) return fail(MC_ERR_ARG, "mc_mesh_upper_plane_table: bad argument");
     if (m->phase < 2) return fail(MC_ERR_STATE, "mc_mesh_upper_plane_table: emit the vertices first");

@@ -209,7 +209,10 @@ class Mesh:
         _lib.check(self._lib.mc_mesh_stage_ms(self.handle, ms))
         nt, pw, fw = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _lib.check(self._lib.mc_mesh_prune_stats(self.handle, C.byref(nt), C.byref(pw), C.byref(fw)))
-        return {"prune": {"tiles": nt.value, "avg_words": (pw.value / nt.value) if nt.value else None,
+        ts = (C.c_uint64 * 4)()
+        _lib.check(self._lib.mc_mesh_tile_stats(self.handle, ts))
+        return {"tiles": {"total": ts[0], "sdf_skipped": ts[1], "active_point_tiles": ts[2], "active_cell_tiles": ts[3]},
+                "prune": {"tiles": nt.value, "avg_words": (pw.value / nt.value) if nt.value else None,
                           "full_words": fw.value},
                 "dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar),
                 "inverted": inv.value, "n_vertices": counts[0], "n_tets": counts[1],
