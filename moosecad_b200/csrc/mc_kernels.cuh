@@ -959,162 +959,194 @@ k_full_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
     }
 }
 
-// Surface tiles.
+// Surface tiles.  The ids / masks / warp flags of the tile's (TS+1)^3 lattice vertices are staged in
+// shared memory first (independent loads), so that the per-cell and per-tet work below never
+// chases global pointers.  Dynamic shared memory layout: see tet_emit_smem_bytes().
+constexpr int TE_H = (int)TS + 1;
+constexpr int TE_NP = TE_H * TE_H * TE_H;
+template <typename IndexT>
+constexpr size_t tet_emit_smem_bytes() {
+    return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + (size_t)TE_NP /*warped*/ + 15 +
+           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, cnt*/;
+}
+
 template <typename IndexT, bool QUALITY>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords,
            unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char te_smem[];
     __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_n;
+    __shared__ double s_step[3][TS];
+    __shared__ uint8_t s_repidx[3][TS];
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
     if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
     if (zhi <= zlo) return;
+    IndexT* s_gid = reinterpret_cast<IndexT*>(te_smem);
+    uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_gid + TE_NP);
+    uint8_t* s_wrp = reinterpret_cast<uint8_t*>(s_mask + TE_NP);
+    uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_wrp + TE_NP) + 15) & ~(uintptr_t)15);
+    uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
+    uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
+    uint16_t* s_cnt = s_list + TILE_POINTS; // un-warped untouched cells per (step, parity) class
+    constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[blockIdx.x];
     QualityAcc qa = {1.0, 0.0, 0u};
-    {
-        constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
-        __shared__ uint16_t s_ci[TILE_POINTS];    // cinfo of the owned cells (0 elsewhere)
-        __shared__ uint16_t s_off[TILE_POINTS];   // first output tet of the cell, relative to the tile
-        __shared__ uint16_t s_list[TILE_POINTS];  // cells with trimmed / dropped tets
-        __shared__ uint32_t s_n;
-        if (threadIdx.x == 0) s_n = 0u;
-        uint32_t run = 0;
-        for (int r = 0; r < TILE_ROUNDS; ++r) {
-            const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
-            const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
-            const uint16_t ci = owned ? S.cinfo[cidx(S, cx, cy, cz)] : (uint16_t)0;
-            const uint32_t count = ci_count(ci);
-            uint32_t ttot;
-            const uint32_t tex = block_exscan(count, &ttot, s_scan);
-            s_ci[j] = ci;
-            s_off[j] = (uint16_t)(run + tex);
-            if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
-            run += ttot;
+    if (threadIdx.x == 0) s_n = 0u;
+    // 1. vertex ids / masks / warp flags of the tile's corners
+    for (int idx = (int)threadIdx.x; idx < TE_NP; idx += TILE_THREADS) {
+        const uint32_t X = X0 + idx % TE_H, Y = Y0 + (idx / TE_H) % TE_H, Z = Z0 + idx / (TE_H * TE_H);
+        IndexT gid = 0;
+        uint16_t mask = 0;
+        uint8_t wr = 0;
+        if (X < L.NX && Y < L.NY && Z <= L.pz1 && S.vuni[tile_of(S.g, X, Y, Z)] != VU_POS) {
+            gid = (IndexT)vertex_gid(S, X, Y, Z, mask);
+            wr = (uint8_t)(L.wcode[pidx(L, X, Y, Z)] & 0x7f);
         }
-        __syncthreads();
-        // quality of the un-warped untouched cells: counted per (step, parity) class, see k_full_tile_quality
-        __shared__ double s_step[3][TS];
-        __shared__ uint8_t s_repidx[3][TS];
-        __shared__ __align__(4) uint16_t s_cnt[TILE_POINTS];
-        if (QUALITY) {
-            for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) s_cnt[j] = 0;
-            if (threadIdx.x < 3 * TS) {
-                const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
-                const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
-                s_step[a][i] = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
-            }
-            __syncthreads();
-            if (threadIdx.x < 3 * TS) {
-                const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
-                uint32_t rep = i;
-                for (uint32_t q = 0; q < i; ++q)
-                    if (s_step[a][q] == s_step[a][i] && ((q ^ i) & 1u) == 0u) { rep = q; break; }
-                s_repidx[a][i] = (uint8_t)rep;
-            }
-            __syncthreads();
+        s_gid[idx] = gid; s_mask[idx] = mask; s_wrp[idx] = wr;
+    }
+    // 2. per-cell info + offsets
+    uint32_t run = 0;
+    for (int r = 0; r < TILE_ROUNDS; ++r) {
+        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
+        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
+        const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
+        const uint16_t ci = owned ? S.cinfo[cidx(S, cx, cy, cz)] : (uint16_t)0;
+        const uint32_t count = ci_count(ci);
+        uint32_t ttot;
+        const uint32_t tex = block_exscan(count, &ttot, s_scan);
+        s_ci[j] = ci;
+        s_off[j] = (uint16_t)(run + tex);
+        if (QUALITY) s_cnt[j] = 0;
+        if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+        run += ttot;
+    }
+    if (QUALITY && threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+        s_step[a][i] = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
+    }
+    __syncthreads();
+    if (QUALITY && threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        uint32_t rep = i;
+        for (uint32_t q = 0; q < i; ++q)
+            if (s_step[a][q] == s_step[a][i] && ((q ^ i) & 1u) == 0u) { rep = q; break; }
+        s_repidx[a][i] = (uint8_t)rep;
+    }
+    __syncthreads();
+    // 3a. cells whose five lattice tets are emitted untouched
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+        if (!(s_ci[j] & CI_FULL)) continue;
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
+        const bool flip = c.flip();
+        IndexT id[8];
+        bool warped = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t X, Y, Z;
+            corner_xyz(c, k, X, Y, Z);
+            const int li = (int)((Z - Z0) * TE_H + (Y - Y0)) * TE_H + (int)(X - X0);
+            id[k] = s_gid[li];
+            warped = warped || s_wrp[li] != 0;
         }
-        // (a) cells whose five lattice tets are emitted untouched
-        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
-            if (!(s_ci[j] & CI_FULL)) continue;
-            const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-            const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
-            const bool flip = c.flip();
-            IndexT id[8];
-            bool warped = false;
+        IndexT* dst = tets + 4 * (tb + s_off[j]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t X, Y, Z;
-                corner_xyz(c, k, X, Y, Z);
-                uint16_t mask;
-                id[k] = (IndexT)vertex_gid(S, X, Y, Z, mask);
-                if (QUALITY) warped = warped || (L.wcode[pidx(L, X, Y, Z)] & 0x7f) != 0;
-            }
-            IndexT* dst = tets + 4 * (tb + s_off[j]);
-#pragma unroll
-            for (int t = 0; t < 5; ++t) {
-                dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
-                dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
-                dst[4 * t + 2] = id[T[t][2]];
-                dst[4 * t + 3] = id[T[t][3]];
-            }
-            if (QUALITY) {
-                if (!warped) {
-                    atomicAdd((unsigned int*)(s_cnt + ((((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx]) & ~1u)),
-                              1u << (16u * (s_repidx[0][lx] & 1u)));
-                } else {
-                    // untouched tets with warped (zero) corners
-                    double pos[8][3];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        uint32_t X, Y, Z;
-                        corner_xyz(c, k, X, Y, Z);
-                        warped_pos(L, X, Y, Z, pos[k]);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) {
-                        if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
-                        else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
-                    }
-                }
-            }
+        for (int t = 0; t < 5; ++t) {
+            dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
+            dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
+            dst[4 * t + 2] = id[T[t][2]];
+            dst[4 * t + 3] = id[T[t][3]];
         }
         if (QUALITY) {
-            __syncthreads();
-            for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
-                const uint32_t cnt = s_cnt[j];
-                if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
-            }
-        }
-        // (b) the lattice tets of the surface cells, one per thread
-        const uint32_t n = s_n;
-        for (uint32_t w = threadIdx.x; w < 5u * n; w += TILE_THREADS) {
-            const uint32_t j = s_list[w / 5u];
-            const int t = (int)(w % 5u);
-            const uint16_t ci = s_ci[j];
-            const uint32_t nt = ci_tet_n(ci, t);
-            if (nt == 0u) continue;
-            uint64_t o = tb + s_off[j];
-            for (int u = 0; u < t; ++u) o += ci_tet_n(ci, u);
-            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
-            TetNodes tn;
-            load_tet(L, c, t, tn);
-            TetOut to;
-            classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
-            double P[4][3];
-            if (QUALITY) {
+            if (!warped) {
+                // 16-bit counters updated through their aligned 32-bit word
+                const uint32_t cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
+                atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
+            } else {
+                // untouched tets with warped (zero) corners
+                double pos[8][3];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) warped_pos(L, tn.X[m], tn.Y[m], tn.Z[m], P[m]);
-            }
-            for (int q = 0; q < to.n; ++q) {
-                IndexT id[4];
-                double pos[4][3];
-                bool have_pos = true;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    const int code = to.node(q, m);
-                    id[m] = node_global_id<IndexT>(S, tn, code);
-                    if (QUALITY) {
-                        if (code < 4) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) pos[m][k] = pick4(P[0][k], P[1][k], P[2][k], P[3][k], code);
-                        } else {
-                            const long long lid = (long long)id[m] - S.vertex_base;
-                            if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
-                            else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
-                        }
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t X, Y, Z;
+                    corner_xyz(c, k, X, Y, Z);
+                    warped_pos(L, X, Y, Z, pos[k]);
                 }
-                IndexT* dst = tets + 4 * o;
-                dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
-                if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
-                ++o;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
+                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
+                }
             }
         }
     }
+    // 3b. the lattice tets of the surface cells, one per thread
+    const uint32_t n = s_n;
+    for (uint32_t w = threadIdx.x; w < 5u * n; w += TILE_THREADS) {
+        const uint32_t j = s_list[w / 5u];
+        const int t = (int)(w % 5u);
+        const uint16_t ci = s_ci[j];
+        const uint32_t nt = ci_tet_n(ci, t);
+        if (nt == 0u) continue;
+        uint64_t o = tb + s_off[j];
+        for (int u = 0; u < t; ++u) o += ci_tet_n(ci, u);
+        const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+        TetNodes tn;
+        load_tet(L, c, t, tn);
+        TetOut to;
+        classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+        double P[4][3];
+        if (QUALITY) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) warped_pos(L, tn.X[m], tn.Y[m], tn.Z[m], P[m]);
+        }
+        int li[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);
+        for (int q = 0; q < to.n; ++q) {
+            IndexT id[4];
+            double pos[4][3];
+            bool have_pos = true;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int code = to.node(q, m);
+                if (code < 4) {
+                    id[m] = s_gid[pick4(li[0], li[1], li[2], li[3], code)];
+                    if (QUALITY) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) pos[m][k] = pick4(P[0][k], P[1][k], P[2][k], P[3][k], code);
+                    }
+                } else {
+                    const int i = (code - 4) >> 2, jn = (code - 4) & 3;
+                    int d = dir_index((int)tet_X(tn, jn) - (int)tet_X(tn, i), (int)tet_Y(tn, jn) - (int)tet_Y(tn, i),
+                                      (int)tet_Z(tn, jn) - (int)tet_Z(tn, i));
+                    const bool own_i = d < 9;
+                    if (!own_i) d -= 9;
+                    const int lo = pick4(li[0], li[1], li[2], li[3], own_i ? i : jn);
+                    id[m] = (IndexT)cut_vertex_id((long long)s_gid[lo], s_mask[lo], d);
+                    if (QUALITY) {
+                        const long long lid = (long long)id[m] - S.vertex_base;
+                        if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
+                        else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
+                    }
+                }
+            }
+            IndexT* dst = tets + 4 * o;
+            dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
+            if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
+            ++o;
+        }
+    }
     if (QUALITY) {
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+            const uint32_t cnt = s_cnt[j];
+            if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));

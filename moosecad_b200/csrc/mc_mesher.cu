@@ -536,6 +536,16 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     if (rc != MC_OK) return rc;
     const Stuff S = make_stuff(m);
     const bool quality = !(m->flags & MC_OPT_SKIP_QUALITY);
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
+            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
+            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
+            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
+            attr_set = true;
+        }
+    }
     MC_CUDA(cudaEventRecord(m->ev[8], s));
     if (m->n_tets > 0) {
         const unsigned grid = (unsigned)m->n_tiles;
@@ -545,20 +555,20 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             if (quality) {
                 k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, coords, counters);
             } else {
                 k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
-                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, coords, counters);
             }
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
             if (quality) {
                 k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, coords, counters);
             } else {
                 k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
-                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, 0, s>>>(S, out, coords, counters);
+                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, coords, counters);
             }
         }
         c->launches++;
