@@ -248,10 +248,16 @@ __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNo
     // 5-comparator network, descending by (phi, first-touch order); tessellate3d/src/lib.rs:262-282
     int ia = 0, ib = 1, ic = 2, id = 3;
     bool flipped = false;
+    // Ties between two exact zeros (warped vertices) are left in place: they only occur as the
+    // (b, c) pair of case 4 or inside case 0, where swapping the labels together with `flipped`
+    // yields the same oriented tet, so the reference's vertex-id tie-break cannot matter there.
+    // Ties between equal non-zero values (symmetric scenes) do change the split and use the
+    // first-touch order like the reference.
 #define MC_LESS(i, j)                                                                               \
     (tet_p(tn, i) < tet_p(tn, j) ||                                                                 \
-     (tet_p(tn, i) == tet_p(tn, j) && first_touch_key(L, tet_X(tn, i), tet_Y(tn, i), tet_Z(tn, i)) <  \
-                                          first_touch_key(L, tet_X(tn, j), tet_Y(tn, j), tet_Z(tn, j))))
+     (tet_p(tn, i) == tet_p(tn, j) && tet_p(tn, i) != 0.0 &&                                        \
+      first_touch_key(L, tet_X(tn, i), tet_Y(tn, i), tet_Z(tn, i)) <                                \
+          first_touch_key(L, tet_X(tn, j), tet_Y(tn, j), tet_Z(tn, j))))
 #define MC_CSWAP(u, v) if (MC_LESS(u, v)) { const int tmp_ = u; u = v; v = tmp_; flipped = !flipped; }
     MC_CSWAP(ia, ib)
     MC_CSWAP(ic, id)
