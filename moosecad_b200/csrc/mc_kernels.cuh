@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -39,6 +39,10 @@ constexpr uint8_t CU_ACTIVE = 0, CU_FULL = 1, CU_EMPTY = 2; // cell tile: every 
 constexpr uint16_t CI_REMOVED_SHIFT = 10;
 constexpr uint16_t CI_FULL = 1u << 15;
 constexpr uint16_t CI_ALL_FULL = (uint16_t)(0x155u | CI_FULL);  // one output tet per lattice tet
+// on a FULL cell the removed bits are free: bit 10 marks "some corner is zero (possibly warped)",
+// i.e. the cell's tets are not congruent to plain lattice tets and get their quality evaluated
+// individually (k_tet_quality_list)
+constexpr uint16_t CI_FULL_ZERO_CORNER = 1u << 10;
 __host__ __device__ __forceinline__ uint32_t ci_tet_n(uint16_t ci, int t) { return (ci >> (2 * t)) & 3u; }
 __host__ __device__ __forceinline__ uint32_t ci_count(uint16_t ci) {
     return (ci & 3u) + ((ci >> 2) & 3u) + ((ci >> 4) & 3u) + ((ci >> 6) & 3u) + ((ci >> 8) & 3u);
@@ -393,7 +397,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
         s_cls[idx] = cl;
     }
     __syncthreads();
-    uint32_t my_out = 0, my_kept = 0;
+    uint32_t my_out = 0, my_kept = 0, my_listed = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
@@ -453,14 +457,16 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             uint16_t ci = (uint16_t)(b & 0x7fffu);
             const uint32_t kept = (uint32_t)__popc((b >> 16) & 31u);
             const bool untouched = kept == 5u && ((b >> 24) & 31u) == 0u && ((b >> CI_REMOVED_SHIFT) & 31u) == 0u;
-            if (untouched && ci_count(ci) == 5u) ci |= CI_FULL;
+            if (untouched && ci_count(ci) == 5u) ci |= (uint16_t)(CI_FULL | CI_FULL_ZERO_CORNER);
             S.cinfo[cidx(S, cx, cy, cz)] = ci;
-            if (cz >= S.c0 && cz < S.c1) { my_out += ci_count(ci); my_kept += kept; }
+            if (cz >= S.c0 && cz < S.c1) { my_out += ci_count(ci); my_kept += kept; my_listed += ci_count(ci); }
         }
         __syncthreads();
     }
     const unsigned long long tot = block_sum((unsigned long long)my_out | ((unsigned long long)my_kept << 32), &s_acc);
     if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+    const unsigned long long listed = block_sum((unsigned long long)my_listed, &s_acc);
+    if (threadIdx.x == 0 && listed) atomicAdd(&counters[CN_LISTED_TETS], listed);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -776,6 +782,23 @@ struct QualityAcc {
         armin = fmin(armin, ar);  // Float::min / max ignore NaN like fmin / fmax
         armax = fmax(armax, ar);
     }
+    // warp reduction + global min / max / count (all 32 lanes must call)
+    __device__ __forceinline__ void flush(unsigned long long* __restrict__ counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            armin = fmin(armin, __shfl_xor_sync(0xffffffffu, armin, o));
+            armax = fmax(armax, __shfl_xor_sync(0xffffffffu, armax, o));
+            inverted += __shfl_xor_sync(0xffffffffu, inverted, o);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            // aspect ratios are >= 0, so their bit patterns order like unsigned integers
+            if (inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)inverted);
+            const unsigned long long bmin = (unsigned long long)__double_as_longlong(armin);
+            const unsigned long long bmax = (unsigned long long)__double_as_longlong(armax);
+            if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
+            if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -814,6 +837,11 @@ static __device__ __forceinline__ void lattice_cell_quality(const Lattice& L, ui
         if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]], mult);
         else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]], mult);
     }
+}
+
+static __device__ __noinline__ void lattice_cell_quality_call(const Lattice& L, uint32_t cx, uint32_t cy, uint32_t cz,
+                                                              unsigned mult, QualityAcc& qa) {
+    lattice_cell_quality(L, cx, cy, cz, mult, qa);
 }
 
 // Interior tiles (every cell emits its five lattice tets, no vertex is warped): ids are pure
@@ -972,7 +1000,7 @@ constexpr size_t tet_emit_smem_bytes() {
 
 template <typename IndexT, bool QUALITY>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords,
+k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ qlist,
            unsigned long long* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char te_smem[];
     __shared__ uint32_t s_scan[9];
@@ -991,23 +1019,20 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
     uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_wrp + TE_NP) + 15) & ~(uintptr_t)15);
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
-    uint16_t* s_cnt = s_list + TILE_POINTS; // un-warped untouched cells per (step, parity) class
+    uint16_t* s_cnt = s_list + TILE_POINTS; // all-negative untouched cells per (step, parity) class
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[blockIdx.x];
-    QualityAcc qa = {1.0, 0.0, 0u};
     if (threadIdx.x == 0) s_n = 0u;
-    // 1. vertex ids / masks / warp flags of the tile's corners
+    // 1. vertex ids / masks of the tile's corners
     for (int idx = (int)threadIdx.x; idx < TE_NP; idx += TILE_THREADS) {
         const uint32_t X = X0 + idx % TE_H, Y = Y0 + (idx / TE_H) % TE_H, Z = Z0 + idx / (TE_H * TE_H);
         IndexT gid = 0;
         uint16_t mask = 0;
-        uint8_t wr = 0;
-        if (X < L.NX && Y < L.NY && Z <= L.pz1 && S.vuni[tile_of(S.g, X, Y, Z)] != VU_POS) {
+        if (X < L.NX && Y < L.NY && Z <= L.pz1 && S.vuni[tile_of(S.g, X, Y, Z)] != VU_POS)
             gid = (IndexT)vertex_gid(S, X, Y, Z, mask);
-            wr = (uint8_t)(L.wcode[pidx(L, X, Y, Z)] & 0x7f);
-        }
-        s_gid[idx] = gid; s_mask[idx] = mask; s_wrp[idx] = wr;
+        s_gid[idx] = gid; s_mask[idx] = mask;
     }
+    (void)s_wrp;
     // 2. per-cell info + offsets
     uint32_t run = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
@@ -1040,21 +1065,20 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
     for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
-        if (!(s_ci[j] & CI_FULL)) continue;
+        const uint16_t ci = s_ci[j];
+        if (!(ci & CI_FULL)) continue;
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
         const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
         const bool flip = c.flip();
         IndexT id[8];
-        bool warped = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             uint32_t X, Y, Z;
             corner_xyz(c, k, X, Y, Z);
-            const int li = (int)((Z - Z0) * TE_H + (Y - Y0)) * TE_H + (int)(X - X0);
-            id[k] = s_gid[li];
-            warped = warped || s_wrp[li] != 0;
+            id[k] = s_gid[(int)((Z - Z0) * TE_H + (Y - Y0)) * TE_H + (int)(X - X0)];
         }
-        IndexT* dst = tets + 4 * (tb + s_off[j]);
+        const uint64_t o = tb + s_off[j];
+        IndexT* dst = tets + 4 * o;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
@@ -1063,24 +1087,15 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
             dst[4 * t + 3] = id[T[t][3]];
         }
         if (QUALITY) {
-            if (!warped) {
-                // 16-bit counters updated through their aligned 32-bit word
+            if (!(ci & CI_FULL_ZERO_CORNER)) {
+                // all corners strictly negative: plain lattice tets, counted per class
+                // (16-bit counters updated through their aligned 32-bit word)
                 const uint32_t cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
                 atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
             } else {
-                // untouched tets with warped (zero) corners
-                double pos[8][3];
+                const unsigned long long at = atomicAdd(&counters[CN_QLIST_FILL], 5ull);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    uint32_t X, Y, Z;
-                    corner_xyz(c, k, X, Y, Z);
-                    warped_pos(L, X, Y, Z, pos[k]);
-                }
-#pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    if (flip) qa.add(pos[T[t][1]], pos[T[t][0]], pos[T[t][2]], pos[T[t][3]]);
-                    else qa.add(pos[T[t][0]], pos[T[t][1]], pos[T[t][2]], pos[T[t][3]]);
-                }
+                for (int t = 0; t < 5; ++t) qlist[at + t] = o + (uint64_t)t;
             }
         }
     }
@@ -1099,27 +1114,18 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
         load_tet(L, c, t, tn);
         TetOut to;
         classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
-        double P[4][3];
-        if (QUALITY) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) warped_pos(L, tn.X[m], tn.Y[m], tn.Z[m], P[m]);
-        }
         int li[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);
+        unsigned long long at = 0ull;
+        if (QUALITY) at = atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)to.n);
         for (int q = 0; q < to.n; ++q) {
             IndexT id[4];
-            double pos[4][3];
-            bool have_pos = true;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int code = to.node(q, m);
                 if (code < 4) {
                     id[m] = s_gid[pick4(li[0], li[1], li[2], li[3], code)];
-                    if (QUALITY) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) pos[m][k] = pick4(P[0][k], P[1][k], P[2][k], P[3][k], code);
-                    }
                 } else {
                     const int i = (code - 4) >> 2, jn = (code - 4) & 3;
                     int d = dir_index((int)tet_X(tn, jn) - (int)tet_X(tn, i), (int)tet_Y(tn, jn) - (int)tet_Y(tn, i),
@@ -1128,40 +1134,49 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, const double* __restrict__ coords
                     if (!own_i) d -= 9;
                     const int lo = pick4(li[0], li[1], li[2], li[3], own_i ? i : jn);
                     id[m] = (IndexT)cut_vertex_id((long long)s_gid[lo], s_mask[lo], d);
-                    if (QUALITY) {
-                        const long long lid = (long long)id[m] - S.vertex_base;
-                        if (lid < 0) have_pos = false;  // cut vertex owned by the rank below
-                        else { pos[m][0] = coords[3 * lid]; pos[m][1] = coords[3 * lid + 1]; pos[m][2] = coords[3 * lid + 2]; }
-                    }
                 }
             }
             IndexT* dst = tets + 4 * o;
             dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
-            if (QUALITY && have_pos) qa.add(pos[0], pos[1], pos[2], pos[3]);
+            if (QUALITY) qlist[at + (unsigned)q] = o;
             ++o;
         }
     }
     if (QUALITY) {
+        // plain lattice tets of this tile, one evaluation per class
+        QualityAcc qa = {1.0, 0.0, 0u};
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
             const uint32_t cnt = s_cnt[j];
-            if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
+            if (cnt) lattice_cell_quality_call(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            qa.armin = fmin(qa.armin, __shfl_xor_sync(0xffffffffu, qa.armin, o));
-            qa.armax = fmax(qa.armax, __shfl_xor_sync(0xffffffffu, qa.armax, o));
-            qa.inverted += __shfl_xor_sync(0xffffffffu, qa.inverted, o);
-        }
-        if ((threadIdx.x & 31u) == 0u) {
-            // aspect ratios are >= 0, so their bit patterns order like unsigned integers
-            if (qa.inverted) atomicAdd(&counters[CN_INVERTED], (unsigned long long)qa.inverted);
-            const unsigned long long bmin = (unsigned long long)__double_as_longlong(qa.armin);
-            const unsigned long long bmax = (unsigned long long)__double_as_longlong(qa.armax);
-            if (bmin < counters[CN_AR_MIN_BITS]) atomicMin(&counters[CN_AR_MIN_BITS], bmin);
-            if (bmax > counters[CN_AR_MAX_BITS]) atomicMax(&counters[CN_AR_MAX_BITS], bmax);
-        }
+        qa.flush(counters);
     }
+}
+
+// check_for_inverted_tets for the listed (trimmed or zero-cornered) tets: one tet per thread,
+// positions gathered from the emitted coordinates
+template <typename IndexT>
+__global__ void __launch_bounds__(256)
+k_tet_quality_list(const double* __restrict__ coords, const IndexT* __restrict__ tets,
+                   const unsigned long long* __restrict__ qlist, uint64_t n, long long vertex_base,
+                   unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    QualityAcc qa = {1.0, 0.0, 0u};
+    if (i < n) {
+        const unsigned long long e = qlist[i];
+        double p[4][3];
+        bool have = true;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const long long id = (long long)tets[4 * e + m] - vertex_base;
+            if (id < 0) { have = false; break; }  // vertex owned by the rank below
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p[m][k] = coords[3 * id + k];
+        }
+        if (have) qa.add(p[0], p[1], p[2], p[3]);
+    }
+    qa.flush(counters);
 }
 
 // id table of the plane z = Z for the rank above: (global id of the vertex's first output << 16) | mask

@@ -550,29 +550,34 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     if (m->n_tets > 0) {
         const unsigned grid = (unsigned)m->n_tiles;
         const double* coords = (const double*)m->d_coords.p;
+        const uint64_t nlist = quality ? m->counters[CN_LISTED_TETS] : 0;
+        DevBuf qlist;
+        rc = c->alloc(std::max<uint64_t>(nlist, 1) * 8, qlist);
+        if (rc != MC_OK) return rc;
+        unsigned long long* ql = (unsigned long long*)qlist.p;
         if (m->index_bytes == 4) {
             uint32_t* out = (uint32_t*)m->d_tets.p;
+            k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
             if (quality) {
-                k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, coords, counters);
+                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
+                if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
             } else {
-                k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
-                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, coords, counters);
+                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
             }
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
+            k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
             if (quality) {
-                k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, coords, counters);
+                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
+                if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
             } else {
-                k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
-                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, coords, counters);
+                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
             }
         }
-        c->launches++;
-        c->launches += quality ? 3 : 2;
+        c->release(qlist);
+        c->launches += quality ? 4 : 2;
         MC_CUDA(cudaGetLastError());
     }
     MC_CUDA(cudaEventRecord(m->ev[9], s));
