@@ -296,9 +296,9 @@ def main():
                     "peak_source": "measured live: mc_probe_fp64_nofma (DADD+DMUL, --fmad=false); "
                                    "not in MEASURED_PEAKS.json (SURVEY.md §8d)",
                     "flops_per_point_evaluate_all": info["flops"], "ms": stage_avg[0]}
-            stuff_ms = sum(stage_avg[1:7])
+            stuff_ms = sum(stage_avg[1:7])  # warp, classify, vertex, bisect, tet emit (+ fused quality)
             bytes_alg = 8 * P_total + 24 * n_verts + 4 * 4 * n_tets
-            roof2 = {"bound": "hbm", "kernels": "warp..quality (stages 1-6)",
+            roof2 = {"bound": "hbm", "kernels": "k_tile_minmax..k_tet_quality_list (all stages after the SDF field)",
                      "achieved": bytes_alg / (stuff_ms * 1e-3) / 1e9 if stuff_ms > 0 else None, "peak": hbm_peak,
                      "unit": "GB/s", "frac": bytes_alg / (stuff_ms * 1e-3) / 1e9 / hbm_peak if stuff_ms > 0 else None,
                      "algorithmic_bytes": bytes_alg, "ms": stuff_ms,
