@@ -188,8 +188,8 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        def one_step():
-            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev)
+        def one_step(flags=0):
+            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev, flags=flags)
             return sm.run()
 
         def stage_ms(h):
@@ -206,6 +206,12 @@ def main():
         for _ in range(warm):
             h = one_step()
             lib.mc_mesh_free(h)
+        # one instrumented pass: FP64 operations the SDF kernel executes per launch (untimed)
+        h = one_step(_lib.MC_OPT_COUNT_FLOPS)
+        ts = (C.c_uint64 * 5)()
+        lib.mc_mesh_tile_stats(h, ts)
+        tile_stats = list(ts)
+        lib.mc_mesh_free(h)
         fp64_peak = ctx.probe_fp64_nofma()
         barrier()
         sampler = ClockSampler(local_rank)
@@ -284,18 +290,25 @@ def main():
             except OSError:
                 pass
             hbm_peak = peaks.get("hbm_gbs", 6650.0)
-            # dominant kernel: k_sdf_field.  Algorithmic flops = evaluate-all flop model of the tape
-            # (mc_tape_program_info) x lattice points evaluated by one launch.
-            p_eval = (n + 1) ** 2 * (min(n, n // world + 4) + 1) if world > 1 else P_total
+            # dominant kernel: the SDF field kernel (k_sdf_field_tiled).  Algorithmic work per launch =
+            # the FP64 operations the tile-specialised evaluator executes (counted by an instrumented
+            # launch of the same kernel, MC_OPT_COUNT_FLOPS; add/sub/mul/max/cmp/div/sqrt = 1, exp 23,
+            # log 27).  The evaluate-all model of the full tape is given for reference.
+            p_eval = last_counts[2]
             sdf_s = stage_avg[0] * 1e-3
-            sdf_flops = info["flops"] * p_eval
-            roof = {"bound": "fp64_nofma", "kernel": "k_sdf_field",
+            sdf_flops = tile_stats[4]
+            roof = {"bound": "fp64_nofma", "kernel": "k_sdf_field_tiled (+ k_tile_decide)",
                     "achieved": sdf_flops / sdf_s / 1e12 if sdf_s > 0 else None,
                     "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                     "frac": (sdf_flops / sdf_s) / fp64_peak if sdf_s > 0 else None, "traffic": None,
                     "peak_source": "measured live: mc_probe_fp64_nofma (DADD+DMUL, --fmad=false); "
-                                   "not in MEASURED_PEAKS.json (SURVEY.md §8d)",
-                    "flops_per_point_evaluate_all": info["flops"], "ms": stage_avg[0]}
+                                   "not in MEASURED_PEAKS.json (SURVEY.md \u00a78d)",
+                    "flops_executed_per_launch": sdf_flops,
+                    "flops_per_point_executed": sdf_flops / p_eval if p_eval else None,
+                    "flops_per_point_evaluate_all_model": info["flops"],
+                    "tiles": {"total": tile_stats[0], "sdf_skipped_proven_uniform": tile_stats[1],
+                              "surface_point_tiles": tile_stats[2], "surface_cell_tiles": tile_stats[3]},
+                    "ms": stage_avg[0]}
             stuff_ms = sum(stage_avg[1:7])  # warp, classify, vertex, bisect, tet emit (+ fused quality)
             bytes_alg = 8 * P_total + 24 * n_verts + 4 * 4 * n_tets
             roof2 = {"bound": "hbm", "kernels": "k_tile_minmax..k_tet_quality_list (all stages after the SDF field)",
@@ -315,7 +328,7 @@ def main():
                                "l2": "working set (>= 8 B x lattice points per array) is far larger than the 126 MB L2; no flush needed",
                                "tape_words": info["words"]},
                     "tets_per_s": n_tets / (ms_step * 1e-3),
-                    "sdf_points_per_s": p_eval * world / sdf_s if sdf_s > 0 else None,
+                    "sdf_points_per_s": P_total / sdf_s if sdf_s > 0 else None,
                     "stage_ms": dict(zip(["sdf_field", "warp", "classify", "vertex", "bisect", "tet_emit", "quality",
                                           "boundary", "sidesets"], [round(x, 3) for x in stage_avg])),
                     "roofline": roof, "roofline_stuffing": roof2,

@@ -148,6 +148,7 @@ typedef struct mc_options {
 #define MC_OPT_SKIP_QUALITY 2u /* skip check_for_inverted_tets (stdout-only in the reference) */
 #define MC_OPT_NO_TILE_PRUNING 4u /* evaluate the full SDF program at every lattice point */
 #define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
+#define MC_OPT_COUNT_FLOPS 16u /* instrumented SDF kernel: count the FP64 operations it executes (slower) */
 
 /* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts
  * (mc_mesh_counts) are known; nothing has been emitted yet. */
@@ -177,8 +178,9 @@ int mc_mesh_counts(const mc_mesh*, uint64_t counts[6]);
 int mc_mesh_prune_stats(const mc_mesh*, uint64_t* n_tiles, uint64_t* pruned_words_total, uint64_t* full_words);
 /* tile bookkeeping of the last run: [0] tiles (16^3 lattice points each), [1] tiles whose SDF
  * evaluation was skipped (proven interior / exterior), [2] point tiles and [3] cell tiles that
- * needed the general stuffing path (the rest took the uniform-sign fast paths) */
-int mc_mesh_tile_stats(const mc_mesh*, uint64_t out[4]);
+ * needed the general stuffing path (the rest took the uniform-sign fast paths), [4] FP64
+ * operations executed by the SDF kernel (MC_OPT_COUNT_FLOPS runs only, else 0) */
+int mc_mesh_tile_stats(const mc_mesh*, uint64_t out[5]);
 /* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
  * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
 int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);

@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -121,10 +121,11 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 // a2: the lattice SDF field, plain evaluator.  Persistent blocks; the program is staged once per
 // block into shared memory; each warp evaluates WX x WY points of one z-plane per step with a
 // warp-uniform program counter and writes them with coalesced stores.
-template <int WX, int WY>
+template <int WX, int WY, bool COUNT>
 __global__ void __launch_bounds__(512)
 k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict__ prog_g, int nwords,
-            int prog_in_smem, uint32_t zplane0, uint32_t nplanes) {
+            int prog_in_smem, uint32_t zplane0, uint32_t nplanes, unsigned long long* __restrict__ flops_total) {
+    unsigned long long my_flops = 0ull;
     extern __shared__ uint64_t s_prog[];
     const uint64_t* prog = prog_g;
     if (prog_in_smem) {
@@ -147,8 +148,14 @@ k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict_
         const bool inside = X < L.NX && Y < L.NY;
         // out-of-range lanes evaluate a clamped point so that the warp stays converged
         const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
-        const double v = vm_eval<true>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z));
-        if (inside) phi_out[pidx(L, X, Y, Z)] = v;
+        unsigned long long fl = 0ull;
+        const double v = vm_eval_impl<true, COUNT>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+        if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_flops += __shfl_xor_sync(0xffffffffu, my_flops, o);
+        if ((threadIdx.x & 31u) == 0u && my_flops) atomicAdd(flops_total, my_flops);
     }
 }
 

@@ -282,7 +282,8 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
                                                                   (uint8_t*)m->d_dec.p, (int8_t*)m->d_tsign.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
-    auto kern = k_sdf_field_tiled<8, 4>;
+    const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
+    auto kern = count ? k_sdf_field_tiled<8, 4, true> : k_sdf_field_tiled<8, 4, false>;
     if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -294,7 +295,8 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                                                    n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
                                                    (const int8_t*)m->d_tsign.p, (m->flags & MC_OPT_KEEP_PHI) ? 0 : 1,
-                                                   pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES);
+                                                   pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES,
+                                                   (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     m->tiled_sdf = true;
@@ -319,7 +321,9 @@ static int launch_sdf_field(mc_mesh* m) {
     // cheap programs are HBM-write bound: 32 consecutive x per warp; heavy ones want compact
     // warp footprints so that bbox guards are warp-coherent
     const bool linear = m->prog.flops < 64;
-    auto kern = linear ? k_sdf_field<32, 1> : k_sdf_field<8, 4>;
+    const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
+    auto kern = linear ? (count ? k_sdf_field<32, 1, true> : k_sdf_field<32, 1, false>)
+                       : (count ? k_sdf_field<8, 4, true> : k_sdf_field<8, 4, false>);
     if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
@@ -330,7 +334,7 @@ static int launch_sdf_field(mc_mesh* m) {
     const uint64_t need = (nsteps + 15) / 16;
     if (grid > need) grid = need ? need : 1;
     kern<<<(unsigned)grid, 512, smem, c->stream>>>(m->L, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p, nwords,
-                                                   in_smem, m->L.pz0, nplanes);
+                                                   in_smem, m->L.pz0, nplanes, (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     return MC_OK;
@@ -637,12 +641,13 @@ int mc_mesh_prune_stats(const mc_mesh* m, uint64_t* n_tiles, uint64_t* pruned_wo
     return MC_OK;
 }
 
-int mc_mesh_tile_stats(const mc_mesh* m, uint64_t out[4]) {
+int mc_mesh_tile_stats(const mc_mesh* m, uint64_t out[5]) {
     if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_tile_stats: bad argument");
     out[0] = m->n_tiles;
     out[1] = m->counters[CN_SKIPPED_TILES];
     out[2] = m->counters[CN_ACTIVE_VTILES];
     out[3] = m->counters[CN_ACTIVE_CTILES];
+    out[4] = m->counters[CN_SDF_FLOPS];
     return MC_OK;
 }
 

@@ -251,13 +251,14 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
 
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
 // smem layout: [out program (max_words)] [dec (n_dec bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
-template <int WX, int WY>
+template <int WX, int WY, bool COUNT>
 __global__ void __launch_bounds__(256)
 k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
                   const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
-                  unsigned long long* __restrict__ skipped_tiles) {
+                  unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total) {
+    unsigned long long my_flops = 0ull;
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
     uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
@@ -409,9 +410,15 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             if (Z > L.pz1) continue;  // warp-uniform
             const bool inside = X < L.NX && Y < L.NY;
             const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
-            const double v = vm_eval<true>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z));
-            if (inside) phi_out[pidx(L, X, Y, Z)] = v;
+            unsigned long long fl = 0ull;
+            const double v = vm_eval_impl<true, COUNT>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+            if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
         }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_flops += __shfl_xor_sync(0xffffffffu, my_flops, o);
+        if ((tid & 31u) == 0u && my_flops) atomicAdd(flops_total, my_flops);
     }
 }
 

@@ -29,9 +29,15 @@ __device__ __forceinline__ double box_distance(const uint64_t* __restrict__ w, i
 }
 
 // rvmin / rvmax over k stacked child values v[0..k) (v[k-1] is `top`)
-template <bool IS_UNION>
+// FP64 operation counts used by the counting build of the evaluator (bench.py's roofline):
+// one per add / sub / mul / max / abs / compare, division and sqrt count 1, mc_exp = 23, mc_log = 27
+// (their main paths)
+#define MC_FLOPS_EXP 23
+#define MC_FLOPS_LOG 27
+
+template <bool IS_UNION, bool COUNT>
 __device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int base, int k, double top,
-                                              double r, double exact_range) {
+                                              double r, double exact_range, unsigned long long& flops) {
     // pass 1: running extremum + "two children are within exact_range" flag
     bool close = false;
     double m = IS_UNION ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL);
@@ -45,21 +51,23 @@ __device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int
             else if ((m - x) < exact_range) close = true;
         }
     }
+    if (COUNT) flops += 3ull * (unsigned)k;
     if (!close) return m;
     const double lim = IS_UNION ? (m + r) : (m - r);
     const double r4 = r / 4.0;
     double s = 0.0;
     for (int i = 0; i < k; ++i) {
         const double x = (i == k - 1) ? top : vs[base + i];
-        if (IS_UNION) { if (x < lim) s = s + mc_exp(-x / r4); }
-        else          { if (x > lim) s = s + mc_exp(x / r4); }
+        if (IS_UNION) { if (x < lim) { s = s + mc_exp(-x / r4); if (COUNT) flops += 4 + MC_FLOPS_EXP; } }
+        else          { if (x > lim) { s = s + mc_exp(x / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; } }
     }
+    if (COUNT) flops += 3 + MC_FLOPS_LOG;
     return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
 }
 
 // Evaluate the program at (x, y, z).  `w` may point to shared or global memory.
-template <bool UNIFORM>
-__device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, double z) {
+template <bool UNIFORM, bool COUNT>
+__device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double y, double z, unsigned long long& flops) {
     double vs[MC_MAX_VALUE_DEPTH + 1];   // element i lives in vs[i + 1]; the newest is `top`
     double ps[3 * MC_MAX_POINT_DEPTH];
     int sp = 0, psp = 0, pc = 0;
@@ -81,6 +89,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             const bool sign_positive = __double_as_longlong(q) >= 0;
             const bool inverted = (sm & 4u) != 0;
             MC_PUSH((sign_positive != inverted) ? (ap - d) : (-ap - d));
+            if (COUNT) flops += 2;
             pc += 2;
             break;
         }
@@ -88,17 +97,20 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             const double v = ((x * ld_f64(w, pc + 1) + y * ld_f64(w, pc + 2)) + z * ld_f64(w, pc + 3)) -
                              ld_f64(w, pc + 4);
             MC_PUSH(v);
+            if (COUNT) flops += 6;
             pc += 5;
             break;
         }
         case MC_OP_USQ: {
             MC_PUSH(((x * x + y * y) + z * z) - 1.0);
+            if (COUNT) flops += 6;
             pc += 1;
             break;
         }
         case MC_OP_CONE: {
             const double radius = fabs(ld_f64(w, pc + 1) * (z + ld_f64(w, pc + 2)));
             MC_PUSH((sqrt(x * x + y * y) - radius) * ld_f64(w, pc + 3));
+            if (COUNT) flops += 9;
             pc += 4;
             break;
         }
@@ -112,7 +124,9 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
                 const double e = (MC_HDR_OP(h) == MC_OP_GSPHERE) ? (sqrt((x * x + y * y) + z * z) - r)
                                                                  : (sqrt(x * x + y * y) - r);
                 if (pass) v = e;
+                if (COUNT) flops += (MC_HDR_OP(h) == MC_OP_GSPHERE) ? 7 : 5;
             }
+            if (COUNT) flops += 12;
             MC_PUSH(v);
             pc += 9;
             break;
@@ -121,6 +135,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             const double a = box_distance(w, pc + 1, x, y, z);
             const bool pass = a <= ld_f64(w, pc + 7);
             const unsigned level = MC_HDR_LEVEL(h);
+            if (COUNT) flops += 12;
             if (UNIFORM) {
                 const unsigned b = __ballot_sync(FULL, pass);
                 if (b == 0u) { MC_PUSH(a); pc = (int)MC_HDR_IDX(h); break; }
@@ -142,6 +157,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
                     const int g = (int)MC_HDR_IDX(h);
                     const double a = box_distance(w, g + 1, x, y, z);
                     if (!(a <= ld_f64(w, g + 7))) top = a;
+                    if (COUNT) flops += 12;
                 }
             }
             // non-uniform mode: only lanes that passed reach ENDG, nothing to select
@@ -150,6 +166,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
         }
         case MC_OP_NEG:
             top = -top;
+            if (COUNT) flops += 1;
             pc += 1;
             break;
         case MC_OP_CHILD:
@@ -157,14 +174,17 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             break;
         case MC_OP_BOXDIST:
             MC_PUSH(box_distance(w, pc + 1, x, y, z));
+            if (COUNT) flops += 11;
             pc += 7;
             break;
         case MC_OP_SPHERE:
             MC_PUSH(sqrt((x * x + y * y) + z * z) - ld_f64(w, pc + 1));
+            if (COUNT) flops += 7;
             pc += 2;
             break;
         case MC_OP_CYL:
             MC_PUSH(sqrt(x * x + y * y) - ld_f64(w, pc + 1));
+            if (COUNT) flops += 5;
             pc += 2;
             break;
         case MC_OP_BOOL: {
@@ -173,8 +193,8 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             const double r = ld_f64(w, pc + 1);
             const double er = ld_f64(w, pc + 2);
             const int base = sp - k + 1;  // v[i] (i < k-1) is vs[base + i]
-            const double res = (sm & 0x80u) ? smooth_fold<true>(vs, base, k, top, r, er)
-                                            : smooth_fold<false>(vs, base, k, top, r, er);
+            const double res = (sm & 0x80u) ? smooth_fold<true, COUNT>(vs, base, k, top, r, er, flops)
+                                            : smooth_fold<false, COUNT>(vs, base, k, top, r, er, flops);
             sp -= k - 1;
             top = res;
             pc += 3;
@@ -188,6 +208,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             const double ny = ((ld_f64(w, pc + 5) * x + ld_f64(w, pc + 6) * y) + ld_f64(w, pc + 7) * z) + ld_f64(w, pc + 8);
             const double nz = ((ld_f64(w, pc + 9) * x + ld_f64(w, pc + 10) * y) + ld_f64(w, pc + 11) * z) + ld_f64(w, pc + 12);
             x = nx; y = ny; z = nz;
+            if (COUNT) flops += 18;
             pc += 13;
             break;
         }
@@ -195,6 +216,7 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
             psp -= 3;
             x = ps[psp]; y = ps[psp + 1]; z = ps[psp + 2];
             top = top * ld_f64(w, pc + 1);
+            if (COUNT) flops += 1;
             pc += 2;
             break;
         }
@@ -203,6 +225,12 @@ __device__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, do
         }
     }
 #undef MC_PUSH
+}
+
+template <bool UNIFORM>
+__device__ __forceinline__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, double z) {
+    unsigned long long unused = 0ull;
+    return vm_eval_impl<UNIFORM, false>(w, x, y, z, unused);
 }
 
 }  // namespace mc
