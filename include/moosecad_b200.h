@@ -150,6 +150,12 @@ typedef struct mc_options {
 #define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
 #define MC_OPT_COUNT_FLOPS 16u /* instrumented SDF kernel: count the FP64 operations it executes (slower) */
 
+/* Load estimate for z-slab sharding: relative cost of every cell layer z (n = dim[2] doubles), from
+ * an interval evaluation of the SDF program over 16^3-point tiles (tiles that may contain the
+ * surface cost the most, proven-interior tiles cost their output, proven-exterior tiles almost
+ * nothing).  Deterministic, so every rank can compute the same partition. */
+int mc_estimate_layer_costs(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n);
+
 /* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts
  * (mc_mesh_counts) are known; nothing has been emitted yet. */
 int mc_tessellate_begin(mc_ctx*, const mc_tape* volume, int32_t root, double resolution,

@@ -340,6 +340,63 @@ static int launch_sdf_field(mc_mesh* m) {
     return MC_OK;
 }
 
+int mc_estimate_layer_costs(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n) {
+    if (!c || !volume || !cost) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
+    if (!volume->valid(root) || !(resolution > 0.0)) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
+    MC_CUDA(cudaSetDevice(c->device));
+    const Box& bb = volume->nodes[(size_t)root].bbox;
+    uint64_t dim[3];
+    for (int k = 0; k < 3; ++k) {
+        const double d = std::ceil((bb.hi[k] - bb.lo[k]) / resolution);
+        if (!(d >= 0.0) || !(d < 4294967295.0) || !std::isfinite(bb.lo[k]))
+            return fail(MC_ERR_BBOX, "mc_estimate_layer_costs: the volume's bounding box is not finite");
+        dim[k] = (uint64_t)d;
+    }
+    if (n != dim[2]) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: expected one entry per cell layer (" + std::to_string(dim[2]) + ")");
+    if (n == 0) return MC_OK;
+    Program prog;
+    std::string err;
+    int rc = volume->compile(root, resolution, prog, err);
+    if (rc != MC_OK) return fail(rc, err);
+    Lattice L{};
+    L.nx = (uint32_t)dim[0]; L.ny = (uint32_t)dim[1]; L.nz = (uint32_t)dim[2];
+    L.NX = L.nx + 1; L.NY = L.ny + 1; L.NZ = L.nz + 1;
+    L.ox = bb.lo[0]; L.oy = bb.lo[1]; L.oz = bb.lo[2];
+    L.res = resolution;
+    L.pz0 = 0; L.pz1 = L.nz;
+    TileGrid g;
+    g.ntx = (L.NX + TS - 1) / TS; g.nty = (L.NY + TS - 1) / TS; g.ntz = (L.NZ + TS - 1) / TS; g.z0 = 0;
+    const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
+    std::vector<double> layer((size_t)g.ntz, 1.0);
+    if (prog.n_decisions > 0) {
+        DevBuf dprog, ddec, dsign;
+        rc = upload_program(c, prog, dprog);
+        if (rc == MC_OK) rc = c->alloc((size_t)prog.n_decisions * ntiles, ddec);
+        if (rc == MC_OK) rc = c->alloc(ntiles + 4, dsign);
+        if (rc != MC_OK) return rc;
+        k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)dprog.p, ntiles,
+                                                                      (uint8_t*)ddec.p, (int8_t*)dsign.p);
+        c->launches++;
+        std::vector<int8_t> sign(ntiles);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sign.data(), dsign.p, ntiles, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        c->release(dprog); c->release(ddec); c->release(dsign);
+        if (e != cudaSuccess) return cuda_fail(e, "mc_estimate_layer_costs");
+        const uint64_t per = (uint64_t)g.ntx * g.nty;
+        for (uint32_t k = 0; k < g.ntz; ++k) {
+            double s = 0.0;
+            for (uint64_t i = 0; i < per; ++i) {
+                const int8_t sg = sign[(size_t)k * per + i];
+                s += sg == 0 ? 1.0 : (sg < 0 ? 0.15 : 0.02);
+            }
+            layer[k] = s;
+        }
+    }
+    for (uint64_t z = 0; z < n; ++z) cost[z] = layer[(size_t)(z / TS)] / (double)TS;
+    return MC_OK;
+}
+
 int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double relative_error,
                         const mc_slab* slab, const mc_options* opts, mc_mesh** out) {
     if (!c || !volume || !out) return fail(MC_ERR_ARG, "mc_tessellate_begin: null handle");

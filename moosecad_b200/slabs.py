@@ -31,6 +31,44 @@ def partition(nz, world_size):
     return out
 
 
+def partition_balanced(costs, world_size):
+    """Contiguous z ranges with (nearly) equal summed cost; every rank gets at least one layer
+    when there are enough layers."""
+    n = len(costs)
+    if world_size <= 1 or n <= world_size:
+        return partition(n, world_size)
+    total = float(sum(costs))
+    if not total > 0.0:
+        return partition(n, world_size)
+    out, z, acc = [], 0, 0.0
+    for r in range(world_size):
+        remaining_ranks = world_size - r
+        if remaining_ranks == 1:
+            out.append((z, n))
+            break
+        target = (total - acc) / remaining_ranks
+        z1, s = z, 0.0
+        # take layers until the target is reached, leaving at least one layer per remaining rank
+        while z1 < n - (remaining_ranks - 1) and (z1 == z or s + 0.5 * costs[z1] <= target):
+            s += costs[z1]
+            z1 += 1
+        out.append((z, z1))
+        acc += s
+        z = z1
+    return out
+
+
+def layer_costs(ctx, obj, resolution):
+    """Per-cell-layer load estimate (C ABI mc_estimate_layer_costs)."""
+    import numpy as np
+    dim = lattice_dim(obj.bbox(), float(resolution))
+    cost = np.zeros(dim[2], dtype=np.float64)
+    if dim[2]:
+        _lib.check(_lib.lib().mc_estimate_layer_costs(ctx.handle, obj.backend.handle, obj.node, float(resolution),
+                                                      cost.ctypes.data_as(_lib._PD), dim[2]))
+    return cost
+
+
 def bases_from_counts(all_counts, rank):
     """Exclusive scan over ranks of (n_vertices, n_tets)."""
     vb = sum(int(c[0]) for c in all_counts[:rank])
@@ -71,14 +109,19 @@ class SlabMesher:
         mesh_handle = sm.run()        # device-resident slab mesh with GLOBAL vertex ids
     """
 
-    def __init__(self, ctx, obj, resolution, relative_error, rank, world, group=None, device=None, flags=0):
+    def __init__(self, ctx, obj, resolution, relative_error, rank, world, group=None, device=None, flags=0,
+                 balanced=True):
         self.ctx, self.obj = ctx, obj
         self.res, self.err = float(resolution), float(relative_error)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.device = device
         self.flags = flags
         self.dim = lattice_dim(obj.bbox(), self.res)
-        self.slabs = partition(self.dim[2], self.world)
+        if self.world > 1 and balanced:
+            # the estimate is deterministic, every rank derives the same partition
+            self.slabs = partition_balanced(layer_costs(ctx, obj, self.res).tolist(), self.world)
+        else:
+            self.slabs = partition(self.dim[2], self.world)
         if any(z1 == z0 for z0, z1 in self.slabs):
             raise ValueError("fewer cell layers than ranks")
         self.all_counts = None

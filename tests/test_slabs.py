@@ -88,3 +88,15 @@ def test_slabs_match_single_slab(scene, n_slabs, ctx):
     # global ids: every vertex referenced, none duplicated
     assert np.unique(tets).size == len(coords)
     assert len(np.unique(coords, axis=0)) == len(coords)
+
+
+def test_partition_balanced():
+    c = [0.02] * 20 + [1.0] * 60 + [0.02] * 20
+    for w in (2, 4, 8):
+        p = slabs.partition_balanced(c, w)
+        assert p[0][0] == 0 and p[-1][1] == len(c) and all(a[1] == b[0] for a, b in zip(p, p[1:]))
+        loads = [sum(c[a:b]) for a, b in p]
+        assert max(loads) <= 1.15 * sum(c) / w
+        assert all(b > a for a, b in p)
+    assert slabs.partition_balanced([0.0] * 10, 2) == [(0, 5), (5, 10)]
+    assert slabs.partition_balanced([1.0] * 3, 1) == [(0, 3)]
