@@ -35,6 +35,11 @@ enum mc_opcode : uint32_t {
     MC_OP_BOXDIST = 14, // [hdr bbox[6]]                       push bbox.distance(p)  (guard fails on the whole tile)
     MC_OP_SPHERE = 15,  // [hdr r]                             push |p| - r            (guard passes on the whole tile)
     MC_OP_CYL = 16,     // [hdr r]                             push |p.xy| - r
+    // fused forms emitted by the lowering for the shapes geom.* builds all the time:
+    MC_OP_GBOX = 17,    // [hdr(dec) bbox[6] slack d[6] r exact_range]  guarded geom.cube: rvmax of the planes
+                        //                                     X, Y, Z, NegX, NegY, NegZ (luascad/src/lib.rs:173-187)
+    MC_OP_BOX = 18,     // [hdr d[6] r exact_range]            the same without the guard (compaction only)
+    MC_OP_GAPUSH = 19,  // [hdr(level, dec, jump) bbox[6] slack m[12]]  GUARD immediately followed by APUSH
 };
 
 #define MC_NO_LEVEL 255u
@@ -65,6 +70,9 @@ static MC_HD inline int mc_op_words(uint32_t op) {
     case MC_OP_APOP: return 2;
     case MC_OP_BOXDIST: return 7;
     case MC_OP_SPHERE: case MC_OP_CYL: return 2;
+    case MC_OP_GBOX: return 16;
+    case MC_OP_BOX: return 9;
+    case MC_OP_GAPUSH: return 20;
     default: return 1;  // END, USQ, ENDG, NEG, CHILD
     }
 }

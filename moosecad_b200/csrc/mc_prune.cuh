@@ -130,6 +130,29 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             MC_IPUSH(v);
             break;
         }
+        case MC_OP_GBOX: {
+            const Ival a = iv_box_distance(w, pc + 1, b);
+            const double slack = ld_f64(w, pc + 7);
+            // hard max of the six plane intervals, widened by the smooth branch's r/4 ln 6
+            Ival e = {-INF, -INF};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double dd = ld_f64(w, pc + 8 + i);
+                const double q0 = b[2 * (i % 3)], q1 = b[2 * (i % 3) + 1];
+                const Ival v = i >= 3 ? Ival{-q1 - dd, -q0 - dd} : Ival{q0 - dd, q1 - dd};
+                e.lo = fmax(e.lo, v.lo); e.hi = fmax(e.hi, v.hi);
+            }
+            e.hi += 0.25 * ld_f64(w, pc + 14) * 1.791759469228055;  // ln 6
+            e = widen(e);
+            uint8_t d = MC_DEC_KEEP;
+            Ival v = {fmin(a.lo, e.lo), fmax(a.hi, e.hi)};
+            if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
+            else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
+            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            MC_IPUSH(v);
+            break;
+        }
+        case MC_OP_GAPUSH:
         case MC_OP_GUARD: {
             const Ival a = iv_box_distance(w, pc + 1, b);
             const double slack = ld_f64(w, pc + 7);
@@ -142,6 +165,25 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
                 MC_IPUSH(a);
                 pc = (int)MC_HDR_IDX(h);
                 continue;
+            }
+            if (op == MC_OP_GAPUSH) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bs[bsp + k] = b[k];
+                bsp += 6;
+                double nb[6];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Ival s = {ld_f64(w, pc + 11 + 4 * i), ld_f64(w, pc + 11 + 4 * i)};
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const Ival t = iv_scale(ld_f64(w, pc + 8 + 4 * i + j), b[2 * j], b[2 * j + 1]);
+                        s.lo += t.lo; s.hi += t.hi;
+                    }
+                    s = widen(s);
+                    nb[2 * i] = s.lo; nb[2 * i + 1] = s.hi;
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) b[k] = nb[k];
             }
             break;
         }
@@ -308,7 +350,7 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             if (op == MC_OP_CHILD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
                 atomicAdd(&s_delta[i + 1], 1);
                 atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
-            } else if (op == MC_OP_GUARD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
+            } else if ((op == MC_OP_GUARD || op == MC_OP_GAPUSH) && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
                 atomicAdd(&s_delta[i + 1], 1);
                 atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
             }
@@ -329,10 +371,13 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             if (i < n_inst && depth == 0) {
                 const uint64_t h = prog[inst_start[i]];
                 const uint32_t op = MC_HDR_OP(h);
-                const uint8_t d = (op == MC_OP_GUARD || op == MC_OP_ENDG || op == MC_OP_GSPHERE || op == MC_OP_GCYL)
+                const uint8_t d = (op == MC_OP_GUARD || op == MC_OP_ENDG || op == MC_OP_GSPHERE || op == MC_OP_GCYL ||
+                                   op == MC_OP_GBOX || op == MC_OP_GAPUSH)
                                       ? s_dec[MC_HDR_DEC(h)] : (uint8_t)MC_DEC_KEEP;
                 switch (op) {
                 case MC_OP_GUARD: len = d == MC_DEC_PASS ? 0u : (d == MC_DEC_FAIL ? 7u : 8u); break;
+                case MC_OP_GAPUSH: len = d == MC_DEC_PASS ? 13u : (d == MC_DEC_FAIL ? 7u : 20u); break;
+                case MC_OP_GBOX: len = d == MC_DEC_PASS ? 9u : (d == MC_DEC_FAIL ? 7u : 16u); break;
                 case MC_OP_ENDG: len = d == MC_DEC_KEEP ? 1u : 0u; break;
                 case MC_OP_GSPHERE: case MC_OP_GCYL: len = d == MC_DEC_PASS ? 2u : (d == MC_DEC_FAIL ? 7u : 9u); break;
                 case MC_OP_CHILD: len = 0u; break;
@@ -366,6 +411,29 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 } else {
                     s_prog[dst] = MC_HDR(MC_OP_GUARD, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
                     for (uint32_t q = 1; q < 8; ++q) s_prog[dst + q] = prog[src + q];
+                }
+                break;
+            case MC_OP_GAPUSH:
+                if (len == 7u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+                } else if (len == 13u) {
+                    s_prog[dst] = MC_HDR(MC_OP_APUSH, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 13; ++q) s_prog[dst + q] = prog[src + 7 + q];
+                } else {
+                    s_prog[dst] = MC_HDR(MC_OP_GAPUSH, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+                    for (uint32_t q = 1; q < 20; ++q) s_prog[dst + q] = prog[src + q];
+                }
+                break;
+            case MC_OP_GBOX:
+                if (len == 7u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+                } else if (len == 9u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOX, 0, 0, 0, 0);
+                    for (uint32_t q = 1; q < 9; ++q) s_prog[dst + q] = prog[src + 7 + q];
+                } else {
+                    for (uint32_t q = 0; q < 16; ++q) s_prog[dst + q] = prog[src + q];
                 }
                 break;
             case MC_OP_ENDG:

@@ -251,6 +251,26 @@ struct Lowering {
         case NK_UNION:
         case NK_INTER: {
             const size_t k = n.children.size();
+            // geom.cube: Intersection of PlaneX, PlaneY, PlaneZ, PlaneNegX, PlaneNegY, PlaneNegZ
+            if (n.kind == NK_INTER && k == 6 && !box_is_infinite(n.bbox)) {
+                bool is_cube = true;
+                for (size_t i = 0; i < 6; ++i) {
+                    const Node& c = tape.nodes[(size_t)n.children[i]];
+                    is_cube = is_cube && c.kind == NK_PLANE && c.axis == (int)(i % 3) && c.inverted == (i >= 3);
+                }
+                if (is_cube) {
+                    word(MC_HDR(MC_OP_GBOX, 0, 0, next_dec++, 0));
+                    box_words(n.bbox, slack);
+                    for (size_t i = 0; i < 6; ++i) dword(tape.nodes[(size_t)n.children[i]].p[0]);
+                    dword(n.r);
+                    dword(n.r * tape.r_multiplier);
+                    prog.flops += 12 + 6 * 2 + 3 * 6 + (2 * 6 + 4 * 6 + 2);
+                    prog.n_exp += 6;
+                    prog.n_ln += 1;
+                    pushed();
+                    return MC_OK;
+                }
+            }
             if (k > 127) { err = "boolean node with more than 127 children"; return MC_ERR_LIMIT; }
             const bool guarded = !box_is_infinite(n.bbox);
             size_t guard_at = 0;
@@ -291,10 +311,9 @@ struct Lowering {
         case NK_AFFINE: {
             const size_t guard_at = prog.words.size();
             const uint32_t guard_dec = next_dec++;
-            word(0);
+            word(0);  // GAPUSH header, patched below
             box_words(n.bbox, slack);
             const int my_level = level++;
-            word(MC_HDR(MC_OP_APUSH, 0, 0, 0, 0));
             for (int i = 0; i < 3; ++i)
                 for (int j = 0; j < 4; ++j) dword(n.m.a[i][j]);
             ++pdepth;
@@ -306,7 +325,7 @@ struct Lowering {
             dword(n.scale_min);
             --level;
             word(MC_HDR(MC_OP_ENDG, 0, lvl(my_level), guard_dec, guard_at));
-            prog.words[guard_at] = MC_HDR(MC_OP_GUARD, 0, lvl(my_level), guard_dec, prog.words.size());
+            prog.words[guard_at] = MC_HDR(MC_OP_GAPUSH, 0, lvl(my_level), guard_dec, prog.words.size());
             prog.flops += 12 + 21 + 1;
             return MC_OK;
         }

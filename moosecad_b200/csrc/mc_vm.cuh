@@ -65,6 +65,40 @@ __device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int
     return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
 }
 
+// geom.cube: rvmax over the six axis planes, everything in registers
+template <bool COUNT>
+__device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int at, double x, double y, double z,
+                                           unsigned long long& flops) {
+    double v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double q = (i % 3) == 0 ? x : ((i % 3) == 1 ? y : z);
+        const double d = ld_f64(w, at + i);
+        const double ap = fabs(q);
+        const bool sign_positive = __double_as_longlong(q) >= 0;
+        const bool inverted = i >= 3;
+        v[i] = (sign_positive != inverted) ? (ap - d) : (-ap - d);
+    }
+    const double r = ld_f64(w, at + 6), exact_range = ld_f64(w, at + 7);
+    bool close = false;
+    double m = __longlong_as_double(0xfff0000000000000LL);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double xx = v[i];
+        if (xx > m) { close = (xx - m) < exact_range; m = xx; }
+        else if ((m - xx) < exact_range) close = true;
+    }
+    if (COUNT) flops += 12 + 18;
+    if (!close) return m;
+    const double lim = m - r, r4 = r / 4.0;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (v[i] > lim) { s = s + mc_exp(v[i] / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; }
+    if (COUNT) flops += 3 + MC_FLOPS_LOG;
+    return mc_log(s) * r4;
+}
+
 // Evaluate the program at (x, y, z).  `w` may point to shared or global memory.
 template <bool UNIFORM, bool COUNT>
 __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double y, double z, unsigned long long& flops) {
@@ -131,6 +165,26 @@ __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double 
             pc += 9;
             break;
         }
+        case MC_OP_GBOX: {
+            const double a = box_distance(w, pc + 1, x, y, z);
+            const bool pass = a <= ld_f64(w, pc + 7);
+            double v = a;
+            if (COUNT) flops += 12;
+            if (UNIFORM ? __any_sync(FULL, pass) : pass) {
+                const double e = box_fold<COUNT>(w, pc + 8, x, y, z, flops);
+                if (pass) v = e;
+            }
+            MC_PUSH(v);
+            pc += 16;
+            break;
+        }
+        case MC_OP_BOX: {
+            const double e = box_fold<COUNT>(w, pc + 1, x, y, z, flops);
+            MC_PUSH(e);
+            pc += 9;
+            break;
+        }
+        case MC_OP_GAPUSH:
         case MC_OP_GUARD: {
             const double a = box_distance(w, pc + 1, x, y, z);
             const bool pass = a <= ld_f64(w, pc + 7);
@@ -147,6 +201,20 @@ __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double 
                 if (!pass) { MC_PUSH(a); pc = (int)MC_HDR_IDX(h); break; }
             }
             pc += 8;
+            if (MC_HDR_OP(h) == MC_OP_GUARD) break;
+            pc -= 1;  // GAPUSH: the matrix follows the guard words; fall into APUSH with pc + 1 = first entry
+        }
+        // fallthrough
+        case MC_OP_APUSH: {
+            ps[psp] = x; ps[psp + 1] = y; ps[psp + 2] = z;
+            psp += 3;
+            // nalgebra transform_point: ((m0*x + m1*y) + m2*z) + t   (n == 1 for affine matrices)
+            const double nx = ((ld_f64(w, pc + 1) * x + ld_f64(w, pc + 2) * y) + ld_f64(w, pc + 3) * z) + ld_f64(w, pc + 4);
+            const double ny = ((ld_f64(w, pc + 5) * x + ld_f64(w, pc + 6) * y) + ld_f64(w, pc + 7) * z) + ld_f64(w, pc + 8);
+            const double nz = ((ld_f64(w, pc + 9) * x + ld_f64(w, pc + 10) * y) + ld_f64(w, pc + 11) * z) + ld_f64(w, pc + 12);
+            x = nx; y = ny; z = nz;
+            if (COUNT) flops += 18;
+            pc += 13;
             break;
         }
         case MC_OP_ENDG: {
@@ -198,18 +266,6 @@ __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double 
             sp -= k - 1;
             top = res;
             pc += 3;
-            break;
-        }
-        case MC_OP_APUSH: {
-            ps[psp] = x; ps[psp + 1] = y; ps[psp + 2] = z;
-            psp += 3;
-            // nalgebra transform_point: ((m0*x + m1*y) + m2*z) + t   (n == 1 for affine matrices)
-            const double nx = ((ld_f64(w, pc + 1) * x + ld_f64(w, pc + 2) * y) + ld_f64(w, pc + 3) * z) + ld_f64(w, pc + 4);
-            const double ny = ((ld_f64(w, pc + 5) * x + ld_f64(w, pc + 6) * y) + ld_f64(w, pc + 7) * z) + ld_f64(w, pc + 8);
-            const double nz = ((ld_f64(w, pc + 9) * x + ld_f64(w, pc + 10) * y) + ld_f64(w, pc + 11) * z) + ld_f64(w, pc + 12);
-            x = nx; y = ny; z = nz;
-            if (COUNT) flops += 18;
-            pc += 13;
             break;
         }
         case MC_OP_APOP: {
