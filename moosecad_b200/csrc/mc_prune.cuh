@@ -133,17 +133,28 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
         case MC_OP_GBOX: {
             const Ival a = iv_box_distance(w, pc + 1, b);
             const double slack = ld_f64(w, pc + 7);
-            // hard max of the six plane intervals, widened by the smooth branch's r/4 ln 6
-            Ival e = {-INF, -INF};
+            // the six plane intervals; a plane is droppable like any rvmax child
+            const double r = ld_f64(w, pc + 14), er = ld_f64(w, pc + 15);
+            const double margin = fmax(r, er);
+            Ival pv[6];
+            double ext = -INF;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 const double dd = ld_f64(w, pc + 8 + i);
                 const double q0 = b[2 * (i % 3)], q1 = b[2 * (i % 3) + 1];
-                const Ival v = i >= 3 ? Ival{-q1 - dd, -q0 - dd} : Ival{q0 - dd, q1 - dd};
-                e.lo = fmax(e.lo, v.lo); e.hi = fmax(e.hi, v.hi);
+                pv[i] = widen(i >= 3 ? Ival{-q1 - dd, -q0 - dd} : Ival{q0 - dd, q1 - dd});
+                ext = fmax(ext, pv[i].lo);
             }
-            e.hi += 0.25 * ld_f64(w, pc + 14) * 1.791759469228055;  // ln 6
-            e = widen(e);
+            Ival e = {-INF, -INF};
+            int kept = 0;
+            const uint32_t dbase = MC_HDR_DEC(h) + 1u;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const bool drop = pv[i].hi <= ext - margin - pad_of(ext - margin);
+                dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
+                if (!drop) { ++kept; e.lo = fmax(e.lo, pv[i].lo); e.hi = fmax(e.hi, pv[i].hi); }
+            }
+            if (kept > 1) { e.hi += 0.25 * r * 1.791759469228055; e = widen(e); }  // smooth branch: <= max + r/4 ln 6
             uint8_t d = MC_DEC_KEEP;
             Ival v = {fmin(a.lo, e.lo), fmax(a.hi, e.hi)};
             if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
@@ -429,11 +440,16 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 if (len == 7u) {
                     s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
                     for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
-                } else if (len == 9u) {
-                    s_prog[dst] = MC_HDR(MC_OP_BOX, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 9; ++q) s_prog[dst + q] = prog[src + 7 + q];
                 } else {
-                    for (uint32_t q = 0; q < 16; ++q) s_prog[dst + q] = prog[src + q];
+                    uint32_t mask = 0;
+                    for (uint32_t q = 0; q < 6; ++q) mask |= (s_dec[MC_HDR_DEC(h) + 1u + q] != MC_DEC_FAIL ? 1u : 0u) << q;
+                    if (len == 9u) {
+                        s_prog[dst] = MC_HDR(MC_OP_BOX, mask, 0, 0, 0);
+                        for (uint32_t q = 1; q < 9; ++q) s_prog[dst + q] = prog[src + 7 + q];
+                    } else {
+                        s_prog[dst] = MC_HDR(MC_OP_GBOX, mask, 0, 0, 0);
+                        for (uint32_t q = 1; q < 16; ++q) s_prog[dst + q] = prog[src + q];
+                    }
                 }
                 break;
             case MC_OP_ENDG:

@@ -259,7 +259,8 @@ struct Lowering {
                     is_cube = is_cube && c.kind == NK_PLANE && c.axis == (int)(i % 3) && c.inverted == (i >= 3);
                 }
                 if (is_cube) {
-                    word(MC_HDR(MC_OP_GBOX, 0, 0, next_dec++, 0));
+                    word(MC_HDR(MC_OP_GBOX, 0x3f, 0, next_dec, 0));  // small = mask of live planes
+                    next_dec += 7;  // the guard + one per plane (tile pruning)
                     box_words(n.bbox, slack);
                     for (size_t i = 0; i < 6; ++i) dword(tape.nodes[(size_t)n.children[i]].p[0]);
                     dword(n.r);

@@ -66,12 +66,15 @@ __device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int
 }
 
 // geom.cube: rvmax over the six axis planes, everything in registers
+// (`mask`: planes that can influence the result on this tile; dropped ones are skipped, which is
+// value-neutral, see mc_prune.cuh)
 template <bool COUNT>
-__device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int at, double x, double y, double z,
-                                           unsigned long long& flops) {
+__device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int at, unsigned mask, double x, double y,
+                                           double z, unsigned long long& flops) {
     double v[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
+        if (!((mask >> i) & 1u)) { v[i] = 0.0; continue; }
         const double q = (i % 3) == 0 ? x : ((i % 3) == 1 ? y : z);
         const double d = ld_f64(w, at + i);
         const double ap = fabs(q);
@@ -84,17 +87,18 @@ __device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int a
     double m = __longlong_as_double(0xfff0000000000000LL);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
+        if (!((mask >> i) & 1u)) continue;
         const double xx = v[i];
         if (xx > m) { close = (xx - m) < exact_range; m = xx; }
         else if ((m - xx) < exact_range) close = true;
     }
-    if (COUNT) flops += 12 + 18;
+    if (COUNT) flops += 5ull * (unsigned)__popc(mask);
     if (!close) return m;
     const double lim = m - r, r4 = r / 4.0;
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-        if (v[i] > lim) { s = s + mc_exp(v[i] / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; }
+        if (((mask >> i) & 1u) && v[i] > lim) { s = s + mc_exp(v[i] / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; }
     if (COUNT) flops += 3 + MC_FLOPS_LOG;
     return mc_log(s) * r4;
 }
@@ -171,7 +175,7 @@ __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double 
             double v = a;
             if (COUNT) flops += 12;
             if (UNIFORM ? __any_sync(FULL, pass) : pass) {
-                const double e = box_fold<COUNT>(w, pc + 8, x, y, z, flops);
+                const double e = box_fold<COUNT>(w, pc + 8, MC_HDR_SMALL(h), x, y, z, flops);
                 if (pass) v = e;
             }
             MC_PUSH(v);
@@ -179,7 +183,7 @@ __device__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double 
             break;
         }
         case MC_OP_BOX: {
-            const double e = box_fold<COUNT>(w, pc + 1, x, y, z, flops);
+            const double e = box_fold<COUNT>(w, pc + 1, MC_HDR_SMALL(h), x, y, z, flops);
             MC_PUSH(e);
             pc += 9;
             break;
