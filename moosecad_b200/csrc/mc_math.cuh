@@ -11,7 +11,7 @@
 
 namespace mc {
 
-__device__ __forceinline__ double mc_exp(double x) {
+static __device__ __noinline__ double mc_exp(double x) {
     const double LN2_HI = 6.93147180369123816490e-01;
     const double LN2_LO = 1.90821492927058770002e-10;
     const double INV_LN2 = 1.44269504088896338700e+00;
@@ -46,7 +46,7 @@ __device__ __forceinline__ double mc_exp(double x) {
     return y * 9.33263618503218878990e-302;
 }
 
-__device__ __forceinline__ double mc_log(double x) {
+static __device__ __noinline__ double mc_log(double x) {
     const double LN2_HI = 6.93147180369123816490e-01;
     const double LN2_LO = 1.90821492927058770002e-10;
     const double L1 = 6.666666666666735130e-01;

@@ -305,7 +305,7 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
 // smem layout: [out program (max_words)] [dec (n_dec bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
 template <int WX, int WY, bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
