@@ -95,11 +95,20 @@ class ObjectAdaptor:
 
 
 class SideSet:
-    """``mesh::SideSet`` (mesh/src/lib.rs:68-102): a named set of (elem, side) pairs."""
+    """``mesh::SideSet`` (mesh/src/lib.rs:68-102): a named set of (elem, side) pairs.
+
+    Large side-sets come back from the device as an (n, 2) uint64 array; the Python ``set`` of
+    tuples the reference's ``HashSet`` corresponds to is only materialised when ``sides()`` is
+    called.  ``array()`` gives the sorted (elem, side) rows without that cost."""
 
     def __init__(self, sides=(), name=None):
         self._name = name
-        self._sides = {(int(e), int(s)) for e, s in sides}
+        self._array = None
+        self._sides = None
+        if isinstance(sides, np.ndarray):
+            self._array = np.ascontiguousarray(sides, dtype=np.uint64).reshape(-1, 2)
+        else:
+            self._sides = {(int(e), int(s)) for e, s in sides}
 
     def name(self):
         return self._name
@@ -108,12 +117,24 @@ class SideSet:
         self._name = str(name)
 
     def add_side(self, elem, side):
-        new = (int(elem), int(side)) not in self._sides
-        self._sides.add((int(elem), int(side)))
+        s = self.sides()
+        new = (int(elem), int(side)) not in s
+        s.add((int(elem), int(side)))
+        self._array = None
         return new
 
     def sides(self):
+        if self._sides is None:
+            self._sides = set(map(tuple, self._array.tolist()))
         return self._sides
+
+    def array(self):
+        if self._array is None:
+            self._array = np.array(sorted(self._sides), dtype=np.uint64).reshape(-1, 2)
+        return self._array
+
+    def __len__(self):
+        return len(self._array) if self._array is not None else len(self._sides)
 
 
 class Mesh:
@@ -173,17 +194,15 @@ class Mesh:
         if n.value == 0:
             return SideSet()
         p = self._lib.mc_mesh_boundary_sides(self.handle)
-        arr = np.ctypeslib.as_array(p, shape=(n.value, 2))
-        return SideSet(map(tuple, arr.tolist()))
+        return SideSet(np.ctypeslib.as_array(p, shape=(n.value, 2)).copy())
 
     def add_boundary_side_set(self, name, boundary_obj):
         """One iteration of the side-set loop of src/main.rs:87-106 for a ``:boundary()`` object."""
         idx = _lib.check(self._lib.mc_mesh_add_sideset(self.handle, boundary_obj.backend.handle, boundary_obj.node))
         n = int(self._lib.mc_mesh_sideset_len(self.handle, idx))
-        sides = []
+        sides = np.zeros((0, 2), dtype=np.uint64)
         if n:
-            arr = np.ctypeslib.as_array(self._lib.mc_mesh_sideset(self.handle, idx), shape=(n, 2))
-            sides = list(map(tuple, arr.tolist()))
+            sides = np.ctypeslib.as_array(self._lib.mc_mesh_sideset(self.handle, idx), shape=(n, 2)).copy()
         ss = SideSet(sides, name)
         self._side_sets.append(ss)
         return ss

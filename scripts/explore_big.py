@@ -25,7 +25,7 @@ for w in which:
         dt = time.time() - t0
         st = mesh.stats()
         if rep == 1:
-            t1 = time.time(); nb = len(mesh.boundary().sides()) if "1024" not in w else -1; tb = time.time() - t1
+            t1 = time.time(); nb = len(mesh.boundary()) if "1024" not in w else -1; tb = time.time() - t1
             print(w, "dim", st["dim"], "verts", st["n_vertices"], "tets", st["n_tets"], "cut", st["n_cut"], "warped", st["n_warped"],
                   "wall %.3fs" % dt, "stage_ms", [round(x, 3) for x in st["stage_ms"]], "boundary", nb, "%.3fs" % tb,
                   "prog", info, "ws GB %.1f" % (ctx.workspace_bytes / 1e9), "ar", st["aspect_ratio"], "inv", st["inverted"], "prune", st["prune"], "tiles", st["tiles"], flush=True)
