@@ -242,9 +242,14 @@ static __global__ void k_face_select(const unsigned long long* __restrict__ key_
     }
     if ((j - i) & 1ull) {
         const unsigned long long at = atomicAdd(out_count, 1ull);
-        out_sides[2 * at] = lastp >> 2;
-        out_sides[2 * at + 1] = lastp & 3ull;
+        out_sides[at] = lastp;  // packed elem * 4 + side; sorted and unpacked afterwards
     }
+}
+
+static __global__ void k_unpack_sides(const unsigned long long* __restrict__ packed, uint64_t n,
+                                      unsigned long long* __restrict__ sides) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { sides[2 * i] = packed[i] >> 2; sides[2 * i + 1] = packed[i] & 3ull; }
 }
 
 // side-set membership: |approx_value(p, EPS)| <= EPS at the three nodes of every surface side
@@ -353,13 +358,30 @@ int compute_boundary(mc_mesh* m) {
         if (rc != MC_OK) return rc;
         k_face_select<<<nb, 256, 0, s>>>((const unsigned long long*)khi.p, (const unsigned long long*)klo.p,
                                          (const unsigned long long*)pay.p, (const unsigned long long*)ia.p, nf,
-                                         (unsigned long long*)m->d_sides.p, totals + 2);
+                                         (unsigned long long*)ka.p, totals + 2);
         c->launches++;
         MC_CUDA(cudaGetLastError());
         unsigned long long ns = 0;
         MC_CUDA(cudaMemcpyAsync(&ns, totals + 2, 8, cudaMemcpyDeviceToHost, s));
         MC_CUDA(cudaStreamSynchronize(s));
         m->n_sides = ns;
+        if (ns) {
+            // sorted by (elem, side): the reference's HashSet order is arbitrary
+            size_t tmp_bytes = 0;
+            MC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (unsigned long long*)ka.p, (unsigned long long*)kb.p,
+                                                   (int64_t)ns, 0, 64, s));
+            DevBuf tmp;
+            rc = c->alloc(tmp_bytes, tmp);
+            if (rc != MC_OK) return rc;
+            MC_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, (unsigned long long*)ka.p, (unsigned long long*)kb.p,
+                                                   (int64_t)ns, 0, 64, s));
+            k_unpack_sides<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>((const unsigned long long*)kb.p, ns,
+                                                                       (unsigned long long*)m->d_sides.p);
+            c->launches += 5;
+            MC_CUDA(cudaGetLastError());
+            MC_CUDA(cudaStreamSynchronize(s));
+            c->release(tmp);
+        }
         c->release(khi); c->release(klo); c->release(pay); c->release(ia); c->release(ib); c->release(ka); c->release(kb);
     }
     MC_CUDA(cudaEventRecord(e1, s));
@@ -372,14 +394,6 @@ int compute_boundary(mc_mesh* m) {
     m->stage_ms[7] = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    {
-        std::vector<std::pair<uint64_t, uint64_t>> v(m->n_sides);
-        for (uint64_t i = 0; i < m->n_sides; ++i) v[i] = {m->h_sides[2 * i], m->h_sides[2 * i + 1]};
-        std::sort(v.begin(), v.end());
-        for (uint64_t i = 0; i < m->n_sides; ++i) { m->h_sides[2 * i] = v[i].first; m->h_sides[2 * i + 1] = v[i].second; }
-        if (m->n_sides) MC_CUDA(cudaMemcpyAsync(m->d_sides.p, m->h_sides.data(), m->n_sides * 16, cudaMemcpyHostToDevice, s));
-        MC_CUDA(cudaStreamSynchronize(s));
-    }
     c->release(ftot); c->release(fbase); c->release(dtotal);
     m->have_boundary = true;
     return MC_OK;

@@ -327,8 +327,14 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         // of tets / edges that contain a vertex of another sign class, and those lie within one
         // lattice step, i.e. inside the neighbourhood.  Such tiles get a placeholder of the right
         // sign instead of being evaluated (unless the caller wants the field itself).
+        bool shell_only = false;
+        double shell_fill = 0.0;
         if (skip_uniform) {
             const int sg = tsign[tile];
+            // a tile of proven sign next to tiles of another / unknown sign: only its outer layer
+            // of points can be part of a tet or edge with a vertex of another sign class
+            shell_only = sg != 0;
+            shell_fill = sg < 0 ? -1.0 : 1.0;
             bool uniform = sg != 0;
             if (uniform) {
                 const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
@@ -485,6 +491,37 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         // 4. evaluate the tile: WX x WY points of one z-plane per warp step
         uint32_t X0, Y0, Z0;
         tile_origin(g, tile, X0, Y0, Z0);
+        if (shell_only) {
+            // interior (14^3 points): placeholder of the proven sign
+            for (uint32_t j = tid; j < (TS - 2) * (TS - 2) * (TS - 2); j += blockDim.x) {
+                const uint32_t X = X0 + 1 + j % (TS - 2), Y = Y0 + 1 + (j / (TS - 2)) % (TS - 2), Z = Z0 + 1 + j / ((TS - 2) * (TS - 2));
+                if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = shell_fill;
+            }
+            // outer layer: 2 * 256 + 14 * 60 = 1352 points, densely mapped onto the lanes
+            constexpr uint32_t NSHELL = 2 * TS * TS + (TS - 2) * (4 * TS - 4);
+            for (uint32_t base = (tid >> 5) * 32u; base < NSHELL; base += blockDim.x) {
+                uint32_t j = base + (tid & 31u);
+                const bool live = j < NSHELL;
+                if (!live) j = NSHELL - 1;
+                uint32_t lx, ly, lz;
+                if (j < 2 * TS * TS) {
+                    lz = j < TS * TS ? 0u : TS - 1; lx = j % TS; ly = (j / TS) % TS;
+                } else {
+                    const uint32_t r = j - 2 * TS * TS, q = r % (4 * TS - 4);
+                    lz = 1 + r / (4 * TS - 4);
+                    if (q < TS) { ly = 0; lx = q; }
+                    else if (q < 2 * TS) { ly = TS - 1; lx = q - TS; }
+                    else { lx = ((q - 2 * TS) / (TS - 2)) ? TS - 1 : 0u; ly = 1 + (q - 2 * TS) % (TS - 2); }
+                }
+                const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+                const bool inside = live && X < L.NX && Y < L.NY && Z <= L.pz1;
+                const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1, Zc = Z <= L.pz1 ? Z : L.pz1;
+                unsigned long long fl = 0ull;
+                const double v = vm_eval_impl<true, COUNT>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Zc), fl);
+                if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
+            }
+            continue;
+        }
         const uint32_t wpx = TS / WX, wpy = TS / WY;
         const uint32_t steps = wpx * wpy * TS;
         const uint32_t lane = tid & 31u, lx = lane % WX, ly = lane / WX;
