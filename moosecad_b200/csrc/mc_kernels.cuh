@@ -133,38 +133,24 @@ k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict_
         __syncthreads();
         prog = s_prog;
     }
-    constexpr int NP = MC_POINTS_PER_LANE;  // consecutive z-planes per lane
     const uint32_t ntx = (L.NX + WX - 1) / WX, nty = (L.NY + WY - 1) / WY;
-    const uint32_t npz = (nplanes + NP - 1) / NP;
-    const uint64_t ntiles = (uint64_t)ntx * nty * npz;
+    const uint64_t ntiles = (uint64_t)ntx * nty * nplanes;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lx = lane % WX, ly = lane / WX;
     const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint32_t zlast = zplane0 + nplanes - 1;
     for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles;
          tile += warps_total) {
         const uint32_t tx = (uint32_t)(tile % ntx);
         const uint64_t r = tile / ntx;
         const uint32_t ty = (uint32_t)(r % nty);
-        const uint32_t Zb = zplane0 + (uint32_t)(r / nty) * NP;
+        const uint32_t Z = zplane0 + (uint32_t)(r / nty);
         const uint32_t X = tx * WX + lx, Y = ty * WY + ly;
         const bool inside = X < L.NX && Y < L.NY;
         // out-of-range lanes evaluate a clamped point so that the warp stays converged
         const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
-        double xin[NP], yin[NP], zin[NP], vout[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            xin[p] = lat_x(L, Xc); yin[p] = lat_y(L, Yc);
-            zin[p] = lat_z(L, Zb + p <= zlast ? Zb + p : zlast);
-        }
         unsigned long long fl = 0ull;
-        vm_eval_multi<NP, COUNT>(prog, xin, yin, zin, vout, fl);
-        if (inside) {
-#pragma unroll
-            for (int p = 0; p < NP; ++p)
-                if (Zb + p <= zlast) phi_out[pidx(L, X, Y, Zb + p)] = vout[p];
-            my_flops += fl;
-        }
+        const double v = vm_eval_impl<true, COUNT>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+        if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
     }
     if (COUNT) {
 #pragma unroll

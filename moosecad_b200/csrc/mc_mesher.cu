@@ -329,7 +329,7 @@ static int launch_sdf_field(mc_mesh* m) {
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
     if (per_sm < 1) per_sm = 1;
     const uint64_t nsteps = (uint64_t)((m->L.NX + (linear ? 31 : 7)) / (linear ? 32 : 8)) *
-                            ((m->L.NY + (linear ? 0 : 3)) / (linear ? 1 : 4)) * ((nplanes + MC_POINTS_PER_LANE - 1) / MC_POINTS_PER_LANE);
+                            ((m->L.NY + (linear ? 0 : 3)) / (linear ? 1 : 4)) * nplanes;
     uint64_t grid = (uint64_t)c->sm_count * per_sm;
     const uint64_t need = (nsteps + 15) / 16;
     if (grid > need) grid = need ? need : 1;

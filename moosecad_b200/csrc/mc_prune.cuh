@@ -312,7 +312,6 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                   const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
                   unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total) {
     unsigned long long my_flops = 0ull;
-    constexpr int NP = MC_POINTS_PER_LANE;
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
     uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
@@ -498,65 +497,39 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 const uint32_t X = X0 + 1 + j % (TS - 2), Y = Y0 + 1 + (j / (TS - 2)) % (TS - 2), Z = Z0 + 1 + j / ((TS - 2) * (TS - 2));
                 if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = shell_fill;
             }
-            // outer layer: 2 * 256 + 14 * 60 = 1352 points, densely mapped onto the lanes, NP per lane
-            constexpr uint32_t NSHELL = 2 * TS * TS + (TS - 2) * (4 * TS - 4);
-            for (uint32_t base = (tid >> 5) * 32u * NP; base < NSHELL; base += blockDim.x * NP) {
-                double xin[NP], yin[NP], zin[NP], vout[NP];
-                size_t at[NP];
-                bool inside[NP];
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    uint32_t j = base + 32u * p + (tid & 31u);
-                    const bool live = j < NSHELL;
-                    if (!live) j = NSHELL - 1;
-                    uint32_t lx, ly, lz;
-                    if (j < 2 * TS * TS) {
-                        lz = j < TS * TS ? 0u : TS - 1; lx = j % TS; ly = (j / TS) % TS;
-                    } else {
-                        const uint32_t r = j - 2 * TS * TS, q = r % (4 * TS - 4);
-                        lz = 1 + r / (4 * TS - 4);
-                        if (q < TS) { ly = 0; lx = q; }
-                        else if (q < 2 * TS) { ly = TS - 1; lx = q - TS; }
-                        else { lx = ((q - 2 * TS) / (TS - 2)) ? TS - 1 : 0u; ly = 1 + (q - 2 * TS) % (TS - 2); }
-                    }
-                    const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-                    inside[p] = live && X < L.NX && Y < L.NY && Z <= L.pz1;
-                    const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1, Zc = Z <= L.pz1 ? Z : L.pz1;
-                    xin[p] = lat_x(L, Xc); yin[p] = lat_y(L, Yc); zin[p] = lat_z(L, Zc);
-                    at[p] = pidx(L, Xc, Yc, Zc);
-                }
-                unsigned long long fl = 0ull;
-                vm_eval_multi<NP, COUNT>(s_prog, xin, yin, zin, vout, fl);
-#pragma unroll
-                for (int p = 0; p < NP; ++p)
-                    if (inside[p]) phi_out[at[p]] = vout[p];
-                my_flops += fl;
-            }
-            continue;
         }
+        // full tile: 8 x 4 points of one z-plane per warp step; shell: 2 * 256 + 14 * 60 = 1352 outer
+        // points mapped densely onto the lanes.  One evaluator call site for both.
+        constexpr uint32_t NSHELL = 2 * TS * TS + (TS - 2) * (4 * TS - 4);
         const uint32_t wpx = TS / WX, wpy = TS / WY;
-        const uint32_t steps = wpx * wpy * (TS / NP);
-        const uint32_t lane = tid & 31u, lx = lane % WX, ly = lane / WX;
+        const uint32_t steps = shell_only ? (NSHELL + 31u) / 32u : wpx * wpy * TS;
+        const uint32_t lane = tid & 31u;
         for (uint32_t s = tid >> 5; s < steps; s += (blockDim.x >> 5)) {
-            const uint32_t sx = s % wpx, sy = (s / wpx) % wpy, sz = s / (wpx * wpy);
-            const uint32_t X = X0 + sx * WX + lx, Y = Y0 + sy * WY + ly, Zb = Z0 + sz * NP;
-            if (Zb > L.pz1) continue;  // warp-uniform
-            const bool inside = X < L.NX && Y < L.NY;
-            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
-            double xin[NP], yin[NP], zin[NP], vout[NP];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                xin[p] = lat_x(L, Xc); yin[p] = lat_y(L, Yc);
-                zin[p] = lat_z(L, Zb + p <= L.pz1 ? Zb + p : L.pz1);
+            uint32_t lx, ly, lz;
+            bool live = true;
+            if (shell_only) {
+                uint32_t j = s * 32u + lane;
+                live = j < NSHELL;
+                if (!live) j = NSHELL - 1;
+                if (j < 2 * TS * TS) {
+                    lz = j < TS * TS ? 0u : TS - 1; lx = j % TS; ly = (j / TS) % TS;
+                } else {
+                    const uint32_t r = j - 2 * TS * TS, q = r % (4 * TS - 4);
+                    lz = 1 + r / (4 * TS - 4);
+                    if (q < TS) { ly = 0; lx = q; }
+                    else if (q < 2 * TS) { ly = TS - 1; lx = q - TS; }
+                    else { lx = ((q - 2 * TS) / (TS - 2)) ? TS - 1 : 0u; ly = 1 + (q - 2 * TS) % (TS - 2); }
+                }
+            } else {
+                lx = (s % wpx) * WX + lane % WX; ly = ((s / wpx) % wpy) * WY + lane / WX; lz = s / (wpx * wpy);
             }
+            const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+            if (!shell_only && Z > L.pz1) continue;  // warp-uniform
+            const bool inside = live && X < L.NX && Y < L.NY && Z <= L.pz1;
+            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1, Zc = Z <= L.pz1 ? Z : L.pz1;
             unsigned long long fl = 0ull;
-            vm_eval_multi<NP, COUNT>(s_prog, xin, yin, zin, vout, fl);
-            if (inside) {
-#pragma unroll
-                for (int p = 0; p < NP; ++p)
-                    if (Zb + p <= L.pz1) phi_out[pidx(L, X, Y, Zb + p)] = vout[p];
-                my_flops += fl;
-            }
+            const double v = vm_eval_impl<true, COUNT>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Zc), fl);
+            if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
         }
     }
     if (COUNT) {

@@ -105,7 +105,7 @@ __device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int a
 
 // Evaluate the program at (x, y, z).  `w` may point to shared or global memory.
 template <bool UNIFORM, bool COUNT>
-__device__ __noinline__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double y, double z, unsigned long long& flops) {
+__device__ __forceinline__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double y, double z, unsigned long long& flops) {
     double vs[MC_MAX_VALUE_DEPTH + 1];   // element i lives in vs[i + 1]; the newest is `top`
     double ps[3 * MC_MAX_POINT_DEPTH];
     int sp = 0, psp = 0, pc = 0;
