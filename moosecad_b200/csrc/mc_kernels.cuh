@@ -121,7 +121,7 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 // a2: the lattice SDF field, plain evaluator.  Persistent blocks; the program is staged once per
 // block into shared memory; each warp evaluates WX x WY points of one z-plane per step with a
 // warp-uniform program counter and writes them with coalesced stores.
-template <int WX, int WY, bool COUNT>
+template <int WX, int WY, bool COUNT, bool SMALL>
 __global__ void __launch_bounds__(512)
 k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict__ prog_g, int nwords,
             int prog_in_smem, uint32_t zplane0, uint32_t nplanes, unsigned long long* __restrict__ flops_total) {
@@ -149,7 +149,7 @@ k_sdf_field(Lattice L, double* __restrict__ phi_out, const uint64_t* __restrict_
         // out-of-range lanes evaluate a clamped point so that the warp stays converged
         const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
         unsigned long long fl = 0ull;
-        const double v = vm_eval_impl<true, COUNT>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+        const double v = vm_eval_impl<true, COUNT, SMALL>(prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
         if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
     }
     if (COUNT) {

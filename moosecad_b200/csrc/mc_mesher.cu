@@ -283,7 +283,9 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     c->launches++;
     MC_CUDA(cudaGetLastError());
     const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
-    auto kern = count ? k_sdf_field_tiled<8, 4, true> : k_sdf_field_tiled<8, 4, false>;
+    const bool small = p.small();
+    auto kern = count ? (small ? k_sdf_field_tiled<8, 4, true, true> : k_sdf_field_tiled<8, 4, true, false>)
+                      : (small ? k_sdf_field_tiled<8, 4, false, true> : k_sdf_field_tiled<8, 4, false, false>);
     if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -322,8 +324,11 @@ static int launch_sdf_field(mc_mesh* m) {
     // warp footprints so that bbox guards are warp-coherent
     const bool linear = m->prog.flops < 64;
     const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
-    auto kern = linear ? (count ? k_sdf_field<32, 1, true> : k_sdf_field<32, 1, false>)
-                       : (count ? k_sdf_field<8, 4, true> : k_sdf_field<8, 4, false>);
+    const bool small = m->prog.small();
+    auto kern = linear ? (count ? (small ? k_sdf_field<32, 1, true, true> : k_sdf_field<32, 1, true, false>)
+                                : (small ? k_sdf_field<32, 1, false, true> : k_sdf_field<32, 1, false, false>))
+                       : (count ? (small ? k_sdf_field<8, 4, true, true> : k_sdf_field<8, 4, true, false>)
+                                : (small ? k_sdf_field<8, 4, false, true> : k_sdf_field<8, 4, false, false>));
     if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));

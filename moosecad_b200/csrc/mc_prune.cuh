@@ -304,7 +304,7 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
 
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
 // smem layout: [out program (max_words)] [dec (n_dec bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
-template <int WX, int WY, bool COUNT>
+template <int WX, int WY, bool COUNT, bool SMALL>
 __global__ void __launch_bounds__(256, 4)
 k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
@@ -528,7 +528,7 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             const bool inside = live && X < L.NX && Y < L.NY && Z <= L.pz1;
             const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1, Zc = Z <= L.pz1 ? Z : L.pz1;
             unsigned long long fl = 0ull;
-            const double v = vm_eval_impl<true, COUNT>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Zc), fl);
+            const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Zc), fl);
             if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
         }
     }

@@ -295,6 +295,7 @@ struct Lowering {
                 if (rc != MC_OK) return rc;
                 prog.words[child_at] = MC_HDR(MC_OP_CHILD, n.kind == NK_UNION ? 1 : 0, 0, dec_base + ci, prog.words.size());
             }
+            if ((int)k > prog.max_bool_children) prog.max_bool_children = (int)k;
             word(MC_HDR(MC_OP_BOOL, (int)k | (n.kind == NK_UNION ? 0x80 : 0), 0, dec_base, 0));
             dword(n.r);
             dword(n.r * tape.r_multiplier);  // exact_range, set_parameters (src/main.rs:53-58)

@@ -44,6 +44,9 @@ struct Program {
     std::vector<uint32_t> inst_start;   // word index of every instruction, in program order
     std::vector<uint16_t> word_inst;    // instruction index of every word that starts an instruction (else 0xffff)
     uint32_t n_decisions = 0;
+    int max_bool_children = 0;
+    // register-stack evaluator applicable (mc_vm.cuh, SMALL)
+    bool small() const { return value_depth <= 4 && point_depth <= 1 && max_bool_children <= 4; }
 };
 
 }  // namespace mc

@@ -65,6 +65,41 @@ __device__ __forceinline__ double smooth_fold(const double* __restrict__ vs, int
     return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
 }
 
+// rvmin / rvmax over k <= 4 operands held in registers (v0..v3 in push order, only the first k used)
+template <bool IS_UNION, bool COUNT>
+__device__ __forceinline__ double smooth_fold4(double v0, double v1, double v2, double v3, int k, double r,
+                                               double exact_range, unsigned long long& flops) {
+    const double v[4] = {v0, v1, v2, v3};
+    bool close = false;
+    double m = IS_UNION ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= k) break;
+        const double x = v[i];
+        if (IS_UNION) {
+            if (x < m) { close = (m - x) < exact_range; m = x; }
+            else if ((x - m) < exact_range) close = true;
+        } else {
+            if (x > m) { close = (x - m) < exact_range; m = x; }
+            else if ((m - x) < exact_range) close = true;
+        }
+    }
+    if (COUNT) flops += 3ull * (unsigned)k;
+    if (!close) return m;
+    const double lim = IS_UNION ? (m + r) : (m - r);
+    const double r4 = r / 4.0;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= k) break;
+        const double x = v[i];
+        if (IS_UNION) { if (x < lim) { s = s + mc_exp(-x / r4); if (COUNT) flops += 4 + MC_FLOPS_EXP; } }
+        else          { if (x > lim) { s = s + mc_exp(x / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; } }
+    }
+    if (COUNT) flops += 3 + MC_FLOPS_LOG;
+    return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
+}
+
 // geom.cube: rvmax over the six axis planes, everything in registers
 // (`mask`: planes that can influence the result on this tile; dropped ones are skipped, which is
 // value-neutral, see mc_prune.cuh)
@@ -104,15 +139,19 @@ __device__ __forceinline__ double box_fold(const uint64_t* __restrict__ w, int a
 }
 
 // Evaluate the program at (x, y, z).  `w` may point to shared or global memory.
-template <bool UNIFORM, bool COUNT>
+// SMALL: programs whose value stack never holds more than 4 entries, whose booleans have at most
+// 4 children and whose affine nodes do not nest keep everything in registers (s1..s3 below `top`,
+// one saved point) instead of the local-memory stacks; the host picks the variant per program.
+template <bool UNIFORM, bool COUNT, bool SMALL>
 __device__ __forceinline__ double vm_eval_impl(const uint64_t* __restrict__ w, double x, double y, double z, unsigned long long& flops) {
-    double vs[MC_MAX_VALUE_DEPTH + 1];   // element i lives in vs[i + 1]; the newest is `top`
-    double ps[3 * MC_MAX_POINT_DEPTH];
+    double vs[SMALL ? 1 : MC_MAX_VALUE_DEPTH + 1];   // element i lives in vs[i + 1]; the newest is `top`
+    double ps[SMALL ? 1 : 3 * MC_MAX_POINT_DEPTH];
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     int sp = 0, psp = 0, pc = 0;
     double top = 0.0;
     unsigned long long allpass = 0ull;  // bit L: every lane passed the guard at nesting level L
     const unsigned FULL = 0xffffffffu;
-#define MC_PUSH(v) do { vs[sp] = top; ++sp; top = (v); } while (0)
+#define MC_PUSH(v) do { if (SMALL) { s3 = s2; s2 = s1; s1 = top; } else { vs[sp] = top; ++sp; } top = (v); } while (0)
     for (;;) {
         const uint64_t h = w[pc];
         switch (MC_HDR_OP(h)) {
@@ -210,8 +249,8 @@ __device__ __forceinline__ double vm_eval_impl(const uint64_t* __restrict__ w, d
         }
         // fallthrough
         case MC_OP_APUSH: {
-            ps[psp] = x; ps[psp + 1] = y; ps[psp + 2] = z;
-            psp += 3;
+            if (SMALL) { sx = x; sy = y; sz = z; }
+            else { ps[psp] = x; ps[psp + 1] = y; ps[psp + 2] = z; psp += 3; }
             // nalgebra transform_point: ((m0*x + m1*y) + m2*z) + t   (n == 1 for affine matrices)
             const double nx = ((ld_f64(w, pc + 1) * x + ld_f64(w, pc + 2) * y) + ld_f64(w, pc + 3) * z) + ld_f64(w, pc + 4);
             const double ny = ((ld_f64(w, pc + 5) * x + ld_f64(w, pc + 6) * y) + ld_f64(w, pc + 7) * z) + ld_f64(w, pc + 8);
@@ -264,17 +303,29 @@ __device__ __forceinline__ double vm_eval_impl(const uint64_t* __restrict__ w, d
             const int k = (int)(sm & 0x7fu);
             const double r = ld_f64(w, pc + 1);
             const double er = ld_f64(w, pc + 2);
-            const int base = sp - k + 1;  // v[i] (i < k-1) is vs[base + i]
-            const double res = (sm & 0x80u) ? smooth_fold<true, COUNT>(vs, base, k, top, r, er, flops)
-                                            : smooth_fold<false, COUNT>(vs, base, k, top, r, er, flops);
-            sp -= k - 1;
+            double res;
+            if (SMALL) {
+                // operands in push order: (.., s3, s2, s1, top)
+                const double o0 = k == 2 ? s1 : (k == 3 ? s2 : s3);
+                const double o1 = k == 2 ? top : (k == 3 ? s1 : s2);
+                const double o2 = k == 3 ? top : s1;
+                res = (sm & 0x80u) ? smooth_fold4<true, COUNT>(o0, o1, o2, top, k, r, er, flops)
+                                   : smooth_fold4<false, COUNT>(o0, o1, o2, top, k, r, er, flops);
+                if (k == 2) { s1 = s2; s2 = s3; }
+                else if (k == 3) { s1 = s3; }
+            } else {
+                const int base = sp - k + 1;  // v[i] (i < k-1) is vs[base + i]
+                res = (sm & 0x80u) ? smooth_fold<true, COUNT>(vs, base, k, top, r, er, flops)
+                                   : smooth_fold<false, COUNT>(vs, base, k, top, r, er, flops);
+                sp -= k - 1;
+            }
             top = res;
             pc += 3;
             break;
         }
         case MC_OP_APOP: {
-            psp -= 3;
-            x = ps[psp]; y = ps[psp + 1]; z = ps[psp + 2];
+            if (SMALL) { x = sx; y = sy; z = sz; }
+            else { psp -= 3; x = ps[psp]; y = ps[psp + 1]; z = ps[psp + 2]; }
             top = top * ld_f64(w, pc + 1);
             if (COUNT) flops += 1;
             pc += 2;
@@ -544,7 +595,7 @@ __device__ __noinline__ void vm_eval_multi(const uint64_t* __restrict__ w, const
 template <bool UNIFORM>
 __device__ __forceinline__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, double z) {
     unsigned long long unused = 0ull;
-    return vm_eval_impl<UNIFORM, false>(w, x, y, z, unused);
+    return vm_eval_impl<UNIFORM, false, false>(w, x, y, z, unused);
 }
 
 }  // namespace mc
