@@ -567,9 +567,23 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
     MC_CUDA(cudaGetLastError());
     MC_CUDA(cudaEventRecord(m->ev[6], s));
     if (m->n_cuts > 0) {
-        k_bisect_edges<<<blocks_for(m->n_cuts, 256), 256, 0, s>>>(
-            S, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts, m->error_threshold,
-            m->max_bisect, (double*)m->d_coords.p, counters);
+        if (m->tiled_sdf && m->d_dec.p) {
+            // the tile-specialised programs are valid on every lattice edge that starts in the tile
+            const Program& p = m->prog;
+            const uint32_t n_inst = (uint32_t)p.inst_start.size(), n_words = (uint32_t)p.words.size();
+            const size_t smem = (size_t)n_words * 8 + ((p.n_decisions + 15u) & ~15u) + (size_t)(n_inst + 1) * 8;
+            auto kern = p.small() ? k_bisect_edges_tiled<true> : k_bisect_edges_tiled<false>;
+            if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)m->n_tiles, TILE_THREADS, smem, s>>>(
+                S, (const uint64_t*)m->d_prog.p, (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
+                n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, m->n_tiles,
+                (const unsigned long long*)m->d_vtile_cbase.p, m->n_cuts, (const unsigned long long*)m->d_cutlist.p,
+                m->error_threshold, m->max_bisect, (double*)m->d_coords.p, counters);
+        } else {
+            k_bisect_edges<<<blocks_for(m->n_cuts, 256), 256, 0, s>>>(
+                S, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts, m->error_threshold,
+                m->max_bisect, (double*)m->d_coords.p, counters);
+        }
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }

@@ -293,13 +293,158 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
     tile_origin(g, tc, X0, Y0, Z0);
-    const uint32_t X1 = min(X0 + TS, L.NX) - 1, Y1 = min(Y0 + TS, L.NY) - 1, Z1 = min(Z0 + TS, L.pz1 + 1) - 1;
-    // lattice coordinates are monotone in the index, so the end points bound the tile exactly
-    const double box[6] = {lat_x(L, X0), lat_x(L, X1), lat_y(L, Y0), lat_y(L, Y1), lat_z(L, Z0), lat_z(L, Z1)};
+    // The box covers the tile's points plus one lattice step on every side, so that the decisions
+    // also hold on every lattice edge that starts in the tile (cut-edge bisection) and on the
+    // centroids of its cells' tets.  Lattice coordinates are monotone in the index, so the end
+    // points bound the box exactly.
+    const uint32_t Xa = X0 > 0 ? X0 - 1 : 0, Ya = Y0 > 0 ? Y0 - 1 : 0, Za = Z0 > 0 ? Z0 - 1 : 0;
+    const uint32_t X1 = min(X0 + TS, L.nx), Y1 = min(Y0 + TS, L.ny), Z1 = min(Z0 + TS, L.nz);
+    const double box[6] = {lat_x(L, Xa), lat_x(L, X1), lat_y(L, Ya), lat_y(L, Y1), lat_z(L, Za), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
     const Ival root = vm_decide(prog, box, dec + tc, (size_t)ntiles);
     // proven sign of the whole tile (the bounds are padded; NaN proves nothing)
     tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
+}
+
+// Block-cooperative compaction of the program for one tile into shared memory (s_prog), using the
+// tile's decisions.  All threads of the block must call it; it ends with the result visible to
+// the whole block once the caller has synchronised.  Returns the number of words via s_newpos[n_inst].
+__device__ __forceinline__ void compact_tile_program(const uint64_t* __restrict__ prog,
+                                                     const uint32_t* __restrict__ inst_start,
+                                                     const uint16_t* __restrict__ word_inst, uint32_t n_inst,
+                                                     uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
+                                                     uint64_t tile, uint64_t* s_prog, uint8_t* s_dec, int* s_delta,
+                                                     uint32_t* s_newpos, uint32_t* s_scan) {
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < n_dec; i += blockDim.x) s_dec[i] = dec_g[(size_t)i * ntiles + tile];
+    for (uint32_t i = tid; i <= n_inst; i += blockDim.x) s_delta[i] = 0;
+    __syncthreads();
+    // 1. dead ranges: dropped boolean children and always-failing guards
+    for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
+        const uint64_t h = prog[inst_start[i]];
+        const uint32_t op = MC_HDR_OP(h);
+        if (op == MC_OP_CHILD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
+            atomicAdd(&s_delta[i + 1], 1);
+            atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
+        } else if ((op == MC_OP_GUARD || op == MC_OP_GAPUSH) && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
+            atomicAdd(&s_delta[i + 1], 1);
+            atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
+        }
+    }
+    __syncthreads();
+    // 2. inclusive scan of the deltas -> nesting depth of dead ranges; new length of every
+    //    instruction; exclusive scan of the lengths -> new word positions
+    uint32_t run_depth = 0, run_pos = 0;
+    for (uint32_t base = 0; base <= n_inst; base += blockDim.x) {
+        const uint32_t i = base + tid;
+        const int dlt = (i <= n_inst) ? s_delta[i] : 0;
+        uint32_t tot;
+        // depths are non-negative at every prefix, so unsigned wrap-around arithmetic is safe
+        const uint32_t ex = block_exscan((uint32_t)dlt, &tot, s_scan);
+        const uint32_t depth = run_depth + ex + (uint32_t)dlt;
+        run_depth += tot;
+        uint32_t len = 0;
+        if (i < n_inst && depth == 0) {
+            const uint64_t h = prog[inst_start[i]];
+            const uint32_t op = MC_HDR_OP(h);
+            const uint8_t d = (op == MC_OP_GUARD || op == MC_OP_ENDG || op == MC_OP_GSPHERE || op == MC_OP_GCYL ||
+                               op == MC_OP_GBOX || op == MC_OP_GAPUSH)
+                                  ? s_dec[MC_HDR_DEC(h)] : (uint8_t)MC_DEC_KEEP;
+            switch (op) {
+            case MC_OP_GUARD: len = d == MC_DEC_PASS ? 0u : (d == MC_DEC_FAIL ? 7u : 8u); break;
+            case MC_OP_GAPUSH: len = d == MC_DEC_PASS ? 13u : (d == MC_DEC_FAIL ? 7u : 20u); break;
+            case MC_OP_GBOX: len = d == MC_DEC_PASS ? 9u : (d == MC_DEC_FAIL ? 7u : 16u); break;
+            case MC_OP_ENDG: len = d == MC_DEC_KEEP ? 1u : 0u; break;
+            case MC_OP_GSPHERE: case MC_OP_GCYL: len = d == MC_DEC_PASS ? 2u : (d == MC_DEC_FAIL ? 7u : 9u); break;
+            case MC_OP_CHILD: len = 0u; break;
+            case MC_OP_BOOL: {
+                const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
+                uint32_t kept = 0;
+                for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
+                len = kept > 1 ? 3u : 0u;
+                break;
+            }
+            default: len = (uint32_t)mc_op_words(op); break;
+            }
+        }
+        const uint32_t pex = block_exscan(len, &tot, s_scan);
+        if (i <= n_inst) { s_newpos[i] = run_pos + pex; s_delta[i] = (int)len; }
+        run_pos += tot;
+    }
+    __syncthreads();
+    // 3. write the compacted program
+    for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
+        const uint32_t len = (uint32_t)s_delta[i];
+        if (len == 0) continue;
+        const uint32_t src = inst_start[i], dst = s_newpos[i];
+        const uint64_t h = prog[src];
+        const uint32_t op = MC_HDR_OP(h);
+        switch (op) {
+        case MC_OP_GUARD:
+            if (len == 7u) {
+                s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+            } else {
+                s_prog[dst] = MC_HDR(MC_OP_GUARD, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+                for (uint32_t q = 1; q < 8; ++q) s_prog[dst + q] = prog[src + q];
+            }
+            break;
+        case MC_OP_GAPUSH:
+            if (len == 7u) {
+                s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+            } else if (len == 13u) {
+                s_prog[dst] = MC_HDR(MC_OP_APUSH, 0, 0, 0, 0);
+                for (uint32_t q = 1; q < 13; ++q) s_prog[dst + q] = prog[src + 7 + q];
+            } else {
+                s_prog[dst] = MC_HDR(MC_OP_GAPUSH, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+                for (uint32_t q = 1; q < 20; ++q) s_prog[dst + q] = prog[src + q];
+            }
+            break;
+        case MC_OP_GBOX:
+            if (len == 7u) {
+                s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+            } else {
+                uint32_t mask = 0;
+                for (uint32_t q = 0; q < 6; ++q) mask |= (s_dec[MC_HDR_DEC(h) + 1u + q] != MC_DEC_FAIL ? 1u : 0u) << q;
+                if (len == 9u) {
+                    s_prog[dst] = MC_HDR(MC_OP_BOX, mask, 0, 0, 0);
+                    for (uint32_t q = 1; q < 9; ++q) s_prog[dst + q] = prog[src + 7 + q];
+                } else {
+                    s_prog[dst] = MC_HDR(MC_OP_GBOX, mask, 0, 0, 0);
+                    for (uint32_t q = 1; q < 16; ++q) s_prog[dst + q] = prog[src + q];
+                }
+            }
+            break;
+        case MC_OP_ENDG:
+            s_prog[dst] = MC_HDR(MC_OP_ENDG, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
+            break;
+        case MC_OP_GSPHERE: case MC_OP_GCYL:
+            if (len == 2u) {
+                s_prog[dst] = MC_HDR(op == MC_OP_GSPHERE ? MC_OP_SPHERE : MC_OP_CYL, 0, 0, 0, 0);
+                s_prog[dst + 1] = prog[src + 8];
+            } else if (len == 7u) {
+                s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
+                for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
+            } else {
+                for (uint32_t q = 0; q < 9; ++q) s_prog[dst + q] = prog[src + q];
+            }
+            break;
+        case MC_OP_BOOL: {
+            const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
+            uint32_t kept = 0;
+            for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
+            s_prog[dst] = MC_HDR(MC_OP_BOOL, kept | (MC_HDR_SMALL(h) & 0x80u), 0, 0, 0);
+            s_prog[dst + 1] = prog[src + 1];
+            s_prog[dst + 2] = prog[src + 2];
+            break;
+        }
+        default:
+            for (uint32_t q = 0; q < len; ++q) s_prog[dst + q] = prog[src + q];
+            break;
+        }
+    }
 }
 
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
@@ -357,135 +502,8 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 continue;
             }
         }
-        for (uint32_t i = tid; i < n_dec; i += blockDim.x) s_dec[i] = dec_g[(size_t)i * ntiles + tile];
-        for (uint32_t i = tid; i <= n_inst; i += blockDim.x) s_delta[i] = 0;
-        __syncthreads();
-        // 1. dead ranges: dropped boolean children and always-failing guards
-        for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
-            const uint64_t h = prog[inst_start[i]];
-            const uint32_t op = MC_HDR_OP(h);
-            if (op == MC_OP_CHILD && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
-                atomicAdd(&s_delta[i + 1], 1);
-                atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
-            } else if ((op == MC_OP_GUARD || op == MC_OP_GAPUSH) && s_dec[MC_HDR_DEC(h)] == MC_DEC_FAIL) {
-                atomicAdd(&s_delta[i + 1], 1);
-                atomicAdd(&s_delta[word_inst[MC_HDR_IDX(h)]], -1);
-            }
-        }
-        __syncthreads();
-        // 2. inclusive scan of the deltas -> nesting depth of dead ranges; new length of every
-        //    instruction; exclusive scan of the lengths -> new word positions
-        uint32_t run_depth = 0, run_pos = 0;
-        for (uint32_t base = 0; base <= n_inst; base += blockDim.x) {
-            const uint32_t i = base + tid;
-            const int dlt = (i <= n_inst) ? s_delta[i] : 0;
-            uint32_t tot;
-            // depths are non-negative at every prefix, so unsigned wrap-around arithmetic is safe
-            const uint32_t ex = block_exscan((uint32_t)dlt, &tot, s_scan);
-            const uint32_t depth = run_depth + ex + (uint32_t)dlt;
-            run_depth += tot;
-            uint32_t len = 0;
-            if (i < n_inst && depth == 0) {
-                const uint64_t h = prog[inst_start[i]];
-                const uint32_t op = MC_HDR_OP(h);
-                const uint8_t d = (op == MC_OP_GUARD || op == MC_OP_ENDG || op == MC_OP_GSPHERE || op == MC_OP_GCYL ||
-                                   op == MC_OP_GBOX || op == MC_OP_GAPUSH)
-                                      ? s_dec[MC_HDR_DEC(h)] : (uint8_t)MC_DEC_KEEP;
-                switch (op) {
-                case MC_OP_GUARD: len = d == MC_DEC_PASS ? 0u : (d == MC_DEC_FAIL ? 7u : 8u); break;
-                case MC_OP_GAPUSH: len = d == MC_DEC_PASS ? 13u : (d == MC_DEC_FAIL ? 7u : 20u); break;
-                case MC_OP_GBOX: len = d == MC_DEC_PASS ? 9u : (d == MC_DEC_FAIL ? 7u : 16u); break;
-                case MC_OP_ENDG: len = d == MC_DEC_KEEP ? 1u : 0u; break;
-                case MC_OP_GSPHERE: case MC_OP_GCYL: len = d == MC_DEC_PASS ? 2u : (d == MC_DEC_FAIL ? 7u : 9u); break;
-                case MC_OP_CHILD: len = 0u; break;
-                case MC_OP_BOOL: {
-                    const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
-                    uint32_t kept = 0;
-                    for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
-                    len = kept > 1 ? 3u : 0u;
-                    break;
-                }
-                default: len = (uint32_t)mc_op_words(op); break;
-                }
-            }
-            const uint32_t pex = block_exscan(len, &tot, s_scan);
-            if (i <= n_inst) { s_newpos[i] = run_pos + pex; s_delta[i] = (int)len; }
-            run_pos += tot;
-        }
-        __syncthreads();
-        // 3. write the compacted program
-        for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
-            const uint32_t len = (uint32_t)s_delta[i];
-            if (len == 0) continue;
-            const uint32_t src = inst_start[i], dst = s_newpos[i];
-            const uint64_t h = prog[src];
-            const uint32_t op = MC_HDR_OP(h);
-            switch (op) {
-            case MC_OP_GUARD:
-                if (len == 7u) {
-                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
-                } else {
-                    s_prog[dst] = MC_HDR(MC_OP_GUARD, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
-                    for (uint32_t q = 1; q < 8; ++q) s_prog[dst + q] = prog[src + q];
-                }
-                break;
-            case MC_OP_GAPUSH:
-                if (len == 7u) {
-                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
-                } else if (len == 13u) {
-                    s_prog[dst] = MC_HDR(MC_OP_APUSH, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 13; ++q) s_prog[dst + q] = prog[src + 7 + q];
-                } else {
-                    s_prog[dst] = MC_HDR(MC_OP_GAPUSH, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
-                    for (uint32_t q = 1; q < 20; ++q) s_prog[dst + q] = prog[src + q];
-                }
-                break;
-            case MC_OP_GBOX:
-                if (len == 7u) {
-                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
-                } else {
-                    uint32_t mask = 0;
-                    for (uint32_t q = 0; q < 6; ++q) mask |= (s_dec[MC_HDR_DEC(h) + 1u + q] != MC_DEC_FAIL ? 1u : 0u) << q;
-                    if (len == 9u) {
-                        s_prog[dst] = MC_HDR(MC_OP_BOX, mask, 0, 0, 0);
-                        for (uint32_t q = 1; q < 9; ++q) s_prog[dst + q] = prog[src + 7 + q];
-                    } else {
-                        s_prog[dst] = MC_HDR(MC_OP_GBOX, mask, 0, 0, 0);
-                        for (uint32_t q = 1; q < 16; ++q) s_prog[dst + q] = prog[src + q];
-                    }
-                }
-                break;
-            case MC_OP_ENDG:
-                s_prog[dst] = MC_HDR(MC_OP_ENDG, 0, MC_HDR_LEVEL(h), 0, s_newpos[word_inst[MC_HDR_IDX(h)]]);
-                break;
-            case MC_OP_GSPHERE: case MC_OP_GCYL:
-                if (len == 2u) {
-                    s_prog[dst] = MC_HDR(op == MC_OP_GSPHERE ? MC_OP_SPHERE : MC_OP_CYL, 0, 0, 0, 0);
-                    s_prog[dst + 1] = prog[src + 8];
-                } else if (len == 7u) {
-                    s_prog[dst] = MC_HDR(MC_OP_BOXDIST, 0, 0, 0, 0);
-                    for (uint32_t q = 1; q < 7; ++q) s_prog[dst + q] = prog[src + q];
-                } else {
-                    for (uint32_t q = 0; q < 9; ++q) s_prog[dst + q] = prog[src + q];
-                }
-                break;
-            case MC_OP_BOOL: {
-                const uint32_t k = MC_HDR_SMALL(h) & 0x7fu, db = MC_HDR_DEC(h);
-                uint32_t kept = 0;
-                for (uint32_t c = 0; c < k; ++c) kept += s_dec[db + c] != MC_DEC_FAIL;
-                s_prog[dst] = MC_HDR(MC_OP_BOOL, kept | (MC_HDR_SMALL(h) & 0x80u), 0, 0, 0);
-                s_prog[dst + 1] = prog[src + 1];
-                s_prog[dst + 2] = prog[src + 2];
-                break;
-            }
-            default:
-                for (uint32_t q = 0; q < len; ++q) s_prog[dst + q] = prog[src + q];
-                break;
-            }
-        }
+        compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta,
+                             s_newpos, s_scan);
         if (tid == 0 && pruned_words_total) atomicAdd(pruned_words_total, (unsigned long long)s_newpos[n_inst]);
         __syncthreads();
         // 4. evaluate the tile: WX x WY points of one z-plane per warp step
@@ -537,6 +555,84 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         for (int o = 16; o > 0; o >>= 1) my_flops += __shfl_xor_sync(0xffffffffu, my_flops, o);
         if ((tid & 31u) == 0u && my_flops) atomicAdd(flops_total, my_flops);
     }
+}
+
+
+// a8 with the tile-specialised program: one block per tile that owns cut edges.  The tile's cut
+// edges are contiguous in the work list (vertex numbering is tile-major).
+template <bool SMALL>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t* __restrict__ inst_start,
+                     const uint16_t* __restrict__ word_inst, uint32_t n_inst, uint32_t n_words, uint32_t n_dec,
+                     const uint8_t* __restrict__ dec_g, uint64_t ntiles, const unsigned long long* __restrict__ tile_cbase,
+                     uint64_t ncut_total, const unsigned long long* __restrict__ cutlist, double error_threshold,
+                     uint32_t max_iters, double* __restrict__ coords, unsigned long long* __restrict__ counters) {
+    extern __shared__ uint64_t smem[];
+    uint64_t* s_prog = smem;
+    uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
+    int* s_delta = (int*)(s_dec + ((n_dec + 15u) & ~15u));
+    uint32_t* s_newpos = (uint32_t*)(s_delta + (n_inst + 1));
+    __shared__ uint32_t s_scan[9];
+    const uint64_t tile = blockIdx.x;
+    if (S.vuni[tile] != VU_ACTIVE) return;
+    const uint64_t c0 = tile_cbase[tile], c1 = tile + 1 < ntiles ? tile_cbase[tile + 1] : ncut_total;
+    if (c1 <= c0) return;
+    compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta, s_newpos,
+                         s_scan);
+    __syncthreads();
+    const Lattice& L = S.L;
+    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    unsigned long long it64 = 0ull;
+    const uint64_t n = c1 - c0;
+    for (uint64_t base = 0; base < n; base += TILE_THREADS) {
+        const uint64_t i = base + threadIdx.x;
+        const bool active = i < n;
+        const unsigned long long e = cutlist[c0 + (active ? i : n - 1)];
+        const size_t pi = (size_t)(e >> 4);
+        const int s = (int)(e & 15ull);
+        const uint32_t Z = L.pz0 + (uint32_t)(pi / per_plane);
+        const uint64_t r = pi % per_plane;
+        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+        const uint32_t WX = X + C_DIR[s][0], WY = Y + C_DIR[s][1], WZ = Z + C_DIR[s][2];
+        const double pv = L.phi[pi];
+        double ax, ay, az, bx, by, bz;
+        if (pv > 0.0) {
+            ax = lat_x(L, X); ay = lat_y(L, Y); az = lat_z(L, Z);
+            bx = lat_x(L, WX); by = lat_y(L, WY); bz = lat_z(L, WZ);
+        } else {
+            bx = lat_x(L, X); by = lat_y(L, Y); bz = lat_z(L, Z);
+            ax = lat_x(L, WX); ay = lat_y(L, WY); az = lat_z(L, WZ);
+        }
+        double cx = 0.0, cy = 0.0, cz = 0.0;
+        bool done = !active;
+        uint32_t iters = 0;
+        while (__any_sync(0xffffffffu, !done)) {
+            const double mx = (ax + bx) * 0.5, my = (ay + by) * 0.5, mz = (az + bz) * 0.5;
+            unsigned long long fl = 0ull;
+            const double phi = vm_eval_impl<true, false, SMALL>(s_prog, mx, my, mz, fl);
+            if (!done) {
+                cx = mx; cy = my; cz = mz;
+                ++iters;
+                if (fabs(phi) <= error_threshold) done = true;
+                else if (phi > 0.0) { ax = mx; ay = my; az = mz; }
+                else { bx = mx; by = my; bz = mz; }
+                if (!done && iters >= max_iters) {
+                    done = true;
+                    atomicAdd(&counters[CN_BISECT_FAIL], 1ull);
+                }
+            }
+        }
+        if (active) {
+            uint16_t mask;
+            const long long vb = vertex_gid(S, X, Y, Z, mask);
+            const long long id = cut_vertex_id(vb, mask, s) - S.vertex_base;
+            coords[3 * id] = cx; coords[3 * id + 1] = cy; coords[3 * id + 2] = cz;
+            it64 += iters;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) it64 += __shfl_xor_sync(0xffffffffu, it64, o);
+    if ((threadIdx.x & 31u) == 0u && it64) atomicAdd(&counters[CN_BISECT_ITERS], it64);
 }
 
 }  // namespace mc
