@@ -293,11 +293,11 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
     tile_origin(g, tc, X0, Y0, Z0);
-    // The box covers the tile's points plus one lattice step on every side, so that the decisions
-    // also hold on every lattice edge that starts in the tile (cut-edge bisection) and on the
-    // centroids of its cells' tets.  Lattice coordinates are monotone in the index, so the end
-    // points bound the box exactly.
-    const uint32_t Xa = X0 > 0 ? X0 - 1 : 0, Ya = Y0 > 0 ? Y0 - 1 : 0, Za = Z0 > 0 ? Z0 - 1 : 0;
+    // The box covers the tile's points plus the reach of the lattice edges OWNED by them (canonical
+    // directions: -1..+1 in x and y, 0..+1 in z), so that the decisions also hold along every cut
+    // edge the tile bisects.  Lattice coordinates are monotone in the index, so the end points
+    // bound the box exactly.
+    const uint32_t Xa = X0 > 0 ? X0 - 1 : 0, Ya = Y0 > 0 ? Y0 - 1 : 0, Za = Z0;
     const uint32_t X1 = min(X0 + TS, L.nx), Y1 = min(Y0 + TS, L.ny), Z1 = min(Z0 + TS, L.nz);
     const double box[6] = {lat_x(L, Xa), lat_x(L, X1), lat_y(L, Ya), lat_y(L, Y1), lat_z(L, Za), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
