@@ -574,12 +574,41 @@ k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
             tile_tot[blockIdx.x] = vu == VU_NEG ? (unsigned long long)b.nxt * b.nyt * (b.zhi - b.zlo) : 0ull;
         return;
     }
+    // post-warp classes of the tile's points with a one-point halo:
+    // 0 none, 1 negative, 2 positive, 3 zero (not in the output), 4 zero used by some output tet
+    constexpr int H = (int)TS + 2;
+    __shared__ uint8_t s_cl[H * H * H];
+    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
+        const int64_t X = (int64_t)b.X0 + idx % H - 1, Y = (int64_t)b.Y0 + (idx / H) % H - 1, Z = (int64_t)b.Z0 + idx / (H * H) - 1;
+        uint8_t cl = 0;
+        if (X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1) {
+            const size_t pi = pidx(L, (uint32_t)X, (uint32_t)Y, (uint32_t)Z);
+            const uint8_t wc = L.wcode[pi];
+            const double pv = (wc & 0x7f) ? 0.0 : L.phi[pi];
+            cl = pv < 0.0 ? 1 : (pv > 0.0 ? 2 : (pv == 0.0 ? ((wc & 0x80) ? 4 : 3) : 0));
+        }
+        s_cl[idx] = cl;
+    }
+    __syncthreads();
     unsigned long long mine = 0ull;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t X = b.X0 + (j & 15u), Y = b.Y0 + ((j >> 4) & 15u), Z = b.Z0 + (j >> 8);
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const uint32_t X = b.X0 + lx, Y = b.Y0 + ly, Z = b.Z0 + lz;
         if (X >= L.NX || Y >= L.NY || Z < b.zlo || Z >= b.zhi) continue;
-        const uint16_t m = vertex_mask(L, X, Y, Z);
+        const int me = (int)((lz + 1) * H + (ly + 1)) * H + (int)(lx + 1);
+        const uint8_t cv = s_cl[me];
+        uint16_t m = (cv == 1 || cv == 4) ? VM_USED : (uint16_t)0;
+        if (cv == 1 || cv == 2) {
+            const uint8_t want = cv == 1 ? 2 : 1;  // strictly opposite sign
+            const bool even = ((X + Y + Z) & 1u) == 0u;
+            const int nd = even ? 9 : 3;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) {
+                if (s >= nd) break;
+                if (s_cl[me + (C_DIR[s][2] * H + C_DIR[s][1]) * H + C_DIR[s][0]] == want) m |= (uint16_t)(1u << s);
+            }
+        }
         S.vmask[pidx(L, X, Y, Z)] = m;
         const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
         mine += (unsigned long long)(ncut + ((m & VM_USED) ? 1u : 0u)) | ((unsigned long long)ncut << 32);
