@@ -200,6 +200,49 @@ def test_synthetic_csg(oracle, ctx):
     assert mesh.stats()["stats"] == om.stats()["stats"]
 
 
+def test_synthetic_csg_256_primitives(oracle, ctx):
+    # BASELINE config 5's scene shape: the ~100 KB program needs the opt-in shared memory path
+    g = mc.Geom()
+    root = scenes.synthetic_csg(g, 256, seed=256, size_scale=0.5)
+    g.backend.set_parameters(0.1, 1.0)
+    res = 1.0 / 28
+    mesh = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx).tessellate()
+    assert mesh.stats()["prune"]["tiles"] > 0
+    go = mc.Geom(oracle.OracleScene())
+    ro = scenes.synthetic_csg(go, 256, seed=256, size_scale=0.5)
+    ro.backend.set_parameters_node(ro.node, 0.1, 1.0)
+    om = ro.backend.tessellate(ro.node, res, 0.2)
+    canon.assert_same_mesh(canon.canonical(mesh.vertices(), mesh.elems()), canon.canonical(om.vertices(), om.elems()))
+    assert mesh.stats()["stats"] == om.stats()["stats"]
+
+
+def test_full_size_xplicit_512_sideset(ctx):
+    """BASELINE config 3: xplicit.lua at 512^3 with an added :boundary() object, checked through
+    properties that do not need the oracle (which cannot finish this size).  Run with
+    --tessellation-error 0.8: with the default 0.2 the reference's cut_edge never terminates on
+    this scene."""
+    mesh = main.run(scenes.XPLICIT_WITH_TOP_LUA, tessellation_resolution=15.0 / 512, tessellation_error=0.8, ctx=ctx)
+    st = mesh.stats()
+    assert st["dim"] == [512, 512, 512] and st["inverted"] == 0
+    v = mesh.vertices()
+    sides = mesh.boundary().array().astype(np.int64)
+    top = mesh.side_sets()[0].array().astype(np.int64)
+    assert mesh.side_sets()[0].name() == "top" and len(top) > 0
+    # gather the node triples of the boundary sides without pulling all tets apart on the host
+    e = mesh.elems()
+    tri = e[sides[:, 0][:, None], canon.FACE[sides[:, 1]]].astype(np.int64)
+    z = v[tri, 2]
+    on_top = (z == 7.5).all(axis=1)
+    # the side-set is exactly the set of surface sides lying in the plane z = 7.5 (the thin slab
+    # 15 x 15 x 0.15 translated to z = 7.5 intersected with the solid has |phi| <= EPSILON only there)
+    key = lambda a: set(map(tuple, a.tolist()))
+    assert key(top) == key(sides[on_top])
+    # surface is closed (even edge counts)
+    edges = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert (cnt % 2 == 0).all()
+
+
 def test_tet_quality_matches_oracle(oracle, ctx):
     rng = np.random.default_rng(3)
     coords = rng.normal(size=(400, 3))
