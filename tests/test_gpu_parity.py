@@ -216,31 +216,55 @@ def test_synthetic_csg_256_primitives(oracle, ctx):
     assert mesh.stats()["stats"] == om.stats()["stats"]
 
 
-def test_full_size_xplicit_512_sideset(ctx):
-    """BASELINE config 3: xplicit.lua at 512^3 with an added :boundary() object, checked through
-    properties that do not need the oracle (which cannot finish this size).  Run with
-    --tessellation-error 0.8: with the default 0.2 the reference's cut_edge never terminates on
-    this scene."""
-    mesh = main.run(scenes.XPLICIT_WITH_TOP_LUA, tessellation_resolution=15.0 / 512, tessellation_error=0.8, ctx=ctx)
-    st = mesh.stats()
-    assert st["dim"] == [512, 512, 512] and st["inverted"] == 0
+def _check_sidesets_against_point_eval(mesh, out, ctx):
+    """Side-set membership recomputed from the boundary object's values at the surface nodes
+    (mc_eval_points, a different kernel path) must reproduce the side-sets (src/main.rs:87-106)."""
+    eps = np.finfo(np.float64).eps
     v = mesh.vertices()
     sides = mesh.boundary().array().astype(np.int64)
-    top = mesh.side_sets()[0].array().astype(np.int64)
-    assert mesh.side_sets()[0].name() == "top" and len(top) > 0
-    # gather the node triples of the boundary sides without pulling all tets apart on the host
     e = mesh.elems()
     tri = e[sides[:, 0][:, None], canon.FACE[sides[:, 1]]].astype(np.int64)
-    z = v[tri, 2]
-    on_top = (z == 7.5).all(axis=1)
-    # the side-set is exactly the set of surface sides lying in the plane z = 7.5 (the thin slab
-    # 15 x 15 x 0.15 translated to z = 7.5 intersected with the solid has |phi| <= EPSILON only there)
-    key = lambda a: set(map(tuple, a.tolist()))
-    assert key(top) == key(sides[on_top])
+    nodes, inv = np.unique(tri, return_inverse=True)
+    sizes = {}
+    for ss in mesh.side_sets():
+        obj = out[ss.name()].boundary()
+        val = mc.ObjectAdaptor(obj, eps, ctx).value(v[nodes], slack=eps)
+        ok = ~((val > eps) | (val < -eps))
+        member = ok[inv.reshape(tri.shape)].all(axis=1)
+        got = ss.array().astype(np.int64)
+        want = sides[member]
+        assert got.shape == want.shape and np.array_equal(got, want), ss.name()
+        sizes[ss.name()] = len(got)
     # surface is closed (even edge counts)
     edges = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
     _, cnt = np.unique(edges, axis=0, return_counts=True)
     assert (cnt % 2 == 0).all()
+    return sizes
+
+
+def test_full_size_xplicit_512_sideset(ctx):
+    """BASELINE config 3: xplicit.lua at 512^3 with an added :boundary() object, checked through
+    properties that do not need the oracle (which cannot finish this size).  Run with
+    --tessellation-error 0.8: with the default 0.2 the reference's cut_edge never terminates on
+    this scene (DESIGN.md section 2).  The side-set tolerance of the reference is f64::EPSILON,
+    so after scale(15) (1/15 is not representable) the set may well be empty; what is checked is
+    that it is exactly what the boundary object's values say."""
+    script = scenes.XPLICIT_WITH_TOP_LUA
+    mesh = main.run(script, tessellation_resolution=15.0 / 512, tessellation_error=0.8, ctx=ctx)
+    st = mesh.stats()
+    assert st["dim"] == [512, 512, 512] and st["inverted"] == 0
+    _check_sidesets_against_point_eval(mesh, luascad.eval(script), ctx)
+
+
+def test_full_size_cube_256_sidesets(ctx):
+    """examples/cube.lua on a 256^3 lattice: every value is exact, so the top / bottom side-sets
+    are the 2 x 256^2 surface triangles of the planes z = +-0.5."""
+    mesh = main.run(scenes.CUBE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
+    st = mesh.stats()
+    assert st["dim"] == [256, 256, 256] and st["n_tets"] == 5 * 256 ** 3 and st["n_vertices"] == 257 ** 3
+    sizes = _check_sidesets_against_point_eval(mesh, luascad.eval(scenes.CUBE_LUA), ctx)
+    assert sizes == {"top": 2 * 256 * 256, "bottom": 2 * 256 * 256}
+    assert len(mesh.boundary()) == 12 * 256 * 256
 
 
 def test_tet_quality_matches_oracle(oracle, ctx):
