@@ -257,13 +257,15 @@ def test_full_size_xplicit_512_sideset(ctx):
 
 
 def test_full_size_cube_256_sidesets(ctx):
-    """examples/cube.lua on a 256^3 lattice: every value is exact, so the top / bottom side-sets
-    are the 2 x 256^2 surface triangles of the planes z = +-0.5."""
+    """examples/cube.lua on a 256^3 lattice: every value is exact.  The `top` object is the cube
+    intersected with a 0.01 thick slab around z = 0.5, so its zero set holds the 2 x 256^2 triangles
+    of the plane z = 0.5 plus the top row (z >= 0.5 - 1/256 > 0.495) of the four side walls."""
     mesh = main.run(scenes.CUBE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
     st = mesh.stats()
     assert st["dim"] == [256, 256, 256] and st["n_tets"] == 5 * 256 ** 3 and st["n_vertices"] == 257 ** 3
     sizes = _check_sidesets_against_point_eval(mesh, luascad.eval(scenes.CUBE_LUA), ctx)
-    assert sizes == {"top": 2 * 256 * 256, "bottom": 2 * 256 * 256}
+    expect = 2 * 256 * 256 + 4 * 256 * 2
+    assert sizes == {"top": expect, "bottom": expect}
     assert len(mesh.boundary()) == 12 * 256 * 256
 
 
