@@ -150,10 +150,22 @@ typedef struct mc_options {
 #define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
 #define MC_OPT_COUNT_FLOPS 16u /* instrumented SDF kernel: count the FP64 operations it executes (slower) */
 
-/* Load estimate for z-slab sharding: relative cost of every cell layer z (n = dim[2] doubles), from
- * an interval evaluation of the SDF program over 16^3-point tiles (tiles that may contain the
- * surface cost the most, proven-interior tiles cost their output, proven-exterior tiles almost
- * nothing).  Deterministic, so every rank can compute the same partition. */
+/* Load estimate for z-slab sharding (no reference counterpart).  An interval evaluation
+ * of the SDF program over the 16^3-point tiles sorts every tile into a cost class:
+ *   0 sign not proven (full SDF evaluation, possibly surface work)
+ *   1 proven inside, neighbourhood too (no SDF evaluation; arithmetic output)
+ *   2 proven inside next to other tiles (shell evaluation + output)
+ *   3 proven outside, neighbourhood too (nothing to do)
+ *   4 proven outside next to other tiles (shell evaluation)
+ * mc_tile_layer_classes returns counts[layer * 5 + class] for the n = ceil((dim[2] + 1) / 16) tile
+ * layers; mc_estimate_layer_costs turns them into a relative cost per CELL layer z (n = dim[2]
+ * doubles) with the weights below.  Deterministic, so every rank derives the same partition. */
+#define MC_SLAB_COST_UNPROVEN 1.0
+#define MC_SLAB_COST_NEG_SKIPPED 0.3
+#define MC_SLAB_COST_NEG_SHELL 0.3
+#define MC_SLAB_COST_POS_SKIPPED 0.03
+#define MC_SLAB_COST_POS_SHELL 0.03
+int mc_tile_layer_classes(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, uint64_t* counts, uint64_t n);
 int mc_estimate_layer_costs(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n);
 
 /* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mc_eval_points": (C.c_int, [_P, _P, _I32, _D, _PD, _U64, _PD]),
     "mc_eval_points_device": (C.c_int, [_P, _P, _I32, _D, _P, _U64, _P]),
     "mc_estimate_layer_costs": (C.c_int, [_P, _P, _I32, _D, _PD, _U64]),
+    "mc_tile_layer_classes": (C.c_int, [_P, _P, _I32, _D, C.POINTER(_U64), _U64]),
     "mc_tessellate_begin": (C.c_int, [_P, _P, _I32, _D, _D, C.POINTER(mc_slab), C.POINTER(mc_options),
                                       C.POINTER(_P)]),
     "mc_tessellate_emit_vertices": (C.c_int, [_P, _U64]),

@@ -30,7 +30,11 @@ struct mc_ctx {
     std::vector<mc::DevBuf> free_list;  // cached device allocations
     uint64_t held_bytes = 0;
 
-    int alloc(size_t bytes, mc::DevBuf& out);
+    bool debug = false, debug_sync = false;  // MC_DEBUG=1: poison allocations + check every stage (2: poison, 3: checks)
+
+    int alloc(size_t bytes, mc::DevBuf& out);          // pool allocation (+ poison fill in debug mode)
+    int alloc_raw(size_t bytes, mc::DevBuf& out);
+    int stage_check(const char* stage);                // debug mode: synchronise + report faults by stage
     void release(mc::DevBuf& b);
     void trim();
 };

@@ -1031,7 +1031,7 @@ constexpr int TE_NP = TE_H * TE_H * TE_H;
 template <typename IndexT>
 constexpr size_t tet_emit_smem_bytes() {
     return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + (size_t)TE_NP /*warped*/ + 15 +
-           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, cnt*/;
+           (size_t)TILE_POINTS * 2 * 3 /*ci, off, list*/;
 }
 
 template <typename IndexT, bool QUALITY>
@@ -1041,8 +1041,6 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     extern __shared__ __align__(16) unsigned char te_smem[];
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_n;
-    __shared__ double s_step[3][TS];
-    __shared__ uint8_t s_repidx[3][TS];
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
@@ -1055,7 +1053,6 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_wrp + TE_NP) + 15) & ~(uintptr_t)15);
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
-    uint16_t* s_cnt = s_list + TILE_POINTS; // all-negative untouched cells per (step, parity) class
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[blockIdx.x];
     if (threadIdx.x == 0) s_n = 0u;
@@ -1081,22 +1078,8 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         const uint32_t tex = block_exscan(count, &ttot, s_scan);
         s_ci[j] = ci;
         s_off[j] = (uint16_t)(run + tex);
-        if (QUALITY) s_cnt[j] = 0;
         if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
         run += ttot;
-    }
-    if (QUALITY && threadIdx.x < 3 * TS) {
-        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
-        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
-        s_step[a][i] = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
-    }
-    __syncthreads();
-    if (QUALITY && threadIdx.x < 3 * TS) {
-        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
-        uint32_t rep = i;
-        for (uint32_t q = 0; q < i; ++q)
-            if (s_step[a][q] == s_step[a][i] && ((q ^ i) & 1u) == 0u) { rep = q; break; }
-        s_repidx[a][i] = (uint8_t)rep;
     }
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
@@ -1122,17 +1105,12 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             dst[4 * t + 2] = id[T[t][2]];
             dst[4 * t + 3] = id[T[t][3]];
         }
-        if (QUALITY) {
-            if (!(ci & CI_FULL_ZERO_CORNER)) {
-                // all corners strictly negative: plain lattice tets, counted per class
-                // (16-bit counters updated through their aligned 32-bit word)
-                const uint32_t cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
-                atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
-            } else {
-                const unsigned long long at = atomicAdd(&counters[CN_QLIST_FILL], 5ull);
+        // zero-cornered untouched cells are not congruent to plain lattice tets: listed for the
+        // per-tet quality pass (the plain ones are handled per class by k_surface_tile_quality)
+        if (QUALITY && (ci & CI_FULL_ZERO_CORNER)) {
+            const unsigned long long at = atomicAdd(&counters[CN_QLIST_FILL], 5ull);
 #pragma unroll
-                for (int t = 0; t < 5; ++t) qlist[at + t] = o + (uint64_t)t;
-            }
+            for (int t = 0; t < 5; ++t) qlist[at + t] = o + (uint64_t)t;
         }
     }
     // 3b. the lattice tets of the surface cells, one per thread
@@ -1178,16 +1156,55 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             ++o;
         }
     }
-    if (QUALITY) {
-        // plain lattice tets of this tile, one evaluation per class
-        QualityAcc qa = {1.0, 0.0, 0u};
-        __syncthreads();
-        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
-            const uint32_t cnt = s_cnt[j];
-            if (cnt) lattice_cell_quality_call(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
-        }
-        qa.flush(counters);
+}
+
+// check_for_inverted_tets for the plain lattice tets of the SURFACE tiles (untouched cells with
+// all corners strictly negative): counted per (step, parity) class of the tile, one evaluation
+// per class — see k_full_tile_quality.
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    __shared__ double s_step[3][TS];
+    __shared__ uint8_t s_repidx[3][TS];
+    __shared__ __align__(4) uint16_t s_cnt[TILE_POINTS];
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) s_cnt[j] = 0;
+    if (threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
+        s_step[a][i] = a == 0 ? lat_x(L, cc + 1) - lat_x(L, cc) : (a == 1 ? lat_y(L, cc + 1) - lat_y(L, cc) : lat_z(L, cc + 1) - lat_z(L, cc));
     }
+    __syncthreads();
+    if (threadIdx.x < 3 * TS) {
+        const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
+        uint32_t rep = i;
+        for (uint32_t q = 0; q < i; ++q)
+            if (s_step[a][q] == s_step[a][i] && ((q ^ i) & 1u) == 0u) { rep = q; break; }
+        s_repidx[a][i] = (uint8_t)rep;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+        const uint32_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
+        if (cx >= L.nx || cy >= L.ny || cz < zlo || cz >= zhi) continue;
+        const uint16_t ci = S.cinfo[cidx(S, cx, cy, cz)];
+        if ((ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER)) {
+            // 16-bit counters updated through their aligned 32-bit word
+            const uint32_t cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
+            atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
+        }
+    }
+    __syncthreads();
+    QualityAcc qa = {1.0, 0.0, 0u};
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+        const uint32_t cnt = s_cnt[j];
+        if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
+    }
+    qa.flush(counters);
 }
 
 // check_for_inverted_tets for the listed (trimmed or zero-cornered) tets: one tet per thread,

@@ -3,6 +3,7 @@
 // entry point here launches CUDA kernels or fails with MC_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -90,7 +91,7 @@ static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsi
 }  // namespace mc
 
 // ---- pooled device memory ---------------------------------------------------------------
-int mc_ctx::alloc(size_t bytes, DevBuf& out) {
+int mc_ctx::alloc_raw(size_t bytes, DevBuf& out) {
     if (bytes == 0) bytes = 8;
     bytes = (bytes + 255) & ~(size_t)255;
     int best = -1;
@@ -113,6 +114,24 @@ int mc_ctx::alloc(size_t bytes, DevBuf& out) {
     held_bytes += bytes;
     out.p = p;
     out.bytes = bytes;
+    return MC_OK;
+}
+// MC_DEBUG=1 in the environment: every buffer handed out is filled with 0xFF first (reads of
+// memory no kernel wrote show up as NaN / huge indices instead of stale-but-plausible data) and
+// every stage is synchronised and checked, so that a fault is reported with the stage's name.
+int mc_ctx::alloc(size_t bytes, mc::DevBuf& out) {
+    int rc = alloc_raw(bytes, out);
+    if (rc == MC_OK && debug) {
+        cudaError_t e = cudaMemsetAsync(out.p, 0xFF, out.bytes, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(poison)");
+    }
+    return rc;
+}
+int mc_ctx::stage_check(const char* stage) {
+    if (!debug_sync) return MC_OK;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, stage);
     return MC_OK;
 }
 void mc_ctx::release(DevBuf& b) {
@@ -152,6 +171,7 @@ mc_ctx* mc_ctx_new(int device, void* stream) {
     if (device < 0 || device >= n) { fail(MC_ERR_ARG, "mc_ctx_new: bad device ordinal"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { fail(MC_ERR_CUDA, "mc_ctx_new: cudaSetDevice failed"); return nullptr; }
     mc_ctx* c = new mc_ctx();
+    { const char* dbg = std::getenv("MC_DEBUG"); const int lvl = dbg ? std::atoi(dbg) : 0; c->debug = lvl == 1 || lvl == 2; c->debug_sync = lvl == 1 || lvl == 3; }
     c->device = device;
     c->stream = (cudaStream_t)stream;
     cudaDeviceProp prop;
@@ -345,20 +365,22 @@ static int launch_sdf_field(mc_mesh* m) {
     return MC_OK;
 }
 
-int mc_estimate_layer_costs(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n) {
-    if (!c || !volume || !cost) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
-    if (!volume->valid(root) || !(resolution > 0.0)) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
+// Interval pass over the whole lattice -> per tile layer, how many tiles fall in each cost class:
+// 0 sign not proven (full SDF evaluation, possibly surface work), 1 proven inside with a proven-inside
+// 27-neighbourhood (no SDF evaluation, arithmetic output), 2 proven inside otherwise (shell evaluation
+// + output), 3 proven outside with a proven-outside neighbourhood (nothing), 4 proven outside
+// otherwise (shell evaluation).
+static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, const char* who,
+                              uint64_t dim[3], std::vector<unsigned long long>& counts, uint32_t& ntz) {
+    if (!volume->valid(root) || !(resolution > 0.0)) return fail(MC_ERR_ARG, std::string(who) + ": bad argument");
     MC_CUDA(cudaSetDevice(c->device));
     const Box& bb = volume->nodes[(size_t)root].bbox;
-    uint64_t dim[3];
     for (int k = 0; k < 3; ++k) {
         const double d = std::ceil((bb.hi[k] - bb.lo[k]) / resolution);
         if (!(d >= 0.0) || !(d < 4294967295.0) || !std::isfinite(bb.lo[k]))
-            return fail(MC_ERR_BBOX, "mc_estimate_layer_costs: the volume's bounding box is not finite");
+            return fail(MC_ERR_BBOX, std::string(who) + ": the volume's bounding box is not finite");
         dim[k] = (uint64_t)d;
     }
-    if (n != dim[2]) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: expected one entry per cell layer (" + std::to_string(dim[2]) + ")");
-    if (n == 0) return MC_OK;
     Program prog;
     std::string err;
     int rc = volume->compile(root, resolution, prog, err);
@@ -372,33 +394,68 @@ int mc_estimate_layer_costs(mc_ctx* c, const mc_tape* volume, int32_t root, doub
     TileGrid g;
     g.ntx = (L.NX + TS - 1) / TS; g.nty = (L.NY + TS - 1) / TS; g.ntz = (L.NZ + TS - 1) / TS; g.z0 = 0;
     const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
-    std::vector<double> layer((size_t)g.ntz, 1.0);
-    if (prog.n_decisions > 0) {
-        DevBuf dprog, ddec, dsign;
-        rc = upload_program(c, prog, dprog);
-        if (rc == MC_OK) rc = c->alloc((size_t)prog.n_decisions * ntiles, ddec);
-        if (rc == MC_OK) rc = c->alloc(ntiles + 4, dsign);
-        if (rc != MC_OK) return rc;
+    ntz = g.ntz;
+    counts.assign((size_t)g.ntz * 5, 0ull);
+    if (prog.n_decisions == 0) {
+        // nothing to prove with: every tile is evaluated in full
+        for (uint32_t k = 0; k < g.ntz; ++k) counts[(size_t)k * 5] = (unsigned long long)g.ntx * g.nty;
+        return MC_OK;
+    }
+    if (ntiles >= (1ull << 31)) return fail(MC_ERR_LIMIT, std::string(who) + ": lattice too large");
+    DevBuf dprog, ddec, dsign, dcnt;
+    rc = upload_program(c, prog, dprog);
+    if (rc == MC_OK) rc = c->alloc((size_t)prog.n_decisions * ntiles, ddec);
+    if (rc == MC_OK) rc = c->alloc(ntiles + 4, dsign);
+    if (rc == MC_OK) rc = c->alloc(counts.size() * 8, dcnt);
+    cudaError_t e = cudaSuccess;
+    if (rc == MC_OK) {
+        e = cudaMemsetAsync(dcnt.p, 0, counts.size() * 8, c->stream);
         k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)dprog.p, ntiles,
                                                                       (uint8_t*)ddec.p, (int8_t*)dsign.p);
-        c->launches++;
-        std::vector<int8_t> sign(ntiles);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(sign.data(), dsign.p, ntiles, cudaMemcpyDeviceToHost, c->stream);
+        k_tile_layer_classes<<<blocks_for(ntiles, 256), 256, 0, c->stream>>>(g, (const int8_t*)dsign.p, ntiles,
+                                                                             (unsigned long long*)dcnt.p);
+        c->launches += 2;
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), dcnt.p, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        c->release(dprog); c->release(ddec); c->release(dsign);
-        if (e != cudaSuccess) return cuda_fail(e, "mc_estimate_layer_costs");
-        const uint64_t per = (uint64_t)g.ntx * g.nty;
-        for (uint32_t k = 0; k < g.ntz; ++k) {
-            double s = 0.0;
-            for (uint64_t i = 0; i < per; ++i) {
-                const int8_t sg = sign[(size_t)k * per + i];
-                s += sg == 0 ? 1.0 : (sg < 0 ? 0.15 : 0.02);
-            }
-            layer[k] = s;
-        }
     }
-    for (uint64_t z = 0; z < n; ++z) cost[z] = layer[(size_t)(z / TS)] / (double)TS;
+    c->release(dprog); c->release(ddec); c->release(dsign); c->release(dcnt);
+    if (rc != MC_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    return MC_OK;
+}
+
+int mc_tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, uint64_t* counts, uint64_t n) {
+    if (!c || !volume || !counts) return fail(MC_ERR_ARG, "mc_tile_layer_classes: bad argument");
+    uint64_t dim[3];
+    std::vector<unsigned long long> cnt;
+    uint32_t ntz = 0;
+    int rc = tile_layer_classes(c, volume, root, resolution, "mc_tile_layer_classes", dim, cnt, ntz);
+    if (rc != MC_OK) return rc;
+    if (n != ntz) return fail(MC_ERR_ARG, "mc_tile_layer_classes: expected one entry per tile layer (" + std::to_string(ntz) + ")");
+    for (size_t i = 0; i < cnt.size(); ++i) counts[i] = cnt[i];
+    return MC_OK;
+}
+
+// relative cost of one tile of each class (fitted to per-slab device times of BASELINE config 4,
+// profiles/r01_notes.md "slab balance")
+static const double SLAB_CLASS_COST[5] = {MC_SLAB_COST_UNPROVEN, MC_SLAB_COST_NEG_SKIPPED, MC_SLAB_COST_NEG_SHELL,
+                                          MC_SLAB_COST_POS_SKIPPED, MC_SLAB_COST_POS_SHELL};
+
+int mc_estimate_layer_costs(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n) {
+    if (!c || !volume || !cost) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
+    uint64_t dim[3];
+    std::vector<unsigned long long> cnt;
+    uint32_t ntz = 0;
+    int rc = tile_layer_classes(c, volume, root, resolution, "mc_estimate_layer_costs", dim, cnt, ntz);
+    if (rc != MC_OK) return rc;
+    if (n != dim[2]) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: expected one entry per cell layer (" + std::to_string(dim[2]) + ")");
+    for (uint64_t z = 0; z < n; ++z) {
+        const size_t k = (size_t)(z / TS);
+        double s = 0.0;
+        for (int q = 0; q < 5; ++q) s += SLAB_CLASS_COST[q] * (double)cnt[k * 5 + q];
+        cost[z] = s / (double)TS;
+    }
     return MC_OK;
 }
 
@@ -502,13 +559,16 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     // a2: SDF field on all stored planes
     MC_TRY_CUDA(cudaEventRecord(m->ev[0], s));
     MC_TRY(launch_sdf_field(m));
+    MC_TRY(c->stage_check("stage sdf_field"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
     // tile sign summary + a6: warp codes
     k_tile_minmax<<<tgrid, TILE_THREADS, 0, s>>>(S);
     k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
+    MC_TRY(c->stage_check("stage tile summary"));
     k_warp_codes<<<tgrid, TILE_THREADS, 0, s>>>(S, counters);
     c->launches += 3;
     MC_TRY_CUDA(cudaGetLastError());
+    MC_TRY(c->stage_check("stage warp codes"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[2], s));
     // a5/a7/a9: classification + counts
     k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
@@ -520,6 +580,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY_CUDA(cudaGetLastError());
     // CN_TETS / CN_KEPT are adjacent: totals[0] = output tets, totals[1] = kept lattice tets
     static_assert(CN_KEPT == CN_TETS + 1, "scan totals layout");
+    MC_TRY(c->stage_check("stage classify"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[3], s));
     // a10 pass 1: vertex masks + counts
     k_vertex_count<<<tgrid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_vtile_tot.p);
@@ -529,6 +590,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     c->launches += 2;
     MC_TRY_CUDA(cudaGetLastError());
     static_assert(CN_CUTS == CN_VERTS + 1, "scan totals layout");
+    MC_TRY(c->stage_check("stage vertex count"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[4], s));
     MC_TRY_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
     MC_TRY_CUDA(cudaStreamSynchronize(s));
@@ -565,6 +627,7 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
                                                                (double*)m->d_coords.p, (unsigned long long*)m->d_cutlist.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
+    if ((rc = c->stage_check("stage vertex emit")) != MC_OK) return rc;
     MC_CUDA(cudaEventRecord(m->ev[6], s));
     if (m->n_cuts > 0) {
         if (m->tiled_sdf && m->d_dec.p) {
@@ -587,6 +650,7 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
         c->launches++;
         MC_CUDA(cudaGetLastError());
     }
+    if ((rc = c->stage_check("stage bisect")) != MC_OK) return rc;
     MC_CUDA(cudaEventRecord(m->ev[7], s));
     // id table of the top owned plane for the rank above
     if (m->c1 < L.nz && m->points_owned > 0) {
@@ -596,6 +660,7 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
         k_export_plane<<<blocks_for(n, 256), 256, 0, s>>>(S, m->oz1, (unsigned long long*)m->d_plane_table.p);
         c->launches++;
         MC_CUDA(cudaGetLastError());
+        if ((rc = c->stage_check("stage export plane")) != MC_OK) return rc;
     }
     m->phase = 2;
     return MC_OK;
@@ -638,9 +703,13 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         if (m->index_bytes == 4) {
             uint32_t* out = (uint32_t*)m->d_tets.p;
             k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
+            if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
+                k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
+                if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
             } else {
                 k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
@@ -648,17 +717,22 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
             k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
+            if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
                 k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
+                k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
+                if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
             } else {
                 k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
             }
         }
         c->release(qlist);
-        c->launches += quality ? 4 : 2;
+        c->launches += quality ? 5 : 2;
         MC_CUDA(cudaGetLastError());
+        if ((rc = c->stage_check("stage tet emit / quality list")) != MC_OK) return rc;
     }
     MC_CUDA(cudaEventRecord(m->ev[9], s));
     MC_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));

@@ -306,6 +306,26 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
 }
 
+// cost classes of the tiles per tile layer (see tile_layer_classes in mc_mesher.cu): counts[layer * 5 + class]
+static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict__ tsign, uint64_t ntiles,
+                                            unsigned long long* __restrict__ counts) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int tix = (int)(t % g.ntx), tiy = (int)((t / g.ntx) % g.nty), tiz = (int)(t / ((uint64_t)g.ntx * g.nty));
+    const int sg = tsign[t];
+    int cls = 0;
+    if (sg != 0) {
+        bool uniform = true;
+        for (int q = 0; q < 27 && uniform; ++q) {
+            const int x = tix + q % 3 - 1, y = tiy + (q / 3) % 3 - 1, z = tiz + q / 9 - 1;
+            if (x < 0 || y < 0 || z < 0 || x >= (int)g.ntx || y >= (int)g.nty || z >= (int)g.ntz) continue;
+            if (tsign[((size_t)z * g.nty + y) * g.ntx + x] != sg) uniform = false;
+        }
+        cls = sg < 0 ? (uniform ? 1 : 2) : (uniform ? 3 : 4);
+    }
+    atomicAdd(&counts[(size_t)tiz * 5 + cls], 1ull);
+}
+
 // Block-cooperative compaction of the program for one tile into shared memory (s_prog), using the
 // tile's decisions.  All threads of the block must call it; it ends with the result visible to
 // the whole block once the caller has synchronised.  Returns the number of words via s_newpos[n_inst].

@@ -102,6 +102,17 @@ def exchange_plane_tables(send_table, recv_table, rank, world, group=None, activ
             w.wait()
 
 
+def tile_layer_classes(ctx, obj, resolution):
+    """Tile counts per tile layer and cost class (C ABI mc_tile_layer_classes): (n_tile_layers, 5)."""
+    import numpy as np
+    dim = lattice_dim(obj.bbox(), float(resolution))
+    n = (dim[2] + 1 + 15) // 16
+    counts = np.zeros((n, 5), dtype=np.uint64)
+    _lib.check(_lib.lib().mc_tile_layer_classes(ctx.handle, obj.backend.handle, obj.node, float(resolution),
+                                                counts.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+    return counts
+
+
 class SlabMesher:
     """Meshes this rank's slab of the global lattice.  Usage (every rank):
 
