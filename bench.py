@@ -170,8 +170,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (moosecad_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host-valued bookkeeping (slab class table, per-slab counts) travels over a host group
+        host_group = dist.new_group(backend="gloo")
     steps, warm = max(1, args.steps), max(3, args.warmup)
 
     stream = torch.cuda.Stream(device=dev)
@@ -188,9 +191,13 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
+        host_ms = {}
+
         def one_step(flags=0):
-            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev, flags=flags)
-            return sm.run()
+            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev, flags=flags, host_group=host_group)
+            h = sm.run()
+            host_ms.update(sm.host_ms)
+            return h
 
         def stage_ms(h):
             ms = (C.c_double * 9)()
@@ -241,6 +248,13 @@ def main():
         ms_step = float(t.item()) / steps
         n_verts, n_tets, launches_all = (int(x) for x in cnt.tolist())
         stage_avg = [a / steps for a in stage_acc]
+        # diagnostics (outside the timed region): every rank's own device time and host phases
+        mine = {"rank": rank, "device_stage_ms_sum": round(sum(stage_avg), 3),
+                "host_ms_last_step": {k: round(v, 3) for k, v in host_ms.items()}}
+        per_rank = [mine]
+        if world > 1:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, mine)
 
         # ---- end to end through the C ABI with HOST buffers ----
         e2e = None
@@ -333,6 +347,17 @@ def main():
                                           "boundary", "sidesets"], [round(x, 3) for x in stage_avg])),
                     "roofline": roof, "roofline_stuffing": roof2,
                     "gpu_launches": launches_all, "clocks": clocks, "e2e": e2e}
+            if world > 1:
+                line["per_rank"] = per_rank
+            # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_sdf_traffic.json")) as f:
+                    tr = json.load(f).get(f"{args.workload}@{world}")
+                if tr:
+                    roof["traffic"] = tr["dram_bytes_per_launch"]
+                    roof["traffic_source"] = tr["source"]
+            except (OSError, ValueError):
+                pass
             if not args.no_cpu_baseline and world == 1:
                 line["cpu_baseline"] = cpu_baseline_sample(args.workload)
             print(json.dumps(line), flush=True)

@@ -157,15 +157,26 @@ typedef struct mc_options {
  *   2 proven inside next to other tiles (shell evaluation + output)
  *   3 proven outside, neighbourhood too (nothing to do)
  *   4 proven outside next to other tiles (shell evaluation)
- * mc_tile_layer_classes returns counts[layer * 5 + class] for the n = ceil((dim[2] + 1) / 16) tile
- * layers; mc_estimate_layer_costs turns them into a relative cost per CELL layer z (n = dim[2]
- * doubles) with the weights below.  Deterministic, so every rank derives the same partition. */
-#define MC_SLAB_COST_UNPROVEN 1.0
-#define MC_SLAB_COST_NEG_SKIPPED 0.3
-#define MC_SLAB_COST_NEG_SHELL 0.3
-#define MC_SLAB_COST_POS_SKIPPED 0.03
-#define MC_SLAB_COST_POS_SHELL 0.03
-int mc_tile_layer_classes(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, uint64_t* counts, uint64_t n);
+ * mc_tile_layer_classes fills counts[layer * MC_TILE_CLASS_STRIDE + q] for the tile layers
+ * [layer_begin, layer_end) of the n = ceil((dim[2] + 1) / 16) tile layers (the other rows are zeroed, so
+ * ranks can each take a range and sum the tables): q = 0..4 the number of tiles per class, q = 5 the summed
+ * per-point work (approximate FP64 operations of the tile-specialised program) of the class-0 tiles,
+ * q = 6 the same for the shell-evaluated tiles (classes 2 and 4).  mc_estimate_layer_costs turns them
+ * into a relative cost per CELL layer z (n = dim[2] doubles) with the weights below (least-squares
+ * fit to per-slab device times, scripts/slab_balance.py).  Deterministic, so every rank derives the
+ * same partition. */
+#define MC_TILE_CLASS_STRIDE 7
+#define MC_SLAB_COST_UNPROVEN 0.05
+#define MC_SLAB_COST_NEG_SKIPPED 0.07
+#define MC_SLAB_COST_NEG_SHELL 0.02
+#define MC_SLAB_COST_POS_SKIPPED 0.002
+#define MC_SLAB_COST_POS_SHELL 0.02
+#define MC_SLAB_COST_UNPROVEN_WORK 1.9e-4
+#define MC_SLAB_COST_SHELL_WORK 0.0
+int mc_tile_layer_classes(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, uint64_t layer_begin,
+                          uint64_t layer_end, uint64_t* counts, uint64_t n);
+/* the MC_TILE_CLASS_STRIDE weights mc_estimate_layer_costs applies to those counts */
+void mc_slab_class_weights(double* out);
 int mc_estimate_layer_costs(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n);
 
 /* Phase 1: SDF field, warp, classification, counting.  After it returns, the per-slab counts
@@ -178,11 +189,29 @@ int mc_tessellate_begin(mc_ctx*, const mc_tape* volume, int32_t root, double res
  * (exclusive scan of mc_mesh_counts()[0] over the ranks; 0 on one GPU).  Afterwards
  * mc_mesh_upper_plane_table() is valid. */
 int mc_tessellate_emit_vertices(mc_mesh*, uint64_t vertex_base);
+/* Optional, between phases 1 and 2: launch the part of phase 2 that does not need vertex_base
+ * (coordinates + bisection) and return without waiting.  A multi-rank caller issues it before
+ * the blocking exchange of the counts, so the device works while the ranks wait for each other. */
+int mc_tessellate_emit_vertices_local(mc_mesh*);
 /* Phase 3: emit this slab's tets with global vertex ids.  tet_base: global index of this
  * slab's first tet.  d_lower_plane: device pointer to the id table of the lattice plane
  * z = z_begin produced by the rank below (its mc_mesh_upper_plane_table), or NULL for the
  * first slab. */
 int mc_tessellate_emit_tets(mc_mesh*, uint64_t tet_base, const void* d_lower_plane);
+/* Optional, before phase 3 on a slab with z_begin > 0: the coordinates of the rank below's top
+ * tile layer (its mc_mesh_upper_layer_coords; `count` vertices with global ids starting at
+ * first_global_id = its vertex_base + its first_local), so that check_for_inverted_tets can also
+ * evaluate the trimmed tets that touch the shared plane.  Without it those tets are left out of
+ * the aspect-ratio / inverted statistics of mc_mesh_stats (the mesh itself is unaffected). */
+int mc_tessellate_set_lower_coords(mc_mesh*, const void* d_coords, uint64_t first_global_id, uint64_t count);
+/* what the rank ABOVE needs for that: the vertices of the tile layer holding this slab's top plane
+ * are the tail of the slab's vertex range: local index of the first one + how many (valid after
+ * phase 1; count = 0 on the top slab), a device pointer to their xyz (valid after
+ * mc_tessellate_emit_vertices(_local)), and an asynchronous copy into a caller's DEVICE buffer
+ * (count * 24 bytes) on the context's stream: the send buffer of the NVLink exchange. */
+int mc_mesh_upper_layer_vertices(const mc_mesh*, uint64_t* first_local, uint64_t* count);
+int mc_mesh_upper_layer_coords(mc_mesh*, void** d_coords);
+int mc_mesh_copy_upper_layer_coords(mc_mesh*, void* d_dst);
 /* all phases for the whole lattice on one device */
 int mc_tessellate(mc_ctx*, const mc_tape* volume, int32_t root, double resolution,
                   double relative_error, const mc_options* opts, mc_mesh** out);

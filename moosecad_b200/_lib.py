@@ -15,6 +15,7 @@ MC_ERR_ARG, MC_ERR_BBOX, MC_ERR_SINGULAR, MC_ERR_UNSUPPORTED = -1, -2, -3, -4
 MC_ERR_CUDA, MC_ERR_LIMIT, MC_ERR_DIVERGED, MC_ERR_STATE = -5, -6, -7, -8
 MC_OPT_KEEP_PHI, MC_OPT_SKIP_QUALITY, MC_OPT_NO_TILE_PRUNING, MC_OPT_FORCE_TILE_PRUNING = 1, 2, 4, 8
 MC_OPT_COUNT_FLOPS = 16
+MC_TILE_CLASS_STRIDE = 7
 
 
 class McError(RuntimeError):
@@ -76,10 +77,16 @@ SIGNATURES = {
     "mc_eval_points": (C.c_int, [_P, _P, _I32, _D, _PD, _U64, _PD]),
     "mc_eval_points_device": (C.c_int, [_P, _P, _I32, _D, _P, _U64, _P]),
     "mc_estimate_layer_costs": (C.c_int, [_P, _P, _I32, _D, _PD, _U64]),
-    "mc_tile_layer_classes": (C.c_int, [_P, _P, _I32, _D, C.POINTER(_U64), _U64]),
+    "mc_tile_layer_classes": (C.c_int, [_P, _P, _I32, _D, _U64, _U64, C.POINTER(_U64), _U64]),
+    "mc_slab_class_weights": (None, [_PD]),
     "mc_tessellate_begin": (C.c_int, [_P, _P, _I32, _D, _D, C.POINTER(mc_slab), C.POINTER(mc_options),
                                       C.POINTER(_P)]),
     "mc_tessellate_emit_vertices": (C.c_int, [_P, _U64]),
+    "mc_tessellate_emit_vertices_local": (C.c_int, [_P]),
+    "mc_tessellate_set_lower_coords": (C.c_int, [_P, _P, _U64, _U64]),
+    "mc_mesh_upper_layer_vertices": (C.c_int, [_P, C.POINTER(_U64), C.POINTER(_U64)]),
+    "mc_mesh_upper_layer_coords": (C.c_int, [_P, C.POINTER(_P)]),
+    "mc_mesh_copy_upper_layer_coords": (C.c_int, [_P, _P]),
     "mc_tessellate_emit_tets": (C.c_int, [_P, _U64, _P]),
     "mc_tessellate": (C.c_int, [_P, _P, _I32, _D, _D, C.POINTER(mc_options), C.POINTER(_P)]),
     "mc_mesh_free": (None, [_P]),

@@ -56,7 +56,11 @@ struct mc_mesh {
     mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign;
     mc::DevBuf d_ttile_tot, d_ttile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
     const void* lower_table = nullptr;  // id table of plane c0 from the rank below (caller-owned)
+    const double* lower_coords = nullptr;  // coordinates of the rank below's top tile layer (caller-owned)
+    uint64_t lower_first = 0, lower_count = 0;  // global ids [first, first + count) of that slice
+    uint64_t top_layer_first = 0;  // local index of the first vertex of the tile layer holding plane c1
     bool tiled_sdf = false;
+    bool vertices_local_done = false;  // mc_tessellate_emit_vertices_local has run
     mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
     mc::DevBuf d_inst_start, d_word_inst, d_dec;  // tile specialisation (mc_prune.cuh)
     uint64_t n_tiles = 0;

@@ -1208,11 +1208,15 @@ k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
 }
 
 // check_for_inverted_tets for the listed (trimmed or zero-cornered) tets: one tet per thread,
-// positions gathered from the emitted coordinates
+// positions gathered from the emitted coordinates.  Vertices owned by the rank below (ids under
+// vertex_base) are looked up in the slice of ITS coordinates that came with the plane table
+// (lower_coords: global ids [lower_first, lower_first + lower_count)); without that slice such
+// tets are left out of the statistics.
 template <typename IndexT>
 __global__ void __launch_bounds__(256)
 k_tet_quality_list(const double* __restrict__ coords, const IndexT* __restrict__ tets,
                    const unsigned long long* __restrict__ qlist, uint64_t n, long long vertex_base,
+                   const double* __restrict__ lower_coords, long long lower_first, long long lower_count,
                    unsigned long long* __restrict__ counters) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     QualityAcc qa = {1.0, 0.0, 0u};
@@ -1222,10 +1226,15 @@ k_tet_quality_list(const double* __restrict__ coords, const IndexT* __restrict__
         bool have = true;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const long long id = (long long)tets[4 * e + m] - vertex_base;
-            if (id < 0) { have = false; break; }  // vertex owned by the rank below
+            const long long gid = (long long)tets[4 * e + m];
+            const double* src = coords + 3 * (gid - vertex_base);
+            if (gid < vertex_base) {
+                const long long lid = gid - lower_first;
+                if (lower_coords == nullptr || lid < 0 || lid >= lower_count) { have = false; break; }
+                src = lower_coords + 3 * lid;
+            }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p[m][k] = coords[3 * id + k];
+            for (int k = 0; k < 3; ++k) p[m][k] = src[k];
         }
         if (have) qa.add(p[0], p[1], p[2], p[3]);
     }

@@ -371,7 +371,8 @@ static int launch_sdf_field(mc_mesh* m) {
 // + output), 3 proven outside with a proven-outside neighbourhood (nothing), 4 proven outside
 // otherwise (shell evaluation).
 static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, const char* who,
-                              uint64_t dim[3], std::vector<unsigned long long>& counts, uint32_t& ntz) {
+                              uint64_t dim[3], uint64_t layer_begin, uint64_t layer_end,
+                              std::vector<unsigned long long>& counts, uint32_t& ntz) {
     if (!volume->valid(root) || !(resolution > 0.0)) return fail(MC_ERR_ARG, std::string(who) + ": bad argument");
     MC_CUDA(cudaSetDevice(c->device));
     const Box& bb = volume->nodes[(size_t)root].bbox;
@@ -393,44 +394,58 @@ static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, do
     L.pz0 = 0; L.pz1 = L.nz;
     TileGrid g;
     g.ntx = (L.NX + TS - 1) / TS; g.nty = (L.NY + TS - 1) / TS; g.ntz = (L.NZ + TS - 1) / TS; g.z0 = 0;
-    const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
     ntz = g.ntz;
-    counts.assign((size_t)g.ntz * 5, 0ull);
+    if (layer_end > ntz) layer_end = ntz;
+    if (layer_begin > layer_end) layer_begin = layer_end;
+    counts.assign((size_t)ntz * MC_TILE_CLASS_STRIDE, 0ull);
+    if (layer_begin == layer_end) return MC_OK;
+    // the tiles of the requested layers plus one layer either side (the neighbourhood test)
+    const uint32_t k_lo = layer_begin > 0 ? (uint32_t)layer_begin - 1 : 0u, k_hi = (uint32_t)std::min<uint64_t>(ntz, layer_end + 1);
+    g.z0 = k_lo * TS;
+    g.ntz = k_hi - k_lo;
+    const uint32_t first = (uint32_t)layer_begin - k_lo, last = (uint32_t)layer_end - k_lo;  // local range that is counted
+    const uint64_t ntiles = (uint64_t)g.ntx * g.nty * g.ntz;
     if (prog.n_decisions == 0) {
         // nothing to prove with: every tile is evaluated in full
-        for (uint32_t k = 0; k < g.ntz; ++k) counts[(size_t)k * 5] = (unsigned long long)g.ntx * g.nty;
+        for (uint64_t k = layer_begin; k < layer_end; ++k) {
+            counts[(size_t)k * MC_TILE_CLASS_STRIDE] = (unsigned long long)g.ntx * g.nty;
+            counts[(size_t)k * MC_TILE_CLASS_STRIDE + 5] = (unsigned long long)g.ntx * g.nty * (unsigned long long)prog.flops;
+        }
         return MC_OK;
     }
     if (ntiles >= (1ull << 31)) return fail(MC_ERR_LIMIT, std::string(who) + ": lattice too large");
-    DevBuf dprog, ddec, dsign, dcnt;
+    DevBuf dprog, ddec, dsign, dcnt, dwork;
     rc = upload_program(c, prog, dprog);
     if (rc == MC_OK) rc = c->alloc((size_t)prog.n_decisions * ntiles, ddec);
     if (rc == MC_OK) rc = c->alloc(ntiles + 4, dsign);
     if (rc == MC_OK) rc = c->alloc(counts.size() * 8, dcnt);
+    if (rc == MC_OK) rc = c->alloc((ntiles + 1) * 4, dwork);
     cudaError_t e = cudaSuccess;
     if (rc == MC_OK) {
         e = cudaMemsetAsync(dcnt.p, 0, counts.size() * 8, c->stream);
         k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)dprog.p, ntiles,
-                                                                      (uint8_t*)ddec.p, (int8_t*)dsign.p);
-        k_tile_layer_classes<<<blocks_for(ntiles, 256), 256, 0, c->stream>>>(g, (const int8_t*)dsign.p, ntiles,
-                                                                             (unsigned long long*)dcnt.p);
+                                                                      (uint8_t*)ddec.p, (int8_t*)dsign.p, (float*)dwork.p);
+        k_tile_layer_classes<<<blocks_for(ntiles, 256), 256, 0, c->stream>>>(
+            g, (const int8_t*)dsign.p, (const float*)dwork.p, ntiles, first, last,
+            (unsigned long long*)dcnt.p + (size_t)k_lo * MC_TILE_CLASS_STRIDE);
         c->launches += 2;
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), dcnt.p, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     }
-    c->release(dprog); c->release(ddec); c->release(dsign); c->release(dcnt);
+    c->release(dprog); c->release(ddec); c->release(dsign); c->release(dcnt); c->release(dwork);
     if (rc != MC_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, who);
     return MC_OK;
 }
 
-int mc_tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, uint64_t* counts, uint64_t n) {
+int mc_tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, uint64_t layer_begin,
+                          uint64_t layer_end, uint64_t* counts, uint64_t n) {
     if (!c || !volume || !counts) return fail(MC_ERR_ARG, "mc_tile_layer_classes: bad argument");
     uint64_t dim[3];
     std::vector<unsigned long long> cnt;
     uint32_t ntz = 0;
-    int rc = tile_layer_classes(c, volume, root, resolution, "mc_tile_layer_classes", dim, cnt, ntz);
+    int rc = tile_layer_classes(c, volume, root, resolution, "mc_tile_layer_classes", dim, layer_begin, layer_end, cnt, ntz);
     if (rc != MC_OK) return rc;
     if (n != ntz) return fail(MC_ERR_ARG, "mc_tile_layer_classes: expected one entry per tile layer (" + std::to_string(ntz) + ")");
     for (size_t i = 0; i < cnt.size(); ++i) counts[i] = cnt[i];
@@ -439,21 +454,26 @@ int mc_tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, double
 
 // relative cost of one tile of each class (fitted to per-slab device times of BASELINE config 4,
 // profiles/r01_notes.md "slab balance")
-static const double SLAB_CLASS_COST[5] = {MC_SLAB_COST_UNPROVEN, MC_SLAB_COST_NEG_SKIPPED, MC_SLAB_COST_NEG_SHELL,
-                                          MC_SLAB_COST_POS_SKIPPED, MC_SLAB_COST_POS_SHELL};
+static const double SLAB_CLASS_COST[MC_TILE_CLASS_STRIDE] = {
+    MC_SLAB_COST_UNPROVEN, MC_SLAB_COST_NEG_SKIPPED, MC_SLAB_COST_NEG_SHELL, MC_SLAB_COST_POS_SKIPPED,
+    MC_SLAB_COST_POS_SHELL, MC_SLAB_COST_UNPROVEN_WORK, MC_SLAB_COST_SHELL_WORK};
+
+void mc_slab_class_weights(double* out) {
+    if (out) for (int q = 0; q < MC_TILE_CLASS_STRIDE; ++q) out[q] = SLAB_CLASS_COST[q];
+}
 
 int mc_estimate_layer_costs(mc_ctx* c, const mc_tape* volume, int32_t root, double resolution, double* cost, uint64_t n) {
     if (!c || !volume || !cost) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: bad argument");
     uint64_t dim[3];
     std::vector<unsigned long long> cnt;
     uint32_t ntz = 0;
-    int rc = tile_layer_classes(c, volume, root, resolution, "mc_estimate_layer_costs", dim, cnt, ntz);
+    int rc = tile_layer_classes(c, volume, root, resolution, "mc_estimate_layer_costs", dim, 0, ~0ull, cnt, ntz);
     if (rc != MC_OK) return rc;
     if (n != dim[2]) return fail(MC_ERR_ARG, "mc_estimate_layer_costs: expected one entry per cell layer (" + std::to_string(dim[2]) + ")");
     for (uint64_t z = 0; z < n; ++z) {
         const size_t k = (size_t)(z / TS);
         double s = 0.0;
-        for (int q = 0; q < 5; ++q) s += SLAB_CLASS_COST[q] * (double)cnt[k * 5 + q];
+        for (int q = 0; q < MC_TILE_CLASS_STRIDE; ++q) s += SLAB_CLASS_COST[q] * (double)cnt[k * MC_TILE_CLASS_STRIDE + q];
         cost[z] = s / (double)TS;
     }
     return MC_OK;
@@ -593,7 +613,17 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->stage_check("stage vertex count"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[4], s));
     MC_TRY_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    // first vertex of the tile layer that holds the top owned plane: from there to the end, the
+    // coordinates are what the rank above needs for the tets that touch the shared plane
+    unsigned long long top_first = 0ull;
+    const bool has_upper = m->c1 < L.nz && nown > 0;
+    if (has_upper) {
+        const uint64_t kz = (m->oz1 - L.pz0) / TS;
+        MC_TRY_CUDA(cudaMemcpyAsync(&top_first, (const unsigned long long*)m->d_vtile_vbase.p + kz * m->g.ntx * m->g.nty, 8,
+                                    cudaMemcpyDeviceToHost, s));
+    }
     MC_TRY_CUDA(cudaStreamSynchronize(s));
+    m->top_layer_first = top_first;
     m->n_verts = m->counters[CN_VERTS];
     m->n_cuts = m->counters[CN_CUTS];
     m->n_tets = m->counters[CN_TETS];
@@ -608,12 +638,16 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     return MC_OK;
 }
 
-int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
-    if (!m || m->phase != 1) return fail(MC_ERR_STATE, "mc_tessellate_emit_vertices: call mc_tessellate_begin first");
+// The part of the vertex emission that does not depend on the slab's global vertex base:
+// coordinates of the lattice vertices, the cut-edge work list and the bisection.  Only launches
+// work; a multi-rank caller issues it before the (blocking) exchange of the counts so that the
+// device is busy while the ranks wait for each other.
+int mc_tessellate_emit_vertices_local(mc_mesh* m) {
+    if (!m || m->phase != 1 || m->vertices_local_done)
+        return fail(MC_ERR_STATE, "mc_tessellate_emit_vertices_local: call it once, after mc_tessellate_begin");
     mc_ctx* c = m->ctx;
     MC_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    m->vertex_base = vertex_base;
     int rc;
     rc = c->alloc(std::max<uint64_t>(m->n_verts, 1) * 24, m->d_coords);
     if (rc != MC_OK) return rc;
@@ -652,6 +686,20 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
     }
     if ((rc = c->stage_check("stage bisect")) != MC_OK) return rc;
     MC_CUDA(cudaEventRecord(m->ev[7], s));
+    m->vertices_local_done = true;
+    return MC_OK;
+}
+
+int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
+    if (!m || m->phase != 1) return fail(MC_ERR_STATE, "mc_tessellate_emit_vertices: call mc_tessellate_begin first");
+    int rc;
+    if (!m->vertices_local_done && (rc = mc_tessellate_emit_vertices_local(m)) != MC_OK) return rc;
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    m->vertex_base = vertex_base;
+    const Lattice& L = m->L;
+    const Stuff S = make_stuff(m);
     // id table of the top owned plane for the rank above
     if (m->c1 < L.nz && m->points_owned > 0) {
         const uint64_t n = (uint64_t)L.NX * L.NY;
@@ -663,6 +711,44 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
         if ((rc = c->stage_check("stage export plane")) != MC_OK) return rc;
     }
     m->phase = 2;
+    return MC_OK;
+}
+
+int mc_tessellate_set_lower_coords(mc_mesh* m, const void* d_coords, uint64_t first_global_id, uint64_t count) {
+    if (!m || m->phase >= 3) return fail(MC_ERR_STATE, "mc_tessellate_set_lower_coords: call it before mc_tessellate_emit_tets");
+    m->lower_coords = count ? (const double*)d_coords : nullptr;
+    m->lower_first = first_global_id;
+    m->lower_count = m->lower_coords ? count : 0;
+    return MC_OK;
+}
+
+int mc_mesh_upper_layer_vertices(const mc_mesh* m, uint64_t* first_local, uint64_t* count) {
+    if (!m || m->phase < 1) return fail(MC_ERR_STATE, "mc_mesh_upper_layer_vertices: call mc_tessellate_begin first");
+    const bool has_upper = m->c1 < m->L.nz && m->points_owned > 0;
+    if (first_local) *first_local = has_upper ? m->top_layer_first : m->n_verts;
+    if (count) *count = has_upper ? m->n_verts - m->top_layer_first : 0;
+    return MC_OK;
+}
+
+int mc_mesh_upper_layer_coords(mc_mesh* m, void** d_coords) {
+    if (!m || !d_coords || !(m->vertices_local_done || m->phase >= 2))
+        return fail(MC_ERR_STATE, "mc_mesh_upper_layer_coords: call mc_tessellate_emit_vertices(_local) first");
+    uint64_t first = 0, count = 0;
+    mc_mesh_upper_layer_vertices(m, &first, &count);
+    *d_coords = count ? (void*)((double*)m->d_coords.p + 3 * first) : nullptr;
+    return MC_OK;
+}
+
+int mc_mesh_copy_upper_layer_coords(mc_mesh* m, void* d_dst) {
+    void* src = nullptr;
+    int rc = mc_mesh_upper_layer_coords(m, &src);
+    if (rc != MC_OK) return rc;
+    uint64_t first = 0, count = 0;
+    mc_mesh_upper_layer_vertices(m, &first, &count);
+    if (!count) return MC_OK;
+    if (!d_dst) return fail(MC_ERR_ARG, "mc_mesh_copy_upper_layer_coords: null destination");
+    MC_CUDA(cudaSetDevice(m->ctx->device));
+    MC_CUDA(cudaMemcpyAsync(d_dst, src, count * 24, cudaMemcpyDeviceToDevice, m->ctx->stream));
     return MC_OK;
 }
 
@@ -710,7 +796,7 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
-                if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
+                if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
                 k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
             }
@@ -724,7 +810,7 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
-                if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, counters);
+                if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
                 k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
             }

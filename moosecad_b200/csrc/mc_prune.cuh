@@ -54,8 +54,12 @@ __device__ __forceinline__ Ival iv_box_distance(const uint64_t* __restrict__ w, 
 
 // Interval evaluation of the program for one tile (this lane); decisions are written to
 // dec[id * dec_stride].  All 32 lanes of the warp run in lock step.
+// *work (optional) receives a rough count of the FP64 operations one point evaluation of the
+// tile-specialised program costs (the load estimate of mc_tile_layer_classes).
 __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
-                          size_t dec_stride) {
+                          size_t dec_stride, float* work = nullptr) {
+    float wk = 0.0f;
+    int dead_end = -1;  // this lane's tile is inside a failed guard up to this word
     Ival vs[MC_MAX_VALUE_DEPTH + 1];
     double bs[6 * MC_MAX_POINT_DEPTH];
     double b[6];
@@ -68,9 +72,11 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
     for (;;) {
         const uint64_t h = w[pc];
         const uint32_t op = MC_HDR_OP(h);
-        if (op == MC_OP_END) return top;
+        if (op == MC_OP_END) { if (work) *work = wk; return top; }
+        const bool alive = pc >= dead_end;
         switch (op) {
         case MC_OP_PLANE: {
+            if (alive) wk += 3.0f;
             const unsigned sm = MC_HDR_SMALL(h);
             const unsigned axis = sm & 3u;
             const double d = ld_f64(w, pc + 1);
@@ -81,6 +87,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         case MC_OP_NPLANE: {
+            if (alive) wk += 6.0f;
             Ival s = {-ld_f64(w, pc + 4), -ld_f64(w, pc + 4)};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -91,6 +98,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         case MC_OP_USQ: {
+            if (alive) wk += 6.0f;
             Ival s = {-1.0, -1.0};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -101,6 +109,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         case MC_OP_CONE: {
+            if (alive) wk += 12.0f;
             const Ival ax = iv_abs(b[0], b[1]), ay = iv_abs(b[2], b[3]);
             const Ival rho = {sqrt(ax.lo * ax.lo + ay.lo * ay.lo), sqrt(ax.hi * ax.hi + ay.hi * ay.hi)};
             const double off = ld_f64(w, pc + 2);
@@ -127,6 +136,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
             else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
             dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (alive) wk += d == MC_DEC_FAIL ? 12.0f : 20.0f;
             MC_IPUSH(v);
             break;
         }
@@ -160,6 +170,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
             else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
             dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (alive) wk += d == MC_DEC_FAIL ? 12.0f : 12.0f + 6.0f * (float)kept + (kept > 1 ? 30.0f * (float)(kept + 1) : 0.0f);
             MC_IPUSH(v);
             break;
         }
@@ -171,6 +182,10 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             if (a.hi <= slack) d = MC_DEC_PASS;
             else if (a.lo > slack) d = MC_DEC_FAIL;
             dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (alive) {
+                wk += op == MC_OP_GAPUSH ? 30.0f : 12.0f;
+                if (d == MC_DEC_FAIL) dead_end = (int)MC_HDR_IDX(h);
+            }
             // the subtree is skipped only when it is dead for all 32 tiles of the warp
             if (__all_sync(0xffffffffu, d == MC_DEC_FAIL)) {
                 MC_IPUSH(a);
@@ -240,6 +255,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
                     else { res.lo = fmax(res.lo, x.lo); res.hi = fmax(res.hi, x.hi); }
                 }
             }
+            if (alive && kept > 1) wk += 30.0f * (float)(kept + 1);
             if (kept > 1) {
                 // smooth branch: rvmin in [min - r/4 ln k, min], rvmax in [max, max + r/4 ln k]
                 const double wdn = 0.25 * r * 1.3862943611198906 * (double)(kept <= 4 ? 1 : 2) * (kept <= 16 ? 1.0 : 2.5);
@@ -251,6 +267,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         case MC_OP_APUSH: {
+            if (alive) wk += 18.0f;
 #pragma unroll
             for (int k = 0; k < 6; ++k) bs[bsp + k] = b[k];
             bsp += 6;
@@ -278,6 +295,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         default:
+            if (work) *work = wk;
             return Ival{-INF, INF};
         }
         pc += mc_op_words(op);
@@ -288,7 +306,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
 // decisions for every tile: one tile per lane
 static __global__ void __launch_bounds__(128)
 k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint8_t* __restrict__ dec,
-              int8_t* __restrict__ tsign) {
+              int8_t* __restrict__ tsign, float* __restrict__ twork = nullptr) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
@@ -301,17 +319,22 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     const uint32_t X1 = min(X0 + TS, L.nx), Y1 = min(Y0 + TS, L.ny), Z1 = min(Z0 + TS, L.nz);
     const double box[6] = {lat_x(L, Xa), lat_x(L, X1), lat_y(L, Ya), lat_y(L, Y1), lat_z(L, Za), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
-    const Ival root = vm_decide(prog, box, dec + tc, (size_t)ntiles);
+    float wk = 0.0f;
+    const Ival root = vm_decide(prog, box, dec + tc, (size_t)ntiles, twork ? &wk : nullptr);
+    if (twork) twork[tc] = wk;
     // proven sign of the whole tile (the bounds are padded; NaN proves nothing)
     tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
 }
 
-// cost classes of the tiles per tile layer (see tile_layer_classes in mc_mesher.cu): counts[layer * 5 + class]
-static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict__ tsign, uint64_t ntiles,
+// cost classes of the tiles per tile layer (see tile_layer_classes in mc_mesher.cu):
+// counts[layer * MC_TILE_CLASS_STRIDE + class], + 5: work of the class-0 tiles, + 6: of the shell tiles
+static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict__ tsign, const float* __restrict__ twork,
+                                            uint64_t ntiles, uint32_t first, uint32_t last,
                                             unsigned long long* __restrict__ counts) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     const int tix = (int)(t % g.ntx), tiy = (int)((t / g.ntx) % g.nty), tiz = (int)(t / ((uint64_t)g.ntx * g.nty));
+    if ((uint32_t)tiz < first || (uint32_t)tiz >= last) return;  // halo layer: only looked at
     const int sg = tsign[t];
     int cls = 0;
     if (sg != 0) {
@@ -323,7 +346,11 @@ static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict
         }
         cls = sg < 0 ? (uniform ? 1 : 2) : (uniform ? 3 : 4);
     }
-    atomicAdd(&counts[(size_t)tiz * 5 + cls], 1ull);
+    atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + cls], 1ull);
+    // per-point work of the tile programs that are evaluated in full / on the shell only
+    const unsigned long long wk = (unsigned long long)twork[t];
+    if (cls == 0) atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 5], wk);
+    else if (cls == 2 || cls == 4) atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 6], wk);
 }
 
 // Block-cooperative compaction of the program for one tile into shared memory (s_prog), using the

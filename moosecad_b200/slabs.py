@@ -69,6 +69,29 @@ def layer_costs(ctx, obj, resolution):
     return cost
 
 
+def combine_stats(per_slab):
+    """Statistics of the whole mesh from the per-slab ones (each a dict with "ntets_stage", "stats",
+    "aspect_ratio", "inverted" as Mesh.stats() returns them): counters add up, the aspect-ratio
+    range is the hull."""
+    out = {"ntets_stage": [0, 0, 0], "stats": [0] * 7, "aspect_ratio": [1.0, 0.0], "inverted": 0}
+    for st in per_slab:
+        out["ntets_stage"] = [a + b for a, b in zip(out["ntets_stage"], st["ntets_stage"])]
+        out["stats"] = [a + b for a, b in zip(out["stats"], st["stats"])]
+        out["aspect_ratio"] = [min(out["aspect_ratio"][0], st["aspect_ratio"][0]),
+                               max(out["aspect_ratio"][1], st["aspect_ratio"][1])]
+        out["inverted"] += st["inverted"]
+    return out
+
+
+def mesh_stats(handle):
+    """The additive part of Mesh.stats() for a raw mc_mesh handle."""
+    lib = _lib.lib()
+    dim, stage, st = (C.c_uint64 * 3)(), (C.c_uint64 * 3)(), (C.c_uint64 * 7)()
+    ar, inv = (C.c_double * 2)(), C.c_uint64()
+    _lib.check(lib.mc_mesh_stats(handle, dim, stage, st, ar, C.byref(inv)))
+    return {"dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar), "inverted": inv.value}
+
+
 def bases_from_counts(all_counts, rank):
     """Exclusive scan over ranks of (n_vertices, n_tets)."""
     vb = sum(int(c[0]) for c in all_counts[:rank])
@@ -76,41 +99,103 @@ def bases_from_counts(all_counts, rank):
     return vb, tb
 
 
-def exchange_counts(n_vertices, n_tets, group=None, device="cpu"):
-    """all-gather of two int64 per rank; returns a list of (n_vertices, n_tets)."""
+_side_streams = {}
+
+
+def _side_stream(device):
+    """A second CUDA stream per device for the small host-synchronous collectives, so that they do
+    not wait for (or hold up) the kernels queued on the meshing stream."""
+    import torch
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def exchange_counts(n_vertices, n_tets, group=None, device="cpu", side_stream=False, extra=()):
+    """all-gather of a few int64 per rank; returns a list of (n_vertices, n_tets, *extra) per rank.
+    With side_stream=True (CUDA devices) the collective runs on its own stream: the counts are
+    host values, nothing on the meshing stream has to finish first."""
+    import contextlib
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    mine = torch.tensor([int(n_vertices), int(n_tets)], dtype=torch.int64, device=device)
-    out = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(out, mine, group=group)
-    return [(int(t[0]), int(t[1])) for t in out]
+    on_cuda = str(device).startswith("cuda")
+    cm = torch.cuda.stream(_side_stream(device)) if (side_stream and on_cuda) else contextlib.nullcontext()
+    with cm:
+        vals = [int(n_vertices), int(n_tets)] + [int(x) for x in extra]
+        mine = torch.tensor(vals, dtype=torch.int64, device=device)
+        out = [torch.zeros(len(vals), dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        return [tuple(int(x) for x in t.tolist()) for t in out]
 
 
-def exchange_plane_tables(send_table, recv_table, rank, world, group=None, active=None):
+def exchange_plane_tables(send_table, recv_table, rank, world, group=None, active=None, send_coords=None,
+                          recv_coords=None):
     """Rank r sends its upper-plane id table to r + 1 and receives r - 1's.  `send_table` /
     `recv_table` are int64 tensors (or None at the ends).  `active[r]` tells whether rank r
-    owns any cell layer; empty ranks are skipped by relaying nothing."""
+    owns any cell layer; empty ranks are skipped by relaying nothing.  `send_coords` /
+    `recv_coords` (float64, optional, possibly empty) carry the coordinates of the sender's top
+    tile layer in the same batch."""
     import torch.distributed as dist
     ops = []
     if send_table is not None and rank + 1 < world:
         ops.append(dist.P2POp(dist.isend, send_table, rank + 1, group))
+        if send_coords is not None and send_coords.numel():
+            ops.append(dist.P2POp(dist.isend, send_coords, rank + 1, group))
     if recv_table is not None and rank > 0:
         ops.append(dist.P2POp(dist.irecv, recv_table, rank - 1, group))
+        if recv_coords is not None and recv_coords.numel():
+            ops.append(dist.P2POp(dist.irecv, recv_coords, rank - 1, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
 
-def tile_layer_classes(ctx, obj, resolution):
-    """Tile counts per tile layer and cost class (C ABI mc_tile_layer_classes): (n_tile_layers, 5)."""
+def tile_layer_classes(ctx, obj, resolution, layer_begin=0, layer_end=None):
+    """Tile counts (and work sums) per tile layer and cost class (C ABI mc_tile_layer_classes):
+    (n_tile_layers, 7); only the rows [layer_begin, layer_end) are computed, the rest are zero."""
     import numpy as np
     dim = lattice_dim(obj.bbox(), float(resolution))
     n = (dim[2] + 1 + 15) // 16
-    counts = np.zeros((n, 5), dtype=np.uint64)
+    counts = np.zeros((n, _lib.MC_TILE_CLASS_STRIDE), dtype=np.uint64)
+    end = n if layer_end is None else int(layer_end)
     _lib.check(_lib.lib().mc_tile_layer_classes(ctx.handle, obj.backend.handle, obj.node, float(resolution),
-                                                counts.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+                                                int(layer_begin), end, counts.ctypes.data_as(C.POINTER(C.c_uint64)), n))
     return counts
+
+
+def class_weights():
+    w = (C.c_double * _lib.MC_TILE_CLASS_STRIDE)()
+    _lib.lib().mc_slab_class_weights(w)
+    return list(w)
+
+
+def costs_from_classes(counts, nz):
+    """Relative cost of every CELL layer from the per-tile-layer class table (the same arithmetic
+    as mc_estimate_layer_costs)."""
+    w = class_weights()
+    per_tile_layer = [sum(w[q] * float(row[q]) for q in range(len(w))) for row in counts]
+    return [per_tile_layer[z // 16] / 16.0 for z in range(nz)]
+
+
+def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=None, host_group=None):
+    """Load estimate with the interval pass itself sharded: every rank classifies 1/world of the tile
+    layers, one all-reduce (SUM) of the small class table makes it whole on every rank."""
+    import torch
+    import torch.distributed as dist
+    dim = lattice_dim(obj.bbox(), float(resolution))
+    n = (dim[2] + 1 + 15) // 16
+    k0, k1 = partition(n, world)[rank]
+    counts = tile_layer_classes(ctx, obj, resolution, k0, k1)
+    t = torch.from_numpy(counts.astype("int64"))
+    if host_group is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=host_group)   # host values over a host (gloo) group
+    else:
+        if device is not None and str(device) != "cpu":
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return costs_from_classes(t.cpu().numpy(), dim[2])
 
 
 class SlabMesher:
@@ -121,26 +206,45 @@ class SlabMesher:
     """
 
     def __init__(self, ctx, obj, resolution, relative_error, rank, world, group=None, device=None, flags=0,
-                 balanced=True):
+                 balanced=True, host_group=None):
+        """group: the device (NCCL) group the plane tables travel over.  host_group: optional host
+        (gloo) group for the two tiny host-valued exchanges (class table, counts); without it they
+        use `group` too, which on NCCL queues them behind the kernels already launched."""
         self.ctx, self.obj = ctx, obj
         self.res, self.err = float(resolution), float(relative_error)
         self.rank, self.world, self.group = int(rank), int(world), group
+        self.host_group = host_group
         self.device = device
         self.flags = flags
         self.dim = lattice_dim(obj.bbox(), self.res)
+        self.host_ms = {}   # wall time of the host-visible phases of the last run (diagnostics)
+        import time
+        t0 = time.perf_counter()
         if self.world > 1 and balanced:
             # the estimate is deterministic, every rank derives the same partition
-            self.slabs = partition_balanced(layer_costs(ctx, obj, self.res).tolist(), self.world)
+            self.slabs = partition_balanced(layer_costs_sharded(ctx, obj, self.res, self.rank, self.world, group, device,
+                                                                host_group),
+                                            self.world)
         else:
             self.slabs = partition(self.dim[2], self.world)
+        self.host_ms["partition"] = (time.perf_counter() - t0) * 1e3
         if any(z1 == z0 for z0, z1 in self.slabs):
             raise ValueError("fewer cell layers than ranks")
         self.all_counts = None
         self.vertex_base = self.tet_base = 0
 
     def run(self):
+        import time
         import torch
         lib = _lib.lib()
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            t1 = time.perf_counter()
+            self.host_ms[name] = (t1 - t0) * 1e3
+            t0 = t1
+
         z0, z1 = self.slabs[self.rank]
         slab = _lib.mc_slab(z0, z1)
         opts = _lib.mc_options(C.sizeof(_lib.mc_options), self.flags, 0, 0)
@@ -148,14 +252,27 @@ class SlabMesher:
         _lib.check(lib.mc_tessellate_begin(self.ctx.handle, self.obj.backend.handle, self.obj.node, self.res, self.err,
                                            C.byref(slab), C.byref(opts), C.byref(out)))
         try:
+            lap("begin")
             counts = (C.c_uint64 * 6)()
             _lib.check(lib.mc_mesh_counts(out, counts))
+            top_first, top_count = C.c_uint64(), C.c_uint64()
+            _lib.check(lib.mc_mesh_upper_layer_vertices(out, C.byref(top_first), C.byref(top_count)))
+            # coordinates + bisection do not need the global bases: keep the device busy while the
+            # counts travel
+            _lib.check(lib.mc_tessellate_emit_vertices_local(out))
+            extra = (top_first.value, top_count.value)
             if self.world > 1:
-                self.all_counts = exchange_counts(counts[0], counts[1], self.group, self.device)
+                if self.host_group is not None:
+                    self.all_counts = exchange_counts(counts[0], counts[1], self.host_group, "cpu", extra=extra)
+                else:
+                    self.all_counts = exchange_counts(counts[0], counts[1], self.group, self.device, side_stream=True,
+                                                      extra=extra)
             else:
-                self.all_counts = [(counts[0], counts[1])]
+                self.all_counts = [(counts[0], counts[1]) + extra]
             self.vertex_base, self.tet_base = bases_from_counts(self.all_counts, self.rank)
+            lap("exchange_counts")
             _lib.check(lib.mc_tessellate_emit_vertices(out, self.vertex_base))
+            lap("emit_vertices_launch")
             lower = None
             if self.world > 1:
                 n = (self.dim[0] + 1) * (self.dim[1] + 1)
@@ -163,13 +280,28 @@ class SlabMesher:
                 if self.rank + 1 < self.world:
                     send = torch.empty(n, dtype=torch.int64, device=self.device)
                     _lib.check(lib.mc_mesh_copy_upper_plane_table(out, C.c_void_p(send.data_ptr())))
+                send_xyz = recv_xyz = None
+                if send is not None:
+                    # coordinates of the top tile layer: the rank above evaluates the quality of the
+                    # trimmed tets that touch the shared plane with them
+                    send_xyz = torch.empty(3 * top_count.value, dtype=torch.float64, device=self.device)
+                    if top_count.value:
+                        _lib.check(lib.mc_mesh_copy_upper_layer_coords(out, C.c_void_p(send_xyz.data_ptr())))
                 if self.rank > 0:
                     recv = torch.empty(n, dtype=torch.int64, device=self.device)
-                exchange_plane_tables(send, recv, self.rank, self.world, self.group)
+                    below = self.all_counts[self.rank - 1]
+                    recv_xyz = torch.empty(3 * below[3], dtype=torch.float64, device=self.device)
+                exchange_plane_tables(send, recv, self.rank, self.world, self.group, send_coords=send_xyz,
+                                      recv_coords=recv_xyz)
                 if recv is not None:
                     lower = C.c_void_p(recv.data_ptr())
-                self._keep = (send, recv)
+                    vb_below, _ = bases_from_counts(self.all_counts, self.rank - 1)
+                    _lib.check(lib.mc_tessellate_set_lower_coords(out, C.c_void_p(recv_xyz.data_ptr()) if below[3] else None,
+                                                                  vb_below + below[2], below[3]))
+                self._keep = (send, recv, send_xyz, recv_xyz)
+            lap("exchange_plane_launch")
             rc = lib.mc_tessellate_emit_tets(out, self.tet_base, lower)
+            lap("emit_tets")
             if rc not in (_lib.MC_OK, _lib.MC_ERR_DIVERGED):
                 _lib.check(rc)
         except Exception:
@@ -178,7 +310,7 @@ class SlabMesher:
         return out
 
 
-def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0):
+def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0, return_stats=False):
     """Mesh the lattice as `n_slabs` z-slabs one after the other on ONE device and merge the
     results on the host (global vertex ids).  Exercises exactly the phases a multi-GPU run
     goes through (counts -> bases -> vertices -> plane table -> tets); also a way to mesh a
@@ -200,10 +332,17 @@ def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, f
             _lib.check(lib.mc_mesh_counts(out, c))
             counts.append((c[0], c[1]))
         lower = None
-        coords, tets = [], []
+        coords, tets, stats = [], [], []
         for r, h in enumerate(handles):
             vb, tb = bases_from_counts(counts, r)
             _lib.check(lib.mc_tessellate_emit_vertices(h, vb))
+            if r > 0:
+                # coordinates of the slab below's top tile layer, straight from its device buffer
+                first, cnt, xyz = C.c_uint64(), C.c_uint64(), C.c_void_p()
+                _lib.check(lib.mc_mesh_upper_layer_vertices(handles[r - 1], C.byref(first), C.byref(cnt)))
+                _lib.check(lib.mc_mesh_upper_layer_coords(handles[r - 1], C.byref(xyz)))
+                vb_below, _ = bases_from_counts(counts, r - 1)
+                _lib.check(lib.mc_tessellate_set_lower_coords(h, xyz, vb_below + first.value, cnt.value))
             rc = lib.mc_tessellate_emit_tets(h, tb, lower)
             if rc not in (_lib.MC_OK, _lib.MC_ERR_DIVERGED):
                 _lib.check(rc)
@@ -216,7 +355,10 @@ def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, f
             _lib.check(lib.mc_mesh_copy_to_host(h, cbuf.ctypes.data_as(C.c_void_p), tbuf.ctypes.data_as(C.c_void_p), 8))
             coords.append(cbuf)
             tets.append(tbuf)
+            stats.append(mesh_stats(h))
     finally:
         for h in handles:
             lib.mc_mesh_free(h)
+    if return_stats:
+        return np.concatenate(coords), np.concatenate(tets), combine_stats(stats)
     return np.concatenate(coords), np.concatenate(tets)

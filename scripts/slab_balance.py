@@ -66,12 +66,12 @@ def main():
         torch.cuda.synchronize()
         print(f"layer cost estimate: {(time.perf_counter() - t0) * 1e3:.2f} ms")
         import numpy as np
-        classes = slabs.tile_layer_classes(ctx, root, res).astype(np.float64)   # (tile layers, 5)
+        classes = slabs.tile_layer_classes(ctx, root, res).astype(np.float64)   # (tile layers, 7)
         rows, obs = [], []
 
         def slab_classes(z0, z1):
             # cell layers [z0, z1) -> fraction of every 16-layer tile layer
-            acc = np.zeros(5)
+            acc = np.zeros(classes.shape[1])
             for k in range(classes.shape[0]):
                 lo, hi = max(z0, 16 * k), min(z1, 16 * k + 16)
                 if hi > lo:
@@ -109,9 +109,9 @@ def main():
         os.makedirs("gpurun_out", exist_ok=True)
         np.savez("gpurun_out/slab_balance_rows.npz", A=A, y=y)
         w, *_ = np.linalg.lstsq(A, y, rcond=None)
-        print("least squares: ms per tile by class [unproven, neg skipped, neg shell, pos skipped, pos shell], per-slab constant")
+        print("least squares: ms per [unproven, neg skipped, neg shell, pos skipped, pos shell] tile, per unit of "
+              "[unproven, shell] work, per-slab constant")
         print("   ", " ".join(f"{x:.3e}" for x in w))
-        print("    relative to unproven:", " ".join(f"{x / w[0]:.3f}" for x in w[:5]), f"constant = {w[5] / w[0]:.0f} tiles")
         print(f"    residual rms {np.sqrt(np.mean((A @ w - y) ** 2)):.2f} ms over {len(y)} slabs")
 
 

@@ -26,6 +26,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    host_group = dist.new_group(backend="gloo")
     lib = _lib.lib()
     stream = torch.cuda.Stream(device=dev)
     ok = True
@@ -37,16 +38,20 @@ def main():
         cases.append(("csg", scenes.synthetic_csg(g, 20, seed=3), 1.0 / 90))
         for name, obj, res in cases:
             obj.backend.set_parameters(0.1, 1.0)
-            sm = slabs.SlabMesher(ctx, obj, res, 0.2, rank, world, None, dev)
+            # the sphere takes the NCCL-only path, the CSG scene sends its host-valued bookkeeping
+            # (class table, counts) over the gloo host group like bench.py does
+            sm = slabs.SlabMesher(ctx, obj, res, 0.2, rank, world, None, dev,
+                                  host_group=host_group if name == "csg" else None)
             h = sm.run()
             cnt = (C.c_uint64 * 6)()
             lib.mc_mesh_counts(h, cnt)
             coords = np.empty((cnt[0], 3), dtype=np.float64)
             tets = np.empty((cnt[1], 4), dtype=np.uint64)
             _lib.check(lib.mc_mesh_copy_to_host(h, coords.ctypes.data_as(C.c_void_p), tets.ctypes.data_as(C.c_void_p), 8))
+            st = slabs.mesh_stats(h)
             lib.mc_mesh_free(h)
             gathered = [None] * world if rank == 0 else None
-            dist.gather_object((coords, tets, sm.vertex_base, sm.tet_base), gathered, dst=0)
+            dist.gather_object((coords, tets, sm.vertex_base, sm.tet_base, st), gathered, dst=0)
             if rank == 0:
                 gathered.sort(key=lambda t: t[2])
                 allc = np.concatenate([t[0] for t in gathered])
@@ -55,6 +60,9 @@ def main():
                 try:
                     canon.assert_same_mesh(canon.canonical(whole.vertices(), whole.elems()), canon.canonical(allc, allt))
                     assert np.unique(allt).size == len(allc)
+                    ws, ss = whole.stats(), slabs.combine_stats([t[4] for t in gathered])
+                    for key in ("ntets_stage", "stats", "aspect_ratio", "inverted"):
+                        assert ss[key] == ws[key], (key, ss[key], ws[key])
                     print(f"SLAB_PARITY_OK {name} world={world} verts={len(allc)} tets={len(allt)}", flush=True)
                 except AssertionError as e:
                     ok = False

@@ -46,7 +46,14 @@ def _gloo_worker(rank, world, port, q):
         send = torch.arange(n, dtype=torch.int64) + 1000 * rank if rank + 1 < world else None
         recv = torch.zeros(n, dtype=torch.int64) if rank > 0 else None
         slabs.exchange_plane_tables(send, recv, rank, world, None)
-        q.put((rank, counts, vb, tb, None if recv is None else recv.tolist()))
+        # second round: counts with the top-layer extras, plane table + coordinate slice in one batch
+        counts2 = slabs.exchange_counts(100 + rank, 1000 * (rank + 1), None, "cpu", extra=(40 + rank, 2 + rank))
+        send_xyz = torch.arange(3 * (2 + rank), dtype=torch.float64) + 0.5 if rank + 1 < world else None
+        recv_xyz = torch.zeros(3 * counts2[rank - 1][3], dtype=torch.float64) if rank > 0 else None
+        recv2 = torch.zeros(n, dtype=torch.int64) if rank > 0 else None
+        slabs.exchange_plane_tables(send, recv2, rank, world, None, send_coords=send_xyz, recv_coords=recv_xyz)
+        q.put((rank, counts, vb, tb, None if recv is None else recv.tolist(), counts2,
+               None if recv_xyz is None else recv_xyz.tolist(), None if recv2 is None else recv2.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -66,6 +73,9 @@ def test_count_scan_and_plane_exchange_gloo_world2():
     assert res[0][1] == res[1][1] == [(100, 1000), (101, 2000)]
     assert (res[0][2], res[0][3]) == (0, 0) and (res[1][2], res[1][3]) == (100, 1000)
     assert res[0][4] is None and res[1][4] == list(range(7))   # rank 1 received rank 0's table
+    assert res[0][5] == res[1][5] == [(100, 1000, 40, 2), (101, 2000, 41, 3)]
+    assert res[0][6] is None and res[1][6] == [0.5 + i for i in range(6)]   # ... and its coordinate slice
+    assert res[1][7] == list(range(7))
 
 
 @pytest.mark.gpu
@@ -81,7 +91,12 @@ def test_slabs_match_single_slab(scene, n_slabs, ctx):
         obj, res = scenes.synthetic_csg(g, 12, seed=5), 1.0 / 45
     obj.backend.set_parameters(0.1, 1.0)
     whole = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx).tessellate()
-    coords, tets = slabs.tessellate_slabs_one_device(ctx, obj, res, 0.2, n_slabs)
+    coords, tets, stats = slabs.tessellate_slabs_one_device(ctx, obj, res, 0.2, n_slabs, return_stats=True)
+    # check_for_inverted_tets over the slabs = over the whole mesh: every tet is evaluated exactly
+    # once, the ones touching a shared plane with the coordinates received from the slab below
+    ws = whole.stats()
+    for key in ("ntets_stage", "stats", "aspect_ratio", "inverted"):
+        assert stats[key] == ws[key], key
     a = canon.canonical(whole.vertices(), whole.elems())
     b = canon.canonical(coords, tets)
     canon.assert_same_mesh(a, b)
@@ -100,3 +115,43 @@ def test_partition_balanced():
         assert all(b > a for a, b in p)
     assert slabs.partition_balanced([0.0] * 10, 2) == [(0, 5), (5, 10)]
     assert slabs.partition_balanced([1.0] * 3, 1) == [(0, 3)]
+
+
+def test_costs_from_classes_arithmetic():
+    """Host side of the sharded load estimate: per-cell-layer cost = weights . class table row / 16."""
+    w = slabs.class_weights()
+    assert len(w) == 7 and all(x >= 0.0 for x in w) and w[5] > 0.0
+    table = np.zeros((3, 7), dtype=np.uint64)
+    table[0, 0], table[0, 5] = 10, 50000
+    table[1, 1] = 7
+    table[2, 3] = 100
+    costs = slabs.costs_from_classes(table, 40)
+    assert len(costs) == 40
+    assert costs[0] == costs[15] == (w[0] * 10 + w[5] * 50000) / 16.0
+    assert costs[16] == costs[31] == w[1] * 7 / 16.0
+    assert costs[32] == costs[39] == w[3] * 100 / 16.0
+
+
+@pytest.mark.gpu
+def test_sharded_load_estimate_matches_whole(ctx):
+    """mc_tile_layer_classes over ranges of tile layers sums to the table of one full pass, and the
+    costs derived from it equal mc_estimate_layer_costs."""
+    import moosecad_b200 as mc
+    from moosecad_b200 import scenes
+    g = mc.Geom()
+    root = scenes.synthetic_csg(g, 16)
+    res = 1.0 / 96
+    whole = slabs.tile_layer_classes(ctx, root, res)
+    n = whole.shape[0]
+    assert whole[:, :5].sum() == n * 7 * 7            # 97 points per axis -> 7 tiles
+    assert whole[:, 1:5].sum() > 0 and whole[:, 0].sum() > 0
+    for world in (2, 3, n):
+        acc = np.zeros_like(whole)
+        for k0, k1 in slabs.partition(n, world):
+            part = slabs.tile_layer_classes(ctx, root, res, k0, k1)
+            assert not part[:k0].any() and not part[k1:].any()
+            acc += part
+        assert np.array_equal(acc, whole)
+    dim = slabs.lattice_dim(root.bbox(), res)
+    direct = slabs.layer_costs(ctx, root, res)
+    assert np.allclose(direct, slabs.costs_from_classes(whole, dim[2]), rtol=1e-12, atol=0.0)
