@@ -1030,8 +1030,18 @@ constexpr int TE_H = (int)TS + 1;
 constexpr int TE_NP = TE_H * TE_H * TE_H;
 template <typename IndexT>
 constexpr size_t tet_emit_smem_bytes() {
-    return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + (size_t)TE_NP /*warped*/ + 15 +
-           (size_t)TILE_POINTS * 2 * 3 /*ci, off, list*/;
+    return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + 15 +
+           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, qoff*/;
+}
+
+// one output tet = one (u32 ids) or two (u64 ids) 16-byte stores
+__device__ __forceinline__ void store_tet(uint32_t* tets, uint64_t o, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    reinterpret_cast<uint4*>(tets)[o] = make_uint4(a, b, c, d);
+}
+__device__ __forceinline__ void store_tet(unsigned long long* tets, uint64_t o, unsigned long long a, unsigned long long b,
+                                          unsigned long long c, unsigned long long d) {
+    reinterpret_cast<ulonglong2*>(tets)[2 * o] = make_ulonglong2(a, b);
+    reinterpret_cast<ulonglong2*>(tets)[2 * o + 1] = make_ulonglong2(c, d);
 }
 
 template <typename IndexT, bool QUALITY>
@@ -1049,37 +1059,87 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     if (zhi <= zlo) return;
     IndexT* s_gid = reinterpret_cast<IndexT*>(te_smem);
     uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_gid + TE_NP);
-    uint8_t* s_wrp = reinterpret_cast<uint8_t*>(s_mask + TE_NP);
-    uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_wrp + TE_NP) + 15) & ~(uintptr_t)15);
+    uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_mask + TE_NP) + 15) & ~(uintptr_t)15);
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
+    uint16_t* s_qoff = s_list + TILE_POINTS; // first quality-list slot of the cell, relative to the tile
+    __shared__ unsigned long long s_qbase;
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[blockIdx.x];
     if (threadIdx.x == 0) s_n = 0u;
-    // 1. vertex ids / masks of the tile's corners
+    // 1. vertex ids / masks of the tile's corners.  The (TS+1)^3 points lie in at most 8 tiles:
+    //    their class, id base and owned box are staged once, so that a point costs no dependent
+    //    global load (interior tiles: arithmetic; surface tiles: its mask and local index).
+    __shared__ TileBox s_tb[8];
+    __shared__ long long s_tbase[8];
+    __shared__ uint8_t s_tvu[8];
+    if (threadIdx.x < 8) {
+        const uint32_t q = threadIdx.x;
+        const uint32_t X = X0 + ((q & 1u) ? TS : 0u), Y = Y0 + ((q & 2u) ? TS : 0u), Z = Z0 + ((q & 4u) ? TS : 0u);
+        uint8_t vu = VU_POS;
+        if (X < L.NX && Y < L.NY && Z <= L.pz1) {
+            const uint32_t t = tile_of(S.g, X, Y, Z);
+            vu = S.vuni[t];
+            s_tb[q] = tile_box(S, t);
+            s_tbase[q] = S.vertex_base + (long long)S.tvbase[t];
+        }
+        s_tvu[q] = vu;
+    }
+    __syncthreads();
     for (int idx = (int)threadIdx.x; idx < TE_NP; idx += TILE_THREADS) {
-        const uint32_t X = X0 + idx % TE_H, Y = Y0 + (idx / TE_H) % TE_H, Z = Z0 + idx / (TE_H * TE_H);
+        const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
+        const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+        const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
         IndexT gid = 0;
         uint16_t mask = 0;
-        if (X < L.NX && Y < L.NY && Z <= L.pz1 && S.vuni[tile_of(S.g, X, Y, Z)] != VU_POS)
-            gid = (IndexT)vertex_gid(S, X, Y, Z, mask);
+        const uint8_t vu = s_tvu[q];
+        if (X < L.NX && Y < L.NY && Z <= L.pz1 && vu != VU_POS) {
+            if (S.lower_table != nullptr && Z == S.c0) {
+                const unsigned long long e = S.lower_table[(size_t)Y * L.NX + X];
+                mask = (uint16_t)(e & 0xffffull);
+                gid = (IndexT)(e >> 16);
+            } else if (vu == VU_NEG) {
+                const TileBox& b = s_tb[q];
+                mask = VM_USED;
+                gid = (IndexT)(s_tbase[q] + (long long)(((Z - b.zlo) * b.nyt + (Y - b.Y0)) * b.nxt + (X - b.X0)));
+            } else {
+                const size_t pi = pidx(L, X, Y, Z);
+                mask = S.vmask[pi];
+                gid = (IndexT)(s_tbase[q] + (long long)S.vloc[pi]);
+            }
+        }
         s_gid[idx] = gid; s_mask[idx] = mask;
     }
-    (void)s_wrp;
-    // 2. per-cell info + offsets
-    uint32_t run = 0;
-    for (int r = 0; r < TILE_ROUNDS; ++r) {
-        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
-        const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
-        const uint16_t ci = owned ? S.cinfo[cidx(S, cx, cy, cz)] : (uint16_t)0;
-        const uint32_t count = ci_count(ci);
-        uint32_t ttot;
-        const uint32_t tex = block_exscan(count, &ttot, s_scan);
-        s_ci[j] = ci;
-        s_off[j] = (uint16_t)(run + tex);
-        if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
-        run += ttot;
+    // 2. per-cell info + offsets: every thread takes one x-row of 16 cells (consecutive in the
+    //    output order), one block scan of the row totals gives the offsets of the output tets
+    //    (low half) and of the tets listed for the per-tet quality pass (high half; <= 61440 each)
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
+        const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
+        const uint16_t* __restrict__ row = S.cinfo + (row_owned ? cidx(S, X0, cy, cz) : 0);
+        const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
+        uint32_t acc = 0;
+        uint32_t pre[TS];
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) {
+            const uint16_t ci = i < nx_row ? row[i] : (uint16_t)0;
+            const uint32_t count = ci_count(ci);
+            const bool listed = QUALITY && count && (!(ci & CI_FULL) || (ci & CI_FULL_ZERO_CORNER));
+            s_ci[threadIdx.x * TS + i] = ci;
+            pre[i] = acc;
+            acc += count | (listed ? count << 16 : 0u);
+            if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)(threadIdx.x * TS + i);
+        }
+        uint32_t tot;
+        const uint32_t ex = block_exscan(acc, &tot, s_scan);
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) {
+            const uint32_t v = ex + pre[i];
+            s_off[threadIdx.x * TS + i] = (uint16_t)(v & 0xffffu);
+            if (QUALITY) s_qoff[threadIdx.x * TS + i] = (uint16_t)(v >> 16);
+        }
+        if (QUALITY && threadIdx.x == 0) s_qbase = (tot >> 16) ? atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)(tot >> 16)) : 0ull;
     }
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
@@ -1097,18 +1157,14 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             id[k] = s_gid[(int)((Z - Z0) * TE_H + (Y - Y0)) * TE_H + (int)(X - X0)];
         }
         const uint64_t o = tb + s_off[j];
-        IndexT* dst = tets + 4 * o;
 #pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            dst[4 * t + 0] = flip ? id[T[t][1]] : id[T[t][0]];
-            dst[4 * t + 1] = flip ? id[T[t][0]] : id[T[t][1]];
-            dst[4 * t + 2] = id[T[t][2]];
-            dst[4 * t + 3] = id[T[t][3]];
-        }
+        for (int t = 0; t < 5; ++t)
+            store_tet(tets, o + (uint64_t)t, flip ? id[T[t][1]] : id[T[t][0]], flip ? id[T[t][0]] : id[T[t][1]],
+                      id[T[t][2]], id[T[t][3]]);
         // zero-cornered untouched cells are not congruent to plain lattice tets: listed for the
         // per-tet quality pass (the plain ones are handled per class by k_surface_tile_quality)
         if (QUALITY && (ci & CI_FULL_ZERO_CORNER)) {
-            const unsigned long long at = atomicAdd(&counters[CN_QLIST_FILL], 5ull);
+            const unsigned long long at = s_qbase + s_qoff[j];
 #pragma unroll
             for (int t = 0; t < 5; ++t) qlist[at + t] = o + (uint64_t)t;
         }
@@ -1121,8 +1177,9 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         const uint16_t ci = s_ci[j];
         const uint32_t nt = ci_tet_n(ci, t);
         if (nt == 0u) continue;
-        uint64_t o = tb + s_off[j];
-        for (int u = 0; u < t; ++u) o += ci_tet_n(ci, u);
+        uint32_t before = 0;
+        for (int u = 0; u < t; ++u) before += ci_tet_n(ci, u);
+        uint64_t o = tb + s_off[j] + before;
         const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
         TetNodes tn;
         load_tet(L, c, t, tn);
@@ -1131,8 +1188,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         int li[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);
-        unsigned long long at = 0ull;
-        if (QUALITY) at = atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)to.n);
+        const unsigned long long at = QUALITY ? s_qbase + s_qoff[j] + before : 0ull;
         for (int q = 0; q < to.n; ++q) {
             IndexT id[4];
 #pragma unroll
@@ -1150,8 +1206,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
                     id[m] = (IndexT)cut_vertex_id((long long)s_gid[lo], s_mask[lo], d);
                 }
             }
-            IndexT* dst = tets + 4 * o;
-            dst[0] = id[0]; dst[1] = id[1]; dst[2] = id[2]; dst[3] = id[3];
+            store_tet(tets, o, id[0], id[1], id[2], id[3]);
             if (QUALITY) qlist[at + (unsigned)q] = o;
             ++o;
         }

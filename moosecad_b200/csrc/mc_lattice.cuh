@@ -63,13 +63,13 @@ static __constant__ int8_t C_DIR[18][3] = {
     {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {-1, 0, -1}, {1, 0, -1}, {0, -1, -1}, {0, 1, -1}};
 
 // direction (dx,dy,dz) in {-1,0,1}^3 -> index into C_DIR, or -1 (not a lattice edge direction)
+// 27-entry table indexed by (dx+1) + 3*(dy+1) + 9*(dz+1)
+static __constant__ int8_t C_DIR_INDEX[27] = {
+    /* dz=-1 */ -1, 16, -1, 14, 11, 15, -1, 17, -1,
+    /* dz= 0 */ 12, 10, 13, 9, -1, 0, 4, 1, 3,
+    /* dz=+1 */ -1, 8, -1, 6, 2, 5, -1, 7, -1};
 __device__ __forceinline__ int dir_index(int dx, int dy, int dz) {
-    // 27-entry table indexed by (dx+1) + 3*(dy+1) + 9*(dz+1)
-    const int8_t T[27] = {
-        /* dz=-1 */ -1, 16, -1, 14, 11, 15, -1, 17, -1,
-        /* dz= 0 */ 12, 10, 13, 9, -1, 0, 4, 1, 3,
-        /* dz=+1 */ -1, 8, -1, 6, 2, 5, -1, 7, -1};
-    return T[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
+    return C_DIR_INDEX[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
 }
 
 struct Cell {
