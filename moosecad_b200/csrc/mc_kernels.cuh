@@ -168,6 +168,36 @@ static __global__ void k_eval_points(const uint64_t* __restrict__ prog, const do
     if (i < n) out[i] = v;
 }
 
+// Stage a cube of H^3 lattice points (origin = tile origin + OFF per axis) through a functor:
+// f(idx, inside, phi, wcode) for every idx in [0, H^3).  Four points per thread are in flight at
+// once: the loads go to clamped (always valid) addresses, so that they are unconditional and can
+// be issued back to back — the staging loops are latency bound otherwise.
+template <int H, int OFF, bool WCODE, typename F>
+__device__ __forceinline__ void stage_points(const Lattice& L, uint32_t X0, uint32_t Y0, uint32_t Z0, F f) {
+    constexpr int N = H * H * H, B = 4;
+    for (int base = (int)threadIdx.x; base < N; base += B * TILE_THREADS) {
+        double v[B];
+        uint8_t wc[B];
+        bool in[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int idx = min(base + u * TILE_THREADS, N - 1);
+            const int64_t X = (int64_t)X0 + idx % H + OFF, Y = (int64_t)Y0 + (idx / H) % H + OFF, Z = (int64_t)Z0 + idx / (H * H) + OFF;
+            in[u] = X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1;
+            const uint32_t Xc = (uint32_t)min(max(X, (int64_t)0), (int64_t)L.NX - 1), Yc = (uint32_t)min(max(Y, (int64_t)0), (int64_t)L.NY - 1);
+            const uint32_t Zc = (uint32_t)min(max(Z, (int64_t)L.pz0), (int64_t)L.pz1);
+            const size_t pi = pidx(L, Xc, Yc, Zc);
+            v[u] = L.phi[pi];
+            wc[u] = WCODE ? L.wcode[pi] : (uint8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int idx = base + u * TILE_THREADS;
+            if (idx < N) f(idx, in[u], v[u], wc[u]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // per-tile sign summary of the raw field: TF_NEG (max < 0), TF_POS (min > 0)
 static __global__ void __launch_bounds__(TILE_THREADS)
@@ -248,6 +278,7 @@ static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long
 // one-point halo) are staged in shared memory; vertices with an edge that does not join two
 // vertices of the same strict sign are collected in a list and processed one per thread.
 constexpr int WT_STRIDE = 97;  // [count, 96 entries] per parity class
+constexpr int WP_STRIDE = 37;  // [count, <= 36 distinct (direction, orientation) pairs in first-visit order]
 constexpr int8_t SG_NEG = -1, SG_ZERO = 0, SG_POS = 1, SG_NONE = 2, SG_NAN = 3;
 
 static __global__ void __launch_bounds__(TILE_THREADS)
@@ -256,22 +287,22 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
     constexpr int H = (int)TS + 2;
     __shared__ int8_t s_sg[H * H * H];
     __shared__ unsigned long long s_tab[8 * WT_STRIDE];
+    __shared__ uint8_t s_pairs[8 * WP_STRIDE];
+    __shared__ uint32_t s_nan;
     __shared__ uint16_t s_list[TILE_POINTS];
     __shared__ uint32_t s_n;
     const Lattice& L = S.L;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (threadIdx.x == 0) s_n = 0u;
+    if (threadIdx.x == 0) { s_n = 0u; s_nan = 0u; }
     for (int i = (int)threadIdx.x; i < 8 * WT_STRIDE; i += TILE_THREADS) s_tab[i] = S.warp_table[i];
-    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
-        const int64_t X = (int64_t)X0 + idx % H - 1, Y = (int64_t)Y0 + (idx / H) % H - 1, Z = (int64_t)Z0 + idx / (H * H) - 1;
-        int8_t sg = SG_NONE;
-        if (X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1) {
-            const double v = L.phi[pidx(L, (uint32_t)X, (uint32_t)Y, (uint32_t)Z)];
-            sg = v > 0.0 ? SG_POS : (v < 0.0 ? SG_NEG : (v == 0.0 ? SG_ZERO : SG_NAN));
-        }
+    for (int i = (int)threadIdx.x; i < 8 * WP_STRIDE; i += TILE_THREADS) s_pairs[i] = (uint8_t)S.warp_table[8 * WT_STRIDE + i];
+    __syncthreads();
+    stage_points<H, -1, false>(L, X0, Y0, Z0, [&](int idx, bool in, double v, uint8_t) {
+        const int8_t sg = !in ? SG_NONE : (v > 0.0 ? SG_POS : (v < 0.0 ? SG_NEG : (v == 0.0 ? SG_ZERO : SG_NAN)));
         s_sg[idx] = sg;
-    }
+        if (sg == SG_NAN) s_nan = 1u;
+    });
     __syncthreads();
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
@@ -303,44 +334,65 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
         const int sv = s_sg[me];
         const double pv = L.phi[pidx(L, X, Y, Z)];
         const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
-        const unsigned long long* tab = s_tab + ((X & 1u) | ((Y & 1u) << 1) | ((Z & 1u) << 2)) * WT_STRIDE;
-        const uint32_t nvis = (uint32_t)tab[0];
-        unsigned long long seen = 0ull;
+        const uint32_t pclass = (X & 1u) | ((Y & 1u) << 1) | ((Z & 1u) << 2);
         bool has = false;
         double best = 0.0;
         uint32_t code = 0u;
-        for (uint32_t i = 1; i <= nvis; ++i) {
-            const unsigned long long e = tab[i];
-            // the cell must exist
-            if (((e & 1ull) && X == 0u) || (!(e & 1ull) && X >= L.nx) || ((e & 2ull) && Y == 0u) || (!(e & 2ull) && Y >= L.ny) ||
-                ((e & 4ull) && Z == 0u) || (!(e & 4ull) && Z >= L.nz)) continue;
-            const uint32_t d = (uint32_t)(e >> 3) & 31u, o = (uint32_t)(e >> 8) & 1u;
-            const uint32_t bit = d * 2u + o;
-            if ((seen >> bit) & 1ull) continue;
-            const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
-            if ((sv == SG_POS || sv == SG_NEG) && sw == sv) continue;  // both ends of one strict sign
-            bool kept = false;  // cut_lattice kept the tet iff a corner has value <= 0
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t off = (uint32_t)(e >> (9 + 6 * c)) & 63u;
-                const int cs = s_sg[me + (((int)((off >> 4) & 3u) - 1) * H + ((int)((off >> 2) & 3u) - 1)) * H + ((int)(off & 3u) - 1)];
-                kept = kept || cs == SG_NEG || cs == SG_ZERO;
-            }
-            if (!kept) continue;
-            seen |= 1ull << bit;
+        // one candidate: the edge to the neighbour in direction d, seen from this vertex as the
+        // first (o = 0) or second (o = 1) node of the tet edge
+        auto candidate = [&](uint32_t d, uint32_t o) {
             const uint32_t WX = X + C_DIR[d][0], WY = Y + C_DIR[d][1], WZ = Z + C_DIR[d][2];
             const double pw = L.phi[pidx(L, WX, WY, WZ)];
             const double alpha = o == 0u ? pv / (pv - pw) : pw / (pw - pv);
             const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
             double dd;
             if (o == 0u) {
-                if (!(alpha < 0.3)) continue;
+                if (!(alpha < 0.3)) return;
                 dd = alpha * sqrt((dx * dx + dy * dy) + dz * dz);
             } else {
-                if (!(alpha > 1.0 - 0.3)) continue;
+                if (!(alpha > 1.0 - 0.3)) return;
                 dd = (1.0 - alpha) * sqrt((dx * dx + dy * dy) + dz * dz);
             }
             if (!has || dd < best) { has = true; best = dd; code = 1u + 2u * d + o; }
+        };
+        if (!s_nan && X >= 1u && X < L.nx && Y >= 1u && Y < L.ny && Z >= 1u && Z < L.nz) {
+            // All 8 cells exist and (no NaN) an edge that does not join two vertices of one strict
+            // sign has an end with value <= 0, so every tet containing it was kept by cut_lattice:
+            // the visit order of the distinct (direction, orientation) pairs is a constant of the
+            // parity class.
+            const uint8_t* pr = s_pairs + pclass * WP_STRIDE;
+            const uint32_t np = pr[0];
+            for (uint32_t i = 1; i <= np; ++i) {
+                const uint32_t d = pr[i] >> 1, o = pr[i] & 1u;
+                const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
+                if ((sv == SG_POS || sv == SG_NEG) && sw == sv) continue;  // both ends of one strict sign
+                candidate(d, o);
+            }
+        } else {
+            const unsigned long long* tab = s_tab + pclass * WT_STRIDE;
+            const uint32_t nvis = (uint32_t)tab[0];
+            unsigned long long seen = 0ull;
+            for (uint32_t i = 1; i <= nvis; ++i) {
+                const unsigned long long e = tab[i];
+                // the cell must exist
+                if (((e & 1ull) && X == 0u) || (!(e & 1ull) && X >= L.nx) || ((e & 2ull) && Y == 0u) || (!(e & 2ull) && Y >= L.ny) ||
+                    ((e & 4ull) && Z == 0u) || (!(e & 4ull) && Z >= L.nz)) continue;
+                const uint32_t d = (uint32_t)(e >> 3) & 31u, o = (uint32_t)(e >> 8) & 1u;
+                const uint32_t bit = d * 2u + o;
+                if ((seen >> bit) & 1ull) continue;
+                const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
+                if ((sv == SG_POS || sv == SG_NEG) && sw == sv) continue;  // both ends of one strict sign
+                bool kept = false;  // cut_lattice kept the tet iff a corner has value <= 0
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = (uint32_t)(e >> (9 + 6 * c)) & 63u;
+                    const int cs = s_sg[me + (((int)((off >> 4) & 3u) - 1) * H + ((int)((off >> 2) & 3u) - 1)) * H + ((int)(off & 3u) - 1)];
+                    kept = kept || cs == SG_NEG || cs == SG_ZERO;
+                }
+                if (!kept) continue;
+                seen |= 1ull << bit;
+                candidate(d, o);
+            }
         }
         if (has) {
             L.wcode[pidx(L, X, Y, Z)] = (uint8_t)code;
@@ -362,7 +414,7 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
 // totals (low 32 bits: output tets, high 32 bits: kept lattice tets) count owned cells only.
 // Cells whose corners are all negative / all positive are settled from the staged classes;
 // the tets of the remaining (surface) cells are collected and classified one per thread.
-static __global__ void __launch_bounds__(TILE_THREADS)
+static __global__ void __launch_bounds__(TILE_THREADS, 3)
 k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long* __restrict__ tile_tot,
                  unsigned long long* __restrict__ counters) {
     __shared__ unsigned long long s_acc;
@@ -392,17 +444,10 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     __shared__ uint32_t s_ci[TILE_POINTS / 2]; // cinfo of the surface cells being assembled, by list slot
     __shared__ uint32_t s_n;
     if (threadIdx.x == 0) s_n = 0u;
-    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
-        const uint32_t X = X0 + idx % H, Y = Y0 + (idx / H) % H, Z = Z0 + idx / (H * H);
-        uint8_t cl = 0;
-        if (X < L.NX && Y < L.NY && Z <= L.pz1) {
-            const size_t pi = pidx(L, X, Y, Z);
-            const double raw = L.phi[pi];
-            const double w = (L.wcode[pi] & 0x7f) ? 0.0 : raw;
-            cl = (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0));
-        }
-        s_cls[idx] = cl;
-    }
+    stage_points<H, 0, true>(L, X0, Y0, Z0, [&](int idx, bool in, double raw, uint8_t wc) {
+        const double w = (wc & 0x7f) ? 0.0 : raw;
+        s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0)) : (uint8_t)0;
+    });
     __syncthreads();
     uint32_t my_out = 0, my_kept = 0, my_listed = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
@@ -578,17 +623,10 @@ k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
     // 0 none, 1 negative, 2 positive, 3 zero (not in the output), 4 zero used by some output tet
     constexpr int H = (int)TS + 2;
     __shared__ uint8_t s_cl[H * H * H];
-    for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
-        const int64_t X = (int64_t)b.X0 + idx % H - 1, Y = (int64_t)b.Y0 + (idx / H) % H - 1, Z = (int64_t)b.Z0 + idx / (H * H) - 1;
-        uint8_t cl = 0;
-        if (X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1) {
-            const size_t pi = pidx(L, (uint32_t)X, (uint32_t)Y, (uint32_t)Z);
-            const uint8_t wc = L.wcode[pi];
-            const double pv = (wc & 0x7f) ? 0.0 : L.phi[pi];
-            cl = pv < 0.0 ? 1 : (pv > 0.0 ? 2 : (pv == 0.0 ? ((wc & 0x80) ? 4 : 3) : 0));
-        }
-        s_cl[idx] = cl;
-    }
+    stage_points<H, -1, true>(L, b.X0, b.Y0, b.Z0, [&](int idx, bool in, double raw, uint8_t wc) {
+        const double pv = (wc & 0x7f) ? 0.0 : raw;
+        s_cl[idx] = !in ? (uint8_t)0 : (pv < 0.0 ? 1 : (pv > 0.0 ? 2 : (pv == 0.0 ? ((wc & 0x80) ? 4 : 3) : 0)));
+    });
     __syncthreads();
     unsigned long long mine = 0ull;
     for (int r = 0; r < TILE_ROUNDS; ++r) {

@@ -37,7 +37,7 @@ static void build_warp_table(std::vector<unsigned long long>& tab) {
     static const int EDGE[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
     static const int DIR[18][3] = {{1, 0, 0},  {0, 1, 0},  {0, 0, 1},  {1, 1, 0},   {-1, 1, 0}, {1, 0, 1},  {-1, 0, 1}, {0, 1, 1},  {0, -1, 1},
                                    {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {-1, 0, -1}, {1, 0, -1}, {0, -1, -1}, {0, 1, -1}};
-    tab.assign(8 * WT_STRIDE, 0ull);
+    tab.assign(8 * (WT_STRIDE + WP_STRIDE), 0ull);
     for (int pc = 0; pc < 8; ++pc) {
         const int par[3] = {pc & 1, (pc >> 1) & 1, (pc >> 2) & 1};
         int n = 0;
@@ -83,6 +83,19 @@ static void build_warp_table(std::vector<unsigned long long>& tab) {
                     }
                 }
         tab[pc * WT_STRIDE] = (unsigned long long)n;
+        // distinct (direction, orientation) pairs in the order of their first visit: the whole visit
+        // order of a vertex whose 8 cells all exist and whose candidate tets are all kept
+        unsigned long long* pairs = tab.data() + 8 * WT_STRIDE + pc * WP_STRIDE;
+        unsigned long long seen = 0ull;
+        int np = 0;
+        for (int i = 1; i <= n; ++i) {
+            const unsigned long long e = tab[pc * WT_STRIDE + i];
+            const unsigned bit = (unsigned)((e >> 3) & 31ull) * 2u + (unsigned)((e >> 8) & 1ull);
+            if ((seen >> bit) & 1ull) continue;
+            seen |= 1ull << bit;
+            pairs[1 + np++] = (unsigned long long)bit;
+        }
+        pairs[0] = (unsigned long long)np;
     }
 }
 
