@@ -443,7 +443,9 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     __shared__ uint16_t s_list[TILE_POINTS];   // surface cells (local index)
     __shared__ uint32_t s_ci[TILE_POINTS / 2]; // cinfo of the surface cells being assembled, by list slot
     __shared__ uint32_t s_n;
+    __shared__ uint32_t s_stat[8];             // trim cases 0..6 + exterior removals of the owned cells
     if (threadIdx.x == 0) s_n = 0u;
+    if (threadIdx.x < 8) s_stat[threadIdx.x] = 0u;
     stage_points<H, 0, true>(L, X0, Y0, Z0, [&](int idx, bool in, double raw, uint8_t wc) {
         const double w = (wc & 0x7f) ? 0.0 : raw;
         s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0)) : (uint8_t)0;
@@ -487,8 +489,8 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             classify_tet<true>(L, c, (int)t, tn, prog, -1, to);
             if (to.kase == -2) continue;  // not kept by cut_lattice
             uint32_t bits = ((uint32_t)to.n << (2u * t)) | (1u << (16u + t));  // bit 16+t: kept
-            if (to.ext_removed) { bits |= 1u << (CI_REMOVED_SHIFT + t); if (own) atomicAdd(&counters[CN_EXT_REMOVED], 1ull); }
-            if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&counters[CN_STAT0 + to.kase], 1ull); }  // bit 24+t: trimmed
+            if (to.ext_removed) { bits |= 1u << (CI_REMOVED_SHIFT + t); if (own) atomicAdd(&s_stat[7], 1u); }
+            if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&s_stat[to.kase], 1u); }  // bit 24+t: trimmed
             atomicOr(&s_ci[q], bits);
             // zero-valued original vertices that made it into the output are "used"
             for (int o = 0; o < to.n; ++o)
@@ -519,6 +521,9 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
     const unsigned long long listed = block_sum((unsigned long long)my_listed, &s_acc);
     if (threadIdx.x == 0 && listed) atomicAdd(&counters[CN_LISTED_TETS], listed);
+    // the statistics leave the block as at most 8 global atomics
+    if (threadIdx.x < 8 && s_stat[threadIdx.x])
+        atomicAdd(&counters[threadIdx.x < 7 ? CN_STAT0 + (int)threadIdx.x : (int)CN_EXT_REMOVED], (unsigned long long)s_stat[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------
