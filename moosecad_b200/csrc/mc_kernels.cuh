@@ -706,34 +706,55 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
         }
         return;
     }
-    uint32_t vrun = 0;
-    uint64_t crun = tile_cbase[blockIdx.x];
+    // Numbering: every thread takes one x-row of 16 points (consecutive in the numbering) and one
+    // block scan of the row totals (low half: output vertices, high half: cut edges; <= 40960 /
+    // 36864 per tile) gives each point's first local id and cut-list slot ...
+    __shared__ uint16_t s_m[TILE_POINTS], s_loc[TILE_POINTS], s_cut[TILE_POINTS];
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t Y = b.Y0 + ly, Z = b.Z0 + lz;
+        const bool row_in = Y < L.NY && Z >= b.zlo && Z < b.zhi;
+        const uint32_t nrow = row_in ? min(TS, L.NX - b.X0) : 0u;
+        const uint16_t* __restrict__ row = S.vmask + (row_in ? pidx(L, b.X0, Y, Z) : 0);
+        uint32_t acc = 0;
+        uint32_t pre[TS];
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) {
+            const uint16_t m = i < nrow ? row[i] : (uint16_t)0;
+            s_m[threadIdx.x * TS + i] = m;
+            const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
+            pre[i] = acc;
+            acc += (ncut + ((m & VM_USED) ? 1u : 0u)) | (ncut << 16);
+        }
+        uint32_t tot;
+        const uint32_t ex = block_exscan(acc, &tot, s_scan);
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) {
+            const uint32_t v = ex + pre[i];
+            s_loc[threadIdx.x * TS + i] = (uint16_t)(v & 0xffffu);
+            s_cut[threadIdx.x * TS + i] = (uint16_t)(v >> 16);
+        }
+    }
+    __syncthreads();
+    // ... and the outputs are written with consecutive lanes on consecutive points
+    const uint64_t cb = tile_cbase[blockIdx.x];
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
         const uint32_t X = b.X0 + (j & 15u), Y = b.Y0 + ((j >> 4) & 15u), Z = b.Z0 + (j >> 8);
-        const bool in = X < L.NX && Y < L.NY && Z >= b.zlo && Z < b.zhi;
-        size_t pi = 0;
-        uint16_t m = 0;
-        if (in) { pi = pidx(L, X, Y, Z); m = S.vmask[pi]; }
-        const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
-        const uint32_t nout = ncut + ((m & VM_USED) ? 1u : 0u);
-        uint32_t tot;
-        const uint32_t ex = block_exscan(nout | (ncut << 16), &tot, s_scan);
-        if (in) {
-            const uint32_t loc = vrun + (ex & 0xffffu);
-            S.vloc[pi] = (uint16_t)loc;
-            if (m & VM_USED) {
-                double p[3];
-                warped_pos(L, X, Y, Z, p);
-                double* o = coords + 3 * (vb + loc);
-                o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-            }
-            uint64_t ci = crun + (ex >> 16);
-            for (int s = 0; s < 9; ++s)
-                if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
+        if (!(X < L.NX && Y < L.NY && Z >= b.zlo && Z < b.zhi)) continue;
+        const size_t pi = pidx(L, X, Y, Z);
+        const uint16_t m = s_m[j];
+        const uint32_t loc = s_loc[j];
+        S.vloc[pi] = (uint16_t)loc;
+        if (m & VM_USED) {
+            double p[3];
+            warped_pos(L, X, Y, Z, p);
+            double* o = coords + 3 * (vb + loc);
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         }
-        vrun += tot & 0xffffu;
-        crun += tot >> 16;
+        uint64_t ci = cb + s_cut[j];
+        for (int s = 0; s < 9; ++s)
+            if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
     }
 }
 
