@@ -215,7 +215,7 @@ def main():
             lib.mc_mesh_free(h)
         # one instrumented pass: FP64 operations the SDF kernel executes per launch (untimed)
         h = one_step(_lib.MC_OPT_COUNT_FLOPS)
-        ts = (C.c_uint64 * 5)()
+        ts = (C.c_uint64 * 6)()
         lib.mc_mesh_tile_stats(h, ts)
         tile_stats = list(ts)
         lib.mc_mesh_free(h)
@@ -321,7 +321,8 @@ def main():
                     "flops_per_point_executed": sdf_flops / p_eval if p_eval else None,
                     "flops_per_point_evaluate_all_model": info["flops"],
                     "tiles": {"total": tile_stats[0], "sdf_skipped_proven_uniform": tile_stats[1],
-                              "surface_point_tiles": tile_stats[2], "surface_cell_tiles": tile_stats[3]},
+                              "surface_point_tiles": tile_stats[2], "surface_cell_tiles": tile_stats[3],
+                              "sub_boxes_proven_of_32_per_evaluated_tile": tile_stats[5]},
                     "ms": stage_avg[0]}
             stuff_ms = sum(stage_avg[1:7])  # warp, classify, vertex, bisect, tet emit (+ fused quality)
             bytes_alg = 8 * P_total + 24 * n_verts + 4 * 4 * n_tets

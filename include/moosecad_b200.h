@@ -226,8 +226,9 @@ int mc_mesh_prune_stats(const mc_mesh*, uint64_t* n_tiles, uint64_t* pruned_word
 /* tile bookkeeping of the last run: [0] tiles (16^3 lattice points each), [1] tiles whose SDF
  * evaluation was skipped (proven interior / exterior), [2] point tiles and [3] cell tiles that
  * needed the general stuffing path (the rest took the uniform-sign fast paths), [4] FP64
- * operations executed by the SDF kernel (MC_OPT_COUNT_FLOPS runs only, else 0) */
-int mc_mesh_tile_stats(const mc_mesh*, uint64_t out[5]);
+ * operations executed by the SDF kernel (MC_OPT_COUNT_FLOPS runs only, else 0), [5] sub-boxes
+ * (8 x 4 x 4 points, 32 per tile) of fully evaluated tiles whose sign was proven, i.e. skipped */
+int mc_mesh_tile_stats(const mc_mesh*, uint64_t out[6]);
 /* id table of the plane z = z_end for the rank above: one uint64 per lattice point of the
  * plane, (global base id << 16) | mask.  Device pointer + length in entries. */
 int mc_mesh_upper_plane_table(mc_mesh*, void** d_table, uint64_t* n_entries);

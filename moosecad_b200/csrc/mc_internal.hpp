@@ -53,7 +53,7 @@ struct mc_mesh {
 
     mc::TileGrid g{};
     mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo;
-    mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign;
+    mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign, d_sub;
     mc::DevBuf d_ttile_tot, d_ttile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
     const void* lower_table = nullptr;  // id table of plane c0 from the rank below (caller-owned)
     const double* lower_coords = nullptr;  // coordinates of the rank below's top tile layer (caller-owned)

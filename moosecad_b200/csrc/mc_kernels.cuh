@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;

@@ -165,7 +165,7 @@ static void mesh_release_all(mc_mesh* m) {
                       &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
                       &m->d_tflag, &m->d_vuni, &m->d_cuni, &m->d_tsign,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
-                      &m->d_inst_start, &m->d_word_inst, &m->d_dec};
+                      &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub};
     for (DevBuf* b : bufs) c->release(*b);
     for (auto& e : m->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -315,6 +315,16 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
                                                                   (uint8_t*)m->d_dec.p, (int8_t*)m->d_tsign.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
+    const bool skip_uniform = !(m->flags & MC_OPT_KEEP_PHI);
+    if (skip_uniform) {
+        rc = c->alloc(ntiles * 8, m->d_sub);
+        if (rc != MC_OK) return rc;
+        k_subbox_decide<<<blocks_for(ntiles, 4), 128, 0, c->stream>>>(L, m->g, (const uint64_t*)m->d_prog.p, ntiles, (const uint8_t*)m->d_dec.p,
+                                                                     (const int8_t*)m->d_tsign.p, (uint32_t*)m->d_sub.p,
+                                                                     (unsigned long long*)m->d_counters.p + CN_SUB_BOXES_PROVEN);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
     const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
     const bool small = p.small();
     auto kern = count ? (small ? k_sdf_field_tiled<8, 4, true, true> : k_sdf_field_tiled<8, 4, true, false>)
@@ -329,9 +339,10 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, m->g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                                                    n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
-                                                   (const int8_t*)m->d_tsign.p, (m->flags & MC_OPT_KEEP_PHI) ? 0 : 1,
+                                                   (const int8_t*)m->d_tsign.p, skip_uniform ? 1 : 0,
                                                    pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES,
-                                                   (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS);
+                                                   (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS,
+                                                   skip_uniform ? (const uint32_t*)m->d_sub.p : nullptr);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     m->tiled_sdf = true;
@@ -890,13 +901,14 @@ int mc_mesh_prune_stats(const mc_mesh* m, uint64_t* n_tiles, uint64_t* pruned_wo
     return MC_OK;
 }
 
-int mc_mesh_tile_stats(const mc_mesh* m, uint64_t out[5]) {
+int mc_mesh_tile_stats(const mc_mesh* m, uint64_t out[6]) {
     if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_tile_stats: bad argument");
     out[0] = m->n_tiles;
     out[1] = m->counters[CN_SKIPPED_TILES];
     out[2] = m->counters[CN_ACTIVE_VTILES];
     out[3] = m->counters[CN_ACTIVE_CTILES];
     out[4] = m->counters[CN_SDF_FLOPS];
+    out[5] = m->counters[CN_SUB_BOXES_PROVEN];
     return MC_OK;
 }
 

@@ -56,8 +56,13 @@ __device__ __forceinline__ Ival iv_box_distance(const uint64_t* __restrict__ w, 
 // dec[id * dec_stride].  All 32 lanes of the warp run in lock step.
 // *work (optional) receives a rough count of the FP64 operations one point evaluation of the
 // tile-specialised program costs (the load estimate of mc_tile_layer_classes).
-__device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
-                          size_t dec_stride, float* work = nullptr) {
+// pdec (optional, then dec must be null): decisions already taken for a box that CONTAINS box0 (all
+// lanes of the warp share them): failed guards and dropped children are skipped outright, passing
+// guards are not re-tested — the evaluation costs what the tile-specialised program costs.
+__device__ __noinline__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], uint8_t* __restrict__ dec,
+                          size_t dec_stride, float* work = nullptr, const uint8_t* __restrict__ pdec = nullptr,
+                          size_t pstride = 0) {
+#define MC_PD(id) (pdec ? pdec[(size_t)(id) * pstride] : (uint8_t)MC_DEC_KEEP)
     float wk = 0.0f;
     int dead_end = -1;  // this lane's tile is inside a failed guard up to this word
     Ival vs[MC_MAX_VALUE_DEPTH + 1];
@@ -120,68 +125,106 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             break;
         }
         case MC_OP_GSPHERE:
-        case MC_OP_GCYL: {
-            const Ival a = iv_box_distance(w, pc + 1, b);
-            const double slack = ld_f64(w, pc + 7), r = ld_f64(w, pc + 8);
+        case MC_OP_GCYL:
+        case MC_OP_SPHERE:
+        case MC_OP_CYL: {
+            // SPHERE / CYL: the guard-free forms the tile compaction leaves behind (radius at pc + 1)
+            const bool guarded = op == MC_OP_GSPHERE || op == MC_OP_GCYL;
+            const double r = ld_f64(w, pc + (guarded ? 8 : 1));
             const Ival ax = iv_abs(b[0], b[1]), ay = iv_abs(b[2], b[3]), az = iv_abs(b[4], b[5]);
             Ival e;
-            if (op == MC_OP_GSPHERE)
+            if (op == MC_OP_GSPHERE || op == MC_OP_SPHERE)
                 e = {sqrt((ax.lo * ax.lo + ay.lo * ay.lo) + az.lo * az.lo) - r,
                      sqrt((ax.hi * ax.hi + ay.hi * ay.hi) + az.hi * az.hi) - r};
             else
                 e = {sqrt(ax.lo * ax.lo + ay.lo * ay.lo) - r, sqrt(ax.hi * ax.hi + ay.hi * ay.hi) - r};
             e = widen(e);
+            if (!guarded) { if (alive) wk += 8.0f; MC_IPUSH(e); break; }
+            const uint8_t pd = MC_PD(MC_HDR_DEC(h));
+            if (pd == MC_DEC_PASS) { MC_IPUSH(e); break; }
+            const Ival a = iv_box_distance(w, pc + 1, b);
+            if (pd == MC_DEC_FAIL) { MC_IPUSH(a); break; }
+            const double slack = ld_f64(w, pc + 7);
             uint8_t d = MC_DEC_KEEP;
             Ival v = {fmin(a.lo, e.lo), fmax(a.hi, e.hi)};
             if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
             else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
-            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (dec) dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
             if (alive) wk += d == MC_DEC_FAIL ? 12.0f : 20.0f;
             MC_IPUSH(v);
             break;
         }
-        case MC_OP_GBOX: {
-            const Ival a = iv_box_distance(w, pc + 1, b);
-            const double slack = ld_f64(w, pc + 7);
+        case MC_OP_BOXDIST:
+            if (alive) wk += 12.0f;
+            MC_IPUSH(iv_box_distance(w, pc + 1, b));
+            break;
+        case MC_OP_GBOX:
+        case MC_OP_BOX: {
+            // BOX: the guard-free form of the tile compaction (planes at pc + 1.., r, er at pc + 7, 8).
+            // `small` = planes that take part (all six in an uncompacted program).
+            const bool guarded = op == MC_OP_GBOX;
+            const int pl = pc + (guarded ? 8 : 1);
+            unsigned mask = MC_HDR_SMALL(h);
+            uint8_t pd = MC_DEC_KEEP;
+            if (guarded && pdec) {
+                pd = MC_PD(MC_HDR_DEC(h));
+                if (pd == MC_DEC_FAIL) { MC_IPUSH(iv_box_distance(w, pc + 1, b)); break; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    if (MC_PD(MC_HDR_DEC(h) + 1u + (uint32_t)i) == MC_DEC_FAIL) mask &= ~(1u << i);
+            }
             // the six plane intervals; a plane is droppable like any rvmax child
-            const double r = ld_f64(w, pc + 14), er = ld_f64(w, pc + 15);
+            const double r = ld_f64(w, pl + 6), er = ld_f64(w, pl + 7);
             const double margin = fmax(r, er);
             Ival pv[6];
             double ext = -INF;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const double dd = ld_f64(w, pc + 8 + i);
+                const double dd = ld_f64(w, pl + i);
                 const double q0 = b[2 * (i % 3)], q1 = b[2 * (i % 3) + 1];
                 pv[i] = widen(i >= 3 ? Ival{-q1 - dd, -q0 - dd} : Ival{q0 - dd, q1 - dd});
-                ext = fmax(ext, pv[i].lo);
+                if ((mask >> i) & 1u) ext = fmax(ext, pv[i].lo);
             }
             Ival e = {-INF, -INF};
             int kept = 0;
             const uint32_t dbase = MC_HDR_DEC(h) + 1u;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const bool drop = pv[i].hi <= ext - margin - pad_of(ext - margin);
-                dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
+                const bool drop = !((mask >> i) & 1u) || pv[i].hi <= ext - margin - pad_of(ext - margin);
+                if (dec && guarded) dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
                 if (!drop) { ++kept; e.lo = fmax(e.lo, pv[i].lo); e.hi = fmax(e.hi, pv[i].hi); }
             }
             if (kept > 1) { e.hi += 0.25 * r * 1.791759469228055; e = widen(e); }  // smooth branch: <= max + r/4 ln 6
+            if (!guarded || pd == MC_DEC_PASS) {
+                if (alive) wk += 6.0f * (float)kept + (kept > 1 ? 30.0f * (float)(kept + 1) : 0.0f);
+                MC_IPUSH(e);
+                break;
+            }
+            const Ival a = iv_box_distance(w, pc + 1, b);
+            const double slack = ld_f64(w, pc + 7);
             uint8_t d = MC_DEC_KEEP;
             Ival v = {fmin(a.lo, e.lo), fmax(a.hi, e.hi)};
             if (a.hi <= slack) { d = MC_DEC_PASS; v = e; }
             else if (a.lo > slack) { d = MC_DEC_FAIL; v = a; }
-            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (dec) dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
             if (alive) wk += d == MC_DEC_FAIL ? 12.0f : 12.0f + 6.0f * (float)kept + (kept > 1 ? 30.0f * (float)(kept + 1) : 0.0f);
             MC_IPUSH(v);
             break;
         }
         case MC_OP_GAPUSH:
         case MC_OP_GUARD: {
-            const Ival a = iv_box_distance(w, pc + 1, b);
+            const uint8_t pd = MC_PD(MC_HDR_DEC(h));
+            const Ival a = pd == MC_DEC_PASS ? Ival{0.0, 0.0} : iv_box_distance(w, pc + 1, b);
+            if (pd == MC_DEC_FAIL) {
+                MC_IPUSH(a);
+                pc = (int)MC_HDR_IDX(h);
+                continue;
+            }
             const double slack = ld_f64(w, pc + 7);
             uint8_t d = MC_DEC_KEEP;
-            if (a.hi <= slack) d = MC_DEC_PASS;
+            if (pd == MC_DEC_PASS || a.hi <= slack) d = MC_DEC_PASS;
             else if (a.lo > slack) d = MC_DEC_FAIL;
-            dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
+            if (dec) dec[(size_t)MC_HDR_DEC(h) * dec_stride] = d;
             if (alive) {
                 wk += op == MC_OP_GAPUSH ? 30.0f : 12.0f;
                 if (d == MC_DEC_FAIL) dead_end = (int)MC_HDR_IDX(h);
@@ -215,6 +258,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
         }
         case MC_OP_ENDG: {
             const int g = (int)MC_HDR_IDX(h);
+            if (MC_PD(MC_HDR_DEC(w[g])) == MC_DEC_PASS) break;  // passes everywhere: subtree value
             const Ival a = iv_box_distance(w, g + 1, b);
             const double slack = ld_f64(w, g + 7);
             if (a.hi <= slack) { /* pass everywhere: subtree value */ }
@@ -226,10 +270,18 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
             top = {-top.hi, -top.lo};
             break;
         case MC_OP_CHILD:
+            if (pdec && MC_PD(MC_HDR_DEC(h)) == MC_DEC_FAIL) { pc = (int)MC_HDR_IDX(h); continue; }  // dropped child
             break;
         case MC_OP_BOOL: {
             const unsigned sm = MC_HDR_SMALL(h);
-            const int k = (int)(sm & 0x7fu);
+            int k = (int)(sm & 0x7fu);
+            if (pdec) {
+                // only the children the containing box kept are on the stack
+                int kept_children = 0;
+                for (int i = 0; i < k; ++i) kept_children += MC_PD(MC_HDR_DEC(h) + (uint32_t)i) != MC_DEC_FAIL;
+                k = kept_children;
+                if (k <= 1) break;
+            }
             const bool is_union = (sm & 0x80u) != 0;
             const double r = ld_f64(w, pc + 1), er = ld_f64(w, pc + 2);
             const double margin = fmax(r, er);
@@ -248,7 +300,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
                 bool drop;
                 if (is_union) drop = x.lo >= ext + margin + pad_of(ext + margin);
                 else drop = x.hi <= ext - margin - pad_of(ext - margin);
-                dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
+                if (dec) dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
                 if (!drop) {
                     ++kept;
                     if (is_union) { res.lo = fmin(res.lo, x.lo); res.hi = fmin(res.hi, x.hi); }
@@ -301,6 +353,7 @@ __device__ Ival vm_decide(const uint64_t* __restrict__ w, const double box0[6], 
         pc += mc_op_words(op);
     }
 #undef MC_IPUSH
+#undef MC_PD
 }
 
 // decisions for every tile: one tile per lane
@@ -311,11 +364,12 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     const uint64_t tc = t < ntiles ? t : ntiles - 1;
     uint32_t X0, Y0, Z0;
     tile_origin(g, tc, X0, Y0, Z0);
-    // The box covers the tile's points plus the reach of the lattice edges OWNED by them (canonical
-    // directions: -1..+1 in x and y, 0..+1 in z), so that the decisions also hold along every cut
-    // edge the tile bisects.  Lattice coordinates are monotone in the index, so the end points
-    // bound the box exactly.
-    const uint32_t Xa = X0 > 0 ? X0 - 1 : 0, Ya = Y0 > 0 ? Y0 - 1 : 0, Za = Z0;
+    // The box covers the tile's points plus one lattice step on every side: the reach of the lattice
+    // edges OWNED by them (canonical directions: -1..+1 in x and y, 0..+1 in z), so that the
+    // decisions also hold along every cut edge the tile bisects, and the neighbourhood the sub-box
+    // sign proofs (k_subbox_decide) look at.  Lattice coordinates are monotone in the index, so
+    // the end points bound the box exactly.
+    const uint32_t Xa = X0 > 0 ? X0 - 1 : 0, Ya = Y0 > 0 ? Y0 - 1 : 0, Za = Z0 > 0 ? Z0 - 1 : 0;
     const uint32_t X1 = min(X0 + TS, L.nx), Y1 = min(Y0 + TS, L.ny), Z1 = min(Z0 + TS, L.nz);
     const double box[6] = {lat_x(L, Xa), lat_x(L, X1), lat_y(L, Ya), lat_y(L, Y1), lat_z(L, Za), lat_z(L, Z1)};
     // lanes past the end redo the last tile (same decisions, benign duplicate stores)
@@ -324,6 +378,52 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     if (twork) twork[tc] = wk;
     // proven sign of the whole tile (the bounds are padded; NaN proves nothing)
     tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
+}
+
+// Sign proofs below the tile level: the 32 sub-boxes (8 x 4 x 4 points) of every tile whose sign is
+// not proven for its whole 27-neighbourhood.  One warp per tile, one sub-box per lane: an interval
+// evaluation of the program over the sub-box plus one lattice step on every side.  A definite
+// sign there means that no tet or edge touching the sub-box's points has a vertex of another sign
+// class, i.e. their values are never read (same argument as for whole tiles) and k_sdf_field_tiled
+// writes the placeholder instead of evaluating them.  The lanes of a warp share the tile, so
+// subtrees whose bounding box is far from the tile are skipped warp-uniformly.
+// sub_masks[2 * tile] = sub-boxes proven negative, [2 * tile + 1] = proven positive.
+static __global__ void __launch_bounds__(128)
+k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles,
+                const uint8_t* __restrict__ dec, const int8_t* __restrict__ tsign, uint32_t* __restrict__ sub_masks,
+                unsigned long long* __restrict__ sub_boxes_proven) {
+    const uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;  // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    const int sg = tsign[tile];
+    if (sg != 0) {
+        // tiles whose whole neighbourhood has the same proven sign are skipped as a whole
+        const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
+        bool same = true;
+        if (lane < 27u) {
+            const int x = tix + (int)(lane % 3u) - 1, y = tiy + (int)((lane / 3u) % 3u) - 1, z = tiz + (int)(lane / 9u) - 1;
+            if (!(x < 0 || y < 0 || z < 0 || x >= (int)g.ntx || y >= (int)g.nty || z >= (int)g.ntz))
+                same = tsign[((size_t)z * g.nty + y) * g.ntx + x] == sg;
+        }
+        if (__all_sync(0xffffffffu, same)) {
+            if (lane == 0) { sub_masks[2 * tile] = 0u; sub_masks[2 * tile + 1] = 0u; }
+            return;
+        }
+    }
+    uint32_t X0, Y0, Z0;
+    tile_origin(g, tile, X0, Y0, Z0);
+    const uint32_t bx = X0 + (lane & 1u) * 8u, by = Y0 + ((lane >> 1) & 3u) * 4u, bz = Z0 + (lane >> 3) * 4u;
+    const uint32_t xa = bx > 0 ? bx - 1 : 0, ya = by > 0 ? by - 1 : 0, za = bz > 0 ? bz - 1 : 0;
+    const double box[6] = {lat_x(L, min(xa, L.nx)), lat_x(L, min(bx + 8u, L.nx)), lat_y(L, min(ya, L.ny)),
+                           lat_y(L, min(by + 4u, L.ny)), lat_z(L, min(za, L.nz)), lat_z(L, min(bz + 4u, L.nz))};
+    // the tile's own decisions hold on its box plus one step on every side, which contains `box`
+    const Ival r = vm_decide(prog, box, nullptr, 0, nullptr, dec + tile, (size_t)ntiles);
+    const unsigned neg = __ballot_sync(0xffffffffu, r.hi < 0.0), pos = __ballot_sync(0xffffffffu, r.lo > 0.0);
+    if (lane == 0) {
+        sub_masks[2 * tile] = neg;
+        sub_masks[2 * tile + 1] = pos;
+        if (neg | pos) atomicAdd(sub_boxes_proven, (unsigned long long)__popc(neg | pos));
+    }
 }
 
 // cost classes of the tiles per tile layer (see tile_layer_classes in mc_mesher.cu):
@@ -502,7 +602,8 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
                   const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
-                  unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total) {
+                  unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total,
+                  const uint32_t* __restrict__ sub_masks) {
     unsigned long long my_flops = 0ull;
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
@@ -519,14 +620,11 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         // of tets / edges that contain a vertex of another sign class, and those lie within one
         // lattice step, i.e. inside the neighbourhood.  Such tiles get a placeholder of the right
         // sign instead of being evaluated (unless the caller wants the field itself).
-        bool shell_only = false;
-        double shell_fill = 0.0;
+        uint32_t X0, Y0, Z0;
+        tile_origin(g, tile, X0, Y0, Z0);
+        uint32_t sub_neg = 0u, sub_pos = 0u;
         if (skip_uniform) {
             const int sg = tsign[tile];
-            // a tile of proven sign next to tiles of another / unknown sign: only its outer layer
-            // of points can be part of a tet or edge with a vertex of another sign class
-            shell_only = sg != 0;
-            shell_fill = sg < 0 ? -1.0 : 1.0;
             bool uniform = sg != 0;
             if (uniform) {
                 const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
@@ -537,13 +635,17 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                     if (tsign[((size_t)z * g.nty + y) * g.ntx + x] != sg) uniform = false;
                 }
             }
-            if (__syncthreads_and(uniform ? 1 : 0)) {
-                uint32_t X0, Y0, Z0;
-                tile_origin(g, tile, X0, Y0, Z0);
-                const double fill = sg < 0 ? -1.0 : 1.0;
+            const bool whole = __syncthreads_and(uniform ? 1 : 0) != 0;
+            // below the tile level: sign proofs of the 32 sub-boxes (8 x 4 x 4 points) by k_subbox_decide
+            if (whole) { sub_neg = sg < 0 ? 0xffffffffu : 0u; sub_pos = ~sub_neg; }
+            else { sub_neg = sub_masks[2 * tile]; sub_pos = sub_masks[2 * tile + 1]; }
+            if ((sub_neg | sub_pos) == 0xffffffffu) {
+                // nothing to evaluate: placeholders only
                 for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
-                    const uint32_t X = X0 + (j & 15u), Y = Y0 + ((j >> 4) & 15u), Z = Z0 + (j >> 8);
-                    if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = fill;
+                    const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+                    const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+                    const uint32_t sub = (lx >> 3) | ((ly >> 2) << 1) | ((lz >> 2) << 3);
+                    if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = ((sub_neg >> sub) & 1u) ? -1.0 : 1.0;
                 }
                 if (tid == 0 && skipped_tiles) atomicAdd(skipped_tiles, 1ull);
                 continue;
@@ -553,47 +655,25 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                              s_newpos, s_scan);
         if (tid == 0 && pruned_words_total) atomicAdd(pruned_words_total, (unsigned long long)s_newpos[n_inst]);
         __syncthreads();
-        // 4. evaluate the tile: WX x WY points of one z-plane per warp step
-        uint32_t X0, Y0, Z0;
-        tile_origin(g, tile, X0, Y0, Z0);
-        if (shell_only) {
-            // interior (14^3 points): placeholder of the proven sign
-            for (uint32_t j = tid; j < (TS - 2) * (TS - 2) * (TS - 2); j += blockDim.x) {
-                const uint32_t X = X0 + 1 + j % (TS - 2), Y = Y0 + 1 + (j / (TS - 2)) % (TS - 2), Z = Z0 + 1 + j / ((TS - 2) * (TS - 2));
-                if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = shell_fill;
-            }
-        }
-        // full tile: 8 x 4 points of one z-plane per warp step; shell: 2 * 256 + 14 * 60 = 1352 outer
-        // points mapped densely onto the lanes.  One evaluator call site for both.
-        constexpr uint32_t NSHELL = 2 * TS * TS + (TS - 2) * (4 * TS - 4);
+        // evaluate the tile: WX x WY points of one z-plane per warp step; the footprint of a step
+        // lies in one sub-box
+        static_assert(WX == 8 && WY == 4, "warp footprint = sub-box cross-section");
         const uint32_t wpx = TS / WX, wpy = TS / WY;
-        const uint32_t steps = shell_only ? (NSHELL + 31u) / 32u : wpx * wpy * TS;
         const uint32_t lane = tid & 31u;
-        for (uint32_t s = tid >> 5; s < steps; s += (blockDim.x >> 5)) {
-            uint32_t lx, ly, lz;
-            bool live = true;
-            if (shell_only) {
-                uint32_t j = s * 32u + lane;
-                live = j < NSHELL;
-                if (!live) j = NSHELL - 1;
-                if (j < 2 * TS * TS) {
-                    lz = j < TS * TS ? 0u : TS - 1; lx = j % TS; ly = (j / TS) % TS;
-                } else {
-                    const uint32_t r = j - 2 * TS * TS, q = r % (4 * TS - 4);
-                    lz = 1 + r / (4 * TS - 4);
-                    if (q < TS) { ly = 0; lx = q; }
-                    else if (q < 2 * TS) { ly = TS - 1; lx = q - TS; }
-                    else { lx = ((q - 2 * TS) / (TS - 2)) ? TS - 1 : 0u; ly = 1 + (q - 2 * TS) % (TS - 2); }
-                }
-            } else {
-                lx = (s % wpx) * WX + lane % WX; ly = ((s / wpx) % wpy) * WY + lane / WX; lz = s / (wpx * wpy);
-            }
+        for (uint32_t s = tid >> 5; s < wpx * wpy * TS; s += (blockDim.x >> 5)) {
+            const uint32_t lx = (s % wpx) * WX + lane % WX, ly = ((s / wpx) % wpy) * WY + lane / WX, lz = s / (wpx * wpy);
             const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-            if (!shell_only && Z > L.pz1) continue;  // warp-uniform
-            const bool inside = live && X < L.NX && Y < L.NY && Z <= L.pz1;
-            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1, Zc = Z <= L.pz1 ? Z : L.pz1;
+            if (Z > L.pz1) continue;  // warp-uniform
+            const bool inside = X < L.NX && Y < L.NY;
+            const uint32_t sub = (s % wpx) | (((s / wpx) % wpy) << 1) | ((lz >> 2) << 3);
+            const bool dn = (sub_neg >> sub) & 1u, dp = (sub_pos >> sub) & 1u;
+            if (dn || dp) {
+                if (inside) phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0;
+                continue;
+            }
+            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
             unsigned long long fl = 0ull;
-            const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Zc), fl);
+            const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
             if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
         }
     }

@@ -228,9 +228,9 @@ class Mesh:
         _lib.check(self._lib.mc_mesh_stage_ms(self.handle, ms))
         nt, pw, fw = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _lib.check(self._lib.mc_mesh_prune_stats(self.handle, C.byref(nt), C.byref(pw), C.byref(fw)))
-        ts = (C.c_uint64 * 5)()
+        ts = (C.c_uint64 * 6)()
         _lib.check(self._lib.mc_mesh_tile_stats(self.handle, ts))
-        return {"tiles": {"total": ts[0], "sdf_skipped": ts[1], "active_point_tiles": ts[2], "active_cell_tiles": ts[3], "sdf_flops_executed": ts[4]},
+        return {"tiles": {"total": ts[0], "sdf_skipped": ts[1], "active_point_tiles": ts[2], "active_cell_tiles": ts[3], "sdf_flops_executed": ts[4], "sub_boxes_proven": ts[5]},
                 "prune": {"tiles": nt.value, "avg_words": (pw.value / nt.value) if nt.value else None,
                           "full_words": fw.value},
                 "dim": list(dim), "ntets_stage": list(stage), "stats": list(st), "aspect_ratio": list(ar),
