@@ -1291,7 +1291,9 @@ k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
     __shared__ double s_step[3][TS];
     __shared__ uint8_t s_repidx[3][TS];
     __shared__ __align__(4) uint16_t s_cnt[TILE_POINTS];
+    __shared__ uint32_t s_need_counts;
     for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) s_cnt[j] = 0;
+    if (threadIdx.x == 0) s_need_counts = 0u;
     if (threadIdx.x < 3 * TS) {
         const uint32_t a = threadIdx.x / TS, i = threadIdx.x % TS;
         const uint32_t cc = (a == 0 ? X0 : (a == 1 ? Y0 : Z0)) + i;
@@ -1306,22 +1308,46 @@ k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
         s_repidx[a][i] = (uint8_t)rep;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+    // The aspect-ratio range only needs to know WHICH classes occur (plain stores, no atomics);
+    // multiplicities matter for the inverted count alone, and un-warped lattice tets are not
+    // inverted: the counting pass below runs only if some class says otherwise.
+    auto class_of = [&](uint32_t j, uint32_t& cls) -> bool {
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
         const uint32_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
-        if (cx >= L.nx || cy >= L.ny || cz < zlo || cz >= zhi) continue;
+        if (cx >= L.nx || cy >= L.ny || cz < zlo || cz >= zhi) return false;
         const uint16_t ci = S.cinfo[cidx(S, cx, cy, cz)];
-        if ((ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER)) {
-            // 16-bit counters updated through their aligned 32-bit word
-            const uint32_t cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
-            atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
-        }
+        if (!((ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER))) return false;
+        cls = ((uint32_t)s_repidx[2][lz] * TS + s_repidx[1][ly]) * TS + s_repidx[0][lx];
+        return true;
+    };
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+        uint32_t cls;
+        if (class_of(j, cls)) s_cnt[cls] = 1;
     }
     __syncthreads();
     QualityAcc qa = {1.0, 0.0, 0u};
-    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
-        const uint32_t cnt = s_cnt[j];
-        if (cnt) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, qa);
+    for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS)
+        if (s_cnt[j]) lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), 1u, qa);
+    if (qa.inverted) s_need_counts = 1u;
+    qa.inverted = 0u;
+    __syncthreads();
+    if (s_need_counts) {
+        // exact multiplicities (16-bit counters updated through their aligned 32-bit word)
+        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) s_cnt[j] = 0;
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+            uint32_t cls;
+            if (class_of(j, cls)) atomicAdd(reinterpret_cast<unsigned int*>(s_cnt + (cls & ~1u)), 1u << (16u * (cls & 1u)));
+        }
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < TILE_POINTS; j += TILE_THREADS) {
+            const uint32_t cnt = s_cnt[j];
+            if (cnt) {
+                QualityAcc one = {1.0, 0.0, 0u};
+                lattice_cell_quality(L, X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8), cnt, one);
+                qa.inverted += one.inverted;
+            }
+        }
     }
     qa.flush(counters);
 }

@@ -342,7 +342,7 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
                                                    (const int8_t*)m->d_tsign.p, skip_uniform ? 1 : 0,
                                                    pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES,
                                                    (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS,
-                                                   skip_uniform ? (const uint32_t*)m->d_sub.p : nullptr);
+                                                   skip_uniform ? (const uint32_t*)m->d_sub.p : nullptr, (uint8_t*)m->d_tflag.p);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     m->tiled_sdf = true;
@@ -605,12 +605,12 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(launch_sdf_field(m));
     MC_TRY(c->stage_check("stage sdf_field"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
-    // tile sign summary + a6: warp codes
-    k_tile_minmax<<<tgrid, TILE_THREADS, 0, s>>>(S);
+    // tile sign summary (the tiled SDF kernel writes it itself) + a6: warp codes
+    if (!m->tiled_sdf) k_tile_minmax<<<tgrid, TILE_THREADS, 0, s>>>(S);
     k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
     MC_TRY(c->stage_check("stage tile summary"));
     k_warp_codes<<<tgrid, TILE_THREADS, 0, s>>>(S, counters);
-    c->launches += 3;
+    c->launches += m->tiled_sdf ? 2 : 3;
     MC_TRY_CUDA(cudaGetLastError());
     MC_TRY(c->stage_check("stage warp codes"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[2], s));

@@ -603,7 +603,7 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
                   const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
                   unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total,
-                  const uint32_t* __restrict__ sub_masks) {
+                  const uint32_t* __restrict__ sub_masks, uint8_t* __restrict__ tflag) {
     unsigned long long my_flops = 0ull;
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
@@ -647,7 +647,14 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                     const uint32_t sub = (lx >> 3) | ((ly >> 2) << 1) | ((lz >> 2) << 3);
                     if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = ((sub_neg >> sub) & 1u) ? -1.0 : 1.0;
                 }
-                if (tid == 0 && skipped_tiles) atomicAdd(skipped_tiles, 1ull);
+                if (tid == 0) {
+                    if (skipped_tiles) atomicAdd(skipped_tiles, 1ull);
+                    // sign summary of the tile (what k_tile_minmax would find)
+                    uint32_t live = 0u;  // sub-boxes with at least one stored point
+                    for (uint32_t sub = 0; sub < 32u; ++sub)
+                        if (X0 + (sub & 1u) * 8u < L.NX && Y0 + ((sub >> 1) & 3u) * 4u < L.NY && Z0 + (sub >> 3) * 4u <= L.pz1) live |= 1u << sub;
+                    tflag[tile] = (uint8_t)(((sub_pos & live) == 0u ? TF_NEG : 0) | ((sub_neg & live) == 0u ? TF_POS : 0));
+                }
                 continue;
             }
         }
@@ -660,6 +667,7 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         static_assert(WX == 8 && WY == 4, "warp footprint = sub-box cross-section");
         const uint32_t wpx = TS / WX, wpy = TS / WY;
         const uint32_t lane = tid & 31u;
+        bool not_neg = false, not_pos = false;  // a stored value that is not < 0 / not > 0 (NaN: both)
         for (uint32_t s = tid >> 5; s < wpx * wpy * TS; s += (blockDim.x >> 5)) {
             const uint32_t lx = (s % wpx) * WX + lane % WX, ly = ((s / wpx) % wpy) * WY + lane / WX, lz = s / (wpx * wpy);
             const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
@@ -668,14 +676,23 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             const uint32_t sub = (s % wpx) | (((s / wpx) % wpy) << 1) | ((lz >> 2) << 3);
             const bool dn = (sub_neg >> sub) & 1u, dp = (sub_pos >> sub) & 1u;
             if (dn || dp) {
-                if (inside) phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0;
+                if (inside) { phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0; not_pos = not_pos || dn; not_neg = not_neg || dp; }
                 continue;
             }
             const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
             unsigned long long fl = 0ull;
             const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
-            if (inside) { phi_out[pidx(L, X, Y, Z)] = v; my_flops += fl; }
+            if (inside) {
+                phi_out[pidx(L, X, Y, Z)] = v;
+                my_flops += fl;
+                not_neg = not_neg || !(v < 0.0);
+                not_pos = not_pos || !(v > 0.0);
+            }
         }
+        // sign summary of the tile (TF_NEG: every value < 0, TF_POS: every value > 0), the job of
+        // k_tile_minmax on the untiled path
+        const int any_not_neg = __syncthreads_or(not_neg ? 1 : 0), any_not_pos = __syncthreads_or(not_pos ? 1 : 0);
+        if (tid == 0) tflag[tile] = (uint8_t)((any_not_neg ? 0 : TF_NEG) | (any_not_pos ? 0 : TF_POS));
     }
     if (COUNT) {
 #pragma unroll
