@@ -665,20 +665,30 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         // evaluate the tile: WX x WY points of one z-plane per warp step; the footprint of a step
         // lies in one sub-box
         static_assert(WX == 8 && WY == 4, "warp footprint = sub-box cross-section");
-        const uint32_t wpx = TS / WX, wpy = TS / WY;
         const uint32_t lane = tid & 31u;
         bool not_neg = false, not_pos = false;  // a stored value that is not < 0 / not > 0 (NaN: both)
-        for (uint32_t s = tid >> 5; s < wpx * wpy * TS; s += (blockDim.x >> 5)) {
-            const uint32_t lx = (s % wpx) * WX + lane % WX, ly = ((s / wpx) % wpy) * WY + lane / WX, lz = s / (wpx * wpy);
+        // placeholders of the proven sub-boxes
+        if (sub_neg | sub_pos) {
+            for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
+                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+                const uint32_t sub = (lx >> 3) | ((ly >> 2) << 1) | ((lz >> 2) << 3);
+                const bool dn = (sub_neg >> sub) & 1u, dp = (sub_pos >> sub) & 1u;
+                const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+                if ((dn || dp) && X < L.NX && Y < L.NY && Z <= L.pz1) {
+                    phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0;
+                    not_pos = not_pos || dn; not_neg = not_neg || dp;
+                }
+            }
+        }
+        // the other sub-boxes, four 8 x 4 warp steps each, dealt round-robin to the warps
+        const uint32_t unproven = ~(sub_neg | sub_pos);
+        const uint32_t nsteps = 4u * (uint32_t)__popc(unproven);
+        for (uint32_t t = tid >> 5; t < nsteps; t += (blockDim.x >> 5)) {
+            const uint32_t sub = __fns(unproven, 0u, (int)(t >> 2) + 1);
+            const uint32_t lx = (sub & 1u) * 8u + lane % WX, ly = ((sub >> 1) & 3u) * 4u + lane / WX, lz = (sub >> 3) * 4u + (t & 3u);
             const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
             if (Z > L.pz1) continue;  // warp-uniform
             const bool inside = X < L.NX && Y < L.NY;
-            const uint32_t sub = (s % wpx) | (((s / wpx) % wpy) << 1) | ((lz >> 2) << 3);
-            const bool dn = (sub_neg >> sub) & 1u, dp = (sub_pos >> sub) & 1u;
-            if (dn || dp) {
-                if (inside) { phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0; not_pos = not_pos || dn; not_neg = not_neg || dp; }
-                continue;
-            }
             const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
             unsigned long long fl = 0ull;
             const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
