@@ -168,9 +168,9 @@ typedef struct mc_options {
 #define MC_TILE_CLASS_STRIDE 7
 #define MC_SLAB_COST_UNPROVEN 0.05
 #define MC_SLAB_COST_NEG_SKIPPED 0.07
-#define MC_SLAB_COST_NEG_SHELL 0.02
+#define MC_SLAB_COST_NEG_SHELL 0.07
 #define MC_SLAB_COST_POS_SKIPPED 0.002
-#define MC_SLAB_COST_POS_SHELL 0.02
+#define MC_SLAB_COST_POS_SHELL 0.002
 #define MC_SLAB_COST_UNPROVEN_WORK 1.9e-4
 #define MC_SLAB_COST_SHELL_WORK 0.0
 int mc_tile_layer_classes(mc_ctx*, const mc_tape* volume, int32_t root, double resolution, uint64_t layer_begin,

@@ -397,18 +397,10 @@ k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64
     const uint32_t lane = threadIdx.x & 31u;
     const int sg = tsign[tile];
     if (sg != 0) {
-        // tiles whose whole neighbourhood has the same proven sign are skipped as a whole
-        const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
-        bool same = true;
-        if (lane < 27u) {
-            const int x = tix + (int)(lane % 3u) - 1, y = tiy + (int)((lane / 3u) % 3u) - 1, z = tiz + (int)(lane / 9u) - 1;
-            if (!(x < 0 || y < 0 || z < 0 || x >= (int)g.ntx || y >= (int)g.nty || z >= (int)g.ntz))
-                same = tsign[((size_t)z * g.nty + y) * g.ntx + x] == sg;
-        }
-        if (__all_sync(0xffffffffu, same)) {
-            if (lane == 0) { sub_masks[2 * tile] = 0u; sub_masks[2 * tile + 1] = 0u; }
-            return;
-        }
+        // the tile's sign is proven on its box plus one lattice step on every side (k_tile_decide),
+        // which contains every sub-box plus its step: all 32 are proven
+        if (lane == 0) { sub_masks[2 * tile] = sg < 0 ? 0xffffffffu : 0u; sub_masks[2 * tile + 1] = sg < 0 ? 0u : 0xffffffffu; }
+        return;
     }
     uint32_t X0, Y0, Z0;
     tile_origin(g, tile, X0, Y0, Z0);
@@ -615,30 +607,17 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();  // previous tile's evaluation is done with s_prog
-        // A tile whose whole 27-neighbourhood is PROVEN to have one strict sign is never read for
-        // its values: every consumer (warp, the 4-sort, bisection end points) only looks at values
-        // of tets / edges that contain a vertex of another sign class, and those lie within one
-        // lattice step, i.e. inside the neighbourhood.  Such tiles get a placeholder of the right
-        // sign instead of being evaluated (unless the caller wants the field itself).
+        // A point whose whole neighbourhood (one lattice step on every side) is PROVEN to have one
+        // strict sign is never read for its value: every consumer (warp, the 4-sort, bisection end
+        // points) only looks at values of tets / edges that contain a vertex of another sign class,
+        // and those lie within one lattice step.  Such points get a placeholder of the right sign
+        // instead of being evaluated (unless the caller wants the field itself).
         uint32_t X0, Y0, Z0;
         tile_origin(g, tile, X0, Y0, Z0);
         uint32_t sub_neg = 0u, sub_pos = 0u;
         if (skip_uniform) {
-            const int sg = tsign[tile];
-            bool uniform = sg != 0;
-            if (uniform) {
-                const int tix = (int)(tile % g.ntx), tiy = (int)((tile / g.ntx) % g.nty), tiz = (int)(tile / ((uint64_t)g.ntx * g.nty));
-                for (int q = (int)tid; q < 27 && uniform; q += 32) {
-                    if (tid >= 32) break;
-                    const int x = tix + q % 3 - 1, y = tiy + (q / 3) % 3 - 1, z = tiz + q / 9 - 1;
-                    if (x < 0 || y < 0 || z < 0 || x >= (int)g.ntx || y >= (int)g.nty || z >= (int)g.ntz) continue;
-                    if (tsign[((size_t)z * g.nty + y) * g.ntx + x] != sg) uniform = false;
-                }
-            }
-            const bool whole = __syncthreads_and(uniform ? 1 : 0) != 0;
-            // below the tile level: sign proofs of the 32 sub-boxes (8 x 4 x 4 points) by k_subbox_decide
-            if (whole) { sub_neg = sg < 0 ? 0xffffffffu : 0u; sub_pos = ~sub_neg; }
-            else { sub_neg = sub_masks[2 * tile]; sub_pos = sub_masks[2 * tile + 1]; }
+            // proven on the tile's box plus one lattice step on every side: see k_subbox_decide
+            sub_neg = sub_masks[2 * tile]; sub_pos = sub_masks[2 * tile + 1];
             if ((sub_neg | sub_pos) == 0xffffffffu) {
                 // nothing to evaluate: placeholders only
                 for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
