@@ -149,6 +149,7 @@ typedef struct mc_options {
 #define MC_OPT_NO_TILE_PRUNING 4u /* evaluate the full SDF program at every lattice point */
 #define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
 #define MC_OPT_COUNT_FLOPS 16u /* instrumented SDF kernel: count the FP64 operations it executes (slower) */
+#define MC_OPT_PER_TILE_QUALITY 32u /* plain lattice tets: evaluate (step, parity) classes per tile, not globally */
 
 /* Load estimate for z-slab sharding (no reference counterpart).  An interval evaluation
  * of the SDF program over the 16^3-point tiles sorts every tile into a cost class:

@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -1349,6 +1349,106 @@ k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
             }
         }
     }
+    qa.flush(counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// check_for_inverted_tets for ALL plain lattice tets at once.  An un-warped lattice tet is built from
+// coordinate differences that are 0 or +-(the step of its cell along an axis), so its volume and
+// aspect ratio are functions of (step_x, step_y, step_z, mirroring) only.  Over the whole lattice
+// the steps take a handful of distinct values (they differ in the last bits), so every axis gets a
+// small class id per cell (host: step value id * 2 + parity, at most QC_K per axis), the kernels
+// below record which (kx, ky, kz) combinations occur among the plain cells, and each combination is
+// evaluated exactly once.  The aspect-ratio range needs nothing else; the inverted COUNT would
+// need multiplicities, so a combination that turns out inverted (it never does for a sane
+// lattice) only raises a flag and the host re-runs the per-tile counting kernels above.
+constexpr int QC_K = 32;  // classes per axis (16 distinct steps x parity); more -> per-tile kernels
+struct QualityClasses {
+    const uint8_t* kx;      // class of every cell column / row / layer (global cell index)
+    const uint8_t* ky;
+    const uint8_t* kz;
+    const double* steps;    // [3][QC_K / 2] distinct step values per axis
+    uint32_t* present;      // [kz * QC_K + ky] bit kx
+};
+
+// interior cell tiles: every cell is plain, all combinations of the tile's classes occur
+static __global__ void __launch_bounds__(32)
+k_quality_mark_full(Stuff S, QualityClasses Q) {
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (S.cuni[blockIdx.x] != CU_FULL || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    const uint32_t lane = threadIdx.x, i = lane & 15u;
+    uint32_t bx = 0u, by = 0u, bz = 0u;
+    if (lane < 16u) {
+        if (X0 + i < L.nx) bx = 1u << Q.kx[X0 + i];
+        if (Y0 + i < L.ny) by = 1u << Q.ky[Y0 + i];
+    } else if (Z0 + i >= zlo && Z0 + i < zhi) {
+        bz = 1u << Q.kz[Z0 + i];
+    }
+    const uint32_t mx = __reduce_or_sync(0xffffffffu, bx), my = __reduce_or_sync(0xffffffffu, by), mz = __reduce_or_sync(0xffffffffu, bz);
+    const uint32_t ny_ = (uint32_t)__popc(my), npairs = ny_ * (uint32_t)__popc(mz);
+    for (uint32_t p = lane; p < npairs; p += 32u) {
+        const uint32_t ky = __fns(my, 0u, (int)(p % ny_) + 1), kz = __fns(mz, 0u, (int)(p / ny_) + 1);
+        uint32_t* w = Q.present + kz * QC_K + ky;
+        if ((*w & mx) != mx) atomicOr(w, mx);
+    }
+}
+
+// surface cell tiles: the plain cells (untouched, all corners strictly negative) one by one
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_quality_mark_surface(Stuff S, QualityClasses Q) {
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
+    if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (zhi <= zlo) return;
+    // one x-row of 16 cells per thread
+    const uint32_t cy = Y0 + (threadIdx.x & 15u), cz = Z0 + (threadIdx.x >> 4);
+    if (cy >= L.ny || cz < zlo || cz >= zhi) return;
+    const uint16_t* __restrict__ row = S.cinfo + cidx(S, X0, cy, cz);
+    const uint32_t n = min(TS, L.nx - X0);
+    uint32_t bits = 0u;
+#pragma unroll
+    for (uint32_t i = 0; i < TS; ++i) {
+        if (i >= n) break;
+        const uint16_t ci = row[i];
+        if ((ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER)) bits |= 1u << Q.kx[X0 + i];
+    }
+    if (bits) {
+        uint32_t* w = Q.present + (uint32_t)Q.kz[cz] * QC_K + Q.ky[cy];
+        if ((*w & bits) != bits) atomicOr(w, bits);
+    }
+}
+
+// one thread per (kx, ky, kz): the five lattice tets of a cell with those steps and mirroring
+static __global__ void __launch_bounds__(256)
+k_quality_classes(QualityClasses Q, unsigned long long* __restrict__ counters) {
+    constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t kx = t % QC_K, ky = (t / QC_K) % QC_K, kz = t / (QC_K * QC_K);
+    QualityAcc qa = {1.0, 0.0, 0u};
+    if (kz < QC_K && ((Q.present[kz * QC_K + ky] >> kx) & 1u)) {
+        const double d[3] = {Q.steps[kx >> 1], Q.steps[QC_K / 2 + (ky >> 1)], Q.steps[QC_K + (kz >> 1)]};
+        const bool f[3] = {(kx & 1u) != 0u, (ky & 1u) != 0u, (kz & 1u) != 0u};
+        double pos[8][3];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) pos[k][a] = ((f[a] ? 1 - C_LAT[k][a] : C_LAT[k][a]) != 0) ? d[a] : 0.0;
+        const bool flip = f[0] ^ f[1] ^ f[2];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            if (flip) qa.add(pos[T[q][1]], pos[T[q][0]], pos[T[q][2]], pos[T[q][3]]);
+            else qa.add(pos[T[q][0]], pos[T[q][1]], pos[T[q][2]], pos[T[q][3]]);
+        }
+    }
+    // an inverted class needs multiplicities: flag it, count nothing here
+    if (qa.inverted) atomicAdd(&counters[CN_CLASS_INVERTED], 1ull);
+    qa.inverted = 0u;
     qa.flush(counters);
 }
 

@@ -13,6 +13,8 @@
 
 using namespace mc;
 
+static_assert(CN_COUNT <= 32, "mc_mesh::counters holds 32 entries");
+
 namespace mc {
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -738,6 +740,35 @@ int mc_tessellate_emit_vertices(mc_mesh* m, uint64_t vertex_base) {
     return MC_OK;
 }
 
+// Per-axis step classes for the global plain-lattice quality pass (k_quality_classes): returns false
+// when an axis has more than QC_K / 2 distinct steps (the per-tile kernels are used instead).
+// Layout of the device buffer: [3][QC_K / 2] doubles, [QC_K * QC_K] uint32 presence words, then the
+// class bytes of the x, y and z cells.
+static bool build_quality_classes(const Lattice& L, std::vector<double>& steps, std::vector<uint8_t>& ids) {
+    steps.assign(3 * (QC_K / 2), 0.0);
+    ids.clear();
+    const uint32_t n[3] = {L.nx, L.ny, L.nz};
+    const double o[3] = {L.ox, L.oy, L.oz};
+    ids.reserve((size_t)n[0] + n[1] + n[2]);
+    for (int a = 0; a < 3; ++a) {
+        int nd = 0;
+        double* st = steps.data() + a * (QC_K / 2);
+        for (uint32_t c = 0; c < n[a]; ++c) {
+            // lat_x / lat_y / lat_z of mc_lattice.cuh, same arithmetic (no contraction on either side)
+            const double p0 = (double)c * L.res + o[a], p1 = (double)(c + 1) * L.res + o[a];
+            const double d = p1 - p0;
+            int k = 0;
+            while (k < nd && std::memcmp(&st[k], &d, 8) != 0) ++k;
+            if (k == nd) {
+                if (nd == QC_K / 2) return false;
+                st[nd++] = d;
+            }
+            ids.push_back((uint8_t)(2 * k + (int)(c & 1u)));
+        }
+    }
+    return true;
+}
+
 int mc_tessellate_set_lower_coords(mc_mesh* m, const void* d_coords, uint64_t first_global_id, uint64_t count) {
     if (!m || m->phase >= 3) return fail(MC_ERR_STATE, "mc_tessellate_set_lower_coords: call it before mc_tessellate_emit_tets");
     m->lower_coords = count ? (const double*)d_coords : nullptr;
@@ -810,13 +841,43 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         rc = c->alloc(std::max<uint64_t>(nlist, 1) * 8, qlist);
         if (rc != MC_OK) return rc;
         unsigned long long* ql = (unsigned long long*)qlist.p;
+        // plain lattice tets: one evaluation per global (step, parity) class when the steps take few
+        // distinct values, else per tile
+        DevBuf qcls;
+        QualityClasses Q{};
+        bool class_quality = false;
+        if (quality) {
+            std::vector<double> steps;
+            std::vector<uint8_t> ids;
+            if (!(m->flags & MC_OPT_PER_TILE_QUALITY) && build_quality_classes(m->L, steps, ids)) {
+                const size_t off_present = steps.size() * 8, off_ids = off_present + (size_t)QC_K * QC_K * 4;
+                rc = c->alloc(off_ids + ids.size() + 16, qcls);
+                if (rc != MC_OK) return rc;
+                char* base = (char*)qcls.p;
+                MC_CUDA(cudaMemcpyAsync(base, steps.data(), steps.size() * 8, cudaMemcpyHostToDevice, s));
+                MC_CUDA(cudaMemsetAsync(base + off_present, 0, (size_t)QC_K * QC_K * 4, s));
+                MC_CUDA(cudaMemcpyAsync(base + off_ids, ids.data(), ids.size(), cudaMemcpyHostToDevice, s));
+                Q.steps = (const double*)base;
+                Q.present = (uint32_t*)(base + off_present);
+                Q.kx = (const uint8_t*)(base + off_ids);
+                Q.ky = Q.kx + m->L.nx;
+                Q.kz = Q.ky + m->L.ny;
+                class_quality = true;
+            }
+        }
         if (m->index_bytes == 4) {
             uint32_t* out = (uint32_t*)m->d_tets.p;
             k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
             if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
-                k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                if (class_quality) {
+                    k_quality_mark_full<<<grid, 32, 0, s>>>(S, Q);
+                    k_quality_mark_surface<<<grid, TILE_THREADS, 0, s>>>(S, Q);
+                    k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
+                } else {
+                    k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
+                    k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
@@ -829,8 +890,14 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
             if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
-                k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
-                k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                if (class_quality) {
+                    k_quality_mark_full<<<grid, 32, 0, s>>>(S, Q);
+                    k_quality_mark_surface<<<grid, TILE_THREADS, 0, s>>>(S, Q);
+                    k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
+                } else {
+                    k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
+                    k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
+                }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
                 k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
@@ -840,13 +907,24 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             }
         }
         c->release(qlist);
-        c->launches += quality ? 5 : 2;
+        c->release(qcls);
+        c->launches += quality ? (class_quality ? 6 : 5) : 2;
         MC_CUDA(cudaGetLastError());
         if ((rc = c->stage_check("stage tet emit / quality list")) != MC_OK) return rc;
     }
     MC_CUDA(cudaEventRecord(m->ev[9], s));
     MC_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
     MC_CUDA(cudaStreamSynchronize(s));
+    if (m->counters[CN_CLASS_INVERTED]) {
+        // some plain lattice tet is inverted (degenerate lattice): the count needs multiplicities
+        const Stuff S2 = make_stuff(m);
+        k_full_tile_quality<<<(unsigned)m->n_tiles, 64, 0, s>>>(S2, counters);
+        k_surface_tile_quality<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S2, counters);
+        c->launches += 2;
+        MC_CUDA(cudaGetLastError());
+        MC_CUDA(cudaMemcpyAsync(m->counters, m->d_counters.p, CN_COUNT * 8, cudaMemcpyDeviceToHost, s));
+        MC_CUDA(cudaStreamSynchronize(s));
+    }
     float ms;
     const int pairs[6][2] = {{0, 1}, {1, 2}, {2, 3}, {5, 6}, {6, 7}, {8, 9}};
     for (int i = 0; i < 6; ++i) {

@@ -159,6 +159,27 @@ def test_ragged_scenes(name, res, flags, oracle, ctx):
     _compare(oracle, ctx, SCRIPTS[name], res, flags=flags)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,n", [("csg", 90), ("sphere", 61), ("xplicit", 48)])
+def test_plain_lattice_quality_paths_agree(scene, n, ctx):
+    """check_for_inverted_tets over the plain lattice tets: one evaluation per global (step, parity)
+    class vs. the per-tile classes (MC_OPT_PER_TILE_QUALITY) -- same aspect-ratio range, same count."""
+    if scene == "csg":
+        g = mc.Geom()
+        obj, res = scenes.synthetic_csg(g, 20, seed=3), 1.0 / n
+    elif scene == "sphere":
+        obj, res = luascad.eval(scenes.SPHERE_LUA)["sphere"].obj, 1.0 / n
+    else:
+        obj, res = luascad.eval(scenes.XPLICIT_LUA)["xplicit"].obj, 15.0 / n
+    obj.backend.set_parameters(0.1, 1.0)
+    a = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx, allow_diverged=True).tessellate().stats()
+    b = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_PER_TILE_QUALITY,
+                              allow_diverged=True).tessellate().stats()
+    for key in ("ntets_stage", "stats", "aspect_ratio", "inverted", "n_tets"):
+        assert a[key] == b[key], key
+    assert a["aspect_ratio"][0] <= a["aspect_ratio"][1] <= 1.0 + 1e-12
+
+
 @pytest.mark.parametrize("nprim,n", [(64, 72), (24, 100)])
 def test_tile_pruning_is_value_neutral(nprim, n, ctx):
     """The tile-specialised evaluator must produce the same bits as the full program at every
