@@ -321,7 +321,8 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     if (skip_uniform) {
         rc = c->alloc(ntiles * 8, m->d_sub);
         if (rc != MC_OK) return rc;
-        k_subbox_decide<<<blocks_for(ntiles, 4), 128, 0, c->stream>>>(L, m->g, (const uint64_t*)m->d_prog.p, ntiles, (const uint8_t*)m->d_dec.p,
+        k_subbox_decide<<<blocks_for(ntiles, 4), 128, 4 * (size_t)((p.n_decisions + 15u) & ~15u), c->stream>>>(
+            L, m->g, (const uint64_t*)m->d_prog.p, ntiles, p.n_decisions, (const uint8_t*)m->d_dec.p,
                                                                      (const int8_t*)m->d_tsign.p, (uint32_t*)m->d_sub.p,
                                                                      (unsigned long long*)m->d_counters.p + CN_SUB_BOXES_PROVEN);
         c->launches++;

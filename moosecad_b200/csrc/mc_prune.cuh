@@ -389,12 +389,14 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
 // subtrees whose bounding box is far from the tile are skipped warp-uniformly.
 // sub_masks[2 * tile] = sub-boxes proven negative, [2 * tile + 1] = proven positive.
 static __global__ void __launch_bounds__(128)
-k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles,
+k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint32_t n_dec,
                 const uint8_t* __restrict__ dec, const int8_t* __restrict__ tsign, uint32_t* __restrict__ sub_masks,
                 unsigned long long* __restrict__ sub_boxes_proven) {
+    extern __shared__ uint8_t s_pd_all[];  // the tiles' decisions, one slice per warp
     const uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ntiles) return;  // warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
+    uint8_t* s_pd = s_pd_all + (size_t)(threadIdx.x >> 5) * ((n_dec + 15u) & ~15u);
     const int sg = tsign[tile];
     if (sg != 0) {
         // the tile's sign is proven on its box plus one lattice step on every side (k_tile_decide),
@@ -408,8 +410,11 @@ k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64
     const uint32_t xa = bx > 0 ? bx - 1 : 0, ya = by > 0 ? by - 1 : 0, za = bz > 0 ? bz - 1 : 0;
     const double box[6] = {lat_x(L, min(xa, L.nx)), lat_x(L, min(bx + 8u, L.nx)), lat_y(L, min(ya, L.ny)),
                            lat_y(L, min(by + 4u, L.ny)), lat_z(L, min(za, L.nz)), lat_z(L, min(bz + 4u, L.nz))};
-    // the tile's own decisions hold on its box plus one step on every side, which contains `box`
-    const Ival r = vm_decide(prog, box, nullptr, 0, nullptr, dec + tile, (size_t)ntiles);
+    // the tile's own decisions hold on its box plus one step on every side, which contains `box`;
+    // they are gathered into shared memory once (the table is decision-major)
+    for (uint32_t i = lane; i < n_dec; i += 32u) s_pd[i] = dec[(size_t)i * ntiles + tile];
+    __syncwarp();
+    const Ival r = vm_decide(prog, box, nullptr, 0, nullptr, s_pd, 1);
     const unsigned neg = __ballot_sync(0xffffffffu, r.hi < 0.0), pos = __ballot_sync(0xffffffffu, r.lo > 0.0);
     if (lane == 0) {
         sub_masks[2 * tile] = neg;
