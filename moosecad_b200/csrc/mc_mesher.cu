@@ -441,26 +441,32 @@ static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, do
         return MC_OK;
     }
     if (ntiles >= (1ull << 31)) return fail(MC_ERR_LIMIT, std::string(who) + ": lattice too large");
-    DevBuf dprog, ddec, dsign, dcnt, dwork;
+    DevBuf dprog, ddec, dsign, dcnt, dwork, dsub;
+    const uint32_t sample = 4;  // sub-box proofs on every 4th tile are enough for a load estimate
     rc = upload_program(c, prog, dprog);
     if (rc == MC_OK) rc = c->alloc((size_t)prog.n_decisions * ntiles, ddec);
     if (rc == MC_OK) rc = c->alloc(ntiles + 4, dsign);
-    if (rc == MC_OK) rc = c->alloc(counts.size() * 8, dcnt);
+    if (rc == MC_OK) rc = c->alloc((counts.size() + 1) * 8, dcnt);  // + a scratch counter
     if (rc == MC_OK) rc = c->alloc((ntiles + 1) * 4, dwork);
+    if (rc == MC_OK) rc = c->alloc(ntiles * 8, dsub);
     cudaError_t e = cudaSuccess;
     if (rc == MC_OK) {
-        e = cudaMemsetAsync(dcnt.p, 0, counts.size() * 8, c->stream);
+        e = cudaMemsetAsync(dcnt.p, 0, (counts.size() + 1) * 8, c->stream);
         k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)dprog.p, ntiles,
                                                                       (uint8_t*)ddec.p, (int8_t*)dsign.p, (float*)dwork.p);
+        k_subbox_decide<<<blocks_for(ntiles, 4), 128, 4 * (size_t)((prog.n_decisions + 15u) & ~15u), c->stream>>>(
+            L, g, (const uint64_t*)dprog.p, ntiles, prog.n_decisions, (const uint8_t*)ddec.p, (const int8_t*)dsign.p,
+            (uint32_t*)dsub.p, (unsigned long long*)dcnt.p + counts.size(), sample);
         k_tile_layer_classes<<<blocks_for(ntiles, 256), 256, 0, c->stream>>>(
-            g, (const int8_t*)dsign.p, (const float*)dwork.p, ntiles, first, last,
+            g, (const int8_t*)dsign.p, (const float*)dwork.p, (const uint32_t*)dsub.p, sample, ntiles, first, last,
             (unsigned long long*)dcnt.p + (size_t)k_lo * MC_TILE_CLASS_STRIDE);
+        c->launches++;
         c->launches += 2;
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), dcnt.p, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     }
-    c->release(dprog); c->release(ddec); c->release(dsign); c->release(dcnt); c->release(dwork);
+    c->release(dprog); c->release(ddec); c->release(dsign); c->release(dcnt); c->release(dwork); c->release(dsub);
     if (rc != MC_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, who);
     return MC_OK;

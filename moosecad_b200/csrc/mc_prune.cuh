@@ -380,6 +380,13 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
     tsign[tc] = root.hi < 0.0 ? (int8_t)-1 : (root.lo > 0.0 ? (int8_t)1 : (int8_t)0);
 }
 
+// 1 / sample of the tiles, spread evenly (the load estimate looks at a sample of the sub-box proofs)
+__device__ __forceinline__ bool tile_sampled(const TileGrid& g, uint64_t tile, uint32_t sample) {
+    if (sample <= 1u) return true;
+    const uint32_t tix = (uint32_t)(tile % g.ntx), tiy = (uint32_t)((tile / g.ntx) % g.nty), tiz = (uint32_t)(tile / ((uint64_t)g.ntx * g.nty)) + g.z0 / TS;
+    return (tix + 2u * tiy + 3u * tiz) % sample == 0u;  // global tile coordinates: independent of the shard
+}
+
 // Sign proofs below the tile level: the 32 sub-boxes (8 x 4 x 4 points) of every tile whose sign is
 // not proven for its whole 27-neighbourhood.  One warp per tile, one sub-box per lane: an interval
 // evaluation of the program over the sub-box plus one lattice step on every side.  A definite
@@ -391,10 +398,11 @@ k_tile_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t
 static __global__ void __launch_bounds__(128)
 k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint32_t n_dec,
                 const uint8_t* __restrict__ dec, const int8_t* __restrict__ tsign, uint32_t* __restrict__ sub_masks,
-                unsigned long long* __restrict__ sub_boxes_proven) {
+                unsigned long long* __restrict__ sub_boxes_proven, uint32_t sample = 1u) {
     extern __shared__ uint8_t s_pd_all[];  // the tiles' decisions, one slice per warp
     const uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ntiles) return;  // warp-uniform
+    if (!tile_sampled(g, tile, sample)) return;  // load estimate: every sample-th tile only
     const uint32_t lane = threadIdx.x & 31u;
     uint8_t* s_pd = s_pd_all + (size_t)(threadIdx.x >> 5) * ((n_dec + 15u) & ~15u);
     const int sg = tsign[tile];
@@ -426,6 +434,7 @@ k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64
 // cost classes of the tiles per tile layer (see tile_layer_classes in mc_mesher.cu):
 // counts[layer * MC_TILE_CLASS_STRIDE + class], + 5: work of the class-0 tiles, + 6: of the shell tiles
 static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict__ tsign, const float* __restrict__ twork,
+                                            const uint32_t* __restrict__ sub_masks, uint32_t sample,
                                             uint64_t ntiles, uint32_t first, uint32_t last,
                                             unsigned long long* __restrict__ counts) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,8 +455,15 @@ static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict
     atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + cls], 1ull);
     // per-point work of the tile programs that are evaluated in full / on the shell only
     const unsigned long long wk = (unsigned long long)twork[t];
-    if (cls == 0) atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 5], wk);
-    else if (cls == 2 || cls == 4) atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 6], wk);
+    if (cls == 0) {
+        // work of the sub-boxes that stay unproven (from the sampled tiles, scaled up)
+        if (tile_sampled(g, t, sample)) {
+            const uint32_t un = (uint32_t)__popc(~(sub_masks[2 * t] | sub_masks[2 * t + 1]));
+            atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 5], wk * un * sample / 32ull);
+        }
+    } else if (cls == 2 || cls == 4) {
+        atomicAdd(&counts[(size_t)tiz * MC_TILE_CLASS_STRIDE + 6], wk);
+    }
 }
 
 // Block-cooperative compaction of the program for one tile into shared memory (s_prog), using the
