@@ -174,7 +174,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # host-valued bookkeeping (slab class table, per-slab counts) travels over a host group
-        host_group = dist.new_group(backend="gloo")
+        # (BENCH_HOST_GROUP=0: everything over NCCL)
+        host_group = dist.new_group(backend="gloo") if os.environ.get("BENCH_HOST_GROUP", "1") != "0" else None
     steps, warm = max(1, args.steps), max(3, args.warmup)
 
     stream = torch.cuda.Stream(device=dev)
@@ -229,8 +230,11 @@ def main():
         stage_acc = [0.0] * 9
         ev0.record(stream)
         last_counts = None
+        step_wall = []
         for _ in range(steps):
+            tw = time.perf_counter()
             h = one_step()
+            step_wall.append(round((time.perf_counter() - tw) * 1e3, 2))
             st = stage_ms(h)
             stage_acc = [a + b for a, b in zip(stage_acc, st)]
             last_counts = counts(h)
@@ -250,7 +254,7 @@ def main():
         stage_avg = [a / steps for a in stage_acc]
         # diagnostics (outside the timed region): every rank's own device time and host phases
         mine = {"rank": rank, "device_stage_ms_sum": round(sum(stage_avg), 3),
-                "host_ms_last_step": {k: round(v, 3) for k, v in host_ms.items()}}
+                "host_ms_last_step": {k: round(v, 3) for k, v in host_ms.items()}, "host_wall_ms_per_step": step_wall}
         per_rank = [mine]
         if world > 1:
             per_rank = [None] * world

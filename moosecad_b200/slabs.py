@@ -257,17 +257,17 @@ class SlabMesher:
             _lib.check(lib.mc_mesh_counts(out, counts))
             top_first, top_count = C.c_uint64(), C.c_uint64()
             _lib.check(lib.mc_mesh_upper_layer_vertices(out, C.byref(top_first), C.byref(top_count)))
-            # coordinates + bisection do not need the global bases: keep the device busy while the
-            # counts travel
-            _lib.check(lib.mc_tessellate_emit_vertices_local(out))
             extra = (top_first.value, top_count.value)
-            if self.world > 1:
-                if self.host_group is not None:
-                    self.all_counts = exchange_counts(counts[0], counts[1], self.host_group, "cpu", extra=extra)
-                else:
-                    self.all_counts = exchange_counts(counts[0], counts[1], self.group, self.device, side_stream=True,
-                                                      extra=extra)
-            else:
+            if self.world > 1 and self.host_group is None:
+                # device group: the stream is idle right after phase 1, the tiny all-gather is not
+                # queued behind anything
+                self.all_counts = exchange_counts(counts[0], counts[1], self.group, self.device, extra=extra)
+            # coordinates + bisection do not need the global bases
+            _lib.check(lib.mc_tessellate_emit_vertices_local(out))
+            if self.world > 1 and self.host_group is not None:
+                # host group: the device works on the vertices while the counts travel
+                self.all_counts = exchange_counts(counts[0], counts[1], self.host_group, "cpu", extra=extra)
+            elif self.world == 1:
                 self.all_counts = [(counts[0], counts[1]) + extra]
             self.vertex_base, self.tet_base = bases_from_counts(self.all_counts, self.rank)
             lap("exchange_counts")
