@@ -29,6 +29,7 @@ WORKLOADS = {
     "csg64_512": (64, 512),
     "csg64_256": (64, 256),
     "csg256_2048": (256, 2048),
+    "csg256_1024": (256, 1024),
     "csg16_64": (16, 64),
 }
 REL_ERR = 0.2  # --tessellation-error default, src/main.rs:48

@@ -187,6 +187,7 @@ mc_ctx* mc_ctx_new(int device, void* stream) {
     if (cudaSetDevice(device) != cudaSuccess) { fail(MC_ERR_CUDA, "mc_ctx_new: cudaSetDevice failed"); return nullptr; }
     mc_ctx* c = new mc_ctx();
     { const char* dbg = std::getenv("MC_DEBUG"); const int lvl = dbg ? std::atoi(dbg) : 0; c->debug = lvl == 1 || lvl == 2; c->debug_sync = lvl == 1 || lvl == 3; }
+    { const char* cap = std::getenv("MC_TILE_PROGRAM_CAP_WORDS"); if (cap && std::atoi(cap) > 0) c->tile_program_cap_words = (uint32_t)std::atoi(cap); }
     c->device = device;
     c->stream = (cudaStream_t)stream;
     cudaDeviceProp prop;
@@ -301,7 +302,11 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     const Program& p = m->prog;
     const uint32_t n_inst = (uint32_t)p.inst_start.size(), n_words = (uint32_t)p.words.size();
     if (n_inst >= 0xffffu || p.n_decisions == 0) return MC_OK;
-    const size_t smem = (size_t)n_words * 8 + ((p.n_decisions + 15u) & ~15u) + (size_t)(n_inst + 1) * 8;
+    // shared-memory budget of a tile-specialised program: long programs (hundreds of primitives)
+    // specialise to a small fraction of their length; the rare tile that does not fit evaluates the
+    // full program from global memory
+    const uint32_t cap_words = std::min<uint32_t>(n_words, c->tile_program_cap_words);
+    const size_t smem = (size_t)cap_words * 8 + ((p.n_decisions + 15u) & ~15u) + (size_t)(n_inst + 1) * 8;
     const size_t smem_cap = c->smem_optin ? c->smem_optin : 48 * 1024;
     if (smem > smem_cap) return MC_OK;
     const Lattice& L = m->L;
@@ -330,8 +335,11 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     }
     const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
     const bool small = p.small();
-    auto kern = count ? (small ? k_sdf_field_tiled<8, 4, true, true> : k_sdf_field_tiled<8, 4, true, false>)
-                      : (small ? k_sdf_field_tiled<8, 4, false, true> : k_sdf_field_tiled<8, 4, false, false>);
+    const bool capped = cap_words < n_words;
+    auto kern = capped ? (count ? (small ? k_sdf_field_tiled<8, 4, true, true, true> : k_sdf_field_tiled<8, 4, true, false, true>)
+                                : (small ? k_sdf_field_tiled<8, 4, false, true, true> : k_sdf_field_tiled<8, 4, false, false, true>))
+                       : (count ? (small ? k_sdf_field_tiled<8, 4, true, true, false> : k_sdf_field_tiled<8, 4, true, false, false>)
+                                : (small ? k_sdf_field_tiled<8, 4, false, true, false> : k_sdf_field_tiled<8, 4, false, false, false>));
     if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -341,7 +349,7 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     unsigned long long* pruned_total = (unsigned long long*)m->d_counters.p + CN_PRUNED_WORDS;
     kern<<<(unsigned)grid, 256, smem, c->stream>>>(L, m->g, (double*)m->d_phi.p, (const uint64_t*)m->d_prog.p,
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
-                                                   n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
+                                                   n_inst, cap_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
                                                    (const int8_t*)m->d_tsign.p, skip_uniform ? 1 : 0,
                                                    pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES,
                                                    (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS,
@@ -700,9 +708,12 @@ int mc_tessellate_emit_vertices_local(mc_mesh* m) {
         if (m->tiled_sdf && m->d_dec.p) {
             // the tile-specialised programs are valid on every lattice edge that starts in the tile
             const Program& p = m->prog;
-            const uint32_t n_inst = (uint32_t)p.inst_start.size(), n_words = (uint32_t)p.words.size();
+            const uint32_t n_inst = (uint32_t)p.inst_start.size();
+            const uint32_t n_words = std::min<uint32_t>((uint32_t)p.words.size(), c->tile_program_cap_words);
             const size_t smem = (size_t)n_words * 8 + ((p.n_decisions + 15u) & ~15u) + (size_t)(n_inst + 1) * 8;
-            auto kern = p.small() ? k_bisect_edges_tiled<true> : k_bisect_edges_tiled<false>;
+            const bool capped = n_words < (uint32_t)p.words.size();
+            auto kern = capped ? (p.small() ? k_bisect_edges_tiled<true, true> : k_bisect_edges_tiled<false, true>)
+                               : (p.small() ? k_bisect_edges_tiled<true, false> : k_bisect_edges_tiled<false, false>);
             if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<(unsigned)m->n_tiles, TILE_THREADS, smem, s>>>(
                 S, (const uint64_t*)m->d_prog.p, (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,

@@ -83,6 +83,7 @@ static MC_HD inline int mc_op_words(uint32_t op) {
 #define MC_DEC_FAIL 2   // guard fails at every point of the tile / boolean child can be dropped
 
 // evaluator limits (device local-memory stacks); the host lowering rejects deeper programs
+#define MC_TILE_PROGRAM_CAP_WORDS 4096u /* shared-memory budget of a tile-specialised program (32 KB) */
 #define MC_MAX_VALUE_DEPTH 48
 #define MC_MAX_POINT_DEPTH 6
 #define MC_MAX_PROGRAM_WORDS (1u << 22)

@@ -466,6 +466,13 @@ static __global__ void k_tile_layer_classes(TileGrid g, const int8_t* __restrict
     }
 }
 
+// Evaluation of the un-specialised program from global memory, out of line: the fallback for the
+// rare tile whose specialised program exceeds the shared-memory budget (same values by
+// construction).  All 32 lanes must call it.
+static __device__ __noinline__ double vm_eval_full_program(const uint64_t* __restrict__ prog, double x, double y, double z) {
+    return vm_eval<true>(prog, x, y, z);
+}
+
 // Block-cooperative compaction of the program for one tile into shared memory (s_prog), using the
 // tile's decisions.  All threads of the block must call it; it ends with the result visible to
 // the whole block once the caller has synchronised.  Returns the number of words via s_newpos[n_inst].
@@ -474,7 +481,7 @@ __device__ __forceinline__ void compact_tile_program(const uint64_t* __restrict_
                                                      const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                                                      uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
                                                      uint64_t tile, uint64_t* s_prog, uint8_t* s_dec, int* s_delta,
-                                                     uint32_t* s_newpos, uint32_t* s_scan) {
+                                                     uint32_t* s_newpos, uint32_t* s_scan, uint32_t cap_words) {
     const uint32_t tid = threadIdx.x;
     for (uint32_t i = tid; i < n_dec; i += blockDim.x) s_dec[i] = dec_g[(size_t)i * ntiles + tile];
     for (uint32_t i = tid; i <= n_inst; i += blockDim.x) s_delta[i] = 0;
@@ -532,7 +539,9 @@ __device__ __forceinline__ void compact_tile_program(const uint64_t* __restrict_
         run_pos += tot;
     }
     __syncthreads();
-    // 3. write the compacted program
+    // 3. write the compacted program (the caller evaluates the full program instead when it does
+    //    not fit the shared-memory budget: s_newpos[n_inst] > cap_words)
+    if (s_newpos[n_inst] > cap_words) return;
     for (uint32_t i = tid; i < n_inst; i += blockDim.x) {
         const uint32_t len = (uint32_t)s_delta[i];
         if (len == 0) continue;
@@ -608,8 +617,11 @@ __device__ __forceinline__ void compact_tile_program(const uint64_t* __restrict_
 }
 
 // per-tile compaction of the program into shared memory + evaluation of the tile's points
-// smem layout: [out program (max_words)] [dec (n_dec bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
-template <int WX, int WY, bool COUNT, bool SMALL>
+// smem layout: [out program (n_words = its capacity: the program's length, capped by the host)] [dec (n_dec
+// bytes, padded)] [delta int32 (n_inst+1)] [newpos u32 (n_inst+1)]
+// CAPPED: the program is longer than the shared-memory budget, a tile's specialised program may
+// not fit (the fallback code is compiled out otherwise)
+template <int WX, int WY, bool COUNT, bool SMALL, bool CAPPED>
 __global__ void __launch_bounds__(256, 4)
 k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uint64_t* __restrict__ prog,
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
@@ -659,8 +671,9 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
             }
         }
         compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta,
-                             s_newpos, s_scan);
+                             s_newpos, s_scan, n_words);
         if (tid == 0 && pruned_words_total) atomicAdd(pruned_words_total, (unsigned long long)s_newpos[n_inst]);
+        const bool fits = !CAPPED || s_newpos[n_inst] <= n_words;
         __syncthreads();
         // evaluate the tile: WX x WY points of one z-plane per warp step; the footprint of a step
         // lies in one sub-box
@@ -680,25 +693,30 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 }
             }
         }
-        // the other sub-boxes, four 8 x 4 warp steps each, dealt round-robin to the warps
+        // the other sub-boxes, four 8 x 4 warp steps each, dealt round-robin to the warps.  The loop is
+        // instantiated twice so that the hot one holds nothing but the inlined evaluator.
         const uint32_t unproven = ~(sub_neg | sub_pos);
         const uint32_t nsteps = 4u * (uint32_t)__popc(unproven);
-        for (uint32_t t = tid >> 5; t < nsteps; t += (blockDim.x >> 5)) {
-            const uint32_t sub = __fns(unproven, 0u, (int)(t >> 2) + 1);
-            const uint32_t lx = (sub & 1u) * 8u + lane % WX, ly = ((sub >> 1) & 3u) * 4u + lane / WX, lz = (sub >> 3) * 4u + (t & 3u);
-            const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-            if (Z > L.pz1) continue;  // warp-uniform
-            const bool inside = X < L.NX && Y < L.NY;
-            const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
-            unsigned long long fl = 0ull;
-            const double v = vm_eval_impl<true, COUNT, SMALL>(s_prog, lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
-            if (inside) {
-                phi_out[pidx(L, X, Y, Z)] = v;
-                my_flops += fl;
-                not_neg = not_neg || !(v < 0.0);
-                not_pos = not_pos || !(v > 0.0);
+        auto run = [&](auto eval) {
+            for (uint32_t t = tid >> 5; t < nsteps; t += (blockDim.x >> 5)) {
+                const uint32_t sub = __fns(unproven, 0u, (int)(t >> 2) + 1);
+                const uint32_t lx = (sub & 1u) * 8u + lane % WX, ly = ((sub >> 1) & 3u) * 4u + lane / WX, lz = (sub >> 3) * 4u + (t & 3u);
+                const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+                if (Z > L.pz1) continue;  // warp-uniform
+                const bool inside = X < L.NX && Y < L.NY;
+                const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
+                unsigned long long fl = 0ull;
+                const double v = eval(lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+                if (inside) {
+                    phi_out[pidx(L, X, Y, Z)] = v;
+                    my_flops += fl;
+                    not_neg = not_neg || !(v < 0.0);
+                    not_pos = not_pos || !(v > 0.0);
+                }
             }
-        }
+        };
+        if (CAPPED && !fits) run([&](double x, double y, double z, unsigned long long&) { return vm_eval_full_program(prog, x, y, z); });
+        else run([&](double x, double y, double z, unsigned long long& fl) { return vm_eval_impl<true, COUNT, SMALL>(s_prog, x, y, z, fl); });
         // sign summary of the tile (TF_NEG: every value < 0, TF_POS: every value > 0), the job of
         // k_tile_minmax on the untiled path
         const int any_not_neg = __syncthreads_or(not_neg ? 1 : 0), any_not_pos = __syncthreads_or(not_pos ? 1 : 0);
@@ -714,7 +732,7 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
 
 // a8 with the tile-specialised program: one block per tile that owns cut edges.  The tile's cut
 // edges are contiguous in the work list (vertex numbering is tile-major).
-template <bool SMALL>
+template <bool SMALL, bool CAPPED>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t* __restrict__ inst_start,
                      const uint16_t* __restrict__ word_inst, uint32_t n_inst, uint32_t n_words, uint32_t n_dec,
@@ -732,7 +750,8 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
     const uint64_t c0 = tile_cbase[tile], c1 = tile + 1 < ntiles ? tile_cbase[tile + 1] : ncut_total;
     if (c1 <= c0) return;
     compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta, s_newpos,
-                         s_scan);
+                         s_scan, n_words);
+    const bool fits = !CAPPED || s_newpos[n_inst] <= n_words;
     __syncthreads();
     const Lattice& L = S.L;
     const uint64_t per_plane = (uint64_t)L.NX * L.NY;
@@ -763,7 +782,8 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
         while (__any_sync(0xffffffffu, !done)) {
             const double mx = (ax + bx) * 0.5, my = (ay + by) * 0.5, mz = (az + bz) * 0.5;
             unsigned long long fl = 0ull;
-            const double phi = vm_eval_impl<true, false, SMALL>(s_prog, mx, my, mz, fl);
+            const double phi = (CAPPED && !fits) ? vm_eval_full_program(prog, mx, my, mz)
+                                                 : vm_eval_impl<true, false, SMALL>(s_prog, mx, my, mz, fl);
             if (!done) {
                 cx = mx; cy = my; cz = mz;
                 ++iters;

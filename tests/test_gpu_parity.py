@@ -237,6 +237,28 @@ def test_synthetic_csg_256_primitives(oracle, ctx):
     assert mesh.stats()["stats"] == om.stats()["stats"]
 
 
+def test_tile_program_over_the_shared_memory_budget(oracle, ctx):
+    """Tiles whose specialised program does not fit the 32 KB shared-memory budget evaluate the full
+    program from global memory instead (same values): 320 overlapping primitives on a lattice of
+    2 x 2 x 2 tiles, where every tile sees nearly the whole scene."""
+    g = mc.Geom()
+    root = scenes.synthetic_csg(g, 320, seed=7)
+    g.backend.set_parameters(0.1, 1.0)
+    res = 1.0 / 20
+    mesh = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_KEEP_PHI).tessellate()
+    pr = mesh.stats()["prune"]
+    assert pr["tiles"] > 0 and pr["full_words"] > 4096 and pr["avg_words"] > 4096, pr
+    go = mc.Geom(oracle.OracleScene())
+    ro = scenes.synthetic_csg(go, 320, seed=7)
+    ro.backend.set_parameters_node(ro.node, 0.1, 1.0)
+    om = ro.backend.tessellate(ro.node, res, 0.2)
+    canon.assert_same_mesh(canon.canonical(mesh.vertices(), mesh.elems()), canon.canonical(om.vertices(), om.elems()))
+    assert mesh.stats()["stats"] == om.stats()["stats"]
+    # bit-identical field against the un-specialised evaluator
+    ref = mc.IsosurfaceStuffing(root, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_NO_TILE_PRUNING | _lib.MC_OPT_KEEP_PHI).tessellate()
+    assert np.array_equal(mesh.phi().view(np.uint64), ref.phi().view(np.uint64))
+
+
 def _check_sidesets_against_point_eval(mesh, out, ctx):
     """Side-set membership recomputed from the boundary object's values at the surface nodes
     (mc_eval_points, a different kernel path) must reproduce the side-sets (src/main.rs:87-106)."""
