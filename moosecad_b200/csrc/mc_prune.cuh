@@ -194,7 +194,22 @@ __device__ __noinline__ Ival vm_decide(const uint64_t* __restrict__ w, const dou
                 if (dec && guarded) dec[(size_t)(dbase + (uint32_t)i) * dec_stride] = drop ? MC_DEC_FAIL : MC_DEC_KEEP;
                 if (!drop) { ++kept; e.lo = fmax(e.lo, pv[i].lo); e.hi = fmax(e.hi, pv[i].hi); }
             }
-            if (kept > 1) { e.hi += 0.25 * r * 1.791759469228055; e = widen(e); }  // smooth branch: <= max + r/4 ln 6
+            if (kept > 1) {
+                // smooth branch: rvmax <= r/4 ln sum exp(hi_i / (r/4)) over the kept planes (<= max + r/4 ln 6);
+                // the exact branch returns the max, which is below that too
+                double up = 0.25 * r * 1.791759469228055;
+                if (r > 0.0) {
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const bool drop = !((mask >> i) & 1u) || pv[i].hi <= ext - margin - pad_of(ext - margin);
+                        if (!drop) ssum += exp((pv[i].hi - e.hi) / (0.25 * r));
+                    }
+                    up = fmin(up, 0.25 * r * log(ssum));
+                }
+                e.hi += up;
+                e = widen(e);
+            }
             if (!guarded || pd == MC_DEC_PASS) {
                 if (alive) wk += 6.0f * (float)kept + (kept > 1 ? 30.0f * (float)(kept + 1) : 0.0f);
                 MC_IPUSH(e);
@@ -309,8 +324,22 @@ __device__ __noinline__ Ival vm_decide(const uint64_t* __restrict__ w, const dou
             }
             if (alive && kept > 1) wk += 30.0f * (float)(kept + 1);
             if (kept > 1) {
-                // smooth branch: rvmin in [min - r/4 ln k, min], rvmax in [max, max + r/4 ln k]
-                const double wdn = 0.25 * r * 1.3862943611198906 * (double)(kept <= 4 ? 1 : 2) * (kept <= 16 ? 1.0 : 2.5);
+                // smooth branch: rvmin = -r/4 ln sum exp(-x_i / (r/4)) over a subset of the kept children
+                // >= -r/4 ln sum exp(-lo_i / (r/4)) over all of them (>= min lo - r/4 ln k); the exact
+                // branch returns the min, which is above that too.  Mirror image for rvmax.  Written
+                // relative to the extremum of the bounds so that no term exceeds 1.
+                double wdn = 0.25 * r * 1.3862943611198906 * (double)(kept <= 4 ? 1 : 2) * (kept <= 16 ? 1.0 : 2.5);
+                if (r > 0.0) {
+                    double ssum = 0.0;
+                    for (int i = 0; i < k; ++i) {
+                        const Ival x = (i == k - 1) ? top : vs[base + i];
+                        bool drop;
+                        if (is_union) drop = x.lo >= ext + margin + pad_of(ext + margin);
+                        else drop = x.hi <= ext - margin - pad_of(ext - margin);
+                        if (!drop) ssum += is_union ? exp(-(x.lo - res.lo) / (0.25 * r)) : exp((x.hi - res.hi) / (0.25 * r));
+                    }
+                    wdn = fmin(wdn, 0.25 * r * log(ssum));
+                }
                 if (is_union) res.lo -= wdn; else res.hi += wdn;
                 res = widen(res);
             }
