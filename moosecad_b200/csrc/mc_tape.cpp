@@ -16,31 +16,6 @@ static const double INF = std::numeric_limits<double>::infinity();
 Box box_infinity() { return {{-INF, -INF, -INF}, {INF, INF, INF}}; }
 Box box_neg_infinity() { return {{INF, INF, INF}, {-INF, -INF, -INF}}; }
 
-static Box box_union(const Box& a, const Box& b) {
-    Box r;
-    for (int k = 0; k < 3; ++k) {
-        r.lo[k] = std::fmin(a.lo[k], b.lo[k]);
-        r.hi[k] = std::fmax(a.hi[k], b.hi[k]);
-    }
-    return r;
-}
-static Box box_intersection(const Box& a, const Box& b) {
-    Box r;
-    for (int k = 0; k < 3; ++k) {
-        r.lo[k] = std::fmax(a.lo[k], b.lo[k]);
-        r.hi[k] = std::fmin(a.hi[k], b.hi[k]);
-    }
-    return r;
-}
-static Box box_dilate(const Box& a, double d) {
-    Box r;
-    for (int k = 0; k < 3; ++k) {
-        r.lo[k] = a.lo[k] - d;
-        r.hi[k] = a.hi[k] + d;
-    }
-    return r;
-}
-
 Mat4 mat_identity() {
     Mat4 m;
     for (int i = 0; i < 4; ++i)
