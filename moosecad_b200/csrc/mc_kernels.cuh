@@ -939,11 +939,6 @@ static __device__ __forceinline__ void lattice_cell_quality(const Lattice& L, ui
     }
 }
 
-static __device__ __noinline__ void lattice_cell_quality_call(const Lattice& L, uint32_t cx, uint32_t cy, uint32_t cz,
-                                                              unsigned mult, QualityAcc& qa) {
-    lattice_cell_quality(L, cx, cy, cz, mult, qa);
-}
-
 // Interior tiles (every cell emits its five lattice tets, no vertex is warped): ids are pure
 // arithmetic, the tets of 256 cells at a time are staged in shared memory and written with
 // fully coalesced 16-byte stores.  Quality: an un-warped lattice tet only depends on the

@@ -88,5 +88,4 @@ static MC_HD inline int mc_op_words(uint32_t op) {
 #define MC_MAX_POINT_DEPTH 6
 #define MC_MAX_PROGRAM_WORDS (1u << 22)
 // lattice points evaluated per lane by the field kernels (shares instruction decode / dispatch)
-#define MC_POINTS_PER_LANE 1  // 2 was measured slower on B200: +registers, -occupancy (profiles/r01_notes.md)
 #define MC_MAX_DECISIONS 65535

@@ -1,5 +1,5 @@
 // Order-free device restatement of tessellate3d's isosurface stuffing:
-//   warp_vertices         tessellate3d/src/lib.rs:138-181   -> warp_eval / warped_pos
+//   warp_vertices         tessellate3d/src/lib.rs:138-181   -> k_warp_codes (mc_kernels.cuh) / warped_pos
 //   first-touch vertex id tessellate3d/src/lib.rs:114-124   -> first_touch_key
 //   trim_spikes           tessellate3d/src/lib.rs:242-367   -> classify_tet
 //   remove_exterior_tets  tessellate3d/src/lib.rs:370-398   -> exterior test inside classify_tet
@@ -60,90 +60,9 @@ static __device__ uint64_t first_touch_key(const Lattice& L, uint32_t X, uint32_
     return ~0ull;
 }
 
-// warp_vertices for one lattice vertex.  Returns 0 (not warped) or 1 + 2*dir + orient where
-// dir indexes C_DIR (the neighbour the winning edge leads to) and orient says whether the
-// vertex was node 0 (orient 0, `alpha < 0.3` branch) or node 1 (orient 1, `alpha > 0.7`
-// branch) of the winning edge visit.  Strict `<` keeps the FIRST minimal candidate in the
-// reference's visit order: tets in cut_lattice order, edges in Tet4::edge order.
-// cheap necessary condition for warp_eval != 0: some lattice edge at the vertex does not join two
-// vertices of the same strict sign
-__device__ __forceinline__ bool warp_candidate_possible(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
-    const double pv = raw_phi(L, X, Y, Z);
-    const bool even = ((X + Y + Z) & 1u) == 0u;
-    for (int d = 0; d < 18; ++d) {
-        if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
-        const int64_t wx = (int64_t)X + C_DIR[d][0], wy = (int64_t)Y + C_DIR[d][1], wz = (int64_t)Z + C_DIR[d][2];
-        if (wx < 0 || wy < 0 || wz < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
-        const double pw = raw_phi(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz);
-        if (!((pv > 0.0 && pw > 0.0) || (pv < 0.0 && pw < 0.0))) return true;
-    }
-    return false;
-}
-
-static __device__ uint32_t warp_eval(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
-    const double pv = raw_phi(L, X, Y, Z);
-    const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);
-    bool has = false;
-    double best = 0.0;
-    uint32_t code = 0u;
-    for (int ax = -1; ax <= 0; ++ax) {
-        const int64_t cx = (int64_t)X + ax;
-        if (cx < 0 || cx >= (int64_t)L.nx) continue;
-        for (int ay = -1; ay <= 0; ++ay) {
-            const int64_t cy = (int64_t)Y + ay;
-            if (cy < 0 || cy >= (int64_t)L.ny) continue;
-            for (int az = -1; az <= 0; ++az) {
-                const int64_t cz = (int64_t)Z + az;
-                if (cz < 0 || cz >= (int64_t)L.nz) continue;
-                const Cell c = make_cell((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-                const int k = corner_of(c, X, Y, Z);
-                for (int t = 0; t < 5; ++t) {
-                    int me = -1;  // my node index in the flipped tet
-#pragma unroll
-                    for (int n = 0; n < 4; ++n)
-                        if (tet_corner(c, t, n) == k) me = n;
-                    if (me < 0) continue;
-                    if (!tet_kept(L, c, t)) continue;
-                    for (int e = 0; e < 6; ++e) {
-                        const int i0 = C_EDGE[e][0], i1 = C_EDGE[e][1];
-                        if (i0 != me && i1 != me) continue;
-                        const int other = (i0 == me) ? i1 : i0;
-                        uint32_t WX, WY, WZ;
-                        corner_xyz(c, tet_corner(c, t, other), WX, WY, WZ);
-                        const double pw = raw_phi(L, WX, WY, WZ);
-                        const double phi0 = (i0 == me) ? pv : pw;
-                        const double phi1 = (i0 == me) ? pw : pv;
-                        if ((phi0 > 0.0 && phi1 > 0.0) || (phi0 < 0.0 && phi1 < 0.0)) continue;
-                        const double alpha = phi0 / (phi0 - phi1);
-                        // nalgebra::distance(x0, x1) = norm(x1 - x0); the squares make the sign moot
-                        const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
-                        double d;
-                        uint32_t orient;
-                        if (alpha < 0.3) {
-                            if (i0 != me) continue;  // candidate belongs to node 0
-                            d = alpha * sqrt((dx * dx + dy * dy) + dz * dz);
-                            orient = 0u;
-                        } else if (alpha > 1.0 - 0.3) {
-                            if (i1 != me) continue;  // candidate belongs to node 1
-                            d = (1.0 - alpha) * sqrt((dx * dx + dy * dy) + dz * dz);
-                            orient = 1u;
-                        } else {
-                            continue;
-                        }
-                        if (!has || d < best) {
-                            has = true;
-                            best = d;
-                            const int di = dir_index((int)WX - (int)X, (int)WY - (int)Y, (int)WZ - (int)Z);
-                            code = 1u + 2u * (uint32_t)di + orient;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    return has ? code : 0u;
-}
-
+// warp codes (k_warp_codes): 0 (not warped) or 1 + 2*dir + orient where dir indexes C_DIR (the
+// neighbour the winning edge leads to) and orient says whether the vertex was node 0 (orient 0,
+// `alpha < 0.3` branch) or node 1 (orient 1, `alpha > 0.7` branch) of the winning edge visit.
 // position after warp_vertices (tessellate3d/src/lib.rs:163,170,177): x += delta
 static __device__ void warped_pos(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z, double out[3]) {
     const double xv = lat_x(L, X), yv = lat_y(L, Y), zv = lat_z(L, Z);

@@ -338,260 +338,6 @@ __device__ __forceinline__ double vm_eval_impl(const uint64_t* __restrict__ w, d
 #undef MC_PUSH
 }
 
-
-// ---------------------------------------------------------------------------------------
-// NP lattice points per lane.  Fetching, decoding and dispatching an instruction costs far more
-// issue slots than its few FP64 operations, so the field kernels evaluate NP points per lane and
-// share that overhead (warp-uniform program counter over 32 * NP points).  Same arithmetic, same
-// order, per point, as vm_eval_impl.
-template <bool IS_UNION, bool COUNT, int NP>
-__device__ __forceinline__ double smooth_fold_strided(const double* __restrict__ vs, int base, int k, double top,
-                                                      double r, double exact_range, unsigned long long& flops) {
-    bool close = false;
-    double m = IS_UNION ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0xfff0000000000000LL);
-    for (int i = 0; i < k; ++i) {
-        const double x = (i == k - 1) ? top : vs[(base + i) * NP];
-        if (IS_UNION) {
-            if (x < m) { close = (m - x) < exact_range; m = x; }
-            else if ((x - m) < exact_range) close = true;
-        } else {
-            if (x > m) { close = (x - m) < exact_range; m = x; }
-            else if ((m - x) < exact_range) close = true;
-        }
-    }
-    if (COUNT) flops += 3ull * (unsigned)k;
-    if (!close) return m;
-    const double lim = IS_UNION ? (m + r) : (m - r);
-    const double r4 = r / 4.0;
-    double s = 0.0;
-    for (int i = 0; i < k; ++i) {
-        const double x = (i == k - 1) ? top : vs[(base + i) * NP];
-        if (IS_UNION) { if (x < lim) { s = s + mc_exp(-x / r4); if (COUNT) flops += 4 + MC_FLOPS_EXP; } }
-        else          { if (x > lim) { s = s + mc_exp(x / r4); if (COUNT) flops += 3 + MC_FLOPS_EXP; } }
-    }
-    if (COUNT) flops += 3 + MC_FLOPS_LOG;
-    return IS_UNION ? (mc_log(s) * -r4) : (mc_log(s) * r4);
-}
-
-template <int NP, bool COUNT>
-__device__ __noinline__ void vm_eval_multi(const uint64_t* __restrict__ w, const double* __restrict__ xin,
-                                           const double* __restrict__ yin, const double* __restrict__ zin,
-                                           double* __restrict__ out, unsigned long long& flops) {
-    double vs[(MC_MAX_VALUE_DEPTH + 1) * NP];  // element i of point p lives in vs[(i + 1) * NP + p]
-    double ps[3 * MC_MAX_POINT_DEPTH * NP];
-    double x[NP], y[NP], z[NP], top[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) { x[p] = xin[p]; y[p] = yin[p]; z[p] = zin[p]; top[p] = 0.0; }
-    int sp = 0, psp = 0, pc = 0;
-    unsigned long long allpass = 0ull;
-    const unsigned FULL = 0xffffffffu;
-#define MC_MPUSH(EXPR) do { _Pragma("unroll") for (int p = 0; p < NP; ++p) { vs[sp * NP + p] = top[p]; top[p] = (EXPR); } ++sp; } while (0)
-    for (;;) {
-        const uint64_t h = w[pc];
-        switch (MC_HDR_OP(h)) {
-        case MC_OP_END:
-#pragma unroll
-            for (int p = 0; p < NP; ++p) out[p] = top[p];
-            return;
-        case MC_OP_PLANE: {
-            const unsigned sm = MC_HDR_SMALL(h);
-            const unsigned axis = sm & 3u;
-            const double d = ld_f64(w, pc + 1);
-            const bool inverted = (sm & 4u) != 0;
-            double v[NP];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const double q = axis == 0 ? x[p] : (axis == 1 ? y[p] : z[p]);
-                const double ap = fabs(q);
-                const bool sign_positive = __double_as_longlong(q) >= 0;
-                v[p] = (sign_positive != inverted) ? (ap - d) : (-ap - d);
-            }
-            MC_MPUSH(v[p]);
-            if (COUNT) flops += 2 * NP;
-            pc += 2;
-            break;
-        }
-        case MC_OP_NPLANE: {
-            const double n0 = ld_f64(w, pc + 1), n1 = ld_f64(w, pc + 2), n2 = ld_f64(w, pc + 3), p0 = ld_f64(w, pc + 4);
-            MC_MPUSH(((x[p] * n0 + y[p] * n1) + z[p] * n2) - p0);
-            if (COUNT) flops += 6 * NP;
-            pc += 5;
-            break;
-        }
-        case MC_OP_USQ:
-            MC_MPUSH(((x[p] * x[p] + y[p] * y[p]) + z[p] * z[p]) - 1.0);
-            if (COUNT) flops += 6 * NP;
-            pc += 1;
-            break;
-        case MC_OP_CONE: {
-            const double sl = ld_f64(w, pc + 1), off = ld_f64(w, pc + 2), mul = ld_f64(w, pc + 3);
-            MC_MPUSH((sqrt(x[p] * x[p] + y[p] * y[p]) - fabs(sl * (z[p] + off))) * mul);
-            if (COUNT) flops += 9 * NP;
-            pc += 4;
-            break;
-        }
-        case MC_OP_GSPHERE:
-        case MC_OP_GCYL: {
-            const double slack = ld_f64(w, pc + 7);
-            double a[NP];
-            bool pass[NP], any = false;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) { a[p] = box_distance(w, pc + 1, x[p], y[p], z[p]); pass[p] = a[p] <= slack; any = any || pass[p]; }
-            if (__any_sync(FULL, any)) {
-                const double r = ld_f64(w, pc + 8);
-                const bool sph = MC_HDR_OP(h) == MC_OP_GSPHERE;
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double e = sph ? (sqrt((x[p] * x[p] + y[p] * y[p]) + z[p] * z[p]) - r) : (sqrt(x[p] * x[p] + y[p] * y[p]) - r);
-                    if (pass[p]) a[p] = e;
-                }
-                if (COUNT) flops += (sph ? 7 : 5) * NP;
-            }
-            if (COUNT) flops += 12 * NP;
-            MC_MPUSH(a[p]);
-            pc += 9;
-            break;
-        }
-        case MC_OP_GBOX: {
-            const double slack = ld_f64(w, pc + 7);
-            double a[NP];
-            bool pass[NP], any = false;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) { a[p] = box_distance(w, pc + 1, x[p], y[p], z[p]); pass[p] = a[p] <= slack; any = any || pass[p]; }
-            if (COUNT) flops += 12 * NP;
-            if (__any_sync(FULL, any)) {
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double e = box_fold<COUNT>(w, pc + 8, MC_HDR_SMALL(h), x[p], y[p], z[p], flops);
-                    if (pass[p]) a[p] = e;
-                }
-            }
-            MC_MPUSH(a[p]);
-            pc += 16;
-            break;
-        }
-        case MC_OP_BOX: {
-            double e[NP];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) e[p] = box_fold<COUNT>(w, pc + 1, MC_HDR_SMALL(h), x[p], y[p], z[p], flops);
-            MC_MPUSH(e[p]);
-            pc += 9;
-            break;
-        }
-        case MC_OP_GAPUSH:
-        case MC_OP_GUARD: {
-            const double slack = ld_f64(w, pc + 7);
-            double a[NP];
-            bool all = true, any = false;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) { a[p] = box_distance(w, pc + 1, x[p], y[p], z[p]); const bool ps_ = a[p] <= slack; all = all && ps_; any = any || ps_; }
-            const unsigned level = MC_HDR_LEVEL(h);
-            if (COUNT) flops += 12 * NP;
-            if (!__any_sync(FULL, any)) { MC_MPUSH(a[p]); pc = (int)MC_HDR_IDX(h); break; }
-            if (level < 64u) {
-                if (__all_sync(FULL, all)) allpass |= (1ull << level);
-                else allpass &= ~(1ull << level);
-            }
-            pc += 8;
-            if (MC_HDR_OP(h) == MC_OP_GUARD) break;
-            pc -= 1;
-        }
-        // fallthrough
-        case MC_OP_APUSH: {
-            const double m0 = ld_f64(w, pc + 1), m1 = ld_f64(w, pc + 2), m2 = ld_f64(w, pc + 3), m3 = ld_f64(w, pc + 4);
-            const double m4 = ld_f64(w, pc + 5), m5 = ld_f64(w, pc + 6), m6 = ld_f64(w, pc + 7), m7 = ld_f64(w, pc + 8);
-            const double m8 = ld_f64(w, pc + 9), m9 = ld_f64(w, pc + 10), m10 = ld_f64(w, pc + 11), m11 = ld_f64(w, pc + 12);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                ps[(psp + 0) * NP + p] = x[p]; ps[(psp + 1) * NP + p] = y[p]; ps[(psp + 2) * NP + p] = z[p];
-                const double nx = ((m0 * x[p] + m1 * y[p]) + m2 * z[p]) + m3;
-                const double ny = ((m4 * x[p] + m5 * y[p]) + m6 * z[p]) + m7;
-                const double nz = ((m8 * x[p] + m9 * y[p]) + m10 * z[p]) + m11;
-                x[p] = nx; y[p] = ny; z[p] = nz;
-            }
-            psp += 3;
-            if (COUNT) flops += 18 * NP;
-            pc += 13;
-            break;
-        }
-        case MC_OP_ENDG: {
-            const unsigned level = MC_HDR_LEVEL(h);
-            if (level >= 64u || !((allpass >> level) & 1ull)) {
-                const int g = (int)MC_HDR_IDX(h);
-                const double slack = ld_f64(w, g + 7);
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double a = box_distance(w, g + 1, x[p], y[p], z[p]);
-                    if (!(a <= slack)) top[p] = a;
-                }
-                if (COUNT) flops += 12 * NP;
-            }
-            pc += 1;
-            break;
-        }
-        case MC_OP_NEG:
-#pragma unroll
-            for (int p = 0; p < NP; ++p) top[p] = -top[p];
-            if (COUNT) flops += NP;
-            pc += 1;
-            break;
-        case MC_OP_CHILD:
-            pc += 1;
-            break;
-        case MC_OP_BOXDIST:
-            MC_MPUSH(box_distance(w, pc + 1, x[p], y[p], z[p]));
-            if (COUNT) flops += 11 * NP;
-            pc += 7;
-            break;
-        case MC_OP_SPHERE: {
-            const double r = ld_f64(w, pc + 1);
-            MC_MPUSH(sqrt((x[p] * x[p] + y[p] * y[p]) + z[p] * z[p]) - r);
-            if (COUNT) flops += 7 * NP;
-            pc += 2;
-            break;
-        }
-        case MC_OP_CYL: {
-            const double r = ld_f64(w, pc + 1);
-            MC_MPUSH(sqrt(x[p] * x[p] + y[p] * y[p]) - r);
-            if (COUNT) flops += 5 * NP;
-            pc += 2;
-            break;
-        }
-        case MC_OP_BOOL: {
-            const unsigned sm = MC_HDR_SMALL(h);
-            const int k = (int)(sm & 0x7fu);
-            const double r = ld_f64(w, pc + 1);
-            const double er = ld_f64(w, pc + 2);
-            const int base = sp - k + 1;
-#pragma unroll
-            for (int p = 0; p < NP; ++p)
-                top[p] = (sm & 0x80u) ? smooth_fold_strided<true, COUNT, NP>(vs + p, base, k, top[p], r, er, flops)
-                                      : smooth_fold_strided<false, COUNT, NP>(vs + p, base, k, top[p], r, er, flops);
-            sp -= k - 1;
-            pc += 3;
-            break;
-        }
-        case MC_OP_APOP: {
-            psp -= 3;
-            const double sc = ld_f64(w, pc + 1);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                x[p] = ps[(psp + 0) * NP + p]; y[p] = ps[(psp + 1) * NP + p]; z[p] = ps[(psp + 2) * NP + p];
-                top[p] = top[p] * sc;
-            }
-            if (COUNT) flops += NP;
-            pc += 2;
-            break;
-        }
-        default:
-#pragma unroll
-            for (int p = 0; p < NP; ++p) out[p] = __longlong_as_double(0x7ff8000000000000LL);
-            return;
-        }
-    }
-#undef MC_MPUSH
-}
-
 template <bool UNIFORM>
 __device__ __forceinline__ double vm_eval(const uint64_t* __restrict__ w, double x, double y, double z) {
     unsigned long long unused = 0ull;
