@@ -294,14 +294,12 @@ int compute_boundary(mc_mesh* m) {
     const Lattice& L = m->L;
     if (m->c0 != 0 || m->c1 != L.nz)
         return fail(MC_ERR_UNSUPPORTED, "Mesh::boundary on a z-slab: gather the slabs on one device first");
-    static bool table_ready = false;
     {
+        // per call: constant memory is per device, and the upload is a few hundred bytes
         FaceTri tab[6][2];
         build_cellface_table(tab);
         MC_CUDA(cudaMemcpyToSymbolAsync(C_CELLFACE, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
-        table_ready = true;
     }
-    (void)table_ready;
     cudaEvent_t e0, e1;
     MC_CUDA(cudaEventCreate(&e0));
     MC_CUDA(cudaEventCreate(&e1));

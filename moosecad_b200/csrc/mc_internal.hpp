@@ -31,6 +31,7 @@ struct mc_ctx {
     uint64_t held_bytes = 0;
 
     uint32_t tile_program_cap_words = MC_TILE_PROGRAM_CAP_WORDS;  // env MC_TILE_PROGRAM_CAP_WORDS overrides (tuning)
+    bool tet_emit_attr_set = false;     // cudaFuncSetAttribute for k_tet_emit done on this device
     bool debug = false, debug_sync = false;  // MC_DEBUG=1: poison allocations + check every stage (2: poison, 3: checks)
 
     int alloc(size_t bytes, mc::DevBuf& out);          // pool allocation (+ poison fill in debug mode)

@@ -840,15 +840,13 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     if (rc != MC_OK) return rc;
     const Stuff S = make_stuff(m);
     const bool quality = !(m->flags & MC_OPT_SKIP_QUALITY);
-    {
-        static bool attr_set = false;
-        if (!attr_set) {
-            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
-            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
-            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
-            MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
-            attr_set = true;
-        }
+    if (!c->tet_emit_attr_set) {
+        // per context (= per device): opt in to the dynamic shared memory of the surface-tile emission
+        MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
+        MC_CUDA(cudaFuncSetAttribute(k_tet_emit<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<uint32_t>()));
+        MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
+        MC_CUDA(cudaFuncSetAttribute(k_tet_emit<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tet_emit_smem_bytes<unsigned long long>()));
+        c->tet_emit_attr_set = true;
     }
     MC_CUDA(cudaEventRecord(m->ev[8], s));
     if (m->n_tets > 0) {
