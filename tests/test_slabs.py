@@ -155,3 +155,14 @@ def test_sharded_load_estimate_matches_whole(ctx):
     dim = slabs.lattice_dim(root.bbox(), res)
     direct = slabs.layer_costs(ctx, root, res)
     assert np.allclose(direct, slabs.costs_from_classes(whole, dim[2]), rtol=1e-12, atol=0.0)
+
+
+def test_combine_stats():
+    """Per-slab statistics add up (counters) / combine by hull (aspect-ratio range)."""
+    a = {"ntets_stage": [10, 8, 9], "stats": [1, 0, 2, 0, 0, 3, 0], "aspect_ratio": [0.5, 0.9], "inverted": 1}
+    b = {"ntets_stage": [5, 5, 5], "stats": [0, 1, 0, 0, 4, 0, 0], "aspect_ratio": [0.4, 0.8], "inverted": 0}
+    c = slabs.combine_stats([a, b])
+    assert c == {"ntets_stage": [15, 13, 14], "stats": [1, 1, 2, 0, 4, 3, 0], "aspect_ratio": [0.4, 0.9], "inverted": 1}
+    # the reference starts the range at (one, zero) (tessellate3d/src/lib.rs:404): an empty slab is neutral
+    empty = {"ntets_stage": [0, 0, 0], "stats": [0] * 7, "aspect_ratio": [1.0, 0.0], "inverted": 0}
+    assert slabs.combine_stats([a, empty]) == slabs.combine_stats([a])
