@@ -190,7 +190,8 @@ int mc_tessellate_begin(mc_ctx*, const mc_tape* volume, int32_t root, double res
  * (exclusive scan of mc_mesh_counts()[0] over the ranks; 0 on one GPU).  Afterwards
  * mc_mesh_upper_plane_table() is valid. */
 int mc_tessellate_emit_vertices(mc_mesh*, uint64_t vertex_base);
-/* Optional, between phases 1 and 2: launch the part of phase 2 that does not need vertex_base
+/* (slab plumbing: no reference counterpart)
+ * Optional, between phases 1 and 2: launch the part of phase 2 that does not need vertex_base
  * (coordinates + bisection) and return without waiting.  A multi-rank caller issues it before
  * the blocking exchange of the counts, so the device works while the ranks wait for each other. */
 int mc_tessellate_emit_vertices_local(mc_mesh*);
@@ -199,7 +200,9 @@ int mc_tessellate_emit_vertices_local(mc_mesh*);
  * z = z_begin produced by the rank below (its mc_mesh_upper_plane_table), or NULL for the
  * first slab. */
 int mc_tessellate_emit_tets(mc_mesh*, uint64_t tet_base, const void* d_lower_plane);
-/* Optional, before phase 3 on a slab with z_begin > 0: the coordinates of the rank below's top
+/* (slab plumbing: no reference counterpart; the statistics themselves are
+ * check_for_inverted_tets, tessellate3d/src/lib.rs:400-418)
+ * Optional, before phase 3 on a slab with z_begin > 0: the coordinates of the rank below's top
  * tile layer (its mc_mesh_upper_layer_coords; `count` vertices with global ids starting at
  * first_global_id = its vertex_base + its first_local), so that check_for_inverted_tets can also
  * evaluate the trimmed tets that touch the shared plane.  Without it those tets are left out of
