@@ -24,23 +24,43 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n_primitives, cells per axis)
+    # name: (n_primitives, cells per axis) — the synthetic CSG scenes of BASELINE configs 4 and 5
     "csg64_1024": (64, 1024),
     "csg64_512": (64, 512),
     "csg64_256": (64, 256),
     "csg256_2048": (256, 2048),
     "csg256_1024": (256, 1024),
     "csg16_64": (16, 64),
+    # name: (script, cells per axis, tessellation error) — BASELINE configs 2 and 3
+    "sphere_256": ("sphere", 256, 0.2),
+    "xplicit_512": ("xplicit", 512, 0.8),   # 0.8: with the default 0.2 the reference's cut_edge never terminates
 }
 REL_ERR = 0.2  # --tessellation-error default, src/main.rs:48
 
 
+def workload_desc(name):
+    w = WORKLOADS[name]
+    if isinstance(w[0], int):
+        return (f"synthetic {w[0]}-primitive smooth CSG scene (numpy default_rng({w[0]})), {w[1]}^3-cell lattice, "
+                f"tessellation error {REL_ERR}")
+    return f"examples/{w[0]}.lua, {w[1]}^3-cell lattice, tessellation error {w[2]}"
+
+
 def build_scene(geom_factory, name):
-    from moosecad_b200 import scenes
-    nprim, n = WORKLOADS[name]
-    g = geom_factory()
-    root = scenes.synthetic_csg(g, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
-    return g, root, 1.0 / n, n
+    """-> (backend owner, volume object, resolution, cells per axis, relative error)"""
+    from moosecad_b200 import luascad, scenes
+    w = WORKLOADS[name]
+    if isinstance(w[0], int):
+        nprim, n = w
+        g = geom_factory()
+        root = scenes.synthetic_csg(g, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
+        return g, root, 1.0 / n, n, REL_ERR
+    script, n, err = w
+    backend = geom_factory().backend
+    out = luascad.eval({"sphere": scenes.SPHERE_LUA, "xplicit": scenes.XPLICIT_LUA}[script], backend=backend)
+    root = [o.volume() for _, o in sorted(out.items()) if o.volume() is not None][0]
+    bb = root.bbox()
+    return root, root, (bb[3] - bb[0]) / n, n, err
 
 
 class ClockSampler:
@@ -94,33 +114,56 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_sample(name, seconds_hint=15.0):
-    """The oracle (C++ restatement of the reference's serial Rust path) timed on the host, one
-    core, on a bounded sample: the SAME scene on a coarser lattice."""
+def _oracle_scene(name):
     import moosecad_b200 as mc
     from oracle import pyoracle
-    pyoracle.set_libm_mode(0)  # the reference calls the platform libm
-    nprim, _ = WORKLOADS[name]
-    n = 40 if nprim <= 64 else 24
-    from moosecad_b200 import scenes
-    go = mc.Geom(pyoracle.OracleScene())
-    root = scenes.synthetic_csg(go, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
+    g, root, res, n, err = build_scene(lambda: mc.Geom(pyoracle.OracleScene()), name)
     root.backend.set_parameters_node(root.node, 0.1, 1.0)
-    t0 = time.perf_counter()
-    om = root.backend.tessellate(root.node, 1.0 / n, REL_ERR)
-    dt = time.perf_counter() - t0
-    pyoracle.set_libm_mode(1)
-    pts = (n + 1) ** 3
+    return root, res, n, err
+
+
+def cpu_sample_cells(name):
+    """Cells per axis of the bounded CPU sample of a workload (about 5 s of single-core work)."""
+    w = WORKLOADS[name]
+    if isinstance(w[0], int):
+        return min(w[1], 40 if w[0] <= 64 else 24)
+    return min(w[1], 96 if w[0] == "sphere" else 48)
+
+
+def cpu_baseline_sample(name, cells=None):
+    """The oracle (C++ restatement of the reference's serial Rust path, platform libm) timed on the
+    host, one core, on a bounded sample: the SAME scene on a coarser lattice (`cells` per axis).
+    The per-point cost of the reference depends on the resolution (far-field points are cheap, the
+    surface fraction scales as 1/N): profiles/r02_cpu_baseline_*.json holds the measured curve."""
+    from oracle import pyoracle
+    pyoracle.set_libm_mode(0)  # the reference calls the platform libm
+    try:
+        root, res_full, n_full, err = _oracle_scene(name)
+        n = cells or cpu_sample_cells(name)
+        res = res_full * n_full / n
+        t0 = time.perf_counter()
+        om = root.backend.tessellate(root.node, res, err)
+        dt = time.perf_counter() - t0
+        st = om.stats()
+    finally:
+        pyoracle.set_libm_mode(1)
+    dim = st["dim"]
+    pts = (dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1)
     nt = len(om.elems())
     return {"value": pts / dt, "unit": "lattice pts/s", "cores": 1, "kind": "port",
-            "sample": f"same scene ({nprim} primitives) on a {n}^3-cell lattice, {pts} lattice points, "
-                      f"{nt} tets, {dt:.2f} s; serial like the reference (no threads in tessellate3d/mesh/main)",
-            "tets_per_s": nt / dt, "seconds": dt, "host_cores_available": os.cpu_count()}
+            "sample": f"same scene on a {n}^3-cell lattice ({pts} lattice points, {nt} tets, {dt:.2f} s) instead of "
+                      f"{n_full}^3; serial like the reference (no threads in tessellate3d / mesh / main)",
+            "sample_cells_per_axis": n, "same_config": n == n_full,
+            "tets_per_s": nt / dt, "seconds": dt, "stage_s": {k: round(v, 4) for k, v in st["times"].items()},
+            "value_calls_per_point": st["n_value_calls"] / pts, "host_cores_available": os.cpu_count()}
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust reference
-    cannot be built here (no toolchain, un-vendored crates), so this times the oracle port."""
+    cannot be built here (no toolchain, un-vendored crates), so this times the oracle port, each step
+    on a bounded sample (the same scene on a coarser lattice: `config.sample_cells_per_axis`,
+    `same_config` false).  A throughput measured on the sample is NOT the throughput the reference
+    would reach on the full lattice."""
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
@@ -131,14 +174,15 @@ def run_reference(args, rank, world):
             vals.append(last)
     secs = sum(v["seconds"] for v in vals) / len(vals)
     v = sum(v["value"] for v in vals) / len(vals)
-    nprim, n = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "lattice_points_per_s", "value": v, "unit": "lattice pts/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": secs * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {nprim}-primitive smooth CSG scene, {n}^3-cell lattice "
-                                   f"(each step: bounded sample, see cpu_baseline.sample)"},
-            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_desc(args.workload) + " — each step a bounded sample: the same scene on a "
+                                   f"{last['sample_cells_per_axis']}^3-cell lattice",
+                       "sample_cells_per_axis": last["sample_cells_per_axis"], "same_config": last["same_config"]},
+            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_cells_per_axis",
+                                                  "same_config", "stage_s")},
             "e2e": {"value": v, "unit": "lattice pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "tets_per_s": sum(x["tets_per_s"] for x in vals) / len(vals)}
     print(json.dumps(line), flush=True)
@@ -183,10 +227,11 @@ def main():
     lib = _lib.lib()
     with torch.cuda.stream(stream):
         ctx = mc.Context(local_rank, stream.cuda_stream)
-        g, root, res, n = build_scene(mc.Geom, args.workload)
+        g, root, res, n, rel_err = build_scene(mc.Geom, args.workload)
         g.backend.set_parameters(0.1, 1.0)
         info = g.backend.program_info(root.node, res)
-        P_total = (n + 1) ** 3
+        dim = slabs.lattice_dim(root.bbox(), res)
+        P_total = (dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1)
 
         def barrier():
             if world > 1:
@@ -196,7 +241,7 @@ def main():
         host_ms = {}
 
         def one_step(flags=0):
-            sm = slabs.SlabMesher(ctx, root, res, REL_ERR, rank, world, None, dev, flags=flags, host_group=host_group)
+            sm = slabs.SlabMesher(ctx, root, res, rel_err, rank, world, None, dev, flags=flags, host_group=host_group)
             h = sm.run()
             host_ms.update(sm.host_ms)
             return h
@@ -232,19 +277,32 @@ def main():
         ev0.record(stream)
         last_counts = None
         step_wall = []
-        for _ in range(steps):
+        for i in range(steps):
             tw = time.perf_counter()
             h = one_step()
             step_wall.append(round((time.perf_counter() - tw) * 1e3, 2))
             st = stage_ms(h)
             stage_acc = [a + b for a, b in zip(stage_acc, st)]
             last_counts = counts(h)
-            lib.mc_mesh_free(h)
+            if i < steps - 1:
+                lib.mc_mesh_free(h)
         ev1.record(stream)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         ms_total = ev0.elapsed_time(ev1)
         launches = ctx.launch_count - launches0
+        # identity of the mesh (outside the timed region): order- and numbering-independent device
+        # checksums of the last step's mesh, summed over the slabs mod 2^64 — equal for every N
+        from moosecad_b200.tessellate3d import mesh_checksum
+        my_cs = mesh_checksum(h)
+        lib.mc_mesh_free(h)
+        all_cs = [my_cs]
+        if world > 1:
+            all_cs = [None] * world
+            dist.all_gather_object(all_cs, my_cs)
+        checksum = {"vertices": "%016x" % (sum(c["vertices"] for c in all_cs) % (1 << 64)),
+                    "tets": "%016x" % (sum(c["tets"] for c in all_cs) % (1 << 64)),
+                    "tets_skipped": sum(c["tets_skipped"] for c in all_cs)}
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         cnt = torch.tensor(last_counts[:2] + [launches], dtype=torch.int64, device=dev)
         if world > 1:
@@ -275,9 +333,9 @@ def main():
             a0.record(stream)
             h2d = 0
             for _ in range(e_steps):
-                g2, root2, _, _ = build_scene(mc.Geom, args.workload)     # scene lowering from host data
+                g2, root2, _, _, _ = build_scene(mc.Geom, args.workload)     # scene lowering from host data
                 g2.backend.set_parameters(0.1, 1.0)
-                sm = slabs.SlabMesher(ctx, root2, res, REL_ERR, rank, world, None, dev)
+                sm = slabs.SlabMesher(ctx, root2, res, rel_err, rank, world, None, dev, host_group=host_group)
                 h = sm.run()
                 ib = C.c_int()
                 lib.mc_mesh_device_views(h, None, None, C.byref(ib))
@@ -336,15 +394,14 @@ def main():
                      "unit": "GB/s", "frac": bytes_alg / (stuff_ms * 1e-3) / 1e9 / hbm_peak if stuff_ms > 0 else None,
                      "algorithmic_bytes": bytes_alg, "ms": stuff_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}
-            nprim, _ = WORKLOADS[args.workload]
             line = {"metric": "lattice_points_per_s", "value": P_total / (ms_step * 1e-3), "unit": "lattice pts/s",
                     "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                     "data": "synthetic",
-                    "config": {"workload": f"synthetic {nprim}-primitive smooth CSG scene "
-                                           f"(numpy default_rng({nprim})), {n}^3-cell lattice, "
-                                           f"tessellation error {REL_ERR}, {'z-slabs over %d GPUs' % world if world > 1 else 'single GPU'}",
+                    "config": {"workload": workload_desc(args.workload) + ", " +
+                                           ("z-slabs over %d GPUs" % world if world > 1 else "single GPU"),
                                "lattice_points": P_total, "output_vertices": n_verts, "output_tets": n_tets,
+                               "mesh_checksum": checksum,
                                "l2": "working set (>= 8 B x lattice points per array) is far larger than the 126 MB L2; no flush needed",
                                "tape_words": info["words"]},
                     "tets_per_s": n_tets / (ms_step * 1e-3),
@@ -365,7 +422,16 @@ def main():
             except (OSError, ValueError):
                 pass
             if not args.no_cpu_baseline and world == 1:
-                line["cpu_baseline"] = cpu_baseline_sample(args.workload)
+                # bounded samples of the same scene: ~5 s and (csg64) ~25 s of single-core work
+                cb = cpu_baseline_sample(args.workload)
+                sizes = [{k: cb[k] for k in ("sample_cells_per_axis", "value", "tets_per_s", "seconds", "stage_s")}]
+                if args.workload.startswith("csg64"):
+                    c2 = cpu_baseline_sample(args.workload, 64)
+                    sizes.append({k: c2[k] for k in ("sample_cells_per_axis", "value", "tets_per_s", "seconds", "stage_s")})
+                cb["sizes"] = sizes
+                cb["note"] = ("throughput on a coarser lattice of the same scene; the measured dependence on the lattice "
+                              "size is in profiles/r02_cpu_baseline_*.json (N = 40..256)")
+                line["cpu_baseline"] = cb
             print(json.dumps(line), flush=True)
         del ctx
     if world > 1:

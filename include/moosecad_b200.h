@@ -103,6 +103,10 @@ int mc_tape_bbox(const mc_tape*, int32_t node, double out_bbox[6]);
 int mc_tape_program_info(const mc_tape*, int32_t root, double slack, uint64_t* words,
                          int32_t* value_depth, int32_t* point_depth, uint64_t* flops_per_point);
 
+/* content hash of that program and the root bounding box (everything the device sees of the
+ * scene): equal scenes lowered twice hash alike.  Key of the slab-partition cache (slabs.py). */
+int mc_tape_program_hash(const mc_tape*, int32_t root, double slack, uint64_t* hash);
+
 /* ------------------------------------------------------------------------------------
  * Device context.
  * ------------------------------------------------------------------------------------ */
@@ -134,7 +138,8 @@ int mc_eval_points_device(mc_ctx*, const mc_tape*, int32_t root, double slack,
  * ------------------------------------------------------------------------------------ */
 typedef struct mc_slab {
     /* z-slab sharding: this call meshes cell layers [z_begin, z_end) of the
-     * global lattice.  {0, 0} means the whole lattice (single GPU). */
+     * global lattice.  A NULL mc_slab pointer means the whole lattice (single GPU); an empty
+     * range (z_begin == z_end) is a legitimate slab that owns nothing. */
     uint64_t z_begin, z_end;
 } mc_slab;
 
@@ -261,8 +266,19 @@ int mc_mesh_device_views(mc_mesh*, void** d_coords, void** d_tets, int* index_by
 /* copy into caller-provided HOST buffers (pinned or pageable): coords = 3*nv doubles,
  * tets = 4*nt entries of index_bytes (4 or 8) each */
 int mc_mesh_copy_to_host(mc_mesh*, double* coords, void* tets, int index_bytes);
-/* the lattice SDF field (MC_OPT_KEEP_PHI): (dim+1)^3 doubles, x fastest, z slowest */
+/* the lattice SDF field: (dim+1)^3 doubles, x fastest, z slowest.  Needs MC_OPT_KEEP_PHI (or a run
+ * that evaluated every point: MC_OPT_NO_TILE_PRUNING / a tiny program); otherwise most entries
+ * are +-1 placeholders of the proven sign and the call fails with MC_ERR_STATE. */
 int mc_mesh_copy_phi(mc_mesh*, double* out, uint64_t n);
+
+/* (test / measurement plumbing: no reference counterpart; SURVEY.md 8c "cheap order-independent
+ * parity probes")  Order- and numbering-independent 64-bit checksums of the emitted mesh, computed on
+ * the device: out[0] = sum over the vertices of H(x, y, z bit patterns), out[1] = sum over the tets of
+ * H(the four vertex hashes, rotated by the even permutation that sorts them first), both mod 2^64 and
+ * therefore additive over the slabs of one lattice; out[2] = tets left out because a node's
+ * coordinates are not on this device (0 unless a slab was emitted without mc_tessellate_set_lower_coords);
+ * out[3] = 0.  tests/canon.py holds the numpy mirror that is applied to the oracle's mesh. */
+int mc_mesh_checksum(mc_mesh*, uint64_t out[4]);
 
 /* ------------------------------------------------------------------------------------
  * Mesh::boundary() (mesh/src/lib.rs:341-357; src/main.rs:86) and the side-set loop

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mc_tape_set_parameters": (C.c_int, [_P, _D, _D]),
     "mc_tape_bbox": (C.c_int, [_P, _I32, _PD]),
     "mc_tape_program_info": (C.c_int, [_P, _I32, _D, _PU64, _PI32, _PI32, _PU64]),
+    "mc_tape_program_hash": (C.c_int, [_P, _I32, _D, _PU64]),
     "mc_ctx_new": (_P, [C.c_int, _P]),
     "mc_ctx_free": (None, [_P]),
     "mc_ctx_device": (C.c_int, [_P]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "mc_mesh_device_views": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int)]),
     "mc_mesh_copy_to_host": (C.c_int, [_P, _P, _P, C.c_int]),
     "mc_mesh_copy_phi": (C.c_int, [_P, _PD, _U64]),
+    "mc_mesh_checksum": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary_sides": (_PU64, [_P]),
     "mc_mesh_add_sideset": (C.c_int, [_P, _P, _I32]),

@@ -259,4 +259,30 @@ int mc_tape_program_info(const mc_tape* t, int32_t root, double slack, uint64_t*
     return MC_OK;
 }
 
+int mc_tape_program_hash(const mc_tape* t, int32_t root, double slack, uint64_t* hash) {
+    if (!t || !hash) return fail(MC_ERR_ARG, "mc_tape_program_hash: bad argument");
+    Program p;
+    std::string err;
+    int rc = t->compile(root, slack, p, err);
+    if (rc != MC_OK) return fail(rc, err);
+    // content hash of everything the device sees: the program words and the root bounding box
+    auto mix = [](uint64_t x) {
+        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+        x ^= x >> 27; x *= 0x94d049bb133111ebull;
+        x ^= x >> 31;
+        return x;
+    };
+    uint64_t h = 0x9e3779b97f4a7c15ull + p.words.size();
+    for (uint64_t w : p.words) h = mix(h + w);
+    const Box& bb = t->nodes[(size_t)root].bbox;
+    for (int k = 0; k < 3; ++k) {
+        uint64_t lo, hi;
+        std::memcpy(&lo, &bb.lo[k], 8);
+        std::memcpy(&hi, &bb.hi[k], 8);
+        h = mix(mix(h + lo) + hi);
+    }
+    *hash = h;
+    return MC_OK;
+}
+
 }  // extern "C"

@@ -557,7 +557,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     L.ox = bb.lo[0]; L.oy = bb.lo[1]; L.oz = bb.lo[2];
     L.res = resolution;
     uint64_t zb = 0, ze = dim[2];
-    if (slab && !(slab->z_begin == 0 && slab->z_end == 0)) { zb = slab->z_begin; ze = slab->z_end; }
+    if (slab) { zb = slab->z_begin; ze = slab->z_end; }  // NULL = the whole lattice; an empty range owns nothing
     if (zb > ze || ze > dim[2]) { delete m; return fail(MC_ERR_ARG, "mc_tessellate_begin: bad slab range"); }
     m->c0 = (uint32_t)zb; m->c1 = (uint32_t)ze;
     const uint32_t nz = L.nz;
@@ -1105,6 +1105,9 @@ int mc_mesh_copy_phi(mc_mesh* m, double* out, uint64_t n) {
     if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_copy_phi: bad argument");
     const uint64_t have = (uint64_t)m->L.NX * m->L.NY * (m->L.pz1 - m->L.pz0 + 1);
     if (n != have) return fail(MC_ERR_ARG, "mc_mesh_copy_phi: expected " + std::to_string(have) + " values");
+    if (m->tiled_sdf && !(m->flags & MC_OPT_KEEP_PHI))
+        return fail(MC_ERR_STATE, "mc_mesh_copy_phi: the field holds sign placeholders where the sign was proven; "
+                                  "tessellate with MC_OPT_KEEP_PHI to read it");
     MC_CUDA(cudaSetDevice(m->ctx->device));
     MC_CUDA(cudaMemcpyAsync(out, m->d_phi.p, n * 8, cudaMemcpyDeviceToHost, m->ctx->stream));
     MC_CUDA(cudaStreamSynchronize(m->ctx->stream));

@@ -106,6 +106,13 @@ class Tape:
         return {"words": words.value, "value_depth": vd.value, "point_depth": pd.value, "flops": flops.value}
 
 
+    def program_hash(self, node, slack):
+        """Content hash of the device program for (node, slack) and the node's bounding box."""
+        h = C.c_uint64()
+        _lib.check(self._lib.mc_tape_program_hash(self.handle, node, slack, C.byref(h)))
+        return h.value
+
+
 class LObject:
     """``luascad::geom::LObject``: a handle to one node of the scene (luascad/src/lib.rs:84-86)."""
 

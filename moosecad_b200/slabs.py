@@ -198,6 +198,31 @@ def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=No
     return costs_from_classes(t.cpu().numpy(), dim[2])
 
 
+_partition_cache = {}
+
+
+def cached_partition(ctx, obj, resolution, rank, world, group=None, device=None, host_group=None):
+    """Balanced z-slab partition of (scene, resolution, world), computed once per process: the load
+    estimate is a deterministic function of the scene's device program, so the key is its content
+    hash (a scene lowered again from the same script hits the cache).  Every rank must call it in
+    the same order (the first call for a key runs one collective)."""
+    res = float(resolution)
+    key = (obj.backend.program_hash(obj.node, res), res, int(world))
+    slabs = _partition_cache.get(key)
+    if slabs is None:
+        slabs = partition_balanced(layer_costs_sharded(ctx, obj, res, rank, world, group, device, host_group), world)
+        _partition_cache[key] = slabs
+    return slabs
+
+
+def _ctx_stream(ctx, device):
+    """The torch view of the CUDA stream a Context launches on."""
+    import torch
+    if getattr(ctx, "stream", 0):
+        return torch.cuda.ExternalStream(ctx.stream, device=device)
+    return torch.cuda.default_stream(device)
+
+
 class SlabMesher:
     """Meshes this rank's slab of the global lattice.  Usage (every rank):
 
@@ -221,10 +246,9 @@ class SlabMesher:
         import time
         t0 = time.perf_counter()
         if self.world > 1 and balanced:
-            # the estimate is deterministic, every rank derives the same partition
-            self.slabs = partition_balanced(layer_costs_sharded(ctx, obj, self.res, self.rank, self.world, group, device,
-                                                                host_group),
-                                            self.world)
+            # the estimate is deterministic, every rank derives the same partition; it is computed
+            # once per (scene, resolution, world) and cached
+            self.slabs = cached_partition(ctx, obj, self.res, self.rank, self.world, group, device, host_group)
         else:
             self.slabs = partition(self.dim[2], self.world)
         self.host_ms["partition"] = (time.perf_counter() - t0) * 1e3
@@ -291,8 +315,13 @@ class SlabMesher:
                     recv = torch.empty(n, dtype=torch.int64, device=self.device)
                     below = self.all_counts[self.rank - 1]
                     recv_xyz = torch.empty(3 * below[3], dtype=torch.float64, device=self.device)
-                exchange_plane_tables(send, recv, self.rank, self.world, self.group, send_coords=send_xyz,
-                                      recv_coords=recv_xyz)
+                # The table / coordinate copies above were queued on the CONTEXT's stream and the tet
+                # emission below reads the received table on it, while the NCCL point-to-point ops order
+                # against torch's CURRENT stream: make the context's stream current for the exchange,
+                # whatever stream the caller is on.
+                with torch.cuda.stream(_ctx_stream(self.ctx, self.device)):
+                    exchange_plane_tables(send, recv, self.rank, self.world, self.group, send_coords=send_xyz,
+                                          recv_coords=recv_xyz)
                 if recv is not None:
                     lower = C.c_void_p(recv.data_ptr())
                     vb_below, _ = bases_from_counts(self.all_counts, self.rank - 1)

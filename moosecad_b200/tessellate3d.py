@@ -26,6 +26,7 @@ class Context:
         if not self.handle:
             raise _lib.McError(_lib.MC_ERR_CUDA, _lib.last_error())
         self.device = int(device)
+        self.stream = int(stream) if stream else 0   # cudaStream_t the context launches on (0 = legacy default)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -238,6 +239,11 @@ class Mesh:
                 "points_evaluated": counts[2], "points_owned": counts[3], "n_cut": counts[4],
                 "n_warped": counts[5], "stage_ms": list(ms)}
 
+    def checksum(self):
+        """Order- and numbering-independent checksums of the emitted mesh, computed on the device
+        (C ABI mc_mesh_checksum): {"vertices": u64, "tets": u64, "tets_skipped": n}."""
+        return mesh_checksum(self.handle)
+
     def phi(self):
         """The lattice SDF field, shape (nz+1, ny+1, nx+1)."""
         d = self.stats()["dim"]
@@ -245,6 +251,13 @@ class Mesh:
         out = np.empty(shape, dtype=np.float64)
         _lib.check(self._lib.mc_mesh_copy_phi(self.handle, out.ctypes.data_as(_lib._PD), out.size))
         return out
+
+
+def mesh_checksum(handle):
+    """mc_mesh_checksum for a raw mc_mesh handle."""
+    out = (C.c_uint64 * 4)()
+    _lib.check(_lib.lib().mc_mesh_checksum(handle, out))
+    return {"vertices": int(out[0]), "tets": int(out[1]), "tets_skipped": int(out[2])}
 
 
 class IsosurfaceStuffing:
