@@ -315,10 +315,10 @@ int compute_boundary(mc_mesh* m) {
     const Stuff S = make_stuff(m);
     if (m->n_tiles > 0) {
         k_face_count<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)ftot.p);
-        k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)ftot.p, m->n_tiles, (unsigned long long*)fbase.p,
-                                        nullptr, totals);
-        c->launches += 2;
+        c->launches += 1;
         MC_CUDA(cudaGetLastError());
+        rc = scan_tiles(c, ftot.p, m->n_tiles, fbase.p, nullptr, m->d_scan_sums.p, totals);
+        if (rc != MC_OK) return rc;
         unsigned long long h[2];
         MC_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, s));
         MC_CUDA(cudaStreamSynchronize(s));

@@ -65,6 +65,8 @@ struct mc_mesh {
     bool vertices_local_done = false;  // mc_tessellate_emit_vertices_local has run
     mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
     mc::DevBuf d_inst_start, d_word_inst, d_dec;  // tile specialisation (mc_prune.cuh)
+    mc::DevBuf d_scan_sums;                       // block sums of the tile scans (k_scan_tiles_local / _add)
+    mc::DevBuf d_tile_list;                       // tiles the SDF kernel evaluates (the others are proven)
     uint64_t n_tiles = 0;
     double avg_pruned_words = 0;
 
@@ -101,6 +103,8 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // upload a compiled program into a pooled device buffer
 int upload_program(mc_ctx* ctx, const Program& p, DevBuf& out);
+// exclusive scan of packed per-tile totals (mc_mesher.cu)
+int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base_hi, void* sums, void* totals);
 // boundary + side-sets implementation (mc_boundary.cu)
 int compute_boundary(mc_mesh* m);
 int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, std::vector<uint64_t>& out);

@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_SDF_LIST, CN_SDF_NEXT, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -114,7 +114,9 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31u) == 0u && v) atomicAdd(s_acc, v);
     __syncthreads();
-    return *s_acc;
+    const unsigned long long r = *s_acc;
+    __syncthreads();  // s_acc may be reset by the next call
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -187,8 +189,9 @@ __device__ __forceinline__ void stage_points(const Lattice& L, uint32_t X0, uint
             const uint32_t Xc = (uint32_t)min(max(X, (int64_t)0), (int64_t)L.NX - 1), Yc = (uint32_t)min(max(Y, (int64_t)0), (int64_t)L.NY - 1);
             const uint32_t Zc = (uint32_t)min(max(Z, (int64_t)L.pz0), (int64_t)L.pz1);
             const size_t pi = pidx(L, Xc, Yc, Zc);
-            v[u] = L.phi[pi];
-            wc[u] = WCODE ? L.wcode[pi] : (uint8_t)0;
+            const int8_t ts = tile_sign_at(L, Xc, Yc, Zc);  // proven tile: nothing stored, the sign is all there is
+            v[u] = ts ? (double)ts : L.phi[pi];
+            wc[u] = (WCODE && !ts) ? L.wcode[pi] : (uint8_t)0;
         }
 #pragma unroll
         for (int u = 0; u < B; ++u) {
@@ -230,10 +233,16 @@ k_tile_minmax(Stuff S) {
     }
 }
 
-// point tiles: 27-neighbourhood uniformly negative / positive?
+// point tiles: uniformly negative / positive together with everything one lattice step around them?
+// Either the interval pass proved it (tile sign: the proof covers the tile's box grown by one step),
+// or the stored values say so for the whole 27-neighbourhood of tiles.
 static __global__ void k_tile_neighbourhood(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
+    if (S.L.tsign != nullptr && S.L.tsign[t] != 0) {
+        S.vuni[t] = S.L.tsign[t] < 0 ? VU_NEG : VU_POS;
+        return;
+    }
     const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
     uint8_t all = TF_NEG | TF_POS;
     for (int dz = -1; dz <= 1; ++dz)
@@ -280,6 +289,13 @@ static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long
 constexpr int WT_STRIDE = 97;  // [count, 96 entries] per parity class
 constexpr int WP_STRIDE = 37;  // [count, <= 36 distinct (direction, orientation) pairs in first-visit order]
 constexpr int8_t SG_NEG = -1, SG_ZERO = 0, SG_POS = 1, SG_NONE = 2, SG_NAN = 3;
+// C_DIR as compile-time constants: unrolled neighbour scans get immediate shared-memory offsets
+struct KDir { int x, y, z; };
+__host__ __device__ constexpr KDir kdir(int d) {
+    constexpr int T[18][3] = {{1, 0, 0},  {0, 1, 0},  {0, 0, 1},  {1, 1, 0},   {-1, 1, 0}, {1, 0, 1},  {-1, 0, 1}, {0, 1, 1},  {0, -1, 1},
+                              {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {-1, 0, -1}, {1, 0, -1}, {0, -1, -1}, {0, 1, -1}};
+    return KDir{T[d][0], T[d][1], T[d][2]};
+}
 
 static __global__ void __launch_bounds__(TILE_THREADS)
 k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
@@ -316,7 +332,8 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
 #pragma unroll
             for (int d = 0; d < 18; ++d) {
                 if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
-                const int sw = s_sg[me + (C_DIR[d][2] * H + C_DIR[d][1]) * H + C_DIR[d][0]];
+                const KDir kd = kdir(d);
+                const int sw = s_sg[me + (kd.z * H + kd.y) * H + kd.x];
                 if (sw != SG_NONE && !((sv == SG_POS || sv == SG_NEG) && sw == sv)) any = true;
             }
             if (any) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
@@ -343,7 +360,13 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
         auto candidate = [&](uint32_t d, uint32_t o) {
             const uint32_t WX = X + C_DIR[d][0], WY = Y + C_DIR[d][1], WZ = Z + C_DIR[d][2];
             const double pw = L.phi[pidx(L, WX, WY, WZ)];
-            const double alpha = o == 0u ? pv / (pv - pw) : pw / (pw - pv);
+            // Cheap exact pre-test: the ends differ in sign class, so alpha = num / t lies in [0, 1]
+            // (or is NaN).  |num| > 0.3000001 |t| means the rounded quotient is certainly >= 0.3
+            // (o = 0; mirror for o = 1: certainly <= 0.7), i.e. no candidate — most edges stop here,
+            // before the division and the square root.  NaN / inf make the comparison false.
+            const double t = o == 0u ? pv - pw : pw - pv;
+            if (o == 0u ? fabs(pv) > 0.3000001 * fabs(t) : fabs(pw) < 0.6999999 * fabs(t)) return;
+            const double alpha = o == 0u ? pv / t : pw / t;
             const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
             double dd;
             if (o == 0u) {
@@ -527,79 +550,81 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
 }
 
 // ---------------------------------------------------------------------------------------
-// exclusive scan of per-tile totals (one block).  Entries pack two 32-bit counters; the low
-// halves are scanned into base_lo, the high halves into base_hi (either may be null);
-// totals[0] / totals[1] receive the sums.
-static __global__ void __launch_bounds__(1024)
-k_scan_tiles(const unsigned long long* __restrict__ tot, uint64_t n, unsigned long long* __restrict__ base_lo,
-             unsigned long long* __restrict__ base_hi, unsigned long long* __restrict__ totals) {
-    __shared__ unsigned long long s_w[2][32];
-    __shared__ unsigned long long s_carry[2];
-    if (threadIdx.x == 0) { s_carry[0] = 0ull; s_carry[1] = 0ull; }
-    __syncthreads();
+// exclusive scan of per-tile totals in two launches.  Entries pack two 32-bit counters; the low
+// halves are scanned into base_lo, the high halves into base_hi (either may be null); totals[0] /
+// totals[1] receive the sums.
+//   k_scan_tiles_local: every block scans SCAN_BLOCK entries in place (block-local prefixes) and
+//                       writes its pair of sums to block_sums
+//   k_scan_tiles_add:   every block adds the sums of the blocks before it (<= a few hundred values,
+//                       summed by the block itself: no third launch, no look-back spinning)
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles_local(const unsigned long long* __restrict__ tot, uint64_t n, unsigned long long* __restrict__ base_lo,
+                   unsigned long long* __restrict__ base_hi, unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long s_w[2][SCAN_THREADS / 32];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    for (uint64_t start = 0; start < n; start += 1024) {
-        const uint64_t i = start + threadIdx.x;
-        const unsigned long long e = i < n ? tot[i] : 0ull;
-        unsigned long long v[2] = {e & 0xffffffffull, e >> 32};
-        unsigned long long inc[2] = {v[0], v[1]};
+    const uint64_t first = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v0[SCAN_ITEMS], v1[SCAN_ITEMS], a0 = 0ull, a1 = 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long n0 = __shfl_up_sync(0xffffffffu, inc[0], o);
-            const unsigned long long n1 = __shfl_up_sync(0xffffffffu, inc[1], o);
-            if (lane >= (unsigned)o) { inc[0] += n0; inc[1] += n1; }
-        }
-        if (lane == 31u) { s_w[0][wid] = inc[0]; s_w[1][wid] = inc[1]; }
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long w0 = s_w[0][lane], w1 = s_w[1][lane];
-            unsigned long long i0 = w0, i1 = w1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long n0 = __shfl_up_sync(0xffffffffu, i0, o);
-                const unsigned long long n1 = __shfl_up_sync(0xffffffffu, i1, o);
-                if (lane >= (unsigned)o) { i0 += n0; i1 += n1; }
-            }
-            s_w[0][lane] = i0 - w0;
-            s_w[1][lane] = i1 - w1;
-        }
-        __syncthreads();
-        const unsigned long long ex0 = s_carry[0] + s_w[0][wid] + inc[0] - v[0];
-        const unsigned long long ex1 = s_carry[1] + s_w[1][wid] + inc[1] - v[1];
-        if (i < n) {
-            if (base_lo) base_lo[i] = ex0;
-            if (base_hi) base_hi[i] = ex1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) { s_carry[0] = ex0 + v[0]; s_carry[1] = ex1 + v[1]; }
-        __syncthreads();
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const unsigned long long e = first + i < n ? tot[first + i] : 0ull;
+        v0[i] = a0; v1[i] = a1;           // exclusive prefix inside the thread
+        a0 += e & 0xffffffffull; a1 += e >> 32;
     }
-    if (threadIdx.x == 0) { totals[0] = s_carry[0]; totals[1] = s_carry[1]; }
+    unsigned long long i0 = a0, i1 = a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n0 = __shfl_up_sync(0xffffffffu, i0, o), n1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= (unsigned)o) { i0 += n0; i1 += n1; }
+    }
+    if (lane == 31u) { s_w[0][wid] = i0; s_w[1][wid] = i1; }
+    __syncthreads();
+    unsigned long long w0 = 0ull, w1 = 0ull, t0 = 0ull, t1 = 0ull;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < (int)wid) { w0 += s_w[0][w]; w1 += s_w[1][w]; }
+        t0 += s_w[0][w]; t1 += s_w[1][w];
+    }
+    const unsigned long long ex0 = w0 + i0 - a0, ex1 = w1 + i1 - a1;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (first + i < n) {
+            if (base_lo) base_lo[first + i] = ex0 + v0[i];
+            if (base_hi) base_hi[first + i] = ex1 + v1[i];
+        }
+    if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = t0; block_sums[2 * blockIdx.x + 1] = t1; }
+}
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles_add(uint64_t n, unsigned long long* __restrict__ base_lo, unsigned long long* __restrict__ base_hi,
+                 const unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long s_acc;
+    // sums of the blocks before this one (block 0 also produces the grand totals)
+    unsigned long long p0 = 0ull, p1 = 0ull, g0 = 0ull, g1 = 0ull;
+    for (unsigned q = threadIdx.x; q < gridDim.x; q += SCAN_THREADS) {
+        const unsigned long long b0 = block_sums[2 * q], b1 = block_sums[2 * q + 1];
+        if (q < blockIdx.x) { p0 += b0; p1 += b1; }
+        g0 += b0; g1 += b1;
+    }
+    p0 = block_sum(p0, &s_acc);
+    p1 = block_sum(p1, &s_acc);
+    if (blockIdx.x == 0) {
+        g0 = block_sum(g0, &s_acc);
+        g1 = block_sum(g1, &s_acc);
+        if (threadIdx.x == 0) { totals[0] = g0; totals[1] = g1; }
+    }
+    if (blockIdx.x == 0) return;  // nothing to add
+    const uint64_t first = (uint64_t)blockIdx.x * SCAN_BLOCK;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)SCAN_BLOCK; i += SCAN_THREADS)
+        if (first + i < n) {
+            if (base_lo) base_lo[first + i] += p0;
+            if (base_hi) base_hi[first + i] += p1;
+        }
 }
 
 // ---------------------------------------------------------------------------------------
 // a10 (vertices), pass 1: for every owned lattice vertex decide whether it is in the output
 // and which of its nine owned edges carry a cut vertex.  Tile totals: low = output vertices,
 // high = cut edges.
-__device__ __forceinline__ uint16_t vertex_mask(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
-    const size_t pi = pidx(L, X, Y, Z);
-    const uint8_t wc = L.wcode[pi];
-    const double pv = (wc & 0x7f) ? 0.0 : L.phi[pi];
-    uint16_t m = 0;
-    if (pv < 0.0 || (pv == 0.0 && (wc & 0x80))) m |= VM_USED;
-    if (pv != 0.0) {
-        const bool even = ((X + Y + Z) & 1u) == 0u;
-        const int nd = even ? 9 : 3;
-        for (int s = 0; s < nd; ++s) {
-            const int64_t wx = (int64_t)X + C_DIR[s][0], wy = (int64_t)Y + C_DIR[s][1], wz = (int64_t)Z + C_DIR[s][2];
-            if (wx < 0 || wy < 0 || wx > (int64_t)L.nx || wy > (int64_t)L.ny || wz > (int64_t)L.nz) continue;
-            const double pw = warped_phi(L, pidx(L, (uint32_t)wx, (uint32_t)wy, (uint32_t)wz));
-            if ((pv > 0.0 && pw < 0.0) || (pv < 0.0 && pw > 0.0)) m |= (uint16_t)(1u << s);
-        }
-    }
-    return m;
-}
-
 // owned points of a tile: x, y extents and the owned z range [zlo, zhi) (may be empty)
 struct TileBox { uint32_t X0, Y0, Z0, nxt, nyt, zlo, zhi; };
 __device__ __forceinline__ TileBox tile_box(const Stuff& S, uint64_t t) {
@@ -649,7 +674,8 @@ k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
 #pragma unroll
             for (int s = 0; s < 9; ++s) {
                 if (s >= nd) break;
-                if (s_cl[me + (C_DIR[s][2] * H + C_DIR[s][1]) * H + C_DIR[s][0]] == want) m |= (uint16_t)(1u << s);
+                const KDir kd = kdir(s);
+                if (s_cl[me + (kd.z * H + kd.y) * H + kd.x] == want) m |= (uint16_t)(1u << s);
             }
         }
         S.vmask[pidx(L, X, Y, Z)] = m;
@@ -697,12 +723,24 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
     if (vu == VU_POS || b.zhi == b.zlo) return;
     const uint64_t vb = S.tvbase[blockIdx.x];
     if (vu == VU_NEG) {
-        // every owned point is an un-warped output vertex: id = tile base + linear index
+        // every owned point is an un-warped output vertex: id = tile base + linear index.  256
+        // vertices at a time go through shared memory so that the xyz triples leave as three fully
+        // coalesced stores per thread instead of 24-byte strided ones.
+        __shared__ double s_xyz[3 * TILE_THREADS];
         const uint32_t n = b.nxt * b.nyt * (b.zhi - b.zlo);
-        for (uint32_t j = threadIdx.x; j < n; j += TILE_THREADS) {
-            const uint32_t x = j % b.nxt, y = (j / b.nxt) % b.nyt, z = j / (b.nxt * b.nyt);
-            double* o = coords + 3 * (vb + j);
-            o[0] = lat_x(L, b.X0 + x); o[1] = lat_y(L, b.Y0 + y); o[2] = lat_z(L, b.zlo + z);
+        for (uint32_t base = 0; base < n; base += TILE_THREADS) {
+            const uint32_t j = base + threadIdx.x;
+            if (j < n) {
+                const uint32_t x = j % b.nxt, y = (j / b.nxt) % b.nyt, z = j / (b.nxt * b.nyt);
+                s_xyz[3 * threadIdx.x] = lat_x(L, b.X0 + x);
+                s_xyz[3 * threadIdx.x + 1] = lat_y(L, b.Y0 + y);
+                s_xyz[3 * threadIdx.x + 2] = lat_z(L, b.zlo + z);
+            }
+            __syncthreads();
+            const uint32_t m3 = 3u * min((uint32_t)TILE_THREADS, n - base);
+            double* o = coords + 3 * (vb + base);
+            for (uint32_t e = threadIdx.x; e < m3; e += TILE_THREADS) o[e] = s_xyz[e];
+            __syncthreads();
         }
         return;
     }

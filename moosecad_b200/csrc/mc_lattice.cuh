@@ -22,6 +22,11 @@ struct Lattice {
     double res;
     const double* __restrict__ phi;  // SDF at lattice points (pre-warp), x fastest, z slowest
     uint8_t* wcode;                  // bits 0..6 warp code (0 = not warped), bit 7 = zero-vertex used
+    // Proven sign per 16^3 tile (+-1, 0 = not proven), or null.  The SDF kernel writes NOTHING into phi
+    // for a proven tile: only the sign of such a point is ever needed (DESIGN.md "Points nobody
+    // reads") and every reader that can meet one asks phi_at() / sign tables instead of the array.
+    const int8_t* __restrict__ tsign;
+    uint32_t tntx, tnty;             // tile grid (x, y) of tsign; z origin is pz0
 };
 
 // The lattice is processed in tiles of TS^3 points; tile (i,j,k) also names the TS^3 CELLS whose
@@ -43,6 +48,15 @@ __device__ __forceinline__ void tile_origin(const TileGrid& g, uint64_t t, uint3
 
 __device__ __forceinline__ size_t pidx(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
     return ((size_t)(Z - L.pz0) * L.NY + Y) * L.NX + X;
+}
+// SDF value at a lattice point as far as any consumer may look at it: the stored value, or +-1 in a
+// tile whose sign is proven (nothing is stored there)
+__device__ __forceinline__ int8_t tile_sign_at(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    return L.tsign ? L.tsign[(((Z - L.pz0) / TS) * L.tnty + Y / TS) * L.tntx + X / TS] : (int8_t)0;
+}
+__device__ __forceinline__ double phi_at(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    const int8_t s = tile_sign_at(L, X, Y, Z);
+    return s ? (double)s : L.phi[pidx(L, X, Y, Z)];
 }
 // tessellate3d/src/lib.rs:84-103: (i as f64) * resolution + origin, per component
 __device__ __forceinline__ double lat_x(const Lattice& L, uint32_t X) { return (double)X * L.res + L.ox; }

@@ -103,6 +103,22 @@ static void build_warp_table(std::vector<unsigned long long>& tab) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+// exclusive scan of n packed per-tile totals (k_scan_tiles_local / _add); `sums` holds 2 words per SCAN_BLOCK entries
+int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base_hi, void* sums, void* totals) {
+    if (n == 0) {
+        MC_CUDA(cudaMemsetAsync(totals, 0, 16, c->stream));
+        return MC_OK;
+    }
+    const unsigned nb = blocks_for(n, SCAN_BLOCK);
+    k_scan_tiles_local<<<nb, SCAN_THREADS, 0, c->stream>>>((const unsigned long long*)tot, n, (unsigned long long*)base_lo,
+                                                           (unsigned long long*)base_hi, (unsigned long long*)sums);
+    k_scan_tiles_add<<<nb, SCAN_THREADS, 0, c->stream>>>(n, (unsigned long long*)base_lo, (unsigned long long*)base_hi,
+                                                         (const unsigned long long*)sums, (unsigned long long*)totals);
+    c->launches += 2;
+    MC_CUDA(cudaGetLastError());
+    return MC_OK;
+}
+
 }  // namespace mc
 
 // ---- pooled device memory ---------------------------------------------------------------
@@ -167,7 +183,7 @@ static void mesh_release_all(mc_mesh* m) {
                       &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
                       &m->d_tflag, &m->d_vuni, &m->d_cuni, &m->d_tsign,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
-                      &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub};
+                      &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub, &m->d_tile_list, &m->d_scan_sums};
     for (DevBuf* b : bufs) c->release(*b);
     for (auto& e : m->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -323,15 +339,21 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
     c->launches++;
     MC_CUDA(cudaGetLastError());
     const bool skip_uniform = !(m->flags & MC_OPT_KEEP_PHI);
+    unsigned long long* cnt = (unsigned long long*)m->d_counters.p;
     if (skip_uniform) {
         rc = c->alloc(ntiles * 8, m->d_sub);
+        if (rc == MC_OK) rc = c->alloc(ntiles * 4, m->d_tile_list);
         if (rc != MC_OK) return rc;
         k_subbox_decide<<<blocks_for(ntiles, 4), 128, 4 * (size_t)((p.n_decisions + 15u) & ~15u), c->stream>>>(
             L, m->g, (const uint64_t*)m->d_prog.p, ntiles, p.n_decisions, (const uint8_t*)m->d_dec.p,
-                                                                     (const int8_t*)m->d_tsign.p, (uint32_t*)m->d_sub.p,
-                                                                     (unsigned long long*)m->d_counters.p + CN_SUB_BOXES_PROVEN);
+            (int8_t*)m->d_tsign.p, (uint32_t*)m->d_sub.p, cnt + CN_SUB_BOXES_PROVEN, 1u, (uint32_t*)m->d_tile_list.p,
+            cnt + CN_SDF_LIST, (uint8_t*)m->d_tflag.p, cnt + CN_SKIPPED_TILES);
         c->launches++;
         MC_CUDA(cudaGetLastError());
+        // from here on readers take the sign of a proven tile from the table: nothing is stored there
+        m->L.tsign = (const int8_t*)m->d_tsign.p;
+        m->L.tntx = m->g.ntx;
+        m->L.tnty = m->g.nty;
     }
     const bool count = (m->flags & MC_OPT_COUNT_FLOPS) != 0;
     const bool small = p.small();
@@ -351,9 +373,10 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
                                                    (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                                                    n_inst, cap_words, p.n_decisions, (const uint8_t*)m->d_dec.p, ntiles,
                                                    (const int8_t*)m->d_tsign.p, skip_uniform ? 1 : 0,
-                                                   pruned_total, (unsigned long long*)m->d_counters.p + CN_SKIPPED_TILES,
-                                                   (unsigned long long*)m->d_counters.p + CN_SDF_FLOPS,
-                                                   skip_uniform ? (const uint32_t*)m->d_sub.p : nullptr, (uint8_t*)m->d_tflag.p);
+                                                   pruned_total, cnt + CN_SDF_FLOPS,
+                                                   skip_uniform ? (const uint32_t*)m->d_sub.p : nullptr, (uint8_t*)m->d_tflag.p,
+                                                   skip_uniform ? (const uint32_t*)m->d_tile_list.p : nullptr,
+                                                   cnt + CN_SDF_LIST, cnt + CN_SDF_NEXT);
     c->launches++;
     MC_CUDA(cudaGetLastError());
     m->tiled_sdf = true;
@@ -463,7 +486,7 @@ static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, do
         k_tile_decide<<<blocks_for(ntiles, 128), 128, 0, c->stream>>>(L, g, (const uint64_t*)dprog.p, ntiles,
                                                                       (uint8_t*)ddec.p, (int8_t*)dsign.p, (float*)dwork.p);
         k_subbox_decide<<<blocks_for(ntiles, 4), 128, 4 * (size_t)((prog.n_decisions + 15u) & ~15u), c->stream>>>(
-            L, g, (const uint64_t*)dprog.p, ntiles, prog.n_decisions, (const uint8_t*)ddec.p, (const int8_t*)dsign.p,
+            L, g, (const uint64_t*)dprog.p, ntiles, prog.n_decisions, (const uint8_t*)ddec.p, (int8_t*)dsign.p,
             (uint32_t*)dsub.p, (unsigned long long*)dcnt.p + counts.size(), sample);
         k_tile_layer_classes<<<blocks_for(ntiles, 256), 256, 0, c->stream>>>(
             g, (const int8_t*)dsign.p, (const float*)dwork.p, (const uint32_t*)dsub.p, sample, ntiles, first, last,
@@ -602,6 +625,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_vbase));
     MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_cbase));
     MC_TRY(c->alloc(64 * 8, m->d_counters));
+    MC_TRY(c->alloc((ntiles / SCAN_BLOCK + 2) * 16, m->d_scan_sums));
     L.phi = (const double*)m->d_phi.p;
     L.wcode = (uint8_t*)m->d_wcode.p;
 
@@ -614,12 +638,12 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     }
     MC_TRY_CUDA(cudaMemsetAsync(m->d_wcode.p, 0, npts, s));
     unsigned long long* counters = (unsigned long long*)m->d_counters.p;
-    const Stuff S = make_stuff(m);
     const unsigned tgrid = (unsigned)ntiles;
 
     // a2: SDF field on all stored planes
     MC_TRY_CUDA(cudaEventRecord(m->ev[0], s));
     MC_TRY(launch_sdf_field(m));
+    const Stuff S = make_stuff(m);  // after the SDF stage: it decides whether the tile-sign table is in use
     MC_TRY(c->stage_check("stage sdf_field"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
     // tile sign summary (the tiled SDF kernel writes it itself) + a6: warp codes
@@ -635,21 +659,18 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
     k_classify_cells<<<tgrid, TILE_THREADS, 0, s>>>(S, (const uint64_t*)m->d_prog.p,
                                                     (unsigned long long*)m->d_ttile_tot.p, counters);
-    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_ttile_tot.p, ntiles,
-                                    (unsigned long long*)m->d_ttile_base.p, nullptr, counters + CN_TETS);
-    c->launches += 3;
+    c->launches += 2;
     MC_TRY_CUDA(cudaGetLastError());
+    MC_TRY(scan_tiles(c, m->d_ttile_tot.p, ntiles, m->d_ttile_base.p, nullptr, m->d_scan_sums.p, counters + CN_TETS));
     // CN_TETS / CN_KEPT are adjacent: totals[0] = output tets, totals[1] = kept lattice tets
     static_assert(CN_KEPT == CN_TETS + 1, "scan totals layout");
     MC_TRY(c->stage_check("stage classify"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[3], s));
     // a10 pass 1: vertex masks + counts
     k_vertex_count<<<tgrid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_vtile_tot.p);
-    k_scan_tiles<<<1, 1024, 0, s>>>((const unsigned long long*)m->d_vtile_tot.p, ntiles,
-                                    (unsigned long long*)m->d_vtile_vbase.p, (unsigned long long*)m->d_vtile_cbase.p,
-                                    counters + CN_VERTS);
-    c->launches += 2;
+    c->launches += 1;
     MC_TRY_CUDA(cudaGetLastError());
+    MC_TRY(scan_tiles(c, m->d_vtile_tot.p, ntiles, m->d_vtile_vbase.p, m->d_vtile_cbase.p, m->d_scan_sums.p, counters + CN_VERTS));
     static_assert(CN_CUTS == CN_VERTS + 1, "scan totals layout");
     MC_TRY(c->stage_check("stage vertex count"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[4], s));

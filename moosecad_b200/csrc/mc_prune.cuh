@@ -424,10 +424,16 @@ __device__ __forceinline__ bool tile_sampled(const TileGrid& g, uint64_t tile, u
 // writes the placeholder instead of evaluating them.  The lanes of a warp share the tile, so
 // subtrees whose bounding box is far from the tile are skipped warp-uniformly.
 // sub_masks[2 * tile] = sub-boxes proven negative, [2 * tile + 1] = proven positive.
+// With `tile_list` (the mesher's call; not the load estimate's): a tile all of whose sub-boxes are
+// proven with ONE sign is promoted to a proven tile (tsign), proven tiles get their sign summary
+// (tflag) here and are not visited by the SDF kernel at all — nothing is stored for them —, the other
+// tiles are appended to the SDF kernel's work list (tile_list[0 .. *n_list)).
 static __global__ void __launch_bounds__(128)
 k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64_t ntiles, uint32_t n_dec,
-                const uint8_t* __restrict__ dec, const int8_t* __restrict__ tsign, uint32_t* __restrict__ sub_masks,
-                unsigned long long* __restrict__ sub_boxes_proven, uint32_t sample = 1u) {
+                const uint8_t* __restrict__ dec, int8_t* __restrict__ tsign, uint32_t* __restrict__ sub_masks,
+                unsigned long long* __restrict__ sub_boxes_proven, uint32_t sample = 1u,
+                uint32_t* __restrict__ tile_list = nullptr, unsigned long long* __restrict__ n_list = nullptr,
+                uint8_t* __restrict__ tflag = nullptr, unsigned long long* __restrict__ skipped_tiles = nullptr) {
     extern __shared__ uint8_t s_pd_all[];  // the tiles' decisions, one slice per warp
     const uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= ntiles) return;  // warp-uniform
@@ -438,7 +444,10 @@ k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64
     if (sg != 0) {
         // the tile's sign is proven on its box plus one lattice step on every side (k_tile_decide),
         // which contains every sub-box plus its step: all 32 are proven
-        if (lane == 0) { sub_masks[2 * tile] = sg < 0 ? 0xffffffffu : 0u; sub_masks[2 * tile + 1] = sg < 0 ? 0u : 0xffffffffu; }
+        if (lane == 0) {
+            sub_masks[2 * tile] = sg < 0 ? 0xffffffffu : 0u; sub_masks[2 * tile + 1] = sg < 0 ? 0u : 0xffffffffu;
+            if (tile_list) { tflag[tile] = sg < 0 ? TF_NEG : TF_POS; atomicAdd(skipped_tiles, 1ull); }
+        }
         return;
     }
     uint32_t X0, Y0, Z0;
@@ -456,7 +465,15 @@ k_subbox_decide(Lattice L, TileGrid g, const uint64_t* __restrict__ prog, uint64
     if (lane == 0) {
         sub_masks[2 * tile] = neg;
         sub_masks[2 * tile + 1] = pos;
-        if (neg | pos) atomicAdd(sub_boxes_proven, (unsigned long long)__popc(neg | pos));
+        if (tile_list && (neg == 0xffffffffu || pos == 0xffffffffu)) {
+            // the 32 grown sub-boxes cover the tile's grown box: the tile is proven after all
+            tsign[tile] = neg ? (int8_t)-1 : (int8_t)1;
+            tflag[tile] = neg ? TF_NEG : TF_POS;
+            atomicAdd(skipped_tiles, 1ull);
+        } else {
+            if (neg | pos) atomicAdd(sub_boxes_proven, (unsigned long long)__popc(neg | pos));
+            if (tile_list) tile_list[atomicAdd(n_list, 1ull)] = (uint32_t)tile;
+        }
     }
 }
 
@@ -656,8 +673,9 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                   const uint32_t* __restrict__ inst_start, const uint16_t* __restrict__ word_inst, uint32_t n_inst,
                   uint32_t n_words, uint32_t n_dec, const uint8_t* __restrict__ dec_g, uint64_t ntiles,
                   const int8_t* __restrict__ tsign, int skip_uniform, unsigned long long* __restrict__ pruned_words_total,
-                  unsigned long long* __restrict__ skipped_tiles, unsigned long long* __restrict__ flops_total,
-                  const uint32_t* __restrict__ sub_masks, uint8_t* __restrict__ tflag) {
+                  unsigned long long* __restrict__ flops_total, const uint32_t* __restrict__ sub_masks,
+                  uint8_t* __restrict__ tflag, const uint32_t* __restrict__ tile_list,
+                  const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ next_item) {
     unsigned long long my_flops = 0ull;
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
@@ -667,38 +685,26 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
     __shared__ uint32_t s_scan[9];
     const uint32_t tid = threadIdx.x;
 
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();  // previous tile's evaluation is done with s_prog
+    // Work items: the tiles k_subbox_decide listed (not proven), or every tile when the caller wants
+    // the whole field.  Blocks take them one at a time from a global counter: the cost of a tile
+    // (unproven sub-boxes x length of its program) varies by two orders of magnitude.
+    __shared__ unsigned long long s_item;
+    const unsigned long long n_items = tile_list ? *n_list : (unsigned long long)ntiles;
+    for (;;) {
+        __syncthreads();  // previous tile's evaluation is done with s_prog (and s_item has been read)
+        if (tid == 0) s_item = atomicAdd(next_item, 1ull);
+        __syncthreads();
+        if (s_item >= n_items) break;
+        const uint64_t tile = tile_list ? (uint64_t)tile_list[s_item] : (uint64_t)s_item;
         // A point whose whole neighbourhood (one lattice step on every side) is PROVEN to have one
         // strict sign is never read for its value: every consumer (warp, the 4-sort, bisection end
         // points) only looks at values of tets / edges that contain a vertex of another sign class,
-        // and those lie within one lattice step.  Such points get a placeholder of the right sign
-        // instead of being evaluated (unless the caller wants the field itself).
+        // and those lie within one lattice step.  Proven sub-boxes of a listed tile get a placeholder
+        // of the right sign instead of being evaluated; proven TILES are not even listed.
         uint32_t X0, Y0, Z0;
         tile_origin(g, tile, X0, Y0, Z0);
         uint32_t sub_neg = 0u, sub_pos = 0u;
-        if (skip_uniform) {
-            // proven on the tile's box plus one lattice step on every side: see k_subbox_decide
-            sub_neg = sub_masks[2 * tile]; sub_pos = sub_masks[2 * tile + 1];
-            if ((sub_neg | sub_pos) == 0xffffffffu) {
-                // nothing to evaluate: placeholders only
-                for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
-                    const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-                    const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-                    const uint32_t sub = (lx >> 3) | ((ly >> 2) << 1) | ((lz >> 2) << 3);
-                    if (X < L.NX && Y < L.NY && Z <= L.pz1) phi_out[pidx(L, X, Y, Z)] = ((sub_neg >> sub) & 1u) ? -1.0 : 1.0;
-                }
-                if (tid == 0) {
-                    if (skipped_tiles) atomicAdd(skipped_tiles, 1ull);
-                    // sign summary of the tile (what k_tile_minmax would find)
-                    uint32_t live = 0u;  // sub-boxes with at least one stored point
-                    for (uint32_t sub = 0; sub < 32u; ++sub)
-                        if (X0 + (sub & 1u) * 8u < L.NX && Y0 + ((sub >> 1) & 3u) * 4u < L.NY && Z0 + (sub >> 3) * 4u <= L.pz1) live |= 1u << sub;
-                    tflag[tile] = (uint8_t)(((sub_pos & live) == 0u ? TF_NEG : 0) | ((sub_neg & live) == 0u ? TF_POS : 0));
-                }
-                continue;
-            }
-        }
+        if (skip_uniform) { sub_neg = sub_masks[2 * tile]; sub_pos = sub_masks[2 * tile + 1]; }
         compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta,
                              s_newpos, s_scan, n_words);
         if (tid == 0 && pruned_words_total) atomicAdd(pruned_words_total, (unsigned long long)s_newpos[n_inst]);

@@ -12,10 +12,14 @@
 namespace mc {
 
 __device__ __forceinline__ double raw_phi(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
-    return L.phi[pidx(L, X, Y, Z)];
+    return phi_at(L, X, Y, Z);
 }
-// phi after warp_vertices: warped vertices are snapped to 0 (tessellate3d/src/lib.rs:178)
-__device__ __forceinline__ double warped_phi(const Lattice& L, size_t i) {
+// phi after warp_vertices: warped vertices are snapped to 0 (tessellate3d/src/lib.rs:178).
+// (A vertex of a proven tile is never warped: all its neighbours have its strict sign.)
+__device__ __forceinline__ double warped_phi(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
+    const int8_t s = tile_sign_at(L, X, Y, Z);
+    if (s) return (double)s;
+    const size_t i = pidx(L, X, Y, Z);
     return (L.wcode[i] & 0x7f) ? 0.0 : L.phi[i];
 }
 
@@ -70,7 +74,9 @@ static __device__ void warped_pos(const Lattice& L, uint32_t X, uint32_t Y, uint
     if (code == 0u) { out[0] = xv; out[1] = yv; out[2] = zv; return; }
     const uint32_t di = (code - 1u) >> 1, orient = (code - 1u) & 1u;
     const uint32_t WX = X + C_DIR[di][0], WY = Y + C_DIR[di][1], WZ = Z + C_DIR[di][2];
-    const double pv = raw_phi(L, X, Y, Z), pw = raw_phi(L, WX, WY, WZ);
+    // a warped vertex and the far end of its winning edge differ in sign class: neither lies in a
+    // proven tile, the stored values are read directly
+    const double pv = L.phi[pidx(L, X, Y, Z)], pw = L.phi[pidx(L, WX, WY, WZ)];
     const double dx = lat_x(L, WX) - xv, dy = lat_y(L, WY) - yv, dz = lat_z(L, WZ) - zv;
     double f;
     if (orient == 0u) {
@@ -126,7 +132,7 @@ __device__ __forceinline__ void load_tet(const Lattice& L, const Cell& c, int t,
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
         corner_xyz(c, tet_corner(c, t, n), tn.X[n], tn.Y[n], tn.Z[n]);
-        tn.p[n] = warped_phi(L, pidx(L, tn.X[n], tn.Y[n], tn.Z[n]));
+        tn.p[n] = warped_phi(L, tn.X[n], tn.Y[n], tn.Z[n]);
     }
 }
 
