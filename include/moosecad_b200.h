@@ -286,13 +286,17 @@ int mc_mesh_checksum(mc_mesh*, uint64_t out[4]);
  * ------------------------------------------------------------------------------------ */
 /* number of surface sides; computes them on first call */
 int mc_mesh_boundary(mc_mesh*, uint64_t* n_sides);
-/* (elem, side) pairs, side in 0..3 per Tet4::face (mesh/src/lib.rs:661-668); host view */
+/* (elem, side) pairs, side in 0..3 per Tet4::face (mesh/src/lib.rs:661-668), sorted by (elem, side)
+ * (the reference's HashSet order is arbitrary); host view, copied on first request */
 const uint64_t* mc_mesh_boundary_sides(mc_mesh*);
+/* the same pairs on the device (uint64 x 2 per side) */
+int mc_mesh_boundary_device(mc_mesh*, void** d_sides, uint64_t* n_sides);
 /* adds one side-set: surface sides whose three nodes all satisfy
  * |approx_value(p, EPSILON)| <= EPSILON for the given boundary object.  Returns its index. */
 int mc_mesh_add_sideset(mc_mesh*, const mc_tape* boundary, int32_t root);
 uint64_t mc_mesh_sideset_len(const mc_mesh*, int index);
 const uint64_t* mc_mesh_sideset(mc_mesh*, int index);
+int mc_mesh_sideset_device(mc_mesh*, int index, void** d_pairs, uint64_t* n);
 
 /* ------------------------------------------------------------------------------------
  * mesh crate predicates on arbitrary tet meshes (mesh/src/lib.rs:292-316), evaluated on the

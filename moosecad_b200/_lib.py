@@ -109,6 +109,8 @@ SIGNATURES = {
     "mc_mesh_checksum": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary_sides": (_PU64, [_P]),
+    "mc_mesh_boundary_device": (C.c_int, [_P, C.POINTER(_P), _PU64]),
+    "mc_mesh_sideset_device": (C.c_int, [_P, C.c_int, C.POINTER(_P), _PU64]),
     "mc_mesh_add_sideset": (C.c_int, [_P, _P, _I32]),
     "mc_mesh_sideset_len": (_U64, [_P, C.c_int]),
     "mc_mesh_sideset": (_PU64, [_P, C.c_int]),

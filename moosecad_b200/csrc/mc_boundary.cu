@@ -1,15 +1,24 @@
 // Mesh::boundary() (mesh/src/lib.rs:341-357) and the side-set loop (src/main.rs:87-106).
 //
-// The reference toggles every face of every tet in and out of a HashMap keyed by the sorted
-// node triple.  Here only the faces that can possibly be unmatched are generated: a "full"
-// cell (all five lattice tets emitted untouched) pairs all its internal faces by
-// construction and its cell-face triangles pair with those of a full neighbour, so it only
-// contributes the triangles facing a non-full neighbour or the lattice border; every other
-// cell contributes all faces of its output tets.  The candidates (O(surface)) are radix
-// sorted by key; a key that occurs an odd number of times is a boundary side, owned by its
-// last occurrence in element order (the toggle semantics).
-#include <cub/device/device_radix_sort.cuh>
-
+// The reference toggles every face of every tet in and out of a HashMap keyed by the sorted node
+// triple: a face is a boundary side iff it occurs an odd number of times, and the side that is
+// reported is its last occurrence.  No map and no sort is needed to evaluate that rule here,
+// because the mesh is structured: every output tet is a piece of ONE lattice tet (whole, or one
+// of the <= 3 tets trim_spikes cuts it into), so a face of an output tet either
+//   * lies inside its lattice tet: it can only occur again among the other pieces of the same
+//     lattice tet (the node ids of a face name the lattice vertices / lattice edges it hangs on), or
+//   * lies in one of the four faces of its lattice tet: it can only occur again among the pieces of
+//     the same lattice tet and of the ONE lattice tet on the other side of that lattice face.
+// So every (lattice tet, piece, side) counts the other occurrences of its face locally —
+// re-classifying the neighbouring lattice tet from the SDF field, like the tet emission does —
+// and reports the face when the total is odd and it is the last of them in a fixed order.  This is
+// the hash-map rule verbatim (it even reproduces the faces that occur three times in the prism
+// split of trim case 3), evaluated per face.  Only cells next to the surface do any work: a cell
+// whose five lattice tets are emitted untouched ("full") next to full cells is skipped outright.
+//
+// Everything is slab-aware: the cell layers next to the slab are classified too (halo), so the tet
+// across a slab boundary is re-classified locally and no exchange is needed.  Sides come out sorted by
+// (elem, side) because tiles, cells, lattice tets and pieces are visited in emission order.
 #include <algorithm>
 #include <limits>
 
@@ -18,431 +27,614 @@
 
 namespace mc {
 
-// the two triangles of every cell face, as (tet, side) of the un-mirrored tile; derived once
-// on the host from Tile::TETS / Tet4::face (a triangle lies in a cell face iff its three
-// corners share a coordinate).
-struct FaceTri { int8_t tet, side; };
-static __constant__ FaceTri C_CELLFACE[6][2];  // [axis*2 + (coordinate==1)][k]
-
-static void build_cellface_table(FaceTri out[6][2]) {
-    static const int LAT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
-    static const int TETS[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};
-    static const int FACE[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
-    int cnt[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < 5; ++t)
-        for (int s = 0; s < 4; ++s)
-            for (int ax = 0; ax < 3; ++ax)
-                for (int v = 0; v < 2; ++v) {
-                    bool all = true;
-                    for (int k = 0; k < 3; ++k) all = all && LAT[TETS[t][FACE[s][k]]][ax] == v;
-                    if (all) { out[ax * 2 + v][cnt[ax * 2 + v]++] = {(int8_t)t, (int8_t)s}; }
-                }
-}
-
-// After the cut_lattice flip (nodes 0 and 1 swapped) the face table is applied to the flipped
-// node order: side s of the emitted tet consists of flipped nodes FACE[s][*].  A triangle that
-// is (un-flipped) side s0 keeps its node SET but may sit at a different side index.
-__device__ __forceinline__ int side_after_flip(int s0) {
-    // un-flipped nodes of side s0 -> positions after swapping 0<->1 -> which FACE row has that set
-    int mask = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int n = C_FACE[s0][k];
-        n = n < 2 ? 1 - n : n;
-        mask |= 1 << n;
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int m = (1 << C_FACE[s][0]) | (1 << C_FACE[s][1]) | (1 << C_FACE[s][2]);
-        if (m == mask) return s;
-    }
-    return -1;
-}
-
 Stuff make_stuff(const mc_mesh* m);  // mc_mesher.cu
 
-__device__ __forceinline__ bool cell_is_full(const Stuff& S, int64_t cx, int64_t cy, int64_t cz) {
+// ---- lattice topology helpers -----------------------------------------------------------------
+// unflipped Tile::TETS positions: the central tet is t = 1 = [0, 2, 5, 7]; across the face opposite
+// its node at position m lies the corner tet NB_CENTRAL[m] of the same cell.  A corner tet
+// (t = 0, 2, 3, 4) touches the central tet through the face opposite its odd ("corner") vertex, which
+// sits at position CORNER_POS[t]; its other three faces lie in cell faces.
+static __constant__ int8_t C_NB_CENTRAL[4] = {3, 2, 4, 0};
+static __constant__ int8_t C_CORNER_POS[5] = {1, -1, 3, 1, 3};
+
+__device__ __forceinline__ unsigned long long pt_id(uint32_t X, uint32_t Y, uint32_t Z) {
+    return ((unsigned long long)Z << 42) | ((unsigned long long)Y << 21) | (unsigned long long)X;
+}
+
+// what a cell emitted: its info word, whether all five lattice tets came out untouched, whether anything did
+struct CellInfo { uint16_t ci; bool full; bool any; };
+__device__ __forceinline__ CellInfo cell_info(const Stuff& S, int64_t cx, int64_t cy, int64_t cz) {
+    CellInfo r = {0, false, false};
     const Lattice& L = S.L;
-    if (cx < 0 || cy < 0 || cz < 0 || cx >= (int64_t)L.nx || cy >= (int64_t)L.ny || cz >= (int64_t)L.nz) return false;
-    if (cz < (int64_t)S.cl0 || cz >= (int64_t)S.cl1) return false;
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= (int64_t)L.nx || cy >= (int64_t)L.ny || cz >= (int64_t)L.nz) return r;
+    if (cz < (int64_t)S.cl0 || cz >= (int64_t)S.cl1) return r;  // never reached for neighbours of owned cells
     const uint8_t cu = S.cuni[tile_of(S.g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)];
-    if (cu == CU_FULL) return true;
-    if (cu == CU_EMPTY) return false;
-    return (S.cinfo[cidx(S, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)] & CI_FULL) != 0;
+    if (cu == CU_EMPTY) return r;
+    if (cu == CU_FULL) { r.ci = CI_ALL_FULL; r.full = true; r.any = true; return r; }
+    r.ci = S.cinfo[cidx(S, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)];
+    r.full = (r.ci & CI_FULL) != 0;
+    r.any = ci_count(r.ci) != 0;
+    return r;
 }
 
-// number of candidate faces of a cell with `count` output tets
-__device__ __forceinline__ uint32_t cell_face_count(const Stuff& S, uint32_t cx, uint32_t cy, uint32_t cz, bool full,
-                                                    uint32_t count) {
-    if (!full) return 4u * count;
-    uint32_t n = 0;
-    n += cell_is_full(S, (int64_t)cx - 1, cy, cz) ? 0u : 2u;
-    n += cell_is_full(S, (int64_t)cx + 1, cy, cz) ? 0u : 2u;
-    n += cell_is_full(S, cx, (int64_t)cy - 1, cz) ? 0u : 2u;
-    n += cell_is_full(S, cx, (int64_t)cy + 1, cz) ? 0u : 2u;
-    n += cell_is_full(S, cx, cy, (int64_t)cz - 1) ? 0u : 2u;
-    n += cell_is_full(S, cx, cy, (int64_t)cz + 1) ? 0u : 2u;
-    return n;
+// the pieces of lattice tet (c, t) as a TetOut (node codes: 0..3 original node, 4 + 4 i + j cut on edge i-j)
+__device__ __forceinline__ void pieces_of(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, TetOut& to) {
+    if (ci & CI_FULL) {  // untouched: the lattice tet itself (on a full cell the "removed" bits mean something else)
+        to.n = 1; to.kase = -1; to.ext_removed = false;
+        to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
+        return;
+    }
+    if (ci_tet_n(ci, t) == 0u) { to.n = 0; to.kase = -2; to.ext_removed = false; to.nodes = 0ull; return; }
+    classify_tet<false>(S.L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
 }
 
-// (full?, output tets) of an owned cell of this tile
-__device__ __forceinline__ void cell_state(const Stuff& S, uint8_t cu, uint32_t cx, uint32_t cy, uint32_t cz, bool& full,
-                                           uint32_t& count, uint16_t& ci) {
-    if (cu == CU_FULL) { full = true; count = 5; ci = CI_ALL_FULL; return; }
-    ci = S.cinfo[cidx(S, cx, cy, cz)];
-    full = (ci & CI_FULL) != 0;
-    count = ci_count(ci);
+// signature of the face (q, s) of `to` relative to lattice face k of its lattice tet, or 0 when the
+// face does not lie in it.  r[n] = rank (0..2) of node n among the three lattice points of face k
+// by point id (r[k] unused): both sides of the lattice face compute the same ranks.  A node becomes
+// a 3-bit set of ranks (original node: one bit, cut vertex: the two ends of its edge), the face the
+// set of its three node sets (8 bits).
+__device__ __forceinline__ uint32_t face_sig(const TetOut& to, int q, int s, int k, int r0, int r1, int r2, int r3) {
+    uint32_t sig = 0u;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int code = to.node(q, C_FACE[s][m]);
+        uint32_t nm;
+        if (code < 4) {
+            if (code == k) return 0u;
+            nm = 1u << pick4(r0, r1, r2, r3, code);
+        } else {
+            const int i = (code - 4) >> 2, j = (code - 4) & 3;
+            if (i == k || j == k) return 0u;
+            nm = (1u << pick4(r0, r1, r2, r3, i)) | (1u << pick4(r0, r1, r2, r3, j));
+        }
+        sig |= 1u << nm;
+    }
+    return sig;
 }
 
-static __global__ void __launch_bounds__(TILE_THREADS)
-k_face_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
-    __shared__ unsigned long long s_acc;
+// order of two occurrences of a face in different lattice tets: emission order of the lattice tets
+__device__ __forceinline__ bool tet_after(const Cell& a, int ta, const Cell& b, int tb) {
+    if (a.cz != b.cz) return a.cz > b.cz;
+    if (a.cy != b.cy) return a.cy > b.cy;
+    if (a.cx != b.cx) return a.cx > b.cx;
+    return ta > tb;
+}
+
+// The faces of the pieces of the lattice tet on the other side of lattice face k of (c, t): up to four
+// signatures (8 bits each); *after = that tet comes later in emission order.
+static __device__ __noinline__ uint32_t neighbour_sigs(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, int k,
+                                                       bool* after) {
     const Lattice& L = S.L;
-    uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    const uint8_t cu = S.cuni[blockIdx.x];
-    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    unsigned long long mine = 0;
-    if (cu != CU_EMPTY && X0 < L.nx && Y0 < L.ny && zhi > zlo) {
-        for (int r = 0; r < TILE_ROUNDS; ++r) {
-            const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-            const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
-            if (cx >= L.nx || cy >= L.ny || cz < zlo || cz >= zhi) continue;
-            bool full; uint32_t count; uint16_t ci;
-            cell_state(S, cu, cx, cy, cz, full, count, ci);
-            if (count) mine += cell_face_count(S, cx, cy, cz, full, count);
+    *after = false;
+    const bool flip = c.flip();
+    const int mk = (flip && k < 2) ? 1 - k : k;  // position of node k in the unflipped Tile::TETS row
+    Cell c2 = c;
+    int t2 = -1;
+    uint32_t fx[3], fy[3], fz[3];
+    {
+        int w = 0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            if (n != k) { fx[w] = tet_X(tn, n); fy[w] = tet_Y(tn, n); fz[w] = tet_Z(tn, n); ++w; }
+    }
+    if (t == 1) t2 = C_NB_CENTRAL[mk];
+    else if (mk == C_CORNER_POS[t]) t2 = 1;
+    else {
+        // the face lies in a cell face: its three points share one coordinate
+        int64_t ncx = c.cx, ncy = c.cy, ncz = c.cz;
+        if (fx[0] == fx[1] && fx[1] == fx[2]) ncx += fx[0] == c.cx ? -1 : 1;
+        else if (fy[0] == fy[1] && fy[1] == fy[2]) ncy += fy[0] == c.cy ? -1 : 1;
+        else ncz += fz[0] == c.cz ? -1 : 1;
+        if (ncx < 0 || ncy < 0 || ncz < 0 || ncx >= (int64_t)L.nx || ncy >= (int64_t)L.ny || ncz >= (int64_t)L.nz) return 0u;
+        c2 = make_cell((uint32_t)ncx, (uint32_t)ncy, (uint32_t)ncz);
+        // its corner tet that holds the three points
+        for (int tt = 0; tt < 5 && t2 < 0; ++tt) {
+            if (tt == 1) continue;
+            int hit = 0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                uint32_t X, Y, Z;
+                corner_xyz(c2, C_TETS[tt][n], X, Y, Z);
+#pragma unroll
+                for (int f = 0; f < 3; ++f) hit += (X == fx[f] && Y == fy[f] && Z == fz[f]) ? 1 : 0;
+            }
+            if (hit == 3) t2 = tt;
+        }
+        if (t2 < 0) return 0u;
+    }
+    CellInfo i2;
+    if (c2.cx == c.cx && c2.cy == c.cy && c2.cz == c.cz) { i2.ci = ci; i2.full = (ci & CI_FULL) != 0; i2.any = true; }
+    else i2 = cell_info(S, c2.cx, c2.cy, c2.cz);
+    if (!i2.any || ci_tet_n(i2.ci, t2) == 0u) return 0u;
+    *after = tet_after(c2, t2, c, t);
+    if (i2.full) return (1u << 1) | (1u << 2) | (1u << 4);  // untouched: the whole lattice face
+    TetNodes tn2;
+    load_tet(L, c2, t2, tn2);
+    TetOut to2;
+    pieces_of(S, c2, t2, i2.ci, tn2, to2);
+    // ranks of the neighbour's nodes among the same three points; k2 = its node off the face
+    unsigned long long g2[4], gf[3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) g2[n] = pt_id(tn2.X[n], tn2.Y[n], tn2.Z[n]);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) gf[f] = pt_id(fx[f], fy[f], fz[f]);
+    int k2 = 0, r2[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        int rk = 0;
+        bool on = false;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) { on = on || g2[n] == gf[f]; rk += gf[f] < g2[n] ? 1 : 0; }
+        if (!on) k2 = n;
+        r2[n] = rk;
+    }
+    uint32_t sigs = 0u;
+    int nsig = 0;
+    for (int q2 = 0; q2 < to2.n; ++q2)
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+            const uint32_t sg = face_sig(to2, q2, s2, k2, r2[0], r2[1], r2[2], r2[3]);
+            if (sg && nsig < 4) { sigs |= sg << (8 * nsig); ++nsig; }
+        }
+    return sigs;
+}
+
+// Boundary sides of the pieces of lattice tet (c, t): bit 4 q + s.  `ci` = the cell's info word.
+static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int t, uint16_t ci) {
+    const Lattice& L = S.L;
+    if (ci_tet_n(ci, t) == 0u) return 0u;
+    TetNodes tn;
+    load_tet(L, c, t, tn);
+    TetOut to;
+    pieces_of(S, c, t, ci, tn, to);
+    if (to.n == 0) return 0u;
+    unsigned long long gid[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) gid[n] = pt_id(tn.X[n], tn.Y[n], tn.Z[n]);
+    uint32_t nb_sigs0 = 0u, nb_sigs1 = 0u, nb_sigs2 = 0u, nb_sigs3 = 0u;
+    uint32_t nb_state = 0u;  // bit k: neighbour across face k known; bit 4 + k: it comes later in emission order
+    uint32_t out = 0u;
+    for (int q = 0; q < to.n; ++q) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            // node-code set of this face, and the lattice faces all its nodes lie in
+            uint32_t codes = 0u, fmask = 0xfu;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int code = to.node(q, C_FACE[s][m]);
+                codes |= 1u << code;
+                fmask &= code < 4 ? ~(1u << code) : ~((1u << ((code - 4) >> 2)) | (1u << ((code - 4) & 3)));
+            }
+            uint32_t cnt = 0u;
+            bool last = true;
+            // ... among the other pieces of this lattice tet
+            for (int q2 = 0; q2 < to.n; ++q2)
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) {
+                    if (q2 == q && s2 == s) continue;
+                    uint32_t c2 = 0u;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) c2 |= 1u << to.node(q2, C_FACE[s2][m]);
+                    if (c2 == codes) { ++cnt; if (q2 > q || (q2 == q && s2 > s)) last = false; }
+                }
+            // ... and among the pieces of the lattice tet across the lattice face it lies in
+            fmask &= 0xfu;
+            if (fmask) {
+                const int k = __ffs((int)fmask) - 1;
+                int r[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    int rk = 0;
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) rk += (o != k && o != n && gid[o] < gid[n]) ? 1 : 0;
+                    r[n] = rk;
+                }
+                const uint32_t mine = face_sig(to, q, s, k, r[0], r[1], r[2], r[3]);
+                if (!((nb_state >> k) & 1u)) {
+                    bool after;
+                    const uint32_t sg = neighbour_sigs(S, c, t, ci, tn, k, &after);
+                    if (k == 0) nb_sigs0 = sg; else if (k == 1) nb_sigs1 = sg; else if (k == 2) nb_sigs2 = sg; else nb_sigs3 = sg;
+                    nb_state |= (1u << k) | (after ? 16u << k : 0u);
+                }
+                const uint32_t sigs = pick4(nb_sigs0, nb_sigs1, nb_sigs2, nb_sigs3, k);
+                const bool after = (nb_state >> (4 + k)) & 1u;
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (mine != 0u && ((sigs >> (8 * f)) & 0xffu) == mine) { ++cnt; if (after) last = false; }
+            }
+            if ((cnt & 1u) == 0u && last) out |= 1u << (4 * q + s);
         }
     }
-    const unsigned long long tot = block_sum(mine, &s_acc);
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+    return out;
 }
 
-__device__ __forceinline__ void sort3(unsigned long long& a, unsigned long long& b, unsigned long long& c) {
-    unsigned long long t;
-    if (a > b) { t = a; a = b; b = t; }
-    if (b > c) { t = b; b = c; c = t; }
-    if (a > b) { t = a; a = b; b = t; }
-}
-
-// emit candidate faces: key = sorted global node ids (k0 <= k1 <= k2), payload = tet * 4 + side
-static __global__ void __launch_bounds__(TILE_THREADS)
-k_face_emit(Stuff S, const unsigned long long* __restrict__ tile_fbase, unsigned long long tet_base,
-            unsigned long long* __restrict__ key_hi, unsigned long long* __restrict__ key_lo,
-            unsigned long long* __restrict__ payload) {
-    __shared__ uint32_t s_scan[9];
-    const Lattice& L = S.L;
+// A cell tile takes part when it can hold a boundary side: any tile that is not uniformly full /
+// empty, and full tiles that touch a tile that is not full (or the lattice border)
+__device__ __forceinline__ bool boundary_tile_candidate(const Stuff& S, uint64_t tile, uint8_t cu) {
+    if (cu == CU_EMPTY) return false;
+    if (cu == CU_ACTIVE) return true;
+    const int tix = (int)(tile % S.g.ntx), tiy = (int)((tile / S.g.ntx) % S.g.nty), tiz = (int)(tile / ((uint64_t)S.g.ntx * S.g.nty));
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    const uint8_t cu = S.cuni[blockIdx.x];
+    tile_origin(S.g, tile, X0, Y0, Z0);
+    if (X0 == 0u || Y0 == 0u || Z0 == 0u || X0 + TS >= S.L.nx || Y0 + TS >= S.L.ny || Z0 + TS >= S.L.nz) return true;
+    const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    for (int f = 0; f < 6; ++f) {
+        const int x = tix + d[f][0], y = tiy + d[f][1], z = tiz + d[f][2];
+        if (x < 0 || y < 0 || z < 0 || x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) return true;
+        if (S.cuni[((size_t)z * S.g.nty + y) * S.g.ntx + x] != CU_FULL) return true;
+    }
+    return false;
+}
+
+// One block per cell tile.  COUNT pass (EMIT = false): tile_io[tile] = number of boundary sides of the
+// tile's owned cells.  EMIT pass: tile_io[tile] = index of the tile's first side; sides[] receives
+// (elem, side) pairs.
+template <bool EMIT>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_boundary_sides(Stuff S, unsigned long long* __restrict__ tile_io, unsigned long long tet_base,
+                 unsigned long long* __restrict__ sides) {
+    __shared__ unsigned long long s_acc;
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint16_t s_ci[TILE_POINTS], s_off[TILE_POINTS], s_list[TILE_POINTS];
+    const Lattice& L = S.L;
+    const uint64_t tile = blockIdx.x;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, tile, X0, Y0, Z0);
+    const uint8_t cu = S.cuni[tile];
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (cu == CU_EMPTY || X0 >= L.nx || Y0 >= L.ny || zhi <= zlo) return;
-    const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
-    const uint64_t tb = S.ttbase[blockIdx.x];
-    uint64_t trun = tb, frun = tile_fbase[blockIdx.x];
-    for (int r = 0; r < TILE_ROUNDS; ++r) {
-        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
-        const bool owned = cx < L.nx && cy < L.ny && cz >= zlo && cz < zhi;
-        bool full = false; uint32_t count = 0; uint16_t ci = 0;
-        if (owned) cell_state(S, cu, cx, cy, cz, full, count, ci);
-        const uint32_t nf = count ? cell_face_count(S, cx, cy, cz, full, count) : 0u;
-        uint32_t ttot, ftot;
-        const uint32_t tex = block_exscan(count, &ttot, s_scan);
-        const uint32_t fex = block_exscan(nf, &ftot, s_scan);
-        if (nf) {
-            const Cell c = make_cell(cx, cy, cz);
-            // slab-local index of the cell's first output tet (same numbering as k_tet_emit)
-            uint64_t o = cu == CU_FULL ? tb + 5ull * (((cz - zlo) * nyt + (cy - Y0)) * nxt + (cx - X0)) : trun + tex;
-            uint64_t f = frun + fex;
-            if (full) {
-                // tets 0..4 are emitted in order; only triangles on open cell faces are candidates
-                for (int ax = 0; ax < 3; ++ax)
-                    for (int v = 0; v < 2; ++v) {
-                        // un-mirrored face (axis, v) sits at global offset v' = mirrored ? 1 - v : v
-                        const bool mir = ax == 0 ? c.fx : (ax == 1 ? c.fy : c.fz);
-                        const int gv = mir ? 1 - v : v;
-                        int64_t ncx = cx, ncy = cy, ncz = cz;
-                        (ax == 0 ? ncx : (ax == 1 ? ncy : ncz)) += gv ? 1 : -1;
-                        if (cell_is_full(S, ncx, ncy, ncz)) continue;
-                        for (int k = 0; k < 2; ++k) {
-                            const FaceTri ft = C_CELLFACE[ax * 2 + v][k];
-                            TetNodes tn;
-                            load_tet(L, c, ft.tet, tn);
-                            const int sd = c.flip() ? side_after_flip(ft.side) : ft.side;
-                            unsigned long long g[3];
+    if (X0 >= L.nx || Y0 >= L.ny || zhi <= zlo || !boundary_tile_candidate(S, tile, cu)) {
+        if (!EMIT && threadIdx.x == 0) tile_io[tile] = 0ull;
+        return;
+    }
+    const uint32_t nxt = min(TS, L.nx - X0);
+    // per-cell info and the offset of the cell's first output tet inside the tile (emission order:
+    // x-rows of cells, see k_tet_emit / k_tet_emit_full)
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
+        const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
+        const uint32_t nx_row = row_owned ? nxt : 0u;
+        uint32_t acc = 0;
+        uint32_t pre[TS];
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) g[q] = node_global_id<unsigned long long>(S, tn, C_FACE[sd][q]);
-                            sort3(g[0], g[1], g[2]);
-                            key_hi[f] = (g[0] << 32) | g[1];
-                            key_lo[f] = g[2];
-                            payload[f] = ((tet_base + o + (uint64_t)ft.tet) << 2) | (unsigned long long)sd;
-                            ++f;
-                        }
-                    }
-            } else {
-                for (int t = 0; t < 5; ++t) {
-                    TetNodes tn;
-                    load_tet(L, c, t, tn);
-                    TetOut to;
-                    classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
-                    for (int q = 0; q < to.n; ++q) {
-                        unsigned long long id[4];
+        for (uint32_t i = 0; i < TS; ++i) {
+            uint16_t ci = 0;
+            if (i < nx_row) ci = cu == CU_FULL ? CI_ALL_FULL : S.cinfo[cidx(S, X0 + i, cy, cz)];
+            s_ci[threadIdx.x * TS + i] = ci;
+            pre[i] = acc;
+            acc += ci_count(ci);
+        }
+        uint32_t tot;
+        const uint32_t ex = block_exscan(acc, &tot, s_scan);
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) id[m] = node_global_id<unsigned long long>(S, tn, to.node(q, m));
-                        for (int sd = 0; sd < 4; ++sd) {
-                            unsigned long long g0 = id[C_FACE[sd][0]], g1 = id[C_FACE[sd][1]], g2 = id[C_FACE[sd][2]];
-                            sort3(g0, g1, g2);
-                            key_hi[f] = (g0 << 32) | g1;
-                            key_lo[f] = g2;
-                            payload[f] = ((tet_base + o) << 2) | (unsigned long long)sd;
-                            ++f;
-                        }
-                        ++o;
-                    }
-                }
+        for (uint32_t i = 0; i < TS; ++i) s_off[threadIdx.x * TS + i] = (uint16_t)(ex + pre[i]);
+    }
+    __syncthreads();
+    // candidate cells in emission order: not full, or full next to a cell that is not
+    uint32_t ncand = 0;
+    for (int rnd = 0; rnd < TILE_ROUNDS; ++rnd) {
+        const uint32_t j = (uint32_t)rnd * TILE_THREADS + threadIdx.x;
+        const uint16_t ci = s_ci[j];
+        bool cand = false;
+        if (ci_count(ci) != 0u) {
+            if (!(ci & CI_FULL)) cand = true;
+            else {
+                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+                const int64_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
+                // neighbours inside the tile (and owned) come from shared memory
+                auto full_at = [&](int dx, int dy, int dz) -> bool {
+                    const int x = (int)lx + dx, y = (int)ly + dy, z = (int)lz + dz;
+                    if (x >= 0 && y >= 0 && z >= 0 && x < (int)TS && y < (int)TS && z < (int)TS && cz + dz >= (int64_t)zlo &&
+                        cz + dz < (int64_t)zhi && cx + dx < (int64_t)L.nx && cy + dy < (int64_t)L.ny)
+                        return (s_ci[(z * (int)TS + y) * (int)TS + x] & CI_FULL) != 0;
+                    return cell_info(S, cx + dx, cy + dy, cz + dz).full;
+                };
+                cand = !(full_at(-1, 0, 0) && full_at(1, 0, 0) && full_at(0, -1, 0) && full_at(0, 1, 0) && full_at(0, 0, -1) &&
+                         full_at(0, 0, 1));
             }
         }
-        trun += ttot;
-        frun += ftot;
+        uint32_t tot;
+        const uint32_t ex = block_exscan(cand ? 1u : 0u, &tot, s_scan);
+        if (cand) s_list[ncand + ex] = (uint16_t)j;
+        ncand += tot;
+    }
+    __syncthreads();
+    // the lattice tets of the candidate cells, in emission order
+    const uint64_t tb = tet_base + S.ttbase[tile];
+    unsigned long long mine = 0ull;
+    uint64_t run = EMIT ? tile_io[tile] : 0ull;
+    for (uint32_t base = 0; base < 5u * ncand; base += TILE_THREADS) {
+        const uint32_t w = base + threadIdx.x;
+        uint32_t mask = 0u, j = 0u, t = 0u;
+        uint16_t ci = 0;
+        if (w < 5u * ncand) {
+            j = s_list[w / 5u];
+            t = w % 5u;
+            ci = s_ci[j];
+            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+            mask = tet_boundary_mask(S, c, (int)t, ci);
+        }
+        if (!EMIT) {
+            mine += (unsigned long long)__popc(mask);
+        } else {
+            uint32_t tot;
+            const uint32_t ex = block_exscan((uint32_t)__popc(mask), &tot, s_scan);
+            if (mask) {
+                uint32_t before = 0;
+                for (uint32_t u = 0; u < t; ++u) before += ci_tet_n(ci, (int)u);
+                uint64_t o = run + ex;
+                for (uint32_t b = 0; b < 12u; ++b)
+                    if ((mask >> b) & 1u) {
+                        sides[2 * o] = tb + s_off[j] + before + (b >> 2);
+                        sides[2 * o + 1] = b & 3u;
+                        ++o;
+                    }
+            }
+            run += tot;
+        }
+    }
+    if (!EMIT) {
+        const unsigned long long tot = block_sum(mine, &s_acc);
+        if (threadIdx.x == 0) tile_io[tile] = tot;
     }
 }
 
-static __global__ void k_iota(unsigned long long* p, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = i;
+// ---- side-sets ----------------------------------------------------------------------------------
+// src/main.rs:87-106: a surface side belongs to a boundary object's side-set iff all three nodes satisfy
+// |approx_value(p, EPSILON)| <= EPSILON.  The object is evaluated once per surface VERTEX:
+//   1. k_mark_side_nodes: flag the nodes of the surface sides (own vertices, and the slice of the rank
+//      below's vertices a slab may reference)          2. k_list_flagged: gather them into a dense list
+//   3. k_eval_side_nodes: value at every listed vertex -> flag 2 (on the object) or 1
+//   4. k_sideset_select: sides whose three nodes carry flag 2, counted per block, scanned, written in order
+template <typename IndexT>
+__device__ __forceinline__ long long side_node(const IndexT* __restrict__ tets, unsigned long long tet_base,
+                                               const unsigned long long* __restrict__ sides, uint64_t i, int k) {
+    const unsigned long long e = sides[2 * i] - tet_base, s = sides[2 * i + 1];
+    return (long long)tets[4 * e + C_FACE[s][k]];
 }
-static __global__ void k_gather(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ idx,
-                         uint64_t n, unsigned long long* __restrict__ dst) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[idx[i]];
+// flag index of a global vertex id: own vertices first, then the slice of the rank below; -1: not here
+__device__ __forceinline__ long long flag_index(long long gid, long long vertex_base, long long n_verts, long long lower_first,
+                                                long long lower_count) {
+    if (gid >= vertex_base) return gid - vertex_base;
+    const long long lid = gid - lower_first;
+    return (lid >= 0 && lid < lower_count) ? n_verts + lid : -1;
 }
 
-// one thread per sorted candidate: the first element of every run of equal keys counts the run
-// and, when the length is odd, appends the run's last element (largest tet id) to the output
-static __global__ void k_face_select(const unsigned long long* __restrict__ key_hi, const unsigned long long* __restrict__ key_lo,
-                              const unsigned long long* __restrict__ payload,
-                              const unsigned long long* __restrict__ order, uint64_t n,
-                              unsigned long long* __restrict__ out_sides, unsigned long long* __restrict__ out_count) {
+template <typename IndexT>
+__global__ void k_mark_side_nodes(const IndexT* __restrict__ tets, unsigned long long tet_base,
+                                  const unsigned long long* __restrict__ sides, uint64_t n, long long vertex_base,
+                                  long long n_verts, long long lower_first, long long lower_count, uint8_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long me = order[i];
-    const unsigned long long h = key_hi[me], l = key_lo[me];
-    if (i > 0) {
-        const unsigned long long pr = order[i - 1];
-        if (key_hi[pr] == h && key_lo[pr] == l) return;  // not a run start
-    }
-    uint64_t j = i + 1;
-    unsigned long long lastp = payload[me];
-    while (j < n) {
-        const unsigned long long nx = order[j];
-        if (key_hi[nx] != h || key_lo[nx] != l) break;
-        const unsigned long long p = payload[nx];
-        if (p > lastp) lastp = p;
-        ++j;
-    }
-    if ((j - i) & 1ull) {
-        const unsigned long long at = atomicAdd(out_count, 1ull);
-        out_sides[at] = lastp;  // packed elem * 4 + side; sorted and unpacked afterwards
-    }
-}
-
-static __global__ void k_unpack_sides(const unsigned long long* __restrict__ packed, uint64_t n,
-                                      unsigned long long* __restrict__ sides) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { sides[2 * i] = packed[i] >> 2; sides[2 * i + 1] = packed[i] & 3ull; }
-}
-
-// side-set membership: |approx_value(p, EPS)| <= EPS at the three nodes of every surface side
-template <typename IndexT>
-__global__ void k_sideset(const uint64_t* __restrict__ prog, const double* __restrict__ coords,
-                          const IndexT* __restrict__ tets, int64_t vertex_base, unsigned long long tet_base,
-                          const unsigned long long* __restrict__ sides, uint64_t n, uint8_t* __restrict__ member) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t ic = i < n ? i : n - 1;
-    const unsigned long long e = sides[2 * ic] - tet_base, s = sides[2 * ic + 1];
-    const double EPS = 2.220446049250313e-16;  // f64::EPSILON
-    bool add = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int64_t id = (int64_t)tets[4 * e + C_FACE[s][k]] - vertex_base;
-        const double phi = vm_eval<true>(prog, coords[3 * id], coords[3 * id + 1], coords[3 * id + 2]);
-        if (phi > EPS || phi < -EPS) add = false;
+        const long long f = flag_index(side_node(tets, tet_base, sides, i, k), vertex_base, n_verts, lower_first, lower_count);
+        if (f >= 0 && flag[f] == 0) flag[f] = 1;
     }
-    if (i < n) member[i] = add ? 1 : 0;
 }
 
-static int sort_u64(mc_ctx* c, unsigned long long* keys_in, unsigned long long* keys_out, unsigned long long* vals_in,
-                    unsigned long long* vals_out, uint64_t n, int end_bit) {
-    size_t tmp_bytes = 0;
-    MC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n, 0,
-                                            end_bit, c->stream));
-    DevBuf tmp;
-    int rc = c->alloc(tmp_bytes, tmp);
-    if (rc != MC_OK) return rc;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n,
-                                                    0, end_bit, c->stream);
-    c->launches += 4;
-    c->release(tmp);
-    if (e != cudaSuccess) return cuda_fail(e, "cub::DeviceRadixSort::SortPairs");
-    return MC_OK;
+static __global__ void k_list_flagged(const uint8_t* __restrict__ flag, uint64_t n, unsigned long long* __restrict__ list,
+                                      unsigned long long* __restrict__ count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < n && flag[i] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, on);
+    if (b == 0u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs((int)b) - 1;
+    unsigned long long base = 0ull;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (on) list[base + __popc(b & ((1u << lane) - 1u))] = i;
 }
+
+static __global__ void __launch_bounds__(256)
+k_eval_side_nodes(const uint64_t* __restrict__ prog, const double* __restrict__ coords, long long n_verts,
+                  const double* __restrict__ lower_coords, const unsigned long long* __restrict__ list,
+                  const unsigned long long* __restrict__ count, uint8_t* __restrict__ flag) {
+    const uint64_t n = *count;
+    const double EPS = 2.220446049250313e-16;  // f64::EPSILON
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long f = list[i < n ? i : n - 1];
+        const double* p = (long long)f < n_verts ? coords + 3 * f : lower_coords + 3 * (f - (unsigned long long)n_verts);
+        const double phi = vm_eval<true>(prog, p[0], p[1], p[2]);
+        if (i < n) flag[f] = (phi > EPS || phi < -EPS) ? 1 : 2;
+    }
+}
+
+// EMIT = false: per block of 256 sides the number of members -> block_io; EMIT = true: write them
+template <typename IndexT, bool EMIT>
+__global__ void __launch_bounds__(256)
+k_sideset_select(const IndexT* __restrict__ tets, unsigned long long tet_base, const unsigned long long* __restrict__ sides,
+                 uint64_t n, long long vertex_base, long long n_verts, long long lower_first, long long lower_count,
+                 const uint8_t* __restrict__ flag, unsigned long long* __restrict__ block_io,
+                 unsigned long long* __restrict__ out) {
+    __shared__ uint32_t s_w[8];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool member = i < n;
+    if (member) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const long long f = flag_index(side_node(tets, tet_base, sides, i, k), vertex_base, n_verts, lower_first, lower_count);
+            member = member && f >= 0 && flag[f] == 2;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, member);
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (lane == 0u) s_w[wid] = (uint32_t)__popc(b);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < (int)wid) before += s_w[w]; total += s_w[w]; }
+    if (!EMIT) {
+        if (threadIdx.x == 0) block_io[blockIdx.x] = total;
+    } else if (member) {
+        const uint64_t o = block_io[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+        out[2 * o] = sides[2 * i];
+        out[2 * o + 1] = sides[2 * i + 1];
+    }
+}
+
+// ---- host orchestration ---------------------------------------------------------------------------
+namespace {
+struct Scratch {  // pooled buffers + events, released on every path
+    mc_ctx* c;
+    std::vector<DevBuf*> bufs;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit Scratch(mc_ctx* ctx) : c(ctx) {}
+    int alloc(size_t bytes, DevBuf& b) { bufs.push_back(&b); return c->alloc(bytes, b); }
+    ~Scratch() {
+        for (DevBuf* b : bufs) c->release(*b);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+}  // namespace
 
 int compute_boundary(mc_mesh* m) {
     mc_ctx* c = m->ctx;
     MC_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const Lattice& L = m->L;
-    if (m->c0 != 0 || m->c1 != L.nz)
-        return fail(MC_ERR_UNSUPPORTED, "Mesh::boundary on a z-slab: gather the slabs on one device first");
-    {
-        // per call: constant memory is per device, and the upload is a few hundred bytes
-        FaceTri tab[6][2];
-        build_cellface_table(tab);
-        MC_CUDA(cudaMemcpyToSymbolAsync(C_CELLFACE, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
-    }
-    cudaEvent_t e0, e1;
-    MC_CUDA(cudaEventCreate(&e0));
-    MC_CUDA(cudaEventCreate(&e1));
-    MC_CUDA(cudaEventRecord(e0, s));
+    if (L.nx >= (1u << 21) || L.ny >= (1u << 21) || L.nz >= (1u << 21))
+        return fail(MC_ERR_LIMIT, "Mesh::boundary: more than 2^21 cells along an axis");
+    Scratch sc(c);
+    MC_CUDA(cudaEventCreate(&sc.e0));
+    MC_CUDA(cudaEventCreate(&sc.e1));
+    MC_CUDA(cudaEventRecord(sc.e0, s));
     DevBuf ftot, fbase, dtotal;
-    int rc = c->alloc((m->n_tiles + 1) * 8, ftot);
-    if (rc == MC_OK) rc = c->alloc((m->n_tiles + 1) * 8, fbase);
-    if (rc == MC_OK) rc = c->alloc(4 * 8, dtotal);
+    int rc = sc.alloc((m->n_tiles + 1) * 8, ftot);
+    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, fbase);
+    if (rc == MC_OK) rc = sc.alloc(4 * 8, dtotal);
     if (rc != MC_OK) return rc;
-    MC_CUDA(cudaMemsetAsync(dtotal.p, 0, 32, s));
     unsigned long long* totals = (unsigned long long*)dtotal.p;
-    uint64_t nf = 0;
     const Stuff S = make_stuff(m);
-    if (m->n_tiles > 0) {
-        k_face_count<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)ftot.p);
-        c->launches += 1;
+    m->n_sides = 0;
+    m->h_sides.clear();
+    m->have_h_sides = false;
+    c->release(m->d_sides);
+    if (m->n_tiles > 0 && m->n_tets > 0) {
+        k_boundary_sides<false><<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)ftot.p, m->tet_base, nullptr);
+        c->launches++;
         MC_CUDA(cudaGetLastError());
         rc = scan_tiles(c, ftot.p, m->n_tiles, fbase.p, nullptr, m->d_scan_sums.p, totals);
         if (rc != MC_OK) return rc;
         unsigned long long h[2];
         MC_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, s));
         MC_CUDA(cudaStreamSynchronize(s));
-        nf = h[0];  // face totals never exceed 32 bits per tile, the scan keeps 64-bit sums
-    }
-    m->n_sides = 0;
-    m->h_sides.clear();
-    if (nf > 0) {
-        DevBuf khi, klo, pay, ia, ib, ka, kb;
-        rc = c->alloc(nf * 8, khi);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, klo);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, pay);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, ia);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, ib);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, ka);
-        if (rc == MC_OK) rc = c->alloc(nf * 8, kb);
-        if (rc == MC_OK) rc = c->alloc(nf * 16, m->d_sides);
-        if (rc != MC_OK) return rc;
-        k_face_emit<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(
-            S, (const unsigned long long*)fbase.p, m->tet_base, (unsigned long long*)khi.p, (unsigned long long*)klo.p,
-            (unsigned long long*)pay.p);
-        const unsigned nb = (unsigned)((nf + 255) / 256);
-        k_iota<<<nb, 256, 0, s>>>((unsigned long long*)ia.p, nf);
-        c->launches += 2;
-        MC_CUDA(cudaGetLastError());
-        // LSD: by the low key first, then (stable) by the high key
-        rc = sort_u64(c, (unsigned long long*)klo.p, (unsigned long long*)ka.p, (unsigned long long*)ia.p,
-                      (unsigned long long*)ib.p, nf, 64);
-        if (rc != MC_OK) return rc;
-        k_gather<<<nb, 256, 0, s>>>((const unsigned long long*)khi.p, (const unsigned long long*)ib.p, nf,
-                                    (unsigned long long*)kb.p);
-        c->launches++;
-        rc = sort_u64(c, (unsigned long long*)kb.p, (unsigned long long*)ka.p, (unsigned long long*)ib.p,
-                      (unsigned long long*)ia.p, nf, 64);
-        if (rc != MC_OK) return rc;
-        k_face_select<<<nb, 256, 0, s>>>((const unsigned long long*)khi.p, (const unsigned long long*)klo.p,
-                                         (const unsigned long long*)pay.p, (const unsigned long long*)ia.p, nf,
-                                         (unsigned long long*)ka.p, totals + 2);
-        c->launches++;
-        MC_CUDA(cudaGetLastError());
-        unsigned long long ns = 0;
-        MC_CUDA(cudaMemcpyAsync(&ns, totals + 2, 8, cudaMemcpyDeviceToHost, s));
-        MC_CUDA(cudaStreamSynchronize(s));
-        m->n_sides = ns;
-        if (ns) {
-            // sorted by (elem, side): the reference's HashSet order is arbitrary
-            size_t tmp_bytes = 0;
-            MC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (unsigned long long*)ka.p, (unsigned long long*)kb.p,
-                                                   (int64_t)ns, 0, 64, s));
-            DevBuf tmp;
-            rc = c->alloc(tmp_bytes, tmp);
+        m->n_sides = h[0];
+        if (m->n_sides) {
+            rc = c->alloc(m->n_sides * 16, m->d_sides);
             if (rc != MC_OK) return rc;
-            MC_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, (unsigned long long*)ka.p, (unsigned long long*)kb.p,
-                                                   (int64_t)ns, 0, 64, s));
-            k_unpack_sides<<<(unsigned)((ns + 255) / 256), 256, 0, s>>>((const unsigned long long*)kb.p, ns,
-                                                                       (unsigned long long*)m->d_sides.p);
-            c->launches += 5;
+            k_boundary_sides<true><<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)fbase.p, m->tet_base,
+                                                                                (unsigned long long*)m->d_sides.p);
+            c->launches++;
             MC_CUDA(cudaGetLastError());
-            MC_CUDA(cudaStreamSynchronize(s));
-            c->release(tmp);
         }
-        c->release(khi); c->release(klo); c->release(pay); c->release(ia); c->release(ib); c->release(ka); c->release(kb);
     }
-    MC_CUDA(cudaEventRecord(e1, s));
-    // host view, sorted (the reference's HashSet order is arbitrary)
-    m->h_sides.resize(m->n_sides * 2);
-    if (m->n_sides) MC_CUDA(cudaMemcpyAsync(m->h_sides.data(), m->d_sides.p, m->n_sides * 16, cudaMemcpyDeviceToHost, s));
-    MC_CUDA(cudaStreamSynchronize(s));
+    MC_CUDA(cudaEventRecord(sc.e1, s));
+    MC_CUDA(cudaEventSynchronize(sc.e1));
     float ms = 0;
-    MC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    MC_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
     m->stage_ms[7] = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    c->release(ftot); c->release(fbase); c->release(dtotal);
     m->have_boundary = true;
     return MC_OK;
 }
 
-int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, std::vector<uint64_t>& out) {
+int boundary_host_view(mc_mesh* m) {
+    if (m->have_h_sides) return MC_OK;
     mc_ctx* c = m->ctx;
     MC_CUDA(cudaSetDevice(c->device));
+    m->h_sides.resize(m->n_sides * 2);
+    if (m->n_sides) {
+        MC_CUDA(cudaMemcpyAsync(m->h_sides.data(), m->d_sides.p, m->n_sides * 16, cudaMemcpyDeviceToHost, c->stream));
+        MC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    m->have_h_sides = true;
+    return MC_OK;
+}
+
+template <typename IndexT>
+static int sideset_impl(mc_mesh* m, const Program& p, SideSetDev& out) {
+    mc_ctx* c = m->ctx;
     cudaStream_t s = c->stream;
-    out.clear();
+    Scratch sc(c);
+    MC_CUDA(cudaEventCreate(&sc.e0));
+    MC_CUDA(cudaEventCreate(&sc.e1));
+    MC_CUDA(cudaEventRecord(sc.e0, s));
+    const uint64_t ns = m->n_sides;
+    const long long nv = (long long)m->n_verts, lf = (long long)m->lower_first, lc = (long long)m->lower_count;
+    const uint64_t nflag = (uint64_t)nv + (uint64_t)lc;
+    const IndexT* tets = (const IndexT*)m->d_tets.p;
+    const unsigned long long* sides = (const unsigned long long*)m->d_sides.p;
+    const unsigned nb = (unsigned)((ns + 255) / 256);
+    int rc = MC_OK;
+    // 1 + 2: the surface vertices, once per mesh
+    if (!m->d_side_nodes.p) {
+        rc = c->alloc(std::max<uint64_t>(nflag, 1), m->d_side_flag);
+        if (rc == MC_OK) rc = c->alloc(std::max<uint64_t>(std::min<uint64_t>(3 * ns, nflag), 1) * 8 + 8, m->d_side_nodes);
+        if (rc != MC_OK) return rc;
+        MC_CUDA(cudaMemsetAsync(m->d_side_flag.p, 0, std::max<uint64_t>(nflag, 1), s));
+        MC_CUDA(cudaMemsetAsync(m->d_side_nodes.p, 0, 8, s));
+        k_mark_side_nodes<IndexT><<<nb, 256, 0, s>>>(tets, m->tet_base, sides, ns, (long long)m->vertex_base, nv, lf, lc,
+                                                     (uint8_t*)m->d_side_flag.p);
+        k_list_flagged<<<(unsigned)((nflag + 255) / 256), 256, 0, s>>>((const uint8_t*)m->d_side_flag.p, nflag,
+                                                                      (unsigned long long*)m->d_side_nodes.p + 1,
+                                                                      (unsigned long long*)m->d_side_nodes.p);
+        c->launches += 2;
+        MC_CUDA(cudaGetLastError());
+    }
+    // 3: the boundary object at every surface vertex
+    DevBuf dp, bcnt, bbase, dtot, sums;
+    sc.bufs.push_back(&dp);
+    rc = upload_program(c, p, dp);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nb + 1) * 8, bcnt);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nb + 1) * 8, bbase);
+    if (rc == MC_OK) rc = sc.alloc(32, dtot);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nb / SCAN_BLOCK + 2) * 16, sums);
+    if (rc != MC_OK) return rc;
+    k_eval_side_nodes<<<(unsigned)c->sm_count * 8u, 256, 0, s>>>((const uint64_t*)dp.p, (const double*)m->d_coords.p, nv, m->lower_coords,
+                                                                (const unsigned long long*)m->d_side_nodes.p + 1,
+                                                                (const unsigned long long*)m->d_side_nodes.p, (uint8_t*)m->d_side_flag.p);
+    // 4: select
+    k_sideset_select<IndexT, false><<<nb, 256, 0, s>>>(tets, m->tet_base, sides, ns, (long long)m->vertex_base, nv, lf, lc,
+                                                       (const uint8_t*)m->d_side_flag.p, (unsigned long long*)bcnt.p, nullptr);
+    c->launches += 2;
+    MC_CUDA(cudaGetLastError());
+    rc = scan_tiles(c, bcnt.p, nb, bbase.p, nullptr, sums.p, dtot.p);
+    if (rc != MC_OK) return rc;
+    unsigned long long h[2];
+    MC_CUDA(cudaMemcpyAsync(h, dtot.p, 16, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    out.n = h[0];
+    if (out.n) {
+        rc = c->alloc(out.n * 16, out.d_pairs);
+        if (rc != MC_OK) return rc;
+        k_sideset_select<IndexT, true><<<nb, 256, 0, s>>>(tets, m->tet_base, sides, ns, (long long)m->vertex_base, nv, lf, lc,
+                                                          (const uint8_t*)m->d_side_flag.p, (unsigned long long*)bbase.p,
+                                                          (unsigned long long*)out.d_pairs.p);
+        c->launches++;
+        MC_CUDA(cudaGetLastError());
+    }
+    MC_CUDA(cudaEventRecord(sc.e1, s));
+    MC_CUDA(cudaEventSynchronize(sc.e1));  // dp is recycled when `sc` goes out of scope
+    float ms = 0;
+    MC_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
+    m->stage_ms[8] += ms;
+    return MC_OK;
+}
+
+int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, SideSetDev& out) {
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    out.n = 0;
     if (m->n_sides == 0) return MC_OK;
     Program p;
     std::string err;
     // boundary.approx_value(point, f64::EPSILON), src/main.rs:95
     int rc = tape->compile(root, std::numeric_limits<double>::epsilon(), p, err);
     if (rc != MC_OK) return fail(rc, err);
-    DevBuf dp, dm;
-    rc = upload_program(c, p, dp);
-    if (rc != MC_OK) return rc;
-    rc = c->alloc(m->n_sides, dm);
-    if (rc != MC_OK) return rc;
-    cudaEvent_t e0, e1;
-    MC_CUDA(cudaEventCreate(&e0));
-    MC_CUDA(cudaEventCreate(&e1));
-    MC_CUDA(cudaEventRecord(e0, s));
-    const unsigned nb = (unsigned)((m->n_sides + 255) / 256);
-    if (m->index_bytes == 4)
-        k_sideset<uint32_t><<<nb, 256, 0, s>>>((const uint64_t*)dp.p, (const double*)m->d_coords.p,
-                                               (const uint32_t*)m->d_tets.p, (int64_t)m->vertex_base, m->tet_base,
-                                               (const unsigned long long*)m->d_sides.p, m->n_sides, (uint8_t*)dm.p);
-    else
-        k_sideset<unsigned long long><<<nb, 256, 0, s>>>((const uint64_t*)dp.p, (const double*)m->d_coords.p,
-                                                         (const unsigned long long*)m->d_tets.p, (int64_t)m->vertex_base,
-                                                         m->tet_base, (const unsigned long long*)m->d_sides.p,
-                                                         m->n_sides, (uint8_t*)dm.p);
-    c->launches++;
-    MC_CUDA(cudaGetLastError());
-    MC_CUDA(cudaEventRecord(e1, s));
-    std::vector<uint8_t> member(m->n_sides);
-    MC_CUDA(cudaMemcpyAsync(member.data(), dm.p, m->n_sides, cudaMemcpyDeviceToHost, s));
-    MC_CUDA(cudaStreamSynchronize(s));
-    float ms = 0;
-    MC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    m->stage_ms[8] += ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    for (uint64_t i = 0; i < m->n_sides; ++i)
-        if (member[i]) { out.push_back(m->h_sides[2 * i]); out.push_back(m->h_sides[2 * i + 1]); }
-    c->release(dp);
-    c->release(dm);
-    return MC_OK;
+    return m->index_bytes == 4 ? sideset_impl<uint32_t>(m, p, out) : sideset_impl<unsigned long long>(m, p, out);
 }
 
 }  // namespace mc

@@ -18,6 +18,14 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+// one side-set: (elem, side) pairs on the device, host copy on demand
+struct SideSetDev {
+    DevBuf d_pairs;
+    uint64_t n = 0;
+    std::vector<uint64_t> h;
+    bool have_h = false;
+};
+
 }  // namespace mc
 
 struct mc_ctx {
@@ -86,11 +94,12 @@ struct mc_mesh {
     bool have_h_coords = false, have_h_tets = false;
 
     // boundary / side-sets (mc_boundary.cu)
-    bool have_boundary = false;
-    mc::DevBuf d_sides;  // (elem, side) pairs, uint64 x 2
+    bool have_boundary = false, have_h_sides = false;
+    mc::DevBuf d_sides;  // (elem, side) pairs, uint64 x 2, sorted
     uint64_t n_sides = 0;
     std::vector<uint64_t> h_sides;
-    std::vector<std::vector<uint64_t>> h_sidesets;
+    mc::DevBuf d_side_flag, d_side_nodes;  // per-vertex flags / list of the surface vertices (side-sets)
+    std::vector<mc::SideSetDev> sidesets;
 };
 
 namespace mc {
@@ -107,5 +116,6 @@ int upload_program(mc_ctx* ctx, const Program& p, DevBuf& out);
 int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base_hi, void* sums, void* totals);
 // boundary + side-sets implementation (mc_boundary.cu)
 int compute_boundary(mc_mesh* m);
-int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, std::vector<uint64_t>& out);
+int boundary_host_view(mc_mesh* m);
+int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, SideSetDev& out);
 }  // namespace mc

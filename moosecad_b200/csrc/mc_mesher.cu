@@ -185,6 +185,9 @@ static void mesh_release_all(mc_mesh* m) {
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
                       &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub, &m->d_tile_list, &m->d_scan_sums};
     for (DevBuf* b : bufs) c->release(*b);
+    c->release(m->d_side_flag);
+    c->release(m->d_side_nodes);
+    for (auto& ss : m->sidesets) c->release(ss.d_pairs);
     for (auto& e : m->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
 }
@@ -1147,25 +1150,49 @@ int mc_mesh_boundary(mc_mesh* m, uint64_t* n_sides) {
 }
 const uint64_t* mc_mesh_boundary_sides(mc_mesh* m) {
     if (mc_mesh_boundary(m, nullptr) != MC_OK) return nullptr;
+    if (boundary_host_view(m) != MC_OK) return nullptr;
     return m->h_sides.data();
+}
+int mc_mesh_boundary_device(mc_mesh* m, void** d_sides, uint64_t* n_sides) {
+    int rc = mc_mesh_boundary(m, n_sides);
+    if (rc != MC_OK) return rc;
+    if (d_sides) *d_sides = m->d_sides.p;
+    return MC_OK;
 }
 int mc_mesh_add_sideset(mc_mesh* m, const mc_tape* boundary, int32_t root) {
     if (!m || !boundary) return fail(MC_ERR_ARG, "mc_mesh_add_sideset: null handle");
     int rc = mc_mesh_boundary(m, nullptr);
     if (rc != MC_OK) return rc;
-    std::vector<uint64_t> set;
-    rc = compute_sideset(m, boundary, root, set);
-    if (rc != MC_OK) return rc;
-    m->h_sidesets.push_back(std::move(set));
-    return (int)m->h_sidesets.size() - 1;
+    SideSetDev ss;
+    rc = compute_sideset(m, boundary, root, ss);
+    if (rc != MC_OK) { m->ctx->release(ss.d_pairs); return rc; }
+    m->sidesets.push_back(std::move(ss));
+    return (int)m->sidesets.size() - 1;
 }
 uint64_t mc_mesh_sideset_len(const mc_mesh* m, int i) {
-    if (!m || i < 0 || (size_t)i >= m->h_sidesets.size()) return 0;
-    return m->h_sidesets[(size_t)i].size() / 2;
+    if (!m || i < 0 || (size_t)i >= m->sidesets.size()) return 0;
+    return m->sidesets[(size_t)i].n;
 }
 const uint64_t* mc_mesh_sideset(mc_mesh* m, int i) {
-    if (!m || i < 0 || (size_t)i >= m->h_sidesets.size()) { fail(MC_ERR_ARG, "mc_mesh_sideset: bad index"); return nullptr; }
-    return m->h_sidesets[(size_t)i].data();
+    if (!m || i < 0 || (size_t)i >= m->sidesets.size()) { fail(MC_ERR_ARG, "mc_mesh_sideset: bad index"); return nullptr; }
+    SideSetDev& ss = m->sidesets[(size_t)i];
+    if (!ss.have_h) {
+        ss.h.resize(ss.n * 2 + 1);
+        if (ss.n) {
+            cudaSetDevice(m->ctx->device);
+            cudaError_t e = cudaMemcpyAsync(ss.h.data(), ss.d_pairs.p, ss.n * 16, cudaMemcpyDeviceToHost, m->ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->ctx->stream);
+            if (e != cudaSuccess) { cuda_fail(e, "mc_mesh_sideset"); return nullptr; }
+        }
+        ss.have_h = true;
+    }
+    return ss.h.data();
+}
+int mc_mesh_sideset_device(mc_mesh* m, int i, void** d_pairs, uint64_t* n) {
+    if (!m || i < 0 || (size_t)i >= m->sidesets.size()) return fail(MC_ERR_ARG, "mc_mesh_sideset_device: bad index");
+    if (d_pairs) *d_pairs = m->sidesets[(size_t)i].d_pairs.p;
+    if (n) *n = m->sidesets[(size_t)i].n;
+    return MC_OK;
 }
 
 // ---- mesh-crate predicates ---------------------------------------------------------------

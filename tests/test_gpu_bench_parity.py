@@ -140,6 +140,13 @@ def test_topology_vs_platform_libm(scene, n, oracle, ctx):
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, f"r02_libm_topology_diff_{scene}_{n}.json"), "w") as f:
             json.dump(d, f, indent=1)
-    # sign-robust everywhere (|phi| >> 1 ulp) except on a measure-zero set: allow a handful
-    assert d["tets_only_a"] + d["tets_only_b"] <= max(8, d["tets_a"] // 10000), d
-    assert abs(d["vertices_a"] - d["vertices_b"]) <= 4, d
+    # Identical on the CSG scene.  xplicit.lua is mirror-symmetric in y / z: a vertex whose two best
+    # warp candidates are equal in exact arithmetic ("first visit wins" decides) sees them differ by
+    # an ulp under one libm and not the other, and is pulled along the mirror-image edge: 8 of 27 288
+    # vertices (one per octant) at N = 48, with the ~23 tets around each.  Counts and statistics agree.
+    assert st["stats"] == ost["stats"] and st["n_warped"] == ost["n_warped"] and st["n_cut"] == ost["n_cut"]
+    assert d["vertices_a"] == d["vertices_b"] and d["tets_a"] == d["tets_b"]
+    assert d["vertices_only_a"] <= max(8, d["vertices_a"] // 2000), d
+    assert d["tets_only_a"] <= max(200, d["tets_a"] // 400), d
+    if scene == "csg64":
+        assert d["tets_only_a"] == 0 and d["vertices_only_a"] == 0, d
