@@ -224,6 +224,16 @@ int mc_mesh_copy_upper_layer_coords(mc_mesh*, void* d_dst);
 /* all phases for the whole lattice on one device */
 int mc_tessellate(mc_ctx*, const mc_tape* volume, int32_t root, double resolution,
                   double relative_error, const mc_options* opts, mc_mesh** out);
+/* The same job sharded into z-slabs over n devices driven by THIS process (the
+ * `devices, ndev` form of the mesher call; what a single-process host like src/main.rs:74-82 uses).
+ * ctxs[i]: the context (device + stream + workspace) that meshes slab i, bottom to top; the contexts
+ * must be distinct (they may share a device).  One host thread per context runs inside the call;
+ * slab boundaries come from the load estimate; the per-slab counts are exchanged in host memory, the
+ * id table of every shared plane and the coordinates next to it travel device to device
+ * (cudaMemcpyPeerAsync).  out[i] receives slab i's mesh: GLOBAL vertex ids, tets / boundary sides
+ * numbered from the slab's global tet offset; the caller frees each with mc_mesh_free. */
+int mc_tessellate_multi(mc_ctx* const* ctxs, int n, const mc_tape* volume, int32_t root, double resolution,
+                        double relative_error, const mc_options* opts, mc_mesh** out);
 void mc_mesh_free(mc_mesh*);
 
 /* counts: [0] vertices owned by this slab, [1] tets, [2] lattice points evaluated (incl.

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mc_mesh_copy_upper_layer_coords": (C.c_int, [_P, _P]),
     "mc_tessellate_emit_tets": (C.c_int, [_P, _U64, _P]),
     "mc_tessellate": (C.c_int, [_P, _P, _I32, _D, _D, C.POINTER(mc_options), C.POINTER(_P)]),
+    "mc_tessellate_multi": (C.c_int, [C.POINTER(_P), C.c_int, _P, _I32, _D, _D, C.POINTER(mc_options), C.POINTER(_P)]),
     "mc_mesh_free": (None, [_P]),
     "mc_mesh_counts": (C.c_int, [_P, _PU64]),
     "mc_mesh_prune_stats": (C.c_int, [_P, _PU64, _PU64, _PU64]),

@@ -65,6 +65,7 @@ struct mc_mesh {
     mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo;
     mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign, d_sub;
     mc::DevBuf d_ttile_tot, d_ttile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
+    mc::DevBuf own_lower_table, own_lower_coords;  // copies pulled from the slab below (mc_tessellate_multi)
     const void* lower_table = nullptr;  // id table of plane c0 from the rank below (caller-owned)
     const double* lower_coords = nullptr;  // coordinates of the rank below's top tile layer (caller-owned)
     uint64_t lower_first = 0, lower_count = 0;  // global ids [first, first + count) of that slice
@@ -73,6 +74,7 @@ struct mc_mesh {
     bool vertices_local_done = false;  // mc_tessellate_emit_vertices_local has run
     mc::DevBuf d_counters, d_cutlist, d_coords, d_tets, d_plane_table;
     mc::DevBuf d_inst_start, d_word_inst, d_dec;  // tile specialisation (mc_prune.cuh)
+    mc::DevBuf d_lists;                           // work lists of the tile kernels: 4 x n_tiles uint32 (TileLists)
     mc::DevBuf d_scan_sums;                       // block sums of the tile scans (k_scan_tiles_local / _add)
     mc::DevBuf d_tile_list;                       // tiles the SDF kernel evaluates (the others are proven)
     uint64_t n_tiles = 0;

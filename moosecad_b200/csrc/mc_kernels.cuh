@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_SDF_LIST, CN_SDF_NEXT, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_SDF_LIST, CN_SDF_NEXT, CN_LIST_VNEG, CN_LIST_CFULL, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -50,6 +50,33 @@ __host__ __device__ __forceinline__ uint32_t ci_count(uint16_t ci) {
 // per-vertex mask written by k_vertex_count (ACTIVE point tiles only)
 constexpr uint16_t VM_CUT_MASK = 0x01ff;   // bit s: the edge along canonical direction s is cut
 constexpr uint16_t VM_USED = 1u << 15;     // the lattice vertex itself is in the output
+
+// Work lists of the tile kernels: only the tiles that have something to do are visited, blocks take
+// them one at a time from a cursor (tiles differ in cost by orders of magnitude).
+struct TileLists {
+    const uint32_t* v_active;  // point tiles on the general path (VU_ACTIVE)
+    const uint32_t* v_neg;     // interior point tiles (VU_NEG): arithmetic vertices
+    const uint32_t* c_active;  // cell tiles on the general path (CU_ACTIVE)
+    const uint32_t* c_full;    // interior cell tiles (CU_FULL): five lattice tets per cell
+    const unsigned long long* n_v_active;  // list lengths (device counters)
+    const unsigned long long* n_v_neg;
+    const unsigned long long* n_c_active;
+    const unsigned long long* n_c_full;
+};
+constexpr int TILE_GRID_PER_SM = 8;  // blocks launched per SM by the list kernels (they loop)
+
+// next work item of this block: false when the list is exhausted.  All threads must call it.
+__device__ __forceinline__ bool next_tile(const uint32_t* __restrict__ list, const unsigned long long* __restrict__ n,
+                                          unsigned long long* __restrict__ cursor, uint32_t& tile) {
+    __shared__ unsigned long long s_item;
+    __syncthreads();  // the previous tile is done with shared memory (and s_item has been read)
+    if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1ull);
+    __syncthreads();
+    const unsigned long long i = s_item;
+    if (i >= *n) return false;
+    tile = list[i];
+    return true;
+}
 
 // everything the stuffing kernels need about one slab
 struct Stuff {
@@ -233,33 +260,61 @@ k_tile_minmax(Stuff S) {
     }
 }
 
+// owned points of a tile: x, y extents and the owned z range [zlo, zhi) (may be empty)
+struct TileBox { uint32_t X0, Y0, Z0, nxt, nyt, zlo, zhi; };
+__device__ __forceinline__ TileBox tile_box(const Stuff& S, uint64_t t) {
+    TileBox b;
+    tile_origin(S.g, t, b.X0, b.Y0, b.Z0);
+    b.nxt = min(TS, S.L.NX - b.X0);
+    b.nyt = min(TS, S.L.NY - b.Y0);
+    b.zlo = max(b.Z0, S.oz0);
+    b.zhi = min(b.Z0 + TS, S.oz1 + 1);
+    if (b.zhi < b.zlo) b.zhi = b.zlo;
+    return b;
+}
+
 // point tiles: uniformly negative / positive together with everything one lattice step around them?
 // Either the interval pass proved it (tile sign: the proof covers the tile's box grown by one step),
-// or the stored values say so for the whole 27-neighbourhood of tiles.
-static __global__ void k_tile_neighbourhood(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters) {
+// or the stored values say so for the whole 27-neighbourhood of tiles.  Uniform tiles get their
+// vertex totals here (interior: every owned point is an output vertex, no cut edges); active and
+// interior tiles are appended to the work lists of the vertex kernels.
+static __global__ void k_tile_neighbourhood(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters,
+                                            uint32_t* __restrict__ list_active, uint32_t* __restrict__ list_neg,
+                                            unsigned long long* __restrict__ vtile_tot) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
+    uint8_t u;
     if (S.L.tsign != nullptr && S.L.tsign[t] != 0) {
-        S.vuni[t] = S.L.tsign[t] < 0 ? VU_NEG : VU_POS;
-        return;
+        u = S.L.tsign[t] < 0 ? VU_NEG : VU_POS;
+    } else {
+        const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
+        uint8_t all = TF_NEG | TF_POS;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int x = tix + dx, y = tiy + dy, z = tiz + dz;
+                    if (x < 0 || y < 0 || z < 0 || x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) continue;
+                    all &= S.tflag[((size_t)z * S.g.nty + y) * S.g.ntx + x];
+                }
+        u = (all & TF_NEG) ? VU_NEG : ((all & TF_POS) ? VU_POS : VU_ACTIVE);
     }
-    const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
-    uint8_t all = TF_NEG | TF_POS;
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = tix + dx, y = tiy + dy, z = tiz + dz;
-                if (x < 0 || y < 0 || z < 0 || x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) continue;
-                all &= S.tflag[((size_t)z * S.g.nty + y) * S.g.ntx + x];
-            }
-    const uint8_t u = (all & TF_NEG) ? VU_NEG : ((all & TF_POS) ? VU_POS : VU_ACTIVE);
     S.vuni[t] = u;
-    if (u == VU_ACTIVE) atomicAdd(&counters[CN_ACTIVE_VTILES], 1ull);
+    if (u == VU_ACTIVE) {
+        list_active[atomicAdd(&counters[CN_ACTIVE_VTILES], 1ull)] = (uint32_t)t;
+    } else {
+        const TileBox b = tile_box(S, t);
+        const unsigned long long n = u == VU_NEG ? (unsigned long long)b.nxt * b.nyt * (b.zhi - b.zlo) : 0ull;
+        vtile_tot[t] = n;
+        if (n) list_neg[atomicAdd(&counters[CN_LIST_VNEG], 1ull)] = (uint32_t)t;
+    }
 }
 
 // cell tiles: the 8 tiles holding the corners are all negative and un-warped (every cell emits
-// its five lattice tets) / all positive (nothing is kept)?
-static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters) {
+// its five lattice tets) / all positive (nothing is kept)?  Uniform tiles get their tet totals here
+// (low 32 bits: output tets, high 32 bits: kept lattice tets, owned cells only).
+static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ counters,
+                                         uint32_t* __restrict__ list_active, uint32_t* __restrict__ list_full,
+                                         unsigned long long* __restrict__ ttile_tot) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     const int tix = (int)(t % S.g.ntx), tiy = (int)((t / S.g.ntx) % S.g.nty), tiz = (int)(t / ((uint64_t)S.g.ntx * S.g.nty));
@@ -274,7 +329,24 @@ static __global__ void k_cell_tile_class(Stuff S, uint64_t ntiles, unsigned long
             }
     const uint8_t u = ((all & TF_NEG) && !(any & TF_HASWARP)) ? CU_FULL : ((all & TF_POS) ? CU_EMPTY : CU_ACTIVE);
     S.cuni[t] = u;
-    if (u == CU_ACTIVE) atomicAdd(&counters[CN_ACTIVE_CTILES], 1ull);
+    const Lattice& L = S.L;
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, t, X0, Y0, Z0);
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    const bool has_cells = X0 < L.nx && Y0 < L.ny;
+    if (u == CU_ACTIVE) {
+        // (classification also covers the halo layers, so every active tile with cells is listed)
+        if (has_cells) list_active[atomicAdd(&counters[CN_ACTIVE_CTILES], 1ull)] = (uint32_t)t;
+        else ttile_tot[t] = 0ull;
+    } else {
+        unsigned long long tot = 0ull;
+        if (u == CU_FULL && has_cells && zhi > zlo) {
+            const unsigned long long n = (unsigned long long)min(TS, L.nx - X0) * min(TS, L.ny - Y0) * (zhi - zlo) * 5ull;
+            tot = n | (n << 32);
+            list_full[atomicAdd(&counters[CN_LIST_CFULL], 1ull)] = (uint32_t)t;
+        }
+        ttile_tot[t] = tot;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -298,8 +370,8 @@ __host__ __device__ constexpr KDir kdir(int d) {
 }
 
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
-    if (S.vuni[blockIdx.x] != VU_ACTIVE) return;
+k_warp_codes(Stuff S, unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
+             const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     constexpr int H = (int)TS + 2;
     __shared__ int8_t s_sg[H * H * H];
     __shared__ unsigned long long s_tab[8 * WT_STRIDE];
@@ -308,11 +380,13 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
     __shared__ uint16_t s_list[TILE_POINTS];
     __shared__ uint32_t s_n;
     const Lattice& L = S.L;
-    uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (threadIdx.x == 0) { s_n = 0u; s_nan = 0u; }
     for (int i = (int)threadIdx.x; i < 8 * WT_STRIDE; i += TILE_THREADS) s_tab[i] = S.warp_table[i];
     for (int i = (int)threadIdx.x; i < 8 * WP_STRIDE; i += TILE_THREADS) s_pairs[i] = (uint8_t)S.warp_table[8 * WT_STRIDE + i];
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {
+    uint32_t X0, Y0, Z0;
+    tile_origin(S.g, tile, X0, Y0, Z0);
+    if (threadIdx.x == 0) { s_n = 0u; s_nan = 0u; }
     __syncthreads();
     stage_points<H, -1, false>(L, X0, Y0, Z0, [&](int idx, bool in, double v, uint8_t) {
         const int8_t sg = !in ? SG_NONE : (v > 0.0 ? SG_POS : (v < 0.0 ? SG_NEG : (v == 0.0 ? SG_ZERO : SG_NAN)));
@@ -425,10 +499,11 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
     }
     // tflag bytes are updated through their aligned 32-bit word
     if (__any_sync(0xffffffffu, warped_any) && (threadIdx.x & 31u) == 0u)
-        atomicOr((unsigned int*)(S.tflag + (blockIdx.x & ~3u)), (unsigned int)TF_HASWARP << (8u * (blockIdx.x & 3u)));
+        atomicOr((unsigned int*)(S.tflag + (tile & ~3u)), (unsigned int)TF_HASWARP << (8u * (tile & 3u)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warped_owned += __shfl_xor_sync(0xffffffffu, warped_owned, o);
     if (warped_owned && (threadIdx.x & 31u) == 0u) atomicAdd(&counters[CN_WARPED], (unsigned long long)warped_owned);
+    }  // tiles
 }
 
 // ---------------------------------------------------------------------------------------
@@ -439,27 +514,14 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters) {
 // the tets of the remaining (surface) cells are collected and classified one per thread.
 static __global__ void __launch_bounds__(TILE_THREADS, 3)
 k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long* __restrict__ tile_tot,
-                 unsigned long long* __restrict__ counters) {
+                 unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
+                 const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     __shared__ unsigned long long s_acc;
     const Lattice& L = S.L;
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {  // active cell tiles (the others were settled by k_cell_tile_class)
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    const uint8_t cu = S.cuni[blockIdx.x];
-    if (cu != CU_ACTIVE) {
-        if (threadIdx.x == 0) {
-            unsigned long long tot = 0ull;
-            if (cu == CU_FULL && X0 < L.nx && Y0 < L.ny) {
-                const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-                if (zhi > zlo) {
-                    const unsigned long long n =
-                        (unsigned long long)min(TS, L.nx - X0) * min(TS, L.ny - Y0) * (zhi - zlo) * 5ull;
-                    tot = n | (n << 32);
-                }
-            }
-            tile_tot[blockIdx.x] = tot;
-        }
-        return;
-    }
+    tile_origin(S.g, tile, X0, Y0, Z0);
     // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0
     constexpr int H = (int)TS + 1;
     __shared__ uint8_t s_cls[H * H * H];
@@ -469,6 +531,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     __shared__ uint32_t s_stat[8];             // trim cases 0..6 + exterior removals of the owned cells
     if (threadIdx.x == 0) s_n = 0u;
     if (threadIdx.x < 8) s_stat[threadIdx.x] = 0u;
+    __syncthreads();
     stage_points<H, 0, true>(L, X0, Y0, Z0, [&](int idx, bool in, double raw, uint8_t wc) {
         const double w = (wc & 0x7f) ? 0.0 : raw;
         s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0)) : (uint8_t)0;
@@ -541,12 +604,13 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
         __syncthreads();
     }
     const unsigned long long tot = block_sum((unsigned long long)my_out | ((unsigned long long)my_kept << 32), &s_acc);
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+    if (threadIdx.x == 0) tile_tot[tile] = tot;
     const unsigned long long listed = block_sum((unsigned long long)my_listed, &s_acc);
     if (threadIdx.x == 0 && listed) atomicAdd(&counters[CN_LISTED_TETS], listed);
     // the statistics leave the block as at most 8 global atomics
     if (threadIdx.x < 8 && s_stat[threadIdx.x])
         atomicAdd(&counters[threadIdx.x < 7 ? CN_STAT0 + (int)threadIdx.x : (int)CN_EXT_REMOVED], (unsigned long long)s_stat[threadIdx.x]);
+    }  // tiles
 }
 
 // ---------------------------------------------------------------------------------------
@@ -625,30 +689,14 @@ k_scan_tiles_add(uint64_t n, unsigned long long* __restrict__ base_lo, unsigned 
 // a10 (vertices), pass 1: for every owned lattice vertex decide whether it is in the output
 // and which of its nine owned edges carry a cut vertex.  Tile totals: low = output vertices,
 // high = cut edges.
-// owned points of a tile: x, y extents and the owned z range [zlo, zhi) (may be empty)
-struct TileBox { uint32_t X0, Y0, Z0, nxt, nyt, zlo, zhi; };
-__device__ __forceinline__ TileBox tile_box(const Stuff& S, uint64_t t) {
-    TileBox b;
-    tile_origin(S.g, t, b.X0, b.Y0, b.Z0);
-    b.nxt = min(TS, S.L.NX - b.X0);
-    b.nyt = min(TS, S.L.NY - b.Y0);
-    b.zlo = max(b.Z0, S.oz0);
-    b.zhi = min(b.Z0 + TS, S.oz1 + 1);
-    if (b.zhi < b.zlo) b.zhi = b.zlo;
-    return b;
-}
-
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
+k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot, const uint32_t* __restrict__ tile_list,
+               const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     __shared__ unsigned long long s_acc;
     const Lattice& L = S.L;
-    const TileBox b = tile_box(S, blockIdx.x);
-    const uint8_t vu = S.vuni[blockIdx.x];
-    if (vu != VU_ACTIVE) {
-        if (threadIdx.x == 0)
-            tile_tot[blockIdx.x] = vu == VU_NEG ? (unsigned long long)b.nxt * b.nyt * (b.zhi - b.zlo) : 0ull;
-        return;
-    }
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {  // active point tiles (the others were settled by k_tile_neighbourhood)
+    const TileBox b = tile_box(S, tile);
     // post-warp classes of the tile's points with a one-point halo:
     // 0 none, 1 negative, 2 positive, 3 zero (not in the output), 4 zero used by some output tet
     constexpr int H = (int)TS + 2;
@@ -683,7 +731,8 @@ k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot) {
         mine += (unsigned long long)(ncut + ((m & VM_USED) ? 1u : 0u)) | ((unsigned long long)ncut << 32);
     }
     const unsigned long long tot = block_sum(mine, &s_acc);
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+    if (threadIdx.x == 0) tile_tot[tile] = tot;
+    }  // tiles
 }
 
 // global id of a lattice vertex's first output + its mask.  Interior tiles are pure arithmetic.
@@ -713,20 +762,18 @@ __device__ __forceinline__ long long cut_vertex_id(long long owner_base, uint16_
 // a10 (vertices), pass 2: number the output vertices tile by tile (lattice vertex first, then
 // its cut edges in slot order), write the coordinates of the lattice vertices (warped where
 // applicable) and append the cut edges to the bisection work list.
+// interior point tiles: every owned point is an un-warped output vertex, id = tile base + linear
+// index.  256 vertices at a time go through shared memory so that the xyz triples leave as three
+// fully coalesced stores per thread instead of 24-byte strided ones.
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double* __restrict__ coords,
-              unsigned long long* __restrict__ cutlist) {
-    __shared__ uint32_t s_scan[9];
+k_vertex_emit_interior(Stuff S, double* __restrict__ coords, const uint32_t* __restrict__ tile_list,
+                       const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
+    __shared__ double s_xyz[3 * TILE_THREADS];
     const Lattice& L = S.L;
-    const TileBox b = tile_box(S, blockIdx.x);
-    const uint8_t vu = S.vuni[blockIdx.x];
-    if (vu == VU_POS || b.zhi == b.zlo) return;
-    const uint64_t vb = S.tvbase[blockIdx.x];
-    if (vu == VU_NEG) {
-        // every owned point is an un-warped output vertex: id = tile base + linear index.  256
-        // vertices at a time go through shared memory so that the xyz triples leave as three fully
-        // coalesced stores per thread instead of 24-byte strided ones.
-        __shared__ double s_xyz[3 * TILE_THREADS];
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {
+        const TileBox b = tile_box(S, tile);
+        const uint64_t vb = S.tvbase[tile];
         const uint32_t n = b.nxt * b.nyt * (b.zhi - b.zlo);
         for (uint32_t base = 0; base < n; base += TILE_THREADS) {
             const uint32_t j = base + threadIdx.x;
@@ -742,8 +789,20 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
             for (uint32_t e = threadIdx.x; e < m3; e += TILE_THREADS) o[e] = s_xyz[e];
             __syncthreads();
         }
-        return;
     }
+}
+
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double* __restrict__ coords,
+              unsigned long long* __restrict__ cutlist, const uint32_t* __restrict__ tile_list,
+              const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
+    __shared__ uint32_t s_scan[9];
+    const Lattice& L = S.L;
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {  // active point tiles
+    const TileBox b = tile_box(S, tile);
+    if (b.zhi == b.zlo) continue;
+    const uint64_t vb = S.tvbase[tile];
     // Numbering: every thread takes one x-row of 16 points (consecutive in the numbering) and one
     // block scan of the row totals (low half: output vertices, high half: cut edges; <= 40960 /
     // 36864 per tile) gives each point's first local id and cut-list slot ...
@@ -775,7 +834,7 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
     }
     __syncthreads();
     // ... and the outputs are written with consecutive lanes on consecutive points
-    const uint64_t cb = tile_cbase[blockIdx.x];
+    const uint64_t cb = tile_cbase[tile];
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
         const uint32_t X = b.X0 + (j & 15u), Y = b.Y0 + ((j >> 4) & 15u), Z = b.Z0 + (j >> 8);
@@ -794,6 +853,7 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
         for (int s = 0; s < 9; ++s)
             if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
     }
+    }  // tiles
 }
 
 // a8: cut_edge — bisection of the real SDF between the positive and the negative end of
@@ -984,14 +1044,15 @@ static __device__ __forceinline__ void lattice_cell_quality(const Lattice& L, ui
 // evaluated once per distinct (step, parity) combination of the tile, weighted by multiplicity.
 template <typename IndexT>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit_full(Stuff S, IndexT* __restrict__ tets) {
+k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, const uint32_t* __restrict__ tile_list,
+                const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     const Lattice& L = S.L;
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {  // interior cell tiles with owned cells
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (S.cuni[blockIdx.x] != CU_FULL || X0 >= L.nx || Y0 >= L.ny) return;
+    tile_origin(S.g, tile, X0, Y0, Z0);
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (zhi <= zlo) return;
-    const uint64_t tb = S.ttbase[blockIdx.x];
+    const uint64_t tb = S.ttbase[tile];
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint32_t nxt = min(TS, L.nx - X0), nyt = min(TS, L.ny - Y0);
     // the (up to) 8 point tiles holding the corners of this cell tile
@@ -1000,9 +1061,9 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets) {
     __shared__ TileBox s_nbox[8];
     __shared__ __align__(16) IndexT s_out[5][TILE_THREADS][4];
     if (threadIdx.x < 8) {
-        const uint32_t tix = (uint32_t)(blockIdx.x % S.g.ntx) + (threadIdx.x & 1u);
-        const uint32_t tiy = (uint32_t)((blockIdx.x / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
-        const uint32_t tiz = (uint32_t)(blockIdx.x / (S.g.ntx * S.g.nty)) + (threadIdx.x >> 2);
+        const uint32_t tix = (uint32_t)(tile % S.g.ntx) + (threadIdx.x & 1u);
+        const uint32_t tiy = (uint32_t)((tile / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
+        const uint32_t tiz = (uint32_t)(tile / (S.g.ntx * S.g.nty)) + (threadIdx.x >> 2);
         uint8_t vu = VU_ACTIVE;
         if (tix < S.g.ntx && tiy < S.g.nty && tiz < S.g.ntz) {
             const uint32_t t = (tiz * S.g.nty + tiy) * S.g.ntx + tix;
@@ -1058,6 +1119,7 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets) {
         }
         __syncthreads();
     }
+    }  // tiles
 }
 
 // check_for_inverted_tets over the interior tiles: an un-warped lattice tet only depends on the
@@ -1144,16 +1206,18 @@ __device__ __forceinline__ void store_tet(unsigned long long* tets, uint64_t o, 
 template <typename IndexT, bool QUALITY>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ qlist,
-           unsigned long long* __restrict__ counters) {
+           unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
+           const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     extern __shared__ __align__(16) unsigned char te_smem[];
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_n;
     const Lattice& L = S.L;
+    uint32_t tile;
+    while (next_tile(tile_list, n_list, cursor, tile)) {  // active cell tiles
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
+    tile_origin(S.g, tile, X0, Y0, Z0);
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (zhi <= zlo) return;
+    if (zhi <= zlo) continue;  // halo layers only
     IndexT* s_gid = reinterpret_cast<IndexT*>(te_smem);
     uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_gid + TE_NP);
     uint16_t* s_ci = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(s_mask + TE_NP) + 15) & ~(uintptr_t)15);
@@ -1162,7 +1226,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     uint16_t* s_qoff = s_list + TILE_POINTS; // first quality-list slot of the cell, relative to the tile
     __shared__ unsigned long long s_qbase;
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
-    const uint64_t tb = S.ttbase[blockIdx.x];
+    const uint64_t tb = S.ttbase[tile];
     if (threadIdx.x == 0) s_n = 0u;
     // 1. vertex ids / masks of the tile's corners.  The (TS+1)^3 points lie in at most 8 tiles:
     //    their class, id base and owned box are staged once, so that a point costs no dependent
@@ -1308,6 +1372,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             ++o;
         }
     }
+    }  // tiles
 }
 
 // check_for_inverted_tets for the plain lattice tets of the SURFACE tiles (untouched cells with
@@ -1405,15 +1470,18 @@ struct QualityClasses {
 };
 
 // interior cell tiles: every cell is plain, all combinations of the tile's classes occur
-static __global__ void __launch_bounds__(32)
-k_quality_mark_full(Stuff S, QualityClasses Q) {
+static __global__ void __launch_bounds__(256)
+k_quality_mark_full(Stuff S, QualityClasses Q, const uint32_t* __restrict__ tile_list,
+                    const unsigned long long* __restrict__ n_list) {
     const Lattice& L = S.L;
+    // one warp per listed tile (interior cell tiles with owned cells)
+    const unsigned long long item = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= *n_list) return;
+    const uint32_t tile = tile_list[item];
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (S.cuni[blockIdx.x] != CU_FULL || X0 >= L.nx || Y0 >= L.ny) return;
+    tile_origin(S.g, tile, X0, Y0, Z0);
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (zhi <= zlo) return;
-    const uint32_t lane = threadIdx.x, i = lane & 15u;
+    const uint32_t lane = threadIdx.x & 31u, i = lane & 15u;
     uint32_t bx = 0u, by = 0u, bz = 0u;
     if (lane < 16u) {
         if (X0 + i < L.nx) bx = 1u << Q.kx[X0 + i];
@@ -1432,16 +1500,18 @@ k_quality_mark_full(Stuff S, QualityClasses Q) {
 
 // surface cell tiles: the plain cells (untouched, all corners strictly negative) one by one
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_quality_mark_surface(Stuff S, QualityClasses Q) {
+k_quality_mark_surface(Stuff S, QualityClasses Q, const uint32_t* __restrict__ tile_list,
+                       const unsigned long long* __restrict__ n_list) {
     const Lattice& L = S.L;
+    for (unsigned long long item = blockIdx.x; item < *n_list; item += gridDim.x) {  // active cell tiles
+    const uint32_t tile = tile_list[item];
     uint32_t X0, Y0, Z0;
-    tile_origin(S.g, blockIdx.x, X0, Y0, Z0);
-    if (S.cuni[blockIdx.x] != CU_ACTIVE || X0 >= L.nx || Y0 >= L.ny) return;
+    tile_origin(S.g, tile, X0, Y0, Z0);
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (zhi <= zlo) return;
+    if (zhi <= zlo) continue;
     // one x-row of 16 cells per thread
     const uint32_t cy = Y0 + (threadIdx.x & 15u), cz = Z0 + (threadIdx.x >> 4);
-    if (cy >= L.ny || cz < zlo || cz >= zhi) return;
+    if (cy >= L.ny || cz < zlo || cz >= zhi) continue;
     const uint16_t* __restrict__ row = S.cinfo + cidx(S, X0, cy, cz);
     const uint32_t n = min(TS, L.nx - X0);
     uint32_t bits = 0u;
@@ -1455,6 +1525,7 @@ k_quality_mark_surface(Stuff S, QualityClasses Q) {
         uint32_t* w = Q.present + (uint32_t)Q.kz[cz] * QC_K + Q.ky[cy];
         if ((*w & bits) != bits) atomicOr(w, bits);
     }
+    }  // tiles
 }
 
 // one thread per (kx, ky, kz): the five lattice tets of a cell with those steps and mirroring

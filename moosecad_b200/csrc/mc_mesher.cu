@@ -14,6 +14,8 @@
 using namespace mc;
 
 static_assert(CN_COUNT <= 32, "mc_mesh::counters holds 32 entries");
+// d_counters has 64 slots: the upper ones are the work cursors of the list kernels, one per launch site
+enum Cursor : int { CUR_WARP = 40, CUR_CLASSIFY, CUR_VCOUNT, CUR_VEMIT_INT, CUR_VEMIT, CUR_BISECT, CUR_TET_FULL, CUR_TET_SURF };
 
 namespace mc {
 
@@ -183,10 +185,12 @@ static void mesh_release_all(mc_mesh* m) {
                       &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
                       &m->d_tflag, &m->d_vuni, &m->d_cuni, &m->d_tsign,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
-                      &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub, &m->d_tile_list, &m->d_scan_sums};
+                      &m->d_inst_start, &m->d_word_inst, &m->d_dec, &m->d_sub, &m->d_tile_list, &m->d_scan_sums, &m->d_lists};
     for (DevBuf* b : bufs) c->release(*b);
     c->release(m->d_side_flag);
     c->release(m->d_side_nodes);
+    c->release(m->own_lower_table);
+    c->release(m->own_lower_coords);
     for (auto& ss : m->sidesets) c->release(ss.d_pairs);
     for (auto& e : m->ev)
         if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -313,6 +317,20 @@ Stuff make_stuff(const mc_mesh* m) {
 }
 }  // namespace mc
 }  // extern "C++"
+
+static TileLists make_lists(const mc_mesh* m) {
+    TileLists T;
+    const uint32_t* base = (const uint32_t*)m->d_lists.p;
+    const unsigned long long* cnt = (const unsigned long long*)m->d_counters.p;
+    T.v_active = base; T.v_neg = base + m->n_tiles; T.c_active = base + 2 * m->n_tiles; T.c_full = base + 3 * m->n_tiles;
+    T.n_v_active = cnt + CN_ACTIVE_VTILES; T.n_v_neg = cnt + CN_LIST_VNEG;
+    T.n_c_active = cnt + CN_ACTIVE_CTILES; T.n_c_full = cnt + CN_LIST_CFULL;
+    return T;
+}
+static inline unsigned list_grid(const mc_mesh* m) {
+    const uint64_t g = (uint64_t)m->ctx->sm_count * TILE_GRID_PER_SM;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(g, m->n_tiles));
+}
 
 // tile-specialised evaluation (mc_prune.cuh): worth it once the program is more than a few nodes
 static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
@@ -629,6 +647,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->alloc((ntiles + 1) * 8, m->d_vtile_cbase));
     MC_TRY(c->alloc(64 * 8, m->d_counters));
     MC_TRY(c->alloc((ntiles / SCAN_BLOCK + 2) * 16, m->d_scan_sums));
+    MC_TRY(c->alloc(std::max<uint64_t>(ntiles, 1) * 4 * 4, m->d_lists));
     L.phi = (const double*)m->d_phi.p;
     L.wcode = (uint8_t*)m->d_wcode.p;
 
@@ -650,18 +669,22 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->stage_check("stage sdf_field"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[1], s));
     // tile sign summary (the tiled SDF kernel writes it itself) + a6: warp codes
+    const TileLists T = make_lists(m);
+    const unsigned lgrid = list_grid(m);
     if (!m->tiled_sdf) k_tile_minmax<<<tgrid, TILE_THREADS, 0, s>>>(S);
-    k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
+    k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters, (uint32_t*)T.v_active, (uint32_t*)T.v_neg,
+                                                                 (unsigned long long*)m->d_vtile_tot.p);
     MC_TRY(c->stage_check("stage tile summary"));
-    k_warp_codes<<<tgrid, TILE_THREADS, 0, s>>>(S, counters);
+    k_warp_codes<<<lgrid, TILE_THREADS, 0, s>>>(S, counters, T.v_active, T.n_v_active, counters + CUR_WARP);
     c->launches += m->tiled_sdf ? 2 : 3;
     MC_TRY_CUDA(cudaGetLastError());
     MC_TRY(c->stage_check("stage warp codes"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[2], s));
     // a5/a7/a9: classification + counts
-    k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters);
-    k_classify_cells<<<tgrid, TILE_THREADS, 0, s>>>(S, (const uint64_t*)m->d_prog.p,
-                                                    (unsigned long long*)m->d_ttile_tot.p, counters);
+    k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters, (uint32_t*)T.c_active, (uint32_t*)T.c_full,
+                                                              (unsigned long long*)m->d_ttile_tot.p);
+    k_classify_cells<<<lgrid, TILE_THREADS, 0, s>>>(S, (const uint64_t*)m->d_prog.p, (unsigned long long*)m->d_ttile_tot.p,
+                                                    counters, T.c_active, T.n_c_active, counters + CUR_CLASSIFY);
     c->launches += 2;
     MC_TRY_CUDA(cudaGetLastError());
     MC_TRY(scan_tiles(c, m->d_ttile_tot.p, ntiles, m->d_ttile_base.p, nullptr, m->d_scan_sums.p, counters + CN_TETS));
@@ -670,7 +693,8 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->stage_check("stage classify"));
     MC_TRY_CUDA(cudaEventRecord(m->ev[3], s));
     // a10 pass 1: vertex masks + counts
-    k_vertex_count<<<tgrid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_vtile_tot.p);
+    k_vertex_count<<<lgrid, TILE_THREADS, 0, s>>>(S, (unsigned long long*)m->d_vtile_tot.p, T.v_active, T.n_v_active,
+                                                  counters + CUR_VCOUNT);
     c->launches += 1;
     MC_TRY_CUDA(cudaGetLastError());
     MC_TRY(scan_tiles(c, m->d_vtile_tot.p, ntiles, m->d_vtile_vbase.p, m->d_vtile_cbase.p, m->d_scan_sums.p, counters + CN_VERTS));
@@ -722,9 +746,13 @@ int mc_tessellate_emit_vertices_local(mc_mesh* m) {
     const Stuff S = make_stuff(m);
     unsigned long long* counters = (unsigned long long*)m->d_counters.p;
     MC_CUDA(cudaEventRecord(m->ev[5], s));
-    k_vertex_emit<<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (const unsigned long long*)m->d_vtile_cbase.p,
-                                                               (double*)m->d_coords.p, (unsigned long long*)m->d_cutlist.p);
-    c->launches++;
+    const TileLists T = make_lists(m);
+    const unsigned lgrid = list_grid(m);
+    k_vertex_emit_interior<<<lgrid, TILE_THREADS, 0, s>>>(S, (double*)m->d_coords.p, T.v_neg, T.n_v_neg, counters + CUR_VEMIT_INT);
+    k_vertex_emit<<<lgrid, TILE_THREADS, 0, s>>>(S, (const unsigned long long*)m->d_vtile_cbase.p, (double*)m->d_coords.p,
+                                                 (unsigned long long*)m->d_cutlist.p, T.v_active, T.n_v_active,
+                                                 counters + CUR_VEMIT);
+    c->launches += 2;
     MC_CUDA(cudaGetLastError());
     if ((rc = c->stage_check("stage vertex emit")) != MC_OK) return rc;
     MC_CUDA(cudaEventRecord(m->ev[6], s));
@@ -739,11 +767,12 @@ int mc_tessellate_emit_vertices_local(mc_mesh* m) {
             auto kern = capped ? (p.small() ? k_bisect_edges_tiled<true, true> : k_bisect_edges_tiled<false, true>)
                                : (p.small() ? k_bisect_edges_tiled<true, false> : k_bisect_edges_tiled<false, false>);
             if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)m->n_tiles, TILE_THREADS, smem, s>>>(
+            kern<<<lgrid, TILE_THREADS, smem, s>>>(
                 S, (const uint64_t*)m->d_prog.p, (const uint32_t*)m->d_inst_start.p, (const uint16_t*)m->d_word_inst.p,
                 n_inst, n_words, p.n_decisions, (const uint8_t*)m->d_dec.p, m->n_tiles,
                 (const unsigned long long*)m->d_vtile_cbase.p, m->n_cuts, (const unsigned long long*)m->d_cutlist.p,
-                m->error_threshold, m->max_bisect, (double*)m->d_coords.p, counters);
+                m->error_threshold, m->max_bisect, (double*)m->d_coords.p, counters, T.v_active, T.n_v_active,
+                counters + CUR_BISECT);
         } else {
             k_bisect_edges<<<blocks_for(m->n_cuts, 256), 256, 0, s>>>(
                 S, (const uint64_t*)m->d_prog.p, (const unsigned long long*)m->d_cutlist.p, m->n_cuts, m->error_threshold,
@@ -875,6 +904,8 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     MC_CUDA(cudaEventRecord(m->ev[8], s));
     if (m->n_tets > 0) {
         const unsigned grid = (unsigned)m->n_tiles;
+        const TileLists T = make_lists(m);
+        const unsigned lgrid = list_grid(m);
         const double* coords = (const double*)m->d_coords.p;
         const uint64_t nlist = quality ? m->counters[CN_LISTED_TETS] : 0;
         DevBuf qlist;
@@ -907,43 +938,43 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         }
         if (m->index_bytes == 4) {
             uint32_t* out = (uint32_t*)m->d_tets.p;
-            k_tet_emit_full<uint32_t><<<grid, TILE_THREADS, 0, s>>>(S, out);
+            k_tet_emit_full<uint32_t><<<lgrid, TILE_THREADS, 0, s>>>(S, out, T.c_full, T.n_c_full, counters + CUR_TET_FULL);
             if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
                 if (class_quality) {
-                    k_quality_mark_full<<<grid, 32, 0, s>>>(S, Q);
-                    k_quality_mark_surface<<<grid, TILE_THREADS, 0, s>>>(S, Q);
+                    k_quality_mark_full<<<blocks_for(m->n_tiles, 8), 256, 0, s>>>(S, Q, T.c_full, T.n_c_full);
+                    k_quality_mark_surface<<<lgrid, TILE_THREADS, 0, s>>>(S, Q, T.c_active, T.n_c_active);
                     k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 } else {
                     k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                     k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
                 }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
-                k_tet_emit<uint32_t, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
+                k_tet_emit<uint32_t, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
-                k_tet_emit<uint32_t, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters);
+                k_tet_emit<uint32_t, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
             }
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
-            k_tet_emit_full<unsigned long long><<<grid, TILE_THREADS, 0, s>>>(S, out);
+            k_tet_emit_full<unsigned long long><<<lgrid, TILE_THREADS, 0, s>>>(S, out, T.c_full, T.n_c_full, counters + CUR_TET_FULL);
             if ((rc = c->stage_check("stage tet emit (interior tiles)")) != MC_OK) return rc;
             if (quality) {
                 if (class_quality) {
-                    k_quality_mark_full<<<grid, 32, 0, s>>>(S, Q);
-                    k_quality_mark_surface<<<grid, TILE_THREADS, 0, s>>>(S, Q);
+                    k_quality_mark_full<<<blocks_for(m->n_tiles, 8), 256, 0, s>>>(S, Q, T.c_full, T.n_c_full);
+                    k_quality_mark_surface<<<lgrid, TILE_THREADS, 0, s>>>(S, Q, T.c_active, T.n_c_active);
                     k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 } else {
                     k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                     k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
                 }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
-                k_tet_emit<unsigned long long, true><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
+                k_tet_emit<unsigned long long, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
-                k_tet_emit<unsigned long long, false><<<grid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters);
+                k_tet_emit<unsigned long long, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
             }
         }
         c->release(qlist);

@@ -773,24 +773,27 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
                      const uint16_t* __restrict__ word_inst, uint32_t n_inst, uint32_t n_words, uint32_t n_dec,
                      const uint8_t* __restrict__ dec_g, uint64_t ntiles, const unsigned long long* __restrict__ tile_cbase,
                      uint64_t ncut_total, const unsigned long long* __restrict__ cutlist, double error_threshold,
-                     uint32_t max_iters, double* __restrict__ coords, unsigned long long* __restrict__ counters) {
+                     uint32_t max_iters, double* __restrict__ coords, unsigned long long* __restrict__ counters,
+                     const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
+                     unsigned long long* __restrict__ cursor) {
     extern __shared__ uint64_t smem[];
     uint64_t* s_prog = smem;
     uint8_t* s_dec = (uint8_t*)(s_prog + n_words);
     int* s_delta = (int*)(s_dec + ((n_dec + 15u) & ~15u));
     uint32_t* s_newpos = (uint32_t*)(s_delta + (n_inst + 1));
     __shared__ uint32_t s_scan[9];
-    const uint64_t tile = blockIdx.x;
-    if (S.vuni[tile] != VU_ACTIVE) return;
+    unsigned long long it64 = 0ull;
+    uint32_t tile32;
+    while (next_tile(tile_list, n_list, cursor, tile32)) {  // active point tiles
+    const uint64_t tile = tile32;
     const uint64_t c0 = tile_cbase[tile], c1 = tile + 1 < ntiles ? tile_cbase[tile + 1] : ncut_total;
-    if (c1 <= c0) return;
+    if (c1 <= c0) continue;
     compact_tile_program(prog, inst_start, word_inst, n_inst, n_dec, dec_g, ntiles, tile, s_prog, s_dec, s_delta, s_newpos,
                          s_scan, n_words);
     const bool fits = !CAPPED || s_newpos[n_inst] <= n_words;
     __syncthreads();
     const Lattice& L = S.L;
     const uint64_t per_plane = (uint64_t)L.NX * L.NY;
-    unsigned long long it64 = 0ull;
     const uint64_t n = c1 - c0;
     for (uint64_t base = 0; base < n; base += TILE_THREADS) {
         const uint64_t i = base + threadIdx.x;
@@ -839,6 +842,7 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
             it64 += iters;
         }
     }
+    }  // tiles
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) it64 += __shfl_xor_sync(0xffffffffu, it64, o);
     if ((threadIdx.x & 31u) == 0u && it64) atomicAdd(&counters[CN_BISECT_ITERS], it64);

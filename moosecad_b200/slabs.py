@@ -339,6 +339,38 @@ class SlabMesher:
         return out
 
 
+def tessellate_multi(ctxs, obj, resolution, relative_error, flags=0):
+    """One process driving several devices (C ABI mc_tessellate_multi): ctxs[i] meshes slab i.
+    Returns the list of raw mc_mesh handles (global vertex ids); free each with mc_mesh_free."""
+    lib = _lib.lib()
+    n = len(ctxs)
+    handles = (C.c_void_p * n)(*[c.handle for c in ctxs])
+    out = (C.c_void_p * n)()
+    opts = _lib.mc_options(C.sizeof(_lib.mc_options), flags, 0, 0)
+    rc = lib.mc_tessellate_multi(handles, n, obj.backend.handle, obj.node, float(resolution), float(relative_error),
+                                 C.byref(opts), out)
+    if rc not in (_lib.MC_OK, _lib.MC_ERR_DIVERGED):
+        _lib.check(rc)
+    return [C.c_void_p(h) for h in out]
+
+
+def gather_slab_meshes(handles):
+    """Host copy of slab meshes with global ids -> (coords (n, 3) f64, tets (m, 4) u64, combined stats)."""
+    import numpy as np
+    lib = _lib.lib()
+    coords, tets, stats = [], [], []
+    for h in handles:
+        c = (C.c_uint64 * 6)()
+        _lib.check(lib.mc_mesh_counts(h, c))
+        cbuf = np.empty((c[0], 3), dtype=np.float64)
+        tbuf = np.empty((c[1], 4), dtype=np.uint64)
+        _lib.check(lib.mc_mesh_copy_to_host(h, cbuf.ctypes.data_as(C.c_void_p), tbuf.ctypes.data_as(C.c_void_p), 8))
+        coords.append(cbuf)
+        tets.append(tbuf)
+        stats.append(mesh_stats(h))
+    return np.concatenate(coords), np.concatenate(tets), combine_stats(stats)
+
+
 def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0, return_stats=False):
     """Mesh the lattice as `n_slabs` z-slabs one after the other on ONE device and merge the
     results on the host (global vertex ids).  Exercises exactly the phases a multi-GPU run

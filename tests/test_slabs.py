@@ -166,3 +166,58 @@ def test_combine_stats():
     # the reference starts the range at (one, zero) (tessellate3d/src/lib.rs:404): an empty slab is neutral
     empty = {"ntets_stage": [0, 0, 0], "stats": [0] * 7, "aspect_ratio": [1.0, 0.0], "inverted": 0}
     assert slabs.combine_stats([a, empty]) == slabs.combine_stats([a])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["xplicit_top", "cube"])
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_tessellate_multi_single_process(n_slabs, scene, ctx):
+    """mc_tessellate_multi (one process, one host thread per context, peer copies of the plane
+    table): several contexts on the ONE device of the test box, against the single-slab mesh —
+    mesh, statistics, device checksums, boundary sides and a side-set (slab-aware)."""
+    import moosecad_b200 as mc
+    from moosecad_b200 import _lib, luascad, scenes
+    from moosecad_b200.tessellate3d import mesh_checksum
+    import ctypes as C
+    out = luascad.eval(scenes.XPLICIT_WITH_TOP_LUA if scene == "xplicit_top" else scenes.CUBE_LUA)
+    obj = [o.volume() for _, o in sorted(out.items()) if o.volume() is not None][0]
+    top = [o.boundary() for n, o in sorted(out.items()) if o.boundary() is not None and n == "top"][0]
+    obj.backend.set_parameters(0.1, 1.0)
+    res = 15.0 / 44 if scene == "xplicit_top" else 1.0 / 21
+    whole = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx).tessellate()
+    ctxs = [mc.Context(0) for _ in range(n_slabs)]
+    handles = slabs.tessellate_multi(ctxs, obj, res, 0.2)
+    lib = _lib.lib()
+    try:
+        coords, tets, stats = slabs.gather_slab_meshes(handles)
+        ws = whole.stats()
+        for key in ("ntets_stage", "stats", "aspect_ratio", "inverted"):
+            assert stats[key] == ws[key], key
+        canon.assert_same_mesh(canon.canonical(whole.vertices(), whole.elems()), canon.canonical(coords, tets))
+        cs = [mesh_checksum(h) for h in handles]
+        wcs = whole.checksum()
+        assert sum(c["vertices"] for c in cs) % (1 << 64) == wcs["vertices"]
+        assert sum(c["tets"] for c in cs) % (1 << 64) == wcs["tets"]
+        assert sum(c["tets_skipped"] for c in cs) == 0
+        # Mesh::boundary and the side-set loop on slabs: global (elem, side) pairs, no exchange
+        sides, members = [], []
+        for h in handles:
+            n = C.c_uint64()
+            _lib.check(lib.mc_mesh_boundary(h, C.byref(n)))
+            if n.value:
+                sides.append(np.ctypeslib.as_array(lib.mc_mesh_boundary_sides(h), shape=(n.value, 2)).copy())
+            idx = _lib.check(lib.mc_mesh_add_sideset(h, top.backend.handle, top.node))
+            k = int(lib.mc_mesh_sideset_len(h, idx))
+            if k:
+                members.append(np.ctypeslib.as_array(lib.mc_mesh_sideset(h, idx), shape=(k, 2)).copy())
+        sides = np.concatenate(sides)
+        members = np.concatenate(members) if members else np.zeros((0, 2), dtype=np.uint64)
+        wtop = whole.add_boundary_side_set("top", top)
+        a = canon.canonical(whole.vertices(), whole.elems(), {"s": sorted(whole.boundary().sides()), "top": sorted(wtop.sides())})[2]
+        b = canon.canonical(coords, tets, {"s": sides, "top": members})[2]
+        assert np.array_equal(a["s"], b["s"]) and np.array_equal(a["top"], b["top"])
+        if scene == "cube":
+            assert len(a["top"]) > 0
+    finally:
+        for h in handles:
+            lib.mc_mesh_free(h)
