@@ -47,20 +47,24 @@ def workload_desc(name):
 
 
 def build_scene(geom_factory, name):
-    """-> (backend owner, volume object, resolution, cells per axis, relative error)"""
+    """-> (backend owner, volume object, resolution, cells per axis, relative error, [(name, boundary object)])
+    The synthetic scenes get one `:boundary()` object (`top`, built like examples/cube.lua's), xplicit.lua
+    the added `top` of BASELINE config 3, so that Mesh::boundary and the side-set loop (src/main.rs:86-106)
+    are part of every step."""
     from moosecad_b200 import luascad, scenes
     w = WORKLOADS[name]
     if isinstance(w[0], int):
         nprim, n = w
         g = geom_factory()
         root = scenes.synthetic_csg(g, nprim, seed=nprim, size_scale=0.5 if nprim >= 256 else 1.0)
-        return g, root, 1.0 / n, n, REL_ERR
+        return g, root, 1.0 / n, n, REL_ERR, [("top", scenes.synthetic_csg_top(g, root))]
     script, n, err = w
     backend = geom_factory().backend
-    out = luascad.eval({"sphere": scenes.SPHERE_LUA, "xplicit": scenes.XPLICIT_LUA}[script], backend=backend)
+    out = luascad.eval({"sphere": scenes.SPHERE_LUA, "xplicit": scenes.XPLICIT_WITH_TOP_LUA}[script], backend=backend)
     root = [o.volume() for _, o in sorted(out.items()) if o.volume() is not None][0]
+    bnds = [(nm, o.boundary()) for nm, o in sorted(out.items()) if o.boundary() is not None]
     bb = root.bbox()
-    return root, root, (bb[3] - bb[0]) / n, n, err
+    return root, root, (bb[3] - bb[0]) / n, n, err, bnds
 
 
 class ClockSampler:
@@ -117,9 +121,11 @@ class ClockSampler:
 def _oracle_scene(name):
     import moosecad_b200 as mc
     from oracle import pyoracle
-    g, root, res, n, err = build_scene(lambda: mc.Geom(pyoracle.OracleScene()), name)
+    g, root, res, n, err, bnds = build_scene(lambda: mc.Geom(pyoracle.OracleScene()), name)
     root.backend.set_parameters_node(root.node, 0.1, 1.0)
-    return root, res, n, err
+    for _, b in bnds:
+        b.backend.set_parameters_node(b.node, 0.1, 1.0)
+    return root, res, n, err, bnds
 
 
 def cpu_sample_cells(name):
@@ -138,11 +144,14 @@ def cpu_baseline_sample(name, cells=None):
     from oracle import pyoracle
     pyoracle.set_libm_mode(0)  # the reference calls the platform libm
     try:
-        root, res_full, n_full, err = _oracle_scene(name)
+        root, res_full, n_full, err, bnds = _oracle_scene(name)
         n = cells or cpu_sample_cells(name)
         res = res_full * n_full / n
         t0 = time.perf_counter()
-        om = root.backend.tessellate(root.node, res, err)
+        om = root.backend.tessellate(root.node, res, err)       # IsosurfaceStuffing::tessellate, src/main.rs:74-82
+        om.boundary()                                           # mesh.boundary(), src/main.rs:86
+        for _, b in bnds:                                       # the side-set loop, src/main.rs:87-106
+            om.add_sideset(b.backend, b.node)
         dt = time.perf_counter() - t0
         st = om.stats()
     finally:
@@ -227,7 +236,7 @@ def main():
     lib = _lib.lib()
     with torch.cuda.stream(stream):
         ctx = mc.Context(local_rank, stream.cuda_stream)
-        g, root, res, n, rel_err = build_scene(mc.Geom, args.workload)
+        g, root, res, n, rel_err, bnds = build_scene(mc.Geom, args.workload)
         g.backend.set_parameters(0.1, 1.0)
         info = g.backend.program_info(root.node, res)
         dim = slabs.lattice_dim(root.bbox(), res)
@@ -240,9 +249,24 @@ def main():
 
         host_ms = {}
 
+        def boundary_and_sidesets(h, objs):
+            # Mesh::boundary + the side-set loop on this rank's slab (slab-aware, no exchange)
+            ns = C.c_uint64()
+            _lib.check(lib.mc_mesh_boundary(h, C.byref(ns)))
+            sizes = []
+            for _, b in objs:
+                idx = _lib.check(lib.mc_mesh_add_sideset(h, b.backend.handle, b.node))
+                sizes.append(int(lib.mc_mesh_sideset_len(h, idx)))
+            return int(ns.value), sizes
+
+        side_counts = {}
+
         def one_step(flags=0):
             sm = slabs.SlabMesher(ctx, root, res, rel_err, rank, world, None, dev, flags=flags, host_group=host_group)
             h = sm.run()
+            t0 = time.perf_counter()
+            side_counts["boundary"], side_counts["sets"] = boundary_and_sidesets(h, bnds)
+            sm.host_ms["boundary_sidesets"] = (time.perf_counter() - t0) * 1e3
             host_ms.update(sm.host_ms)
             return h
 
@@ -304,12 +328,12 @@ def main():
                     "tets": "%016x" % (sum(c["tets"] for c in all_cs) % (1 << 64)),
                     "tets_skipped": sum(c["tets_skipped"] for c in all_cs)}
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        cnt = torch.tensor(last_counts[:2] + [launches], dtype=torch.int64, device=dev)
+        cnt = torch.tensor(last_counts[:2] + [launches, side_counts["boundary"]] + side_counts["sets"], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         ms_step = float(t.item()) / steps
-        n_verts, n_tets, launches_all = (int(x) for x in cnt.tolist())
+        n_verts, n_tets, launches_all, n_sides, *set_sizes = (int(x) for x in cnt.tolist())
         stage_avg = [a / steps for a in stage_acc]
         # diagnostics (outside the timed region): every rank's own device time and host phases
         mine = {"rank": rank, "device_stage_ms_sum": round(sum(stage_avg), 3),
@@ -333,14 +357,17 @@ def main():
             a0.record(stream)
             h2d = 0
             for _ in range(e_steps):
-                g2, root2, _, _, _ = build_scene(mc.Geom, args.workload)     # scene lowering from host data
+                g2, root2, _, _, _, bnds2 = build_scene(mc.Geom, args.workload)     # scene lowering from host data
                 g2.backend.set_parameters(0.1, 1.0)
                 sm = slabs.SlabMesher(ctx, root2, res, rel_err, rank, world, None, dev, host_group=host_group)
                 h = sm.run()
+                boundary_and_sidesets(h, bnds2)
+                t_copy = time.perf_counter()
                 ib = C.c_int()
                 lib.mc_mesh_device_views(h, None, None, C.byref(ib))
                 idx_bytes = ib.value
                 _lib.check(lib.mc_mesh_copy_to_host(h, C.c_void_p(coords_h.data_ptr()), C.c_void_p(tets_h.data_ptr()), 4))
+                copy_ms = (time.perf_counter() - t_copy) * 1e3
                 h2d = g2.backend.program_info(root2.node, res)["words"] * 8
                 lib.mc_mesh_free(h)
             a1.record(stream)
@@ -356,8 +383,14 @@ def main():
             e2e = {"value": P_total / (ms_e2e * 1e-3), "unit": "lattice pts/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h.item()),
                    "tets_per_s": n_tets / (ms_e2e * 1e-3),
-                   "what": "scene lowering + program upload + meshing + copy of coords (f64) and tets "
-                           f"(u{idx_bytes * 8}) into pinned host buffers, via the C ABI"}
+                   "what": "scene lowering + program upload + meshing + Mesh::boundary + side-sets + copy of coords "
+                           f"(f64) and tets (u{idx_bytes * 8}) into pinned host buffers, via the C ABI"}
+            mine["e2e_copy_ms_last_step"] = round(copy_ms, 2)
+            mine["e2e_copy_gb_per_s"] = round((my_c[0] * 24 + my_c[1] * 4 * idx_bytes) / (copy_ms * 1e-3) / 1e9, 2)
+            if world > 1:
+                dist.all_gather_object(per_rank, mine)
+            else:
+                per_rank = [mine]
             del coords_h, tets_h
 
         if rank == 0:
@@ -387,7 +420,7 @@ def main():
                               "surface_point_tiles": tile_stats[2], "surface_cell_tiles": tile_stats[3],
                               "sub_boxes_proven_of_32_per_evaluated_tile": tile_stats[5]},
                     "ms": stage_avg[0]}
-            stuff_ms = sum(stage_avg[1:7])  # warp, classify, vertex, bisect, tet emit (+ fused quality)
+            stuff_ms = sum(stage_avg[1:9])  # warp, classify, vertex, bisect, tet emit (+ fused quality), boundary, side-sets
             bytes_alg = 8 * P_total + 24 * n_verts + 4 * 4 * n_tets
             roof2 = {"bound": "hbm", "kernels": "k_tile_minmax..k_tet_quality_list (all stages after the SDF field)",
                      "achieved": bytes_alg / (stuff_ms * 1e-3) / 1e9 if stuff_ms > 0 else None, "peak": hbm_peak,
@@ -401,6 +434,8 @@ def main():
                     "config": {"workload": workload_desc(args.workload) + ", " +
                                            ("z-slabs over %d GPUs" % world if world > 1 else "single GPU"),
                                "lattice_points": P_total, "output_vertices": n_verts, "output_tets": n_tets,
+                               "boundary_sides": n_sides,
+                               "side_sets": dict(zip([nm for nm, _ in bnds], set_sizes)),
                                "mesh_checksum": checksum,
                                "l2": "working set (>= 8 B x lattice points per array) is far larger than the 126 MB L2; no flush needed",
                                "tape_words": info["words"]},

@@ -309,6 +309,24 @@ const uint64_t* mc_mesh_sideset(mc_mesh*, int index);
 int mc_mesh_sideset_device(mc_mesh*, int index, void** d_pairs, uint64_t* n);
 
 /* ------------------------------------------------------------------------------------
+ * The consumer right after the path: exodus::write(&mesh, path) (exodus/src/lib.rs:14-155) builds
+ * three big arrays from the mesh on one thread.  These calls produce them on the device, in the
+ * writer's layout, and stream them into caller HOST buffers (pinned or pageable; chunked, the
+ * layout kernel of one chunk overlaps the copy of the previous one), so that the Rust side goes
+ * straight to `put_values`:
+ *   coord        [num_dim = 3][num_nodes] f64 (exodus/src/lib.rs:55-63): this mesh / slab fills columns
+ *                [vertex_base, vertex_base + n_vertices) of the three rows of a buffer with
+ *                num_nodes_total columns (one GPU: vertex_base = 0, num_nodes_total = n_vertices)
+ *   connect1     [num_el_in_blk1][4] i64, 1-based (exodus/src/lib.rs:84-96): this slab's n_tets rows
+ *   elem_ss<i> / side_ss<i>  i32, 1-based (exodus/src/lib.rs:118-132) of side-set `index`
+ *                (mc_mesh_sideset_len entries each); MC_ERR_LIMIT when an element number does not
+ *                fit i32 (the reference's `*elem as i32 + 1` would wrap silently)
+ * ------------------------------------------------------------------------------------ */
+int mc_mesh_exodus_coord(mc_mesh*, double* coord, uint64_t num_nodes_total);
+int mc_mesh_exodus_connect(mc_mesh*, int64_t* connect1);
+int mc_mesh_exodus_sideset(mc_mesh*, int index, int32_t* elem_ss, int32_t* side_ss);
+
+/* ------------------------------------------------------------------------------------
  * mesh crate predicates on arbitrary tet meshes (mesh/src/lib.rs:292-316), evaluated on the
  * device; used by the parity tests of check_for_inverted_tets.  HOST buffers.
  * ------------------------------------------------------------------------------------ */

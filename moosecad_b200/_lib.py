@@ -108,6 +108,9 @@ SIGNATURES = {
     "mc_mesh_copy_to_host": (C.c_int, [_P, _P, _P, C.c_int]),
     "mc_mesh_copy_phi": (C.c_int, [_P, _PD, _U64]),
     "mc_mesh_checksum": (C.c_int, [_P, _PU64]),
+    "mc_mesh_exodus_coord": (C.c_int, [_P, _P, _U64]),
+    "mc_mesh_exodus_connect": (C.c_int, [_P, _P]),
+    "mc_mesh_exodus_sideset": (C.c_int, [_P, C.c_int, _P, _P]),
     "mc_mesh_boundary": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary_sides": (_PU64, [_P]),
     "mc_mesh_boundary_device": (C.c_int, [_P, C.POINTER(_P), _PU64]),

@@ -1075,6 +1075,58 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, const uint32_t* __restrict__
     }
     __syncthreads();
     const uint32_t n = nxt * nyt * (zhi - zlo);
+    if (sizeof(IndexT) == 4) {
+        // 32-bit ids: the ids of the tile's (TS + 1)^3 corner points are tabulated once (every point is
+        // shared by up to 8 cells), a cell then costs eight shared-memory loads and a few adds
+        constexpr int H = (int)TS + 1;
+        __shared__ uint32_t s_id[sizeof(IndexT) == 4 ? H * H * H : 1];  // (unused by the 64-bit instantiation)
+        for (int idx = (int)threadIdx.x; idx < H * H * H; idx += TILE_THREADS) {
+            const uint32_t lx = idx % H, ly = (idx / H) % H, lz = idx / (H * H);
+            const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+            uint32_t id = 0u;
+            if (lx <= nxt && ly <= nyt && Z >= zlo && Z <= zhi) {
+                const uint32_t which = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
+                if (s_nvu[which] == VU_NEG && !(S.lower_table != nullptr && Z == S.c0)) {
+                    const TileBox& nb = s_nbox[which];
+                    id = (uint32_t)(S.vertex_base + (long long)s_nbase[which] +
+                                    (long long)(((Z - nb.zlo) * nb.nyt + (Y - nb.Y0)) * nb.nxt + (X - nb.X0)));
+                } else {
+                    uint16_t mask;
+                    id = (uint32_t)vertex_gid(S, X, Y, Z, mask);
+                }
+            }
+            s_id[idx] = id;
+        }
+        __syncthreads();
+        uint4* s_out4 = reinterpret_cast<uint4*>(&s_out[0][0][0]);
+        for (uint32_t base = 0; base < n; base += TILE_THREADS) {
+            const uint32_t j = base + threadIdx.x;
+            if (j < n) {
+                const uint32_t lx = j % nxt, ly = (j / nxt) % nyt, lz = zlo - Z0 + j / (nxt * nyt);
+                // corner k of the (possibly mirrored) cell: offset 0 or 1 per axis, mirrored axes count down
+                const uint32_t fx = (X0 + lx) & 1u, fy = (Y0 + ly) & 1u, fz = (Z0 + lz) & 1u;
+                const int at = (int)((lz + fz) * H + (ly + fy)) * H + (int)(lx + fx);
+                const int ax = fx ? -1 : 1, ay = fy ? -H : H, az = fz ? -H * H : H * H;
+                // Tile::LATTICE: 0 (0,0,0) 1 (1,0,0) 2 (1,1,0) 3 (0,1,0) 4 (0,0,1) 5 (1,0,1) 6 (1,1,1) 7 (0,1,1)
+                const uint32_t i0 = s_id[at], i1 = s_id[at + ax], i2 = s_id[at + ax + ay], i3 = s_id[at + ay];
+                const uint32_t i4 = s_id[at + az], i5 = s_id[at + ax + az], i6 = s_id[at + ax + ay + az], i7 = s_id[at + ay + az];
+                const bool flip = (fx ^ fy ^ fz) != 0u;
+                // Tile::TETS, nodes 0 and 1 swapped when the cell is mirrored an odd number of times
+                s_out4[0 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i1, i0, i5, i2) : make_uint4(i0, i1, i5, i2);
+                s_out4[1 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i2, i0, i5, i7) : make_uint4(i0, i2, i5, i7);
+                s_out4[2 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i7, i0, i5, i4) : make_uint4(i0, i7, i5, i4);
+                s_out4[3 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i6, i2, i5, i7) : make_uint4(i2, i6, i5, i7);
+                s_out4[4 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i2, i0, i7, i3) : make_uint4(i0, i2, i7, i3);
+            }
+            __syncthreads();
+            // coalesced copy: output tet g of this round = cell g / 5, lattice tet g % 5
+            const uint32_t ncell = min((uint32_t)TILE_THREADS, n - base);
+            uint4* dst4 = reinterpret_cast<uint4*>(tets + 4 * (tb + 5ull * base));
+            for (uint32_t g = threadIdx.x; g < 5u * ncell; g += TILE_THREADS) dst4[g] = s_out4[(g % 5u) * TILE_THREADS + g / 5u];
+            __syncthreads();
+        }
+        continue;
+    }
     for (uint32_t base = 0; base < n; base += TILE_THREADS) {
         const uint32_t j = base + threadIdx.x;
         if (j < n) {
@@ -1106,17 +1158,10 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, const uint32_t* __restrict__
             }
         }
         __syncthreads();
-        // coalesced copy: output tet g of this round = cell g / 5, lattice tet g % 5
         const uint32_t ncell = min((uint32_t)TILE_THREADS, n - base);
         IndexT* dst = tets + 4 * (tb + 5ull * base);
-        if (sizeof(IndexT) == 4) {
-            uint4* dst4 = reinterpret_cast<uint4*>(dst);
-            for (uint32_t g = threadIdx.x; g < 5u * ncell; g += TILE_THREADS)
-                dst4[g] = *reinterpret_cast<const uint4*>(&s_out[g % 5u][g / 5u][0]);
-        } else {
-            for (uint32_t g = threadIdx.x; g < 20u * ncell; g += TILE_THREADS)
-                dst[g] = s_out[(g >> 2) % 5u][(g >> 2) / 5u][g & 3u];
-        }
+        for (uint32_t g = threadIdx.x; g < 20u * ncell; g += TILE_THREADS)
+            dst[g] = s_out[(g >> 2) % 5u][(g >> 2) / 5u][g & 3u];
         __syncthreads();
     }
     }  // tiles

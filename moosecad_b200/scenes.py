@@ -56,3 +56,10 @@ def synthetic_csg(geom, n_primitives=64, seed=None, size_scale=1.0, smooth=0.05)
     for i, p in enumerate(prims[1:]):
         acc = acc.difference(p, smooth) if i % 4 == 3 else acc.union(p, smooth)
     return acc.intersection(geom.cube(1.0, 1.0, 1.0, 0.0), 0.0)
+
+
+def synthetic_csg_top(geom, root):
+    """A ``:boundary()`` object for the synthetic scene, built like ``top`` of examples/cube.lua: the
+    solid intersected with a 0.01 thick slab around the plane z = +0.5 of its bounding cube.  Its zero
+    set holds the flat caps where the unit cube cuts the scene."""
+    return root.intersection(geom.cube(1.0, 1.0, 0.01, 0.0).translate(0.0, 0.0, 0.5), 0.0)

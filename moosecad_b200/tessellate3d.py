@@ -239,6 +239,23 @@ class Mesh:
                 "points_evaluated": counts[2], "points_owned": counts[3], "n_cut": counts[4],
                 "n_warped": counts[5], "stage_ms": list(ms)}
 
+    def exodus_arrays(self):
+        """The arrays ``exodus::write`` builds from the mesh (exodus/src/lib.rs:55-63,84-96,118-132), laid
+        out on the device: {"coord": (3, num_nodes) f64, "connect1": (num_elem, 4) i64 1-based,
+        "side_sets": [(elem_ss i32, side_ss i32) 1-based per side-set added so far]}."""
+        nv, nt = self.num_vertices(), self.num_elems()
+        coord = np.empty((3, nv), dtype=np.float64)
+        connect = np.empty((nt, 4), dtype=np.int64)
+        _lib.check(self._lib.mc_mesh_exodus_coord(self.handle, coord.ctypes.data_as(C.c_void_p), nv))
+        _lib.check(self._lib.mc_mesh_exodus_connect(self.handle, connect.ctypes.data_as(C.c_void_p)))
+        sets = []
+        for i in range(len(self._side_sets)):
+            n = int(self._lib.mc_mesh_sideset_len(self.handle, i))
+            e, s = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+            _lib.check(self._lib.mc_mesh_exodus_sideset(self.handle, i, e.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)))
+            sets.append((e, s))
+        return {"coord": coord, "connect1": connect, "side_sets": sets}
+
     def checksum(self):
         """Order- and numbering-independent checksums of the emitted mesh, computed on the device
         (C ABI mc_mesh_checksum): {"vertices": u64, "tets": u64, "tets_skipped": n}."""

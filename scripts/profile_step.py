@@ -22,10 +22,10 @@ from moosecad_b200 import _lib  # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "csg64_1024"
     flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    with_boundary = len(sys.argv) > 3 and sys.argv[3] == "boundary"
+    with_boundary = not (len(sys.argv) > 3 and sys.argv[3] == "noboundary")
     lib = _lib.lib()
     ctx = mc.Context(0)
-    g, root, res, n, err = bench.build_scene(mc.Geom, name)
+    g, root, res, n, err, bnds = bench.build_scene(mc.Geom, name)
     g.backend.set_parameters(0.1, 1.0)
 
     def step():
@@ -37,6 +37,8 @@ def main():
         if with_boundary:
             ns = C.c_uint64()
             _lib.check(lib.mc_mesh_boundary(out, C.byref(ns)))
+            for _, b in bnds:
+                _lib.check(lib.mc_mesh_add_sideset(out, b.backend.handle, b.node))
         lib.mc_mesh_free(out)
 
     step()

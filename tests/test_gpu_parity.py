@@ -373,3 +373,18 @@ def test_full_size_properties_sphere_256(ctx):
     # idempotence: a second run gives the identical arrays
     mesh2 = main.run(scenes.SPHERE_LUA, tessellation_resolution=1.0 / 256, ctx=ctx)
     assert np.array_equal(mesh2.vertices(), v) and np.array_equal(mesh2.elems().astype(np.int64), e)
+
+
+@pytest.mark.parametrize("script,res", [(scenes.CUBE_LUA, 1.0 / 9), (scenes.XPLICIT_WITH_TOP_LUA, 15.0 / 70)])
+def test_exodus_layout(script, res, ctx):
+    """exodus::write's arrays (exodus/src/lib.rs:55-63 coord, :84-96 connect1, :118-132 elem_ss / side_ss)
+    produced on the device against a numpy restatement of the writer's loops."""
+    mesh = main.run(script, tessellation_resolution=res, ctx=ctx)
+    ex = mesh.exodus_arrays()
+    v, e = mesh.vertices(), mesh.elems()
+    assert ex["coord"].shape == (3, len(v)) and np.array_equal(ex["coord"], v.T)          # vertices[i + num_nodes * j] = v[j]
+    assert ex["connect1"].dtype == np.int64 and np.array_equal(ex["connect1"], e.astype(np.int64) + 1)   # e.node(j) as i64 + 1
+    assert len(ex["side_sets"]) == len(mesh.side_sets())
+    for (elem_ss, side_ss), ss in zip(ex["side_sets"], mesh.side_sets()):
+        a = ss.array().astype(np.int64)
+        assert elem_ss.dtype == np.int32 and np.array_equal(elem_ss, a[:, 0] + 1) and np.array_equal(side_ss, a[:, 1] + 1)
