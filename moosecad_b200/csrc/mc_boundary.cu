@@ -57,27 +57,41 @@ __device__ __forceinline__ CellInfo cell_info(const Stuff& S, int64_t cx, int64_
     return r;
 }
 
-// the pieces of lattice tet (c, t) as a TetOut (node codes: 0..3 original node, 4 + 4 i + j cut on edge i-j)
-__device__ __forceinline__ void pieces_of(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, TetOut& to) {
-    if (ci & CI_FULL) {  // untouched: the lattice tet itself (on a full cell the "removed" bits mean something else)
-        to.n = 1; to.kase = -1; to.ext_removed = false;
-        to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
-        return;
-    }
-    if (ci_tet_n(ci, t) == 0u) { to.n = 0; to.kase = -2; to.ext_removed = false; to.nodes = 0ull; return; }
-    classify_tet<false>(S.L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+// state of a lattice tet, from its cell's info word: nothing emitted / emitted untouched (one piece,
+// the lattice tet itself) / trimmed (needs classify_tet)
+enum : int { TET_NONE = 0, TET_WHOLE = 1, TET_TRIM = 2 };
+__device__ __forceinline__ int tet_state(uint16_t ci, int t) {
+    if (ci & CI_FULL) return TET_WHOLE;
+    if (ci_tet_n(ci, t) == 0u) return TET_NONE;
+    return ((ci >> (CI_UNTOUCHED_SHIFT + t)) & 1u) ? TET_WHOLE : TET_TRIM;
+}
+// signature (see face_sig) of a whole lattice face: its three original nodes
+constexpr uint32_t SIG_WHOLE_FACE = (1u << 1) | (1u << 2) | (1u << 4);
+// side (Tet4::face row) opposite node k: FACE = {0,1,2} {0,2,3} {0,3,1} {1,3,2}
+__device__ __forceinline__ int side_opposite(int k) { return k == 0 ? 3 : (k == 1 ? 1 : (k == 2 ? 2 : 0)); }
+
+// the pieces of a TRIMMED lattice tet (node codes: 0..3 original node, 4 + 4 i + j cut on edge i-j); one
+// copy of the classification code per kernel
+static __device__ __noinline__ void trimmed_pieces(const Lattice& L, const Cell& c, int t, TetNodes& tn, TetOut& to) {
+    load_tet(L, c, t, tn);
+    classify_tet<false>(L, c, t, tn, nullptr, 0, to);  // emitted, hence not dropped by the exterior test
+}
+
+// lattice coordinates of the (flipped) nodes of lattice tet (c, t), without touching the field
+__device__ __forceinline__ void tet_coords(const Cell& c, int t, TetNodes& tn) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) corner_xyz(c, tet_corner(c, t, n), tn.X[n], tn.Y[n], tn.Z[n]);
 }
 
 // signature of the face (q, s) of `to` relative to lattice face k of its lattice tet, or 0 when the
-// face does not lie in it.  r[n] = rank (0..2) of node n among the three lattice points of face k
-// by point id (r[k] unused): both sides of the lattice face compute the same ranks.  A node becomes
-// a 3-bit set of ranks (original node: one bit, cut vertex: the two ends of its edge), the face the
-// set of its three node sets (8 bits).
-__device__ __forceinline__ uint32_t face_sig(const TetOut& to, int q, int s, int k, int r0, int r1, int r2, int r3) {
+// face does not lie in it.  r0..r3 = rank (0..2) of node n among the three lattice points of face k
+// by point id (the rank of node k is unused): both sides of the lattice face compute the same ranks.
+// A node becomes a 3-bit set of ranks (original node: one bit, cut vertex: the two ends of its edge),
+// the face the set of its three node sets (8 bits).
+static __device__ __noinline__ uint32_t face_sig(unsigned long long nodes, int q, int s, int k, int r0, int r1, int r2, int r3) {
     uint32_t sig = 0u;
-#pragma unroll
     for (int m = 0; m < 3; ++m) {
-        const int code = to.node(q, C_FACE[s][m]);
+        const int code = (int)((nodes >> (5 * (4 * q + C_FACE[s][m]))) & 31ull);
         uint32_t nm;
         if (code < 4) {
             if (code == k) return 0u;
@@ -92,7 +106,7 @@ __device__ __forceinline__ uint32_t face_sig(const TetOut& to, int q, int s, int
     return sig;
 }
 
-// order of two occurrences of a face in different lattice tets: emission order of the lattice tets
+// order of two occurrences of a face in different lattice tets: a fixed total order of the lattice tets
 __device__ __forceinline__ bool tet_after(const Cell& a, int ta, const Cell& b, int tb) {
     if (a.cz != b.cz) return a.cz > b.cz;
     if (a.cy != b.cy) return a.cy > b.cy;
@@ -100,80 +114,70 @@ __device__ __forceinline__ bool tet_after(const Cell& a, int ta, const Cell& b, 
     return ta > tb;
 }
 
-// The faces of the pieces of the lattice tet on the other side of lattice face k of (c, t): up to four
-// signatures (8 bits each); *after = that tet comes later in emission order.
-static __device__ __noinline__ uint32_t neighbour_sigs(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, int k,
-                                                       bool* after) {
+// The lattice tet on the other side of lattice face k of (c, t) (tn: the tet's node coordinates):
+// returns its state (TET_NONE also when there is none: lattice border); c2 / t2 / ci2 describe it.
+static __device__ __noinline__ int neighbour_tet(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, int k,
+                                                 Cell& c2, int& t2, uint16_t& ci2) {
     const Lattice& L = S.L;
-    *after = false;
-    const bool flip = c.flip();
-    const int mk = (flip && k < 2) ? 1 - k : k;  // position of node k in the unflipped Tile::TETS row
-    Cell c2 = c;
-    int t2 = -1;
-    uint32_t fx[3], fy[3], fz[3];
-    {
-        int w = 0;
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-            if (n != k) { fx[w] = tet_X(tn, n); fy[w] = tet_Y(tn, n); fz[w] = tet_Z(tn, n); ++w; }
-    }
+    const int mk = (c.flip() && k < 2) ? 1 - k : k;  // position of node k in the unflipped Tile::TETS row
+    c2 = c;
+    t2 = -1;
+    ci2 = ci;
     if (t == 1) t2 = C_NB_CENTRAL[mk];
     else if (mk == C_CORNER_POS[t]) t2 = 1;
     else {
         // the face lies in a cell face: its three points share one coordinate
+        uint32_t fx[3], fy[3], fz[3];
+        int w = 0;
+        for (int n = 0; n < 4; ++n)
+            if (n != k) { fx[w] = tet_X(tn, n); fy[w] = tet_Y(tn, n); fz[w] = tet_Z(tn, n); ++w; }
         int64_t ncx = c.cx, ncy = c.cy, ncz = c.cz;
         if (fx[0] == fx[1] && fx[1] == fx[2]) ncx += fx[0] == c.cx ? -1 : 1;
         else if (fy[0] == fy[1] && fy[1] == fy[2]) ncy += fy[0] == c.cy ? -1 : 1;
         else ncz += fz[0] == c.cz ? -1 : 1;
-        if (ncx < 0 || ncy < 0 || ncz < 0 || ncx >= (int64_t)L.nx || ncy >= (int64_t)L.ny || ncz >= (int64_t)L.nz) return 0u;
+        const CellInfo i2 = cell_info(S, ncx, ncy, ncz);  // (outside the lattice: nothing)
+        if (!i2.any) return TET_NONE;
         c2 = make_cell((uint32_t)ncx, (uint32_t)ncy, (uint32_t)ncz);
+        ci2 = i2.ci;
         // its corner tet that holds the three points
         for (int tt = 0; tt < 5 && t2 < 0; ++tt) {
             if (tt == 1) continue;
             int hit = 0;
-#pragma unroll
             for (int n = 0; n < 4; ++n) {
                 uint32_t X, Y, Z;
                 corner_xyz(c2, C_TETS[tt][n], X, Y, Z);
-#pragma unroll
                 for (int f = 0; f < 3; ++f) hit += (X == fx[f] && Y == fy[f] && Z == fz[f]) ? 1 : 0;
             }
             if (hit == 3) t2 = tt;
         }
-        if (t2 < 0) return 0u;
+        if (t2 < 0) return TET_NONE;
     }
-    CellInfo i2;
-    if (c2.cx == c.cx && c2.cy == c.cy && c2.cz == c.cz) { i2.ci = ci; i2.full = (ci & CI_FULL) != 0; i2.any = true; }
-    else i2 = cell_info(S, c2.cx, c2.cy, c2.cz);
-    if (!i2.any || ci_tet_n(i2.ci, t2) == 0u) return 0u;
-    *after = tet_after(c2, t2, c, t);
-    if (i2.full) return (1u << 1) | (1u << 2) | (1u << 4);  // untouched: the whole lattice face
+    return tet_state(ci2, t2);
+}
+
+// signatures (up to four, 8 bits each) of the faces that the pieces of TRIMMED tet (c2, t2) have in the
+// lattice face whose three points are the nodes != k of (gid[0..3])
+static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, const Cell& c2, int t2, const unsigned long long gid[4],
+                                                             int k) {
     TetNodes tn2;
-    load_tet(L, c2, t2, tn2);
     TetOut to2;
-    pieces_of(S, c2, t2, i2.ci, tn2, to2);
-    // ranks of the neighbour's nodes among the same three points; k2 = its node off the face
-    unsigned long long g2[4], gf[3];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) g2[n] = pt_id(tn2.X[n], tn2.Y[n], tn2.Z[n]);
-#pragma unroll
-    for (int f = 0; f < 3; ++f) gf[f] = pt_id(fx[f], fy[f], fz[f]);
+    trimmed_pieces(L, c2, t2, tn2, to2);
+    unsigned long long g2[4];
+    for (int n = 0; n < 4; ++n) g2[n] = pt_id(tet_X(tn2, n), tet_Y(tn2, n), tet_Z(tn2, n));
     int k2 = 0, r2[4];
-#pragma unroll
     for (int n = 0; n < 4; ++n) {
         int rk = 0;
         bool on = false;
-#pragma unroll
-        for (int f = 0; f < 3; ++f) { on = on || g2[n] == gf[f]; rk += gf[f] < g2[n] ? 1 : 0; }
+        for (int o = 0; o < 4; ++o)
+            if (o != k) { on = on || g2[n] == gid[o]; rk += gid[o] < g2[n] ? 1 : 0; }
         if (!on) k2 = n;
         r2[n] = rk;
     }
     uint32_t sigs = 0u;
     int nsig = 0;
     for (int q2 = 0; q2 < to2.n; ++q2)
-#pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
-            const uint32_t sg = face_sig(to2, q2, s2, k2, r2[0], r2[1], r2[2], r2[3]);
+            const uint32_t sg = face_sig(to2.nodes, q2, s2, k2, r2[0], r2[1], r2[2], r2[3]);
             if (sg && nsig < 4) { sigs |= sg << (8 * nsig); ++nsig; }
         }
     return sigs;
@@ -182,24 +186,39 @@ static __device__ __noinline__ uint32_t neighbour_sigs(const Stuff& S, const Cel
 // Boundary sides of the pieces of lattice tet (c, t): bit 4 q + s.  `ci` = the cell's info word.
 static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int t, uint16_t ci) {
     const Lattice& L = S.L;
-    if (ci_tet_n(ci, t) == 0u) return 0u;
+    const int st = tet_state(ci, t);
+    if (st == TET_NONE) return 0u;
     TetNodes tn;
-    load_tet(L, c, t, tn);
     TetOut to;
-    pieces_of(S, c, t, ci, tn, to);
-    if (to.n == 0) return 0u;
+    if (st == TET_WHOLE) tet_coords(c, t, tn);
+    else trimmed_pieces(L, c, t, tn, to);
     unsigned long long gid[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) gid[n] = pt_id(tn.X[n], tn.Y[n], tn.Z[n]);
-    uint32_t nb_sigs0 = 0u, nb_sigs1 = 0u, nb_sigs2 = 0u, nb_sigs3 = 0u;
-    uint32_t nb_state = 0u;  // bit k: neighbour across face k known; bit 4 + k: it comes later in emission order
+    for (int n = 0; n < 4; ++n) gid[n] = pt_id(tet_X(tn, n), tet_Y(tn, n), tet_Z(tn, n));
     uint32_t out = 0u;
+    if (st == TET_WHOLE) {
+        // four whole lattice faces: each is matched by an untouched neighbour, unmatched next to nothing
+        for (int k = 0; k < 4; ++k) {
+            Cell c2;
+            int t2;
+            uint16_t ci2;
+            const int st2 = neighbour_tet(S, c, t, ci, tn, k, c2, t2, ci2);
+            if (st2 == TET_WHOLE) continue;
+            uint32_t cnt = 0u;
+            if (st2 == TET_TRIM) {
+                const uint32_t sigs = trimmed_sigs_on_face(L, c2, t2, gid, k);
+                for (int f = 0; f < 4; ++f) cnt += ((sigs >> (8 * f)) & 0xffu) == SIG_WHOLE_FACE ? 1u : 0u;
+            }
+            if ((cnt & 1u) == 0u && !(cnt != 0u && tet_after(c2, t2, c, t))) out |= 1u << side_opposite(k);
+        }
+        return out;
+    }
+    if (to.n == 0) return 0u;
+    uint32_t nb_sigs0 = 0u, nb_sigs1 = 0u, nb_sigs2 = 0u, nb_sigs3 = 0u;
+    uint32_t nb_state = 0u;  // bit k: neighbour across face k known; bit 4 + k: it comes later in the tet order
     for (int q = 0; q < to.n; ++q) {
-#pragma unroll
         for (int s = 0; s < 4; ++s) {
             // node-code set of this face, and the lattice faces all its nodes lie in
             uint32_t codes = 0u, fmask = 0xfu;
-#pragma unroll
             for (int m = 0; m < 3; ++m) {
                 const int code = to.node(q, C_FACE[s][m]);
                 codes |= 1u << code;
@@ -209,36 +228,36 @@ static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int 
             bool last = true;
             // ... among the other pieces of this lattice tet
             for (int q2 = 0; q2 < to.n; ++q2)
-#pragma unroll
                 for (int s2 = 0; s2 < 4; ++s2) {
                     if (q2 == q && s2 == s) continue;
-                    uint32_t c2 = 0u;
-#pragma unroll
-                    for (int m = 0; m < 3; ++m) c2 |= 1u << to.node(q2, C_FACE[s2][m]);
-                    if (c2 == codes) { ++cnt; if (q2 > q || (q2 == q && s2 > s)) last = false; }
+                    uint32_t cd2 = 0u;
+                    for (int m = 0; m < 3; ++m) cd2 |= 1u << to.node(q2, C_FACE[s2][m]);
+                    if (cd2 == codes) { ++cnt; if (q2 > q || (q2 == q && s2 > s)) last = false; }
                 }
             // ... and among the pieces of the lattice tet across the lattice face it lies in
             fmask &= 0xfu;
             if (fmask) {
                 const int k = __ffs((int)fmask) - 1;
                 int r[4];
-#pragma unroll
                 for (int n = 0; n < 4; ++n) {
                     int rk = 0;
-#pragma unroll
                     for (int o = 0; o < 4; ++o) rk += (o != k && o != n && gid[o] < gid[n]) ? 1 : 0;
                     r[n] = rk;
                 }
-                const uint32_t mine = face_sig(to, q, s, k, r[0], r[1], r[2], r[3]);
+                const uint32_t mine = face_sig(to.nodes, q, s, k, r[0], r[1], r[2], r[3]);
                 if (!((nb_state >> k) & 1u)) {
-                    bool after;
-                    const uint32_t sg = neighbour_sigs(S, c, t, ci, tn, k, &after);
+                    Cell c2;
+                    int t2;
+                    uint16_t ci2;
+                    const int st2 = neighbour_tet(S, c, t, ci, tn, k, c2, t2, ci2);
+                    uint32_t sg = 0u;
+                    if (st2 == TET_WHOLE) sg = SIG_WHOLE_FACE;
+                    else if (st2 == TET_TRIM) sg = trimmed_sigs_on_face(L, c2, t2, gid, k);
                     if (k == 0) nb_sigs0 = sg; else if (k == 1) nb_sigs1 = sg; else if (k == 2) nb_sigs2 = sg; else nb_sigs3 = sg;
-                    nb_state |= (1u << k) | (after ? 16u << k : 0u);
+                    nb_state |= (1u << k) | ((st2 != TET_NONE && tet_after(c2, t2, c, t)) ? 16u << k : 0u);
                 }
                 const uint32_t sigs = pick4(nb_sigs0, nb_sigs1, nb_sigs2, nb_sigs3, k);
                 const bool after = (nb_state >> (4 + k)) & 1u;
-#pragma unroll
                 for (int f = 0; f < 4; ++f)
                     if (mine != 0u && ((sigs >> (8 * f)) & 0xffu) == mine) { ++cnt; if (after) last = false; }
             }
@@ -266,59 +285,69 @@ __device__ __forceinline__ bool boundary_tile_candidate(const Stuff& S, uint64_t
     return false;
 }
 
-// One block per cell tile.  COUNT pass (EMIT = false): tile_io[tile] = number of boundary sides of the
-// tile's owned cells.  EMIT pass: tile_io[tile] = index of the tile's first side; sides[] receives
-// (elem, side) pairs.
-template <bool EMIT>
-__global__ void __launch_bounds__(TILE_THREADS)
-k_boundary_sides(Stuff S, unsigned long long* __restrict__ tile_io, unsigned long long tet_base,
-                 unsigned long long* __restrict__ sides) {
-    __shared__ unsigned long long s_acc;
-    __shared__ uint32_t s_scan[9];
-    __shared__ uint16_t s_ci[TILE_POINTS], s_off[TILE_POINTS], s_list[TILE_POINTS];
-    const Lattice& L = S.L;
-    const uint64_t tile = blockIdx.x;
+// the cell tiles that can hold a boundary side -> work list (its index is the tile's slot in the mask scratch)
+static __global__ void k_boundary_tiles(Stuff S, uint64_t ntiles, uint32_t* __restrict__ list, unsigned long long* __restrict__ n_list) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
     uint32_t X0, Y0, Z0;
+    tile_origin(S.g, t, X0, Y0, Z0);
+    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
+    if (X0 >= S.L.nx || Y0 >= S.L.ny || zhi <= zlo || !boundary_tile_candidate(S, t, S.cuni[t])) return;
+    list[atomicAdd(n_list, 1ull)] = (uint32_t)t;
+}
+
+// per-cell info of a tile's owned cells -> s_ci (0 for cells that are not owned / outside the lattice)
+__device__ __forceinline__ void stage_cell_info(const Stuff& S, uint32_t tile, uint16_t* s_ci, uint32_t& X0, uint32_t& Y0, uint32_t& Z0,
+                                                uint32_t& zlo, uint32_t& zhi) {
+    const Lattice& L = S.L;
     tile_origin(S.g, tile, X0, Y0, Z0);
     const uint8_t cu = S.cuni[tile];
-    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (X0 >= L.nx || Y0 >= L.ny || zhi <= zlo || !boundary_tile_candidate(S, tile, cu)) {
-        if (!EMIT && threadIdx.x == 0) tile_io[tile] = 0ull;
-        return;
-    }
+    zlo = max(Z0, S.c0); zhi = min(Z0 + TS, S.c1);
     const uint32_t nxt = min(TS, L.nx - X0);
-    // per-cell info and the offset of the cell's first output tet inside the tile (emission order:
-    // x-rows of cells, see k_tet_emit / k_tet_emit_full)
-    {
-        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
-        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
-        const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
-        const uint32_t nx_row = row_owned ? nxt : 0u;
-        uint32_t acc = 0;
-        uint32_t pre[TS];
+    const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+    const uint32_t cy = Y0 + ly, cz = Z0 + lz;
+    const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
+    const uint32_t nx_row = row_owned ? nxt : 0u;
 #pragma unroll
-        for (uint32_t i = 0; i < TS; ++i) {
-            uint16_t ci = 0;
-            if (i < nx_row) ci = cu == CU_FULL ? CI_ALL_FULL : S.cinfo[cidx(S, X0 + i, cy, cz)];
-            s_ci[threadIdx.x * TS + i] = ci;
-            pre[i] = acc;
-            acc += ci_count(ci);
-        }
-        uint32_t tot;
-        const uint32_t ex = block_exscan(acc, &tot, s_scan);
-#pragma unroll
-        for (uint32_t i = 0; i < TS; ++i) s_off[threadIdx.x * TS + i] = (uint16_t)(ex + pre[i]);
+    for (uint32_t i = 0; i < TS; ++i) {
+        uint16_t ci = 0;
+        if (i < nx_row) ci = cu == CU_FULL ? CI_ALL_FULL : S.cinfo[cidx(S, X0 + i, cy, cz)];
+        s_ci[threadIdx.x * TS + i] = ci;
     }
-    __syncthreads();
-    // candidate cells in emission order: not full, or full next to a cell that is not
-    uint32_t ncand = 0;
-    for (int rnd = 0; rnd < TILE_ROUNDS; ++rnd) {
-        const uint32_t j = (uint32_t)rnd * TILE_THREADS + threadIdx.x;
-        const uint16_t ci = s_ci[j];
-        bool cand = false;
-        if (ci_count(ci) != 0u) {
-            if (!(ci & CI_FULL)) cand = true;
-            else {
+}
+
+// Pass 1, one listed tile at a time: the boundary sides of every lattice tet of the tile's owned cells as a
+// 12-bit mask (bit 4 q + s), written to masks[slot][t][cell] (5 x 4096 uint16 per tile), and the tile's
+// number of sides -> tile_tot[tile].  Only cells next to the surface do any work: the cells that are not
+// full, and full cells with a neighbour that is not; their lattice tets are dealt to the threads one by one.
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
+                 unsigned long long* __restrict__ cursor, uint16_t* __restrict__ masks, unsigned long long* __restrict__ tile_tot) {
+    __shared__ unsigned long long s_acc;
+    __shared__ unsigned long long s_item;
+    __shared__ uint16_t s_ci[TILE_POINTS], s_list[TILE_POINTS];
+    __shared__ uint32_t s_n;
+    const Lattice& L = S.L;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1ull);
+        __syncthreads();
+        const unsigned long long slot = s_item;
+        if (slot >= *n_list) break;
+        const uint32_t tile = tile_list[slot];
+        uint32_t X0, Y0, Z0, zlo, zhi;
+        stage_cell_info(S, tile, s_ci, X0, Y0, Z0, zlo, zhi);
+        if (threadIdx.x == 0) s_n = 0u;
+        // this tile's masks start out empty
+        uint4* mz = reinterpret_cast<uint4*>(masks + slot * (5ull * TILE_POINTS));
+        for (uint32_t i = threadIdx.x; i < 5u * TILE_POINTS * 2u / 16u; i += TILE_THREADS) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        for (int rnd = 0; rnd < TILE_ROUNDS; ++rnd) {
+            const uint32_t j = (uint32_t)rnd * TILE_THREADS + threadIdx.x;
+            const uint16_t ci = s_ci[j];
+            if (ci_count(ci) == 0u) continue;
+            bool cand = !(ci & CI_FULL);
+            if (!cand) {
                 const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
                 const int64_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
                 // neighbours inside the tile (and owned) come from shared memory
@@ -332,50 +361,66 @@ k_boundary_sides(Stuff S, unsigned long long* __restrict__ tile_io, unsigned lon
                 cand = !(full_at(-1, 0, 0) && full_at(1, 0, 0) && full_at(0, -1, 0) && full_at(0, 1, 0) && full_at(0, 0, -1) &&
                          full_at(0, 0, 1));
             }
+            if (cand) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+        }
+        __syncthreads();
+        const uint32_t ncand = s_n;
+        unsigned long long mine = 0ull;
+        uint16_t* mt = masks + slot * (5ull * TILE_POINTS);
+        for (uint32_t w = threadIdx.x; w < 5u * ncand; w += TILE_THREADS) {
+            const uint32_t j = s_list[w / 5u], t = w % 5u;
+            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+            const uint32_t mask = tet_boundary_mask(S, c, (int)t, s_ci[j]);
+            if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+        }
+        const unsigned long long tot = block_sum(mine, &s_acc);
+        if (threadIdx.x == 0) tile_tot[tile] = tot;
+    }
+}
+
+// Pass 2: expand the masks into (elem, side) pairs in emission order (tiles, x-rows of cells, lattice tets,
+// pieces, sides): the output is sorted by (elem, side).  tile_base[tile] = index of the tile's first side.
+static __global__ void __launch_bounds__(TILE_THREADS)
+k_boundary_emit(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
+                unsigned long long* __restrict__ cursor, const uint16_t* __restrict__ masks,
+                const unsigned long long* __restrict__ tile_base, unsigned long long tet_base, unsigned long long* __restrict__ sides) {
+    __shared__ unsigned long long s_item;
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint16_t s_ci[TILE_POINTS];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1ull);
+        __syncthreads();
+        const unsigned long long slot = s_item;
+        if (slot >= *n_list) break;
+        const uint32_t tile = tile_list[slot];
+        uint32_t X0, Y0, Z0, zlo, zhi;
+        stage_cell_info(S, tile, s_ci, X0, Y0, Z0, zlo, zhi);   // every thread stages (and then owns) one x-row
+        const uint16_t* mt = masks + slot * (5ull * TILE_POINTS);
+        // tets and sides of this thread's row
+        uint32_t ntet = 0, nside = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) {
+            const uint32_t j = threadIdx.x * TS + i;
+            ntet += ci_count(s_ci[j]);
+#pragma unroll
+            for (uint32_t t = 0; t < 5u; ++t) nside += (uint32_t)__popc((uint32_t)mt[t * TILE_POINTS + j]);
         }
         uint32_t tot;
-        const uint32_t ex = block_exscan(cand ? 1u : 0u, &tot, s_scan);
-        if (cand) s_list[ncand + ex] = (uint16_t)j;
-        ncand += tot;
-    }
-    __syncthreads();
-    // the lattice tets of the candidate cells, in emission order
-    const uint64_t tb = tet_base + S.ttbase[tile];
-    unsigned long long mine = 0ull;
-    uint64_t run = EMIT ? tile_io[tile] : 0ull;
-    for (uint32_t base = 0; base < 5u * ncand; base += TILE_THREADS) {
-        const uint32_t w = base + threadIdx.x;
-        uint32_t mask = 0u, j = 0u, t = 0u;
-        uint16_t ci = 0;
-        if (w < 5u * ncand) {
-            j = s_list[w / 5u];
-            t = w % 5u;
-            ci = s_ci[j];
-            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
-            mask = tet_boundary_mask(S, c, (int)t, ci);
-        }
-        if (!EMIT) {
-            mine += (unsigned long long)__popc(mask);
-        } else {
-            uint32_t tot;
-            const uint32_t ex = block_exscan((uint32_t)__popc(mask), &tot, s_scan);
-            if (mask) {
-                uint32_t before = 0;
-                for (uint32_t u = 0; u < t; ++u) before += ci_tet_n(ci, (int)u);
-                uint64_t o = run + ex;
-                for (uint32_t b = 0; b < 12u; ++b)
-                    if ((mask >> b) & 1u) {
-                        sides[2 * o] = tb + s_off[j] + before + (b >> 2);
-                        sides[2 * o + 1] = b & 3u;
-                        ++o;
-                    }
+        const uint32_t ex = block_exscan(ntet | (nside << 16), &tot, s_scan);  // <= 61440 tets, sides are far fewer
+        if ((tot >> 16) == 0u) continue;
+        uint64_t elem = tet_base + S.ttbase[tile] + (ex & 0xffffu);
+        uint64_t o = tile_base[tile] + (ex >> 16);
+        for (uint32_t i = 0; i < TS && nside != 0u; ++i) {
+            const uint32_t j = threadIdx.x * TS + i;
+            const uint16_t ci = s_ci[j];
+            for (uint32_t t = 0; t < 5u; ++t) {
+                const uint32_t mask = mt[t * TILE_POINTS + j];
+                for (uint32_t b = 0; b < 12u && mask; ++b)
+                    if ((mask >> b) & 1u) { sides[2 * o] = elem + (b >> 2); sides[2 * o + 1] = b & 3u; ++o; }
+                elem += ci_tet_n(ci, (int)t);
             }
-            run += tot;
         }
-    }
-    if (!EMIT) {
-        const unsigned long long tot = block_sum(mine, &s_acc);
-        if (threadIdx.x == 0) tile_io[tile] = tot;
     }
 }
 
@@ -502,34 +547,51 @@ int compute_boundary(mc_mesh* m) {
     MC_CUDA(cudaEventCreate(&sc.e0));
     MC_CUDA(cudaEventCreate(&sc.e1));
     MC_CUDA(cudaEventRecord(sc.e0, s));
-    DevBuf ftot, fbase, dtotal;
+    DevBuf ftot, fbase, dctl, dlist, dmasks;
     int rc = sc.alloc((m->n_tiles + 1) * 8, ftot);
     if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, fbase);
-    if (rc == MC_OK) rc = sc.alloc(4 * 8, dtotal);
+    if (rc == MC_OK) rc = sc.alloc(8 * 8, dctl);   // [0..1] totals, [2] list length, [3] / [4] cursors
+    if (rc == MC_OK) rc = sc.alloc(std::max<uint64_t>(m->n_tiles, 1) * 4, dlist);
     if (rc != MC_OK) return rc;
-    unsigned long long* totals = (unsigned long long*)dtotal.p;
+    unsigned long long* ctl = (unsigned long long*)dctl.p;
     const Stuff S = make_stuff(m);
     m->n_sides = 0;
     m->h_sides.clear();
     m->have_h_sides = false;
     c->release(m->d_sides);
     if (m->n_tiles > 0 && m->n_tets > 0) {
-        k_boundary_sides<false><<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)ftot.p, m->tet_base, nullptr);
+        MC_CUDA(cudaMemsetAsync(dctl.p, 0, 64, s));
+        MC_CUDA(cudaMemsetAsync(ftot.p, 0, (m->n_tiles + 1) * 8, s));
+        k_boundary_tiles<<<(unsigned)((m->n_tiles + 255) / 256), 256, 0, s>>>(S, m->n_tiles, (uint32_t*)dlist.p, ctl + 2);
         c->launches++;
         MC_CUDA(cudaGetLastError());
-        rc = scan_tiles(c, ftot.p, m->n_tiles, fbase.p, nullptr, m->d_scan_sums.p, totals);
-        if (rc != MC_OK) return rc;
-        unsigned long long h[2];
-        MC_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, s));
+        unsigned long long nlist = 0;
+        MC_CUDA(cudaMemcpyAsync(&nlist, ctl + 2, 8, cudaMemcpyDeviceToHost, s));
         MC_CUDA(cudaStreamSynchronize(s));
-        m->n_sides = h[0];
-        if (m->n_sides) {
-            rc = c->alloc(m->n_sides * 16, m->d_sides);
+        if (nlist) {
+            // 5 x 4096 uint16 masks per listed tile
+            rc = sc.alloc(nlist * 5ull * TILE_POINTS * 2ull, dmasks);
             if (rc != MC_OK) return rc;
-            k_boundary_sides<true><<<(unsigned)m->n_tiles, TILE_THREADS, 0, s>>>(S, (unsigned long long*)fbase.p, m->tet_base,
-                                                                                (unsigned long long*)m->d_sides.p);
+            const unsigned grid = (unsigned)std::min<uint64_t>(nlist, (uint64_t)c->sm_count * TILE_GRID_PER_SM);
+            k_boundary_masks<<<grid, TILE_THREADS, 0, s>>>(S, (const uint32_t*)dlist.p, ctl + 2, ctl + 3, (uint16_t*)dmasks.p,
+                                                          (unsigned long long*)ftot.p);
             c->launches++;
             MC_CUDA(cudaGetLastError());
+            rc = scan_tiles(c, ftot.p, m->n_tiles, fbase.p, nullptr, m->d_scan_sums.p, ctl);
+            if (rc != MC_OK) return rc;
+            unsigned long long h[2];
+            MC_CUDA(cudaMemcpyAsync(h, ctl, 16, cudaMemcpyDeviceToHost, s));
+            MC_CUDA(cudaStreamSynchronize(s));
+            m->n_sides = h[0];
+            if (m->n_sides) {
+                rc = c->alloc(m->n_sides * 16, m->d_sides);
+                if (rc != MC_OK) return rc;
+                k_boundary_emit<<<grid, TILE_THREADS, 0, s>>>(S, (const uint32_t*)dlist.p, ctl + 2, ctl + 4, (const uint16_t*)dmasks.p,
+                                                             (const unsigned long long*)fbase.p, m->tet_base,
+                                                             (unsigned long long*)m->d_sides.p);
+                c->launches++;
+                MC_CUDA(cudaGetLastError());
+            }
         }
     }
     MC_CUDA(cudaEventRecord(sc.e1, s));

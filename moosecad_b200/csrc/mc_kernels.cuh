@@ -34,9 +34,10 @@ constexpr uint8_t TF_NEG = 1, TF_POS = 2, TF_HASWARP = 4;
 constexpr uint8_t VU_ACTIVE = 0, VU_NEG = 1, VU_POS = 2;    // point tile: 27-neighbourhood all NEG / all POS
 constexpr uint8_t CU_ACTIVE = 0, CU_FULL = 1, CU_EMPTY = 2; // cell tile: every cell emits its 5 lattice tets / nothing
 // per-cell info written by k_classify_cells (ACTIVE cell tiles only):
-// bits 2t..2t+1 = number of output tets of lattice tet t (0..3), bits 10..14 = tet t dropped by the
-// exterior test, bit 15 = all five lattice tets emitted untouched
-constexpr uint16_t CI_REMOVED_SHIFT = 10;
+// bits 2t..2t+1 = number of output tets of lattice tet t (0..3), bits 10..14 = lattice tet t is emitted
+// untouched (kept, not trimmed, not dropped by the exterior test: its one output tet is the lattice
+// tet itself), bit 15 = all five lattice tets emitted untouched
+constexpr uint16_t CI_UNTOUCHED_SHIFT = 10;
 constexpr uint16_t CI_FULL = 1u << 15;
 constexpr uint16_t CI_ALL_FULL = (uint16_t)(0x155u | CI_FULL);  // one output tet per lattice tet
 // on a FULL cell the removed bits are free: bit 10 marks "some corner is zero (possibly warped)",
@@ -575,7 +576,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             classify_tet<true>(L, c, (int)t, tn, prog, -1, to);
             if (to.kase == -2) continue;  // not kept by cut_lattice
             uint32_t bits = ((uint32_t)to.n << (2u * t)) | (1u << (16u + t));  // bit 16+t: kept
-            if (to.ext_removed) { bits |= 1u << (CI_REMOVED_SHIFT + t); if (own) atomicAdd(&s_stat[7], 1u); }
+            if (to.ext_removed) { bits |= 1u << (10u + t); if (own) atomicAdd(&s_stat[7], 1u); }  // bit 10+t: dropped by the exterior test
             if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&s_stat[to.kase], 1u); }  // bit 24+t: trimmed
             atomicOr(&s_ci[q], bits);
             // zero-valued original vertices that made it into the output are "used"
@@ -594,10 +595,12 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             const uint32_t j = s_list[pass + q];
             const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
             const uint32_t b = s_ci[q];
-            uint16_t ci = (uint16_t)(b & 0x7fffu);
-            const uint32_t kept = (uint32_t)__popc((b >> 16) & 31u);
-            const bool untouched = kept == 5u && ((b >> 24) & 31u) == 0u && ((b >> CI_REMOVED_SHIFT) & 31u) == 0u;
-            if (untouched && ci_count(ci) == 5u) ci |= (uint16_t)(CI_FULL | CI_FULL_ZERO_CORNER);
+            const uint32_t kept_bits = (b >> 16) & 31u, removed_bits = (b >> 10) & 31u, trimmed_bits = (b >> 24) & 31u;
+            const uint32_t untouched_bits = kept_bits & ~removed_bits & ~trimmed_bits;
+            uint16_t ci = (uint16_t)((b & 0x3ffu) | (untouched_bits << CI_UNTOUCHED_SHIFT));
+            const uint32_t kept = (uint32_t)__popc(kept_bits);
+            // (on a FULL cell bit 10 doubles as CI_FULL_ZERO_CORNER: all five untouched bits are set anyway)
+            if (untouched_bits == 31u && ci_count(ci) == 5u) ci |= (uint16_t)(CI_FULL | CI_FULL_ZERO_CORNER);
             S.cinfo[cidx(S, cx, cy, cz)] = ci;
             if (cz >= S.c0 && cz < S.c1) { my_out += ci_count(ci); my_kept += kept; my_listed += ci_count(ci); }
         }
@@ -1390,7 +1393,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         TetNodes tn;
         load_tet(L, c, t, tn);
         TetOut to;
-        classify_tet<false>(L, c, t, tn, nullptr, (ci >> (CI_REMOVED_SHIFT + t)) & 1, to);
+        classify_tet<false>(L, c, t, tn, nullptr, 0, to);  // nt != 0: not dropped by the exterior test
         int li[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);

@@ -49,9 +49,15 @@ def main():
             tets = np.empty((cnt[1], 4), dtype=np.uint64)
             _lib.check(lib.mc_mesh_copy_to_host(h, coords.ctypes.data_as(C.c_void_p), tets.ctypes.data_as(C.c_void_p), 8))
             st = slabs.mesh_stats(h)
+            # Mesh::boundary on the slab (global (elem, side) pairs) and the device checksums
+            from moosecad_b200.tessellate3d import mesh_checksum
+            ns = C.c_uint64()
+            _lib.check(lib.mc_mesh_boundary(h, C.byref(ns)))
+            sides = np.ctypeslib.as_array(lib.mc_mesh_boundary_sides(h), shape=(ns.value, 2)).copy() if ns.value else np.zeros((0, 2), dtype=np.uint64)
+            cs = mesh_checksum(h)
             lib.mc_mesh_free(h)
             gathered = [None] * world if rank == 0 else None
-            dist.gather_object((coords, tets, sm.vertex_base, sm.tet_base, st), gathered, dst=0)
+            dist.gather_object((coords, tets, sm.vertex_base, sm.tet_base, st, sides, cs), gathered, dst=0)
             if rank == 0:
                 gathered.sort(key=lambda t: t[2])
                 allc = np.concatenate([t[0] for t in gathered])
@@ -63,6 +69,14 @@ def main():
                     ws, ss = whole.stats(), slabs.combine_stats([t[4] for t in gathered])
                     for key in ("ntets_stage", "stats", "aspect_ratio", "inverted"):
                         assert ss[key] == ws[key], (key, ss[key], ws[key])
+                    alls = np.concatenate([t[5] for t in gathered])
+                    a = canon.canonical(whole.vertices(), whole.elems(), {"s": sorted(whole.boundary().sides())})[2]["s"]
+                    b = canon.canonical(allc, allt, {"s": alls})[2]["s"]
+                    assert np.array_equal(a, b), "boundary sides differ"
+                    wcs = whole.checksum()
+                    assert sum(t[6]["vertices"] for t in gathered) % (1 << 64) == wcs["vertices"]
+                    assert sum(t[6]["tets"] for t in gathered) % (1 << 64) == wcs["tets"]
+                    assert sum(t[6]["tets_skipped"] for t in gathered) == 0
                     print(f"SLAB_PARITY_OK {name} world={world} verts={len(allc)} tets={len(allt)}", flush=True)
                 except AssertionError as e:
                     ok = False
