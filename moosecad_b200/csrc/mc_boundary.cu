@@ -20,6 +20,7 @@
 // across a slab boundary is re-classified locally and no exchange is needed.  Sides come out sorted by
 // (elem, side) because tiles, cells, lattice tets and pieces are visited in emission order.
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "mc_internal.hpp"
@@ -30,12 +31,51 @@ namespace mc {
 Stuff make_stuff(const mc_mesh* m);  // mc_mesher.cu
 
 // ---- lattice topology helpers -----------------------------------------------------------------
-// unflipped Tile::TETS positions: the central tet is t = 1 = [0, 2, 5, 7]; across the face opposite
-// its node at position m lies the corner tet NB_CENTRAL[m] of the same cell.  A corner tet
-// (t = 0, 2, 3, 4) touches the central tet through the face opposite its odd ("corner") vertex, which
-// sits at position CORNER_POS[t]; its other three faces lie in cell faces.
-static __constant__ int8_t C_NB_CENTRAL[4] = {3, 2, 4, 0};
-static __constant__ int8_t C_CORNER_POS[5] = {1, -1, 3, 1, 3};
+// The lattice tet across lattice face k (= opposite node k of the flipped node order) of tet t of a
+// cell with mirroring class p = fx | fy << 1 | fz << 2: (dx + 1) | (dy + 1) << 2 | (dz + 1) << 4 |
+// t2 << 6.  Built on the host from Tile::LATTICE / Tile::TETS by brute force (build_nb_table).
+static __constant__ uint16_t C_NB_TABLE[8][5][4];
+
+static void build_nb_table(uint16_t tab[8][5][4]) {
+    static const int LAT[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    static const int TETS[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};
+    // node n (flipped order) of tet t of the cell at offset o (cells), mirroring from the parity of p0 + o
+    auto node = [&](const int par[3], const int off[3], int t, int n, int out[3]) {
+        bool mir[3];
+        for (int a = 0; a < 3; ++a) mir[a] = ((par[a] + off[a]) & 1) != 0;
+        const bool flip = mir[0] ^ mir[1] ^ mir[2];
+        const int k = TETS[t][(flip && n < 2) ? 1 - n : n];
+        for (int a = 0; a < 3; ++a) out[a] = off[a] + (mir[a] ? 1 - LAT[k][a] : LAT[k][a]);
+    };
+    for (int p = 0; p < 8; ++p) {
+        const int par[3] = {p & 1, (p >> 1) & 1, (p >> 2) & 1};
+        const int zero[3] = {0, 0, 0};
+        for (int t = 0; t < 5; ++t)
+            for (int k = 0; k < 4; ++k) {
+                int face[3][3], w = 0;
+                for (int n = 0; n < 4; ++n)
+                    if (n != k) node(par, zero, t, n, face[w++]);
+                uint16_t found = 0xffffu;
+                for (int dx = -1; dx <= 1; ++dx)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dz = -1; dz <= 1; ++dz) {
+                            if (std::abs(dx) + std::abs(dy) + std::abs(dz) > 1) continue;
+                            const int off[3] = {dx, dy, dz};
+                            for (int t2 = 0; t2 < 5; ++t2) {
+                                if (dx == 0 && dy == 0 && dz == 0 && t2 == t) continue;
+                                int hit = 0;
+                                for (int n = 0; n < 4; ++n) {
+                                    int q[3];
+                                    node(par, off, t2, n, q);
+                                    for (int f = 0; f < 3; ++f) hit += (q[0] == face[f][0] && q[1] == face[f][1] && q[2] == face[f][2]) ? 1 : 0;
+                                }
+                                if (hit == 3) found = (uint16_t)((dx + 1) | ((dy + 1) << 2) | ((dz + 1) << 4) | (t2 << 6));
+                            }
+                        }
+                tab[p][t][k] = found;
+            }
+    }
+}
 
 __device__ __forceinline__ unsigned long long pt_id(uint32_t X, uint32_t Y, uint32_t Z) {
     return ((unsigned long long)Z << 42) | ((unsigned long long)Y << 21) | (unsigned long long)X;
@@ -114,44 +154,17 @@ __device__ __forceinline__ bool tet_after(const Cell& a, int ta, const Cell& b, 
     return ta > tb;
 }
 
-// The lattice tet on the other side of lattice face k of (c, t) (tn: the tet's node coordinates):
-// returns its state (TET_NONE also when there is none: lattice border); c2 / t2 / ci2 describe it.
-static __device__ __noinline__ int neighbour_tet(const Stuff& S, const Cell& c, int t, uint16_t ci, const TetNodes& tn, int k,
-                                                 Cell& c2, int& t2, uint16_t& ci2) {
-    const Lattice& L = S.L;
-    const int mk = (c.flip() && k < 2) ? 1 - k : k;  // position of node k in the unflipped Tile::TETS row
-    c2 = c;
-    t2 = -1;
-    ci2 = ci;
-    if (t == 1) t2 = C_NB_CENTRAL[mk];
-    else if (mk == C_CORNER_POS[t]) t2 = 1;
-    else {
-        // the face lies in a cell face: its three points share one coordinate
-        uint32_t fx[3], fy[3], fz[3];
-        int w = 0;
-        for (int n = 0; n < 4; ++n)
-            if (n != k) { fx[w] = tet_X(tn, n); fy[w] = tet_Y(tn, n); fz[w] = tet_Z(tn, n); ++w; }
-        int64_t ncx = c.cx, ncy = c.cy, ncz = c.cz;
-        if (fx[0] == fx[1] && fx[1] == fx[2]) ncx += fx[0] == c.cx ? -1 : 1;
-        else if (fy[0] == fy[1] && fy[1] == fy[2]) ncy += fy[0] == c.cy ? -1 : 1;
-        else ncz += fz[0] == c.cz ? -1 : 1;
-        const CellInfo i2 = cell_info(S, ncx, ncy, ncz);  // (outside the lattice: nothing)
-        if (!i2.any) return TET_NONE;
-        c2 = make_cell((uint32_t)ncx, (uint32_t)ncy, (uint32_t)ncz);
-        ci2 = i2.ci;
-        // its corner tet that holds the three points
-        for (int tt = 0; tt < 5 && t2 < 0; ++tt) {
-            if (tt == 1) continue;
-            int hit = 0;
-            for (int n = 0; n < 4; ++n) {
-                uint32_t X, Y, Z;
-                corner_xyz(c2, C_TETS[tt][n], X, Y, Z);
-                for (int f = 0; f < 3; ++f) hit += (X == fx[f] && Y == fy[f] && Z == fz[f]) ? 1 : 0;
-            }
-            if (hit == 3) t2 = tt;
-        }
-        if (t2 < 0) return TET_NONE;
-    }
+// The lattice tet on the other side of lattice face k of (c, t): returns its state (TET_NONE also when
+// there is none: lattice border); c2 / t2 / ci2 describe it.
+__device__ __forceinline__ int neighbour_tet(const Stuff& S, const Cell& c, int t, uint16_t ci, int k, Cell& c2, int& t2, uint16_t& ci2) {
+    const uint32_t e = C_NB_TABLE[(c.fx ? 1 : 0) | (c.fy ? 2 : 0) | (c.fz ? 4 : 0)][t][k];
+    t2 = (int)(e >> 6);
+    const int dx = (int)(e & 3u) - 1, dy = (int)((e >> 2) & 3u) - 1, dz = (int)((e >> 4) & 3u) - 1;
+    if ((dx | dy | dz) == 0) { c2 = c; ci2 = ci; return tet_state(ci, t2); }
+    const CellInfo i2 = cell_info(S, (int64_t)c.cx + dx, (int64_t)c.cy + dy, (int64_t)c.cz + dz);  // (outside the lattice: nothing)
+    if (!i2.any) return TET_NONE;
+    c2 = make_cell(c.cx + dx, c.cy + dy, c.cz + dz);
+    ci2 = i2.ci;
     return tet_state(ci2, t2);
 }
 
@@ -201,7 +214,7 @@ static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int 
             Cell c2;
             int t2;
             uint16_t ci2;
-            const int st2 = neighbour_tet(S, c, t, ci, tn, k, c2, t2, ci2);
+            const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
             if (st2 == TET_WHOLE) continue;
             uint32_t cnt = 0u;
             if (st2 == TET_TRIM) {
@@ -249,7 +262,7 @@ static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int 
                     Cell c2;
                     int t2;
                     uint16_t ci2;
-                    const int st2 = neighbour_tet(S, c, t, ci, tn, k, c2, t2, ci2);
+                    const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
                     uint32_t sg = 0u;
                     if (st2 == TET_WHOLE) sg = SIG_WHOLE_FACE;
                     else if (st2 == TET_TRIM) sg = trimmed_sigs_on_face(L, c2, t2, gid, k);
@@ -543,6 +556,12 @@ int compute_boundary(mc_mesh* m) {
     const Lattice& L = m->L;
     if (L.nx >= (1u << 21) || L.ny >= (1u << 21) || L.nz >= (1u << 21))
         return fail(MC_ERR_LIMIT, "Mesh::boundary: more than 2^21 cells along an axis");
+    {
+        // constant memory is per device; the upload is 320 bytes
+        uint16_t tab[8][5][4];
+        build_nb_table(tab);
+        MC_CUDA(cudaMemcpyToSymbolAsync(C_NB_TABLE, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, s));
+    }
     Scratch sc(c);
     MC_CUDA(cudaEventCreate(&sc.e0));
     MC_CUDA(cudaEventCreate(&sc.e1));
