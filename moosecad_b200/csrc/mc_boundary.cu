@@ -168,114 +168,145 @@ __device__ __forceinline__ int neighbour_tet(const Stuff& S, const Cell& c, int 
     return tet_state(ci2, t2);
 }
 
+// node-code set (bit per code 0..19) of face (q, s) of a piece list, and the lattice faces (bit k =
+// face opposite node k) every node of it lies in
+__device__ __forceinline__ void face_codes(unsigned long long nodes, int q, int s, uint32_t& codes, uint32_t& fmask) {
+    codes = 0u;
+    fmask = 0xfu;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int code = (int)((nodes >> (5 * (4 * q + C_FACE[s][m]))) & 31ull);
+        codes |= 1u << code;
+        fmask &= code < 4 ? ~(1u << code) : ~((1u << ((code - 4) >> 2)) | (1u << ((code - 4) & 3)));
+    }
+    fmask &= 0xfu;
+}
+
 // signatures (up to four, 8 bits each) of the faces that the pieces of TRIMMED tet (c2, t2) have in the
 // lattice face whose three points are the nodes != k of (gid[0..3])
-static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, const Cell& c2, int t2, const unsigned long long gid[4],
-                                                             int k) {
+static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, const Cell& c2, int t2, unsigned long long g0,
+                                                             unsigned long long g1, unsigned long long g2_, unsigned long long g3, int k) {
     TetNodes tn2;
     TetOut to2;
     trimmed_pieces(L, c2, t2, tn2, to2);
-    unsigned long long g2[4];
-    for (int n = 0; n < 4; ++n) g2[n] = pt_id(tet_X(tn2, n), tet_Y(tn2, n), tet_Z(tn2, n));
+    const unsigned long long gid[4] = {g0, g1, g2_, g3};
+    unsigned long long h[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) h[n] = pt_id(tn2.X[n], tn2.Y[n], tn2.Z[n]);
     int k2 = 0, r2[4];
+#pragma unroll
     for (int n = 0; n < 4; ++n) {
         int rk = 0;
         bool on = false;
+#pragma unroll
         for (int o = 0; o < 4; ++o)
-            if (o != k) { on = on || g2[n] == gid[o]; rk += gid[o] < g2[n] ? 1 : 0; }
+            if (o != k) { on = on || h[n] == gid[o]; rk += gid[o] < h[n] ? 1 : 0; }
         if (!on) k2 = n;
         r2[n] = rk;
     }
     uint32_t sigs = 0u;
     int nsig = 0;
     for (int q2 = 0; q2 < to2.n; ++q2)
+#pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
+            uint32_t codes, fmask;
+            face_codes(to2.nodes, q2, s2, codes, fmask);
+            if (!((fmask >> k2) & 1u)) continue;  // not in the shared lattice face
             const uint32_t sg = face_sig(to2.nodes, q2, s2, k2, r2[0], r2[1], r2[2], r2[3]);
             if (sg && nsig < 4) { sigs |= sg << (8 * nsig); ++nsig; }
         }
     return sigs;
 }
 
-// Boundary sides of the pieces of lattice tet (c, t): bit 4 q + s.  `ci` = the cell's info word.
-static __device__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int t, uint16_t ci) {
+// Boundary sides of an UNTOUCHED lattice tet (c, t) (one piece): bit s.  Its four faces are whole lattice
+// faces: matched by an untouched neighbour, unmatched next to nothing.  *heavy is set (and 0 returned) when a
+// neighbour is trimmed: the caller queues the tet for tet_boundary_mask.
+__device__ __forceinline__ uint32_t whole_tet_mask(const Stuff& S, const Cell& c, int t, uint16_t ci, bool* heavy) {
+    uint32_t out = 0u;
+    *heavy = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        Cell c2;
+        int t2;
+        uint16_t ci2;
+        const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
+        if (st2 == TET_TRIM) *heavy = true;
+        else if (st2 == TET_NONE) out |= 1u << side_opposite(k);
+    }
+    return *heavy ? 0u : out;
+}
+
+// Boundary sides of the pieces of lattice tet (c, t), general procedure: bit 4 q + s.
+static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int t, uint16_t ci) {
     const Lattice& L = S.L;
     const int st = tet_state(ci, t);
     if (st == TET_NONE) return 0u;
     TetNodes tn;
     TetOut to;
-    if (st == TET_WHOLE) tet_coords(c, t, tn);
-    else trimmed_pieces(L, c, t, tn, to);
-    unsigned long long gid[4];
-    for (int n = 0; n < 4; ++n) gid[n] = pt_id(tet_X(tn, n), tet_Y(tn, n), tet_Z(tn, n));
-    uint32_t out = 0u;
     if (st == TET_WHOLE) {
-        // four whole lattice faces: each is matched by an untouched neighbour, unmatched next to nothing
-        for (int k = 0; k < 4; ++k) {
-            Cell c2;
-            int t2;
-            uint16_t ci2;
-            const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
-            if (st2 == TET_WHOLE) continue;
-            uint32_t cnt = 0u;
-            if (st2 == TET_TRIM) {
-                const uint32_t sigs = trimmed_sigs_on_face(L, c2, t2, gid, k);
-                for (int f = 0; f < 4; ++f) cnt += ((sigs >> (8 * f)) & 0xffu) == SIG_WHOLE_FACE ? 1u : 0u;
-            }
-            if ((cnt & 1u) == 0u && !(cnt != 0u && tet_after(c2, t2, c, t))) out |= 1u << side_opposite(k);
-        }
-        return out;
+        tet_coords(c, t, tn);
+        to.n = 1;
+        to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
+    } else {
+        trimmed_pieces(L, c, t, tn, to);
     }
     if (to.n == 0) return 0u;
-    uint32_t nb_sigs0 = 0u, nb_sigs1 = 0u, nb_sigs2 = 0u, nb_sigs3 = 0u;
-    uint32_t nb_state = 0u;  // bit k: neighbour across face k known; bit 4 + k: it comes later in the tet order
-    for (int q = 0; q < to.n; ++q) {
-        for (int s = 0; s < 4; ++s) {
-            // node-code set of this face, and the lattice faces all its nodes lie in
-            uint32_t codes = 0u, fmask = 0xfu;
-            for (int m = 0; m < 3; ++m) {
-                const int code = to.node(q, C_FACE[s][m]);
-                codes |= 1u << code;
-                fmask &= code < 4 ? ~(1u << code) : ~((1u << ((code - 4) >> 2)) | (1u << ((code - 4) & 3)));
+    unsigned long long gid[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) gid[n] = pt_id(tn.X[n], tn.Y[n], tn.Z[n]);
+    // the faces of the pieces: node-code sets and the lattice face each lies in
+    uint32_t fc[12], fm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        fc[i] = 0u; fm[i] = 0u;
+        if ((i >> 2) < to.n) face_codes(to.nodes, i >> 2, i & 3, fc[i], fm[i]);
+    }
+    // the other side of the four lattice faces, looked at only when a face of ours lies in it
+    uint32_t nb_sigs[4] = {0u, 0u, 0u, 0u};
+    bool nb_after[4] = {false, false, false, false};
+    uint32_t used = 0u;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) used |= fm[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!((used >> k) & 1u)) continue;
+        Cell c2;
+        int t2;
+        uint16_t ci2;
+        const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
+        if (st2 == TET_NONE) continue;
+        nb_after[k] = tet_after(c2, t2, c, t);
+        nb_sigs[k] = st2 == TET_WHOLE ? SIG_WHOLE_FACE : trimmed_sigs_on_face(L, c2, t2, gid[0], gid[1], gid[2], gid[3], k);
+    }
+    uint32_t out = 0u;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if ((i >> 2) >= to.n) continue;
+        uint32_t cnt = 0u;
+        bool last = true;
+        // ... occurrences among the other pieces of this lattice tet
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+            if (j != i && fc[j] == fc[i]) { ++cnt; if (j > i) last = false; }
+        // ... and among the pieces of the lattice tet across the lattice face it lies in
+        if (fm[i]) {
+            const int k = __ffs((int)fm[i]) - 1;
+            int r[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                int rk = 0;
+#pragma unroll
+                for (int o = 0; o < 4; ++o) rk += (o != k && o != n && gid[o] < gid[n]) ? 1 : 0;
+                r[n] = rk;
             }
-            uint32_t cnt = 0u;
-            bool last = true;
-            // ... among the other pieces of this lattice tet
-            for (int q2 = 0; q2 < to.n; ++q2)
-                for (int s2 = 0; s2 < 4; ++s2) {
-                    if (q2 == q && s2 == s) continue;
-                    uint32_t cd2 = 0u;
-                    for (int m = 0; m < 3; ++m) cd2 |= 1u << to.node(q2, C_FACE[s2][m]);
-                    if (cd2 == codes) { ++cnt; if (q2 > q || (q2 == q && s2 > s)) last = false; }
-                }
-            // ... and among the pieces of the lattice tet across the lattice face it lies in
-            fmask &= 0xfu;
-            if (fmask) {
-                const int k = __ffs((int)fmask) - 1;
-                int r[4];
-                for (int n = 0; n < 4; ++n) {
-                    int rk = 0;
-                    for (int o = 0; o < 4; ++o) rk += (o != k && o != n && gid[o] < gid[n]) ? 1 : 0;
-                    r[n] = rk;
-                }
-                const uint32_t mine = face_sig(to.nodes, q, s, k, r[0], r[1], r[2], r[3]);
-                if (!((nb_state >> k) & 1u)) {
-                    Cell c2;
-                    int t2;
-                    uint16_t ci2;
-                    const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
-                    uint32_t sg = 0u;
-                    if (st2 == TET_WHOLE) sg = SIG_WHOLE_FACE;
-                    else if (st2 == TET_TRIM) sg = trimmed_sigs_on_face(L, c2, t2, gid, k);
-                    if (k == 0) nb_sigs0 = sg; else if (k == 1) nb_sigs1 = sg; else if (k == 2) nb_sigs2 = sg; else nb_sigs3 = sg;
-                    nb_state |= (1u << k) | ((st2 != TET_NONE && tet_after(c2, t2, c, t)) ? 16u << k : 0u);
-                }
-                const uint32_t sigs = pick4(nb_sigs0, nb_sigs1, nb_sigs2, nb_sigs3, k);
-                const bool after = (nb_state >> (4 + k)) & 1u;
-                for (int f = 0; f < 4; ++f)
-                    if (mine != 0u && ((sigs >> (8 * f)) & 0xffu) == mine) { ++cnt; if (after) last = false; }
-            }
-            if ((cnt & 1u) == 0u && last) out |= 1u << (4 * q + s);
+            const uint32_t mine = face_sig(to.nodes, i >> 2, i & 3, k, r[0], r[1], r[2], r[3]);
+            const uint32_t sigs = pick4(nb_sigs[0], nb_sigs[1], nb_sigs[2], nb_sigs[3], k);
+            const bool after = pick4(nb_after[0], nb_after[1], nb_after[2], nb_after[3], k);
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if (mine != 0u && ((sigs >> (8 * f)) & 0xffu) == mine) { ++cnt; if (after) last = false; }
         }
+        if ((cnt & 1u) == 0u && last) out |= 1u << i;
     }
     return out;
 }
@@ -338,8 +369,8 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
                  unsigned long long* __restrict__ cursor, uint16_t* __restrict__ masks, unsigned long long* __restrict__ tile_tot) {
     __shared__ unsigned long long s_acc;
     __shared__ unsigned long long s_item;
-    __shared__ uint16_t s_ci[TILE_POINTS], s_list[TILE_POINTS];
-    __shared__ uint32_t s_n;
+    __shared__ uint16_t s_ci[TILE_POINTS], s_list[TILE_POINTS], s_heavy[8 * TILE_THREADS];
+    __shared__ uint32_t s_n, s_nheavy;
     const Lattice& L = S.L;
     for (;;) {
         __syncthreads();
@@ -380,11 +411,35 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         const uint32_t ncand = s_n;
         unsigned long long mine = 0ull;
         uint16_t* mt = masks + slot * (5ull * TILE_POINTS);
-        for (uint32_t w = threadIdx.x; w < 5u * ncand; w += TILE_THREADS) {
-            const uint32_t j = s_list[w / 5u], t = w % 5u;
-            const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
-            const uint32_t mask = tet_boundary_mask(S, c, (int)t, s_ci[j]);
-            if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+        // Two speeds: an untouched lattice tet whose neighbours are untouched / absent is settled from the
+        // info words alone; trimmed tets (and untouched ones next to a trimmed one) are queued and then
+        // processed densely, so that the expensive re-classification does not run in half-empty warps.
+        constexpr uint32_t CHUNK = 8u * TILE_THREADS;
+        for (uint32_t base = 0; base < 5u * ncand; base += CHUNK) {
+            if (threadIdx.x == 0) s_nheavy = 0u;
+            __syncthreads();
+            for (uint32_t w = base + threadIdx.x; w < min(base + CHUNK, 5u * ncand); w += TILE_THREADS) {
+                const uint32_t j = s_list[w / 5u], t = w % 5u;
+                const uint16_t ci = s_ci[j];
+                const int st = tet_state(ci, (int)t);
+                if (st == TET_NONE) continue;
+                bool heavy = st == TET_TRIM;
+                if (!heavy) {
+                    const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+                    const uint32_t mask = whole_tet_mask(S, c, (int)t, ci, &heavy);
+                    if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+                }
+                if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)(j | (t << 12));
+            }
+            __syncthreads();
+            const uint32_t nh = s_nheavy;
+            for (uint32_t w = threadIdx.x; w < nh; w += TILE_THREADS) {
+                const uint32_t j = s_heavy[w] & 0xfffu, t = s_heavy[w] >> 12;
+                const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
+                const uint32_t mask = tet_boundary_mask(S, c, (int)t, s_ci[j]);
+                if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+            }
+            __syncthreads();
         }
         const unsigned long long tot = block_sum(mine, &s_acc);
         if (threadIdx.x == 0) tile_tot[tile] = tot;

@@ -23,7 +23,7 @@ echo "ncu full rc=$?"
 ncu -i /tmp/${TAG}_hot.ncu-rep --page raw --csv > gpurun_out/${TAG}_hot_raw.csv 2>/dev/null
 ncu -i /tmp/${TAG}_hot.ncu-rep --page details --csv > gpurun_out/${TAG}_hot_details.csv 2>/dev/null
 for k in k_warp_codes k_classify_cells k_vertex_count k_vertex_emit k_tet_emit_full k_tet_emit k_sdf_field_tiled k_boundary_sides; do
-  ncu -i /tmp/${TAG}_hot.ncu-rep --page source --csv --kernel-name regex:"^(void )?(mc::)?$k[<(]" > gpurun_out/${TAG}_src_$k.csv 2>/dev/null
+  ncu -i /tmp/${TAG}_hot.ncu-rep --page source --csv --kernel-name regex:"^$k$" > gpurun_out/${TAG}_src_$k.csv 2>/dev/null
 done
 xz -T4 -f gpurun_out/${TAG}_hot_raw.csv gpurun_out/${TAG}_hot_details.csv gpurun_out/${TAG}_src_*.csv
 du -sh gpurun_out; ls -la gpurun_out | tail -30
