@@ -128,8 +128,9 @@ __device__ __forceinline__ void tet_coords(const Cell& c, int t, TetNodes& tn) {
 // by point id (the rank of node k is unused): both sides of the lattice face compute the same ranks.
 // A node becomes a 3-bit set of ranks (original node: one bit, cut vertex: the two ends of its edge),
 // the face the set of its three node sets (8 bits).
-static __device__ __noinline__ uint32_t face_sig(unsigned long long nodes, int q, int s, int k, int r0, int r1, int r2, int r3) {
+__device__ __forceinline__ uint32_t face_sig(unsigned long long nodes, int q, int s, int k, int r0, int r1, int r2, int r3) {
     uint32_t sig = 0u;
+#pragma unroll
     for (int m = 0; m < 3; ++m) {
         const int code = (int)((nodes >> (5 * (4 * q + C_FACE[s][m]))) & 31ull);
         uint32_t nm;
@@ -218,18 +219,28 @@ static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, c
     return sigs;
 }
 
-// Boundary sides of an UNTOUCHED lattice tet (c, t) (one piece): bit s.  Its four faces are whole lattice
-// faces: matched by an untouched neighbour, unmatched next to nothing.  *heavy is set (and 0 returned) when a
-// neighbour is trimmed: the caller queues the tet for tet_boundary_mask.
-__device__ __forceinline__ uint32_t whole_tet_mask(const Stuff& S, const Cell& c, int t, uint16_t ci, bool* heavy) {
+// info words of the six face-neighbour cells (-x, +x, -y, +y, -z, +z), 0 = nothing there
+struct NbInfo { uint16_t ci[6]; };
+__device__ __forceinline__ int nb_slot(int dx, int dy, int dz) { return dx ? (dx < 0 ? 0 : 1) : (dy ? (dy < 0 ? 2 : 3) : (dz < 0 ? 4 : 5)); }
+
+// Boundary sides of an UNTOUCHED lattice tet t (one piece) of a cell with mirroring class p and info word ci,
+// from the info words alone: bit s.  Its four faces are whole lattice faces: matched by an untouched
+// neighbour, unmatched next to nothing.  *heavy is set (and 0 returned) when a neighbour is trimmed: the
+// caller queues the tet for tet_boundary_mask.
+__device__ __forceinline__ uint32_t whole_tet_mask(uint32_t p, int t, uint16_t ci, const NbInfo& nb, bool* heavy) {
     uint32_t out = 0u;
     *heavy = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        Cell c2;
-        int t2;
-        uint16_t ci2;
-        const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
+        const uint32_t e = C_NB_TABLE[p][t][k];
+        const int t2 = (int)(e >> 6);
+        const int dx = (int)(e & 3u) - 1, dy = (int)((e >> 2) & 3u) - 1, dz = (int)((e >> 4) & 3u) - 1;
+        uint16_t ci2 = ci;
+        if ((dx | dy | dz) != 0) {
+            const int sl = nb_slot(dx, dy, dz);
+            ci2 = sl == 0 ? nb.ci[0] : (sl == 1 ? nb.ci[1] : (sl == 2 ? nb.ci[2] : (sl == 3 ? nb.ci[3] : (sl == 4 ? nb.ci[4] : nb.ci[5]))));
+        }
+        const int st2 = tet_state(ci2, t2);
         if (st2 == TET_TRIM) *heavy = true;
         else if (st2 == TET_NONE) out |= 1u << side_opposite(k);
     }
@@ -414,22 +425,34 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         // Two speeds: an untouched lattice tet whose neighbours are untouched / absent is settled from the
         // info words alone; trimmed tets (and untouched ones next to a trimmed one) are queued and then
         // processed densely, so that the expensive re-classification does not run in half-empty warps.
-        constexpr uint32_t CHUNK = 8u * TILE_THREADS;
-        for (uint32_t base = 0; base < 5u * ncand; base += CHUNK) {
+        constexpr uint32_t CHUNK = 8u * TILE_THREADS / 5u;  // cells per round: at most 8 * TILE_THREADS queued tets
+        for (uint32_t base = 0; base < ncand; base += CHUNK) {
             if (threadIdx.x == 0) s_nheavy = 0u;
             __syncthreads();
-            for (uint32_t w = base + threadIdx.x; w < min(base + CHUNK, 5u * ncand); w += TILE_THREADS) {
-                const uint32_t j = s_list[w / 5u], t = w % 5u;
+            for (uint32_t w = base + threadIdx.x; w < min(base + CHUNK, ncand); w += TILE_THREADS) {
+                const uint32_t j = s_list[w];
                 const uint16_t ci = s_ci[j];
-                const int st = tet_state(ci, (int)t);
-                if (st == TET_NONE) continue;
-                bool heavy = st == TET_TRIM;
-                if (!heavy) {
-                    const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
-                    const uint32_t mask = whole_tet_mask(S, c, (int)t, ci, &heavy);
-                    if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+                const int64_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
+                // the six neighbour cells once per cell (independent loads)
+                NbInfo nb;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    const int dx = f == 0 ? -1 : (f == 1 ? 1 : 0), dy = f == 2 ? -1 : (f == 3 ? 1 : 0), dz = f == 4 ? -1 : (f == 5 ? 1 : 0);
+                    nb.ci[f] = cell_info(S, cx + dx, cy + dy, cz + dz).ci;
                 }
-                if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)(j | (t << 12));
+                const uint32_t p = (uint32_t)(cx & 1) | ((uint32_t)(cy & 1) << 1) | ((uint32_t)(cz & 1) << 2);
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const int st = tet_state(ci, t);
+                    if (st == TET_NONE) continue;
+                    bool heavy = st == TET_TRIM;
+                    if (!heavy) {
+                        const uint32_t mask = whole_tet_mask(p, t, ci, nb, &heavy);
+                        if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
+                    }
+                    if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)(j | ((uint32_t)t << 12));
+                }
             }
             __syncthreads();
             const uint32_t nh = s_nheavy;
