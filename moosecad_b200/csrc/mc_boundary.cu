@@ -155,18 +155,19 @@ __device__ __forceinline__ bool tet_after(const Cell& a, int ta, const Cell& b, 
     return ta > tb;
 }
 
-// The lattice tet on the other side of lattice face k of (c, t): returns its state (TET_NONE also when
-// there is none: lattice border); c2 / t2 / ci2 describe it.
-__device__ __forceinline__ int neighbour_tet(const Stuff& S, const Cell& c, int t, uint16_t ci, int k, Cell& c2, int& t2, uint16_t& ci2) {
-    const uint32_t e = C_NB_TABLE[(c.fx ? 1 : 0) | (c.fy ? 2 : 0) | (c.fz ? 4 : 0)][t][k];
-    t2 = (int)(e >> 6);
+// The info words of a tile's cells with a one-cell halo are staged in shared memory (BH^3 entries,
+// 0 = nothing there / outside the lattice); `at` = index of the cell in that box.
+constexpr int BH = (int)TS + 2;
+// The lattice tet on the other side of lattice face k of tet t of the cell at `at` (mirroring class p):
+// returns its state (TET_NONE also when there is none: lattice border); *at2 / *t2 / *ci2 describe it.
+__device__ __forceinline__ int neighbour_tet(const uint16_t* __restrict__ s_cih, int at, uint32_t p, int t, int k, int* at2, int* t2,
+                                             uint16_t* ci2) {
+    const uint32_t e = C_NB_TABLE[p][t][k];
+    *t2 = (int)(e >> 6);
     const int dx = (int)(e & 3u) - 1, dy = (int)((e >> 2) & 3u) - 1, dz = (int)((e >> 4) & 3u) - 1;
-    if ((dx | dy | dz) == 0) { c2 = c; ci2 = ci; return tet_state(ci, t2); }
-    const CellInfo i2 = cell_info(S, (int64_t)c.cx + dx, (int64_t)c.cy + dy, (int64_t)c.cz + dz);  // (outside the lattice: nothing)
-    if (!i2.any) return TET_NONE;
-    c2 = make_cell(c.cx + dx, c.cy + dy, c.cz + dz);
-    ci2 = i2.ci;
-    return tet_state(ci2, t2);
+    *at2 = at + (dz * BH + dy) * BH + dx;
+    *ci2 = s_cih[*at2];
+    return tet_state(*ci2, *t2);
 }
 
 // node-code set (bit per code 0..19) of face (q, s) of a piece list, and the lattice faces (bit k =
@@ -219,28 +220,17 @@ static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, c
     return sigs;
 }
 
-// info words of the six face-neighbour cells (-x, +x, -y, +y, -z, +z), 0 = nothing there
-struct NbInfo { uint16_t ci[6]; };
-__device__ __forceinline__ int nb_slot(int dx, int dy, int dz) { return dx ? (dx < 0 ? 0 : 1) : (dy ? (dy < 0 ? 2 : 3) : (dz < 0 ? 4 : 5)); }
-
-// Boundary sides of an UNTOUCHED lattice tet t (one piece) of a cell with mirroring class p and info word ci,
-// from the info words alone: bit s.  Its four faces are whole lattice faces: matched by an untouched
-// neighbour, unmatched next to nothing.  *heavy is set (and 0 returned) when a neighbour is trimmed: the
-// caller queues the tet for tet_boundary_mask.
-__device__ __forceinline__ uint32_t whole_tet_mask(uint32_t p, int t, uint16_t ci, const NbInfo& nb, bool* heavy) {
+// Boundary sides of an UNTOUCHED lattice tet (one piece) from the info words alone: bit s.  Its four faces
+// are whole lattice faces: matched by an untouched neighbour, unmatched next to nothing.  *heavy is set (and
+// 0 returned) when a neighbour is trimmed: the caller queues the tet for tet_boundary_mask.
+__device__ __forceinline__ uint32_t whole_tet_mask(const uint16_t* __restrict__ s_cih, int at, uint32_t p, int t, bool* heavy) {
     uint32_t out = 0u;
     *heavy = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t e = C_NB_TABLE[p][t][k];
-        const int t2 = (int)(e >> 6);
-        const int dx = (int)(e & 3u) - 1, dy = (int)((e >> 2) & 3u) - 1, dz = (int)((e >> 4) & 3u) - 1;
-        uint16_t ci2 = ci;
-        if ((dx | dy | dz) != 0) {
-            const int sl = nb_slot(dx, dy, dz);
-            ci2 = sl == 0 ? nb.ci[0] : (sl == 1 ? nb.ci[1] : (sl == 2 ? nb.ci[2] : (sl == 3 ? nb.ci[3] : (sl == 4 ? nb.ci[4] : nb.ci[5]))));
-        }
-        const int st2 = tet_state(ci2, t2);
+        int at2, t2;
+        uint16_t ci2;
+        const int st2 = neighbour_tet(s_cih, at, p, t, k, &at2, &t2, &ci2);
         if (st2 == TET_TRIM) *heavy = true;
         else if (st2 == TET_NONE) out |= 1u << side_opposite(k);
     }
@@ -248,8 +238,10 @@ __device__ __forceinline__ uint32_t whole_tet_mask(uint32_t p, int t, uint16_t c
 }
 
 // Boundary sides of the pieces of lattice tet (c, t), general procedure: bit 4 q + s.
-static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const Cell& c, int t, uint16_t ci) {
+static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const uint16_t* __restrict__ s_cih, int at, const Cell& c, int t) {
     const Lattice& L = S.L;
+    const uint16_t ci = s_cih[at];
+    const uint32_t p = (c.fx ? 1u : 0u) | (c.fy ? 2u : 0u) | (c.fz ? 4u : 0u);
     const int st = tet_state(ci, t);
     if (st == TET_NONE) return 0u;
     TetNodes tn;
@@ -281,11 +273,13 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (!((used >> k) & 1u)) continue;
-        Cell c2;
-        int t2;
+        int at2, t2;
         uint16_t ci2;
-        const int st2 = neighbour_tet(S, c, t, ci, k, c2, t2, ci2);
+        const int st2 = neighbour_tet(s_cih, at, p, t, k, &at2, &t2, &ci2);
         if (st2 == TET_NONE) continue;
+        const int d = at2 - at;  // the neighbour cell relative to this one
+        const Cell c2 = make_cell(c.cx + (uint32_t)(d == 1 ? 1 : (d == -1 ? -1 : 0)), c.cy + (uint32_t)(d == BH ? 1 : (d == -BH ? -1 : 0)),
+                                  c.cz + (uint32_t)(d == BH * BH ? 1 : (d == -BH * BH ? -1 : 0)));
         nb_after[k] = tet_after(c2, t2, c, t);
         nb_sigs[k] = st2 == TET_WHOLE ? SIG_WHOLE_FACE : trimmed_sigs_on_face(L, c2, t2, gid[0], gid[1], gid[2], gid[3], k);
     }
@@ -380,7 +374,7 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
                  unsigned long long* __restrict__ cursor, uint16_t* __restrict__ masks, unsigned long long* __restrict__ tile_tot) {
     __shared__ unsigned long long s_acc;
     __shared__ unsigned long long s_item;
-    __shared__ uint16_t s_ci[TILE_POINTS], s_list[TILE_POINTS], s_heavy[8 * TILE_THREADS];
+    __shared__ uint16_t s_cih[BH * BH * BH], s_list[TILE_POINTS], s_heavy[8 * TILE_THREADS];
     __shared__ uint32_t s_n, s_nheavy;
     const Lattice& L = S.L;
     for (;;) {
@@ -390,32 +384,29 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         const unsigned long long slot = s_item;
         if (slot >= *n_list) break;
         const uint32_t tile = tile_list[slot];
-        uint32_t X0, Y0, Z0, zlo, zhi;
-        stage_cell_info(S, tile, s_ci, X0, Y0, Z0, zlo, zhi);
+        uint32_t X0, Y0, Z0;
+        tile_origin(S.g, tile, X0, Y0, Z0);
+        const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
         if (threadIdx.x == 0) s_n = 0u;
+        // info words of the tile's cells and of the cells around it
+        for (int idx = (int)threadIdx.x; idx < BH * BH * BH; idx += TILE_THREADS) {
+            const int lx = idx % BH - 1, ly = (idx / BH) % BH - 1, lz = idx / (BH * BH) - 1;
+            s_cih[idx] = cell_info(S, (int64_t)X0 + lx, (int64_t)Y0 + ly, (int64_t)Z0 + lz).ci;
+        }
         // this tile's masks start out empty
         uint4* mz = reinterpret_cast<uint4*>(masks + slot * (5ull * TILE_POINTS));
         for (uint32_t i = threadIdx.x; i < 5u * TILE_POINTS * 2u / 16u; i += TILE_THREADS) mz[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
+        // candidate cells: owned, emitting something, and not a full cell surrounded by full cells
         for (int rnd = 0; rnd < TILE_ROUNDS; ++rnd) {
             const uint32_t j = (uint32_t)rnd * TILE_THREADS + threadIdx.x;
-            const uint16_t ci = s_ci[j];
+            const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+            if (Z0 + lz < zlo || Z0 + lz >= zhi) continue;
+            const int at = (int)((lz + 1u) * BH + (ly + 1u)) * BH + (int)(lx + 1u);
+            const uint16_t ci = s_cih[at];
             if (ci_count(ci) == 0u) continue;
-            bool cand = !(ci & CI_FULL);
-            if (!cand) {
-                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-                const int64_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
-                // neighbours inside the tile (and owned) come from shared memory
-                auto full_at = [&](int dx, int dy, int dz) -> bool {
-                    const int x = (int)lx + dx, y = (int)ly + dy, z = (int)lz + dz;
-                    if (x >= 0 && y >= 0 && z >= 0 && x < (int)TS && y < (int)TS && z < (int)TS && cz + dz >= (int64_t)zlo &&
-                        cz + dz < (int64_t)zhi && cx + dx < (int64_t)L.nx && cy + dy < (int64_t)L.ny)
-                        return (s_ci[(z * (int)TS + y) * (int)TS + x] & CI_FULL) != 0;
-                    return cell_info(S, cx + dx, cy + dy, cz + dz).full;
-                };
-                cand = !(full_at(-1, 0, 0) && full_at(1, 0, 0) && full_at(0, -1, 0) && full_at(0, 1, 0) && full_at(0, 0, -1) &&
-                         full_at(0, 0, 1));
-            }
+            const bool cand = !(ci & CI_FULL) ||
+                              !(s_cih[at - 1] & s_cih[at + 1] & s_cih[at - BH] & s_cih[at + BH] & s_cih[at - BH * BH] & s_cih[at + BH * BH] & CI_FULL);
             if (cand) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
         }
         __syncthreads();
@@ -425,41 +416,32 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         // Two speeds: an untouched lattice tet whose neighbours are untouched / absent is settled from the
         // info words alone; trimmed tets (and untouched ones next to a trimmed one) are queued and then
         // processed densely, so that the expensive re-classification does not run in half-empty warps.
-        constexpr uint32_t CHUNK = 8u * TILE_THREADS / 5u;  // cells per round: at most 8 * TILE_THREADS queued tets
-        for (uint32_t base = 0; base < ncand; base += CHUNK) {
+        constexpr uint32_t CHUNK = 8u * TILE_THREADS;
+        for (uint32_t base = 0; base < 5u * ncand; base += CHUNK) {
             if (threadIdx.x == 0) s_nheavy = 0u;
             __syncthreads();
-            for (uint32_t w = base + threadIdx.x; w < min(base + CHUNK, ncand); w += TILE_THREADS) {
-                const uint32_t j = s_list[w];
-                const uint16_t ci = s_ci[j];
+            for (uint32_t w = base + threadIdx.x; w < min(base + CHUNK, 5u * ncand); w += TILE_THREADS) {
+                const uint32_t j = s_list[w / 5u], t = w % 5u;
                 const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-                const int64_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
-                // the six neighbour cells once per cell (independent loads)
-                NbInfo nb;
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    const int dx = f == 0 ? -1 : (f == 1 ? 1 : 0), dy = f == 2 ? -1 : (f == 3 ? 1 : 0), dz = f == 4 ? -1 : (f == 5 ? 1 : 0);
-                    nb.ci[f] = cell_info(S, cx + dx, cy + dy, cz + dz).ci;
+                const int at = (int)((lz + 1u) * BH + (ly + 1u)) * BH + (int)(lx + 1u);
+                const int st = tet_state(s_cih[at], (int)t);
+                if (st == TET_NONE) continue;
+                bool heavy = st == TET_TRIM;
+                if (!heavy) {
+                    const uint32_t p = ((X0 + lx) & 1u) | (((Y0 + ly) & 1u) << 1) | (((Z0 + lz) & 1u) << 2);
+                    const uint32_t mask = whole_tet_mask(s_cih, at, p, (int)t, &heavy);
+                    if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
                 }
-                const uint32_t p = (uint32_t)(cx & 1) | ((uint32_t)(cy & 1) << 1) | ((uint32_t)(cz & 1) << 2);
-#pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    const int st = tet_state(ci, t);
-                    if (st == TET_NONE) continue;
-                    bool heavy = st == TET_TRIM;
-                    if (!heavy) {
-                        const uint32_t mask = whole_tet_mask(p, t, ci, nb, &heavy);
-                        if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
-                    }
-                    if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)(j | ((uint32_t)t << 12));
-                }
+                if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)(j | (t << 12));
             }
             __syncthreads();
             const uint32_t nh = s_nheavy;
             for (uint32_t w = threadIdx.x; w < nh; w += TILE_THREADS) {
                 const uint32_t j = s_heavy[w] & 0xfffu, t = s_heavy[w] >> 12;
-                const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
-                const uint32_t mask = tet_boundary_mask(S, c, (int)t, s_ci[j]);
+                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+                const int at = (int)((lz + 1u) * BH + (ly + 1u)) * BH + (int)(lx + 1u);
+                const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
+                const uint32_t mask = tet_boundary_mask(S, s_cih, at, c, (int)t);
                 if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
             }
             __syncthreads();
