@@ -113,8 +113,9 @@ __device__ __forceinline__ int side_opposite(int k) { return k == 0 ? 3 : (k == 
 // the pieces of a TRIMMED lattice tet (node codes: 0..3 original node, 4 + 4 i + j cut on edge i-j); one
 // copy of the classification code per kernel
 static __device__ __noinline__ void trimmed_pieces(const Lattice& L, const Cell& c, int t, TetNodes& tn, TetOut& to) {
-    load_tet(L, c, t, tn);
-    classify_tet<false>(L, c, t, tn, nullptr, 0, to);  // emitted, hence not dropped by the exterior test
+    // trimmed: kept by cut_lattice with vertices on both sides of zero, and not dropped by the exterior test
+    load_tet_mixed(L, c, t, tn);
+    classify_tet<false, true>(L, c, t, tn, nullptr, 0, to);
 }
 
 // lattice coordinates of the (flipped) nodes of lattice tet (c, t), without touching the field

@@ -1391,9 +1391,18 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         uint64_t o = tb + s_off[j] + before;
         const Cell c = make_cell(X0 + (j & 15u), Y0 + ((j >> 4) & 15u), Z0 + (j >> 8));
         TetNodes tn;
-        load_tet(L, c, t, tn);
         TetOut to;
-        classify_tet<false>(L, c, t, tn, nullptr, 0, to);  // nt != 0: not dropped by the exterior test
+        if ((ci >> (CI_UNTOUCHED_SHIFT + t)) & 1u) {
+            // untouched: the lattice tet itself, no need to look at the field
+#pragma unroll
+            for (int m = 0; m < 4; ++m) corner_xyz(c, tet_corner(c, t, m), tn.X[m], tn.Y[m], tn.Z[m]);
+            to.n = 1; to.kase = -1; to.ext_removed = false;
+            to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
+        } else {
+            // trimmed (nt != 0, so kept and not dropped by the exterior test): vertices on both sides of zero
+            load_tet_mixed(L, c, t, tn);
+            classify_tet<false, true>(L, c, t, tn, nullptr, 0, to);
+        }
         int li[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);

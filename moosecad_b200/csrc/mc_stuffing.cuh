@@ -136,15 +136,27 @@ __device__ __forceinline__ void load_tet(const Lattice& L, const Cell& c, int t,
     }
 }
 
+// the same for a tet that is known to have a vertex of each side of zero (a trimmed tet): none of its
+// vertices lies in a proven tile, the stored values are read directly
+__device__ __forceinline__ void load_tet_mixed(const Lattice& L, const Cell& c, int t, TetNodes& tn) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        corner_xyz(c, tet_corner(c, t, n), tn.X[n], tn.Y[n], tn.Z[n]);
+        const size_t i = pidx(L, tn.X[n], tn.Y[n], tn.Z[n]);
+        tn.p[n] = (L.wcode[i] & 0x7f) ? 0.0 : L.phi[i];
+    }
+}
+
 // `removed_hint`: < 0 -> evaluate the exterior test with the SDF program; 0/1 -> cached result
-template <bool CAN_EVAL>
+// KNOWN_KEPT: the caller knows that cut_lattice kept the tet (it produced output)
+template <bool CAN_EVAL, bool KNOWN_KEPT = false>
 __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNodes& tn,
                              const uint64_t* __restrict__ prog, int removed_hint, TetOut& out) {
     out.n = 0;
     out.kase = -2;
     out.ext_removed = false;
     out.nodes = 0ull;
-    if (!tet_kept(L, c, t)) return;
+    if (!KNOWN_KEPT && !tet_kept(L, c, t)) return;
     const double* p = tn.p;
     if (p[0] <= 0.0 && p[1] <= 0.0 && p[2] <= 0.0 && p[3] <= 0.0) {
         out.kase = -1;
