@@ -268,6 +268,8 @@ def main():
             side_counts["boundary"], side_counts["sets"] = boundary_and_sidesets(h, bnds)
             sm.host_ms["boundary_sidesets"] = (time.perf_counter() - t0) * 1e3
             host_ms.update(sm.host_ms)
+            host_ms["slab"] = list(sm.slabs[rank])
+            slabs.report_device_time(sm, sum(stage_ms(h)))   # measured-load refinement of the slabs (first runs only)
             return h
 
         def stage_ms(h):

@@ -199,6 +199,18 @@ def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=No
 
 
 _partition_cache = {}
+FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "6"))   # 0 disables the measured-load refinement
+
+
+class _Partition:
+    """Cache entry of one (scene, resolution, world): the slabs in use, the per-layer cost estimate they
+    came from, this rank's device time of the last run with them (reported by the caller) and the
+    number of measured-load refinements applied so far."""
+
+    def __init__(self, costs, slabs):
+        self.costs, self.slabs = list(costs), slabs
+        self.my_last_us = 0       # device time of this rank's last run with `slabs` (microseconds, 0 = unknown)
+        self.rounds = 0
 
 
 def cached_partition(ctx, obj, resolution, rank, world, group=None, device=None, host_group=None):
@@ -208,11 +220,36 @@ def cached_partition(ctx, obj, resolution, rank, world, group=None, device=None,
     the same order (the first call for a key runs one collective)."""
     res = float(resolution)
     key = (obj.backend.program_hash(obj.node, res), res, int(world))
-    slabs = _partition_cache.get(key)
-    if slabs is None:
-        slabs = partition_balanced(layer_costs_sharded(ctx, obj, res, rank, world, group, device, host_group), world)
-        _partition_cache[key] = slabs
-    return slabs
+    ent = _partition_cache.get(key)
+    if ent is None:
+        costs = layer_costs_sharded(ctx, obj, res, rank, world, group, device, host_group)
+        ent = _Partition(costs, partition_balanced(costs, world))
+        _partition_cache[key] = ent
+    return ent
+
+
+def refine_partition(ent, times_us):
+    """Measured-load refinement: the cost estimate of every slab is rescaled so that it sums to the
+    device time its rank just measured, and the lattice is cut again.  Deterministic in its inputs
+    (every rank holds the same times after the all-gather), applied a few times only
+    (FEEDBACK_ROUNDS), skipped when a time is missing or the slabs are already within 1.5 %."""
+    if ent.rounds >= FEEDBACK_ROUNDS or any(t <= 0 for t in times_us):
+        return False
+    mean = sum(times_us) / len(times_us)
+    if max(times_us) <= 1.015 * mean:
+        ent.rounds = FEEDBACK_ROUNDS
+        return False
+    costs = list(ent.costs)
+    for (z0, z1), t in zip(ent.slabs, times_us):
+        est = sum(costs[z0:z1])
+        if est > 0.0:
+            f = t / est
+            for z in range(z0, z1):
+                costs[z] *= f
+    ent.costs = costs
+    ent.slabs = partition_balanced(costs, len(times_us))
+    ent.rounds += 1
+    return True
 
 
 def _ctx_stream(ctx, device):
@@ -248,8 +285,10 @@ class SlabMesher:
         if self.world > 1 and balanced:
             # the estimate is deterministic, every rank derives the same partition; it is computed
             # once per (scene, resolution, world) and cached
-            self.slabs = cached_partition(ctx, obj, self.res, self.rank, self.world, group, device, host_group)
+            self._part = cached_partition(ctx, obj, self.res, self.rank, self.world, group, device, host_group)
+            self.slabs = self._part.slabs
         else:
+            self._part = None
             self.slabs = partition(self.dim[2], self.world)
         self.host_ms["partition"] = (time.perf_counter() - t0) * 1e3
         if any(z1 == z0 for z0, z1 in self.slabs):
@@ -281,7 +320,8 @@ class SlabMesher:
             _lib.check(lib.mc_mesh_counts(out, counts))
             top_first, top_count = C.c_uint64(), C.c_uint64()
             _lib.check(lib.mc_mesh_upper_layer_vertices(out, C.byref(top_first), C.byref(top_count)))
-            extra = (top_first.value, top_count.value)
+            # (+ this rank's device time of the previous run with the same slabs: measured-load refinement)
+            extra = (top_first.value, top_count.value, self._part.my_last_us if self._part is not None else 0)
             if self.world > 1 and self.host_group is None:
                 # device group: the stream is idle right after phase 1, the tiny all-gather is not
                 # queued behind anything
@@ -294,6 +334,10 @@ class SlabMesher:
             elif self.world == 1:
                 self.all_counts = [(counts[0], counts[1]) + extra]
             self.vertex_base, self.tet_base = bases_from_counts(self.all_counts, self.rank)
+            if self._part is not None and self.world > 1:
+                # the next run of this scene uses slabs refined with the times every rank just shared
+                if refine_partition(self._part, [int(c[4]) for c in self.all_counts]):
+                    self._part.my_last_us = 0
             lap("exchange_counts")
             _lib.check(lib.mc_tessellate_emit_vertices(out, self.vertex_base))
             lap("emit_vertices_launch")
@@ -337,6 +381,15 @@ class SlabMesher:
             lib.mc_mesh_free(out)
             raise
         return out
+
+
+def report_device_time(sm, device_ms):
+    """Tell the partition cache how long this rank's device worked on its slab in the run `sm` just did
+    (meshing + whatever the caller ran on the slab afterwards, e.g. Mesh::boundary): the next runs of
+    the same scene rebalance the slabs with it (refine_partition)."""
+    part = getattr(sm, "_part", None)
+    if part is not None and part.slabs == sm.slabs:
+        part.my_last_us = max(1, int(device_ms * 1000.0))
 
 
 def tessellate_multi(ctxs, obj, resolution, relative_error, flags=0):

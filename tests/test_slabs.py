@@ -221,3 +221,25 @@ def test_tessellate_multi_single_process(n_slabs, scene, ctx):
     finally:
         for h in handles:
             lib.mc_mesh_free(h)
+
+
+def test_measured_load_refinement_converges():
+    """refine_partition: slabs cut from a wrong cost estimate, rebalanced with the times the ranks measure."""
+    rng = np.random.default_rng(1)
+    n, world = 1024, 8
+    true = 0.2 + np.abs(np.sin(np.arange(n) / 90.0)) + 0.5 * rng.random(n)      # what a layer really costs
+    est = list(1.0 + 0.0 * true)                                                  # a flat (wrong) estimate
+    ent = slabs._Partition(est, slabs.partition_balanced(est, world))
+    def times(sl):
+        return [int(1e3 * true[a:b].sum()) for a, b in sl]
+    t0 = times(ent.slabs)
+    for _ in range(slabs.FEEDBACK_ROUNDS + 2):
+        slabs.refine_partition(ent, times(ent.slabs))
+    t1 = times(ent.slabs)
+    assert ent.rounds <= slabs.FEEDBACK_ROUNDS
+    assert ent.slabs[0][0] == 0 and ent.slabs[-1][1] == n and all(a[1] == b[0] for a, b in zip(ent.slabs, ent.slabs[1:]))
+    assert max(t1) / (sum(t1) / world) < 1.03 < max(t0) / (sum(t0) / world)
+    # a missing time (a rank that has not reported yet) changes nothing
+    before = list(ent.slabs)
+    ent.rounds = 0
+    assert not slabs.refine_partition(ent, [0] + times(ent.slabs)[1:]) and ent.slabs == before
