@@ -185,13 +185,36 @@ __device__ __forceinline__ void face_codes(unsigned long long nodes, int q, int 
     fmask &= 0xfu;
 }
 
+// what a block knows about the tile it works on
+struct TileView {
+    const uint16_t* cih;    // info words of the tile's cells with a one-cell halo (BH^3)
+    const uint16_t* soff;   // surface-cell number of the tile's owned cells (piece cache), TS^3
+    unsigned long long sbase;
+    uint32_t X0, Y0, Z0, zlo, zhi;
+    bool cached;            // the piece cache holds this tile's trimmed tets
+};
+
+// the pieces of TRIMMED tet t of cell c: from the cache k_tet_emit filled (owned cells of this tile) or by
+// classifying it again; tn receives the node coordinates (and, on the second path, the values)
+__device__ __forceinline__ void pieces_of_trimmed(const Stuff& S, const TileView& V, const Cell& c, int t, TetNodes& tn, TetOut& to) {
+    const uint32_t lx = c.cx - V.X0, ly = c.cy - V.Y0, lz = c.cz - V.Z0;   // (wraps for cells before the tile)
+    if (V.cached && lx < TS && ly < TS && lz < TS && c.cz >= V.zlo && c.cz < V.zhi) {
+        const unsigned long long e = S.pieces[5ull * (V.sbase + V.soff[(lz * TS + ly) * TS + lx]) + (unsigned)t];
+        tet_coords(c, t, tn);
+        to.nodes = e & 0x0fffffffffffffffull;
+        to.n = (int)(e >> 60);
+        return;
+    }
+    trimmed_pieces(S.L, c, t, tn, to);
+}
+
 // signatures (up to four, 8 bits each) of the faces that the pieces of TRIMMED tet (c2, t2) have in the
 // lattice face whose three points are the nodes != k of (gid[0..3])
-static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Lattice& L, const Cell& c2, int t2, unsigned long long g0,
+static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Stuff& S, const TileView& V, const Cell& c2, int t2, unsigned long long g0,
                                                              unsigned long long g1, unsigned long long g2_, unsigned long long g3, int k) {
     TetNodes tn2;
     TetOut to2;
-    trimmed_pieces(L, c2, t2, tn2, to2);
+    pieces_of_trimmed(S, V, c2, t2, tn2, to2);
     const unsigned long long gid[4] = {g0, g1, g2_, g3};
     unsigned long long h[4];
 #pragma unroll
@@ -239,8 +262,8 @@ __device__ __forceinline__ uint32_t whole_tet_mask(const uint16_t* __restrict__ 
 }
 
 // Boundary sides of the pieces of lattice tet (c, t), general procedure: bit 4 q + s.
-static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const uint16_t* __restrict__ s_cih, int at, const Cell& c, int t) {
-    const Lattice& L = S.L;
+static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const TileView& V, int at, const Cell& c, int t) {
+    const uint16_t* __restrict__ s_cih = V.cih;
     const uint16_t ci = s_cih[at];
     const uint32_t p = (c.fx ? 1u : 0u) | (c.fy ? 2u : 0u) | (c.fz ? 4u : 0u);
     const int st = tet_state(ci, t);
@@ -252,7 +275,7 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
         to.n = 1;
         to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
     } else {
-        trimmed_pieces(L, c, t, tn, to);
+        pieces_of_trimmed(S, V, c, t, tn, to);
     }
     if (to.n == 0) return 0u;
     unsigned long long gid[4];
@@ -282,7 +305,7 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
         const Cell c2 = make_cell(c.cx + (uint32_t)(d == 1 ? 1 : (d == -1 ? -1 : 0)), c.cy + (uint32_t)(d == BH ? 1 : (d == -BH ? -1 : 0)),
                                   c.cz + (uint32_t)(d == BH * BH ? 1 : (d == -BH * BH ? -1 : 0)));
         nb_after[k] = tet_after(c2, t2, c, t);
-        nb_sigs[k] = st2 == TET_WHOLE ? SIG_WHOLE_FACE : trimmed_sigs_on_face(L, c2, t2, gid[0], gid[1], gid[2], gid[3], k);
+        nb_sigs[k] = st2 == TET_WHOLE ? SIG_WHOLE_FACE : trimmed_sigs_on_face(S, V, c2, t2, gid[0], gid[1], gid[2], gid[3], k);
     }
     uint32_t out = 0u;
 #pragma unroll
@@ -375,8 +398,9 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
                  unsigned long long* __restrict__ cursor, uint16_t* __restrict__ masks, unsigned long long* __restrict__ tile_tot) {
     __shared__ unsigned long long s_acc;
     __shared__ unsigned long long s_item;
-    __shared__ uint16_t s_cih[BH * BH * BH], s_list[TILE_POINTS], s_heavy[8 * TILE_THREADS];
+    __shared__ uint16_t s_cih[BH * BH * BH], s_list[TILE_POINTS], s_heavy[8 * TILE_THREADS], s_soff[TILE_POINTS];
     __shared__ uint32_t s_n, s_nheavy;
+    __shared__ uint32_t s_scan[9];
     const Lattice& L = S.L;
     for (;;) {
         __syncthreads();
@@ -397,6 +421,28 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         // this tile's masks start out empty
         uint4* mz = reinterpret_cast<uint4*>(masks + slot * (5ull * TILE_POINTS));
         for (uint32_t i = threadIdx.x; i < 5u * TILE_POINTS * 2u / 16u; i += TILE_THREADS) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        // surface-cell numbers of the piece cache: the owned cells that are not full, in emission order
+        // (x-rows of cells, like k_tet_emit)
+        {
+            const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+            const bool row_owned = Y0 + ly < L.ny && Z0 + lz >= zlo && Z0 + lz < zhi;
+            uint32_t surf = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < TS; ++i) {
+                const uint16_t ci = s_cih[(int)((lz + 1u) * BH + (ly + 1u)) * BH + (int)(i + 1u)];
+                s_soff[threadIdx.x * TS + i] = (uint16_t)surf;
+                if (row_owned && X0 + i < L.nx && ci_count(ci) != 0u && !(ci & CI_FULL)) ++surf;
+            }
+            uint32_t stot;
+            const uint32_t sex = block_exscan(surf, &stot, s_scan);
+#pragma unroll
+            for (uint32_t i = 0; i < TS; ++i) s_soff[threadIdx.x * TS + i] = (uint16_t)(s_soff[threadIdx.x * TS + i] + sex);
+        }
+        TileView V;
+        V.cih = s_cih; V.soff = s_soff; V.X0 = X0; V.Y0 = Y0; V.Z0 = Z0; V.zlo = zlo; V.zhi = zhi;
+        V.cached = S.pieces != nullptr && S.cuni[tile] == CU_ACTIVE;
+        V.sbase = V.cached ? S.tile_sbase[tile] : 0ull;
         __syncthreads();
         // candidate cells: owned, emitting something, and not a full cell surrounded by full cells
         for (int rnd = 0; rnd < TILE_ROUNDS; ++rnd) {
@@ -442,7 +488,7 @@ k_boundary_masks(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
                 const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
                 const int at = (int)((lz + 1u) * BH + (ly + 1u)) * BH + (int)(lx + 1u);
                 const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
-                const uint32_t mask = tet_boundary_mask(S, s_cih, at, c, (int)t);
+                const uint32_t mask = tet_boundary_mask(S, V, at, c, (int)t);
                 if (mask) { mt[t * TILE_POINTS + j] = (uint16_t)mask; mine += (unsigned long long)__popc(mask); }
             }
             __syncthreads();

@@ -80,7 +80,8 @@ struct mc_mesh {
     uint64_t n_tiles = 0;
     double avg_pruned_words = 0;
 
-    uint64_t counters[32] = {0};
+    uint64_t counters[40] = {0};
+    mc::DevBuf d_pieces, d_tile_sbase;  // piece cache of the surface cells for Mesh::boundary (k_tet_emit writes it)
     uint64_t n_verts = 0, n_cuts = 0, n_tets = 0, n_kept = 0;
     uint64_t points_evaluated = 0, points_owned = 0;
     uint64_t vertex_base = 0, tet_base = 0;

@@ -22,7 +22,7 @@ namespace mc {
 enum Counter : int {
     CN_VERTS = 0, CN_CUTS, CN_TETS, CN_KEPT, CN_STAT0, /* ..CN_STAT0+6 */
     CN_WARPED = CN_STAT0 + 7, CN_EXT_REMOVED, CN_BISECT_FAIL, CN_BISECT_ITERS, CN_INVERTED,
-    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_SDF_LIST, CN_SDF_NEXT, CN_LIST_VNEG, CN_LIST_CFULL, CN_COUNT
+    CN_AR_MIN_BITS, CN_AR_MAX_BITS, CN_PRUNED_WORDS, CN_ACTIVE_VTILES, CN_ACTIVE_CTILES, CN_SKIPPED_TILES, CN_LISTED_TETS, CN_QLIST_FILL, CN_SDF_FLOPS, CN_SUB_BOXES_PROVEN, CN_CLASS_INVERTED, CN_SDF_LIST, CN_SDF_NEXT, CN_LIST_VNEG, CN_LIST_CFULL, CN_SURF_CELLS, CN_SURF_FILL, CN_COUNT
 };
 
 constexpr int TILE_THREADS = 256;
@@ -93,6 +93,11 @@ struct Stuff {
     uint16_t* vmask;      // [points] VM_*
     uint16_t* vloc;       // [points] offset of the vertex's first output inside its tile
     uint16_t* cinfo;      // [cells of classified layers] CI_*
+    // Piece cache written by k_tet_emit and read by Mesh::boundary (mc_boundary.cu): the owned cells of
+    // a tile that are not full ("surface cells") are numbered in emission order from tile_sbase[tile];
+    // pieces[5 * (that number) + t] = TetOut::nodes | n << 60 of lattice tet t (0 when nothing came out)
+    unsigned long long* pieces;
+    unsigned long long* tile_sbase;
     const unsigned long long* warp_table;  // visit-order table of warp_vertices, see build_warp_table
     const unsigned long long* tvbase;  // [tiles] first output vertex of the tile (slab-local)
     const unsigned long long* ttbase;  // [tiles] first output tet of the tile (slab-local)
@@ -538,7 +543,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
         s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0)) : (uint8_t)0;
     });
     __syncthreads();
-    uint32_t my_out = 0, my_kept = 0, my_listed = 0;
+    uint32_t my_out = 0, my_kept = 0, my_listed = 0, my_surf = 0;
     for (int r = 0; r < TILE_ROUNDS; ++r) {
         const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
@@ -602,14 +607,20 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             // (on a FULL cell bit 10 doubles as CI_FULL_ZERO_CORNER: all five untouched bits are set anyway)
             if (untouched_bits == 31u && ci_count(ci) == 5u) ci |= (uint16_t)(CI_FULL | CI_FULL_ZERO_CORNER);
             S.cinfo[cidx(S, cx, cy, cz)] = ci;
-            if (cz >= S.c0 && cz < S.c1) { my_out += ci_count(ci); my_kept += kept; my_listed += ci_count(ci); }
+            if (cz >= S.c0 && cz < S.c1) {
+                my_out += ci_count(ci); my_kept += kept; my_listed += ci_count(ci);
+                if (ci_count(ci) != 0u && !(ci & CI_FULL)) ++my_surf;
+            }
         }
         __syncthreads();
     }
     const unsigned long long tot = block_sum((unsigned long long)my_out | ((unsigned long long)my_kept << 32), &s_acc);
     if (threadIdx.x == 0) tile_tot[tile] = tot;
-    const unsigned long long listed = block_sum((unsigned long long)my_listed, &s_acc);
-    if (threadIdx.x == 0 && listed) atomicAdd(&counters[CN_LISTED_TETS], listed);
+    const unsigned long long listed = block_sum((unsigned long long)my_listed | ((unsigned long long)my_surf << 32), &s_acc);
+    if (threadIdx.x == 0 && listed) {
+        if (listed & 0xffffffffull) atomicAdd(&counters[CN_LISTED_TETS], listed & 0xffffffffull);
+        if (listed >> 32) atomicAdd(&counters[CN_SURF_CELLS], listed >> 32);
+    }
     // the statistics leave the block as at most 8 global atomics
     if (threadIdx.x < 8 && s_stat[threadIdx.x])
         atomicAdd(&counters[threadIdx.x < 7 ? CN_STAT0 + (int)threadIdx.x : (int)CN_EXT_REMOVED], (unsigned long long)s_stat[threadIdx.x]);
@@ -1238,7 +1249,7 @@ constexpr int TE_NP = TE_H * TE_H * TE_H;
 template <typename IndexT>
 constexpr size_t tet_emit_smem_bytes() {
     return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + 15 +
-           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, qoff*/;
+           (size_t)TILE_POINTS * 2 * 5 /*ci, off, list, qoff, soff*/;
 }
 
 // one output tet = one (u32 ids) or two (u64 ids) 16-byte stores
@@ -1272,7 +1283,8 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
     uint16_t* s_qoff = s_list + TILE_POINTS; // first quality-list slot of the cell, relative to the tile
-    __shared__ unsigned long long s_qbase;
+    uint16_t* s_soff = s_qoff + TILE_POINTS; // number of surface (not full) cells before the cell in the tile
+    __shared__ unsigned long long s_qbase, s_sbase;
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[tile];
     if (threadIdx.x == 0) s_n = 0u;
@@ -1328,7 +1340,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
         const uint16_t* __restrict__ row = S.cinfo + (row_owned ? cidx(S, X0, cy, cz) : 0);
         const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
-        uint32_t acc = 0;
+        uint32_t acc = 0, surf = 0;
         uint32_t pre[TS];
 #pragma unroll
         for (uint32_t i = 0; i < TS; ++i) {
@@ -1338,7 +1350,8 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             s_ci[threadIdx.x * TS + i] = ci;
             pre[i] = acc;
             acc += count | (listed ? count << 16 : 0u);
-            if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)(threadIdx.x * TS + i);
+            s_soff[threadIdx.x * TS + i] = (uint16_t)surf;   // (inside the row for now)
+            if (count && !(ci & CI_FULL)) { s_list[atomicAdd(&s_n, 1u)] = (uint16_t)(threadIdx.x * TS + i); ++surf; }
         }
         uint32_t tot;
         const uint32_t ex = block_exscan(acc, &tot, s_scan);
@@ -1349,6 +1362,15 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             if (QUALITY) s_qoff[threadIdx.x * TS + i] = (uint16_t)(v >> 16);
         }
         if (QUALITY && threadIdx.x == 0) s_qbase = (tot >> 16) ? atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)(tot >> 16)) : 0ull;
+        // surface-cell numbering of the piece cache
+        uint32_t stot;
+        const uint32_t sex = block_exscan(surf, &stot, s_scan);
+#pragma unroll
+        for (uint32_t i = 0; i < TS; ++i) s_soff[threadIdx.x * TS + i] = (uint16_t)(s_soff[threadIdx.x * TS + i] + sex);
+        if (threadIdx.x == 0) {
+            s_sbase = stot ? atomicAdd(&counters[CN_SURF_FILL], (unsigned long long)stot) : 0ull;
+            if (S.tile_sbase) S.tile_sbase[tile] = s_sbase;
+        }
     }
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
@@ -1402,6 +1424,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             // trimmed (nt != 0, so kept and not dropped by the exterior test): vertices on both sides of zero
             load_tet_mixed(L, c, t, tn);
             classify_tet<false, true>(L, c, t, tn, nullptr, 0, to);
+            if (S.pieces) S.pieces[5ull * (s_sbase + s_soff[j]) + (unsigned)t] = to.nodes | ((unsigned long long)to.n << 60);
         }
         int li[4];
 #pragma unroll

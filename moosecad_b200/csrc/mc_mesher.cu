@@ -13,7 +13,7 @@
 
 using namespace mc;
 
-static_assert(CN_COUNT <= 32, "mc_mesh::counters holds 32 entries");
+static_assert(CN_COUNT <= 40, "mc_mesh::counters holds 40 entries, the device slots above are work cursors");
 // d_counters has 64 slots: the upper ones are the work cursors of the list kernels, one per launch site
 enum Cursor : int { CUR_WARP = 40, CUR_CLASSIFY, CUR_VCOUNT, CUR_VEMIT_INT, CUR_VEMIT, CUR_BISECT, CUR_TET_FULL, CUR_TET_SURF };
 
@@ -189,6 +189,8 @@ static void mesh_release_all(mc_mesh* m) {
     for (DevBuf* b : bufs) c->release(*b);
     c->release(m->d_side_flag);
     c->release(m->d_side_nodes);
+    c->release(m->d_pieces);
+    c->release(m->d_tile_sbase);
     c->release(m->own_lower_table);
     c->release(m->own_lower_coords);
     for (auto& ss : m->sidesets) c->release(ss.d_pairs);
@@ -311,6 +313,8 @@ Stuff make_stuff(const mc_mesh* m) {
     S.tvbase = (const unsigned long long*)m->d_vtile_vbase.p;
     S.ttbase = (const unsigned long long*)m->d_ttile_base.p;
     S.lower_table = (const unsigned long long*)m->lower_table;
+    S.pieces = (unsigned long long*)m->d_pieces.p;
+    S.tile_sbase = (unsigned long long*)m->d_tile_sbase.p;
     S.warp_table = (const unsigned long long*)m->ctx->d_warp_table.p;
     S.vertex_base = (long long)m->vertex_base;
     return S;
@@ -891,6 +895,12 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     m->index_bytes = (m->vertex_base + m->n_verts < (1ull << 32)) ? 4 : 8;
     int rc = c->alloc(std::max<uint64_t>(m->n_tets, 1) * 4 * (size_t)m->index_bytes, m->d_tets);
     if (rc != MC_OK) return rc;
+    // piece cache for Mesh::boundary: 5 words per owned surface cell (counted by the classification)
+    if (!(m->flags & MC_OPT_NO_BOUNDARY_CACHE) && m->counters[CN_SURF_CELLS] > 0) {
+        rc = c->alloc(m->counters[CN_SURF_CELLS] * 40, m->d_pieces);
+        if (rc == MC_OK) rc = c->alloc((m->n_tiles + 1) * 8, m->d_tile_sbase);
+        if (rc != MC_OK) return rc;
+    }
     const Stuff S = make_stuff(m);
     const bool quality = !(m->flags & MC_OPT_SKIP_QUALITY);
     if (!c->tet_emit_attr_set) {
