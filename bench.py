@@ -268,7 +268,7 @@ def main():
             side_counts["boundary"], side_counts["sets"] = boundary_and_sidesets(h, bnds)
             sm.host_ms["boundary_sidesets"] = (time.perf_counter() - t0) * 1e3
             host_ms.update(sm.host_ms)
-            host_ms["slab"] = list(sm.slabs[rank])
+            side_counts["slab"] = list(sm.slabs[rank])
             slabs.report_device_time(sm, sum(stage_ms(h)))   # measured-load refinement of the slabs (first runs only)
             return h
 
@@ -339,7 +339,8 @@ def main():
         stage_avg = [a / steps for a in stage_acc]
         # diagnostics (outside the timed region): every rank's own device time and host phases
         mine = {"rank": rank, "device_stage_ms_sum": round(sum(stage_avg), 3),
-                "host_ms_last_step": {k: round(v, 3) for k, v in host_ms.items()}, "host_wall_ms_per_step": step_wall}
+                "host_ms_last_step": {k: round(v, 3) for k, v in host_ms.items()}, "host_wall_ms_per_step": step_wall,
+                "slab_cell_layers": side_counts.get("slab")}
         per_rank = [mine]
         if world > 1:
             per_rank = [None] * world
