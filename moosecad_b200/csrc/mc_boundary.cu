@@ -129,9 +129,8 @@ __device__ __forceinline__ void tet_coords(const Cell& c, int t, TetNodes& tn) {
 // by point id (the rank of node k is unused): both sides of the lattice face compute the same ranks.
 // A node becomes a 3-bit set of ranks (original node: one bit, cut vertex: the two ends of its edge),
 // the face the set of its three node sets (8 bits).
-__device__ __forceinline__ uint32_t face_sig(unsigned long long nodes, int q, int s, int k, int r0, int r1, int r2, int r3) {
+static __device__ __noinline__ uint32_t face_sig(unsigned long long nodes, int q, int s, int k, int r0, int r1, int r2, int r3) {
     uint32_t sig = 0u;
-#pragma unroll
     for (int m = 0; m < 3; ++m) {
         const int code = (int)((nodes >> (5 * (4 * q + C_FACE[s][m]))) & 31ull);
         uint32_t nm;
@@ -173,10 +172,9 @@ __device__ __forceinline__ int neighbour_tet(const uint16_t* __restrict__ s_cih,
 
 // node-code set (bit per code 0..19) of face (q, s) of a piece list, and the lattice faces (bit k =
 // face opposite node k) every node of it lies in
-__device__ __forceinline__ void face_codes(unsigned long long nodes, int q, int s, uint32_t& codes, uint32_t& fmask) {
+static __device__ __noinline__ void face_codes(unsigned long long nodes, int q, int s, uint32_t& codes, uint32_t& fmask) {
     codes = 0u;
     fmask = 0xfu;
-#pragma unroll
     for (int m = 0; m < 3; ++m) {
         const int code = (int)((nodes >> (5 * (4 * q + C_FACE[s][m]))) & 31ull);
         codes |= 1u << code;
@@ -217,14 +215,11 @@ static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Stuff& S, con
     pieces_of_trimmed(S, V, c2, t2, tn2, to2);
     const unsigned long long gid[4] = {g0, g1, g2_, g3};
     unsigned long long h[4];
-#pragma unroll
     for (int n = 0; n < 4; ++n) h[n] = pt_id(tn2.X[n], tn2.Y[n], tn2.Z[n]);
     int k2 = 0, r2[4];
-#pragma unroll
     for (int n = 0; n < 4; ++n) {
         int rk = 0;
         bool on = false;
-#pragma unroll
         for (int o = 0; o < 4; ++o)
             if (o != k) { on = on || h[n] == gid[o]; rk += gid[o] < h[n] ? 1 : 0; }
         if (!on) k2 = n;
@@ -233,7 +228,6 @@ static __device__ __noinline__ uint32_t trimmed_sigs_on_face(const Stuff& S, con
     uint32_t sigs = 0u;
     int nsig = 0;
     for (int q2 = 0; q2 < to2.n; ++q2)
-#pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
             uint32_t codes, fmask;
             face_codes(to2.nodes, q2, s2, codes, fmask);
@@ -279,11 +273,9 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
     }
     if (to.n == 0) return 0u;
     unsigned long long gid[4];
-#pragma unroll
     for (int n = 0; n < 4; ++n) gid[n] = pt_id(tn.X[n], tn.Y[n], tn.Z[n]);
     // the faces of the pieces: node-code sets and the lattice face each lies in
     uint32_t fc[12], fm[12];
-#pragma unroll
     for (int i = 0; i < 12; ++i) {
         fc[i] = 0u; fm[i] = 0u;
         if ((i >> 2) < to.n) face_codes(to.nodes, i >> 2, i & 3, fc[i], fm[i]);
@@ -292,9 +284,7 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
     uint32_t nb_sigs[4] = {0u, 0u, 0u, 0u};
     bool nb_after[4] = {false, false, false, false};
     uint32_t used = 0u;
-#pragma unroll
     for (int i = 0; i < 12; ++i) used |= fm[i];
-#pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (!((used >> k) & 1u)) continue;
         int at2, t2;
@@ -308,30 +298,25 @@ static __device__ __noinline__ uint32_t tet_boundary_mask(const Stuff& S, const 
         nb_sigs[k] = st2 == TET_WHOLE ? SIG_WHOLE_FACE : trimmed_sigs_on_face(S, V, c2, t2, gid[0], gid[1], gid[2], gid[3], k);
     }
     uint32_t out = 0u;
-#pragma unroll
     for (int i = 0; i < 12; ++i) {
         if ((i >> 2) >= to.n) continue;
         uint32_t cnt = 0u;
         bool last = true;
         // ... occurrences among the other pieces of this lattice tet
-#pragma unroll
         for (int j = 0; j < 12; ++j)
             if (j != i && fc[j] == fc[i]) { ++cnt; if (j > i) last = false; }
         // ... and among the pieces of the lattice tet across the lattice face it lies in
         if (fm[i]) {
             const int k = __ffs((int)fm[i]) - 1;
             int r[4];
-#pragma unroll
             for (int n = 0; n < 4; ++n) {
                 int rk = 0;
-#pragma unroll
                 for (int o = 0; o < 4; ++o) rk += (o != k && o != n && gid[o] < gid[n]) ? 1 : 0;
                 r[n] = rk;
             }
             const uint32_t mine = face_sig(to.nodes, i >> 2, i & 3, k, r[0], r[1], r[2], r[3]);
             const uint32_t sigs = pick4(nb_sigs[0], nb_sigs[1], nb_sigs[2], nb_sigs[3], k);
             const bool after = pick4(nb_after[0], nb_after[1], nb_after[2], nb_after[3], k);
-#pragma unroll
             for (int f = 0; f < 4; ++f)
                 if (mine != 0u && ((sigs >> (8 * f)) & 0xffu) == mine) { ++cnt; if (after) last = false; }
         }
