@@ -38,6 +38,7 @@ struct mc_ctx {
     std::vector<mc::DevBuf> free_list;  // cached device allocations
     uint64_t held_bytes = 0;
 
+    uint64_t tiled_min_flops = 16;   // programs at least this expensive per point take the tile-specialised, sign-proving SDF path (env MC_TILED_MIN_FLOPS)
     uint32_t tile_program_cap_words = MC_TILE_PROGRAM_CAP_WORDS;  // env MC_TILE_PROGRAM_CAP_WORDS overrides (tuning)
     bool tet_emit_attr_set = false;     // cudaFuncSetAttribute for k_tet_emit done on this device
     bool debug = false, debug_sync = false;  // MC_DEBUG=1: poison allocations + check every stage (2: poison, 3: checks)

@@ -213,6 +213,7 @@ mc_ctx* mc_ctx_new(int device, void* stream) {
     mc_ctx* c = new mc_ctx();
     { const char* dbg = std::getenv("MC_DEBUG"); const int lvl = dbg ? std::atoi(dbg) : 0; c->debug = lvl == 1 || lvl == 2; c->debug_sync = lvl == 1 || lvl == 3; }
     { const char* cap = std::getenv("MC_TILE_PROGRAM_CAP_WORDS"); if (cap && std::atoi(cap) > 0) c->tile_program_cap_words = (uint32_t)std::atoi(cap); }
+    { const char* mf = std::getenv("MC_TILED_MIN_FLOPS"); if (mf && std::atoi(mf) >= 0) c->tiled_min_flops = (uint64_t)std::atoi(mf); }
     c->device = device;
     c->stream = (cudaStream_t)stream;
     cudaDeviceProp prop;
@@ -411,7 +412,7 @@ static int launch_sdf_field_tiled(mc_mesh* m, bool* done) {
 
 static int launch_sdf_field(mc_mesh* m) {
     mc_ctx* c = m->ctx;
-    if ((m->prog.flops >= 256 || (m->flags & MC_OPT_FORCE_TILE_PRUNING)) && !(m->flags & MC_OPT_NO_TILE_PRUNING)) {
+    if ((m->prog.flops >= c->tiled_min_flops || (m->flags & MC_OPT_FORCE_TILE_PRUNING)) && !(m->flags & MC_OPT_NO_TILE_PRUNING)) {
         bool done = false;
         int rc = launch_sdf_field_tiled(m, &done);
         if (rc != MC_OK || done) return rc;

@@ -108,7 +108,7 @@ def test_sdf_values_vs_platform_libm(oracle, ctx):
 def test_lattice_field_bit_exact(oracle, ctx):
     res = 15.0 / 24
     a = luascad.eval(scenes.XPLICIT_LUA)["xplicit"].obj
-    mesh = mc.IsosurfaceStuffing(a, res, 0.2, ctx=ctx).tessellate()
+    mesh = mc.IsosurfaceStuffing(a, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_KEEP_PHI).tessellate()
     b = luascad.eval(scenes.XPLICIT_LUA, backend=oracle.OracleScene())["xplicit"].obj
     want = b.backend.eval_lattice(b.node, res, res, mesh.stats()["dim"])
     got = mesh.phi()
