@@ -1,5 +1,6 @@
 // Internal host-side structures behind the opaque C handles.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only)
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -62,6 +63,7 @@ struct mc_mesh {
     uint32_t flags = 0, max_bisect = 200;
     mc::Program prog;
 
+    alignas(64) CUtensorMap tmap_phi;  // {NX, NY, planes} f64 tensor over d_phi, box 18 x 18 x 9 (mc_tma.cuh)
     mc::TileGrid g{};
     mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo;
     mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign, d_sub;

@@ -15,6 +15,7 @@
 // only the bytes of its output.
 #pragma once
 #include "mc_stuffing.cuh"
+#include "mc_tma.cuh"
 
 namespace mc {
 
@@ -234,6 +235,46 @@ __device__ __forceinline__ void stage_points(const Lattice& L, uint32_t X0, uint
     }
 }
 
+// The same staging through the TMA unit: the (TS + 2)^3 box of phi around a tile (origin = tile origin + OFF)
+// is brought into shared memory by two bulk tensor copies of BOX_HZ planes each (one thread issues them, the
+// block waits on an mbarrier), then f(idx, inside, phi) is called for every idx in [0, 18^3).  Nothing is stored
+// for points of proven tiles: their sign comes from the tile-sign table (27 neighbours, staged first).
+constexpr int BOX_H = (int)TS + 2, BOX_HZ = BOX_H / 2;
+constexpr uint32_t BOX_BYTES = (uint32_t)(BOX_HZ * BOX_H * BOX_H * 8);
+template <int OFF, typename F>
+__device__ __forceinline__ void tma_stage_phi(const Lattice& L, const TileGrid& g, const CUtensorMap* tmap, unsigned long long* bar,
+                                              uint32_t& parity, double* box, int8_t* s_ts, uint32_t tile, uint32_t X0, uint32_t Y0,
+                                              uint32_t Z0, F f) {
+    if (threadIdx.x < 27) {
+        const int dx = (int)(threadIdx.x % 3) - 1, dy = (int)((threadIdx.x / 3) % 3) - 1, dz = (int)(threadIdx.x / 9) - 1;
+        const int tx = (int)(tile % g.ntx) + dx, ty = (int)((tile / g.ntx) % g.nty) + dy, tz = (int)(tile / (g.ntx * g.nty)) + dz;
+        int8_t sgn = 0;
+        if (L.tsign != nullptr && tx >= 0 && ty >= 0 && tz >= 0 && tx < (int)g.ntx && ty < (int)g.nty && tz < (int)g.ntz)
+            sgn = L.tsign[((size_t)tz * g.nty + ty) * g.ntx + tx];
+        s_ts[threadIdx.x] = sgn;
+    }
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();  // the box is free again (and the tile signs are visible)
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, BOX_BYTES);
+            tma_load_3d(box, tmap, (int)X0 + OFF, (int)Y0 + OFF, (int)(Z0 - L.pz0) + OFF + BOX_HZ * half, bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        for (int i = (int)threadIdx.x; i < BOX_HZ * BOX_H * BOX_H; i += TILE_THREADS) {
+            const int bx = i % BOX_H, by = (i / BOX_H) % BOX_H, bz = i / (BOX_H * BOX_H) + BOX_HZ * half;
+            const int lx = bx + OFF, ly = by + OFF, lz = bz + OFF;   // relative to the tile origin
+            const int64_t X = (int64_t)X0 + lx, Y = (int64_t)Y0 + ly, Z = (int64_t)Z0 + lz;
+            const bool in = X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1;
+            const int tsx = lx < 0 ? 0 : (lx >= (int)TS ? 2 : 1), tsy = ly < 0 ? 0 : (ly >= (int)TS ? 2 : 1), tsz = lz < 0 ? 0 : (lz >= (int)TS ? 2 : 1);
+            const int8_t ts = s_ts[(tsz * 3 + tsy) * 3 + tsx];
+            f((bz * BOX_H + by) * BOX_H + bx, in, ts ? (double)ts : box[i]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // per-tile sign summary of the raw field: TF_NEG (max < 0), TF_POS (min > 0)
 static __global__ void __launch_bounds__(TILE_THREADS)
@@ -376,9 +417,16 @@ __host__ __device__ constexpr KDir kdir(int d) {
 }
 
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_warp_codes(Stuff S, unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
-             const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
+k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned long long* __restrict__ counters,
+             const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
+             unsigned long long* __restrict__ cursor) {
     constexpr int H = (int)TS + 2;
+    static_assert(H == BOX_H, "the TMA box is the tile with a one-point halo");
+    __shared__ __align__(128) double s_box[BOX_HZ * BOX_H * BOX_H];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int8_t s_ts[27];
+    uint32_t parity = 0u;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1u);
     __shared__ int8_t s_sg[H * H * H];
     __shared__ unsigned long long s_tab[8 * WT_STRIDE];
     __shared__ uint8_t s_pairs[8 * WP_STRIDE];
@@ -393,8 +441,7 @@ k_warp_codes(Stuff S, unsigned long long* __restrict__ counters, const uint32_t*
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, tile, X0, Y0, Z0);
     if (threadIdx.x == 0) { s_n = 0u; s_nan = 0u; }
-    __syncthreads();
-    stage_points<H, -1, false>(L, X0, Y0, Z0, [&](int idx, bool in, double v, uint8_t) {
+    tma_stage_phi<-1>(L, S.g, &tmap_phi, &s_bar, parity, s_box, s_ts, tile, X0, Y0, Z0, [&](int idx, bool in, double v) {
         const int8_t sg = !in ? SG_NONE : (v > 0.0 ? SG_POS : (v < 0.0 ? SG_NEG : (v == 0.0 ? SG_ZERO : SG_NAN)));
         s_sg[idx] = sg;
         if (sg == SG_NAN) s_nan = 1u;
@@ -884,10 +931,10 @@ k_bisect_edges(Stuff S, const uint64_t* __restrict__ prog, const unsigned long l
     const unsigned long long e = cutlist[active ? i : (ncut - 1)];
     const size_t pi = (size_t)(e >> 4);
     const int s = (int)(e & 15ull);
-    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t per_plane = (uint64_t)L.PX * L.NY;
     const uint32_t Z = L.pz0 + (uint32_t)(pi / per_plane);
     const uint64_t r = pi % per_plane;
-    const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+    const uint32_t Y = (uint32_t)(r / L.PX), X = (uint32_t)(r % L.PX);
     const uint32_t WX = X + C_DIR[s][0], WY = Y + C_DIR[s][1], WZ = Z + C_DIR[s][2];
     const double pv = L.phi[pi];
     // `a` starts at the positive end (every call site passes the phi > 0 vertex first)

@@ -17,6 +17,8 @@ namespace mc {
 struct Lattice {
     uint32_t nx, ny, nz;  // cells of the global lattice
     uint32_t NX, NY, NZ;  // points per axis (n + 1)
+    uint32_t PX;          // row pitch of the per-point arrays in points: NX rounded up to a multiple of 16, so that
+                          // every 16-point tile row of phi is one aligned 128-byte line and rows are 16-byte aligned (TMA)
     uint32_t pz0, pz1;    // stored point planes [pz0, pz1] of phi / wcode / vmask / vbase
     double ox, oy, oz;    // bbox.min (tessellate3d/src/lib.rs:57)
     double res;
@@ -47,7 +49,7 @@ __device__ __forceinline__ void tile_origin(const TileGrid& g, uint64_t t, uint3
 }
 
 __device__ __forceinline__ size_t pidx(const Lattice& L, uint32_t X, uint32_t Y, uint32_t Z) {
-    return ((size_t)(Z - L.pz0) * L.NY + Y) * L.NX + X;
+    return ((size_t)(Z - L.pz0) * L.NY + Y) * L.PX + X;
 }
 // SDF value at a lattice point as far as any consumer may look at it: the stored value, or +-1 in a
 // tile whose sign is proven (nothing is stored there)

@@ -105,6 +105,34 @@ static void build_warp_table(std::vector<unsigned long long>& tab) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+// Tensor map of the lattice field for the TMA staging of the tile kernels (mc_tma.cuh): a 3-D f64 tensor
+// {NX, NY, stored planes} with the padded row pitch, box BOX_H x BOX_H x BOX_HZ.  The driver's encoder is
+// looked up at run time (no link dependency on libcuda).
+int make_phi_tensor_map(mc_mesh* m) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (EncodeTiled)fn;
+    }
+    const Lattice& L = m->L;
+    const cuuint64_t dims[3] = {L.NX, L.NY, (cuuint64_t)(L.pz1 - L.pz0 + 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)L.PX * 8, (cuuint64_t)L.PX * L.NY * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)BOX_H, (cuuint32_t)BOX_H, (cuuint32_t)BOX_HZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(&m->tmap_phi, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, m->d_phi.p, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return MC_OK;
+}
+
 // exclusive scan of n packed per-tile totals (k_scan_tiles_local / _add); `sums` holds 2 words per SCAN_BLOCK entries
 int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base_hi, void* sums, void* totals) {
     if (n == 0) {
@@ -473,6 +501,7 @@ static int tile_layer_classes(mc_ctx* c, const mc_tape* volume, int32_t root, do
     Lattice L{};
     L.nx = (uint32_t)dim[0]; L.ny = (uint32_t)dim[1]; L.nz = (uint32_t)dim[2];
     L.NX = L.nx + 1; L.NY = L.ny + 1; L.NZ = L.nz + 1;
+    L.PX = (L.NX + 15u) & ~15u;
     L.ox = bb.lo[0]; L.oy = bb.lo[1]; L.oz = bb.lo[2];
     L.res = resolution;
     L.pz0 = 0; L.pz1 = L.nz;
@@ -603,6 +632,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     Lattice& L = m->L;
     L.nx = (uint32_t)dim[0]; L.ny = (uint32_t)dim[1]; L.nz = (uint32_t)dim[2];
     L.NX = L.nx + 1; L.NY = L.ny + 1; L.NZ = L.nz + 1;
+    L.PX = (L.NX + 15u) & ~15u;
     L.ox = bb.lo[0]; L.oy = bb.lo[1]; L.oz = bb.lo[2];
     L.res = resolution;
     uint64_t zb = 0, ze = dim[2];
@@ -622,10 +652,10 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
 
     const uint64_t per_plane = (uint64_t)L.NX * L.NY;
     const uint32_t nplanes = L.pz1 - L.pz0 + 1;
-    const uint64_t npts = per_plane * nplanes;
+    const uint64_t npts = (uint64_t)L.PX * L.NY * nplanes;   // entries of the per-point arrays (padded rows)
     const uint64_t ncls = (uint64_t)L.nx * L.ny * (m->cl1 - m->cl0);
     const uint64_t nown = (m->oz1 >= m->oz0) ? per_plane * (m->oz1 - m->oz0 + 1) : 0;
-    m->points_evaluated = npts;
+    m->points_evaluated = per_plane * nplanes;
     m->points_owned = nown;
     m->g.ntx = (L.NX + TS - 1) / TS; m->g.nty = (L.NY + TS - 1) / TS; m->g.ntz = (nplanes + TS - 1) / TS;
     m->g.z0 = L.pz0;
@@ -655,6 +685,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->alloc(std::max<uint64_t>(ntiles, 1) * 4 * 4, m->d_lists));
     L.phi = (const double*)m->d_phi.p;
     L.wcode = (uint8_t*)m->d_wcode.p;
+    MC_TRY(make_phi_tensor_map(m));
 
     cudaStream_t s = c->stream;
     {
@@ -680,7 +711,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     k_tile_neighbourhood<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters, (uint32_t*)T.v_active, (uint32_t*)T.v_neg,
                                                                  (unsigned long long*)m->d_vtile_tot.p);
     MC_TRY(c->stage_check("stage tile summary"));
-    k_warp_codes<<<lgrid, TILE_THREADS, 0, s>>>(S, counters, T.v_active, T.n_v_active, counters + CUR_WARP);
+    k_warp_codes<<<lgrid, TILE_THREADS, 0, s>>>(S, m->tmap_phi, counters, T.v_active, T.n_v_active, counters + CUR_WARP);
     c->launches += m->tiled_sdf ? 2 : 3;
     MC_TRY_CUDA(cudaGetLastError());
     MC_TRY(c->stage_check("stage warp codes"));
@@ -1175,7 +1206,9 @@ int mc_mesh_copy_phi(mc_mesh* m, double* out, uint64_t n) {
         return fail(MC_ERR_STATE, "mc_mesh_copy_phi: the field holds sign placeholders where the sign was proven; "
                                   "tessellate with MC_OPT_KEEP_PHI to read it");
     MC_CUDA(cudaSetDevice(m->ctx->device));
-    MC_CUDA(cudaMemcpyAsync(out, m->d_phi.p, n * 8, cudaMemcpyDeviceToHost, m->ctx->stream));
+    // the rows of the field are padded to L.PX points on the device
+    MC_CUDA(cudaMemcpy2DAsync(out, (size_t)m->L.NX * 8, m->d_phi.p, (size_t)m->L.PX * 8, (size_t)m->L.NX * 8,
+                              (size_t)m->L.NY * (m->L.pz1 - m->L.pz0 + 1), cudaMemcpyDeviceToHost, m->ctx->stream));
     MC_CUDA(cudaStreamSynchronize(m->ctx->stream));
     return MC_OK;
 }

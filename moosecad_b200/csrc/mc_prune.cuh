@@ -793,7 +793,7 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
     const bool fits = !CAPPED || s_newpos[n_inst] <= n_words;
     __syncthreads();
     const Lattice& L = S.L;
-    const uint64_t per_plane = (uint64_t)L.NX * L.NY;
+    const uint64_t per_plane = (uint64_t)L.PX * L.NY;
     const uint64_t n = c1 - c0;
     for (uint64_t base = 0; base < n; base += TILE_THREADS) {
         const uint64_t i = base + threadIdx.x;
@@ -803,7 +803,7 @@ k_bisect_edges_tiled(Stuff S, const uint64_t* __restrict__ prog, const uint32_t*
         const int s = (int)(e & 15ull);
         const uint32_t Z = L.pz0 + (uint32_t)(pi / per_plane);
         const uint64_t r = pi % per_plane;
-        const uint32_t Y = (uint32_t)(r / L.NX), X = (uint32_t)(r % L.NX);
+        const uint32_t Y = (uint32_t)(r / L.PX), X = (uint32_t)(r % L.PX);
         const uint32_t WX = X + C_DIR[s][0], WY = Y + C_DIR[s][1], WZ = Z + C_DIR[s][2];
         const double pv = L.phi[pi];
         double ax, ay, az, bx, by, bz;
