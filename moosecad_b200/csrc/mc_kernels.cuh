@@ -239,8 +239,11 @@ __device__ __forceinline__ void stage_points(const Lattice& L, uint32_t X0, uint
 // is brought into shared memory by two bulk tensor copies of BOX_HZ planes each (one thread issues them, the
 // block waits on an mbarrier), then f(idx, inside, phi) is called for every idx in [0, 18^3).  Nothing is stored
 // for points of proven tiles: their sign comes from the tile-sign table (27 neighbours, staged first).
-constexpr int BOX_H = (int)TS + 2, BOX_HZ = BOX_H / 2;
-constexpr uint32_t BOX_BYTES = (uint32_t)(BOX_HZ * BOX_H * BOX_H * 8);
+// The innermost start coordinate of a TMA box must be 16-byte aligned (measured: scripts/probe/tma_probe.cu),
+// i.e. even for doubles: the box starts at x = tile origin - 2 and is BOX_W = 20 wide, columns 1..18 (OFF = -1)
+// or 2..19 (OFF = 0) are used.
+constexpr int BOX_H = (int)TS + 2, BOX_HZ = BOX_H / 2, BOX_W = BOX_H + 2;
+constexpr uint32_t BOX_BYTES = (uint32_t)(BOX_HZ * BOX_H * BOX_W * 8);
 template <int OFF, typename F>
 __device__ __forceinline__ void tma_stage_phi(const Lattice& L, const TileGrid& g, const CUtensorMap* tmap, unsigned long long* bar,
                                               uint32_t& parity, double* box, int8_t* s_ts, uint32_t tile, uint32_t X0, uint32_t Y0,
@@ -259,7 +262,7 @@ __device__ __forceinline__ void tma_stage_phi(const Lattice& L, const TileGrid& 
         if (threadIdx.x == 0) {
             fence_proxy_async();
             mbar_expect_tx(bar, BOX_BYTES);
-            tma_load_3d(box, tmap, (int)X0 + OFF, (int)Y0 + OFF, (int)(Z0 - L.pz0) + OFF + BOX_HZ * half, bar);
+            tma_load_3d(box, tmap, (int)X0 - 2, (int)Y0 + OFF, (int)(Z0 - L.pz0) + OFF + BOX_HZ * half, bar);
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
@@ -270,7 +273,7 @@ __device__ __forceinline__ void tma_stage_phi(const Lattice& L, const TileGrid& 
             const bool in = X >= 0 && Y >= 0 && X < (int64_t)L.NX && Y < (int64_t)L.NY && Z >= (int64_t)L.pz0 && Z <= (int64_t)L.pz1;
             const int tsx = lx < 0 ? 0 : (lx >= (int)TS ? 2 : 1), tsy = ly < 0 ? 0 : (ly >= (int)TS ? 2 : 1), tsz = lz < 0 ? 0 : (lz >= (int)TS ? 2 : 1);
             const int8_t ts = s_ts[(tsz * 3 + tsy) * 3 + tsx];
-            f((bz * BOX_H + by) * BOX_H + bx, in, ts ? (double)ts : box[i]);
+            f((bz * BOX_H + by) * BOX_H + bx, in, ts ? (double)ts : box[((bz - BOX_HZ * half) * BOX_H + by) * BOX_W + (lx + 2)]);
         }
     }
 }
@@ -422,7 +425,7 @@ k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned lon
              unsigned long long* __restrict__ cursor) {
     constexpr int H = (int)TS + 2;
     static_assert(H == BOX_H, "the TMA box is the tile with a one-point halo");
-    __shared__ __align__(128) double s_box[BOX_HZ * BOX_H * BOX_H];
+    __shared__ __align__(128) double s_box[BOX_HZ * BOX_H * BOX_W];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int8_t s_ts[27];
     uint32_t parity = 0u;

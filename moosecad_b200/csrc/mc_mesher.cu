@@ -106,7 +106,7 @@ static void build_warp_table(std::vector<unsigned long long>& tab) {
 static inline unsigned blocks_for(uint64_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
 // Tensor map of the lattice field for the TMA staging of the tile kernels (mc_tma.cuh): a 3-D f64 tensor
-// {NX, NY, stored planes} with the padded row pitch, box BOX_H x BOX_H x BOX_HZ.  The driver's encoder is
+// {NX, NY, stored planes} with the padded row pitch, box BOX_W x BOX_H x BOX_HZ.  The driver's encoder is
 // looked up at run time (no link dependency on libcuda).
 int make_phi_tensor_map(mc_mesh* m) {
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -124,7 +124,7 @@ int make_phi_tensor_map(mc_mesh* m) {
     const Lattice& L = m->L;
     const cuuint64_t dims[3] = {L.NX, L.NY, (cuuint64_t)(L.pz1 - L.pz0 + 1)};
     const cuuint64_t strides[2] = {(cuuint64_t)L.PX * 8, (cuuint64_t)L.PX * L.NY * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)BOX_H, (cuuint32_t)BOX_H, (cuuint32_t)BOX_HZ};
+    const cuuint32_t box[3] = {(cuuint32_t)BOX_W, (cuuint32_t)BOX_H, (cuuint32_t)BOX_HZ};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(&m->tmap_phi, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, m->d_phi.p, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
