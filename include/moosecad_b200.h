@@ -49,6 +49,7 @@ typedef enum mc_status {
 typedef struct mc_tape mc_tape; /* a recorded scene: the flat node list luascad lowers to */
 typedef struct mc_ctx mc_ctx;   /* device + stream + reusable workspace */
 typedef struct mc_mesh mc_mesh; /* result of one tessellation (device resident, host views on demand) */
+typedef struct mc_surface mc_surface; /* Mesh::to_boundary(): the surface as a triangle mesh */
 
 const char* mc_last_error(void);
 int mc_abi_version(void);
@@ -308,6 +309,16 @@ int mc_mesh_add_sideset(mc_mesh*, const mc_tape* boundary, int32_t root);
 uint64_t mc_mesh_sideset_len(const mc_mesh*, int index);
 const uint64_t* mc_mesh_sideset(mc_mesh*, int index);
 int mc_mesh_sideset_device(mc_mesh*, int index, void** d_pairs, uint64_t* n);
+
+/* Mesh::to_boundary() (mesh/src/lib.rs:359-386; what meshview renders): one Tri3 per surface side (the side's
+ * nodes in Tet4::face order), vertices compacted to the referenced ones (Mesh::compact).  Host views: coords
+ * xyz AoS f64, tris 3 x node id, valid until mc_surface_free.  Single device (not on a z-slab). */
+int mc_mesh_to_boundary(mc_mesh*, mc_surface** out);
+void mc_surface_free(mc_surface*);
+uint64_t mc_surface_num_vertices(const mc_surface*);
+uint64_t mc_surface_num_tris(const mc_surface*);
+const double* mc_surface_coords(const mc_surface*);
+const uint64_t* mc_surface_tris(const mc_surface*);
 
 /* ------------------------------------------------------------------------------------
  * The consumer right after the path: exodus::write(&mesh, path) (exodus/src/lib.rs:14-155) builds

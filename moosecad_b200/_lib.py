@@ -112,6 +112,12 @@ SIGNATURES = {
     "mc_mesh_exodus_coord": (C.c_int, [_P, _P, _U64]),
     "mc_mesh_exodus_connect": (C.c_int, [_P, _P]),
     "mc_mesh_exodus_sideset": (C.c_int, [_P, C.c_int, _P, _P]),
+    "mc_mesh_to_boundary": (C.c_int, [_P, C.POINTER(_P)]),
+    "mc_surface_free": (None, [_P]),
+    "mc_surface_num_vertices": (_U64, [_P]),
+    "mc_surface_num_tris": (_U64, [_P]),
+    "mc_surface_coords": (_PD, [_P]),
+    "mc_surface_tris": (_PU64, [_P]),
     "mc_mesh_boundary": (C.c_int, [_P, _PU64]),
     "mc_mesh_boundary_sides": (_PU64, [_P]),
     "mc_mesh_boundary_device": (C.c_int, [_P, C.POINTER(_P), _PU64]),

@@ -811,3 +811,108 @@ int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, SideSetDev& o
 }
 
 }  // namespace mc
+
+// ---- Mesh::to_boundary (mesh/src/lib.rs:359-386) -------------------------------------------------
+// The surface as a triangle mesh: one Tri3 per boundary side (the side's nodes in Tet4::face order), the
+// vertices compacted to the referenced ones (Mesh::compact, mesh/src/lib.rs:318-339; numbering by vertex
+// id instead of first appearance — compared after canonical sorting like every other mesh here).
+namespace mc {
+
+static __global__ void k_flag_prefix(const uint8_t* __restrict__ flag, uint64_t n, unsigned long long* __restrict__ block_cnt) {
+    __shared__ uint32_t s_w[8];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned b = __ballot_sync(0xffffffffu, i < n && flag[i] != 0);
+    if ((threadIdx.x & 31u) == 0u) s_w[threadIdx.x >> 5] = (uint32_t)__popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        block_cnt[blockIdx.x] = t;
+    }
+}
+// new id of every flagged vertex (ids in vertex order) + its coordinates
+static __global__ void k_surface_vertices(const uint8_t* __restrict__ flag, uint64_t n, const unsigned long long* __restrict__ block_base,
+                                          const double* __restrict__ coords, unsigned long long* __restrict__ new_id,
+                                          double* __restrict__ out_xyz) {
+    __shared__ uint32_t s_w[8];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < n && flag[i] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, on);
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (lane == 0u) s_w[wid] = (uint32_t)__popc(b);
+    __syncthreads();
+    uint32_t before = 0;
+    for (unsigned w = 0; w < wid; ++w) before += s_w[w];
+    if (on) {
+        const unsigned long long id = block_base[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+        new_id[i] = id;
+        out_xyz[3 * id] = coords[3 * i]; out_xyz[3 * id + 1] = coords[3 * i + 1]; out_xyz[3 * id + 2] = coords[3 * i + 2];
+    }
+}
+template <typename IndexT>
+__global__ void k_surface_tris(const IndexT* __restrict__ tets, unsigned long long tet_base, const unsigned long long* __restrict__ sides,
+                               uint64_t n, long long vertex_base, const unsigned long long* __restrict__ new_id,
+                               unsigned long long* __restrict__ tris) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tris[3 * i + k] = new_id[side_node(tets, tet_base, sides, i, k) - vertex_base];
+}
+
+int compute_surface(mc_mesh* m, mc_surface* out) {
+    mc_ctx* c = m->ctx;
+    MC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (m->lower_count != 0 || m->vertex_base != 0)
+        return fail(MC_ERR_UNSUPPORTED, "Mesh::to_boundary on a z-slab: the surface vertices of the shared plane live on the slab below");
+    const uint64_t ns = m->n_sides, nv = m->n_verts;
+    out->n_tris = ns;
+    out->n_verts = 0;
+    if (ns == 0) return MC_OK;
+    Scratch sc(c);
+    DevBuf flag, newid, bcnt, bbase, dtot, sums;
+    const unsigned nbv = (unsigned)((nv + 255) / 256), nbs = (unsigned)((ns + 255) / 256);
+    int rc = sc.alloc(std::max<uint64_t>(nv, 1), flag);
+    if (rc == MC_OK) rc = sc.alloc(std::max<uint64_t>(nv, 1) * 8, newid);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nbv + 1) * 8, bcnt);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nbv + 1) * 8, bbase);
+    if (rc == MC_OK) rc = sc.alloc(32, dtot);
+    if (rc == MC_OK) rc = sc.alloc(((size_t)nbv / SCAN_BLOCK + 2) * 16, sums);
+    if (rc != MC_OK) return rc;
+    MC_CUDA(cudaMemsetAsync(flag.p, 0, std::max<uint64_t>(nv, 1), s));
+    const unsigned long long* sides = (const unsigned long long*)m->d_sides.p;
+    if (m->index_bytes == 4)
+        k_mark_side_nodes<uint32_t><<<nbs, 256, 0, s>>>((const uint32_t*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p);
+    else
+        k_mark_side_nodes<unsigned long long><<<nbs, 256, 0, s>>>((const unsigned long long*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p);
+    k_flag_prefix<<<nbv, 256, 0, s>>>((const uint8_t*)flag.p, nv, (unsigned long long*)bcnt.p);
+    c->launches += 2;
+    MC_CUDA(cudaGetLastError());
+    rc = scan_tiles(c, bcnt.p, nbv, bbase.p, nullptr, sums.p, dtot.p);
+    if (rc != MC_OK) return rc;
+    unsigned long long h[2];
+    MC_CUDA(cudaMemcpyAsync(h, dtot.p, 16, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    out->n_verts = h[0];
+    rc = c->alloc(std::max<uint64_t>(out->n_verts, 1) * 24, out->d_coords);
+    if (rc == MC_OK) rc = c->alloc(ns * 24, out->d_tris);
+    if (rc != MC_OK) return rc;
+    k_surface_vertices<<<nbv, 256, 0, s>>>((const uint8_t*)flag.p, nv, (const unsigned long long*)bbase.p, (const double*)m->d_coords.p,
+                                           (unsigned long long*)newid.p, (double*)out->d_coords.p);
+    if (m->index_bytes == 4)
+        k_surface_tris<uint32_t><<<nbs, 256, 0, s>>>((const uint32_t*)m->d_tets.p, m->tet_base, sides, ns, 0, (const unsigned long long*)newid.p,
+                                                     (unsigned long long*)out->d_tris.p);
+    else
+        k_surface_tris<unsigned long long><<<nbs, 256, 0, s>>>((const unsigned long long*)m->d_tets.p, m->tet_base, sides, ns, 0,
+                                                               (const unsigned long long*)newid.p, (unsigned long long*)out->d_tris.p);
+    c->launches += 2;
+    MC_CUDA(cudaGetLastError());
+    out->h_coords.resize(out->n_verts * 3);
+    out->h_tris.resize(ns * 3);
+    if (out->n_verts) MC_CUDA(cudaMemcpyAsync(out->h_coords.data(), out->d_coords.p, out->n_verts * 24, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaMemcpyAsync(out->h_tris.data(), out->d_tris.p, ns * 24, cudaMemcpyDeviceToHost, s));
+    MC_CUDA(cudaStreamSynchronize(s));
+    return MC_OK;
+}
+
+}  // namespace mc

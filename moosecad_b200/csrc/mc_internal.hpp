@@ -108,6 +108,15 @@ struct mc_mesh {
     std::vector<mc::SideSetDev> sidesets;
 };
 
+// Mesh::to_boundary result: a triangle mesh (mesh/src/lib.rs:359-386)
+struct mc_surface {
+    mc_ctx* ctx = nullptr;
+    uint64_t n_verts = 0, n_tris = 0;
+    mc::DevBuf d_coords, d_tris;       // xyz f64; 3 x uint64 node ids per triangle
+    std::vector<double> h_coords;
+    std::vector<uint64_t> h_tris;
+};
+
 namespace mc {
 int cuda_fail(cudaError_t e, const char* what);
 #define MC_CUDA(call)                                              \
@@ -124,4 +133,5 @@ int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base
 int compute_boundary(mc_mesh* m);
 int boundary_host_view(mc_mesh* m);
 int compute_sideset(mc_mesh* m, const mc_tape* tape, int32_t root, SideSetDev& out);
+int compute_surface(mc_mesh* m, mc_surface* out);
 }  // namespace mc

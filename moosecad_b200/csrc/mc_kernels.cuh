@@ -419,7 +419,7 @@ __host__ __device__ constexpr KDir kdir(int d) {
     return KDir{T[d][0], T[d][1], T[d][2]};
 }
 
-static __global__ void __launch_bounds__(TILE_THREADS)
+static __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned long long* __restrict__ counters,
              const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
              unsigned long long* __restrict__ cursor) {

@@ -1270,6 +1270,32 @@ int mc_mesh_sideset_device(mc_mesh* m, int i, void** d_pairs, uint64_t* n) {
     return MC_OK;
 }
 
+// ---- Mesh::to_boundary -------------------------------------------------------------------
+int mc_mesh_to_boundary(mc_mesh* m, mc_surface** out) {
+    if (!m || !out) return fail(MC_ERR_ARG, "mc_mesh_to_boundary: bad argument");
+    *out = nullptr;
+    int rc = mc_mesh_boundary(m, nullptr);
+    if (rc != MC_OK) return rc;
+    mc_surface* sf = new mc_surface();
+    sf->ctx = m->ctx;
+    rc = compute_surface(m, sf);
+    if (rc != MC_OK) { mc_surface_free(sf); return rc; }
+    *out = sf;
+    return MC_OK;
+}
+void mc_surface_free(mc_surface* sf) {
+    if (!sf) return;
+    cudaSetDevice(sf->ctx->device);
+    cudaStreamSynchronize(sf->ctx->stream);
+    sf->ctx->release(sf->d_coords);
+    sf->ctx->release(sf->d_tris);
+    delete sf;
+}
+uint64_t mc_surface_num_vertices(const mc_surface* sf) { return sf ? sf->n_verts : 0; }
+uint64_t mc_surface_num_tris(const mc_surface* sf) { return sf ? sf->n_tris : 0; }
+const double* mc_surface_coords(const mc_surface* sf) { return sf ? sf->h_coords.data() : nullptr; }
+const uint64_t* mc_surface_tris(const mc_surface* sf) { return sf ? sf->h_tris.data() : nullptr; }
+
 // ---- mesh-crate predicates ---------------------------------------------------------------
 int mc_tet_quality(mc_ctx* c, const double* coords, uint64_t nv, const uint64_t* tets, uint64_t nt, double* volume,
                    double* aspect_ratio) {

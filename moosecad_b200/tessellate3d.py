@@ -197,6 +197,19 @@ class Mesh:
         p = self._lib.mc_mesh_boundary_sides(self.handle)
         return SideSet(np.ctypeslib.as_array(p, shape=(n.value, 2)).copy())
 
+    def to_boundary(self):
+        """``Mesh::to_boundary`` (mesh/src/lib.rs:359-386): the surface as a triangle mesh,
+        (vertices (n, 3) float64, triangles (m, 3) uint64), vertices compacted."""
+        out = C.c_void_p()
+        _lib.check(self._lib.mc_mesh_to_boundary(self.handle, C.byref(out)))
+        try:
+            nv, nt = int(self._lib.mc_surface_num_vertices(out)), int(self._lib.mc_surface_num_tris(out))
+            v = np.ctypeslib.as_array(self._lib.mc_surface_coords(out), shape=(nv, 3)).copy() if nv else np.zeros((0, 3))
+            t = np.ctypeslib.as_array(self._lib.mc_surface_tris(out), shape=(nt, 3)).copy() if nt else np.zeros((0, 3), dtype=np.uint64)
+        finally:
+            self._lib.mc_surface_free(out)
+        return v, t
+
     def add_boundary_side_set(self, name, boundary_obj):
         """One iteration of the side-set loop of src/main.rs:87-106 for a ``:boundary()`` object."""
         idx = _lib.check(self._lib.mc_mesh_add_sideset(self.handle, boundary_obj.backend.handle, boundary_obj.node))

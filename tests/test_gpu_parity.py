@@ -388,3 +388,27 @@ def test_exodus_layout(script, res, ctx):
     for (elem_ss, side_ss), ss in zip(ex["side_sets"], mesh.side_sets()):
         a = ss.array().astype(np.int64)
         assert elem_ss.dtype == np.int32 and np.array_equal(elem_ss, a[:, 0] + 1) and np.array_equal(side_ss, a[:, 1] + 1)
+
+
+def _canonical_tris(coords, tris):
+    """Triangles as coordinate triples, rotated (cyclic, orientation preserved) to start at their smallest
+    vertex, sorted."""
+    c = np.asarray(coords, dtype=np.float64)[np.asarray(tris, dtype=np.int64)] + 0.0    # (m, 3, 3)
+    key = np.lexsort((c[..., 2], c[..., 1], c[..., 0]), axis=1)[:, 0]                   # index of the smallest vertex
+    rot = (np.arange(3)[None, :] + key[:, None]) % 3
+    c = c[np.arange(len(c))[:, None], rot].reshape(len(c), 9)
+    return c[np.lexsort(c.T[::-1])]
+
+
+@pytest.mark.parametrize("script,res", [(scenes.SPHERE_LUA, 1.0 / 23), (scenes.XPLICIT_LUA, 15.0 / 31)])
+def test_to_boundary(script, res, oracle, ctx):
+    """Mesh::to_boundary (mesh/src/lib.rs:359-386): one Tri3 per surface side in Tet4::face node order,
+    vertices compacted — against the same construction on the oracle's mesh."""
+    mesh = main.run(script, tessellation_resolution=res, ctx=ctx)
+    v, t = mesh.to_boundary()
+    om, _, _ = _oracle_run(oracle, script, res)
+    ov, oe, osides = om.vertices(), om.elems().astype(np.int64), om.boundary().astype(np.int64)
+    otris = oe[osides[:, 0][:, None], canon.FACE[osides[:, 1]]]
+    assert t.shape == otris.shape
+    assert len(v) == np.unique(otris).size and np.unique(t).size == len(v) and int(t.max()) == len(v) - 1   # compact
+    assert np.array_equal(_canonical_tris(v, t), _canonical_tris(ov, otris))
