@@ -43,6 +43,27 @@
 namespace orc {
 
 static int g_libm_mode = 1;  // see oracle_math.h
+
+// Named assumptions about the un-vendored crates, switchable so that the sensitivity
+// of every parity configuration to each recollection can be measured (scripts/assumption_sensitivity.py).
+// Value 0 is what the oracle (and the device path) implement; the alternatives are the other plausible readings.
+enum Assumption : int {
+    A_UNION_BBOX_DILATION = 0,   // 0: r * 0.2f32 as f64   1: r * 0.2 (f64)   2: r   3: none
+    A_INTERSECTION_BBOX_DILATION,// 0: not dilated         1: dilated like the union
+    A_EULER_ORDER,               // 0: Rz(yaw) Ry(pitch) Rx(roll) (nalgebra from_euler_angles)   1: Rx Ry Rz
+    A_SMOOTH_LIMIT,              // 0: children with x < m + r enter the exponential sum   1: x < m + exact_range
+    A_BOOLEAN_SLACK,             // 0: children get slack + r                             1: slack unchanged
+    A_COUNT
+};
+static int g_assume[A_COUNT] = {0, 0, 0, 0, 0};
+static inline double union_dilation(double r) {
+    switch (g_assume[A_UNION_BBOX_DILATION]) {
+        case 1: return r * 0.2;
+        case 2: return r;
+        case 3: return 0.0;
+        default: return r * (double)0.2f;
+    }
+}
 static inline double m_exp(double x) { return g_libm_mode ? portable_exp(x) : std::exp(x); }
 static inline double m_ln(double x) { return g_libm_mode ? portable_log(x) : std::log(x); }
 
@@ -205,6 +226,12 @@ static M4 euler_matrix(V3 r) {
     double sp = std::sin(r.y), cp = std::cos(r.y);
     double sy = std::sin(r.z), cy = std::cos(r.z);
     M4 m = M4::identity();
+    if (g_assume[A_EULER_ORDER]) {  // [A] the other composition order: Rx(roll) Ry(pitch) Rz(yaw)
+        m.at(0, 0) = cp * cy;                m.at(0, 1) = -cp * sy;               m.at(0, 2) = sp;
+        m.at(1, 0) = sr * sp * cy + cr * sy; m.at(1, 1) = -sr * sp * sy + cr * cy; m.at(1, 2) = -sr * cp;
+        m.at(2, 0) = -cr * sp * cy + sr * sy; m.at(2, 1) = cr * sp * sy + sr * cy; m.at(2, 2) = cr * cp;
+        return m;
+    }
     m.at(0, 0) = cy * cp;
     m.at(0, 1) = cy * sp * sr - sy * cr;
     m.at(0, 2) = cy * sp * cr + sy * sr;
@@ -246,7 +273,7 @@ static double rvmin(const std::vector<double>& v, double r, double exact_range) 
         }
     }
     if (!close_min) return minimum;
-    double min_plus_r = minimum + r;
+    double min_plus_r = minimum + (g_assume[A_SMOOTH_LIMIT] ? exact_range : r);   // [A] A_SMOOTH_LIMIT
     double r4 = r / 4.0;
     double exp_sum = 0.0;
     for (double x : v)
@@ -265,7 +292,7 @@ static double rvmax(const std::vector<double>& v, double r, double exact_range) 
         }
     }
     if (!close_max) return maximum;
-    double max_minus_r = maximum - r;
+    double max_minus_r = maximum - (g_assume[A_SMOOTH_LIMIT] ? exact_range : r);  // [A] A_SMOOTH_LIMIT
     double r4 = r / 4.0;
     double exp_sum = 0.0;
     for (double x : v)
@@ -358,11 +385,11 @@ struct Boolean : Object {
         if (is_union) {
             BBox b = BBox::neg_infinity();
             for (auto& o : objs) b = b.union_(o->bbox_);
-            bbox_ = b.dilate(r * (double)0.2f);
+            bbox_ = b.dilate(union_dilation(r));               // [A] A_UNION_BBOX_DILATION
         } else {
             BBox b = BBox::infinity();
             for (auto& o : objs) b = b.intersection(o->bbox_);
-            bbox_ = b;
+            bbox_ = g_assume[A_INTERSECTION_BBOX_DILATION] ? b.dilate(union_dilation(r)) : b;   // [A]
         }
     }
     double approx_value(V3 p, double slack) const override {
@@ -370,7 +397,7 @@ struct Boolean : Object {
         if (approx <= slack) {
             std::vector<double> vals;  // the reference collects into a Vec per call
             vals.reserve(objs.size());
-            for (auto& o : objs) vals.push_back(o->approx_value(p, slack + r));
+            for (auto& o : objs) vals.push_back(o->approx_value(p, g_assume[A_BOOLEAN_SLACK] ? slack : slack + r));   // [A]
             return is_union ? rvmin(vals, r, exact_range) : rvmax(vals, r, exact_range);
         }
         return approx;
@@ -843,6 +870,14 @@ using namespace orc;
 extern "C" {
 
 void orc_set_libm_mode(int mode) { g_libm_mode = mode; }
+// named Appendix-A assumptions (see enum Assumption); returns the previous value, -1 for a bad id
+int orc_set_assumption(int id, int value) {
+    if (id < 0 || id >= A_COUNT) return -1;
+    const int old = g_assume[id];
+    g_assume[id] = value;
+    return old;
+}
+int orc_num_assumptions() { return A_COUNT; }
 int orc_get_libm_mode() { return g_libm_mode; }
 double orc_exp(double x) { return m_exp(x); }
 double orc_ln(double x) { return m_ln(x); }

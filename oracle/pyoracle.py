@@ -32,6 +32,7 @@ def lib():
         V, D, I, U = C.c_void_p, C.c_double, C.c_int, C.c_uint64
         sig = {
             "orc_set_libm_mode": (None, [I]), "orc_get_libm_mode": (I, []),
+            "orc_set_assumption": (I, [I, I]), "orc_num_assumptions": (I, []),
             "orc_exp": (D, [D]), "orc_ln": (D, [D]),
             "orc_scene_new": (V, []), "orc_scene_free": (None, [V]),
             "orc_plane": (I, [V, I, I, D]), "orc_plane_hesian": (I, [V, D, D, D, D]),
@@ -69,6 +70,34 @@ def lib():
 def set_libm_mode(mode):
     """0: platform libm (what the reference binary executes); 1: portable restatement (default)."""
     lib().orc_set_libm_mode(int(mode))
+
+
+# Named assumptions about the un-vendored crates (SURVEY.md Appendix A; enum Assumption in oracle.cpp).
+# Value 0 is what the oracle and the device path implement, the others are the alternative readings.
+ASSUMPTIONS = {
+    "union_bbox_dilation": (0, {0: "r * 0.2f32 as f64", 1: "r * 0.2 (f64)", 2: "r", 3: "none"}),
+    "intersection_bbox_dilation": (1, {0: "not dilated", 1: "dilated like the union"}),
+    "euler_order": (2, {0: "Rz(yaw) Ry(pitch) Rx(roll)", 1: "Rx(roll) Ry(pitch) Rz(yaw)"}),
+    "smooth_limit": (3, {0: "x < m + r enters the exponential sum", 1: "x < m + exact_range"}),
+    "boolean_slack": (4, {0: "children get slack + r", 1: "slack unchanged"}),
+}
+
+
+def set_assumption(name, value):
+    """Switch one named Appendix-A assumption of the oracle; returns the previous value.  Scenes must be
+    built AFTER the switch (bounding boxes and matrices are computed at construction)."""
+    idx, values = ASSUMPTIONS[name]
+    if value not in values:
+        raise ValueError(f"{name}: {value} not in {sorted(values)}")
+    old = lib().orc_set_assumption(idx, int(value))
+    if old < 0:
+        raise RuntimeError("oracle rejected the assumption id")
+    return old
+
+
+def reset_assumptions():
+    for name in ASSUMPTIONS:
+        set_assumption(name, 0)
 
 
 class OracleScene:

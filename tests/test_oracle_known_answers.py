@@ -158,3 +158,42 @@ def test_libm_modes_agree(oracle, mode):
         assert ulp.max() <= 1.0
     finally:
         oracle.set_libm_mode(1)
+
+
+def test_named_assumptions_switch(oracle):
+    """The recalled implicit3d / bbox / nalgebra details are named switches of the
+    oracle.  The reference-held known answers (luascad test_primitives, config 1) hold under every
+    alternative - they do not discriminate them - while a rotated smooth scene does (see
+    profiles/r02_assumption_sensitivity.json, scripts/assumption_sensitivity.py)."""
+    def cube_answers():
+        res = luascad.eval(scenes.CUBE_LUA, backend=oracle.OracleScene())
+        top = res["top"].boundary()
+        return (top.backend.approx_value(top.node, (0.0, 0.0, 0.5), 0.0),
+                top.backend.approx_value(top.node, (0.0, 0.0, 1.0), 0.0))
+
+    def rotated_value():
+        sc = oracle.OracleScene()
+        g = luascad.Geom(sc)
+        o = g.cube(1, 0.6, 0.4, 0.05).rotate(0.3, 0.5, 0.7).union(g.sphere(0.35).translate(0.2, 0.1, 0), 0.1)
+        return o.backend.approx_value(o.node, (0.31, -0.22, 0.17), 0.0)
+
+    try:
+        oracle.reset_assumptions()
+        base = rotated_value()
+        assert cube_answers() == (0.0, 0.5)
+        changed = set()
+        for name, (_, values) in oracle.ASSUMPTIONS.items():
+            for v in values:
+                if v == 0:
+                    continue
+                oracle.reset_assumptions()
+                assert oracle.set_assumption(name, v) == 0
+                assert cube_answers() == (0.0, 0.5)
+                if rotated_value() != base:
+                    changed.add(name)
+        assert "euler_order" in changed
+        with pytest.raises(ValueError):
+            oracle.set_assumption("euler_order", 7)
+    finally:
+        oracle.reset_assumptions()
+    assert rotated_value() == base
