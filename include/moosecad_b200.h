@@ -156,7 +156,7 @@ typedef struct mc_options {
 #define MC_OPT_FORCE_TILE_PRUNING 8u /* use the tile-specialised evaluator even for tiny programs */
 #define MC_OPT_COUNT_FLOPS 16u /* instrumented SDF kernel: count the FP64 operations it executes (slower) */
 #define MC_OPT_PER_TILE_QUALITY 32u /* plain lattice tets: evaluate (step, parity) classes per tile, not globally */
-#define MC_OPT_NO_BOUNDARY_CACHE 64u /* do not keep the trimmed tets' pieces for mc_mesh_boundary (40 bytes per surface cell); it re-classifies them instead */
+#define MC_OPT_RECLASSIFY_EMIT 64u /* A/B check: the tet emission reads the field and sorts every trimmed tet again instead of using the shape bytes the classification recorded */
 
 /* Load estimate for z-slab sharding (no reference counterpart).  An interval evaluation
  * of the SDF program over the 16^3-point tiles sorts every tile into a cost class:

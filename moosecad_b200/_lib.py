@@ -16,7 +16,7 @@ MC_ERR_CUDA, MC_ERR_LIMIT, MC_ERR_DIVERGED, MC_ERR_STATE = -5, -6, -7, -8
 MC_OPT_KEEP_PHI, MC_OPT_SKIP_QUALITY, MC_OPT_NO_TILE_PRUNING, MC_OPT_FORCE_TILE_PRUNING = 1, 2, 4, 8
 MC_OPT_COUNT_FLOPS = 16
 MC_OPT_PER_TILE_QUALITY = 32
-MC_OPT_NO_BOUNDARY_CACHE = 64
+MC_OPT_RECLASSIFY_EMIT = 64
 MC_TILE_CLASS_STRIDE = 7
 
 

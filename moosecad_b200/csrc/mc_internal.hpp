@@ -42,6 +42,8 @@ struct mc_ctx {
     uint64_t tiled_min_flops = 16;   // programs at least this expensive per point take the tile-specialised, sign-proving SDF path (env MC_TILED_MIN_FLOPS)
     uint32_t tile_program_cap_words = MC_TILE_PROGRAM_CAP_WORDS;  // env MC_TILE_PROGRAM_CAP_WORDS overrides (tuning)
     bool tet_emit_attr_set = false;     // cudaFuncSetAttribute for k_tet_emit done on this device
+    bool boundary_attr_set = false;     // ... and for k_boundary_sides
+    mc::DevBuf d_shapes;                // shape tables (mc_shapes.hpp), uploaded at context creation
     bool debug = false, debug_sync = false;  // MC_DEBUG=1: poison allocations + check every stage (2: poison, 3: checks)
 
     int alloc(size_t bytes, mc::DevBuf& out);          // pool allocation (+ poison fill in debug mode)
@@ -65,7 +67,7 @@ struct mc_mesh {
 
     alignas(64) CUtensorMap tmap_phi;  // {NX, NY, planes} f64 tensor over d_phi, box 18 x 18 x 9 (mc_tma.cuh)
     mc::TileGrid g{};
-    mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo;
+    mc::DevBuf d_prog, d_phi, d_wcode, d_vmask, d_vloc, d_cinfo, d_cshape;
     mc::DevBuf d_tflag, d_vuni, d_cuni, d_tsign, d_sub;
     mc::DevBuf d_ttile_tot, d_ttile_base, d_vtile_tot, d_vtile_vbase, d_vtile_cbase;
     mc::DevBuf own_lower_table, own_lower_coords;  // copies pulled from the slab below (mc_tessellate_multi)
@@ -84,7 +86,6 @@ struct mc_mesh {
     double avg_pruned_words = 0;
 
     uint64_t counters[40] = {0};
-    mc::DevBuf d_pieces, d_tile_sbase;  // piece cache of the surface cells for Mesh::boundary (k_tet_emit writes it)
     uint64_t n_verts = 0, n_cuts = 0, n_tets = 0, n_kept = 0;
     uint64_t points_evaluated = 0, points_owned = 0;
     uint64_t vertex_base = 0, tet_base = 0;

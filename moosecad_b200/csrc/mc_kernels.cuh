@@ -14,6 +14,7 @@
 // are pure arithmetic (vertex and tet numbering is tile-major), so the bulk of the lattice costs
 // only the bytes of its output.
 #pragma once
+#include "mc_shapes.hpp"
 #include "mc_stuffing.cuh"
 #include "mc_tma.cuh"
 
@@ -94,11 +95,12 @@ struct Stuff {
     uint16_t* vmask;      // [points] VM_*
     uint16_t* vloc;       // [points] offset of the vertex's first output inside its tile
     uint16_t* cinfo;      // [cells of classified layers] CI_*
-    // Piece cache written by k_tet_emit and read by Mesh::boundary (mc_boundary.cu): the owned cells of
-    // a tile that are not full ("surface cells") are numbered in emission order from tile_sbase[tile];
-    // pieces[5 * (that number) + t] = TetOut::nodes | n << 60 of lattice tet t (0 when nothing came out)
-    unsigned long long* pieces;
-    unsigned long long* tile_sbase;
+    // Shape bytes (mc_shapes.hpp) of the five lattice tets of every SURFACE cell (classified, neither full nor
+    // empty), byte t of cshape[cidx]; written by k_classify_cells, read by the tet emission and by
+    // Mesh::boundary (mc_boundary.cu).  Full / empty cells are told apart by cinfo alone.
+    unsigned long long* cshape;
+    const ShapeTables* shapes;         // device copy of the shape tables (per context)
+    bool emit_reclassify;              // MC_OPT_RECLASSIFY_EMIT: the tet emission sorts again instead of using cshape (A/B check)
     const unsigned long long* warp_table;  // visit-order table of warp_vertices, see build_warp_table
     const unsigned long long* tvbase;  // [tiles] first output vertex of the tile (slab-local)
     const unsigned long long* ttbase;  // [tiles] first output tet of the tile (slab-local)
@@ -583,6 +585,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     __shared__ uint8_t s_cls[H * H * H];
     __shared__ uint16_t s_list[TILE_POINTS];   // surface cells (local index)
     __shared__ uint32_t s_ci[TILE_POINTS / 2]; // cinfo of the surface cells being assembled, by list slot
+    __shared__ __align__(8) uint8_t s_shape[TILE_POINTS / 2][8];  // their shape bytes (mc_shapes.hpp), one per lattice tet
     __shared__ uint32_t s_n;
     __shared__ uint32_t s_stat[8];             // trim cases 0..6 + exterior removals of the owned cells
     if (threadIdx.x == 0) s_n = 0u;
@@ -617,7 +620,10 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     // a tile has at most 4096 surface cells; the assembly buffer holds 2048 list slots per pass
     for (uint32_t pass = 0; pass < n; pass += TILE_POINTS / 2) {
         const uint32_t m = min(n - pass, TILE_POINTS / 2);
-        for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) s_ci[q] = 0u;
+        for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) {
+            s_ci[q] = 0u;
+            *reinterpret_cast<unsigned long long*>(s_shape[q]) = 0ull;
+        }
         __syncthreads();
         for (uint32_t w = threadIdx.x; w < 5u * m; w += TILE_THREADS) {
             const uint32_t q = w / 5u, t = w % 5u;
@@ -634,6 +640,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             if (to.ext_removed) { bits |= 1u << (10u + t); if (own) atomicAdd(&s_stat[7], 1u); }  // bit 10+t: dropped by the exterior test
             if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&s_stat[to.kase], 1u); }  // bit 24+t: trimmed
             atomicOr(&s_ci[q], bits);
+            if (to.n != 0) s_shape[q][t] = (uint8_t)(to.kase < 0 ? SHAPE_WHOLE : SHAPE_TRIM0 + 24 * (to.kase - 1) + to.perm);
             // zero-valued original vertices that made it into the output are "used"
             for (int o = 0; o < to.n; ++o)
 #pragma unroll
@@ -657,6 +664,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             // (on a FULL cell bit 10 doubles as CI_FULL_ZERO_CORNER: all five untouched bits are set anyway)
             if (untouched_bits == 31u && ci_count(ci) == 5u) ci |= (uint16_t)(CI_FULL | CI_FULL_ZERO_CORNER);
             S.cinfo[cidx(S, cx, cy, cz)] = ci;
+            S.cshape[cidx(S, cx, cy, cz)] = *reinterpret_cast<const unsigned long long*>(s_shape[q]);
             if (cz >= S.c0 && cz < S.c1) {
                 my_out += ci_count(ci); my_kept += kept; my_listed += ci_count(ci);
                 if (ci_count(ci) != 0u && !(ci & CI_FULL)) ++my_surf;
@@ -1299,7 +1307,7 @@ constexpr int TE_NP = TE_H * TE_H * TE_H;
 template <typename IndexT>
 constexpr size_t tet_emit_smem_bytes() {
     return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + 15 +
-           (size_t)TILE_POINTS * 2 * 5 /*ci, off, list, qoff, soff*/;
+           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, qoff*/;
 }
 
 // one output tet = one (u32 ids) or two (u64 ids) 16-byte stores
@@ -1333,8 +1341,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
     uint16_t* s_qoff = s_list + TILE_POINTS; // first quality-list slot of the cell, relative to the tile
-    uint16_t* s_soff = s_qoff + TILE_POINTS; // number of surface (not full) cells before the cell in the tile
-    __shared__ unsigned long long s_qbase, s_sbase;
+    __shared__ unsigned long long s_qbase;
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[tile];
     if (threadIdx.x == 0) s_n = 0u;
@@ -1390,7 +1397,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
         const uint16_t* __restrict__ row = S.cinfo + (row_owned ? cidx(S, X0, cy, cz) : 0);
         const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
-        uint32_t acc = 0, surf = 0;
+        uint32_t acc = 0;
         uint32_t pre[TS];
 #pragma unroll
         for (uint32_t i = 0; i < TS; ++i) {
@@ -1400,8 +1407,7 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             s_ci[threadIdx.x * TS + i] = ci;
             pre[i] = acc;
             acc += count | (listed ? count << 16 : 0u);
-            s_soff[threadIdx.x * TS + i] = (uint16_t)surf;   // (inside the row for now)
-            if (count && !(ci & CI_FULL)) { s_list[atomicAdd(&s_n, 1u)] = (uint16_t)(threadIdx.x * TS + i); ++surf; }
+            if (count && !(ci & CI_FULL)) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)(threadIdx.x * TS + i);
         }
         uint32_t tot;
         const uint32_t ex = block_exscan(acc, &tot, s_scan);
@@ -1412,15 +1418,6 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             if (QUALITY) s_qoff[threadIdx.x * TS + i] = (uint16_t)(v >> 16);
         }
         if (QUALITY && threadIdx.x == 0) s_qbase = (tot >> 16) ? atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)(tot >> 16)) : 0ull;
-        // surface-cell numbering of the piece cache
-        uint32_t stot;
-        const uint32_t sex = block_exscan(surf, &stot, s_scan);
-#pragma unroll
-        for (uint32_t i = 0; i < TS; ++i) s_soff[threadIdx.x * TS + i] = (uint16_t)(s_soff[threadIdx.x * TS + i] + sex);
-        if (threadIdx.x == 0) {
-            s_sbase = stot ? atomicAdd(&counters[CN_SURF_FILL], (unsigned long long)stot) : 0ull;
-            if (S.tile_sbase) S.tile_sbase[tile] = s_sbase;
-        }
     }
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
@@ -1470,11 +1467,18 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             for (int m = 0; m < 4; ++m) corner_xyz(c, tet_corner(c, t, m), tn.X[m], tn.Y[m], tn.Z[m]);
             to.n = 1; to.kase = -1; to.ext_removed = false;
             to.nodes = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15);
+        } else if (!S.emit_reclassify) {
+            // trimmed: the pieces follow from the shape byte k_classify_cells recorded (no look at the field)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) corner_xyz(c, tet_corner(c, t, m), tn.X[m], tn.Y[m], tn.Z[m]);
+            const uint32_t shape = (uint32_t)(S.cshape[cidx(S, c.cx, c.cy, c.cz)] >> (8 * t)) & 0xffu;
+            const unsigned long long e = S.shapes->nodes[shape];
+            to.n = (int)(e >> 60); to.kase = 0; to.ext_removed = false;
+            to.nodes = e & 0x0fffffffffffffffull;
         } else {
-            // trimmed (nt != 0, so kept and not dropped by the exterior test): vertices on both sides of zero
+            // the same from the field (nt != 0, so kept and not dropped by the exterior test): vertices on both sides of zero
             load_tet_mixed(L, c, t, tn);
             classify_tet<false, true>(L, c, t, tn, nullptr, 0, to);
-            if (S.pieces) S.pieces[5ull * (s_sbase + s_soff[j]) + (unsigned)t] = to.nodes | ((unsigned long long)to.n << 60);
         }
         int li[4];
 #pragma unroll

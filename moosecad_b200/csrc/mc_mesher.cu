@@ -209,7 +209,7 @@ void mc_ctx::trim() {
 
 static void mesh_release_all(mc_mesh* m) {
     mc_ctx* c = m->ctx;
-    DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vloc, &m->d_cinfo, &m->d_ttile_tot,
+    DevBuf* bufs[] = {&m->d_prog, &m->d_phi, &m->d_wcode, &m->d_vmask, &m->d_vloc, &m->d_cinfo, &m->d_cshape, &m->d_ttile_tot,
                       &m->d_ttile_base, &m->d_vtile_tot, &m->d_vtile_vbase, &m->d_vtile_cbase, &m->d_counters,
                       &m->d_tflag, &m->d_vuni, &m->d_cuni, &m->d_tsign,
                       &m->d_cutlist, &m->d_coords, &m->d_tets, &m->d_plane_table, &m->d_sides,
@@ -217,8 +217,6 @@ static void mesh_release_all(mc_mesh* m) {
     for (DevBuf* b : bufs) c->release(*b);
     c->release(m->d_side_flag);
     c->release(m->d_side_nodes);
-    c->release(m->d_pieces);
-    c->release(m->d_tile_sbase);
     c->release(m->own_lower_table);
     c->release(m->own_lower_coords);
     for (auto& ss : m->sidesets) c->release(ss.d_pairs);
@@ -262,6 +260,21 @@ mc_ctx* mc_ctx_new(int device, void* stream) {
         c->d_warp_table.p = p;
         c->d_warp_table.bytes = tab.size() * 8;
     }
+    {
+        static ShapeTables tables;   // 28 KB, the same for every context
+        static const bool ok = build_shape_tables(tables);
+        void* p = nullptr;
+        if (!ok || cudaMalloc(&p, sizeof(ShapeTables)) != cudaSuccess ||
+            cudaMemcpy(p, &tables, sizeof(ShapeTables), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail(ok ? MC_ERR_CUDA : MC_ERR_STATE, "mc_ctx_new: cannot build / upload the shape tables");
+            if (p) cudaFree(p);
+            cudaFree(c->d_warp_table.p);
+            delete c;
+            return nullptr;
+        }
+        c->d_shapes.p = p;
+        c->d_shapes.bytes = sizeof(ShapeTables);
+    }
     return c;
 }
 void mc_ctx_free(mc_ctx* c) {
@@ -270,6 +283,7 @@ void mc_ctx_free(mc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->trim();
     if (c->d_warp_table.p) cudaFree(c->d_warp_table.p);
+    if (c->d_shapes.p) cudaFree(c->d_shapes.p);
     delete c;
 }
 int mc_ctx_device(const mc_ctx* c) { return c ? c->device : MC_ERR_ARG; }
@@ -342,8 +356,9 @@ Stuff make_stuff(const mc_mesh* m) {
     S.tvbase = (const unsigned long long*)m->d_vtile_vbase.p;
     S.ttbase = (const unsigned long long*)m->d_ttile_base.p;
     S.lower_table = (const unsigned long long*)m->lower_table;
-    S.pieces = (unsigned long long*)m->d_pieces.p;
-    S.tile_sbase = (unsigned long long*)m->d_tile_sbase.p;
+    S.cshape = (unsigned long long*)m->d_cshape.p;
+    S.shapes = (const ShapeTables*)m->ctx->d_shapes.p;
+    S.emit_reclassify = (m->flags & MC_OPT_RECLASSIFY_EMIT) != 0;
     S.warp_table = (const unsigned long long*)m->ctx->d_warp_table.p;
     S.vertex_base = (long long)m->vertex_base;
     return S;
@@ -672,6 +687,7 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     MC_TRY(c->alloc(npts * 2, m->d_vmask));
     MC_TRY(c->alloc(npts * 2, m->d_vloc));
     MC_TRY(c->alloc(std::max<uint64_t>(ncls, 1) * 2, m->d_cinfo));
+    MC_TRY(c->alloc(std::max<uint64_t>(ncls, 1) * 8, m->d_cshape));
     MC_TRY(c->alloc(ntiles + 4, m->d_tflag));
     MC_TRY(c->alloc(ntiles + 4, m->d_vuni));
     MC_TRY(c->alloc(ntiles + 4, m->d_cuni));
@@ -927,12 +943,6 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
     m->index_bytes = (m->vertex_base + m->n_verts < (1ull << 32)) ? 4 : 8;
     int rc = c->alloc(std::max<uint64_t>(m->n_tets, 1) * 4 * (size_t)m->index_bytes, m->d_tets);
     if (rc != MC_OK) return rc;
-    // piece cache for Mesh::boundary: 5 words per owned surface cell (counted by the classification)
-    if (!(m->flags & MC_OPT_NO_BOUNDARY_CACHE) && m->counters[CN_SURF_CELLS] > 0) {
-        rc = c->alloc(m->counters[CN_SURF_CELLS] * 40, m->d_pieces);
-        if (rc == MC_OK) rc = c->alloc((m->n_tiles + 1) * 8, m->d_tile_sbase);
-        if (rc != MC_OK) return rc;
-    }
     const Stuff S = make_stuff(m);
     const bool quality = !(m->flags & MC_OPT_SKIP_QUALITY);
     if (!c->tet_emit_attr_set) {

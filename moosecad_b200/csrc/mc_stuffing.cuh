@@ -7,6 +7,7 @@
 // piece; nothing depends on a traversal order.
 #pragma once
 #include "mc_lattice.cuh"
+#include "mc_shapes.hpp"
 #include "mc_vm.cuh"
 
 namespace mc {
@@ -100,6 +101,7 @@ __device__ __forceinline__ T pick4(T a, T b, T c, T d, int i) { return i == 0 ? 
 struct TetOut {
     int n;               // number of output tets (0..3)
     int kase;            // -2 not kept, -1 passed through, 0..6 trim case
+    int perm;            // dense index of the sorted node order (shape_perm_index), trim cases only
     bool ext_removed;    // all-zero tet dropped by the centroid test
     unsigned long long nodes;  // 5 bits per node code, node m of output tet q at bit 5 * (4 q + m)
     __device__ __forceinline__ int node(int q, int m) const { return (int)((nodes >> (5 * (4 * q + m))) & 31ull); }
@@ -155,6 +157,7 @@ __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNo
     out.n = 0;
     out.kase = -2;
     out.ext_removed = false;
+    out.perm = 0;
     out.nodes = 0ull;
     if (!KNOWN_KEPT && !tet_kept(L, c, t)) return;
     const double* p = tn.p;
@@ -213,6 +216,7 @@ __device__ void classify_tet(const Lattice& L, const Cell& c, int t, const TetNo
     else if (pb == 0.0) kase = 5;
     else kase = 6;
     out.kase = kase;
+    out.perm = shape_perm_index(ia, ib, ic);
     out.n = C_CASE_N[kase];
     unsigned long long nodes = 0ull;
     for (int q = 0; q < out.n; ++q) {

@@ -180,6 +180,30 @@ def test_plain_lattice_quality_paths_agree(scene, n, ctx):
     assert a["aspect_ratio"][0] <= a["aspect_ratio"][1] <= 1.0 + 1e-12
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,n", [("csg", 90), ("sphere", 61), ("xplicit", 48), ("cube", 33)])
+def test_shape_bytes_reproduce_the_classification(scene, n, ctx):
+    """The tet emission rebuilds the pieces of a trimmed tet from the one-byte shape k_classify_cells
+    recorded (trim case x sorted node order, mc_shapes.hpp).  MC_OPT_RECLASSIFY_EMIT makes it read the
+    field and run the 4-sort again: same tets, in the same places."""
+    if scene == "csg":
+        g = mc.Geom()
+        obj, res = scenes.synthetic_csg(g, 20, seed=3), 1.0 / n
+    elif scene == "sphere":
+        obj, res = luascad.eval(scenes.SPHERE_LUA)["sphere"].obj, 1.0 / n
+    elif scene == "cube":
+        obj, res = luascad.eval(scenes.CUBE_LUA)["cube"].obj, 1.0 / n
+    else:
+        obj, res = luascad.eval(scenes.XPLICIT_LUA)["xplicit"].obj, 15.0 / n
+    obj.backend.set_parameters(0.1, 1.0)
+    a = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx, allow_diverged=True).tessellate()
+    b = mc.IsosurfaceStuffing(obj, res, 0.2, ctx=ctx, flags=_lib.MC_OPT_RECLASSIFY_EMIT, allow_diverged=True).tessellate()
+    assert np.array_equal(a.elems(), b.elems())
+    assert np.array_equal(a.vertices().view(np.uint64), b.vertices().view(np.uint64))
+    assert a.stats()["stats"] == b.stats()["stats"]
+    assert sorted(a.boundary().sides()) == sorted(b.boundary().sides())
+
+
 @pytest.mark.parametrize("nprim,n", [(64, 72), (24, 100)])
 def test_tile_pruning_is_value_neutral(nprim, n, ctx):
     """The tile-specialised evaluator must produce the same bits as the full program at every
