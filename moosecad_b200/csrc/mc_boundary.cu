@@ -38,25 +38,83 @@ Stuff make_stuff(const mc_mesh* m);  // mc_mesher.cu
 
 // A cell as the boundary kernels see it: bits 0..15 its info word (CI_*), bits 16 + 8 t .. its five shape bytes.
 constexpr unsigned long long CELL_ALL_FULL = (unsigned long long)CI_ALL_FULL | (0x0101010101ull << 16);
-__device__ __forceinline__ unsigned long long cell_word(const Stuff& S, int64_t cx, int64_t cy, int64_t cz) {
-    const Lattice& L = S.L;
-    if (cx < 0 || cy < 0 || cz < 0 || cx >= (int64_t)L.nx || cy >= (int64_t)L.ny || cz >= (int64_t)L.nz) return 0ull;
-    if (cz < (int64_t)S.cl0 || cz >= (int64_t)S.cl1) return 0ull;  // never reached for neighbours of owned cells
-    const uint8_t cu = S.cuni[tile_of(S.g, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)];
-    if (cu == CU_EMPTY) return 0ull;
-    if (cu == CU_FULL) return CELL_ALL_FULL;
-    const size_t i = cidx(S, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-    const uint16_t ci = S.cinfo[i];
-    if (ci_count(ci) == 0u) return 0ull;
-    if (ci & CI_FULL) return CELL_ALL_FULL;
-    return (unsigned long long)ci | (S.cshape[i] << 16);
-}
 __device__ __forceinline__ uint32_t cell_shape(unsigned long long w, int t) { return (uint32_t)(w >> (16 + 8 * t)) & 0xffu; }
 
 // The words of a tile's cells with a one-cell halo are staged in shared memory (BH^3 entries, 0 = nothing
 // there / outside the lattice); `at` = index of the cell in that box.
 constexpr int BH = (int)TS + 2;
-constexpr size_t BND_SMEM = (size_t)BH * BH * BH * 8 /*cell words*/ + (size_t)5 * TILE_POINTS * 2 /*masks*/ + (size_t)TILE_POINTS * 2 /*list*/;
+constexpr int BH3 = BH * BH * BH;
+// Stage the cell words of tile (X0, Y0, Z0) + halo.  Two rounds of independent loads (every thread issues a
+// batch before it uses any): the info words of all cells, then the shape bytes of the surface cells among them.
+// s_cu[27]: class (CU_*) of the 27 cell tiles around, CU_EMPTY where there is none.
+__device__ __forceinline__ void stage_cell_words(const Stuff& S, uint32_t tile, uint32_t X0, uint32_t Y0, uint32_t Z0,
+                                                 unsigned long long* __restrict__ s_cell, uint8_t* __restrict__ s_cu) {
+    const Lattice& L = S.L;
+    if (threadIdx.x < 27) {
+        const int dx = (int)(threadIdx.x % 3u) - 1, dy = (int)((threadIdx.x / 3u) % 3u) - 1, dz = (int)(threadIdx.x / 9u) - 1;
+        const int tix = (int)(tile % S.g.ntx) + dx, tiy = (int)((tile / S.g.ntx) % S.g.nty) + dy,
+                  tiz = (int)(tile / ((uint64_t)S.g.ntx * S.g.nty)) + dz;
+        uint8_t cu = CU_EMPTY;
+        if (tix >= 0 && tiy >= 0 && tiz >= 0 && tix < (int)S.g.ntx && tiy < (int)S.g.nty && tiz < (int)S.g.ntz)
+            cu = S.cuni[((size_t)tiz * S.g.nty + tiy) * S.g.ntx + tix];
+        s_cu[threadIdx.x] = cu;
+    }
+    __syncthreads();
+    constexpr int BATCH = 4;
+    // round 1: info words
+    for (int base = (int)threadIdx.x; base < BH3; base += BATCH * TILE_THREADS) {
+        uint16_t ci[BATCH];
+        uint8_t cu[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const int idx = base + b * TILE_THREADS;
+            ci[b] = 0;
+            cu[b] = CU_EMPTY;
+            if (idx < BH3) {
+                const int lx = idx % BH - 1, ly = (idx / BH) % BH - 1, lz = idx / (BH * BH) - 1;
+                const int64_t cx = (int64_t)X0 + lx, cy = (int64_t)Y0 + ly, cz = (int64_t)Z0 + lz;
+                // (cells outside the classified layers are never reached for neighbours of owned cells)
+                if (cx >= 0 && cy >= 0 && cx < (int64_t)L.nx && cy < (int64_t)L.ny && cz >= (int64_t)S.cl0 && cz < (int64_t)S.cl1) {
+                    cu[b] = s_cu[((lz < 0 ? 0 : (lz >= (int)TS ? 2 : 1)) * 3 + (ly < 0 ? 0 : (ly >= (int)TS ? 2 : 1))) * 3 +
+                                 (lx < 0 ? 0 : (lx >= (int)TS ? 2 : 1))];
+                    if (cu[b] == CU_ACTIVE) ci[b] = S.cinfo[cidx(S, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz)];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const int idx = base + b * TILE_THREADS;
+            if (idx >= BH3) continue;
+            unsigned long long w = 0ull;
+            if (cu[b] == CU_FULL || (ci[b] & CI_FULL)) w = CELL_ALL_FULL;
+            else if (ci_count(ci[b]) != 0u) w = (unsigned long long)ci[b];
+            s_cell[idx] = w;
+        }
+    }
+    __syncthreads();
+    // round 2: shape bytes of the surface cells (a word without shape bytes so far)
+    for (int base = (int)threadIdx.x; base < BH3; base += BATCH * TILE_THREADS) {
+        unsigned long long sh[BATCH];
+        bool need[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const int idx = base + b * TILE_THREADS;
+            sh[b] = 0ull;
+            need[b] = false;
+            if (idx < BH3) {
+                const unsigned long long w = s_cell[idx];
+                need[b] = w != 0ull && (w >> 16) == 0ull;
+                if (need[b]) {
+                    const int lx = idx % BH - 1, ly = (idx / BH) % BH - 1, lz = idx / (BH * BH) - 1;
+                    sh[b] = S.cshape[cidx(S, X0 + (uint32_t)lx, Y0 + (uint32_t)ly, Z0 + (uint32_t)lz)];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b)
+            if (need[b]) s_cell[base + b * TILE_THREADS] |= sh[b] << 16;
+    }
+}
 
 // Boundary sides of the pieces of lattice tet t (shape A != 0) of the cell at `at` (mirroring class p): bit 4 q + s.
 __device__ __forceinline__ uint32_t tet_boundary_mask(const ShapeTables* __restrict__ T, const unsigned long long* __restrict__ s_cell, int at,
@@ -88,68 +146,79 @@ __device__ __forceinline__ uint32_t tet_boundary_mask(const ShapeTables* __restr
     return ~odd & ~notlast & valid;   // the other occurrences are even in number and none comes later
 }
 
-// A cell tile takes part when it can hold a boundary side: any tile that is not uniformly full /
-// empty, and full tiles that touch a tile that is not full (or the lattice border)
+// A cell tile takes part when it can hold a boundary side: any tile that is not uniformly full / empty, and
+// full tiles on the border of the lattice.  A full tile elsewhere has none: all 17^3 corner points of its cells
+// are strictly negative and un-warped, so the lattice tet across any of its lattice faces shares three strictly
+// negative nodes with it — it was kept, it is not all-zero (no exterior test), and whatever trim_spikes did to
+// it (nothing, or case 2 when the fourth node is positive) the shared face is a whole face of one of its pieces.
 __device__ __forceinline__ bool boundary_tile_candidate(const Stuff& S, uint64_t tile, uint8_t cu) {
     if (cu == CU_EMPTY) return false;
     if (cu == CU_ACTIVE) return true;
-    const int tix = (int)(tile % S.g.ntx), tiy = (int)((tile / S.g.ntx) % S.g.nty), tiz = (int)(tile / ((uint64_t)S.g.ntx * S.g.nty));
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, tile, X0, Y0, Z0);
-    if (X0 == 0u || Y0 == 0u || Z0 == 0u || X0 + TS >= S.L.nx || Y0 + TS >= S.L.ny || Z0 + TS >= S.L.nz) return true;
-    const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
-    for (int f = 0; f < 6; ++f) {
-        const int x = tix + d[f][0], y = tiy + d[f][1], z = tiz + d[f][2];
-        if (x < 0 || y < 0 || z < 0 || x >= (int)S.g.ntx || y >= (int)S.g.nty || z >= (int)S.g.ntz) return true;
-        if (S.cuni[((size_t)z * S.g.nty + y) * S.g.ntx + x] != CU_FULL) return true;
-    }
-    return false;
+    return X0 == 0u || Y0 == 0u || Z0 == 0u || X0 + TS >= S.L.nx || Y0 + TS >= S.L.ny || Z0 + TS >= S.L.nz;
 }
 
-// the cell tiles that can hold a boundary side -> work list
-static __global__ void k_boundary_tiles(Stuff S, uint64_t ntiles, uint32_t* __restrict__ list, unsigned long long* __restrict__ n_list) {
+// The cell tiles that can hold a boundary side, as an ORDERED work list (flag, scan, scatter): the sides are
+// written tile by tile in list order, so the list decides their order.
+static __global__ void k_boundary_tile_flags(Stuff S, uint64_t ntiles, unsigned long long* __restrict__ flag) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, t, X0, Y0, Z0);
     const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (X0 >= S.L.nx || Y0 >= S.L.ny || zhi <= zlo || !boundary_tile_candidate(S, t, S.cuni[t])) return;
-    list[atomicAdd(n_list, 1ull)] = (uint32_t)t;
+    flag[t] = (X0 >= S.L.nx || Y0 >= S.L.ny || zhi <= zlo || !boundary_tile_candidate(S, t, S.cuni[t])) ? 0ull : 1ull;
+}
+static __global__ void k_boundary_tile_list(uint64_t ntiles, const unsigned long long* __restrict__ flag,
+                                            const unsigned long long* __restrict__ pos, uint32_t* __restrict__ list) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles && flag[t]) list[pos[t]] = (uint32_t)t;
 }
 
-// One listed tile at a time: the boundary sides of every lattice tet of the tile's owned cells as a 12-bit
-// mask (bit 4 q + s) in shared memory.  Only cells next to the surface do any work: the cells that are not
-// full, and full cells with a neighbour that is not; their lattice tets are dealt to the threads one by one.
-//   EMIT = false: the tile's number of sides -> tile_tot[tile]
-//   EMIT = true:  the masks are expanded into (elem, side) pairs in emission order (tiles, x-rows of cells,
-//                 lattice tets, pieces, sides), so the output is sorted by (elem, side); tile_base[tile] =
-//                 index of the tile's first side.  (The masks are computed again: a few look-ups per tet.)
-template <bool EMIT>
-__global__ void __launch_bounds__(TILE_THREADS)
+constexpr size_t BND_SMEM = (size_t)BH3 * 8 /*cell words*/ + (size_t)TILE_POINTS * 2 /*list*/ + (size_t)5 * TILE_POINTS * 2 /*masks*/;
+
+// ONE pass over the listed tiles, a tile at a time per block:
+//   1. the boundary sides of every lattice tet of the tile's owned cells as a 12-bit mask (bit 4 q + s) in
+//      shared memory.  Only cells next to the surface do any work: the cells that are not full, and full cells
+//      with a neighbour that is not; their lattice tets are dealt to the threads one by one;
+//   2. room for the tile's sides is taken from a running counter (nobody waits for anybody);
+//   3. the masks are expanded into (elem, side) pairs in emission order (x-rows of cells, lattice tets, pieces,
+//      sides) at that place of a STAGING buffer; slot_first / slot_count record where.
+// k_boundary_order then copies the tiles' runs into list order (a scan of the counts gives the places), so that
+// the result is sorted by (elem, side) whatever order the blocks ran in.
+// `capacity` sides fit the staging buffer; a tile that would run over it is counted but not written (the host
+// sees total > capacity and repeats the pass with the exact size).
+static __global__ void __launch_bounds__(TILE_THREADS)
 k_boundary_sides(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned long long* __restrict__ n_list,
-                 unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ tile_tot,
-                 const unsigned long long* __restrict__ tile_base, unsigned long long tet_base, unsigned long long* __restrict__ sides) {
+                 unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ slot_first,
+                 unsigned long long* __restrict__ slot_count, unsigned long long capacity,
+                 unsigned long long* __restrict__ ctl_total, unsigned long long tet_base, unsigned long long* __restrict__ sides) {
     extern __shared__ __align__(16) unsigned char bnd_smem[];
     unsigned long long* s_cell = reinterpret_cast<unsigned long long*>(bnd_smem);
-    uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_cell + BH * BH * BH);
-    uint16_t* s_list = s_mask + 5 * TILE_POINTS;
-    __shared__ unsigned long long s_acc;
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_cell + BH3);
+    uint16_t* s_mask = s_list + TILE_POINTS;
+    __shared__ uint8_t s_cu[27];
+    __shared__ unsigned long long s_item, s_base;
     __shared__ uint32_t s_n;
     __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_rowsides[TILE_THREADS];   // sides of every x-row of cells
     const Lattice& L = S.L;
     const ShapeTables* __restrict__ T = S.shapes;
-    uint32_t tile;
-    while (next_tile(tile_list, n_list, cursor, tile)) {
+    for (;;) {
+        __syncthreads();  // the previous tile is done with shared memory
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1ull);
+        __syncthreads();
+        const unsigned long long slot = s_item, nslots = *n_list;
+        if (slot >= nslots) break;
+        const uint32_t tile = tile_list[slot];
         uint32_t X0, Y0, Z0;
         tile_origin(S.g, tile, X0, Y0, Z0);
         const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
         if (threadIdx.x == 0) s_n = 0u;
+        s_rowsides[threadIdx.x] = 0u;
         // the tile's cells and the cells around it
-        for (int idx = (int)threadIdx.x; idx < BH * BH * BH; idx += TILE_THREADS) {
-            const int lx = idx % BH - 1, ly = (idx / BH) % BH - 1, lz = idx / (BH * BH) - 1;
-            s_cell[idx] = cell_word(S, (int64_t)X0 + lx, (int64_t)Y0 + ly, (int64_t)Z0 + lz);
-        }
-        if (EMIT) {
+        stage_cell_words(S, tile, X0, Y0, Z0, s_cell, s_cu);
+        {
             uint4* mz = reinterpret_cast<uint4*>(s_mask);
             for (uint32_t i = threadIdx.x; i < 5u * TILE_POINTS * 2u / 16u; i += TILE_THREADS) mz[i] = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -168,7 +237,6 @@ k_boundary_sides(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
         }
         __syncthreads();
         const uint32_t ncand = s_n;
-        unsigned long long mine = 0ull;
         for (uint32_t w = threadIdx.x; w < 5u * ncand; w += TILE_THREADS) {
             const uint32_t j = s_list[w / 5u], t = w % 5u;
             const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
@@ -178,51 +246,62 @@ k_boundary_sides(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
             const uint32_t p = ((X0 + lx) & 1u) | (((Y0 + ly) & 1u) << 1) | (((Z0 + lz) & 1u) << 2);
             const uint32_t mask = tet_boundary_mask(T, s_cell, at, p, (int)t, A);
             if (mask) {
-                if (EMIT) s_mask[t * TILE_POINTS + j] = (uint16_t)mask;
-                mine += (unsigned long long)__popc(mask);
+                s_mask[t * TILE_POINTS + j] = (uint16_t)mask;
+                atomicAdd(&s_rowsides[j >> 4], (uint32_t)__popc(mask));
             }
-        }
-        if (!EMIT) {
-            const unsigned long long tot = block_sum(mine, &s_acc);
-            if (threadIdx.x == 0) tile_tot[tile] = tot;
-            continue;
         }
         __syncthreads();
         // every thread owns one x-row of cells: its tets and sides, then the offsets from one block scan
         const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
         const bool row_owned = Y0 + ly < L.ny && Z0 + lz >= zlo && Z0 + lz < zhi;
-        const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
+        const uint32_t nx_row = (row_owned && ncand != 0u) ? min(TS, L.nx - X0) : 0u;
         const int at0 = (int)((lz + 1u) * BH + (ly + 1u)) * BH + 1;
-        uint32_t ntet = 0, nside = 0;
-        for (uint32_t i = 0; i < nx_row; ++i) {
-            const uint32_t j = threadIdx.x * TS + i;
-            ntet += ci_count((uint16_t)s_cell[at0 + (int)i]);
-#pragma unroll
-            for (uint32_t t = 0; t < 5u; ++t) nside += (uint32_t)__popc((uint32_t)s_mask[t * TILE_POINTS + j]);
-        }
+        uint32_t ntet = 0;
+        const uint32_t nside = s_rowsides[threadIdx.x];
+        for (uint32_t i = 0; i < nx_row; ++i) ntet += ci_count((uint16_t)s_cell[at0 + (int)i]);
         uint32_t tot;
         const uint32_t ex = block_exscan(ntet | (nside << 16), &tot, s_scan);  // <= 61440 tets, sides are far fewer
-        if ((tot >> 16) == 0u) continue;
+        const unsigned long long tile_sides = tot >> 16;
+        if (threadIdx.x == 0) {
+            const unsigned long long base = tile_sides ? atomicAdd(ctl_total, tile_sides) : 0ull;
+            s_base = base;
+            slot_first[slot] = base;
+            slot_count[slot] = base + tile_sides <= capacity ? tile_sides : 0ull;   // (low half: scanned by scan_tiles)
+        }
+        __syncthreads();
+        if (tile_sides == 0ull || s_base + tile_sides > capacity) continue;
         uint64_t elem = tet_base + S.ttbase[tile] + (ex & 0xffffu);
-        uint64_t o = tile_base[tile] + (ex >> 16);
+        uint64_t o = s_base + (ex >> 16);
         for (uint32_t i = 0; i < nx_row && nside != 0u; ++i) {
             const uint32_t j = threadIdx.x * TS + i;
             const uint16_t ci = (uint16_t)s_cell[at0 + (int)i];
             for (uint32_t t = 0; t < 5u; ++t) {
                 const uint32_t mask = s_mask[t * TILE_POINTS + j];
-                for (uint32_t b = 0; b < 12u && mask; ++b)
-                    if ((mask >> b) & 1u) { sides[2 * o] = elem + (b >> 2); sides[2 * o + 1] = b & 3u; ++o; }
+                for (uint32_t bb = 0; bb < 12u && mask; ++bb)
+                    if ((mask >> bb) & 1u) { reinterpret_cast<ulonglong2*>(sides)[o] = make_ulonglong2(elem + (bb >> 2), bb & 3u); ++o; }
                 elem += ci_tet_n(ci, (int)t);
             }
         }
     }
 }
 
+// the tiles' runs of sides, from where they were written to their place in list order
+static __global__ void __launch_bounds__(256)
+k_boundary_order(uint64_t nslots_max, const unsigned long long* __restrict__ n_list, const unsigned long long* __restrict__ slot_first,
+                 const unsigned long long* __restrict__ slot_count, const unsigned long long* __restrict__ slot_pos,
+                 const ulonglong2* __restrict__ staged, ulonglong2* __restrict__ sides) {
+    const uint64_t nslots = min((uint64_t)*n_list, nslots_max);
+    for (uint64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const unsigned long long n = slot_count[slot], src = slot_first[slot], dst = slot_pos[slot];
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) sides[dst + i] = staged[src + i];
+    }
+}
+
 // ---- side-sets ----------------------------------------------------------------------------------
 // src/main.rs:87-106: a surface side belongs to a boundary object's side-set iff all three nodes satisfy
 // |approx_value(p, EPSILON)| <= EPSILON.  The object is evaluated once per surface VERTEX:
-//   1. k_mark_side_nodes: flag the nodes of the surface sides (own vertices, and the slice of the rank
-//      below's vertices a slab may reference)          2. k_list_flagged: gather them into a dense list
+//   1 + 2. k_mark_side_nodes: flag the nodes of the surface sides (own vertices, and the slice of the rank
+//      below's vertices a slab may reference); whoever flags a vertex first appends it to a dense list
 //   3. k_eval_side_nodes: value at every listed vertex -> flag 2 (on the object) or 1
 //   4. k_sideset_select: sides whose three nodes carry flag 2, counted per block, scanned, written in order
 template <typename IndexT>
@@ -239,31 +318,24 @@ __device__ __forceinline__ long long flag_index(long long gid, long long vertex_
     return (lid >= 0 && lid < lower_count) ? n_verts + lid : -1;
 }
 
+// list != null: the thread that flags a vertex first (claimed through the aligned 32-bit word of its flag byte)
+// also appends it to the list of surface vertices (any order), *count = its length
 template <typename IndexT>
 __global__ void k_mark_side_nodes(const IndexT* __restrict__ tets, unsigned long long tet_base,
                                   const unsigned long long* __restrict__ sides, uint64_t n, long long vertex_base,
-                                  long long n_verts, long long lower_first, long long lower_count, uint8_t* __restrict__ flag) {
+                                  long long n_verts, long long lower_first, long long lower_count, uint8_t* __restrict__ flag,
+                                  unsigned long long* __restrict__ list, unsigned long long* __restrict__ count) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const long long f = flag_index(side_node(tets, tet_base, sides, i, k), vertex_base, n_verts, lower_first, lower_count);
-        if (f >= 0 && flag[f] == 0) flag[f] = 1;
+        if (f < 0 || flag[f] != 0) continue;
+        if (list == nullptr) { flag[f] = 1; continue; }
+        const unsigned bit = 1u << (8u * (unsigned)(f & 3));
+        const unsigned old = atomicOr(reinterpret_cast<unsigned*>(flag + (f & ~3ll)), bit);
+        if (!(old & bit)) list[atomicAdd(count, 1ull)] = (unsigned long long)f;
     }
-}
-
-static __global__ void k_list_flagged(const uint8_t* __restrict__ flag, uint64_t n, unsigned long long* __restrict__ list,
-                                      unsigned long long* __restrict__ count) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = i < n && flag[i] != 0;
-    const unsigned b = __ballot_sync(0xffffffffu, on);
-    if (b == 0u) return;
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs((int)b) - 1;
-    unsigned long long base = 0ull;
-    if ((int)lane == leader) base = atomicAdd(count, (unsigned long long)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (on) list[base + __popc(b & ((1u << lane) - 1u))] = i;
 }
 
 static __global__ void __launch_bounds__(256)
@@ -338,19 +410,21 @@ int compute_boundary(mc_mesh* m) {
     if (L.nx >= (1u << 21) || L.ny >= (1u << 21) || L.nz >= (1u << 21))
         return fail(MC_ERR_LIMIT, "Mesh::boundary: more than 2^21 cells along an axis");
     if (!c->boundary_attr_set) {
-        MC_CUDA(cudaFuncSetAttribute(k_boundary_sides<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BND_SMEM));
-        MC_CUDA(cudaFuncSetAttribute(k_boundary_sides<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BND_SMEM));
+        MC_CUDA(cudaFuncSetAttribute(k_boundary_sides, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BND_SMEM));
         c->boundary_attr_set = true;
     }
     Scratch sc(c);
     MC_CUDA(cudaEventCreate(&sc.e0));
     MC_CUDA(cudaEventCreate(&sc.e1));
     MC_CUDA(cudaEventRecord(sc.e0, s));
-    DevBuf ftot, fbase, dctl, dlist;
-    int rc = sc.alloc((m->n_tiles + 1) * 8, ftot);
-    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, fbase);
-    if (rc == MC_OK) rc = sc.alloc(8 * 8, dctl);   // [0..1] totals, [2] list length, [3] / [4] cursors
+    DevBuf fflag, fpos, dctl, dlist, sfirst, scount, spos, staged;
+    int rc = sc.alloc((m->n_tiles + 1) * 8, fflag);
+    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, fpos);
+    if (rc == MC_OK) rc = sc.alloc(8 * 8, dctl);   // [0] number of sides, [2..3] list length (scan totals), [4] cursor, [6..7] scan totals
     if (rc == MC_OK) rc = sc.alloc(std::max<uint64_t>(m->n_tiles, 1) * 4, dlist);
+    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, sfirst);
+    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, scount);
+    if (rc == MC_OK) rc = sc.alloc((m->n_tiles + 1) * 8, spos);
     if (rc != MC_OK) return rc;
     unsigned long long* ctl = (unsigned long long*)dctl.p;
     const Stuff S = make_stuff(m);
@@ -359,29 +433,52 @@ int compute_boundary(mc_mesh* m) {
     m->have_h_sides = false;
     c->release(m->d_sides);
     if (m->n_tiles > 0 && m->n_tets > 0) {
+        const unsigned tb = (unsigned)((m->n_tiles + 255) / 256);
+        k_boundary_tile_flags<<<tb, 256, 0, s>>>(S, m->n_tiles, (unsigned long long*)fflag.p);
         MC_CUDA(cudaMemsetAsync(dctl.p, 0, 64, s));
-        MC_CUDA(cudaMemsetAsync(ftot.p, 0, (m->n_tiles + 1) * 8, s));
-        k_boundary_tiles<<<(unsigned)((m->n_tiles + 255) / 256), 256, 0, s>>>(S, m->n_tiles, (uint32_t*)dlist.p, ctl + 2);
-        const unsigned grid = (unsigned)std::min<uint64_t>(m->n_tiles, (uint64_t)c->sm_count * 2);  // 2 blocks of BND_SMEM per SM
-        k_boundary_sides<false><<<grid, TILE_THREADS, BND_SMEM, s>>>(S, (const uint32_t*)dlist.p, ctl + 2, ctl + 3, (unsigned long long*)ftot.p,
-                                                                    nullptr, 0ull, nullptr);
-        c->launches += 2;
-        MC_CUDA(cudaGetLastError());
-        rc = scan_tiles(c, ftot.p, m->n_tiles, fbase.p, nullptr, m->d_scan_sums.p, ctl);
+        rc = scan_tiles(c, fflag.p, m->n_tiles, fpos.p, nullptr, m->d_scan_sums.p, ctl + 2);
         if (rc != MC_OK) return rc;
-        unsigned long long h[2];
-        MC_CUDA(cudaMemcpyAsync(h, ctl, 16, cudaMemcpyDeviceToHost, s));
-        MC_CUDA(cudaStreamSynchronize(s));
-        m->n_sides = h[0];
+        k_boundary_tile_list<<<tb, 256, 0, s>>>(m->n_tiles, (const unsigned long long*)fflag.p, (const unsigned long long*)fpos.p, (uint32_t*)dlist.p);
+        c->launches += 2;
+        // Room for the sides: a generous guess from what the host knows (surface cells, border of the slab);
+        // the pass counts exactly, and is repeated with the exact size in the rare case the guess was short.
+        const uint64_t nl = m->c1 - m->c0;
+        uint64_t capacity = std::max<uint64_t>(1ull << 20, 8ull * m->counters[CN_SURF_CELLS] +
+                                                           12ull * ((uint64_t)L.nx * L.ny + ((uint64_t)L.nx + L.ny) * nl));
+        capacity = std::min<uint64_t>(capacity, 4ull * m->n_tets);
+        if (const char* cap = std::getenv("MC_BOUNDARY_CAPACITY")) capacity = std::max<long long>(1, std::atoll(cap));  // tests: force the second pass
+        const unsigned grid = (unsigned)std::min<uint64_t>(m->n_tiles, (uint64_t)c->sm_count * 2);  // 2 blocks of BND_SMEM fit an SM
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            rc = c->alloc(capacity * 16, staged);
+            if (rc != MC_OK) return rc;
+            MC_CUDA(cudaMemsetAsync(scount.p, 0, (m->n_tiles + 1) * 8, s));
+            MC_CUDA(cudaMemsetAsync(ctl, 0, 8, s));
+            MC_CUDA(cudaMemsetAsync(ctl + 4, 0, 8, s));
+            k_boundary_sides<<<grid, TILE_THREADS, BND_SMEM, s>>>(S, (const uint32_t*)dlist.p, ctl + 2, ctl + 4, (unsigned long long*)sfirst.p,
+                                                                 (unsigned long long*)scount.p, capacity, ctl, m->tet_base,
+                                                                 (unsigned long long*)staged.p);
+            c->launches++;
+            MC_CUDA(cudaGetLastError());
+            unsigned long long total = 0;
+            MC_CUDA(cudaMemcpyAsync(&total, ctl, 8, cudaMemcpyDeviceToHost, s));
+            MC_CUDA(cudaStreamSynchronize(s));
+            m->n_sides = total;
+            if (total <= capacity) break;
+            if (attempt == 1) { c->release(staged); return fail(MC_ERR_STATE, "Mesh::boundary: the side count changed between two passes"); }
+            c->release(staged);
+            capacity = total;
+        }
         if (m->n_sides) {
             rc = c->alloc(m->n_sides * 16, m->d_sides);
-            if (rc != MC_OK) return rc;
-            k_boundary_sides<true><<<grid, TILE_THREADS, BND_SMEM, s>>>(S, (const uint32_t*)dlist.p, ctl + 2, ctl + 4, nullptr,
-                                                                       (const unsigned long long*)fbase.p, m->tet_base,
-                                                                       (unsigned long long*)m->d_sides.p);
+            if (rc == MC_OK) rc = scan_tiles(c, scount.p, m->n_tiles, spos.p, nullptr, m->d_scan_sums.p, ctl + 6);
+            if (rc != MC_OK) { c->release(staged); return rc; }
+            k_boundary_order<<<(unsigned)std::min<uint64_t>(m->n_tiles, (uint64_t)c->sm_count * 16), 256, 0, s>>>(
+                m->n_tiles, ctl + 2, (const unsigned long long*)sfirst.p, (const unsigned long long*)scount.p,
+                (const unsigned long long*)spos.p, (const ulonglong2*)staged.p, (ulonglong2*)m->d_sides.p);
             c->launches++;
             MC_CUDA(cudaGetLastError());
         }
+        sc.bufs.push_back(&staged);   // released with the other scratch buffers (after the event below)
     }
     MC_CUDA(cudaEventRecord(sc.e1, s));
     MC_CUDA(cudaEventSynchronize(sc.e1));
@@ -422,17 +519,15 @@ static int sideset_impl(mc_mesh* m, const Program& p, SideSetDev& out) {
     int rc = MC_OK;
     // 1 + 2: the surface vertices, once per mesh
     if (!m->d_side_nodes.p) {
-        rc = c->alloc(std::max<uint64_t>(nflag, 1), m->d_side_flag);
+        rc = c->alloc(nflag + 4, m->d_side_flag);
         if (rc == MC_OK) rc = c->alloc(std::max<uint64_t>(std::min<uint64_t>(3 * ns, nflag), 1) * 8 + 8, m->d_side_nodes);
         if (rc != MC_OK) return rc;
-        MC_CUDA(cudaMemsetAsync(m->d_side_flag.p, 0, std::max<uint64_t>(nflag, 1), s));
+        MC_CUDA(cudaMemsetAsync(m->d_side_flag.p, 0, nflag + 4, s));
         MC_CUDA(cudaMemsetAsync(m->d_side_nodes.p, 0, 8, s));
         k_mark_side_nodes<IndexT><<<nb, 256, 0, s>>>(tets, m->tet_base, sides, ns, (long long)m->vertex_base, nv, lf, lc,
-                                                     (uint8_t*)m->d_side_flag.p);
-        k_list_flagged<<<(unsigned)((nflag + 255) / 256), 256, 0, s>>>((const uint8_t*)m->d_side_flag.p, nflag,
-                                                                      (unsigned long long*)m->d_side_nodes.p + 1,
-                                                                      (unsigned long long*)m->d_side_nodes.p);
-        c->launches += 2;
+                                                     (uint8_t*)m->d_side_flag.p, (unsigned long long*)m->d_side_nodes.p + 1,
+                                                     (unsigned long long*)m->d_side_nodes.p);
+        c->launches += 1;
         MC_CUDA(cudaGetLastError());
     }
     // 3: the boundary object at every surface vertex
@@ -560,9 +655,9 @@ int compute_surface(mc_mesh* m, mc_surface* out) {
     MC_CUDA(cudaMemsetAsync(flag.p, 0, std::max<uint64_t>(nv, 1), s));
     const unsigned long long* sides = (const unsigned long long*)m->d_sides.p;
     if (m->index_bytes == 4)
-        k_mark_side_nodes<uint32_t><<<nbs, 256, 0, s>>>((const uint32_t*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p);
+        k_mark_side_nodes<uint32_t><<<nbs, 256, 0, s>>>((const uint32_t*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p, nullptr, nullptr);
     else
-        k_mark_side_nodes<unsigned long long><<<nbs, 256, 0, s>>>((const unsigned long long*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p);
+        k_mark_side_nodes<unsigned long long><<<nbs, 256, 0, s>>>((const unsigned long long*)m->d_tets.p, m->tet_base, sides, ns, 0, (long long)nv, 0, 0, (uint8_t*)flag.p, nullptr, nullptr);
     k_flag_prefix<<<nbv, 256, 0, s>>>((const uint8_t*)flag.p, nv, (unsigned long long*)bcnt.p);
     c->launches += 2;
     MC_CUDA(cudaGetLastError());

@@ -631,6 +631,21 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
             const Cell c = make_cell(cx, cy, cz);
             const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
+            // sign classes of the four nodes first: a tet whose nodes are all strictly negative passes through
+            // untouched, one whose raw values are all positive was never kept — neither needs the field
+            uint8_t andc = 3;
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+                uint32_t X, Y, Z;
+                corner_xyz(c, (int)C_TETS[t][nn], X, Y, Z);
+                andc &= s_cls[((Z - Z0) * H + (Y - Y0)) * H + (X - X0)];
+            }
+            if (andc & 2) continue;   // not kept by cut_lattice
+            if (andc & 1) {
+                atomicOr(&s_ci[q], (1u << (2u * t)) | (1u << (16u + t)));
+                s_shape[q][t] = (uint8_t)SHAPE_WHOLE;
+                continue;
+            }
             TetNodes tn;
             load_tet(L, c, (int)t, tn);
             TetOut to;
@@ -1364,29 +1379,56 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         s_tvu[q] = vu;
     }
     __syncthreads();
-    for (int idx = (int)threadIdx.x; idx < TE_NP; idx += TILE_THREADS) {
-        const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
-        const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-        const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
-        IndexT gid = 0;
-        uint16_t mask = 0;
-        const uint8_t vu = s_tvu[q];
-        if (X < L.NX && Y < L.NY && Z <= L.pz1 && vu != VU_POS) {
-            if (S.lower_table != nullptr && Z == S.c0) {
-                const unsigned long long e = S.lower_table[(size_t)Y * L.NX + X];
-                mask = (uint16_t)(e & 0xffffull);
-                gid = (IndexT)(e >> 16);
-            } else if (vu == VU_NEG) {
-                const TileBox& b = s_tb[q];
-                mask = VM_USED;
-                gid = (IndexT)(s_tbase[q] + (long long)(((Z - b.zlo) * b.nyt + (Y - b.Y0)) * b.nxt + (X - b.X0)));
-            } else {
-                const size_t pi = pidx(L, X, Y, Z);
-                mask = S.vmask[pi];
-                gid = (IndexT)(s_tbase[q] + (long long)S.vloc[pi]);
+    // (batches of independent loads: every thread issues TE_BATCH points' loads before it uses any)
+    constexpr int TE_BATCH = 4;
+    for (int base = (int)threadIdx.x; base < TE_NP; base += TE_BATCH * TILE_THREADS) {
+        unsigned long long tab[TE_BATCH];
+        uint16_t vm[TE_BATCH], vl[TE_BATCH];
+        uint8_t kind[TE_BATCH];   // 0 nothing, 1 lower table, 2 interior tile, 3 surface tile
+#pragma unroll
+        for (int b = 0; b < TE_BATCH; ++b) {
+            const int idx = base + b * TILE_THREADS;
+            kind[b] = 0; tab[b] = 0ull; vm[b] = 0; vl[b] = 0;
+            if (idx >= TE_NP) continue;
+            const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
+            const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
+            const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
+            const uint8_t vu = s_tvu[q];
+            if (X < L.NX && Y < L.NY && Z <= L.pz1 && vu != VU_POS) {
+                if (S.lower_table != nullptr && Z == S.c0) {
+                    kind[b] = 1;
+                    tab[b] = S.lower_table[(size_t)Y * L.NX + X];
+                } else if (vu == VU_NEG) {
+                    kind[b] = 2;
+                } else {
+                    kind[b] = 3;
+                    const size_t pi = pidx(L, X, Y, Z);
+                    vm[b] = S.vmask[pi];
+                    vl[b] = S.vloc[pi];
+                }
             }
         }
-        s_gid[idx] = gid; s_mask[idx] = mask;
+#pragma unroll
+        for (int b = 0; b < TE_BATCH; ++b) {
+            const int idx = base + b * TILE_THREADS;
+            if (idx >= TE_NP) continue;
+            const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
+            const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
+            IndexT gid = 0;
+            uint16_t mask = 0;
+            if (kind[b] == 1) {
+                mask = (uint16_t)(tab[b] & 0xffffull);
+                gid = (IndexT)(tab[b] >> 16);
+            } else if (kind[b] == 2) {
+                const TileBox& tbx = s_tb[q];
+                mask = VM_USED;
+                gid = (IndexT)(s_tbase[q] + (long long)((((Z0 + lz) - tbx.zlo) * tbx.nyt + ((Y0 + ly) - tbx.Y0)) * tbx.nxt + ((X0 + lx) - tbx.X0)));
+            } else if (kind[b] == 3) {
+                mask = vm[b];
+                gid = (IndexT)(s_tbase[q] + (long long)vl[b]);
+            }
+            s_gid[idx] = gid; s_mask[idx] = mask;
+        }
     }
     // 2. per-cell info + offsets: every thread takes one x-row of 16 cells (consecutive in the
     //    output order), one block scan of the row totals gives the offsets of the output tets

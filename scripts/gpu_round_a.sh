@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     --log-file gpurun_out/${TAG}_launches_csg64_1024.csv python scripts/profile_step.py csg64_1024 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 echo "ncu launches rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:'k_warp_codes|k_classify_cells|k_vertex_count|k_vertex_emit|k_tet_emit|k_bisect_edges_tiled|k_sdf_field_tiled|k_tile_decide|k_subbox_decide|k_tet_quality_list|k_quality_mark|k_boundary_sides|k_sideset|k_eval_side|k_mark_side|k_list_flagged' \
+    -k regex:'k_warp_codes|k_classify_cells|k_vertex_count|k_vertex_emit|k_tet_emit|k_bisect_edges_tiled|k_sdf_field_tiled|k_tile_decide|k_subbox_decide|k_tet_quality_list|k_quality_mark|k_boundary_sides|k_sideset|k_eval_side|k_mark_side' \
     -o /tmp/${TAG}_hot -f python scripts/profile_step.py csg64_1024 > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ncu -i /tmp/${TAG}_hot.ncu-rep --page raw --csv > gpurun_out/${TAG}_hot_raw.csv 2>/dev/null

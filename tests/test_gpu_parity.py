@@ -436,3 +436,20 @@ def test_to_boundary(script, res, oracle, ctx):
     assert t.shape == otris.shape
     assert len(v) == np.unique(otris).size and np.unique(t).size == len(v) and int(t.max()) == len(v) - 1   # compact
     assert np.array_equal(_canonical_tris(v, t), _canonical_tris(ov, otris))
+
+
+@pytest.mark.gpu
+def test_boundary_capacity_overflow_repeats_the_pass(ctx, monkeypatch):
+    """Mesh::boundary writes the sides in one pass into a buffer sized from a guess; when the guess is short
+    the pass only counts and is repeated with the exact size (forced here through MC_BOUNDARY_CAPACITY)."""
+    obj = luascad.eval(scenes.SPHERE_LUA)["sphere"].obj
+    obj.backend.set_parameters(0.1, 1.0)
+    a = mc.IsosurfaceStuffing(obj, 1.0 / 40, 0.2, ctx=ctx).tessellate()
+    want = a.boundary().array()
+    assert len(want) > 1000
+    monkeypatch.setenv("MC_BOUNDARY_CAPACITY", "100")
+    b = mc.IsosurfaceStuffing(obj, 1.0 / 40, 0.2, ctx=ctx).tessellate()
+    got = b.boundary().array()
+    assert np.array_equal(got, want)
+    key = got[:, 0] * 4 + got[:, 1]
+    assert np.all(key[1:] > key[:-1])   # the device writes the sides in (elem, side) order
