@@ -43,6 +43,7 @@ struct mc_ctx {
     uint32_t tile_program_cap_words = MC_TILE_PROGRAM_CAP_WORDS;  // env MC_TILE_PROGRAM_CAP_WORDS overrides (tuning)
     bool tet_emit_attr_set = false;     // cudaFuncSetAttribute for k_tet_emit done on this device
     bool boundary_attr_set = false;     // ... and for k_boundary_sides
+    bool classify_attr_set = false;     // ... and for k_classify_cells
     mc::DevBuf d_shapes;                // shape tables (mc_shapes.hpp), uploaded at context creation
     bool debug = false, debug_sync = false;  // MC_DEBUG=1: poison allocations + check every stage (2: poison, 3: checks)
 

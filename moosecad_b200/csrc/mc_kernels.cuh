@@ -436,8 +436,10 @@ k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned lon
     __shared__ unsigned long long s_tab[8 * WT_STRIDE];
     __shared__ uint8_t s_pairs[8 * WP_STRIDE];
     __shared__ uint32_t s_nan;
-    __shared__ uint16_t s_list[TILE_POINTS];
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_box);   // [TILE_POINTS]; the box is dead once the sign classes are staged
+    static_assert(sizeof(s_box) >= TILE_POINTS * sizeof(uint16_t), "the vertex list reuses the TMA box");
     __shared__ uint32_t s_n;
+    __shared__ uint32_t s_rowm[3][H * H];   // bit masks of the box's point rows
     const Lattice& L = S.L;
     for (int i = (int)threadIdx.x; i < 8 * WT_STRIDE; i += TILE_THREADS) s_tab[i] = S.warp_table[i];
     for (int i = (int)threadIdx.x; i < 8 * WP_STRIDE; i += TILE_THREADS) s_pairs[i] = (uint8_t)S.warp_table[8 * WT_STRIDE + i];
@@ -452,23 +454,46 @@ k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned lon
         if (sg == SG_NAN) s_nan = 1u;
     });
     __syncthreads();
-    for (int r = 0; r < TILE_ROUNDS; ++r) {
-        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-        const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-        if (X < L.NX && Y < L.NY && Z >= S.wz0 && Z <= S.wz1) {
-            const int me = (int)((lz + 1) * H + (ly + 1)) * H + (int)(lx + 1);
-            const int sv = s_sg[me];
-            const bool even = ((X + Y + Z) & 1u) == 0u;
-            bool any = false;
+    // Which vertices have an edge that does not join two vertices of one strict sign?  Per point row of the box
+    // three bit masks (bit bx): the point exists and is not negative / not positive / exists at all ...
+    for (int r = (int)threadIdx.x; r < H * H; r += TILE_THREADS) {
+        uint32_t ex = 0u, ng = 0u, ps = 0u;
 #pragma unroll
-            for (int d = 0; d < 18; ++d) {
-                if (!even && !(d < 3 || (d >= 9 && d < 12))) continue;
-                const KDir kd = kdir(d);
-                const int sw = s_sg[me + (kd.z * H + kd.y) * H + kd.x];
-                if (sw != SG_NONE && !((sv == SG_POS || sv == SG_NEG) && sw == sv)) any = true;
+        for (int i = 0; i < H; ++i) {
+            const int sg = s_sg[r * H + i];
+            ex |= (sg != SG_NONE ? 1u : 0u) << i;
+            ng |= (sg == SG_NEG ? 1u : 0u) << i;
+            ps |= (sg == SG_POS ? 1u : 0u) << i;
+        }
+        s_rowm[0][r] = ex & ~ng; s_rowm[1][r] = ex & ~ps; s_rowm[2][r] = ex;
+    }
+    __syncthreads();
+    // ... and every thread settles one x-row of 16 vertices: a negative vertex looks for a neighbour that is not
+    // negative, a positive one for one that is not positive, any other for any neighbour at all; vertices with
+    // even X + Y + Z have 18 neighbours (axes + face diagonals), the others the 6 along the axes.
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t Y = Y0 + ly, Z = Z0 + lz;
+        if (X0 < L.NX && Y < L.NY && Z >= S.wz0 && Z <= S.wz1) {
+            const int r = (int)(lz + 1u) * H + (int)(ly + 1u);
+            uint32_t any[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t* M = s_rowm[k];
+                const uint32_t c = M[r], yp = M[r + 1], ym = M[r - 1], zp = M[r + H], zm = M[r - H];
+                const uint32_t axis = (c >> 1) | (c << 1) | yp | ym | zp | zm;
+                const uint32_t diag = (yp >> 1) | (yp << 1) | (ym >> 1) | (ym << 1) | (zp >> 1) | (zp << 1) | (zm >> 1) | (zm << 1) |
+                                      M[r + H + 1] | M[r + H - 1] | M[r - H + 1] | M[r - H - 1];
+                any[k] = axis | (diag & (((X0 + Y + Z) & 1u) ? 0x55555555u : 0xaaaaaaaau));   // bit bx <-> X = X0 + bx - 1
             }
-            if (any) s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+            const uint32_t ng = s_rowm[2][r] & ~s_rowm[0][r], ps = s_rowm[2][r] & ~s_rowm[1][r];
+            const uint32_t nxt = min(TS, L.NX - X0);
+            const uint32_t valid = (nxt >= 16u ? 0xffffu : ((1u << nxt) - 1u)) << 1;
+            uint32_t sel = ((ng & any[0]) | (ps & any[1]) | (~ng & ~ps & any[2])) & valid;
+            if (sel) {
+                uint32_t at = atomicAdd(&s_n, (uint32_t)__popc(sel));
+                for (; sel; sel &= sel - 1u) s_list[at++] = (uint16_t)(threadIdx.x * TS + (uint32_t)(__ffs((int)sel) - 2));
+            }
         }
     }
     __syncthreads();
@@ -570,22 +595,36 @@ k_warp_codes(Stuff S, const __grid_constant__ CUtensorMap tmap_phi, unsigned lon
 // totals (low 32 bits: output tets, high 32 bits: kept lattice tets) count owned cells only.
 // Cells whose corners are all negative / all positive are settled from the staged classes;
 // the tets of the remaining (surface) cells are collected and classified one per thread.
+// tie-break of the 4-sort between two equal non-zero values: first-touch order of nodes i and k of tet (c, t)
+// (rare: symmetric scenes; kept out of line)
+static __device__ __noinline__ bool first_touch_less(const Lattice& L, const Cell& c, int t, int i, int k) {
+    uint32_t Xi, Yi, Zi, Xk, Yk, Zk;
+    corner_xyz(c, tet_corner(c, t, i), Xi, Yi, Zi);
+    corner_xyz(c, tet_corner(c, t, k), Xk, Yk, Zk);
+    return first_touch_key(L, Xi, Yi, Zi) < first_touch_key(L, Xk, Yk, Zk);
+}
+
+constexpr int CC_H = (int)TS + 1, CC_NP = CC_H * CC_H * CC_H;
+constexpr uint32_t CC_PASS = TILE_POINTS / 4;    // surface cells assembled per pass
+constexpr size_t CLASSIFY_SMEM = (size_t)CC_NP * 8;   // post-warp phi of the tile's cell corners (dynamic shared memory)
 static __global__ void __launch_bounds__(TILE_THREADS, 3)
 k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long* __restrict__ tile_tot,
                  unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
                  const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
+    extern __shared__ __align__(16) double s_phi[];   // [CC_NP] post-warp values (0 for a warped vertex)
     __shared__ unsigned long long s_acc;
     const Lattice& L = S.L;
     uint32_t tile;
     while (next_tile(tile_list, n_list, cursor, tile)) {  // active cell tiles (the others were settled by k_cell_tile_class)
     uint32_t X0, Y0, Z0;
     tile_origin(S.g, tile, X0, Y0, Z0);
-    // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0
-    constexpr int H = (int)TS + 1;
-    __shared__ uint8_t s_cls[H * H * H];
+    // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0, bit 2 = raw phi <= 0
+    constexpr int H = CC_H;
+    __shared__ uint8_t s_cls[CC_NP];
+    __shared__ uint32_t s_rowneg[H * H], s_rowpos[H * H];  // bit i of a point row: class bit 0 / bit 1 of its point i
     __shared__ uint16_t s_list[TILE_POINTS];   // surface cells (local index)
-    __shared__ uint32_t s_ci[TILE_POINTS / 2]; // cinfo of the surface cells being assembled, by list slot
-    __shared__ __align__(8) uint8_t s_shape[TILE_POINTS / 2][8];  // their shape bytes (mc_shapes.hpp), one per lattice tet
+    __shared__ uint32_t s_ci[CC_PASS];         // cinfo of the surface cells being assembled, by list slot
+    __shared__ __align__(8) uint8_t s_shape[CC_PASS][8];  // their shape bytes (mc_shapes.hpp), one per lattice tet
     __shared__ uint32_t s_n;
     __shared__ uint32_t s_stat[8];             // trim cases 0..6 + exterior removals of the owned cells
     if (threadIdx.x == 0) s_n = 0u;
@@ -593,33 +632,57 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     __syncthreads();
     stage_points<H, 0, true>(L, X0, Y0, Z0, [&](int idx, bool in, double raw, uint8_t wc) {
         const double w = (wc & 0x7f) ? 0.0 : raw;
-        s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0)) : (uint8_t)0;
+        s_phi[idx] = w;
+        s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0) | (raw <= 0.0 ? 4 : 0)) : (uint8_t)0;
     });
     __syncthreads();
-    uint32_t my_out = 0, my_kept = 0, my_listed = 0, my_surf = 0;
-    for (int r = 0; r < TILE_ROUNDS; ++r) {
-        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-        const uint32_t cx = X0 + lx, cy = Y0 + ly, cz = Z0 + lz;
-        if (cx >= L.nx || cy >= L.ny || cz < S.cl0 || cz >= S.cl1) continue;
-        uint8_t andc = 3;
+    for (int r = (int)threadIdx.x; r < H * H; r += TILE_THREADS) {
+        uint32_t neg = 0u, pos = 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            andc &= s_cls[((lz + (uint32_t)C_LAT[k][2]) * H + (ly + (uint32_t)C_LAT[k][1])) * H + (lx + (uint32_t)C_LAT[k][0])];
-        if (andc & 1) {          // every corner negative: five untouched lattice tets
-            S.cinfo[cidx(S, cx, cy, cz)] = CI_ALL_FULL;
-            if (cz >= S.c0 && cz < S.c1) { my_out += 5; my_kept += 5; }
-        } else if (andc & 2) {   // every corner positive: nothing kept
-            S.cinfo[cidx(S, cx, cy, cz)] = 0;
-        } else {
-            s_list[atomicAdd(&s_n, 1u)] = (uint16_t)j;
+        for (int i = 0; i < H; ++i) {
+            const uint32_t c = s_cls[r * H + i];
+            neg |= (c & 1u) << i;
+            pos |= ((c >> 1) & 1u) << i;
+        }
+        s_rowneg[r] = neg; s_rowpos[r] = pos;
+    }
+    __syncthreads();
+    uint32_t my_out = 0, my_kept = 0, my_listed = 0, my_surf = 0;
+    {
+        // every thread settles one x-row of 16 cells from the four point rows around it: a cell whose eight
+        // corners are all negative emits five untouched lattice tets, all positive: nothing; the rest is listed
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
+        if (X0 < L.nx && cy < L.ny && cz >= S.cl0 && cz < S.cl1) {
+            const uint32_t nxt = min(TS, L.nx - X0), valid = nxt >= 16u ? 0xffffu : ((1u << nxt) - 1u);
+            const uint32_t r00 = lz * H + ly, r01 = r00 + 1u, r10 = r00 + H, r11 = r10 + 1u;
+            const uint32_t n4 = s_rowneg[r00] & s_rowneg[r01] & s_rowneg[r10] & s_rowneg[r11];
+            const uint32_t p4 = s_rowpos[r00] & s_rowpos[r01] & s_rowpos[r10] & s_rowpos[r11];
+            const uint32_t full = n4 & (n4 >> 1) & valid, empty = p4 & (p4 >> 1) & valid;
+            const uint32_t surf = valid & ~full & ~empty;
+            uint16_t* row = S.cinfo + cidx(S, X0, cy, cz);
+            if (nxt == 16u && (reinterpret_cast<uintptr_t>(row) & 15u) == 0u) {
+                uint32_t wds[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    wds[i] = (((full >> (2 * i)) & 1u) ? (uint32_t)CI_ALL_FULL : 0u) | ((((full >> (2 * i + 1)) & 1u) ? (uint32_t)CI_ALL_FULL : 0u) << 16);
+                reinterpret_cast<uint4*>(row)[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                reinterpret_cast<uint4*>(row)[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+            } else {
+                for (uint32_t i = 0; i < nxt; ++i) row[i] = ((full >> i) & 1u) ? CI_ALL_FULL : (uint16_t)0;
+            }
+            if (cz >= S.c0 && cz < S.c1) { my_out += 5u * (uint32_t)__popc(full); my_kept += 5u * (uint32_t)__popc(full); }
+            if (surf) {
+                uint32_t at = atomicAdd(&s_n, (uint32_t)__popc(surf));
+                for (uint32_t m = surf; m; m &= m - 1u) s_list[at++] = (uint16_t)(threadIdx.x * TS + (uint32_t)(__ffs((int)m) - 1));
+            }
         }
     }
     __syncthreads();
     const uint32_t n = s_n;
-    // a tile has at most 4096 surface cells; the assembly buffer holds 2048 list slots per pass
-    for (uint32_t pass = 0; pass < n; pass += TILE_POINTS / 2) {
-        const uint32_t m = min(n - pass, TILE_POINTS / 2);
+    // a tile has at most 4096 surface cells; the assembly buffer holds CC_PASS list slots per pass
+    for (uint32_t pass = 0; pass < n; pass += CC_PASS) {
+        const uint32_t m = min(n - pass, CC_PASS);
         for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) {
             s_ci[q] = 0u;
             *reinterpret_cast<unsigned long long*>(s_shape[q]) = 0ull;
@@ -631,41 +694,63 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
             const uint32_t cx = X0 + (j & 15u), cy = Y0 + ((j >> 4) & 15u), cz = Z0 + (j >> 8);
             const Cell c = make_cell(cx, cy, cz);
             const bool own = cz >= S.c0 && cz < S.c1;  // halo layers only contribute flags
-            // sign classes of the four nodes first: a tet whose nodes are all strictly negative passes through
-            // untouched, one whose raw values are all positive was never kept — neither needs the field
-            uint8_t andc = 3;
+            // the four nodes (flipped order): local index in the staged box, sign classes, post-warp values
+            int li[4];
+            uint8_t andc = 3, orc = 0;
 #pragma unroll
             for (int nn = 0; nn < 4; ++nn) {
                 uint32_t X, Y, Z;
-                corner_xyz(c, (int)C_TETS[t][nn], X, Y, Z);
-                andc &= s_cls[((Z - Z0) * H + (Y - Y0)) * H + (X - X0)];
+                corner_xyz(c, tet_corner(c, (int)t, nn), X, Y, Z);
+                li[nn] = (int)((Z - Z0) * H + (Y - Y0)) * H + (int)(X - X0);
+                const uint8_t cl = s_cls[li[nn]];
+                andc &= cl; orc |= cl;
             }
-            if (andc & 2) continue;   // not kept by cut_lattice
-            if (andc & 1) {
+            if (!(orc & 4)) continue;   // no corner with a raw value <= 0: not kept by cut_lattice
+            if (andc & 1) {             // all strictly negative: passed through untouched
                 atomicOr(&s_ci[q], (1u << (2u * t)) | (1u << (16u + t)));
                 s_shape[q][t] = (uint8_t)SHAPE_WHOLE;
                 continue;
             }
-            TetNodes tn;
-            load_tet(L, c, (int)t, tn);
-            TetOut to;
-            classify_tet<true>(L, c, (int)t, tn, prog, -1, to);
-            if (to.kase == -2) continue;  // not kept by cut_lattice
-            uint32_t bits = ((uint32_t)to.n << (2u * t)) | (1u << (16u + t));  // bit 16+t: kept
-            if (to.ext_removed) { bits |= 1u << (10u + t); if (own) atomicAdd(&s_stat[7], 1u); }  // bit 10+t: dropped by the exterior test
-            if (to.kase >= 0) { bits |= 1u << (24u + t); if (own) atomicAdd(&s_stat[to.kase], 1u); }  // bit 24+t: trimmed
-            atomicOr(&s_ci[q], bits);
-            if (to.n != 0) s_shape[q][t] = (uint8_t)(to.kase < 0 ? SHAPE_WHOLE : SHAPE_TRIM0 + 24 * (to.kase - 1) + to.perm);
-            // zero-valued original vertices that made it into the output are "used"
-            for (int o = 0; o < to.n; ++o)
-#pragma unroll
-                for (int mm = 0; mm < 4; ++mm) {
-                    const int nd = to.node(o, mm);
-                    if (nd < 4 && tet_p(tn, nd) == 0.0) {
-                        const size_t pi = pidx(L, tet_X(tn, nd), tet_Y(tn, nd), tet_Z(tn, nd));
-                        L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
+            const double p0 = s_phi[li[0]], p1 = s_phi[li[1]], p2 = s_phi[li[2]], p3 = s_phi[li[3]];
+            uint32_t nout, shape;
+            uint32_t bits = 1u << (16u + t);  // bit 16+t: kept
+            if (p0 <= 0.0 && p1 <= 0.0 && p2 <= 0.0 && p3 <= 0.0) {
+                // no positive vertex: passed through, unless all four are zero and the exterior test drops it
+                nout = 1u; shape = SHAPE_WHOLE;
+                if (p0 == 0.0 && p1 == 0.0 && p2 == 0.0 && p3 == 0.0) {
+                    TetNodes tn;
+                    load_tet(L, c, (int)t, tn);
+                    TetOut to;
+                    classify_tet<true, true>(L, c, (int)t, tn, prog, -1, to);
+                    if (to.ext_removed) {
+                        nout = 0u; shape = SHAPE_NONE;
+                        bits |= 1u << (10u + t);   // bit 10+t: dropped by the exterior test
+                        if (own) atomicAdd(&s_stat[7], 1u);
                     }
                 }
+            } else {
+                int kase, perm;
+                sort_case(p0, p1, p2, p3, [&](int i, int k) { return first_touch_less(L, c, (int)t, i, k); }, kase, perm);
+                nout = C_CASE_N[kase];
+                shape = nout ? (uint32_t)(SHAPE_TRIM0 + 24 * (kase - 1) + perm) : (uint32_t)SHAPE_NONE;
+                bits |= 1u << (24u + t);           // bit 24+t: trimmed
+                if (own) atomicAdd(&s_stat[kase], 1u);
+            }
+            bits |= nout << (2u * t);
+            atomicOr(&s_ci[q], bits);
+            s_shape[q][t] = (uint8_t)shape;
+            // zero-valued original vertices that made it into the output are "used"
+            const uint32_t used = S.shapes->used[shape];
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+                const double pn = nn == 0 ? p0 : (nn == 1 ? p1 : (nn == 2 ? p2 : p3));
+                if (((used >> nn) & 1u) && pn == 0.0) {
+                    uint32_t X, Y, Z;
+                    corner_xyz(c, tet_corner(c, (int)t, nn), X, Y, Z);
+                    const size_t pi = pidx(L, X, Y, Z);
+                    L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
+                }
+            }
         }
         __syncthreads();
         for (uint32_t q = threadIdx.x; q < m; q += TILE_THREADS) {
@@ -1379,55 +1464,52 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         s_tvu[q] = vu;
     }
     __syncthreads();
-    // (batches of independent loads: every thread issues TE_BATCH points' loads before it uses any)
-    constexpr int TE_BATCH = 4;
-    for (int base = (int)threadIdx.x; base < TE_NP; base += TE_BATCH * TILE_THREADS) {
-        unsigned long long tab[TE_BATCH];
-        uint16_t vm[TE_BATCH], vl[TE_BATCH];
-        uint8_t kind[TE_BATCH];   // 0 nothing, 1 lower table, 2 interior tile, 3 surface tile
-#pragma unroll
-        for (int b = 0; b < TE_BATCH; ++b) {
-            const int idx = base + b * TILE_THREADS;
-            kind[b] = 0; tab[b] = 0ull; vm[b] = 0; vl[b] = 0;
-            if (idx >= TE_NP) continue;
-            const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
-            const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
-            const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
-            const uint8_t vu = s_tvu[q];
-            if (X < L.NX && Y < L.NY && Z <= L.pz1 && vu != VU_POS) {
-                if (S.lower_table != nullptr && Z == S.c0) {
-                    kind[b] = 1;
-                    tab[b] = S.lower_table[(size_t)Y * L.NX + X];
-                } else if (vu == VU_NEG) {
-                    kind[b] = 2;
-                } else {
-                    kind[b] = 3;
-                    const size_t pi = pidx(L, X, Y, Z);
-                    vm[b] = S.vmask[pi];
-                    vl[b] = S.vloc[pi];
-                }
+    // One x-row of 17 points per thread and round: the masks / local indices of its first 16 points are two
+    // aligned 32-byte runs (the row pitch is a multiple of 16 points), fetched with 16-byte loads.
+    for (int r = (int)threadIdx.x; r < TE_H * TE_H; r += TILE_THREADS) {
+        const uint32_t ly = (uint32_t)r % TE_H, lz = (uint32_t)r / TE_H;
+        const uint32_t Y = Y0 + ly, Z = Z0 + lz;
+        const uint32_t q0 = (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
+        const bool row_in = Y < L.NY && Z <= L.pz1;
+        const bool from_table = row_in && S.lower_table != nullptr && Z == S.c0;
+        const uint8_t vu0 = row_in ? s_tvu[q0] : VU_POS, vu1 = (row_in && X0 + TS < L.NX) ? s_tvu[q0 | 1u] : VU_POS;
+        uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0, l0 = m0, l1 = m0;
+        uint32_t mlast = 0u, llast = 0u;
+        if (!from_table) {
+            const size_t pi = pidx(L, X0, Y, Z);
+            if (vu0 == VU_ACTIVE) {
+                m0 = *reinterpret_cast<const uint4*>(S.vmask + pi); m1 = *reinterpret_cast<const uint4*>(S.vmask + pi + 8);
+                l0 = *reinterpret_cast<const uint4*>(S.vloc + pi);  l1 = *reinterpret_cast<const uint4*>(S.vloc + pi + 8);
             }
+            if (vu1 == VU_ACTIVE) { mlast = S.vmask[pi + TS]; llast = S.vloc[pi + TS]; }
         }
+        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const int idx0 = r * TE_H;
 #pragma unroll
-        for (int b = 0; b < TE_BATCH; ++b) {
-            const int idx = base + b * TILE_THREADS;
-            if (idx >= TE_NP) continue;
-            const uint32_t lx = idx % TE_H, ly = (idx / TE_H) % TE_H, lz = idx / (TE_H * TE_H);
-            const uint32_t q = (lx == TS ? 1u : 0u) | (ly == TS ? 2u : 0u) | (lz == TS ? 4u : 0u);
+        for (uint32_t i = 0; i <= TS; ++i) {
+            const uint32_t X = X0 + i;
+            const uint32_t q = i == TS ? (q0 | 1u) : q0;
+            const uint8_t vu = i == TS ? vu1 : vu0;
             IndexT gid = 0;
             uint16_t mask = 0;
-            if (kind[b] == 1) {
-                mask = (uint16_t)(tab[b] & 0xffffull);
-                gid = (IndexT)(tab[b] >> 16);
-            } else if (kind[b] == 2) {
-                const TileBox& tbx = s_tb[q];
-                mask = VM_USED;
-                gid = (IndexT)(s_tbase[q] + (long long)((((Z0 + lz) - tbx.zlo) * tbx.nyt + ((Y0 + ly) - tbx.Y0)) * tbx.nxt + ((X0 + lx) - tbx.X0)));
-            } else if (kind[b] == 3) {
-                mask = vm[b];
-                gid = (IndexT)(s_tbase[q] + (long long)vl[b]);
+            if (X < L.NX) {
+                if (from_table) {
+                    const unsigned long long e = vu != VU_POS ? S.lower_table[(size_t)Y * L.NX + X] : 0ull;
+                    mask = (uint16_t)(e & 0xffffull);
+                    gid = (IndexT)(e >> 16);
+                } else if (vu == VU_NEG) {
+                    const TileBox& tbx = s_tb[q];
+                    mask = VM_USED;
+                    gid = (IndexT)(s_tbase[q] + (long long)(((Z - tbx.zlo) * tbx.nyt + (Y - tbx.Y0)) * tbx.nxt + (X - tbx.X0)));
+                } else if (vu == VU_ACTIVE) {
+                    const uint32_t mv = i == TS ? mlast : ((mw[i >> 1] >> (16u * (i & 1u))) & 0xffffu);
+                    const uint32_t lv = i == TS ? llast : ((lw[i >> 1] >> (16u * (i & 1u))) & 0xffffu);
+                    mask = (uint16_t)mv;
+                    gid = (IndexT)(s_tbase[q] + (long long)lv);
+                }
             }
-            s_gid[idx] = gid; s_mask[idx] = mask;
+            s_gid[idx0 + (int)i] = gid; s_mask[idx0 + (int)i] = mask;
         }
     }
     // 2. per-cell info + offsets: every thread takes one x-row of 16 cells (consecutive in the

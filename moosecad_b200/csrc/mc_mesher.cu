@@ -735,7 +735,11 @@ int mc_tessellate_begin(mc_ctx* c, const mc_tape* volume, int32_t root, double r
     // a5/a7/a9: classification + counts
     k_cell_tile_class<<<blocks_for(ntiles, 256), 256, 0, s>>>(S, ntiles, counters, (uint32_t*)T.c_active, (uint32_t*)T.c_full,
                                                               (unsigned long long*)m->d_ttile_tot.p);
-    k_classify_cells<<<lgrid, TILE_THREADS, 0, s>>>(S, (const uint64_t*)m->d_prog.p, (unsigned long long*)m->d_ttile_tot.p,
+    if (!c->classify_attr_set) {
+        MC_TRY_CUDA(cudaFuncSetAttribute(k_classify_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLASSIFY_SMEM));
+        c->classify_attr_set = true;
+    }
+    k_classify_cells<<<lgrid, TILE_THREADS, CLASSIFY_SMEM, s>>>(S, (const uint64_t*)m->d_prog.p, (unsigned long long*)m->d_ttile_tot.p,
                                                     counters, T.c_active, T.n_c_active, counters + CUR_CLASSIFY);
     c->launches += 2;
     MC_TRY_CUDA(cudaGetLastError());

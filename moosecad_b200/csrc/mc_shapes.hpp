@@ -51,6 +51,7 @@ struct ShapeTables {
     uint8_t pfsig[N_SHAPES][6][12];   // signature of piece-face i for rank permutation pi of its lattice face's nodes
     uint32_t fsig[N_SHAPES][4][6];    // the (<= 4) signatures of the piece-faces in lattice face k, 8 bits each
     uint32_t geo[8][5][4];
+    uint8_t used[N_SHAPES];           // bit n: original node n (flipped node order) occurs in some piece
 };
 
 namespace shapes_detail {
@@ -159,6 +160,9 @@ inline bool build_shape_tables(ShapeTables& T) {
             }
         }
         T.own[A] = odd | (notlast << 12) | ((uint32_t)(4 * n) << 24);
+        for (int q = 0; q < n; ++q)
+            for (int m = 0; m < 4; ++m)
+                if (code_of(nodes, q, m) < 4) T.used[A] = (uint8_t)(T.used[A] | (1u << code_of(nodes, q, m)));
         for (int k = 0; k < 4; ++k)
             for (int pi = 0; pi < 6; ++pi) {
                 int r[4] = {0, 0, 0, 0}, pos = 0;

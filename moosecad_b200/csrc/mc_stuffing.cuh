@@ -149,6 +149,35 @@ __device__ __forceinline__ void load_tet_mixed(const Lattice& L, const Cell& c, 
     }
 }
 
+// The 4-sort of trim_spikes on its own (tessellate3d/src/lib.rs:262-282) for a tet with a positive vertex:
+// trim case and the dense index of the sorted node order (mc_shapes.hpp).  The values travel with the
+// labels through the comparator network, so nothing is indexed dynamically; `tie(i, j)` is only asked for
+// two equal non-zero values (first-touch order of nodes i and j, like the reference's vertex ids).
+template <typename Tie>
+__device__ __forceinline__ void sort_case(double p0, double p1, double p2, double p3, Tie tie, int& kase, int& perm) {
+    int ia = 0, ib = 1, ic = 2, id = 3;
+    double pa = p0, pb = p1, pc = p2, pd = p3;
+#define MC_CSWAP2(iu, iv, pu, pv)                                             \
+    if (pu < pv || (pu == pv && pu != 0.0 && tie(iu, iv))) {                  \
+        const int ti_ = iu; iu = iv; iv = ti_;                                \
+        const double tp_ = pu; pu = pv; pv = tp_;                             \
+    }
+    MC_CSWAP2(ia, ib, pa, pb)
+    MC_CSWAP2(ic, id, pc, pd)
+    MC_CSWAP2(ia, ic, pa, pc)
+    MC_CSWAP2(ib, id, pb, pd)
+    MC_CSWAP2(ib, ic, pb, pc)
+#undef MC_CSWAP2
+    if (pd == 0.0) kase = 0;
+    else if (pc > 0.0) kase = 1;
+    else if (pb < 0.0) kase = 2;
+    else if (pb > 0.0 && pc < 0.0) kase = 3;
+    else if (pb == 0.0 && pc == 0.0) kase = 4;
+    else if (pb == 0.0) kase = 5;
+    else kase = 6;
+    perm = shape_perm_index(ia, ib, ic);
+}
+
 // `removed_hint`: < 0 -> evaluate the exterior test with the SDF program; 0/1 -> cached result
 // KNOWN_KEPT: the caller knows that cut_lattice kept the tet (it produced output)
 template <bool CAN_EVAL, bool KNOWN_KEPT = false>
