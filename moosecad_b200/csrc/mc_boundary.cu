@@ -276,9 +276,10 @@ k_boundary_sides(Stuff S, const uint32_t* __restrict__ tile_list, const unsigned
             const uint32_t j = threadIdx.x * TS + i;
             const uint16_t ci = (uint16_t)s_cell[at0 + (int)i];
             for (uint32_t t = 0; t < 5u; ++t) {
-                const uint32_t mask = s_mask[t * TILE_POINTS + j];
-                for (uint32_t bb = 0; bb < 12u && mask; ++bb)
-                    if ((mask >> bb) & 1u) { reinterpret_cast<ulonglong2*>(sides)[o] = make_ulonglong2(elem + (bb >> 2), bb & 3u); ++o; }
+                for (uint32_t mask = s_mask[t * TILE_POINTS + j]; mask; mask &= mask - 1u) {
+                    const uint32_t bb = (uint32_t)__ffs((int)mask) - 1u;
+                    reinterpret_cast<ulonglong2*>(sides)[o++] = make_ulonglong2(elem + (bb >> 2), bb & 3u);
+                }
                 elem += ci_tet_n(ci, (int)t);
             }
         }

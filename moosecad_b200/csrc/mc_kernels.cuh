@@ -108,6 +108,16 @@ struct Stuff {
     long long vertex_base;             // global id of this slab's first vertex
 };
 
+constexpr int QC_K = 32;  // classes per axis (16 distinct steps x parity); more -> per-tile kernels
+// classes of the plain lattice cells for check_for_inverted_tets (see k_quality_classes)
+struct QualityClasses {
+    const uint8_t* kx;      // class of every cell column / row / layer (global cell index)
+    const uint8_t* ky;
+    const uint8_t* kz;
+    const double* steps;    // [3][QC_K / 2] distinct step values per axis
+    uint32_t* present;      // [kz * QC_K + ky] bit kx
+};
+
 __device__ __forceinline__ size_t cidx(const Stuff& S, uint32_t cx, uint32_t cy, uint32_t cz) {
     return ((size_t)(cz - S.cl0) * S.L.ny + cy) * S.L.nx + cx;
 }
@@ -1022,8 +1032,8 @@ k_vertex_emit(Stuff S, const unsigned long long* __restrict__ tile_cbase, double
             o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         }
         uint64_t ci = cb + s_cut[j];
-        for (int s = 0; s < 9; ++s)
-            if (m & (1u << s)) cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)s;
+        for (uint32_t cm = m & VM_CUT_MASK; cm; cm &= cm - 1u)
+            cutlist[ci++] = ((unsigned long long)pi << 4) | (unsigned long long)(__ffs((int)cm) - 1);
     }
     }  // tiles
 }
@@ -1422,7 +1432,7 @@ __device__ __forceinline__ void store_tet(unsigned long long* tets, uint64_t o, 
 
 template <typename IndexT, bool QUALITY>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ qlist,
+k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ qlist, QualityClasses Q,
            unsigned long long* __restrict__ counters, const uint32_t* __restrict__ tile_list,
            const unsigned long long* __restrict__ n_list, unsigned long long* __restrict__ cursor) {
     extern __shared__ __align__(16) unsigned char te_smem[];
@@ -1445,6 +1455,23 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[tile];
     if (threadIdx.x == 0) s_n = 0u;
+    // (issued first, used in step 2) this thread's x-row of cell info words: 32 contiguous bytes
+    uint32_t crow[TS / 2];
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
+        const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
+        const uint16_t* __restrict__ row = S.cinfo + (row_owned ? cidx(S, X0, cy, cz) : 0);
+        const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
+        if (nx_row == TS && (reinterpret_cast<uintptr_t>(row) & 15u) == 0u) {
+            const uint4 a = reinterpret_cast<const uint4*>(row)[0], b = reinterpret_cast<const uint4*>(row)[1];
+            crow[0] = a.x; crow[1] = a.y; crow[2] = a.z; crow[3] = a.w; crow[4] = b.x; crow[5] = b.y; crow[6] = b.z; crow[7] = b.w;
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < TS / 2; ++i)
+                crow[i] = (2u * i < nx_row ? (uint32_t)row[2u * i] : 0u) | ((2u * i + 1u < nx_row ? (uint32_t)row[2u * i + 1u] : 0u) << 16);
+        }
+    }
     // 1. vertex ids / masks of the tile's corners.  The (TS+1)^3 points lie in at most 8 tiles:
     //    their class, id base and owned box are staged once, so that a point costs no dependent
     //    global load (interior tiles: arithmetic; surface tiles: its mask and local index).
@@ -1516,18 +1543,15 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     //    output order), one block scan of the row totals gives the offsets of the output tets
     //    (low half) and of the tets listed for the per-tet quality pass (high half; <= 61440 each)
     {
-        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
-        const uint32_t cy = Y0 + ly, cz = Z0 + lz;
-        const bool row_owned = cy < L.ny && cz >= zlo && cz < zhi;
-        const uint16_t* __restrict__ row = S.cinfo + (row_owned ? cidx(S, X0, cy, cz) : 0);
-        const uint32_t nx_row = row_owned ? min(TS, L.nx - X0) : 0u;
-        uint32_t acc = 0;
+        uint32_t acc = 0, qbits = 0;
         uint32_t pre[TS];
 #pragma unroll
         for (uint32_t i = 0; i < TS; ++i) {
-            const uint16_t ci = i < nx_row ? row[i] : (uint16_t)0;
+            const uint16_t ci = (uint16_t)(crow[i >> 1] >> (16u * (i & 1u)));
             const uint32_t count = ci_count(ci);
             const bool listed = QUALITY && count && (!(ci & CI_FULL) || (ci & CI_FULL_ZERO_CORNER));
+            // plain cells (untouched, all corners strictly negative): their (step, parity) class occurs
+            if (QUALITY && Q.present != nullptr && (ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER)) qbits |= 1u << Q.kx[X0 + i];
             s_ci[threadIdx.x * TS + i] = ci;
             pre[i] = acc;
             acc += count | (listed ? count << 16 : 0u);
@@ -1542,6 +1566,10 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             if (QUALITY) s_qoff[threadIdx.x * TS + i] = (uint16_t)(v >> 16);
         }
         if (QUALITY && threadIdx.x == 0) s_qbase = (tot >> 16) ? atomicAdd(&counters[CN_QLIST_FILL], (unsigned long long)(tot >> 16)) : 0ull;
+        if (QUALITY && qbits) {
+            uint32_t* w = Q.present + (uint32_t)Q.kz[Z0 + (threadIdx.x >> 4)] * QC_K + Q.ky[Y0 + (threadIdx.x & 15u)];
+            if ((*w & qbits) != qbits) atomicOr(w, qbits);
+        }
     }
     __syncthreads();
     // 3a. cells whose five lattice tets are emitted untouched
@@ -1549,15 +1577,16 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
         const uint16_t ci = s_ci[j];
         if (!(ci & CI_FULL)) continue;
         const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-        const Cell c = make_cell(X0 + lx, Y0 + ly, Z0 + lz);
-        const bool flip = c.flip();
+        // corner k of Tile::LATTICE sits at (lx ^ fx, ly ^ fy, lz ^ fz) of the cell: six offsets per cell
+        const uint32_t fx = (X0 + lx) & 1u, fy = (Y0 + ly) & 1u, fz = (Z0 + lz) & 1u;
+        const bool flip = ((fx ^ fy ^ fz) & 1u) != 0u;
+        const int base = (int)((lz * TE_H + ly) * TE_H + lx);
+        const int ox[2] = {(int)fx, 1 - (int)fx}, oy[2] = {(int)fy * TE_H, (1 - (int)fy) * TE_H},
+                  oz[2] = {(int)fz * TE_H * TE_H, (1 - (int)fz) * TE_H * TE_H};
+        constexpr int LB[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};  // Tile::LATTICE
         IndexT id[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t X, Y, Z;
-            corner_xyz(c, k, X, Y, Z);
-            id[k] = s_gid[(int)((Z - Z0) * TE_H + (Y - Y0)) * TE_H + (int)(X - X0)];
-        }
+        for (int k = 0; k < 8; ++k) id[k] = s_gid[base + ox[LB[k][0]] + oy[LB[k][1]] + oz[LB[k][2]]];
         const uint64_t o = tb + s_off[j];
 #pragma unroll
         for (int t = 0; t < 5; ++t)
@@ -1718,14 +1747,6 @@ k_surface_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
 // evaluated exactly once.  The aspect-ratio range needs nothing else; the inverted COUNT would
 // need multiplicities, so a combination that turns out inverted (it never does for a sane
 // lattice) only raises a flag and the host re-runs the per-tile counting kernels above.
-constexpr int QC_K = 32;  // classes per axis (16 distinct steps x parity); more -> per-tile kernels
-struct QualityClasses {
-    const uint8_t* kx;      // class of every cell column / row / layer (global cell index)
-    const uint8_t* ky;
-    const uint8_t* kz;
-    const double* steps;    // [3][QC_K / 2] distinct step values per axis
-    uint32_t* present;      // [kz * QC_K + ky] bit kx
-};
 
 // interior cell tiles: every cell is plain, all combinations of the tile's classes occur
 static __global__ void __launch_bounds__(256)
@@ -1754,36 +1775,6 @@ k_quality_mark_full(Stuff S, QualityClasses Q, const uint32_t* __restrict__ tile
         uint32_t* w = Q.present + kz * QC_K + ky;
         if ((*w & mx) != mx) atomicOr(w, mx);
     }
-}
-
-// surface cell tiles: the plain cells (untouched, all corners strictly negative) one by one
-static __global__ void __launch_bounds__(TILE_THREADS)
-k_quality_mark_surface(Stuff S, QualityClasses Q, const uint32_t* __restrict__ tile_list,
-                       const unsigned long long* __restrict__ n_list) {
-    const Lattice& L = S.L;
-    for (unsigned long long item = blockIdx.x; item < *n_list; item += gridDim.x) {  // active cell tiles
-    const uint32_t tile = tile_list[item];
-    uint32_t X0, Y0, Z0;
-    tile_origin(S.g, tile, X0, Y0, Z0);
-    const uint32_t zlo = max(Z0, S.c0), zhi = min(Z0 + TS, S.c1);
-    if (zhi <= zlo) continue;
-    // one x-row of 16 cells per thread
-    const uint32_t cy = Y0 + (threadIdx.x & 15u), cz = Z0 + (threadIdx.x >> 4);
-    if (cy >= L.ny || cz < zlo || cz >= zhi) continue;
-    const uint16_t* __restrict__ row = S.cinfo + cidx(S, X0, cy, cz);
-    const uint32_t n = min(TS, L.nx - X0);
-    uint32_t bits = 0u;
-#pragma unroll
-    for (uint32_t i = 0; i < TS; ++i) {
-        if (i >= n) break;
-        const uint16_t ci = row[i];
-        if ((ci & CI_FULL) && !(ci & CI_FULL_ZERO_CORNER)) bits |= 1u << Q.kx[X0 + i];
-    }
-    if (bits) {
-        uint32_t* w = Q.present + (uint32_t)Q.kz[cz] * QC_K + Q.ky[cy];
-        if ((*w & bits) != bits) atomicOr(w, bits);
-    }
-    }  // tiles
 }
 
 // one thread per (kx, ky, kz): the five lattice tets of a cell with those steps and mirroring

@@ -999,18 +999,18 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             if (quality) {
                 if (class_quality) {
                     k_quality_mark_full<<<blocks_for(m->n_tiles, 8), 256, 0, s>>>(S, Q, T.c_full, T.n_c_full);
-                    k_quality_mark_surface<<<lgrid, TILE_THREADS, 0, s>>>(S, Q, T.c_active, T.n_c_active);
-                    k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 } else {
                     k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                     k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
                 }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
-                k_tet_emit<uint32_t, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                // (the surface tiles' plain cells are marked by the emission itself)
+                k_tet_emit<uint32_t, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, Q, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                if (class_quality) k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<uint32_t><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
-                k_tet_emit<uint32_t, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                k_tet_emit<uint32_t, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<uint32_t>(), s>>>(S, out, ql, Q, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
             }
         } else {
             unsigned long long* out = (unsigned long long*)m->d_tets.p;
@@ -1019,23 +1019,23 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             if (quality) {
                 if (class_quality) {
                     k_quality_mark_full<<<blocks_for(m->n_tiles, 8), 256, 0, s>>>(S, Q, T.c_full, T.n_c_full);
-                    k_quality_mark_surface<<<lgrid, TILE_THREADS, 0, s>>>(S, Q, T.c_active, T.n_c_active);
-                    k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 } else {
                     k_full_tile_quality<<<grid, 64, 0, s>>>(S, counters);
                     k_surface_tile_quality<<<grid, TILE_THREADS, 0, s>>>(S, counters);
                 }
                 if ((rc = c->stage_check("stage tile quality")) != MC_OK) return rc;
-                k_tet_emit<unsigned long long, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                // (the surface tiles' plain cells are marked by the emission itself)
+                k_tet_emit<unsigned long long, true><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, Q, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                if (class_quality) k_quality_classes<<<QC_K * QC_K * QC_K / 256, 256, 0, s>>>(Q, counters);
                 if ((rc = c->stage_check("stage tet emit (surface tiles)")) != MC_OK) return rc;
                 if (nlist) k_tet_quality_list<unsigned long long><<<blocks_for(nlist, 256), 256, 0, s>>>(coords, out, ql, nlist, (long long)m->vertex_base, m->lower_coords, (long long)m->lower_first, (long long)m->lower_count, counters);
             } else {
-                k_tet_emit<unsigned long long, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
+                k_tet_emit<unsigned long long, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, Q, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
             }
         }
         c->release(qlist);
         c->release(qcls);
-        c->launches += quality ? (class_quality ? 6 : 5) : 2;
+        c->launches += quality ? 5 : 2;
         MC_CUDA(cudaGetLastError());
         if ((rc = c->stage_check("stage tet emit / quality list")) != MC_OK) return rc;
     }
