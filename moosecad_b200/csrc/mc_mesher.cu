@@ -155,6 +155,14 @@ int scan_tiles(mc_ctx* c, const void* tot, uint64_t n, void* base_lo, void* base
 int mc_ctx::alloc_raw(size_t bytes, DevBuf& out) {
     if (bytes == 0) bytes = 8;
     bytes = (bytes + 255) & ~(size_t)255;
+    // Size classes (eight per power of two, <= 12.5 % slack) above 1 MB: a job that comes back with slightly
+    // different array sizes (another slab of the same lattice, a refined partition) reuses the cached
+    // buffers instead of going to cudaMalloc / growing the cache.
+    if (bytes > (1u << 20)) {
+        size_t step = (size_t)1 << 17;
+        while ((step << 4) < bytes) step <<= 1;   // step = 2^(floor(log2(bytes - 1)) - 3)
+        bytes = (bytes + step - 1) / step * step;
+    }
     int best = -1;
     for (int i = 0; i < (int)free_list.size(); ++i)
         if (free_list[i].bytes >= bytes && (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;

@@ -199,7 +199,7 @@ def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=No
 
 
 _partition_cache = {}
-FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "6"))   # 0 disables the measured-load refinement
+FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "2"))   # 0 disables the measured-load refinement
 
 
 class _Partition:
