@@ -428,7 +428,7 @@ def main():
             roof2 = {"bound": "hbm", "kernels": "k_tile_minmax..k_tet_quality_list (all stages after the SDF field)",
                      "achieved": bytes_alg / (stuff_ms * 1e-3) / 1e9 if stuff_ms > 0 else None, "peak": hbm_peak,
                      "unit": "GB/s", "frac": bytes_alg / (stuff_ms * 1e-3) / 1e9 / hbm_peak if stuff_ms > 0 else None,
-                     "algorithmic_bytes": bytes_alg, "ms": stuff_ms,
+                     "algorithmic_bytes": bytes_alg, "traffic": None, "ms": stuff_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}
             line = {"metric": "lattice_points_per_s", "value": P_total / (ms_step * 1e-3), "unit": "lattice pts/s",
                     "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
@@ -452,11 +452,21 @@ def main():
                 line["per_rank"] = per_rank
             # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload
             try:
-                with open(os.path.join(ROOT, "profiles", "r01_sdf_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r02_sdf_traffic.json")) as f:
                     tr = json.load(f).get(f"{args.workload}@{world}")
                 if tr:
                     roof["traffic"] = tr["dram_bytes_per_launch"]
                     roof["traffic_source"] = tr["source"]
+            except (OSError, ValueError):
+                pass
+            # ... and of the stuffing / boundary / side-set kernels (same capture): wasted re-reads show up here
+            try:
+                with open(os.path.join(ROOT, "profiles", "r02_stuffing_traffic.json")) as f:
+                    tr = json.load(f).get(f"{args.workload}@{world}")
+                if tr:
+                    roof2["traffic"] = tr["dram_bytes_per_step"]
+                    roof2["traffic_per_kernel"] = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tr["per_kernel"].items()}
+                    roof2["traffic_source"] = tr["source"]
             except (OSError, ValueError):
                 pass
             if not args.no_cpu_baseline and world == 1:

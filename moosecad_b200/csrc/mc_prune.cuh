@@ -717,13 +717,15 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
         bool not_neg = false, not_pos = false;  // a stored value that is not < 0 / not > 0 (NaN: both)
         // placeholders of the proven sub-boxes
         if (sub_neg | sub_pos) {
-            for (uint32_t j = tid; j < TS * TS * TS; j += blockDim.x) {
-                const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
+            // (two points per thread, one 16-byte store: rows are padded to an even pitch, X is even)
+            for (uint32_t j = tid; j < TS * TS * TS / 2u; j += blockDim.x) {
+                const uint32_t lx = (j & 7u) * 2u, ly = (j >> 3) & 15u, lz = j >> 7;
                 const uint32_t sub = (lx >> 3) | ((ly >> 2) << 1) | ((lz >> 2) << 3);
                 const bool dn = (sub_neg >> sub) & 1u, dp = (sub_pos >> sub) & 1u;
                 const uint32_t X = X0 + lx, Y = Y0 + ly, Z = Z0 + lz;
                 if ((dn || dp) && X < L.NX && Y < L.NY && Z <= L.pz1) {
-                    phi_out[pidx(L, X, Y, Z)] = dn ? -1.0 : 1.0;
+                    const double ph = dn ? -1.0 : 1.0;
+                    *reinterpret_cast<double2*>(phi_out + pidx(L, X, Y, Z)) = make_double2(ph, ph);
                     not_pos = not_pos || dn; not_neg = not_neg || dp;
                 }
             }
@@ -742,8 +744,11 @@ k_sdf_field_tiled(Lattice L, TileGrid g, double* __restrict__ phi_out, const uin
                 const uint32_t Xc = X < L.NX ? X : L.NX - 1, Yc = Y < L.NY ? Y : L.NY - 1;
                 unsigned long long fl = 0ull;
                 const double v = eval(lat_x(L, Xc), lat_y(L, Yc), lat_z(L, Z), fl);
+                // even lanes store their own value and their right neighbour's with one 16-byte store (the row
+                // pitch is even, so the slot after the last point of a row exists)
+                const double vr = __shfl_down_sync(0xffffffffu, v, 1);
+                if (inside && (lane & 1u) == 0u) *reinterpret_cast<double2*>(phi_out + pidx(L, X, Y, Z)) = make_double2(v, vr);
                 if (inside) {
-                    phi_out[pidx(L, X, Y, Z)] = v;
                     my_flops += fl;
                     not_neg = not_neg || !(v < 0.0);
                     not_pos = not_pos || !(v > 0.0);

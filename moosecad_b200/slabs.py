@@ -199,7 +199,9 @@ def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=No
 
 
 _partition_cache = {}
-FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "2"))   # 0 disables the measured-load refinement
+# Rounds of measured-load refinement (0 disables it).  A round needs one run measured with the current slabs, so
+# the slabs change before runs 3 and 5 of a scene and are final from then on (inside a 5-step warm-up).
+FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "2"))
 
 
 class _Partition:
