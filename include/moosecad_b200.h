@@ -351,6 +351,13 @@ int mc_tet_quality(mc_ctx*, const double* coords, uint64_t nv, const uint64_t* t
 /* sustained DADD+DMUL (no FMA) rate in flop/s over `ms` milliseconds of work */
 int mc_probe_fp64_nofma(mc_ctx*, double* flops_per_s);
 
+/* ------------------------------------------------------------------------------------
+ * Host-only self description (no device needed): the shape tables behind the tet emission and
+ * Mesh::boundary (csrc/mc_shapes.hpp), copied into `out` (`bytes` must be sizeof(mc::ShapeTables),
+ * returned by a call with out == NULL as a positive number).  Used by the CPU tests.
+ * ------------------------------------------------------------------------------------ */
+int64_t mc_shape_tables(void* out, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,7 @@ SIGNATURES = {
     "mc_mesh_sideset": (_PU64, [_P, C.c_int]),
     "mc_tet_quality": (C.c_int, [_P, _PD, _U64, _PU64, _U64, _PD, _PD]),
     "mc_probe_fp64_nofma": (C.c_int, [_P, _PD]),
+    "mc_shape_tables": (C.c_int64, [_P, C.c_uint64]),
 }
 
 _lib = None

@@ -1347,6 +1347,16 @@ int mc_tet_quality(mc_ctx* c, const double* coords, uint64_t nv, const uint64_t*
     return rc;
 }
 
+// ---- host-only self description -------------------------------------------------------------
+int64_t mc_shape_tables(void* out, uint64_t bytes) {
+    if (!out) return (int64_t)sizeof(ShapeTables);
+    if (bytes != sizeof(ShapeTables)) return fail(MC_ERR_ARG, "mc_shape_tables: bytes != sizeof(ShapeTables)");
+    static ShapeTables tables;
+    if (!build_shape_tables(tables)) return fail(MC_ERR_STATE, "mc_shape_tables: the tables failed their consistency checks");
+    memcpy(out, &tables, sizeof(ShapeTables));
+    return MC_OK;
+}
+
 // ---- probes -----------------------------------------------------------------------------
 int mc_probe_fp64_nofma(mc_ctx* c, double* flops_per_s) {
     if (!c || !flops_per_s) return fail(MC_ERR_ARG, "mc_probe_fp64_nofma: bad argument");

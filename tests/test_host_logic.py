@@ -121,3 +121,69 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in lib.mc_last_error()
     with pytest.raises(_lib.McError):
         mc.Context(0)
+
+
+def test_shape_tables_are_self_consistent():
+    """The tables behind the tet emission and Mesh::boundary (csrc/mc_shapes.hpp): 146 shapes (nothing, whole, 6 trim
+    cases x 24 node orders), the lattice tet across every lattice face and what the two sides agree on."""
+    import ctypes as C
+    import numpy as np
+    lib = _lib.lib()
+    n = lib.mc_shape_tables(None, 0)
+    assert n > 0
+    buf = (C.c_uint8 * n)()
+    assert lib.mc_shape_tables(buf, n) == 0
+    raw = np.frombuffer(buf, dtype=np.uint8)
+    NS = 2 + 6 * 24
+    off = 0
+
+    def take(dtype, shape):
+        nonlocal off
+        cnt = int(np.prod(shape))
+        a = raw[off:off + cnt * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+        off += cnt * np.dtype(dtype).itemsize
+        return a
+
+    nodes = take(np.uint64, (NS,))
+    own = take(np.uint32, (NS,))
+    pfk = take(np.uint16, (NS, 4))
+    pfsig = take(np.uint8, (NS, 6, 12))
+    fsig = take(np.uint32, (NS, 4, 6))
+    geo = take(np.uint32, (8, 5, 4))
+    used = take(np.uint8, (NS,))
+    # pieces: case 1, 4, 6 -> one tet, 5 -> two, 2 and 3 -> three (C_CASE_N); nothing -> none
+    npieces = (nodes >> np.uint64(60)).astype(int)
+    assert npieces[0] == 0 and npieces[1] == 1
+    for kase, want in zip(range(1, 7), (1, 3, 3, 1, 2, 1)):
+        assert set(npieces[2 + 24 * (kase - 1):2 + 24 * kase]) == {want}
+    assert np.all(nodes[2:] != 0) and len(set(nodes[2:].tolist())) >= 100   # (some orders of a case give the same pieces)
+    assert np.all((own >> 24) == 4 * npieces)
+    # the untouched lattice tet: side s lies in the lattice face opposite node 3, 1, 2, 0 (Tet4::face)
+    assert pfk[1].tolist() == [1 << 3, 1 << 1, 1 << 2, 1 << 0] and own[1] & 0xffffff == 0 and used[1] == 0xf
+    assert np.all(fsig[1] == 0x16)                      # a whole lattice face, whatever the rank order
+    # every piece-face lies in at most one lattice face, and only existing faces are listed
+    for a in range(1, NS):
+        faces = [int(x) for x in pfk[a]]
+        assert sum(bin(f).count("1") for f in faces) == bin(faces[0] | faces[1] | faces[2] | faces[3]).count("1")
+        assert (faces[0] | faces[1] | faces[2] | faces[3]) < (1 << (4 * npieces[a]))
+        for k in range(4):
+            for pi in range(6):
+                sigs = [(int(fsig[a, k, pi]) >> (8 * i)) & 0xff for i in range(4)]
+                mine = [int(pfsig[a, pi, i]) for i in range(12) if (faces[k] >> i) & 1]
+                assert [s for s in sigs if s] == mine and all(mine)
+    # geometry: the tet across a face sees us across the same face, with the roles of the rank permutations
+    # swapped, and exactly one of the two comes later
+    for p in range(8):
+        for t in range(5):
+            for k in range(4):
+                g = int(geo[p, t, k])
+                assert g & (1 << 18)
+                d = [((g >> s) & 3) - 1 for s in (0, 2, 4)]
+                t2, k2 = (g >> 6) & 7, (g >> 9) & 3
+                assert sum(abs(x) for x in d) <= 1 and (d != [0, 0, 0] or t2 != t)
+                p2 = p ^ (1 if d[0] else 0) ^ (2 if d[1] else 0) ^ (4 if d[2] else 0)
+                g2 = int(geo[p2, t2, k2])
+                assert [((g2 >> s) & 3) - 1 for s in (0, 2, 4)] == [-x for x in d]
+                assert ((g2 >> 6) & 7, (g2 >> 9) & 3) == (t, k)
+                assert (g >> 11) & 7 == (g2 >> 14) & 7 and (g >> 14) & 7 == (g2 >> 11) & 7
+                assert bool(g & (1 << 17)) != bool(g2 & (1 << 17))
