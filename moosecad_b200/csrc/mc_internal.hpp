@@ -120,6 +120,17 @@ struct mc_surface {
 };
 
 namespace mc {
+// pooled scratch buffers that go back to the context's cache on every path out of a scope
+struct PoolScope {
+    mc_ctx* c;
+    std::vector<DevBuf*> bufs;
+    explicit PoolScope(mc_ctx* ctx) : c(ctx) {}
+    PoolScope(const PoolScope&) = delete;
+    PoolScope& operator=(const PoolScope&) = delete;
+    int alloc(size_t bytes, DevBuf& b) { bufs.push_back(&b); return c->alloc(bytes, b); }
+    void adopt(DevBuf& b) { bufs.push_back(&b); }
+    ~PoolScope() { for (DevBuf* b : bufs) c->release(*b); }
+};
 int cuda_fail(cudaError_t e, const char* what);
 #define MC_CUDA(call)                                              \
     do {                                                           \

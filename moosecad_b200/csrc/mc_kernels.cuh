@@ -888,29 +888,61 @@ k_vertex_count(Stuff S, unsigned long long* __restrict__ tile_tot, const uint32_
         s_cl[idx] = !in ? (uint8_t)0 : (pv < 0.0 ? 1 : (pv > 0.0 ? 2 : (pv == 0.0 ? ((wc & 0x80) ? 4 : 3) : 0)));
     });
     __syncthreads();
-    unsigned long long mine = 0ull;
-    for (int r = 0; r < TILE_ROUNDS; ++r) {
-        const uint32_t j = (uint32_t)r * TILE_THREADS + threadIdx.x;
-        const uint32_t lx = j & 15u, ly = (j >> 4) & 15u, lz = j >> 8;
-        const uint32_t X = b.X0 + lx, Y = b.Y0 + ly, Z = b.Z0 + lz;
-        if (X >= L.NX || Y >= L.NY || Z < b.zlo || Z >= b.zhi) continue;
-        const int me = (int)((lz + 1) * H + (ly + 1)) * H + (int)(lx + 1);
-        const uint8_t cv = s_cl[me];
-        uint16_t m = (cv == 1 || cv == 4) ? VM_USED : (uint16_t)0;
-        if (cv == 1 || cv == 2) {
-            const uint8_t want = cv == 1 ? 2 : 1;  // strictly opposite sign
-            const bool even = ((X + Y + Z) & 1u) == 0u;
-            const int nd = even ? 9 : 3;
+    // bit masks of the box's point rows (bit bx): negative / positive / zero-but-used
+    __shared__ uint32_t s_rn[H * H], s_rp[H * H], s_ru[H * H];
+    for (int r = (int)threadIdx.x; r < H * H; r += TILE_THREADS) {
+        uint32_t ng = 0u, ps = 0u, us = 0u;
 #pragma unroll
-            for (int s = 0; s < 9; ++s) {
-                if (s >= nd) break;
-                const KDir kd = kdir(s);
-                if (s_cl[me + (kd.z * H + kd.y) * H + kd.x] == want) m |= (uint16_t)(1u << s);
-            }
+        for (int i = 0; i < H; ++i) {
+            const uint32_t c = s_cl[r * H + i];
+            ng |= (c == 1u ? 1u : 0u) << i;
+            ps |= (c == 2u ? 1u : 0u) << i;
+            us |= (c == 4u ? 1u : 0u) << i;
         }
-        S.vmask[pidx(L, X, Y, Z)] = m;
-        const uint32_t ncut = (uint32_t)__popc(m & VM_CUT_MASK);
-        mine += (unsigned long long)(ncut + ((m & VM_USED) ? 1u : 0u)) | ((unsigned long long)ncut << 32);
+        s_rn[r] = ng; s_rp[r] = ps; s_ru[r] = us;
+    }
+    __syncthreads();
+    // every thread settles one x-row of 16 vertices: the edge along canonical direction s is cut iff its ends
+    // have strictly opposite signs — nine row masks, then transposed into the per-vertex words
+    unsigned long long mine = 0ull;
+    {
+        const uint32_t ly = threadIdx.x & 15u, lz = threadIdx.x >> 4;
+        const uint32_t Y = b.Y0 + ly, Z = b.Z0 + lz;
+        if (b.X0 < L.NX && Y < L.NY && Z >= b.zlo && Z < b.zhi) {
+            const int r = (int)(lz + 1u) * H + (int)(ly + 1u);
+            const uint32_t nxt = min(TS, L.NX - b.X0);
+            const uint32_t valid = (nxt >= 16u ? 0xffffu : ((1u << nxt) - 1u)) << 1;
+            const uint32_t ng = s_rn[r], ps = s_rp[r];
+            // vertices with even X + Y + Z own nine edges, the others the three along the axes (bit bx <-> X = X0 + bx - 1)
+            const uint32_t even = ((b.X0 + Y + Z) & 1u) ? 0x55555555u : 0xaaaaaaaau;
+            uint32_t cut[9];
+#pragma unroll
+            for (int sdir = 0; sdir < 9; ++sdir) {
+                const KDir kd = kdir(sdir);
+                const int rn = r + kd.z * H + kd.y;
+                uint32_t nn = s_rn[rn], pp = s_rp[rn];
+                if (kd.x > 0) { nn >>= 1; pp >>= 1; }
+                if (kd.x < 0) { nn <<= 1; pp <<= 1; }
+                cut[sdir] = ((ng & pp) | (ps & nn)) & valid & (sdir < 3 ? 0xffffffffu : even);
+            }
+            const uint32_t used = (ng | s_ru[r]) & valid;
+            uint32_t ncut = 0u;
+#pragma unroll
+            for (int sdir = 0; sdir < 9; ++sdir) ncut += (uint32_t)__popc(cut[sdir]);
+            mine = (unsigned long long)(ncut + (uint32_t)__popc(used)) | ((unsigned long long)ncut << 32);
+            uint32_t wds[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                uint32_t m = ((used >> (i + 1)) & 1u) ? (uint32_t)VM_USED : 0u;
+#pragma unroll
+                for (int sdir = 0; sdir < 9; ++sdir) m |= ((cut[sdir] >> (i + 1)) & 1u) << sdir;
+                if (i & 1) wds[i >> 1] |= m << 16; else wds[i >> 1] = m;
+            }
+            // the row of masks is 32 aligned bytes (row pitch and tile origin are multiples of 16 points)
+            uint4* out = reinterpret_cast<uint4*>(S.vmask + pidx(L, b.X0, Y, Z));
+            out[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            out[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+        }
     }
     const unsigned long long tot = block_sum(mine, &s_acc);
     if (threadIdx.x == 0) tile_tot[tile] = tot;

@@ -315,15 +315,16 @@ int mc_eval_points_device(mc_ctx* c, const mc_tape* t, int32_t root, double slac
     std::string err;
     int rc = t->compile(root, slack, p, err);
     if (rc != MC_OK) return fail(rc, err);
+    PoolScope scratch(c);
     DevBuf dp;
+    scratch.adopt(dp);
     rc = upload_program(c, p, dp);
     if (rc != MC_OK) return rc;
     k_eval_points<<<blocks_for(n, 256), 256, 0, c->stream>>>((const uint64_t*)dp.p, (const double*)d_points, n,
                                                               (double*)d_out);
     c->launches++;
     MC_CUDA(cudaGetLastError());
-    MC_CUDA(cudaStreamSynchronize(c->stream));  // dp is recycled below
-    c->release(dp);
+    MC_CUDA(cudaStreamSynchronize(c->stream));  // dp is recycled when `scratch` goes out of scope
     return MC_OK;
 }
 
@@ -332,11 +333,11 @@ int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, cons
     if (!c || !t || (n && (!points || !out))) return fail(MC_ERR_ARG, "mc_eval_points: bad argument");
     if (n == 0) return MC_OK;
     MC_CUDA(cudaSetDevice(c->device));
+    PoolScope scratch(c);
     DevBuf dpts, dout;
-    int rc = c->alloc(n * 24, dpts);
+    int rc = scratch.alloc(n * 24, dpts);
+    if (rc == MC_OK) rc = scratch.alloc(n * 8, dout);
     if (rc != MC_OK) return rc;
-    rc = c->alloc(n * 8, dout);
-    if (rc != MC_OK) { c->release(dpts); return rc; }
     MC_CUDA(cudaMemcpyAsync(dpts.p, points, n * 24, cudaMemcpyHostToDevice, c->stream));
     rc = mc_eval_points_device(c, t, root, slack, dpts.p, n, dout.p);
     if (rc == MC_OK) {
@@ -344,8 +345,6 @@ int mc_eval_points(mc_ctx* c, const mc_tape* t, int32_t root, double slack, cons
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy back");
     }
-    c->release(dpts);
-    c->release(dout);
     return rc;
 }
 
@@ -972,8 +971,9 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
         const unsigned lgrid = list_grid(m);
         const double* coords = (const double*)m->d_coords.p;
         const uint64_t nlist = quality ? m->counters[CN_LISTED_TETS] : 0;
+        PoolScope scratch(c);   // (kernels queued on the stream keep using the buffers: the cache hands them out in stream order)
         DevBuf qlist;
-        rc = c->alloc(std::max<uint64_t>(nlist, 1) * 8, qlist);
+        rc = scratch.alloc(std::max<uint64_t>(nlist, 1) * 8, qlist);
         if (rc != MC_OK) return rc;
         unsigned long long* ql = (unsigned long long*)qlist.p;
         // plain lattice tets: one evaluation per global (step, parity) class when the steps take few
@@ -986,7 +986,7 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
             std::vector<uint8_t> ids;
             if (!(m->flags & MC_OPT_PER_TILE_QUALITY) && build_quality_classes(m->L, steps, ids)) {
                 const size_t off_present = steps.size() * 8, off_ids = off_present + (size_t)QC_K * QC_K * 4;
-                rc = c->alloc(off_ids + ids.size() + 16, qcls);
+                rc = scratch.alloc(off_ids + ids.size() + 16, qcls);
                 if (rc != MC_OK) return rc;
                 char* base = (char*)qcls.p;
                 MC_CUDA(cudaMemcpyAsync(base, steps.data(), steps.size() * 8, cudaMemcpyHostToDevice, s));
@@ -1041,8 +1041,6 @@ int mc_tessellate_emit_tets(mc_mesh* m, uint64_t tet_base, const void* d_lower_p
                 k_tet_emit<unsigned long long, false><<<lgrid, TILE_THREADS, tet_emit_smem_bytes<unsigned long long>(), s>>>(S, out, ql, Q, counters, T.c_active, T.n_c_active, counters + CUR_TET_SURF);
             }
         }
-        c->release(qlist);
-        c->release(qcls);
         c->launches += quality ? 5 : 2;
         MC_CUDA(cudaGetLastError());
         if ((rc = c->stage_check("stage tet emit / quality list")) != MC_OK) return rc;
