@@ -426,11 +426,13 @@ def gather_slab_meshes(handles):
     return np.concatenate(coords), np.concatenate(tets), combine_stats(stats)
 
 
-def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0, return_stats=False):
+def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, flags=0, return_stats=False, id_offset=0):
     """Mesh the lattice as `n_slabs` z-slabs one after the other on ONE device and merge the
     results on the host (global vertex ids).  Exercises exactly the phases a multi-GPU run
     goes through (counts -> bases -> vertices -> plane table -> tets); also a way to mesh a
-    lattice whose working set exceeds one GPU.  Returns (coords (n,3) f64, tets (m,4) u64)."""
+    lattice whose working set exceeds one GPU.  Returns (coords (n,3) f64, tets (m,4) u64).
+    id_offset: the global vertex ids start there instead of at 0 (as if slabs with that many vertices lay
+    below; ids >= 2^32 take the 64-bit index kernels)."""
     import numpy as np
     lib = _lib.lib()
     dim = lattice_dim(obj.bbox(), float(resolution))
@@ -451,6 +453,7 @@ def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, f
         coords, tets, stats = [], [], []
         for r, h in enumerate(handles):
             vb, tb = bases_from_counts(counts, r)
+            vb += int(id_offset)
             _lib.check(lib.mc_tessellate_emit_vertices(h, vb))
             if r > 0:
                 # coordinates of the slab below's top tile layer, straight from its device buffer
@@ -458,7 +461,7 @@ def tessellate_slabs_one_device(ctx, obj, resolution, relative_error, n_slabs, f
                 _lib.check(lib.mc_mesh_upper_layer_vertices(handles[r - 1], C.byref(first), C.byref(cnt)))
                 _lib.check(lib.mc_mesh_upper_layer_coords(handles[r - 1], C.byref(xyz)))
                 vb_below, _ = bases_from_counts(counts, r - 1)
-                _lib.check(lib.mc_tessellate_set_lower_coords(h, xyz, vb_below + first.value, cnt.value))
+                _lib.check(lib.mc_tessellate_set_lower_coords(h, xyz, vb_below + int(id_offset) + first.value, cnt.value))
             rc = lib.mc_tessellate_emit_tets(h, tb, lower)
             if rc not in (_lib.MC_OK, _lib.MC_ERR_DIVERGED):
                 _lib.check(rc)

@@ -105,6 +105,23 @@ def test_slabs_match_single_slab(scene, n_slabs, ctx):
     assert len(np.unique(coords, axis=0)) == len(coords)
 
 
+@pytest.mark.gpu
+def test_vertex_ids_beyond_32_bits(ctx):
+    """Global vertex ids >= 2^32 (a slab high up in a very large lattice) switch the tet emission, the quality
+    list, the checksums and the boundary to 64-bit indices: same mesh, ids shifted."""
+    import moosecad_b200 as mc
+    g = mc.Geom()
+    from moosecad_b200 import scenes
+    obj, res = scenes.synthetic_csg(g, 12, seed=5), 1.0 / 41
+    obj.backend.set_parameters(0.1, 1.0)
+    base = (1 << 32) + 12345
+    c0, t0, s0 = slabs.tessellate_slabs_one_device(ctx, obj, res, 0.2, 2, return_stats=True)
+    c1, t1, s1 = slabs.tessellate_slabs_one_device(ctx, obj, res, 0.2, 2, return_stats=True, id_offset=base)
+    assert np.array_equal(c0.view(np.uint64), c1.view(np.uint64))
+    assert t1.min() >= base and np.array_equal(t1 - np.uint64(base), t0)
+    assert s0 == s1
+
+
 def test_partition_balanced():
     c = [0.02] * 20 + [1.0] * 60 + [0.02] * 20
     for w in (2, 4, 8):
