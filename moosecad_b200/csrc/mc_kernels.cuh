@@ -1273,7 +1273,10 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, const uint32_t* __restrict__
     __shared__ uint8_t s_nvu[8];
     __shared__ unsigned long long s_nbase[8];
     __shared__ TileBox s_nbox[8];
-    __shared__ __align__(16) IndexT s_out[5][TILE_THREADS][4];
+    // (row stride TILE_THREADS + 5 tets: the copy-out below reads (tet g % 5, cell g / 5) and 5 t + c takes every
+    // residue mod 8 over eight consecutive g, so its 16-byte shared-memory loads are free of bank conflicts)
+    constexpr uint32_t OUT_STRIDE = TILE_THREADS + 5;
+    __shared__ __align__(16) IndexT s_out[5][OUT_STRIDE][4];
     if (threadIdx.x < 8) {
         const uint32_t tix = (uint32_t)(tile % S.g.ntx) + (threadIdx.x & 1u);
         const uint32_t tiy = (uint32_t)((tile / S.g.ntx) % S.g.nty) + ((threadIdx.x >> 1) & 1u);
@@ -1326,17 +1329,17 @@ k_tet_emit_full(Stuff S, IndexT* __restrict__ tets, const uint32_t* __restrict__
                 const uint32_t i4 = s_id[at + az], i5 = s_id[at + ax + az], i6 = s_id[at + ax + ay + az], i7 = s_id[at + ay + az];
                 const bool flip = (fx ^ fy ^ fz) != 0u;
                 // Tile::TETS, nodes 0 and 1 swapped when the cell is mirrored an odd number of times
-                s_out4[0 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i1, i0, i5, i2) : make_uint4(i0, i1, i5, i2);
-                s_out4[1 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i2, i0, i5, i7) : make_uint4(i0, i2, i5, i7);
-                s_out4[2 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i7, i0, i5, i4) : make_uint4(i0, i7, i5, i4);
-                s_out4[3 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i6, i2, i5, i7) : make_uint4(i2, i6, i5, i7);
-                s_out4[4 * TILE_THREADS + threadIdx.x] = flip ? make_uint4(i2, i0, i7, i3) : make_uint4(i0, i2, i7, i3);
+                s_out4[0 * OUT_STRIDE + threadIdx.x] = flip ? make_uint4(i1, i0, i5, i2) : make_uint4(i0, i1, i5, i2);
+                s_out4[1 * OUT_STRIDE + threadIdx.x] = flip ? make_uint4(i2, i0, i5, i7) : make_uint4(i0, i2, i5, i7);
+                s_out4[2 * OUT_STRIDE + threadIdx.x] = flip ? make_uint4(i7, i0, i5, i4) : make_uint4(i0, i7, i5, i4);
+                s_out4[3 * OUT_STRIDE + threadIdx.x] = flip ? make_uint4(i6, i2, i5, i7) : make_uint4(i2, i6, i5, i7);
+                s_out4[4 * OUT_STRIDE + threadIdx.x] = flip ? make_uint4(i2, i0, i7, i3) : make_uint4(i0, i2, i7, i3);
             }
             __syncthreads();
             // coalesced copy: output tet g of this round = cell g / 5, lattice tet g % 5
             const uint32_t ncell = min((uint32_t)TILE_THREADS, n - base);
             uint4* dst4 = reinterpret_cast<uint4*>(tets + 4 * (tb + 5ull * base));
-            for (uint32_t g = threadIdx.x; g < 5u * ncell; g += TILE_THREADS) dst4[g] = s_out4[(g % 5u) * TILE_THREADS + g / 5u];
+            for (uint32_t g = threadIdx.x; g < 5u * ncell; g += TILE_THREADS) dst4[g] = s_out4[(g % 5u) * OUT_STRIDE + g / 5u];
             __syncthreads();
         }
         continue;
