@@ -631,6 +631,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     // corner classes of the tile's cells: bit 0 = post-warp phi < 0, bit 1 = raw phi > 0, bit 2 = raw phi <= 0
     constexpr int H = CC_H;
     __shared__ uint8_t s_cls[CC_NP];
+    __shared__ uint8_t s_wc[CC_NP];            // warp codes of the corners (final since k_warp_codes)
     __shared__ uint32_t s_rowneg[H * H], s_rowpos[H * H];  // bit i of a point row: class bit 0 / bit 1 of its point i
     __shared__ uint16_t s_list[TILE_POINTS];   // surface cells (local index)
     __shared__ uint32_t s_ci[CC_PASS];         // cinfo of the surface cells being assembled, by list slot
@@ -643,6 +644,7 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
     stage_points<H, 0, true>(L, X0, Y0, Z0, [&](int idx, bool in, double raw, uint8_t wc) {
         const double w = (wc & 0x7f) ? 0.0 : raw;
         s_phi[idx] = w;
+        s_wc[idx] = (uint8_t)(wc & 0x7f);
         s_cls[idx] = in ? (uint8_t)((w < 0.0 ? 1 : 0) | (raw > 0.0 ? 2 : 0) | (raw <= 0.0 ? 4 : 0)) : (uint8_t)0;
     });
     __syncthreads();
@@ -757,8 +759,8 @@ k_classify_cells(Stuff S, const uint64_t* __restrict__ prog, unsigned long long*
                 if (((used >> nn) & 1u) && pn == 0.0) {
                     uint32_t X, Y, Z;
                     corner_xyz(c, tet_corner(c, (int)t, nn), X, Y, Z);
-                    const size_t pi = pidx(L, X, Y, Z);
-                    L.wcode[pi] = (uint8_t)(L.wcode[pi] | 0x80u);
+                    // (a plain store: the warp code in the low bits is final, everybody who marks the vertex writes the same byte)
+                    L.wcode[pidx(L, X, Y, Z)] = (uint8_t)(s_wc[li[nn]] | 0x80u);
                 }
             }
         }
@@ -1449,10 +1451,13 @@ k_full_tile_quality(Stuff S, unsigned long long* __restrict__ counters) {
 // chases global pointers.  Dynamic shared memory layout: see tet_emit_smem_bytes().
 constexpr int TE_H = (int)TS + 1;
 constexpr int TE_NP = TE_H * TE_H * TE_H;
+// direction index (C_DIR) of the lattice edge between two corners of the staged box, by the difference of their
+// box indices (dz * TE_H^2 + dy * TE_H + dx + TE_DIRMID), 255 = not an edge
+constexpr int TE_DIRMID = TE_H * TE_H + TE_H + 1, TE_DIRTAB = 2 * TE_DIRMID + 2;
 template <typename IndexT>
 constexpr size_t tet_emit_smem_bytes() {
     return (size_t)TE_NP * sizeof(IndexT) + (size_t)TE_NP * 2 /*mask*/ + 15 +
-           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, qoff*/;
+           (size_t)TILE_POINTS * 2 * 4 /*ci, off, list, qoff*/ + (size_t)TILE_THREADS * 4 * 4 /*node indices*/ + TE_DIRTAB /*directions*/;
 }
 
 // one output tet = one (u32 ids) or two (u64 ids) 16-byte stores
@@ -1474,6 +1479,16 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_n;
     const Lattice& L = S.L;
+    {
+        // (same carve-up as below; filled once per block)
+        IndexT* g0 = reinterpret_cast<IndexT*>(te_smem);
+        uint16_t* m0 = reinterpret_cast<uint16_t*>(g0 + TE_NP);
+        uint16_t* c0 = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(m0 + TE_NP) + 15) & ~(uintptr_t)15);
+        uint8_t* tab = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(c0 + 4 * TILE_POINTS) + 4 * TILE_THREADS);
+        for (int i = (int)threadIdx.x; i < TE_DIRTAB; i += TILE_THREADS) tab[i] = 255;
+        __syncthreads();
+        if (threadIdx.x < 18) tab[(C_DIR[threadIdx.x][2] * TE_H + C_DIR[threadIdx.x][1]) * TE_H + C_DIR[threadIdx.x][0] + TE_DIRMID] = (uint8_t)threadIdx.x;
+    }
     uint32_t tile;
     while (next_tile(tile_list, n_list, cursor, tile)) {  // active cell tiles
     uint32_t X0, Y0, Z0;
@@ -1486,6 +1501,8 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
     uint16_t* s_off = s_ci + TILE_POINTS;   // first output tet of the cell, relative to the tile
     uint16_t* s_list = s_off + TILE_POINTS; // cells with trimmed / dropped tets
     uint16_t* s_qoff = s_list + TILE_POINTS; // first quality-list slot of the cell, relative to the tile
+    int* s_li = reinterpret_cast<int*>(s_qoff + TILE_POINTS) + 4 * threadIdx.x;   // this thread's four node indices (run-time indexed)
+    uint8_t* s_dirtab = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(s_qoff + TILE_POINTS) + 4 * TILE_THREADS);
     __shared__ unsigned long long s_qbase;
     constexpr int T[5][4] = {{0, 1, 5, 2}, {0, 2, 5, 7}, {0, 7, 5, 4}, {2, 6, 5, 7}, {0, 2, 7, 3}};  // Tile::TETS
     const uint64_t tb = S.ttbase[tile];
@@ -1668,9 +1685,9 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             load_tet_mixed(L, c, t, tn);
             classify_tet<false, true>(L, c, t, tn, nullptr, 0, to);
         }
-        int li[4];
+        // the four nodes' indices in the staged box live in shared memory: the node codes index them at run time
 #pragma unroll
-        for (int m = 0; m < 4; ++m) li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);
+        for (int m = 0; m < 4; ++m) s_li[m] = (int)((tn.Z[m] - Z0) * TE_H + (tn.Y[m] - Y0)) * TE_H + (int)(tn.X[m] - X0);
         const unsigned long long at = QUALITY ? s_qbase + s_qoff[j] + before : 0ull;
         for (int q = 0; q < to.n; ++q) {
             IndexT id[4];
@@ -1678,14 +1695,14 @@ k_tet_emit(Stuff S, IndexT* __restrict__ tets, unsigned long long* __restrict__ 
             for (int m = 0; m < 4; ++m) {
                 const int code = to.node(q, m);
                 if (code < 4) {
-                    id[m] = s_gid[pick4(li[0], li[1], li[2], li[3], code)];
+                    id[m] = s_gid[s_li[code]];
                 } else {
-                    const int i = (code - 4) >> 2, jn = (code - 4) & 3;
-                    int d = dir_index((int)tet_X(tn, jn) - (int)tet_X(tn, i), (int)tet_Y(tn, jn) - (int)tet_Y(tn, i),
-                                      (int)tet_Z(tn, jn) - (int)tet_Z(tn, i));
+                    // cut vertex on the edge i -> jn: owned by the end from which the direction is canonical (d < 9)
+                    const int li_i = s_li[(code - 4) >> 2], li_j = s_li[(code - 4) & 3];
+                    int d = (int)s_dirtab[li_j - li_i + TE_DIRMID];
                     const bool own_i = d < 9;
                     if (!own_i) d -= 9;
-                    const int lo = pick4(li[0], li[1], li[2], li[3], own_i ? i : jn);
+                    const int lo = own_i ? li_i : li_j;
                     id[m] = (IndexT)cut_vertex_id((long long)s_gid[lo], s_mask[lo], d);
                 }
             }
