@@ -199,9 +199,10 @@ def layer_costs_sharded(ctx, obj, resolution, rank, world, group=None, device=No
 
 
 _partition_cache = {}
-# Rounds of measured-load refinement (0 disables it).  A round needs one run measured with the current slabs, so
-# the slabs change before runs 3 and 5 of a scene and are final from then on (inside a 5-step warm-up).
-FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "2"))
+# Rounds of measured-load refinement (0 disables it).  A round uses the device times of the previous run of the
+# scene, shared by a tiny all-gather BEFORE the run starts, so the slabs change at the start of runs 2..5 and are
+# final from then on (inside a 5-step warm-up); the best partition seen wins if a round makes things worse.
+FEEDBACK_ROUNDS = int(__import__("os").environ.get("MC_SLAB_FEEDBACK", "4"))
 
 
 class _Partition:
@@ -213,6 +214,7 @@ class _Partition:
         self.costs, self.slabs = list(costs), slabs
         self.my_last_us = 0       # device time of this rank's last run with `slabs` (microseconds, 0 = unknown)
         self.rounds = 0
+        self.best = None          # (slowest rank's time, slabs) of the best partition measured so far
 
 
 def cached_partition(ctx, obj, resolution, rank, world, group=None, device=None, host_group=None):
@@ -238,6 +240,13 @@ def refine_partition(ent, times_us):
     if ent.rounds >= FEEDBACK_ROUNDS or any(t <= 0 for t in times_us):
         return False
     mean = sum(times_us) / len(times_us)
+    best = getattr(ent, "best", None)
+    if best is not None and max(times_us) > best[0]:
+        # the last round made the slowest rank slower: back to the best partition seen, and stop
+        ent.slabs = best[1]
+        ent.rounds = FEEDBACK_ROUNDS
+        return True
+    ent.best = (max(times_us), list(ent.slabs))
     if max(times_us) <= 1.015 * mean:
         ent.rounds = FEEDBACK_ROUNDS
         return False
@@ -288,6 +297,13 @@ class SlabMesher:
             # the estimate is deterministic, every rank derives the same partition; it is computed
             # once per (scene, resolution, world) and cached
             self._part = cached_partition(ctx, obj, self.res, self.rank, self.world, group, device, host_group)
+            if self._part.rounds < FEEDBACK_ROUNDS and self._part.my_last_us > 0:
+                # measured-load refinement: every rank holds a device time of the previous run with these slabs
+                # (report_device_time; all ranks report or none does, so they take this branch together)
+                g, d = (host_group, "cpu") if host_group is not None else (group, device)
+                times = [int(c[0]) for c in exchange_counts(self._part.my_last_us, 0, g, d)]
+                refine_partition(self._part, times)
+                self._part.my_last_us = 0
             self.slabs = self._part.slabs
         else:
             self._part = None
@@ -322,8 +338,7 @@ class SlabMesher:
             _lib.check(lib.mc_mesh_counts(out, counts))
             top_first, top_count = C.c_uint64(), C.c_uint64()
             _lib.check(lib.mc_mesh_upper_layer_vertices(out, C.byref(top_first), C.byref(top_count)))
-            # (+ this rank's device time of the previous run with the same slabs: measured-load refinement)
-            extra = (top_first.value, top_count.value, self._part.my_last_us if self._part is not None else 0)
+            extra = (top_first.value, top_count.value)
             if self.world > 1 and self.host_group is None:
                 # device group: the stream is idle right after phase 1, the tiny all-gather is not
                 # queued behind anything
@@ -336,10 +351,6 @@ class SlabMesher:
             elif self.world == 1:
                 self.all_counts = [(counts[0], counts[1]) + extra]
             self.vertex_base, self.tet_base = bases_from_counts(self.all_counts, self.rank)
-            if self._part is not None and self.world > 1:
-                # the next run of this scene uses slabs refined with the times every rank just shared
-                if refine_partition(self._part, [int(c[4]) for c in self.all_counts]):
-                    self._part.my_last_us = 0
             lap("exchange_counts")
             _lib.check(lib.mc_tessellate_emit_vertices(out, self.vertex_base))
             lap("emit_vertices_launch")

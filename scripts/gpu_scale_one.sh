@@ -8,7 +8,7 @@ if [ "${PYTEST:-0}" = "1" ]; then
   echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; tail -3 gpurun_out/${TAG}_pytest.log
 fi
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
-    bench.py --gpus $N --steps 10 --warmup 4 $EXTRA > gpurun_out/${TAG}_bench_$N.json 2> gpurun_out/${TAG}_bench_$N.err
+    bench.py --gpus $N --steps ${STEPS:-20} --warmup ${WARMUP:-5} $EXTRA > gpurun_out/${TAG}_bench_$N.json 2> gpurun_out/${TAG}_bench_$N.err
 echo "bench N=$N rc=$?"; tail -3 gpurun_out/${TAG}_bench_$N.err
 python - <<PY
 import json
