@@ -260,3 +260,23 @@ def test_measured_load_refinement_converges():
     before = list(ent.slabs)
     ent.rounds = 0
     assert not slabs.refine_partition(ent, [0] + times(ent.slabs)[1:]) and ent.slabs == before
+
+
+def test_refinement_keeps_the_best_partition_seen():
+    """A refinement round that makes the slowest rank slower is undone: the best partition measured so far comes
+    back and the refinement stops (the cost model inside a slab is only a rescaled estimate)."""
+    n, world = 256, 4
+    ent = slabs._Partition([1.0] * n, slabs.partition_balanced([1.0] * n, world))
+    first = list(ent.slabs)
+    assert slabs.refine_partition(ent, [900, 1000, 1100, 1000]) and ent.slabs != first and ent.rounds == 1
+    assert ent.best == (1100, first)
+    # the new slabs turn out worse (slowest rank 1300 > 1100): back to the first partition, no further rounds
+    assert slabs.refine_partition(ent, [700, 1300, 1000, 1000]) and ent.slabs == first
+    assert ent.rounds == slabs.FEEDBACK_ROUNDS
+    assert not slabs.refine_partition(ent, [900, 1000, 1100, 1000]) and ent.slabs == first
+    # ... while a round that helps is kept and becomes the new best
+    ent2 = slabs._Partition([1.0] * n, slabs.partition_balanced([1.0] * n, world))
+    slabs.refine_partition(ent2, [900, 1000, 1100, 1000])
+    second = list(ent2.slabs)
+    slabs.refine_partition(ent2, [1000, 1010, 1030, 1000])
+    assert ent2.best == (1030, second)
