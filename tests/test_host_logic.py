@@ -187,3 +187,42 @@ def test_shape_tables_are_self_consistent():
                 assert ((g2 >> 6) & 7, (g2 >> 9) & 3) == (t, k)
                 assert (g >> 11) & 7 == (g2 >> 14) & 7 and (g >> 14) & 7 == (g2 >> 11) & 7
                 assert bool(g & (1 << 17)) != bool(g2 & (1 << 17))
+
+
+def _random_tree(g, rng, depth):
+    """A random geom.* expression: primitives under translate / rotate / scale and smooth booleans."""
+    if depth == 0 or rng.random() < 0.3:
+        k = int(rng.integers(0, 4))
+        if k == 0:
+            o = g.sphere(float(rng.uniform(0.05, 0.6)))
+        elif k == 1:
+            o = g.cube(*(float(x) for x in rng.uniform(0.1, 0.9, 3)), float(rng.choice([0.0, 0.02, 0.1])))
+        elif k == 2:
+            o = g.cylinder(float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.05, 0.4)), float(rng.uniform(0.05, 0.4)),
+                           float(rng.choice([0.0, 0.05])))
+        else:
+            o = g.sphere(float(rng.uniform(0.1, 0.4))).scale(*(float(x) for x in rng.uniform(0.5, 2.0, 3)))
+    else:
+        a, b = _random_tree(g, rng, depth - 1), _random_tree(g, rng, depth - 1)
+        r = float(rng.choice([0.0, 0.03, 0.2]))
+        o = [a.union, a.intersection, a.difference][int(rng.integers(0, 3))](b, r)
+    for _ in range(int(rng.integers(0, 3))):
+        k = int(rng.integers(0, 3))
+        v = [float(x) for x in (rng.uniform(-1, 1, 3) if k == 0 else rng.uniform(-3.2, 3.2, 3) if k == 1 else rng.uniform(0.3, 2.5, 3))]
+        o = [o.translate, o.rotate, o.scale][k](*v)
+    return o
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_scenes_bbox_and_lowering(seed, oracle):
+    """Host lowering against the oracle on random scenes: identical bounding boxes (bbox 0.11.2 / implicit3d rules:
+    union dilation, cofactor inverse of composed transforms) at every level, and the program compiles within the
+    evaluator's limits."""
+    rng_a, rng_b = np.random.default_rng(seed), np.random.default_rng(seed)
+    ga, gb = mc.Geom(), mc.Geom(oracle.OracleScene())
+    a, b = _random_tree(ga, rng_a, 3), _random_tree(gb, rng_b, 3)
+    ba, bb = np.array(a.bbox()), np.array(b.bbox())
+    assert np.array_equal(ba, bb), (seed, ba, bb)
+    if np.all(np.isfinite(ba)) and np.all(ba[3:] > ba[:3]):
+        info = ga.backend.program_info(a.node, 0.01)
+        assert 0 < info["words"] < (1 << 22) and info["value_depth"] <= 48 and info["point_depth"] <= 6
