@@ -107,6 +107,9 @@ int mc_tape_program_info(const mc_tape*, int32_t root, double slack, uint64_t* w
 /* content hash of that program and the root bounding box (everything the device sees of the
  * scene): equal scenes lowered twice hash alike.  Key of the slab-partition cache (slabs.py). */
 int mc_tape_program_hash(const mc_tape*, int32_t root, double slack, uint64_t* hash);
+/* the flat device program itself (csrc/mc_program.h), host only: returns its length in 8-byte words and, when
+ * `out` is given (capacity words), copies it.  tests/program_interp.py evaluates it on the CPU against the oracle. */
+int64_t mc_tape_program_words(const mc_tape*, int32_t root, double slack, uint64_t* out, uint64_t capacity);
 
 /* ------------------------------------------------------------------------------------
  * Device context.

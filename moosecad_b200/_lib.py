@@ -71,6 +71,7 @@ SIGNATURES = {
     "mc_tape_bbox": (C.c_int, [_P, _I32, _PD]),
     "mc_tape_program_info": (C.c_int, [_P, _I32, _D, _PU64, _PI32, _PI32, _PU64]),
     "mc_tape_program_hash": (C.c_int, [_P, _I32, _D, _PU64]),
+    "mc_tape_program_words": (C.c_int64, [_P, _I32, _D, _PU64, C.c_uint64]),
     "mc_ctx_new": (_P, [C.c_int, _P]),
     "mc_ctx_free": (None, [_P]),
     "mc_ctx_device": (C.c_int, [_P]),

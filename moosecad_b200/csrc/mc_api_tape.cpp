@@ -259,6 +259,19 @@ int mc_tape_program_info(const mc_tape* t, int32_t root, double slack, uint64_t*
     return MC_OK;
 }
 
+int64_t mc_tape_program_words(const mc_tape* t, int32_t root, double slack, uint64_t* out, uint64_t capacity) {
+    if (!t) return fail(MC_ERR_ARG, "mc_tape_program_words: null tape");
+    Program p;
+    std::string err;
+    int rc = t->compile(root, slack, p, err);
+    if (rc != MC_OK) return fail(rc, err);
+    if (out) {
+        if (capacity < p.words.size()) return fail(MC_ERR_ARG, "mc_tape_program_words: buffer too small");
+        for (size_t i = 0; i < p.words.size(); ++i) out[i] = p.words[i];
+    }
+    return (int64_t)p.words.size();
+}
+
 int mc_tape_program_hash(const mc_tape* t, int32_t root, double slack, uint64_t* hash) {
     if (!t || !hash) return fail(MC_ERR_ARG, "mc_tape_program_hash: bad argument");
     Program p;

@@ -226,3 +226,64 @@ def test_random_scenes_bbox_and_lowering(seed, oracle):
     if np.all(np.isfinite(ba)) and np.all(ba[3:] > ba[:3]):
         info = ga.backend.program_info(a.node, 0.01)
         assert 0 < info["words"] < (1 << 22) and info["value_depth"] <= 48 and info["point_depth"] <= 6
+
+
+def _program_words(obj, slack):
+    import ctypes as C
+    lib = _lib.lib()
+    n = lib.mc_tape_program_words(obj.backend.handle, obj.node, float(slack), None, 0)
+    assert n > 0
+    buf = (C.c_uint64 * n)()
+    assert lib.mc_tape_program_words(obj.backend.handle, obj.node, float(slack), buf, n) == n
+    return list(buf)
+
+
+LOWERING_SCRIPTS = {
+    "cube": scenes.CUBE_LUA, "sphere": scenes.SPHERE_LUA, "xplicit": scenes.XPLICIT_WITH_TOP_LUA,
+    "cyl": "return { c = geom.cylinder(2.0, 0.5, 0.25, 0.1):rotate(0.3, 0.2, 0.1):translate(1, 2, 3):scale(2, 3, 4):volume() }",
+    "mix": "a = geom.sphere(0.3):translate(0.2, 0, 0)\nb = geom.cube(0.5, 0.4, 0.3, 0.05):rotate(1, 2, 3)\n"
+           "c = geom.plane_hesian(1, 2, 3, 0.1)\nd = geom.plane_3_points(0,0,0.2, 1,0,0.25, 0,1,0.3)\n"
+           "return { u = a:union(b, 0.1):intersection(c, 0.05):difference(d, 0.0):volume(), "
+           "k = geom.i_cone(0.5):intersection(geom.i_cylinder(0.4), 0.1):scale(1, 2, 1):boundary() }",
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOWERING_SCRIPTS))
+def test_lowered_program_evaluates_like_the_oracle(name, oracle):
+    """The flat device program the host lowering emits (opcodes, parameters, per-node slack constants, composed
+    matrices, jump targets), run by a plain-Python reference interpreter (tests/program_interp.py), gives the
+    oracle's recursive approx_value bit for bit — the lowering is checked on the CPU, independently of the CUDA
+    evaluator (which tests/test_gpu_parity.py checks against the same oracle on the device)."""
+    import program_interp
+    oracle.set_libm_mode(1)
+    L = oracle.lib()
+    a, b = _both(LOWERING_SCRIPTS[name], oracle)
+    rng = np.random.default_rng(3)
+    for k in sorted(a):
+        bb = np.array(a[k].obj.bbox())
+        lo = np.where(np.isfinite(bb[:3]), bb[:3], -2.0) - 0.3
+        hi = np.where(np.isfinite(bb[3:]), bb[3:], 2.0) + 0.3
+        pts = rng.uniform(lo, hi, size=(300, 3))
+        pts[:3] = 0.0
+        for slack in (0.0, 0.07, 1.0):
+            run = program_interp.Interp(_program_words(a[k].obj, slack), L.orc_exp, L.orc_ln)
+            want = b[k].obj.backend.eval_points(b[k].obj.node, slack, pts)
+            got = np.array([run(float(p[0]), float(p[1]), float(p[2])) for p in pts])
+            same = (got.view(np.uint64) == want.view(np.uint64)) | (got == want)
+            assert same.all(), (name, k, slack, pts[~same][:3], got[~same][:3], want[~same][:3])
+
+
+def test_synthetic_scene_program_evaluates_like_the_oracle(oracle):
+    import program_interp
+    oracle.set_libm_mode(1)
+    L = oracle.lib()
+    g, go = mc.Geom(), mc.Geom(oracle.OracleScene())
+    root, root_o = scenes.synthetic_csg(g, 16, seed=16), scenes.synthetic_csg(go, 16, seed=16)
+    g.backend.set_parameters(0.1, 1.0)
+    root_o.backend.set_parameters_node(root_o.node, 0.1, 1.0)
+    pts = np.random.default_rng(5).uniform(-0.6, 0.6, size=(400, 3))
+    slack = 1.0 / 64
+    run = program_interp.Interp(_program_words(root, slack), L.orc_exp, L.orc_ln)
+    want = root_o.backend.eval_points(root_o.node, slack, pts)
+    got = np.array([run(*map(float, p)) for p in pts])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or np.array_equal(got, want)
